@@ -1,0 +1,63 @@
+// ABI bookkeeping + tensor-map encode through the driver entry point (no -lcuda link).
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace hvs {
+
+std::atomic<uint64_t> g_launches{0};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return HVS_ERR_DRIVER;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? HVS_OK : HVS_ERR_DRIVER;
+}
+
+}  // namespace hvs
+
+extern "C" {
+
+int hvs_abi_version(void) { return 1; }
+
+uint64_t hvs_launch_count(void) { return hvs::g_launches.load(std::memory_order_relaxed); }
+
+const char* hvs_error_string(int code) {
+    switch (code) {
+        case HVS_OK: return "ok";
+        case HVS_ERR_BAD_ARG: return "bad argument (null pointer or negative size)";
+        case HVS_ERR_UNSUPPORTED: return "shape or option not supported by the sm_100a kernels";
+        case HVS_ERR_ALIGNMENT: return "pointer or stride alignment";
+        case HVS_ERR_WORKSPACE: return "workspace too small";
+        case HVS_ERR_DRIVER: return "CUDA driver entry point unavailable or tensor-map encode failed";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+}  // extern "C"

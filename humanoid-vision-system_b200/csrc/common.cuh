@@ -1,0 +1,44 @@
+// Host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/hvs_b200.h"
+
+namespace hvs {
+
+extern std::atomic<uint64_t> g_launches;
+
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+inline int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev] = v;
+    }
+    return cached[dev];
+}
+
+#define HVS_CUDA_TRY(expr)                      \
+    do {                                        \
+        cudaError_t _e = (expr);                \
+        if (_e != cudaSuccess) return (int)_e;  \
+    } while (0)
+
+// Returns the launch status without clearing a sticky error of an earlier kernel.
+inline int launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? HVS_OK : (int)e;
+}
+
+// 2-D bf16 tensor map: [rows][cols] row-major, box [box_rows][64 cols] (=128 B inner), 128-byte swizzle.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+}  // namespace hvs

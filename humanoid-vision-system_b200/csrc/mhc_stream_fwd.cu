@@ -1,0 +1,409 @@
+// K1 forward: one fused sm_100a kernel per 16-token tile of the stream mHC layer.
+//
+//   x [T,4,512] bf16 --TMA--> smem (128B-swizzled 64x64 boxes, 3-stage ring)
+//   P1 (16 worker warps, split-K): RMS statistics + the 2048x24 coefficient projection on the
+//       warp MMA path, the bf16 operand scale*phi resident in registers, fp32 accumulate
+//   P2 (1 coefficient warp, thread per token): rsqrt, sigmoid / 2*sigmoid gates, softmax init and
+//       the Sinkhorn-Knopp row/column iterations in fp32 registers
+//   P3 (workers): y = (H_res + H_post H_pre^T) x in fp32, one rounding to bf16, written in place
+//       into the smem tile and TMA-stored.
+// P2 of tile k overlaps P3 of tile k-1 and P1 of tile k+1 (named-barrier handshakes), the
+// producer warp recycles a stage as soon as its store has drained.
+//
+// Reference arithmetic: RMSNorm src/models/manifold_layers.py:449-456, gates :213/:216,
+// SinkhornKnoppProjection.forward :56-77 (batched branch).  Oracle: oracle/mhc_ref.py.
+#include "common.cuh"
+#include "mhc_stream_shared.cuh"
+#include "ptx_sm100.cuh"
+
+namespace hvs {
+namespace {
+
+constexpr int kWorkers = 16;                       // worker warps (split-K over 32-channel slices)
+constexpr int kThreads = (kWorkers + 2) * 32;      // + coefficient warp + producer warp
+constexpr int kWorkerThreads = kWorkers * 32;
+constexpr int kStages = 3;
+constexpr int kStageBytes = kTileTok * kRowBytes;  // 64 KB
+constexpr int kBoxBytes = 64 * 128;                // one TMA box: 64 rows x 64 bf16
+constexpr int kPartStride = 26;                    // 24 logits + sum of squares (+1 pad, keeps float2 alignment)
+constexpr int kRedStride = 25;
+constexpr int kCoefStride = 20;                    // 16 mixing + 4 H_pre
+
+constexpr int kOffPart = kStages * kStageBytes;
+constexpr int kOffRed = kOffPart + kWorkers * kTileTok * kPartStride * 4;
+constexpr int kOffCoef = kOffRed + 2 * kTileTok * kRedStride * 4;
+constexpr int kOffBar = kOffCoef + 2 * kTileTok * kCoefStride * 4;
+constexpr int kSmemBytes = kOffBar + 2 * kStages * 8 + 1024;   // + slack for 1024-byte alignment
+static_assert(kOffBar % 8 == 0, "mbarrier alignment");
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+// named barrier ids (0 is __syncthreads)
+constexpr int kBarW1 = 1, kBarW2 = 2, kBarRed = 3 /*,4*/, kBarCoef = 5 /*,6*/;
+
+struct FwdParams {
+    const float* phi;
+    const float* bias;
+    const float* alpha;
+    const float* scale;
+    __nv_bfloat16* u;
+    float* coeffs;
+    int64_t T;
+    int num_tiles;
+    int sk_iters;
+    float eps_rms;
+    float eps_sk;
+    int has_y;
+};
+
+__device__ __forceinline__ float sum_sq8(uint4 v) {
+    float s = 0.f, a;
+    a = bf16lo(v.x); s = fmaf(a, a, s); a = bf16hi(v.x); s = fmaf(a, a, s);
+    a = bf16lo(v.y); s = fmaf(a, a, s); a = bf16hi(v.y); s = fmaf(a, a, s);
+    a = bf16lo(v.z); s = fmaf(a, a, s); a = bf16hi(v.z); s = fmaf(a, a, s);
+    a = bf16lo(v.w); s = fmaf(a, a, s); a = bf16hi(v.w); s = fmaf(a, a, s);
+    return s;
+}
+
+__global__ void __maxnreg__(112)
+mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
+                      const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* part = reinterpret_cast<float*>(smem + kOffPart);
+    float* red = reinterpret_cast<float*>(smem + kOffRed);
+    float* coef = reinterpret_cast<float*>(smem + kOffCoef);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffBar);
+    uint64_t* bar_done = bar_full + kStages;          // workers finished with a stage (y written in place)
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_done[s], kWorkerThreads);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == kWorkers + 1) {
+        // ===================================================== producer / store warp (one lane)
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_x);
+            tma_prefetch_desc(&tmap_y);
+            auto load_tile = [&](int it) {
+                const int s = it % kStages;
+                const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * (kTileTok * kN);
+                mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
+#pragma unroll
+                for (int cb = 0; cb < kC / 64; ++cb)
+                    tma_load_2d(smem + s * kStageBytes + cb * kBoxBytes, &tmap_x, &bar_full[s], cb * 64, row0);
+            };
+            for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
+            for (int it = 0; it < n_local; ++it) {
+                const int s = it % kStages;
+                mbar_wait(&bar_done[s], (it / kStages) & 1);
+                if (p.has_y) {
+                    const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * (kTileTok * kN);
+#pragma unroll
+                    for (int cb = 0; cb < kC / 64; ++cb)
+                        tma_store_2d(&tmap_y, smem + s * kStageBytes + cb * kBoxBytes, cb * 64, row0);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                }
+                if (it + kStages < n_local) load_tile(it + kStages);
+            }
+            bulk_wait<0>();
+        }
+    } else if (warp == kWorkers) {
+        // ===================================================== coefficient warp (thread per token)
+        float bias_r[kL];
+#pragma unroll
+        for (int k = 0; k < kL; ++k) bias_r[k] = __ldg(p.bias + k);
+        const float a_pre = __ldg(p.alpha + 0), a_post = __ldg(p.alpha + 1), a_res = __ldg(p.alpha + 2);
+        for (int it = 0; it < n_local; ++it) {
+            const int buf = it & 1;
+            bar_sync(kBarRed + buf, kWorkerThreads + 32);
+            if (lane < kTileTok) {
+                const float* r = red + (buf * kTileTok + lane) * kRedStride;
+                float l[kL];
+#pragma unroll
+                for (int k = 0; k < kL; ++k) l[k] = r[k];
+                const float ss = r[kL];
+                const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(ss, 1.0f / kRow, p.eps_rms)));
+                float hpre[kN], hpost[kN], pm[kN * kN];
+                coefficients_from_raw(l, inv_rms, bias_r, a_pre, a_post, a_res, p.sk_iters, p.eps_sk, hpre, hpost, pm);
+                float* c = coef + (buf * kTileTok + lane) * kCoefStride;
+#pragma unroll
+                for (int i = 0; i < kN; ++i) {
+                    float4 m;
+                    m.x = fmaf(hpost[i], hpre[0], pm[i * 4 + 0]);
+                    m.y = fmaf(hpost[i], hpre[1], pm[i * 4 + 1]);
+                    m.z = fmaf(hpost[i], hpre[2], pm[i * 4 + 2]);
+                    m.w = fmaf(hpost[i], hpre[3], pm[i * 4 + 3]);
+                    *reinterpret_cast<float4*>(c + i * 4) = m;
+                }
+                *reinterpret_cast<float4*>(c + 16) = make_float4(hpre[0], hpre[1], hpre[2], hpre[3]);
+                const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTileTok + lane;
+                if (p.coeffs != nullptr && tok < p.T) {
+                    float4* o = reinterpret_cast<float4*>(p.coeffs + tok * kL);
+                    o[0] = make_float4(hpre[0], hpre[1], hpre[2], hpre[3]);
+                    o[1] = make_float4(hpost[0], hpost[1], hpost[2], hpost[3]);
+#pragma unroll
+                    for (int i = 0; i < kN; ++i) o[2 + i] = make_float4(pm[i * 4], pm[i * 4 + 1], pm[i * 4 + 2], pm[i * 4 + 3]);
+                }
+            }
+            __threadfence_block();
+            bar_arrive(kBarCoef + buf, kWorkerThreads + 32);
+        }
+    } else {
+        // ===================================================== worker warps
+        const int w = warp, g = lane >> 2, t = lane & 3;
+        // bf16 projection operand scale*phi for this warp's K slice, in mma B-fragment order.
+        // K index of logical k-column {2t,2t+1,2t+8,2t+9} of k-step (j,q): j*512 + 32w + 8t + 4q + {0,1,2,3}
+        uint32_t bfrag[kN][2][3][2];
+#pragma unroll
+        for (int j = 0; j < kN; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int k0 = j * kC + 32 * w + 8 * t + 4 * q;
+                float sc[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sc[e] = __ldg(p.scale + k0 + e);
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt) {
+                    const int col = nt * 8 + g;
+                    float f[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) f[e] = __ldg(p.phi + (size_t)(k0 + e) * kL + col) * sc[e];
+                    bfrag[j][q][nt][0] = pack_bf16(f[0], f[1]);
+                    bfrag[j][q][nt][1] = pack_bf16(f[2], f[3]);
+                }
+            }
+        // swizzled byte offsets of this thread's 16-byte chunk in rows (token g, stream j); token g+8: +4096
+        const int cb = w >> 1, hh = w & 1;
+        uint32_t off[kN];
+#pragma unroll
+        for (int j = 0; j < kN; ++j) {
+            const int row = g * kN + j;
+            off[j] = cb * kBoxBytes + row * 128 + (((4 * hh + t) ^ (row & 7)) << 4);
+        }
+        const uint32_t stage0 = smem_u32(smem);
+
+        auto mix_tile = [&](int itp) {
+            const int bufp = itp & 1;
+            const uint32_t sbase = stage0 + (itp % kStages) * kStageBytes;
+            const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)itp * gridDim.x) * kTileTok;
+            bar_sync(kBarCoef + bufp, kWorkerThreads + 32);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int tl = g + 8 * half;
+                const float* c = coef + (bufp * kTileTok + tl) * kCoefStride;
+                uint32_t xr[kN][4];
+#pragma unroll
+                for (int j = 0; j < kN; ++j) {
+                    const uint4 v = lds128(sbase + off[j] + half * 4096);
+                    xr[j][0] = v.x; xr[j][1] = v.y; xr[j][2] = v.z; xr[j][3] = v.w;
+                }
+                if (p.has_y) {
+                    // two output streams at a time keeps the live set small (the bf16 operand of the
+                    // projection stays resident in 48 registers for the whole kernel)
+#pragma unroll
+                    for (int ip = 0; ip < kN; ip += 2) {
+                        const float4 m0 = *reinterpret_cast<const float4*>(c + 4 * ip);
+                        const float4 m1 = *reinterpret_cast<const float4*>(c + 4 * ip + 4);
+                        uint32_t y0[4], y1[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float l0 = bf16lo(xr[0][e]), h0 = bf16hi(xr[0][e]);
+                            const float l1 = bf16lo(xr[1][e]), h1 = bf16hi(xr[1][e]);
+                            const float l2 = bf16lo(xr[2][e]), h2 = bf16hi(xr[2][e]);
+                            const float l3 = bf16lo(xr[3][e]), h3 = bf16hi(xr[3][e]);
+                            const float a0 = fmaf(m0.w, l3, fmaf(m0.z, l2, fmaf(m0.y, l1, m0.x * l0)));
+                            const float b0 = fmaf(m0.w, h3, fmaf(m0.z, h2, fmaf(m0.y, h1, m0.x * h0)));
+                            const float a1 = fmaf(m1.w, l3, fmaf(m1.z, l2, fmaf(m1.y, l1, m1.x * l0)));
+                            const float b1 = fmaf(m1.w, h3, fmaf(m1.z, h2, fmaf(m1.y, h1, m1.x * h0)));
+                            y0[e] = pack_bf16(a0, b0);
+                            y1[e] = pack_bf16(a1, b1);
+                        }
+                        sts128(sbase + off[ip] + half * 4096, make_uint4(y0[0], y0[1], y0[2], y0[3]));
+                        sts128(sbase + off[ip + 1] + half * 4096, make_uint4(y1[0], y1[1], y1[2], y1[3]));
+                    }
+                }
+                if (p.u != nullptr && tok0 + tl < p.T) {
+                    const float4 hp = *reinterpret_cast<const float4*>(c + 16);
+                    uint32_t uo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float a = hp.x * bf16lo(xr[0][e]), b = hp.x * bf16hi(xr[0][e]);
+                        a = fmaf(hp.y, bf16lo(xr[1][e]), a); b = fmaf(hp.y, bf16hi(xr[1][e]), b);
+                        a = fmaf(hp.z, bf16lo(xr[2][e]), a); b = fmaf(hp.z, bf16hi(xr[2][e]), b);
+                        a = fmaf(hp.w, bf16lo(xr[3][e]), a); b = fmaf(hp.w, bf16hi(xr[3][e]), b);
+                        uo[e] = pack_bf16(a, b);
+                    }
+                    *reinterpret_cast<uint4*>(p.u + (tok0 + tl) * kC + 32 * w + 8 * t) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+                }
+            }
+            if (p.has_y) fence_proxy_async_smem();
+            mbar_arrive(&bar_done[itp % kStages]);
+        };
+
+        for (int it = 0; it < n_local; ++it) {
+            const int s = it % kStages;
+            const uint32_t sbase = stage0 + s * kStageBytes;
+            mbar_wait(&bar_full[s], (it / kStages) & 1);
+            // ---- P1: projection partials over this warp's 128-wide K slice + sum of squares
+            float acc[3][4];
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+            float ssa = 0.f, ssb = 0.f;
+#pragma unroll
+            for (int j = 0; j < kN; ++j) {
+                const uint4 xa = lds128(sbase + off[j]);
+                const uint4 xb = lds128(sbase + off[j] + 4096);
+                ssa += sum_sq8(xa);
+                ssb += sum_sq8(xb);
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt) {
+                    mma_bf16_16816(acc[nt], xa.x, xb.x, xa.y, xb.y, bfrag[j][0][nt][0], bfrag[j][0][nt][1]);
+                    mma_bf16_16816(acc[nt], xa.z, xb.z, xa.w, xb.w, bfrag[j][1][nt][0], bfrag[j][1][nt][1]);
+                }
+            }
+            ssa += __shfl_xor_sync(0xffffffffu, ssa, 1); ssa += __shfl_xor_sync(0xffffffffu, ssa, 2);
+            ssb += __shfl_xor_sync(0xffffffffu, ssb, 1); ssb += __shfl_xor_sync(0xffffffffu, ssb, 2);
+            bar_sync(kBarW1, kWorkerThreads);     // previous tile's cross-warp reduction has read `part`
+            {
+                float* pa = part + (w * kTileTok + g) * kPartStride;
+                float* pb = pa + 8 * kPartStride;
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt) {
+                    *reinterpret_cast<float2*>(pa + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+                    *reinterpret_cast<float2*>(pb + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+                }
+                if (t == 0) { pa[kL] = ssa; pb[kL] = ssb; }
+            }
+            bar_sync(kBarW2, kWorkerThreads);
+            // ---- fixed-order cross-warp reduction -> red[buf][token][0..24]
+            {
+                const int tid = threadIdx.x;
+                if (tid < kTileTok * (kL + 1)) {
+                    const int tok = tid / (kL + 1), col = tid - tok * (kL + 1);
+                    float s0 = 0.f;
+#pragma unroll
+                    for (int ww = 0; ww < kWorkers; ++ww) s0 += part[(ww * kTileTok + tok) * kPartStride + col];
+                    red[((it & 1) * kTileTok + tok) * kRedStride + col] = s0;
+                }
+            }
+            __threadfence_block();
+            bar_arrive(kBarRed + (it & 1), kWorkerThreads + 32);
+            // ---- P3 of the previous tile while the coefficient warp works on this one
+            if (it > 0) mix_tile(it - 1);
+        }
+        if (n_local > 0) mix_tile(n_local - 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = H_res x + H_post (x) fu  (the layer wrapped around a real F): pure streaming kernel.
+// One warp per token: lane owns 16 channels (2 x 16 B) of each stream.
+__global__ void __launch_bounds__(256)
+mhc_stream_post_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ coeffs,
+                       const __nv_bfloat16* __restrict__ fu, __nv_bfloat16* __restrict__ y, int64_t T) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t tok = warp_global; tok < T; tok += nwarps) {
+        const float* c = coeffs + tok * kL;
+        float hpost[kN], hres[kN * kN];
+#pragma unroll
+        for (int i = 0; i < kN; ++i) hpost[i] = __ldg(c + kN + i);
+#pragma unroll
+        for (int i = 0; i < kN * kN; ++i) hres[i] = __ldg(c + 2 * kN + i);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const int ch = part * 256 + lane * 8;
+            uint4 xr[kN];
+#pragma unroll
+            for (int j = 0; j < kN; ++j) xr[j] = *reinterpret_cast<const uint4*>(x + (tok * kN + j) * kC + ch);
+            const uint4 fr = *reinterpret_cast<const uint4*>(fu + tok * kC + ch);
+            const uint32_t* fw = reinterpret_cast<const uint32_t*>(&fr);
+#pragma unroll
+            for (int i = 0; i < kN; ++i) {
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float a = 0.f, b = 0.f;
+#pragma unroll
+                    for (int j = 0; j < kN; ++j) {
+                        const uint32_t v = reinterpret_cast<const uint32_t*>(&xr[j])[e];
+                        a = fmaf(hres[i * 4 + j], bf16lo(v), a);
+                        b = fmaf(hres[i * 4 + j], bf16hi(v), b);
+                    }
+                    a = fmaf(hpost[i], bf16lo(fw[e]), a);
+                    b = fmaf(hpost[i], bf16hi(fw[e]), b);
+                    o[e] = pack_bf16(a, b);
+                }
+                *reinterpret_cast<uint4*>(y + (tok * kN + i) * kC + ch) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
+}  // namespace
+}  // namespace hvs
+
+extern "C" int hvs_mhc_stream_fwd(const void* x, const float* phi, const float* bias, const float* alpha,
+                                  const float* scale, void* y, void* u, float* coeffs, int64_t T, int n, int C,
+                                  int sk_iters, float eps_rms, float eps_sk, uint32_t flags, void* stream) {
+    using namespace hvs;
+    if (!x || !phi || !bias || !alpha || !scale || T < 0) return HVS_ERR_BAD_ARG;
+    if (n != kN || C != kC || sk_iters < 0 || sk_iters > 64) return HVS_ERR_UNSUPPORTED;
+    if (flags & HVS_MHC_SPLIT_PHI) return HVS_ERR_UNSUPPORTED;
+    if (T * kN >= (int64_t)1 << 31) return HVS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(u) |
+         reinterpret_cast<uintptr_t>(coeffs)) & 15)
+        return HVS_ERR_ALIGNMENT;
+    if (T == 0) return HVS_OK;
+    CUtensorMap tx, ty;
+    int rc = make_tmap_bf16_2d(&tx, x, (uint64_t)T * kN, kC, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&ty, y ? y : x, (uint64_t)T * kN, kC, 64);
+    if (rc) return rc;
+    FwdParams p;
+    p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale;
+    p.u = reinterpret_cast<__nv_bfloat16*>(u);
+    p.coeffs = coeffs;
+    p.T = T;
+    p.num_tiles = (int)((T + kTileTok - 1) / kTileTok);
+    p.sk_iters = sk_iters; p.eps_rms = eps_rms; p.eps_sk = eps_sk;
+    p.has_y = y != nullptr;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HVS_CUDA_TRY(cudaFuncSetAttribute(mhc_stream_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set = true;
+    }
+    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    mhc_stream_fwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tx, ty, p);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int hvs_mhc_stream_post(const void* x, const float* coeffs, const void* fu, void* y, int64_t T, int n,
+                                   int C, void* stream) {
+    using namespace hvs;
+    if (!x || !coeffs || !fu || !y || T < 0) return HVS_ERR_BAD_ARG;
+    if (n != kN || C != kC) return HVS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(fu)) & 15)
+        return HVS_ERR_ALIGNMENT;
+    if (T == 0) return HVS_OK;
+    int64_t blocks = (T + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    mhc_stream_post_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), coeffs, reinterpret_cast<const __nv_bfloat16*>(fu),
+        reinterpret_cast<__nv_bfloat16*>(y), T);
+    count_launch();
+    return launch_status();
+}

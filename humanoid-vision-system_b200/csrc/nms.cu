@@ -1,0 +1,340 @@
+// Greedy NMS, bit-exact against the reference's two implementations:
+//   class-agnostic  YOLODetectionHead.non_max_suppression / compute_iou   src/models/yolo_head.py:678-755
+//   class-aware     NMSFilter.apply / _standard_nms / _compute_iou        src/inference/postprocessing.py:505-607, 772-802
+// and the two-stage multi-scale merge YOLODetectionHead.post_process      src/models/yolo_head.py:571-676.
+//
+// One CTA per candidate set.  Both reference loops keep at most max_det boxes in descending score
+// order and never look back, so instead of a sort + N x N mask the CTA repeats, at most max_det
+// times: (1) block-wide arg-max over the still-alive scores (ties -> lower index; scores cached in
+// shared memory, a suppressed candidate becomes -inf), (2) one IoU of the winner against every alive
+// candidate, 32 candidates per warp, the warp's verdicts gathered with __ballot_sync into the 32-bit
+// alive word of that group.  Work is O(kept x N) integer/compare work on L2-resident boxes.
+//
+// IoU is evaluated with explicitly rounded fp32 intrinsics (no FMA contraction), in the reference's
+// operation order: inter / (((a1 + a2) - inter) + 1e-6).  max/min/clamp propagate NaN like torch.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace hvs {
+namespace {
+
+constexpr int kMaxGroups = 4;
+
+struct NmsGroup {
+    const float* boxes;       // [problems, stride, 4]
+    const float* scores;      // [problems, stride]
+    const int64_t* classes;   // [problems, stride] or null
+    int64_t stride;           // elements between consecutive problems of this group
+    int n;                    // candidates per problem (ignored when counts/offsets are given)
+};
+
+struct NmsArgs {
+    NmsGroup g[kMaxGroups];
+    int num_groups;            // problem p -> group p % num_groups, batch item p / num_groups
+    const int64_t* offsets;    // optional [P+1]: problem p = [offsets[p], offsets[p+1]) of group 0
+    const int32_t* counts;     // optional [P]: candidates of problem p (<= g.n)
+    float score_thr, iou_thr;
+    int max_det, mode;
+    int64_t* keep_idx;         // [P, max_det] index into the compacted (score > thr) list, may be null
+    int64_t* keep_src;         // [P, max_det] index into the problem's candidates
+    int32_t* keep_count;       // [P]
+};
+
+__device__ __forceinline__ float max_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+__device__ __forceinline__ float min_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+__device__ __forceinline__ float clamp0_nan(float a) { return a < 0.f ? 0.f : a; }
+
+__device__ __forceinline__ float4 load_box(const float* boxes, int64_t i, bool cxcywh) {
+    float4 b = __ldg(reinterpret_cast<const float4*>(boxes) + i);
+    if (cxcywh) {   // postprocessing.py:540-549
+        const float hw = __fmul_rn(b.z, 0.5f), hh = __fmul_rn(b.w, 0.5f);
+        b = make_float4(__fsub_rn(b.x, hw), __fsub_rn(b.y, hh), __fadd_rn(b.x, hw), __fadd_rn(b.y, hh));
+    }
+    return b;
+}
+
+__device__ __forceinline__ float iou_ref(const float4& a, float area_a, const float4& b) {
+    const float ix1 = max_nan(a.x, b.x), iy1 = max_nan(a.y, b.y);
+    const float ix2 = min_nan(a.z, b.z), iy2 = min_nan(a.w, b.w);
+    const float iw = clamp0_nan(__fsub_rn(ix2, ix1)), ih = clamp0_nan(__fsub_rn(iy2, iy1));
+    const float inter = __fmul_rn(iw, ih);
+    const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    const float uni = __fadd_rn(__fsub_rn(__fadd_rn(area_a, area_b), inter), 1e-6f);
+    return __fdiv_rn(inter, uni);
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) nms_kernel(const NmsArgs a) {
+    extern __shared__ float s_score[];                 // [n] alive score or -inf
+    __shared__ float s_wbest[THREADS / 32];
+    __shared__ int s_wbesti[THREADS / 32];
+    __shared__ int s_pick;
+    const int p = blockIdx.x;
+    const int gi = a.offsets ? 0 : p % a.num_groups;
+    const int bi = a.offsets ? 0 : p / a.num_groups;
+    const NmsGroup& grp = a.g[gi];
+    int64_t start = (int64_t)bi * grp.stride;
+    int n = grp.n;
+    if (a.offsets) { start = a.offsets[p]; n = (int)(a.offsets[p + 1] - start); }
+    if (a.counts) n = a.counts[p];
+    const float* boxes = grp.boxes + start * 4;
+    const float* scores = grp.scores + start;
+    const int64_t* classes = grp.classes ? grp.classes + start : nullptr;
+    const bool class_aware = (a.mode & 15) == HVS_NMS_CLASS_AWARE;
+    const bool cxcywh = class_aware && !(a.mode & HVS_NMS_BOXES_XYXY);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < n; i += THREADS) {
+        const float s = scores[i];
+        s_score[i] = (s > a.score_thr) ? s : -INFINITY;     // strict >, NaN never passes (yolo_head.py:605)
+    }
+    __syncthreads();
+
+    int kept = 0;
+    while (kept < a.max_det) {
+        // ---- (1) arg-max over alive candidates, ties -> lower index
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+        for (int i = tid; i < n; i += THREADS) {
+            const float s = s_score[i];
+            if (s > best) { best = s; besti = i; }          // ascending i: first maximum wins
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) { s_wbest[warp] = best; s_wbesti[warp] = besti; }
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < THREADS / 32 ? s_wbest[lane] : -INFINITY;
+            besti = lane < THREADS / 32 ? s_wbesti[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            }
+            if (lane == 0) s_pick = (best == -INFINITY) ? -1 : besti;   // +inf scores are legal, -inf is "dead"
+        }
+        __syncthreads();
+        const int pick = s_pick;
+        if (pick < 0) break;
+        if (tid == 0) {
+            a.keep_src[(int64_t)p * a.max_det + kept] = pick;
+            s_score[pick] = -INFINITY;
+        }
+        ++kept;
+        if (kept >= a.max_det) break;                        // yolo_head.py:710-711
+        // ---- (2) suppress against the winner
+        const float4 wb = load_box(boxes, pick, cxcywh);
+        const float warea = __fmul_rn(__fsub_rn(wb.z, wb.x), __fsub_rn(wb.w, wb.y));
+        const int64_t wcls = class_aware ? classes[pick] : 0;
+        __syncthreads();                                     // winner's own slot is dead before the sweep
+        for (int i0 = warp * 32; i0 < n; i0 += THREADS) {
+            const int i = i0 + lane;
+            bool alive = i < n && s_score[i] != -INFINITY;
+            if (__ballot_sync(0xffffffffu, alive) == 0u) continue;
+            bool kill = false;
+            if (alive) {
+                if (class_aware) {
+                    if (classes[i] == wcls) kill = iou_ref(wb, warea, load_box(boxes, i, cxcywh)) > a.iou_thr;  // postprocessing.py:594
+                } else {
+                    kill = !(iou_ref(wb, warea, load_box(boxes, i, false)) < a.iou_thr);                      // yolo_head.py:727
+                }
+            }
+            const unsigned dead = __ballot_sync(0xffffffffu, kill);
+            if ((dead >> lane) & 1u) s_score[i] = -INFINITY;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) a.keep_count[p] = kept;
+    // index into the compacted list of candidates that passed the score threshold
+    if (a.keep_idx != nullptr) {
+        __syncthreads();
+        for (int r = warp; r < kept; r += THREADS / 32) {
+            const int src = (int)a.keep_src[(int64_t)p * a.max_det + r];
+            int cnt = 0;
+            for (int i0 = 0; i0 < src; i0 += 32) {
+                const int i = i0 + lane;
+                cnt += __popc(__ballot_sync(0xffffffffu, i < src && scores[i] > a.score_thr));
+            }
+            if (lane == 0) a.keep_idx[(int64_t)p * a.max_det + r] = cnt;
+        }
+    }
+}
+
+int launch_nms(const NmsArgs& a, int num_problems, int64_t max_n, cudaStream_t stream) {
+    if (num_problems == 0) return HVS_OK;
+    if (max_n > 49152) return HVS_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)(max_n > 0 ? max_n : 1) * sizeof(float);
+    if (max_n <= 4096) {
+        nms_kernel<256><<<num_problems, 256, smem, stream>>>(a);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            HVS_CUDA_TRY(cudaFuncSetAttribute(nms_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 * 4));
+            attr = true;
+        }
+        nms_kernel<1024><<<num_problems, 1024, smem, stream>>>(a);
+    }
+    count_launch();
+    return launch_status();
+}
+
+// ---- post_process glue -------------------------------------------------------------------------
+struct GatherArgs {
+    NmsGroup g[kMaxGroups];
+    int num_groups, max_det;
+    const int64_t* s1_src;     // [B*S, max_det]
+    const int32_t* s1_count;   // [B*S]
+    float* cat_boxes; float* cat_scores; int64_t* cat_labels; int32_t* cat_count;   // [B, S*max_det(,4)]
+};
+
+// concatenate the per-scale survivors in scale order, kept order inside a scale (yolo_head.py:646-654)
+__global__ void gather_scales_kernel(const GatherArgs a) {
+    const int b = blockIdx.x;
+    const int cap = a.num_groups * a.max_det;
+    int base = 0;
+    for (int s = 0; s < a.num_groups; ++s) {
+        const int p = b * a.num_groups + s;
+        const int cnt = a.s1_count[p];
+        const NmsGroup& g = a.g[s];
+        for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+            const int64_t src = (int64_t)b * g.stride + a.s1_src[(int64_t)p * a.max_det + r];
+            const int64_t dst = (int64_t)b * cap + base + r;
+            reinterpret_cast<float4*>(a.cat_boxes)[dst] = __ldg(reinterpret_cast<const float4*>(g.boxes) + src);
+            a.cat_scores[dst] = g.scores[src];
+            a.cat_labels[dst] = g.classes[src];
+        }
+        base += cnt;
+    }
+    if (threadIdx.x == 0) a.cat_count[b] = base;
+}
+
+__global__ void gather_final_kernel(const float* cat_boxes, const float* cat_scores, const int64_t* cat_labels,
+                                    const int64_t* s2_src, const int32_t* s2_count, int cap, int max_det,
+                                    float* det_boxes, float* det_scores, int64_t* det_labels, int32_t* det_count) {
+    const int b = blockIdx.x;
+    const int cnt = s2_count[b];
+    for (int r = threadIdx.x; r < max_det; r += blockDim.x) {
+        const int64_t dst = (int64_t)b * max_det + r;
+        if (r < cnt) {
+            const int64_t src = (int64_t)b * cap + s2_src[dst];
+            reinterpret_cast<float4*>(det_boxes)[dst] = reinterpret_cast<const float4*>(cat_boxes)[src];
+            det_scores[dst] = cat_scores[src];
+            det_labels[dst] = cat_labels[src];
+        } else {
+            reinterpret_cast<float4*>(det_boxes)[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
+            det_scores[dst] = 0.f;
+            det_labels[dst] = -1;
+        }
+    }
+    if (threadIdx.x == 0) det_count[b] = cnt;
+}
+
+inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct PostWs {
+    float* cat_boxes; float* cat_scores; int64_t* cat_labels; int32_t* cat_count;
+    int64_t* s1_src; int32_t* s1_count; int64_t* s2_src; int32_t* s2_count;
+    size_t total;
+};
+
+PostWs carve(void* base, int B, int S, int max_det) {
+    PostWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return reinterpret_cast<uint8_t*>(base) + o; };
+    const size_t cap = (size_t)S * max_det;
+    w.cat_boxes = reinterpret_cast<float*>(take((size_t)B * cap * 16));
+    w.cat_scores = reinterpret_cast<float*>(take((size_t)B * cap * 4));
+    w.cat_labels = reinterpret_cast<int64_t*>(take((size_t)B * cap * 8));
+    w.cat_count = reinterpret_cast<int32_t*>(take((size_t)B * 4));
+    w.s1_src = reinterpret_cast<int64_t*>(take((size_t)B * S * max_det * 8));
+    w.s1_count = reinterpret_cast<int32_t*>(take((size_t)B * S * 4));
+    w.s2_src = reinterpret_cast<int64_t*>(take((size_t)B * max_det * 8));
+    w.s2_count = reinterpret_cast<int32_t*>(take((size_t)B * 4));
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+}  // namespace hvs
+
+extern "C" int hvs_nms(const float* boxes, const float* scores, const int64_t* classes, const int64_t* offsets,
+                       int num_problems, int64_t max_n, float score_thr, float iou_thr, int max_det, int mode,
+                       int64_t* keep_idx, int64_t* keep_src, int32_t* keep_count, void* stream) {
+    using namespace hvs;
+    if (num_problems < 0 || max_n < 0 || max_det <= 0 || !keep_src || !keep_count || !offsets) return HVS_ERR_BAD_ARG;
+    if (num_problems > 0 && max_n > 0 && (!boxes || !scores)) return HVS_ERR_BAD_ARG;
+    if ((mode & 15) == HVS_NMS_CLASS_AWARE && max_n > 0 && !classes) return HVS_ERR_BAD_ARG;
+    if ((mode & 15) > HVS_NMS_CLASS_AWARE) return HVS_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(boxes) & 15) return HVS_ERR_ALIGNMENT;
+    NmsArgs a{};
+    a.g[0] = NmsGroup{boxes, scores, classes, 0, 0};
+    a.num_groups = 1;
+    a.offsets = offsets;
+    a.counts = nullptr;
+    a.score_thr = score_thr; a.iou_thr = iou_thr; a.max_det = max_det; a.mode = mode;
+    a.keep_idx = keep_idx; a.keep_src = keep_src; a.keep_count = keep_count;
+    return launch_nms(a, num_problems, max_n, (cudaStream_t)stream);
+}
+
+extern "C" size_t hvs_post_process_workspace(int B, int num_scales, int max_det) {
+    if (B <= 0 || num_scales <= 0 || max_det <= 0) return 0;
+    return hvs::carve(nullptr, B, num_scales, max_det).total;
+}
+
+extern "C" int hvs_post_process(const float* const* boxes_host, const float* const* class_scores_host,
+                                const int64_t* const* class_idx_host, const int* n_per_scale_host, int num_scales,
+                                int B, float conf_thr, float iou_thr, int max_det, float* det_boxes,
+                                float* det_scores, int64_t* det_labels, int32_t* det_count, void* workspace,
+                                size_t workspace_bytes, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!boxes_host || !class_scores_host || !class_idx_host || !n_per_scale_host || !det_boxes || !det_scores ||
+        !det_labels || !det_count || B < 0 || max_det <= 0)
+        return HVS_ERR_BAD_ARG;
+    if (num_scales <= 0 || num_scales > kMaxGroups) return HVS_ERR_UNSUPPORTED;
+    if (B == 0) return HVS_OK;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return HVS_ERR_ALIGNMENT;
+    const PostWs w = carve(workspace, B, num_scales, max_det);
+    if (workspace_bytes < w.total) return HVS_ERR_WORKSPACE;
+    // stage 1: per (image, scale), class-agnostic, score > conf (yolo_head.py:605, :625-629)
+    NmsArgs a{};
+    int64_t max_n = 0;
+    for (int s = 0; s < num_scales; ++s) {
+        if (!boxes_host[s] || !class_scores_host[s] || !class_idx_host[s] || n_per_scale_host[s] < 0) return HVS_ERR_BAD_ARG;
+        a.g[s] = NmsGroup{boxes_host[s], class_scores_host[s], class_idx_host[s], n_per_scale_host[s], n_per_scale_host[s]};
+        if (n_per_scale_host[s] > max_n) max_n = n_per_scale_host[s];
+    }
+    a.num_groups = num_scales;
+    a.score_thr = conf_thr; a.iou_thr = iou_thr; a.max_det = max_det; a.mode = HVS_NMS_AGNOSTIC;
+    a.keep_idx = nullptr; a.keep_src = w.s1_src; a.keep_count = w.s1_count;
+    int rc = launch_nms(a, B * num_scales, max_n, stream);
+    if (rc) return rc;
+    // concatenate survivors in scale order (:646-654)
+    GatherArgs ga{};
+    for (int s = 0; s < num_scales; ++s) ga.g[s] = a.g[s];
+    ga.num_groups = num_scales; ga.max_det = max_det;
+    ga.s1_src = w.s1_src; ga.s1_count = w.s1_count;
+    ga.cat_boxes = w.cat_boxes; ga.cat_scores = w.cat_scores; ga.cat_labels = w.cat_labels; ga.cat_count = w.cat_count;
+    gather_scales_kernel<<<B, 128, 0, stream>>>(ga);
+    count_launch();
+    // stage 2: NMS across scales on the concatenation, no score threshold (:658-662)
+    const int cap = num_scales * max_det;
+    NmsArgs b2{};
+    b2.g[0] = NmsGroup{w.cat_boxes, w.cat_scores, w.cat_labels, cap, cap};
+    b2.num_groups = 1;
+    b2.counts = w.cat_count;
+    b2.score_thr = -INFINITY; b2.iou_thr = iou_thr; b2.max_det = max_det; b2.mode = HVS_NMS_AGNOSTIC;
+    b2.keep_idx = nullptr; b2.keep_src = w.s2_src; b2.keep_count = w.s2_count;
+    rc = launch_nms(b2, B, cap, stream);
+    if (rc) return rc;
+    gather_final_kernel<<<B, 128, 0, stream>>>(w.cat_boxes, w.cat_scores, w.cat_labels, w.s2_src, w.s2_count, cap,
+                                                max_det, det_boxes, det_scores, det_labels, det_count);
+    count_launch();
+    return launch_status();
+}

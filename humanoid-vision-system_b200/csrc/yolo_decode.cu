@@ -1,0 +1,159 @@
+// YOLODecoder.forward (src/models/yolo_head.py:220-294) for one scale, reading the prediction
+// head's output in place through element strides.
+//   box centre  (gx + sigmoid(tx)) / W, (gy + sigmoid(ty)) / H            (:262-263, repair R7)
+//   box size    anchor_w * exp(tw), anchor_h * exp(th), anchors / 416      (:269-270, :50-51)
+//   corners     c -/+ size / 2                                             (:273-276)
+//   scores      sigmoid(obj) * sigmoid(cls), max / first argmax over classes (:282-285)
+// HBM-bound streaming kernel: (5+C) values in, 7 values out per cell.  Two mappings:
+//   * channel-strided input (the permuted NCHW conv output): a thread per cell, lanes along W, so
+//     every channel plane is read with full 128-byte lines;
+//   * channel-contiguous input: a warp per cell, lanes along the channel axis.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace hvs {
+namespace {
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ float sigmoidf_rn(float v) { return __fdiv_rn(1.0f, 1.0f + expf(-v)); }
+
+struct DecodeParams {
+    const void* pred;
+    int64_t s[5];
+    const float* anchor_wh;
+    float* boxes;
+    float* class_scores;
+    int64_t* class_idx;
+    float* objectness;
+    float* scores;
+    int B, A, H, W, C;
+};
+
+__device__ __forceinline__ void write_box(const DecodeParams& p, int64_t cell, int a, int h, int w, float tx, float ty,
+                                          float tw, float th) {
+    const float bx = __fdiv_rn((float)w + sigmoidf_rn(tx), (float)p.W);
+    const float by = __fdiv_rn((float)h + sigmoidf_rn(ty), (float)p.H);
+    const float bw = __ldg(p.anchor_wh + 2 * a) * expf(tw);
+    const float bh = __ldg(p.anchor_wh + 2 * a + 1) * expf(th);
+    const float hw = bw * 0.5f, hh = bh * 0.5f;      // x / 2 == x * 0.5 exactly
+    reinterpret_cast<float4*>(p.boxes)[cell] = make_float4(bx - hw, by - hh, bx + hw, by + hh);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) decode_cell_per_thread(const DecodeParams p) {
+    const int64_t ncell = (int64_t)p.B * p.A * p.H * p.W;
+    const T* base = reinterpret_cast<const T*>(p.pred);
+    for (int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cell < ncell;
+         cell += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(cell % p.W);
+        int64_t r = cell / p.W;
+        const int h = (int)(r % p.H); r /= p.H;
+        const int a = (int)(r % p.A);
+        const int b = (int)(r / p.A);
+        const T* q = base + b * p.s[0] + a * p.s[1] + h * p.s[2] + w * p.s[3];
+        const float tx = to_f32(q[0]), ty = to_f32(q[p.s[4]]), tw = to_f32(q[2 * p.s[4]]), th = to_f32(q[3 * p.s[4]]);
+        write_box(p, cell, a, h, w, tx, ty, tw, th);
+        const float obj = sigmoidf_rn(to_f32(q[4 * p.s[4]]));
+        float best = -INFINITY;
+        int besti = 0;
+        for (int c = 0; c < p.C; ++c) {
+            const float sc = obj * sigmoidf_rn(to_f32(q[(5 + c) * p.s[4]]));
+            if (p.scores != nullptr) p.scores[cell * p.C + c] = sc;
+            if (c == 0 || sc > best) { best = sc; besti = c; }
+        }
+        p.class_scores[cell] = best;
+        p.class_idx[cell] = besti;
+        if (p.objectness != nullptr) p.objectness[cell] = obj;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) decode_cell_per_warp(const DecodeParams p) {
+    const int64_t ncell = (int64_t)p.B * p.A * p.H * p.W;
+    const T* base = reinterpret_cast<const T*>(p.pred);
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t cell = wid; cell < ncell; cell += nw) {
+        const int w = (int)(cell % p.W);
+        int64_t r = cell / p.W;
+        const int h = (int)(r % p.H); r /= p.H;
+        const int a = (int)(r % p.A);
+        const int b = (int)(r / p.A);
+        const T* q = base + b * p.s[0] + a * p.s[1] + h * p.s[2] + w * p.s[3];
+        // lanes 0..4 hold tx,ty,tw,th,obj
+        const float head = lane < 5 ? to_f32(q[lane]) : 0.f;
+        const float tx = __shfl_sync(0xffffffffu, head, 0), ty = __shfl_sync(0xffffffffu, head, 1);
+        const float tw = __shfl_sync(0xffffffffu, head, 2), th = __shfl_sync(0xffffffffu, head, 3);
+        const float obj = sigmoidf_rn(__shfl_sync(0xffffffffu, head, 4));
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+        for (int c = lane; c < p.C; c += 32) {
+            const float sc = obj * sigmoidf_rn(to_f32(q[5 + c]));
+            if (p.scores != nullptr) p.scores[cell * p.C + c] = sc;
+            if (sc > best || besti == 0x7fffffff) { best = sc; besti = c; }
+        }
+        // max with first-index tie-break; a NaN score never wins over a number (matches `>`)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+        }
+        if (lane == 0) {
+            write_box(p, cell, a, h, w, tx, ty, tw, th);
+            p.class_scores[cell] = best;
+            p.class_idx[cell] = besti;
+            if (p.objectness != nullptr) p.objectness[cell] = obj;
+        }
+    }
+}
+
+template <typename T>
+int launch_decode(const DecodeParams& p, cudaStream_t stream) {
+    const int64_t ncell = (int64_t)p.B * p.A * p.H * p.W;
+    const int cap = sm_count() * 8;
+    if (p.s[4] == 1) {
+        int64_t blocks = (ncell + 7) / 8;
+        if (blocks > cap) blocks = cap;
+        decode_cell_per_warp<T><<<(int)blocks, 256, 0, stream>>>(p);
+    } else {
+        int64_t blocks = (ncell + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        decode_cell_per_thread<T><<<(int)blocks, 256, 0, stream>>>(p);
+    }
+    count_launch();
+    return launch_status();
+}
+
+}  // namespace
+}  // namespace hvs
+
+extern "C" int hvs_yolo_decode(const void* pred, int pred_dtype, const int64_t* pred_stride_host, const float* anchor_wh,
+                               float* boxes, float* class_scores, int64_t* class_idx, float* objectness, float* scores,
+                               int B, int A, int H, int W, int C, void* stream) {
+    using namespace hvs;
+    if (!pred || !pred_stride_host || !anchor_wh || !boxes || !class_scores || !class_idx) return HVS_ERR_BAD_ARG;
+    if (B < 0 || A <= 0 || H <= 0 || W <= 0 || C <= 0) return HVS_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(boxes) & 15) return HVS_ERR_ALIGNMENT;
+    if (B == 0) return HVS_OK;
+    DecodeParams p;
+    p.pred = pred;
+    for (int i = 0; i < 5; ++i) p.s[i] = pred_stride_host[i];
+    p.anchor_wh = anchor_wh; p.boxes = boxes; p.class_scores = class_scores; p.class_idx = class_idx;
+    p.objectness = objectness; p.scores = scores;
+    p.B = B; p.A = A; p.H = H; p.W = W; p.C = C;
+    switch (pred_dtype) {
+        case HVS_DTYPE_F32: return launch_decode<float>(p, (cudaStream_t)stream);
+        case HVS_DTYPE_F16: return launch_decode<__half>(p, (cudaStream_t)stream);
+        case HVS_DTYPE_BF16: return launch_decode<__nv_bfloat16>(p, (cudaStream_t)stream);
+        default: return HVS_ERR_UNSUPPORTED;
+    }
+}

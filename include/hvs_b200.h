@@ -1,0 +1,161 @@
+/* hvs_b200.h -- C ABI of libhvs_b200.so: the B200 (sm_100a) implementation of the
+ * humanoid-vision-system hot path (mHC residual layer + detection decode / NMS).
+ *
+ * The reference (nazimurahman/humanoid-vision-system) is pure Python/PyTorch and has
+ * no FFI layer: its boundary for this path is the nn.Module surface listed in
+ * SURVEY.md section 8(b).  Each entry point below names the reference code it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the
+ * reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions never allocate, never synchronise and are re-entrant across
+ *     streams; the caller passes outputs and, where stated, a workspace;
+ *   - return value: 0 = ok; > 0 = a cudaError_t; < 0 = HVS_ERR_* argument error.
+ *     hvs_error_string() turns either into text;
+ *   - there is NO CPU path: without a CUDA device the calls return the CUDA error.
+ */
+#ifndef HVS_B200_H
+#define HVS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVS_OK 0
+#define HVS_ERR_BAD_ARG (-1)       /* null pointer / negative size                      */
+#define HVS_ERR_UNSUPPORTED (-2)   /* shape outside what the kernels are built for      */
+#define HVS_ERR_ALIGNMENT (-3)     /* pointer or stride not aligned as documented       */
+#define HVS_ERR_WORKSPACE (-4)     /* workspace too small                               */
+#define HVS_ERR_DRIVER (-5)        /* driver entry point (tensor-map encode) missing    */
+
+int hvs_abi_version(void);
+const char* hvs_error_string(int code);
+/* number of kernels this library has launched since load (for bench.py's gpu_launches) */
+uint64_t hvs_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * K1: stream mHC layer (north_star; SURVEY.md section 8(c) "K1 oracle").
+ * Composed from the reference primitives RMSNorm (src/models/manifold_layers.py:449-456),
+ * the sigmoid / 2*sigmoid gates (:213, :216) and the batched Sinkhorn-Knopp projection
+ * (:32-93), applied per token to n residual streams of C channels.
+ *
+ *   x      [T, n, C] bf16, contiguous, 16-byte aligned
+ *   phi    [n*C, n*n+2n] fp32   projection to (H_pre | H_post | H_res) logits
+ *   bias   [n*n+2n] fp32
+ *   alpha  [3] fp32             logit scale per group (pre, post, res)
+ *   scale  [n*C] fp32           RMSNorm gain
+ *   y      [T, n, C] bf16       y = H_res x + H_post (x) (H_pre^T x)      (may be NULL)
+ *   u      [T, C] bf16          layer input H_pre^T x                      (may be NULL)
+ *   coeffs [T, n*n+2n] fp32     H_pre (n) | H_post (n) | H_res (n*n, row-major) (may be NULL)
+ *
+ * flags: HVS_MHC_SPLIT_PHI keeps the projection operand at fp32 accuracy (two bf16
+ * terms) instead of rounding scale*phi to bf16.
+ * Supported: n == 4, C == 512, sk_iters in [0, 64].
+ * ---------------------------------------------------------------------------------- */
+#define HVS_MHC_SPLIT_PHI 1u
+
+int hvs_mhc_stream_fwd(const void* x, const float* phi, const float* bias, const float* alpha,
+                       const float* scale, void* y, void* u, float* coeffs, int64_t T, int n, int C,
+                       int sk_iters, float eps_rms, float eps_sk, uint32_t flags, void* stream);
+
+/* y = H_res x + H_post (x) fu  with coefficients produced by hvs_mhc_stream_fwd(y=NULL);
+ * fu [T, C] bf16 is the wrapped layer's output F(u). */
+int hvs_mhc_stream_post(const void* x, const float* coeffs, const void* fu, void* y, int64_t T, int n,
+                        int C, void* stream);
+
+/* Backward of hvs_mhc_stream_fwd (F = identity), coefficients recomputed.
+ *   dy [T,n,C] bf16 -> dx [T,n,C] bf16, dphi [n*C, n*n+2n] fp32, dbias [n*n+2n], dalpha [3],
+ *   dscale [n*C]  (parameter gradients are OVERWRITTEN, not accumulated).
+ * workspace: hvs_mhc_stream_bwd_workspace(T, n, C) bytes, 256-byte aligned. */
+size_t hvs_mhc_stream_bwd_workspace(int64_t T, int n, int C);
+int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* phi, const float* bias,
+                       const float* alpha, const float* scale, void* dx, float* dphi, float* dbias,
+                       float* dalpha, float* dscale, int64_t T, int n, int C, int sk_iters,
+                       float eps_rms, float eps_sk, uint32_t flags, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Sinkhorn-Knopp projection, SinkhornKnoppProjection.forward (manifold_layers.py:32-93):
+ * out = SK(in) for `batch` matrices of n x m fp32, row-major, contiguous.
+ * `history` (may be NULL) receives |mean(row_sum) - 1| per iteration ([iters] fp32), the
+ * reference's convergence_history buffer (:76-77).
+ * Supported: n*m <= 64 per matrix for batch > 1 ("per-token" blocks), or batch == 1 with
+ * n, m <= 2048 (a layer's D x D H_res_raw).
+ * ---------------------------------------------------------------------------------- */
+int hvs_sinkhorn(const float* in, float* out, int64_t batch, int n, int m, int iters, float eps,
+                 float tau, float* history, void* stream);
+
+/* ManifoldHyperConnection.constrained_matrices (manifold_layers.py:205-221) for one layer:
+ * H_pre = sigmoid(H_pre_raw) [D,nD], H_post = 2 sigmoid(H_post_raw) [nD,D],
+ * H_res = SK(H_res_raw) [D,D]. */
+int hvs_mhc_constrained_matrices(const float* h_pre_raw, const float* h_post_raw, const float* h_res_raw,
+                                 float* h_pre, float* h_post, float* h_res, int D, int hidden, int iters,
+                                 float eps, float* history, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * YOLODecoder.forward (src/models/yolo_head.py:220-294), one scale.
+ *   pred      [B, A, H, W, 5+C] viewed through element strides pred_stride[5]
+ *             (the head's permuted NCHW conv output is read in place), fp32 / fp16 / bf16
+ *   anchor_wh [A, 2] fp32  anchor (w,h) / 416 (:50-51)
+ *   boxes [B,A,H,W,4] fp32 xyxy normalised; class_scores [B,A,H,W] fp32;
+ *   class_idx [B,A,H,W] int64; objectness [B,A,H,W] fp32 (may be NULL);
+ *   scores [B,A,H,W,C] fp32 obj*cls (may be NULL).
+ * ---------------------------------------------------------------------------------- */
+#define HVS_DTYPE_F32 0
+#define HVS_DTYPE_F16 1
+#define HVS_DTYPE_BF16 2
+
+int hvs_yolo_decode(const void* pred, int pred_dtype, const int64_t* pred_stride_host, const float* anchor_wh,
+                    float* boxes, float* class_scores, int64_t* class_idx, float* objectness, float* scores,
+                    int B, int A, int H, int W, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Greedy NMS over `num_problems` independent candidate sets (one CTA each).
+ *   boxes   [sum N, 4] fp32; scores [sum N] fp32; classes [sum N] int64 (class-aware only)
+ *   offsets [num_problems+1] int64 (device): prefix of set sizes; max_n: upper bound on any set's size
+ *   (sizes the shared-memory score cache; max_n <= 49152)
+ *   A candidate takes part only if score > score_thr (strict, yolo_head.py:605); pass
+ *   -INFINITY to take all.  Ties in score: lower index first.
+ * mode HVS_NMS_AGNOSTIC   = YOLODetectionHead.non_max_suppression (yolo_head.py:678-731):
+ *                           xyxy boxes, a later box survives iff iou < iou_thr.
+ * mode HVS_NMS_CLASS_AWARE= NMSFilter.apply/_standard_nms (src/inference/postprocessing.py:505-607):
+ *                           cx,cy,w,h boxes converted as :540-549 (unless HVS_NMS_BOXES_XYXY),
+ *                           a later box of the SAME class is suppressed iff iou > iou_thr.
+ * IoU = inter / (((a1 + a2) - inter) + 1e-6) in fp32 without FMA contraction
+ * (yolo_head.py:733-755, postprocessing.py:772-802).
+ * Outputs per problem p: keep_count[p] <= max_det, and for r < keep_count[p]
+ *   keep_idx[p*max_det + r]  index into the problem's candidates that passed score_thr,
+ *                            numbered in input order (the reference's compacted list),
+ *   keep_src[p*max_det + r]  index into the problem's full candidate list.
+ * Both are in descending-score order.
+ * ---------------------------------------------------------------------------------- */
+#define HVS_NMS_AGNOSTIC 0
+#define HVS_NMS_CLASS_AWARE 1
+#define HVS_NMS_BOXES_XYXY 16
+
+int hvs_nms(const float* boxes, const float* scores, const int64_t* classes, const int64_t* offsets,
+            int num_problems, int64_t max_n, float score_thr, float iou_thr, int max_det, int mode, int64_t* keep_idx,
+            int64_t* keep_src, int32_t* keep_count, void* stream);
+
+/* YOLODetectionHead.post_process (yolo_head.py:571-676) for a whole batch: per scale
+ * thresholded class-agnostic NMS capped at max_det, concatenation of the survivors in scale
+ * order, second NMS.  Inputs are the per-scale decode outputs (num_scales <= 4):
+ *   boxes[s] [B, N_s, 4], class_scores[s] [B, N_s], class_idx[s] [B, N_s]
+ * Outputs: det_boxes [B, max_det, 4], det_scores [B, max_det], det_labels [B, max_det] int64,
+ * det_count [B] int32.  workspace: hvs_post_process_workspace(B, num_scales, max_det) bytes. */
+size_t hvs_post_process_workspace(int B, int num_scales, int max_det);
+int hvs_post_process(const float* const* boxes_host, const float* const* class_scores_host,
+                     const int64_t* const* class_idx_host, const int* n_per_scale_host, int num_scales,
+                     int B, float conf_thr, float iou_thr, int max_det, float* det_boxes,
+                     float* det_scores, int64_t* det_labels, int32_t* det_count, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVS_B200_H */

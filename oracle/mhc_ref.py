@@ -119,7 +119,7 @@ def bf16_round(t: torch.Tensor) -> torch.Tensor:
 def stream_mhc_coeffs(x: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor,
                       alpha: torch.Tensor, rms_scale: torch.Tensor,
                       sk_iterations: int = 20, eps: float = 1e-8,
-                      split_phi: bool = False):
+                      split_phi: bool = False, dtype: torch.dtype = torch.float32):
     """Coefficient stage of the stream kernel.
 
     x          [T,n,C] bf16 (or fp32 holding bf16 values)
@@ -140,14 +140,15 @@ def stream_mhc_coeffs(x: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor,
     Returns (H_pre [T,n], H_post [T,n], H_res [T,n,n], logits [T,n*n+2n]), fp32.
     """
     t, n, c = x.shape
-    xf = x.to(torch.float32).reshape(t, n * c)
+    xf = x.to(dtype).reshape(t, n * c)
     inv_rms = 1.0 / torch.sqrt(torch.mean(xf * xf, dim=-1, keepdim=True) + eps)  # :451
-    w = rms_scale.to(torch.float32)[:, None] * phi.to(torch.float32)
+    w = rms_scale.to(dtype)[:, None] * phi.to(dtype)
     if not split_phi:
-        w = w.to(torch.bfloat16).to(torch.float32)
+        w = w.to(torch.bfloat16).to(dtype)
     raw = (xf @ w) * inv_rms                                  # == rms_norm(x) @ phi
+    alpha = alpha.to(dtype)
     a = torch.cat([alpha[0].expand(n), alpha[1].expand(n), alpha[2].expand(n * n)])
-    logits = raw * a + bias
+    logits = raw * a + bias.to(dtype)
     h_pre = torch.sigmoid(logits[:, :n])                       # :213
     h_post = 2.0 * torch.sigmoid(logits[:, n:2 * n])           # :216
     h_res = sinkhorn_knopp(logits[:, 2 * n:].reshape(t, n, n), sk_iterations)  # :219, batched branch
@@ -158,7 +159,8 @@ def stream_mhc_forward(x: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor,
                        alpha: torch.Tensor, rms_scale: torch.Tensor,
                        sk_iterations: int = 20, eps: float = 1e-8,
                        fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
-                       split_phi: bool = False, round_output: bool = True):
+                       split_phi: bool = False, round_output: bool = True,
+                       dtype: torch.dtype = torch.float32):
     """Full stream-mHC layer:  y = H_res x + H_post (x) fn(H_pre^T x).
 
     ``fn=None`` is the identity (the microbenchmark of BASELINE.json config 2);
@@ -170,13 +172,13 @@ def stream_mhc_forward(x: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor,
     """
     t, n, c = x.shape
     h_pre, h_post, h_res, logits = stream_mhc_coeffs(
-        x, phi, bias, alpha, rms_scale, sk_iterations, eps, split_phi)
-    xs = x.to(torch.float32)
+        x, phi, bias, alpha, rms_scale, sk_iterations, eps, split_phi, dtype)
+    xs = x.to(dtype)
     u = torch.einsum("tj,tjc->tc", h_pre, xs)
     if fn is None:
         fu = u
     else:
-        fu = fn(u.to(torch.bfloat16)).to(torch.float32)
+        fu = fn(u.to(torch.bfloat16)).to(dtype)
     y = torch.einsum("tij,tjc->tic", h_res, xs) + h_post[:, :, None] * fu[:, None, :]
     if round_output:
         y = y.to(torch.bfloat16)

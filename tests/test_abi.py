@@ -1,0 +1,50 @@
+"""The C-ABI library builds, loads, and exports every symbol include/hvs_b200.h declares (CPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "hvs_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hvs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_hot_path():
+    syms = declared_symbols()
+    for need in ("hvs_mhc_stream_fwd", "hvs_mhc_stream_bwd", "hvs_sinkhorn", "hvs_yolo_decode", "hvs_nms",
+                 "hvs_post_process", "hvs_mhc_constrained_matrices"):
+        assert need in syms
+
+
+def test_library_exports_every_declared_symbol():
+    import hvs_b200
+    lib = hvs_b200.load_library()
+    raw = ctypes.CDLL(hvs_b200._lib.lib_path())
+    for s in declared_symbols():
+        assert hasattr(raw, s), f"{s} declared in hvs_b200.h but not exported"
+    assert set(hvs_b200._lib.EXPORTED_SYMBOLS) == set(declared_symbols())
+    assert lib.hvs_abi_version() == 1
+    assert b"not supported" in lib.hvs_error_string(-2)
+
+
+def test_no_cpu_fallback():
+    import torch
+    import hvs_b200
+    with pytest.raises(hvs_b200.HvsError):
+        hvs_b200.ops.sinkhorn(torch.zeros(2, 4, 4))
+    with pytest.raises(hvs_b200.HvsError):
+        hvs_b200.ops.nms(torch.zeros(3, 4), torch.zeros(3))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "humanoid-vision-system_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f

@@ -1,0 +1,166 @@
+"""Decode (tolerance) and NMS / post_process (bit-exact keep indices) on the GPU vs oracle and golden."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import detect_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def random_boxes_cxcywh(g, n):
+    cx, cy = torch.rand(n, generator=g), torch.rand(n, generator=g)
+    w, h = 0.05 + 0.3 * torch.rand(n, generator=g), 0.05 + 0.3 * torch.rand(n, generator=g)
+    return torch.stack([cx, cy, w, h], -1)
+
+
+def gpu_keep(boxes, scores, classes=None, **kw):
+    import hvs_b200
+    ki, ks, kc = hvs_b200.ops.nms(torch.as_tensor(boxes).cuda(), torch.as_tensor(scores).cuda(),
+                                  None if classes is None else torch.as_tensor(classes).cuda(), **kw)
+    n = int(kc[0])
+    return ki[0, :n].cpu().tolist(), ks[0, :n].cpu().tolist()
+
+
+def test_decode_golden_and_layouts(golden):
+    import hvs_b200
+    g = golden("decode")
+    pred = torch.from_numpy(g["pred"]).cuda()                       # [B,A,H,W,85] channel-contiguous
+    b, a, h, w, d = pred.shape
+    nchw = pred.permute(0, 1, 4, 2, 3).contiguous()                 # conv layout [B,A,85,H,W]
+    strided = nchw.permute(0, 1, 3, 4, 2)                           # the head's non-contiguous view
+    assert not strided.is_contiguous()
+    for s in range(3):
+        awh = torch.from_numpy(g[f"s{s}/anchor_wh"]).cuda()
+        for p in (pred, strided):
+            out = hvs_b200.ops.yolo_decode(p, awh, want_scores=True)
+            assert torch.allclose(out["boxes"].cpu(), torch.from_numpy(g[f"s{s}/boxes"]), rtol=2e-6, atol=2e-7)
+            assert torch.allclose(out["class_scores"].cpu(), torch.from_numpy(g[f"s{s}/class_scores"]), rtol=2e-6, atol=1e-8)
+            assert torch.allclose(out["objectness"].cpu(), torch.from_numpy(g[f"s{s}/objectness"]), rtol=2e-6)
+            assert torch.equal(out["class_indices"].cpu(), torch.from_numpy(g[f"s{s}/class_indices"]))
+            ref = detect_ref.yolo_decode(pred.cpu(), awh.cpu())
+            assert torch.allclose(out["scores"].cpu(), ref["scores"], rtol=2e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_decode_half_inputs(dtype):
+    import hvs_b200
+    g = torch.Generator().manual_seed(7)
+    pred = (torch.randn(2, 3, 20, 20, 85, generator=g) * 1.5).to(dtype)
+    awh = detect_ref.anchors_wh(2)
+    out = hvs_b200.ops.yolo_decode(pred.cuda(), awh.cuda())
+    ref = detect_ref.yolo_decode(pred, awh)
+    assert torch.allclose(out["boxes"].cpu(), ref["boxes"], rtol=2e-6, atol=2e-7)
+    assert torch.allclose(out["class_scores"].cpu(), ref["class_scores"], rtol=2e-6, atol=1e-8)
+
+
+def test_nms_golden_bit_exact(golden):
+    g = golden("nms")
+    ki, _ = gpu_keep(g["ka/boxes"], g["ka/scores"], g["ka/classes"], iou_threshold=0.5, class_aware=True, boxes_xyxy=False)
+    assert ki == [0, 2]                                   # reference test_inference.py:361-379
+    for tag in ("ag300", "ag1000", "ag64cap5", "ag1"):
+        ki, _ = gpu_keep(g[f"{tag}/boxes"], g[f"{tag}/scores"], iou_threshold=float(g[f"{tag}/thr"]),
+                         max_detections=int(g[f"{tag}/cap"]))
+        assert ki == g[f"{tag}/keep"].tolist(), tag
+    for tag in ("ca400", "ca600", "ca200cap1000"):
+        ki, _ = gpu_keep(g[f"{tag}/boxes"], g[f"{tag}/scores"], g[f"{tag}/classes"], iou_threshold=float(g[f"{tag}/thr"]),
+                         max_detections=int(g[f"{tag}/cap"]), class_aware=True, boxes_xyxy=False)
+        assert ki == g[f"{tag}/keep"].tolist(), tag
+
+
+@pytest.mark.parametrize("n,thr", [(2, 0.5), (33, 0.3), (2500, 0.45), (20000, 0.6)])
+def test_nms_agnostic_vs_oracle(n, thr):
+    g = torch.Generator().manual_seed(n)
+    boxes = detect_ref.center_to_corner(random_boxes_cxcywh(g, n).numpy())
+    scores = torch.rand(n, generator=g).numpy()
+    want = detect_ref.nms_agnostic(boxes, scores, thr, 100).tolist()
+    ki, ks = gpu_keep(boxes, scores, iou_threshold=thr, max_detections=100)
+    assert ki == want and ks == want
+
+
+def test_nms_threshold_compaction_indices():
+    g = torch.Generator().manual_seed(1)
+    n = 5000
+    boxes = detect_ref.center_to_corner(random_boxes_cxcywh(g, n).numpy())
+    scores = torch.rand(n, generator=g).numpy()
+    mask = scores > np.float32(0.7)
+    want = detect_ref.nms_agnostic(boxes[mask], scores[mask], 0.45, 50).tolist()
+    ki, ks = gpu_keep(boxes, scores, iou_threshold=0.45, max_detections=50, score_threshold=0.7)
+    assert ki == want                                     # index into the compacted list (yolo_head.py:620-629)
+    assert ks == np.nonzero(mask)[0][want].tolist()       # index into the dense list
+
+
+def test_nms_edge_cases():
+    import hvs_b200
+    # empty set
+    ki, ks, kc = hvs_b200.ops.nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda())
+    assert int(kc[0]) == 0
+    # all identical boxes
+    b = np.tile(np.array([[0.1, 0.1, 0.5, 0.5]], np.float32), (40, 1))
+    s = np.linspace(0.1, 0.9, 40).astype(np.float32)
+    assert gpu_keep(b, s)[0] == [39]
+    assert gpu_keep(b, s, np.arange(40) % 2, class_aware=True)[0] == [39, 38]
+    # equal scores: lower index first
+    b2 = detect_ref.center_to_corner(random_boxes_cxcywh(torch.Generator().manual_seed(3), 64).numpy())
+    s2 = np.full(64, 0.5, np.float32)
+    assert gpu_keep(b2, s2, iou_threshold=0.5)[0] == detect_ref.nms_agnostic(b2, s2, 0.5).tolist()
+    # NaN box: IoU is NaN -> suppressed by the agnostic rule (iou < thr fails), kept by the class-aware one
+    b3 = np.array([[0.1, 0.1, 0.4, 0.4], [np.nan, 0.1, 0.4, 0.4], [0.6, 0.6, 0.9, 0.9]], np.float32)
+    s3 = np.array([0.9, 0.8, 0.7], np.float32)
+    assert gpu_keep(b3, s3)[0] == detect_ref.nms_agnostic(b3, s3).tolist() == [0, 2]
+    assert gpu_keep(b3, s3, np.zeros(3, np.int64), class_aware=True)[0] == \
+        detect_ref.nms_class_aware(b3, s3, np.zeros(3), 0.5, boxes_are_corners=True).tolist() == [0, 1, 2]
+    # nothing passes the score threshold
+    assert gpu_keep(b3, s3, score_threshold=0.95)[0] == []
+
+
+def test_nms_batched_offsets():
+    import hvs_b200
+    g = torch.Generator().manual_seed(4)
+    sizes = [0, 17, 300, 1, 2048]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    n = int(offs[-1])
+    boxes = detect_ref.center_to_corner(random_boxes_cxcywh(g, n).numpy())
+    scores = torch.rand(n, generator=g).numpy()
+    cls = torch.randint(0, 7, (n,), generator=g).numpy()
+    ki, ks, kc = hvs_b200.ops.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), torch.from_numpy(cls).cuda(),
+                                  iou_threshold=0.45, max_detections=100, class_aware=True, boxes_xyxy=True,
+                                  offsets=torch.from_numpy(offs).cuda(), max_n=max(sizes))
+    for p, sz in enumerate(sizes):
+        lo, hi = offs[p], offs[p + 1]
+        want = detect_ref.nms_class_aware(boxes[lo:hi], scores[lo:hi], cls[lo:hi], 0.45, 100, boxes_are_corners=True).tolist()
+        assert ki[p, :int(kc[p])].cpu().tolist() == want
+
+
+def test_post_process_golden_and_oracle(golden):
+    import hvs_b200
+    g = golden("nms")
+    conf, thr, cap = float(g["pp/conf"]), float(g["pp/thr"]), int(g["pp/cap"])
+    # same decoded tensors for both sides ("on the same inputs"): decode on the CPU oracle
+    decoded = [detect_ref.yolo_decode(torch.from_numpy(g[f"pp/pred{s}"]), detect_ref.anchors_wh(s)) for s in range(3)]
+    dev = [{k: v.cuda() for k, v in d.items() if k in ("boxes", "class_scores", "class_indices")} for d in decoded]
+    db, ds, dl, dc = hvs_b200.ops.post_process(dev, conf, thr, cap)
+    for b in range(2):
+        k = int(dc[b])
+        assert np.array_equal(db[b, :k].cpu().numpy(), g[f"pp/{b}/boxes"])
+        assert np.array_equal(ds[b, :k].cpu().numpy(), g[f"pp/{b}/scores"])
+        assert np.array_equal(dl[b, :k].cpu().numpy(), g[f"pp/{b}/labels"])
+
+
+def test_post_process_full_size_worst_case():
+    """640x640 grids (80/40/20), every candidate above the threshold (SURVEY D18 worst case)."""
+    import hvs_b200
+    g = torch.Generator().manual_seed(8)
+    decoded = []
+    for s, hw in enumerate((80, 40, 20)):
+        pred = torch.randn(2, 3, hw, hw, 85, generator=g)
+        pred[..., 2:4] *= 0.3
+        decoded.append(detect_ref.yolo_decode(pred, detect_ref.anchors_wh(s)))
+    want = detect_ref.post_process(decoded, 0.05, 0.45, 100)
+    dev = [{k: v.cuda() for k, v in d.items() if k in ("boxes", "class_scores", "class_indices")} for d in decoded]
+    db, ds, dl, dc = hvs_b200.ops.post_process(dev, 0.05, 0.45, 100)
+    for b in range(2):
+        k = int(dc[b])
+        assert k == len(want[b]["scores"])
+        assert np.array_equal(db[b, :k].cpu().numpy(), want[b]["boxes"])
+        assert np.array_equal(dl[b, :k].cpu().numpy(), want[b]["labels"])
