@@ -20,7 +20,8 @@ namespace hvs {
 namespace {
 
 constexpr int kWorkers = 16;                       // worker warps (split-K over 32-channel slices)
-constexpr int kThreads = (kWorkers + 2) * 32;      // + coefficient warp + producer warp
+constexpr int kThreads = (kWorkers + 4) * 32;      // + one warpgroup: coefficient warp, producer warp, 2 idle
+constexpr int kWorkerRegs = 104, kRoleRegs = 64;   // launch 640 x 96; the role warpgroup releases 128 x 32, the 512 workers take + 8 each
 constexpr int kWorkerThreads = kWorkers * 32;
 constexpr int kStages = 3;
 constexpr int kStageBytes = kTileTok * kRowBytes;  // 64 KB
@@ -64,7 +65,7 @@ __device__ __forceinline__ float sum_sq8(uint4 v) {
     return s;
 }
 
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(kThreads, 1)
 mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                       const FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -88,7 +89,10 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     }
     __syncthreads();
 
-    if (warp == kWorkers + 1) {
+    if (warp >= kWorkers) {
+      // one warpgroup: coefficient warp, producer warp, two idle warps; hands registers to the workers
+      reg_dealloc<kRoleRegs>();
+      if (warp == kWorkers + 1) {
         // ===================================================== producer / store warp (one lane)
         if (lane == 0) {
             tma_prefetch_desc(&tmap_x);
@@ -117,7 +121,7 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             }
             bulk_wait<0>();
         }
-    } else if (warp == kWorkers) {
+      } else if (warp == kWorkers) {
         // ===================================================== coefficient warp (thread per token)
         float bias_r[kL];
 #pragma unroll
@@ -158,8 +162,10 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             __threadfence_block();
             bar_arrive(kBarCoef + buf, kWorkerThreads + 32);
         }
+      }
     } else {
         // ===================================================== worker warps
+        reg_alloc<kWorkerRegs>();
         const int w = warp, g = lane >> 2, t = lane & 3;
         // bf16 projection operand scale*phi for this warp's K slice, in mma B-fragment order.
         // K index of logical k-column {2t,2t+1,2t+8,2t+9} of k-step (j,q): j*512 + 32w + 8t + 4q + {0,1,2,3}
@@ -358,8 +364,10 @@ extern "C" int hvs_mhc_stream_fwd(const void* x, const float* phi, const float* 
                                   const float* scale, void* y, void* u, float* coeffs, int64_t T, int n, int C,
                                   int sk_iters, float eps_rms, float eps_sk, uint32_t flags, void* stream) {
     using namespace hvs;
-    if (!x || !phi || !bias || !alpha || !scale || T < 0) return HVS_ERR_BAD_ARG;
+    if (T < 0) return HVS_ERR_BAD_ARG;
     if (n != kN || C != kC || sk_iters < 0 || sk_iters > 64) return HVS_ERR_UNSUPPORTED;
+    if (T == 0) return HVS_OK;
+    if (!x || !phi || !bias || !alpha || !scale) return HVS_ERR_BAD_ARG;
     if (flags & HVS_MHC_SPLIT_PHI) return HVS_ERR_UNSUPPORTED;
     if (T * kN >= (int64_t)1 << 31) return HVS_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(u) |
@@ -393,8 +401,10 @@ extern "C" int hvs_mhc_stream_fwd(const void* x, const float* phi, const float* 
 extern "C" int hvs_mhc_stream_post(const void* x, const float* coeffs, const void* fu, void* y, int64_t T, int n,
                                    int C, void* stream) {
     using namespace hvs;
-    if (!x || !coeffs || !fu || !y || T < 0) return HVS_ERR_BAD_ARG;
+    if (T < 0) return HVS_ERR_BAD_ARG;
     if (n != kN || C != kC) return HVS_ERR_UNSUPPORTED;
+    if (T == 0) return HVS_OK;
+    if (!x || !coeffs || !fu || !y) return HVS_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(fu)) & 15)
         return HVS_ERR_ALIGNMENT;
     if (T == 0) return HVS_OK;

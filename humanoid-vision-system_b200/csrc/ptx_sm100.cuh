@@ -79,6 +79,16 @@ __device__ __forceinline__ void bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// ---------------------------------------------------------------- register re-allocation between warpgroups
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ---------------------------------------------------------------- shared memory vector access
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
