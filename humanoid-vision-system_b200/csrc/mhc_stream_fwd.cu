@@ -3,8 +3,8 @@
 //   x [T,4,512] bf16 --TMA--> smem (128B-swizzled 64x64 boxes, 3-stage ring)
 //   P1 (16 worker warps, split-K): RMS statistics + the 2048x24 coefficient projection on the
 //       warp MMA path, the bf16 operand scale*phi resident in registers, fp32 accumulate
-//   P2 (1 coefficient warp, thread per token): rsqrt, sigmoid / 2*sigmoid gates, softmax init and
-//       the Sinkhorn-Knopp row/column iterations in fp32 registers
+//   P2 (2 coefficient warps, 4 lanes per token): rsqrt, sigmoid / 2*sigmoid gates, softmax init and the
+//       Sinkhorn-Knopp iterations in fp32 registers, column sums by warp shuffles
 //   P3 (workers): y = (H_res + H_post H_pre^T) x in fp32, one rounding to bf16, written in place
 //       into the smem tile and TMA-stored.
 // P2 of tile k overlaps P3 of tile k-1 and P1 of tile k+1 (named-barrier handshakes), the
@@ -34,7 +34,7 @@ constexpr int kOffPart = kStages * kStageBytes;
 constexpr int kOffRed = kOffPart + kWorkers * kTileTok * kPartStride * 4;
 constexpr int kOffCoef = kOffRed + 2 * kTileTok * kRedStride * 4;
 constexpr int kOffBar = kOffCoef + 2 * kTileTok * kCoefStride * 4;
-constexpr int kSmemBytes = kOffBar + 2 * kStages * 8 + 1024;   // + slack for 1024-byte alignment
+constexpr int kSmemBytes = kOffBar + 2 * kStages * 8;
 static_assert(kOffBar % 8 == 0, "mbarrier alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
@@ -68,8 +68,8 @@ __device__ __forceinline__ float sum_sq8(uint4 v) {
 __global__ void __launch_bounds__(kThreads, 1)
 mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                       const FwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled TMA boxes need 1024-byte alignment
+    if (smem_u32(smem) & 1023u) __trap();
     float* part = reinterpret_cast<float*>(smem + kOffPart);
     float* red = reinterpret_cast<float*>(smem + kOffRed);
     float* coef = reinterpret_cast<float*>(smem + kOffCoef);
@@ -121,46 +121,43 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             }
             bulk_wait<0>();
         }
-      } else if (warp == kWorkers) {
-        // ===================================================== coefficient warp (thread per token)
-        float bias_r[kL];
-#pragma unroll
-        for (int k = 0; k < kL; ++k) bias_r[k] = __ldg(p.bias + k);
+      } else if (warp == kWorkers || warp == kWorkers + 2) {
+        // ===================================================== 2 coefficient warps, 8 tokens each,
+        // 4 lanes per token: lane i of a group owns row i of the 4x4 block (and gate i of H_pre / H_post).
+        const int cw = (warp - kWorkers) >> 1;
+        const int tl = cw * 8 + (lane >> 2), i = lane & 3;
+        const float b_pre = __ldg(p.bias + i), b_post = __ldg(p.bias + kN + i);
+        const float4 b_res = __ldg(reinterpret_cast<const float4*>(p.bias + 2 * kN) + i);
         const float a_pre = __ldg(p.alpha + 0), a_post = __ldg(p.alpha + 1), a_res = __ldg(p.alpha + 2);
         for (int it = 0; it < n_local; ++it) {
             const int buf = it & 1;
-            bar_sync(kBarRed + buf, kWorkerThreads + 32);
-            if (lane < kTileTok) {
-                const float* r = red + (buf * kTileTok + lane) * kRedStride;
-                float l[kL];
-#pragma unroll
-                for (int k = 0; k < kL; ++k) l[k] = r[k];
-                const float ss = r[kL];
-                const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(ss, 1.0f / kRow, p.eps_rms)));
-                float hpre[kN], hpost[kN], pm[kN * kN];
-                coefficients_from_raw(l, inv_rms, bias_r, a_pre, a_post, a_res, p.sk_iters, p.eps_sk, hpre, hpost, pm);
-                float* c = coef + (buf * kTileTok + lane) * kCoefStride;
-#pragma unroll
-                for (int i = 0; i < kN; ++i) {
-                    float4 m;
-                    m.x = fmaf(hpost[i], hpre[0], pm[i * 4 + 0]);
-                    m.y = fmaf(hpost[i], hpre[1], pm[i * 4 + 1]);
-                    m.z = fmaf(hpost[i], hpre[2], pm[i * 4 + 2]);
-                    m.w = fmaf(hpost[i], hpre[3], pm[i * 4 + 3]);
-                    *reinterpret_cast<float4*>(c + i * 4) = m;
-                }
-                *reinterpret_cast<float4*>(c + 16) = make_float4(hpre[0], hpre[1], hpre[2], hpre[3]);
-                const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTileTok + lane;
-                if (p.coeffs != nullptr && tok < p.T) {
-                    float4* o = reinterpret_cast<float4*>(p.coeffs + tok * kL);
-                    o[0] = make_float4(hpre[0], hpre[1], hpre[2], hpre[3]);
-                    o[1] = make_float4(hpost[0], hpost[1], hpost[2], hpost[3]);
-#pragma unroll
-                    for (int i = 0; i < kN; ++i) o[2 + i] = make_float4(pm[i * 4], pm[i * 4 + 1], pm[i * 4 + 2], pm[i * 4 + 3]);
-                }
+            bar_sync(kBarRed + buf, kWorkerThreads + 64);
+            const float* r = red + (buf * kTileTok + tl) * kRedStride;
+            const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(r[kL], 1.0f / kRow, p.eps_rms)));
+            const float hpre = sigmoid_f32(fmaf(a_pre, r[i] * inv_rms, b_pre));
+            const float hpost = 2.0f * sigmoid_f32(fmaf(a_post, r[kN + i] * inv_rms, b_post));
+            float p0 = fmaf(a_res, r[2 * kN + 4 * i + 0] * inv_rms, b_res.x);
+            float p1 = fmaf(a_res, r[2 * kN + 4 * i + 1] * inv_rms, b_res.y);
+            float p2 = fmaf(a_res, r[2 * kN + 4 * i + 2] * inv_rms, b_res.z);
+            float p3 = fmaf(a_res, r[2 * kN + 4 * i + 3] * inv_rms, b_res.w);
+            sinkhorn_row_lane(p0, p1, p2, p3, p.sk_iters, p.eps_sk);
+            // M = H_res + H_post (x) H_pre needs all four H_pre of the token
+            const int gbase = lane & ~3;
+            const float h0 = __shfl_sync(0xffffffffu, hpre, gbase + 0), h1 = __shfl_sync(0xffffffffu, hpre, gbase + 1);
+            const float h2 = __shfl_sync(0xffffffffu, hpre, gbase + 2), h3 = __shfl_sync(0xffffffffu, hpre, gbase + 3);
+            float* c = coef + (buf * kTileTok + tl) * kCoefStride;
+            *reinterpret_cast<float4*>(c + 4 * i) =
+                make_float4(fmaf(hpost, h0, p0), fmaf(hpost, h1, p1), fmaf(hpost, h2, p2), fmaf(hpost, h3, p3));
+            c[16 + i] = hpre;
+            const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTileTok + tl;
+            if (p.coeffs != nullptr && tok < p.T) {
+                float* o = p.coeffs + tok * kL;
+                o[i] = hpre;
+                o[kN + i] = hpost;
+                *reinterpret_cast<float4*>(o + 2 * kN + 4 * i) = make_float4(p0, p1, p2, p3);
             }
             __threadfence_block();
-            bar_arrive(kBarCoef + buf, kWorkerThreads + 32);
+            bar_arrive(kBarCoef + buf, kWorkerThreads + 64);
         }
       }
     } else {
@@ -202,7 +199,7 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             const int bufp = itp & 1;
             const uint32_t sbase = stage0 + (itp % kStages) * kStageBytes;
             const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)itp * gridDim.x) * kTileTok;
-            bar_sync(kBarCoef + bufp, kWorkerThreads + 32);
+            bar_sync(kBarCoef + bufp, kWorkerThreads + 64);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int tl = g + 8 * half;
@@ -303,7 +300,7 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 }
             }
             __threadfence_block();
-            bar_arrive(kBarRed + (it & 1), kWorkerThreads + 32);
+            bar_arrive(kBarRed + (it & 1), kWorkerThreads + 64);
             // ---- P3 of the previous tile while the coefficient warp works on this one
             if (it > 0) mix_tile(it - 1);
         }

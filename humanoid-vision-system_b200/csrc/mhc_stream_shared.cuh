@@ -13,7 +13,14 @@ constexpr int kL = kN * kN + 2 * kN;  // logits per token: H_pre | H_post | H_re
 constexpr int kTileTok = 16;          // tokens per tile (= M of the warp MMA)
 constexpr int kRowBytes = kRow * 2;
 
-__device__ __forceinline__ float sigmoid_f32(float v) { return __fdiv_rn(1.0f, 1.0f + expf(-v)); }
+// exp through the hardware ex2 unit: relative error ~2^-22 plus |v| * 2^-24 from the argument scaling;
+// the coefficient tests bound the end-to-end deviation from the fp32 oracle at 1e-5 relative.
+__device__ __forceinline__ float fast_exp(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v * 1.4426950408889634f));
+    return r;
+}
+__device__ __forceinline__ float sigmoid_f32(float v) { return rcp_approx(1.0f + fast_exp(-v)); }
 
 // Sinkhorn-Knopp on a 4x4 block held in registers (SinkhornKnoppProjection.forward,
 // src/models/manifold_layers.py:56-77): softmax over each row times m (:57), then `iters` x
@@ -24,13 +31,13 @@ __device__ __forceinline__ void sinkhorn4x4(float (&pm)[16], int iters, float ep
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float mx = fmaxf(fmaxf(pm[4 * i], pm[4 * i + 1]), fmaxf(pm[4 * i + 2], pm[4 * i + 3]));
-        const float e0 = expf(pm[4 * i] - mx), e1 = expf(pm[4 * i + 1] - mx);
-        const float e2 = expf(pm[4 * i + 2] - mx), e3 = expf(pm[4 * i + 3] - mx);
-        const float s = (e0 + e1) + (e2 + e3);
-        pm[4 * i] = __fdiv_rn(e0, s) * 4.0f;
-        pm[4 * i + 1] = __fdiv_rn(e1, s) * 4.0f;
-        pm[4 * i + 2] = __fdiv_rn(e2, s) * 4.0f;
-        pm[4 * i + 3] = __fdiv_rn(e3, s) * 4.0f;
+        const float e0 = fast_exp(pm[4 * i] - mx), e1 = fast_exp(pm[4 * i + 1] - mx);
+        const float e2 = fast_exp(pm[4 * i + 2] - mx), e3 = fast_exp(pm[4 * i + 3] - mx);
+        const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
+        pm[4 * i] = e0 * r4;
+        pm[4 * i + 1] = e1 * r4;
+        pm[4 * i + 2] = e2 * r4;
+        pm[4 * i + 3] = e3 * r4;
     }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -43,6 +50,26 @@ __device__ __forceinline__ void sinkhorn4x4(float (&pm)[16], int iters, float ep
             const float r = rcp_approx(((pm[j] + pm[4 + j]) + (pm[8 + j] + pm[12 + j])) + eps);
             pm[j] *= r; pm[4 + j] *= r; pm[8 + j] *= r; pm[12 + j] *= r;
         }
+    }
+}
+
+// The same projection with the 4x4 block spread over 4 adjacent lanes: this lane holds row i = lane & 3
+// (p0..p3).  Row sums are local, column sums take two xor-shuffles inside the 4-lane group.
+__device__ __forceinline__ void sinkhorn_row_lane(float& p0, float& p1, float& p2, float& p3, int iters, float eps) {
+    {
+        const float mx = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
+        const float e0 = fast_exp(p0 - mx), e1 = fast_exp(p1 - mx), e2 = fast_exp(p2 - mx), e3 = fast_exp(p3 - mx);
+        const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
+        p0 = e0 * r4; p1 = e1 * r4; p2 = e2 * r4; p3 = e3 * r4;
+    }
+    for (int it = 0; it < iters; ++it) {
+        const float r = rcp_approx(((p0 + p1) + (p2 + p3)) + eps);
+        p0 *= r; p1 *= r; p2 *= r; p3 *= r;
+        float c0 = p0 + __shfl_xor_sync(0xffffffffu, p0, 1), c1 = p1 + __shfl_xor_sync(0xffffffffu, p1, 1);
+        float c2 = p2 + __shfl_xor_sync(0xffffffffu, p2, 1), c3 = p3 + __shfl_xor_sync(0xffffffffu, p3, 1);
+        c0 += __shfl_xor_sync(0xffffffffu, c0, 2); c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, 2); c3 += __shfl_xor_sync(0xffffffffu, c3, 2);
+        p0 *= rcp_approx(c0 + eps); p1 *= rcp_approx(c1 + eps); p2 *= rcp_approx(c2 + eps); p3 *= rcp_approx(c3 + eps);
     }
 }
 
