@@ -1,13 +1,650 @@
-// K1 backward (placeholder until the fused kernel lands in this file).
+// K1 backward (F = identity), coefficients recomputed from x -- nothing is saved by the forward.
+//
+// Kernel B1 (per-token, HBM-bound: reads x and dy, writes dx; 8-token tiles, 3-stage TMA ring):
+//   P1 workers (16 warps, split-K)  raw = x.W on the warp MMA path (W = bf16(scale*phi) in registers),
+//                                   sum x^2 and the per-token 4x4  G = dy x^T  as MMAs on the smem tiles
+//   reducer warp                    fixed-order sum of the 16 split-K partials
+//   coefficient warp (4 lanes/token) forward gates + Sinkhorn keeping the normalisers, then the exact
+//                                   reverse sweep through all iterations -> dlogits, e = d raw, kappa
+//   P3 workers                      dx = M^T dy  +  e W^T (MMA, W^T by movmatrix from the same registers)
+//                                        + kappa x, one rounding to bf16, in place over dy, TMA store
+//   The coefficient warp also emits E[T,24] (fp32) and per-CTA partial sums of dbias / dalpha.
+// Kernel B2: dW = x^T E on the warp MMA path (x re-read once; E split into two bf16 terms), per-CTA
+//   partials; finalize: dphi = scale * dW, dscale = sum_k phi * dW, dbias, dalpha (fixed order).
+//
+// Oracle: autograd through oracle/mhc_ref.py::stream_mhc_forward (reference primitives
+// src/models/manifold_layers.py:56-77, :213-216, :449-456).
 #include "common.cuh"
+#include "mhc_stream_shared.cuh"
+#include "ptx_sm100.cuh"
 
-extern "C" size_t hvs_mhc_stream_bwd_workspace(int64_t T, int n, int C) {
-    (void)T; (void)n; (void)C;
-    return 0;
+namespace hvs {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ B1
+constexpr int kTok = 8;                               // tokens per tile
+constexpr int kWorkers = 16;
+constexpr int kWorkerThreads = kWorkers * 32;
+constexpr int kThreads = (kWorkers + 4) * 32;         // + coefficient, producer, reducer, idle warps
+constexpr int kWorkerRegs = 104, kRoleRegs = 64;
+constexpr int kStages = 3;
+constexpr int kHalfBytes = kTok * kRowBytes;          // 32 KB: x tile or dy tile
+constexpr int kStageBytes = 2 * kHalfBytes;           // x | dy
+constexpr int kBoxBytes = 32 * 128;                   // TMA box: 32 rows (8 tokens x 4 streams) x 64 bf16
+constexpr int kPartStride = 42;                       // raw[24] ss[1] pad[1] G[16]
+constexpr int kPartG = 26;
+constexpr int kRedStride = 43;                        // odd stride: conflict-free per-lane walks
+constexpr int kCoefStride = 36;                       // M^T[16] | e bf16[24 -> 16 words incl. pad] | kappa | pad
+constexpr int kCoefE = 16, kCoefKappa = 32;
+constexpr int kSkStride = 8;                          // per (iteration): row d[4], col d[4]
+constexpr int kMaxIters = 32;
+
+constexpr int kOffPart = kStages * kStageBytes;
+constexpr int kOffRed = kOffPart + kWorkers * kTok * kPartStride * 4;
+constexpr int kOffCoef = kOffRed + 2 * kTok * kRedStride * 4;
+constexpr int kOffSk = kOffCoef + 2 * kTok * kCoefStride * 4;
+constexpr int kOffBar = kOffSk + kTok * kMaxIters * kSkStride * 4;
+constexpr int kSmemBytes = kOffBar + 2 * kStages * 8;
+static_assert(kOffBar % 8 == 0, "mbarrier alignment");
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+constexpr int kBarPartFree = 1, kBarPart = 2 /*,3*/, kBarRed = 4 /*,5*/, kBarCoef = 6 /*,7*/;
+constexpr int kAccum = kL + 3;                        // per-CTA partials: dbias[24], dalpha[3]
+
+struct BwdParams {
+    const float* phi;
+    const float* bias;
+    const float* alpha;
+    const float* scale;
+    float* e_out;          // [T,24] fp32
+    float* cta_accum;      // [grid, 27]
+    int64_t T;
+    int num_tiles;
+    int sk_iters;
+    float eps_rms, eps_sk;
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t v) {
+    uint32_t r;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ float group_sum4(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
 }
 
-extern "C" int hvs_mhc_stream_bwd(const void*, const void*, const float*, const float*, const float*, const float*,
-                                  void*, float*, float*, float*, float*, int64_t, int, int, int, float, float,
-                                  uint32_t, void*, size_t, void*) {
-    return HVS_ERR_UNSUPPORTED;
+__global__ void __launch_bounds__(kThreads, 1)
+mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                      const __grid_constant__ CUtensorMap tmap_dx, const BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (smem_u32(smem) & 1023u) __trap();
+    float* part = reinterpret_cast<float*>(smem + kOffPart);
+    float* red = reinterpret_cast<float*>(smem + kOffRed);
+    float* coef = reinterpret_cast<float*>(smem + kOffCoef);
+    float* sk = reinterpret_cast<float*>(smem + kOffSk);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffBar);
+    uint64_t* bar_done = bar_full + kStages;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_done[s], kWorkerThreads);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp >= kWorkers) {
+      reg_dealloc<kRoleRegs>();
+      if (warp == kWorkers + 1) {
+        // ===================================================== producer / store (one lane)
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_x);
+            tma_prefetch_desc(&tmap_dy);
+            tma_prefetch_desc(&tmap_dx);
+            auto load_tile = [&](int it) {
+                const int s = it % kStages;
+                const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * (kTok * kN);
+                uint8_t* st = smem + s * kStageBytes;
+                mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
+#pragma unroll
+                for (int cb = 0; cb < kC / 64; ++cb) {
+                    tma_load_2d(st + cb * kBoxBytes, &tmap_x, &bar_full[s], cb * 64, row0);
+                    tma_load_2d(st + kHalfBytes + cb * kBoxBytes, &tmap_dy, &bar_full[s], cb * 64, row0);
+                }
+            };
+            for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
+            for (int it = 0; it < n_local; ++it) {
+                const int s = it % kStages;
+                mbar_wait(&bar_done[s], (it / kStages) & 1);
+                const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * (kTok * kN);
+#pragma unroll
+                for (int cb = 0; cb < kC / 64; ++cb)
+                    tma_store_2d(&tmap_dx, smem + s * kStageBytes + kHalfBytes + cb * kBoxBytes, cb * 64, row0);
+                bulk_commit();
+                bulk_wait_read<0>();
+                if (it + kStages < n_local) load_tile(it + kStages);
+            }
+            bulk_wait<0>();
+        }
+      } else if (warp == kWorkers + 2) {
+        // ===================================================== reducer: fixed-order sum of split-K partials
+        bar_arrive(kBarPartFree, kWorkerThreads + 32);              // `part` starts out free
+        for (int it = 0; it < n_local; ++it) {
+            const int buf = it & 1;
+            bar_sync(kBarPart + buf, kWorkerThreads + 32);
+            for (int idx = lane; idx < kTok * kPartStride; idx += 32) {
+                const int tok = idx / kPartStride, col = idx - tok * kPartStride;
+                if (col >= kL + 1 && col < kPartG) continue;
+                float s0 = 0.f;
+#pragma unroll
+                for (int ww = 0; ww < kWorkers; ++ww) s0 += part[(ww * kTok + tok) * kPartStride + col];
+                red[(buf * kTok + tok) * kRedStride + col] = s0;
+            }
+            __threadfence_block();
+            if (it + 1 < n_local) bar_arrive(kBarPartFree, kWorkerThreads + 32);   // workers may overwrite `part`
+            bar_arrive(kBarRed + buf, 64);                           // coefficient warp may read `red`
+        }
+      } else if (warp == kWorkers) {
+        // ===================================================== coefficient warp: lane (tk, i) owns row i of token tk
+        const int tk = lane >> 2, i = lane & 3, gbase = lane & ~3;
+        const float b_pre = __ldg(p.bias + i), b_post = __ldg(p.bias + kN + i);
+        const float4 b_res = __ldg(reinterpret_cast<const float4*>(p.bias + 2 * kN) + i);
+        const float a_pre = __ldg(p.alpha + 0), a_post = __ldg(p.alpha + 1), a_res = __ldg(p.alpha + 2);
+        float acc_b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dbias: pre_i, post_i, res_i0..3
+        float acc_a[3] = {0.f, 0.f, 0.f};                  // dalpha partials of this lane
+        float* skl = sk + tk * kMaxIters * kSkStride;
+        for (int it = 0; it < n_local; ++it) {
+            const int buf = it & 1;
+            bar_sync(kBarRed + buf, 64);
+            const float* r = red + (buf * kTok + tk) * kRedStride;
+            const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(r[kL], 1.0f / kRow, p.eps_rms)));
+            // normalised projections z = inv_rms * raw of this lane's six logits
+            const float z_pre = r[i] * inv_rms, z_post = r[kN + i] * inv_rms;
+            const float z0 = r[2 * kN + 4 * i] * inv_rms, z1 = r[2 * kN + 4 * i + 1] * inv_rms;
+            const float z2 = r[2 * kN + 4 * i + 2] * inv_rms, z3 = r[2 * kN + 4 * i + 3] * inv_rms;
+            const float hpre = sigmoid_f32(fmaf(a_pre, z_pre, b_pre));
+            const float hpost = 2.0f * sigmoid_f32(fmaf(a_post, z_post, b_post));
+            float p0 = fmaf(a_res, z0, b_res.x), p1 = fmaf(a_res, z1, b_res.y);
+            float p2 = fmaf(a_res, z2, b_res.z), p3 = fmaf(a_res, z3, b_res.w);
+            // ---- forward Sinkhorn, remembering the normalisers (row: own; columns: all four)
+            {
+                const float mx = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
+                const float e0 = fast_exp(p0 - mx), e1 = fast_exp(p1 - mx), e2 = fast_exp(p2 - mx), e3 = fast_exp(p3 - mx);
+                const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
+                p0 = e0 * r4; p1 = e1 * r4; p2 = e2 * r4; p3 = e3 * r4;
+            }
+            const float s0 = p0, s1 = p1, s2 = p2, s3 = p3;     // softmax * 4 (start of the iteration)
+            for (int k = 0; k < p.sk_iters; ++k) {
+                const float dr = ((p0 + p1) + (p2 + p3)) + p.eps_sk;
+                const float rr = rcp_approx(dr);
+                p0 *= rr; p1 *= rr; p2 *= rr; p3 *= rr;
+                float c0 = p0 + __shfl_xor_sync(0xffffffffu, p0, 1), c1 = p1 + __shfl_xor_sync(0xffffffffu, p1, 1);
+                float c2 = p2 + __shfl_xor_sync(0xffffffffu, p2, 1), c3 = p3 + __shfl_xor_sync(0xffffffffu, p3, 1);
+                c0 += __shfl_xor_sync(0xffffffffu, c0, 2); c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+                c2 += __shfl_xor_sync(0xffffffffu, c2, 2); c3 += __shfl_xor_sync(0xffffffffu, c3, 2);
+                c0 += p.eps_sk; c1 += p.eps_sk; c2 += p.eps_sk; c3 += p.eps_sk;
+                p0 *= rcp_approx(c0); p1 *= rcp_approx(c1); p2 *= rcp_approx(c2); p3 *= rcp_approx(c3);
+                skl[k * kSkStride + i] = dr;
+                if (i == 0) *reinterpret_cast<float4*>(skl + k * kSkStride + 4) = make_float4(c0, c1, c2, c3);
+            }
+            __syncwarp();
+            // ---- mixing matrix M = P + hpost (x) hpre, stored transposed for the dx pass
+            const float h0 = __shfl_sync(0xffffffffu, hpre, gbase + 0), h1 = __shfl_sync(0xffffffffu, hpre, gbase + 1);
+            const float h2 = __shfl_sync(0xffffffffu, hpre, gbase + 2), h3 = __shfl_sync(0xffffffffu, hpre, gbase + 3);
+            float* c = coef + (buf * kTok + tk) * kCoefStride;
+            c[0 * 4 + i] = fmaf(hpost, h0, p0);          // M^T[j][i] = M[i][j]
+            c[1 * 4 + i] = fmaf(hpost, h1, p1);
+            c[2 * 4 + i] = fmaf(hpost, h2, p2);
+            c[3 * 4 + i] = fmaf(hpost, h3, p3);
+            // ---- gradients of the coefficients from G = dy x^T (row i of G in this lane)
+            const float g0 = r[kPartG + 4 * i], g1 = r[kPartG + 4 * i + 1], g2 = r[kPartG + 4 * i + 2], g3 = r[kPartG + 4 * i + 3];
+            const float dhpost = fmaf(g3, h3, fmaf(g2, h2, fmaf(g1, h1, g0 * h0)));
+            // dhpre[j] = sum_i G[i][j] hpost[i]; lane i keeps j == i
+            const float t0 = group_sum4(g0 * hpost), t1 = group_sum4(g1 * hpost);
+            const float t2 = group_sum4(g2 * hpost), t3 = group_sum4(g3 * hpost);
+            const float dhpre = i == 0 ? t0 : i == 1 ? t1 : i == 2 ? t2 : t3;
+            const float dl_pre = dhpre * hpre * (1.0f - hpre);
+            const float dl_post = dhpost * hpost * (1.0f - 0.5f * hpost);
+            // ---- reverse sweep through the Sinkhorn iterations (dP = G)
+            float d0 = g0, d1 = g1, d2 = g2, d3 = g3;
+            for (int k = p.sk_iters - 1; k >= 0; --k) {
+                const float4 cd = *reinterpret_cast<const float4*>(skl + k * kSkStride + 4);
+                const float dr = skl[k * kSkStride + i];
+                // column step  y = x / c  (c per column):  dx = (dy - sum_rows(dy*y)) / c ;  x = y * c
+                const float q0 = group_sum4(d0 * p0), q1 = group_sum4(d1 * p1);
+                const float q2 = group_sum4(d2 * p2), q3 = group_sum4(d3 * p3);
+                d0 = (d0 - q0) * rcp_approx(cd.x); d1 = (d1 - q1) * rcp_approx(cd.y);
+                d2 = (d2 - q2) * rcp_approx(cd.z); d3 = (d3 - q3) * rcp_approx(cd.w);
+                p0 *= cd.x; p1 *= cd.y; p2 *= cd.z; p3 *= cd.w;
+                // row step  y = x / dr
+                const float qr = fmaf(d3, p3, fmaf(d2, p2, fmaf(d1, p1, d0 * p0)));
+                const float rr = rcp_approx(dr);
+                d0 = (d0 - qr) * rr; d1 = (d1 - qr) * rr; d2 = (d2 - qr) * rr; d3 = (d3 - qr) * rr;
+                p0 *= dr; p1 *= dr; p2 *= dr; p3 *= dr;
+            }
+            // softmax * 4 backward (row-local): dl = s * (d - sum(d*s)/4)
+            const float qs = 0.25f * fmaf(d3, s3, fmaf(d2, s2, fmaf(d1, s1, d0 * s0)));
+            const float dl0 = s0 * (d0 - qs), dl1 = s1 * (d1 - qs), dl2 = s2 * (d2 - qs), dl3 = s3 * (d3 - qs);
+            // ---- parameter-gradient partials, e = d raw, kappa (RMSNorm backward)
+            acc_b[0] += dl_pre; acc_b[1] += dl_post;
+            acc_b[2] += dl0; acc_b[3] += dl1; acc_b[4] += dl2; acc_b[5] += dl3;
+            acc_a[0] = fmaf(dl_pre, z_pre, acc_a[0]);
+            acc_a[1] = fmaf(dl_post, z_post, acc_a[1]);
+            acc_a[2] += fmaf(dl3, z3, fmaf(dl2, z2, fmaf(dl1, z1, dl0 * z0)));
+            const float e_pre = a_pre * dl_pre * inv_rms, e_post = a_post * dl_post * inv_rms;
+            const float e0 = a_res * dl0 * inv_rms, e1 = a_res * dl1 * inv_rms;
+            const float e2 = a_res * dl2 * inv_rms, e3 = a_res * dl3 * inv_rms;
+            // d inv_rms = sum_k dz_k raw_k = sum_k e_k raw_k / inv_rms ;  kappa = -d inv_rms * inv_rms^3 / N
+            float dsum = e_pre * r[i] + e_post * r[kN + i] +
+                         (e0 * r[2 * kN + 4 * i] + e1 * r[2 * kN + 4 * i + 1] + e2 * r[2 * kN + 4 * i + 2] + e3 * r[2 * kN + 4 * i + 3]);
+            dsum = group_sum4(dsum);
+            __nv_bfloat16* eb = reinterpret_cast<__nv_bfloat16*>(c + kCoefE);
+            eb[i] = __float2bfloat16_rn(e_pre);
+            eb[kN + i] = __float2bfloat16_rn(e_post);
+            *reinterpret_cast<uint2*>(eb + 2 * kN + 4 * i) = make_uint2(pack_bf16(e0, e1), pack_bf16(e2, e3));
+            if (i == 0) {
+                *reinterpret_cast<uint4*>(eb + kL) = make_uint4(0u, 0u, 0u, 0u);      // logits 24..31: zero pad
+                c[kCoefKappa] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
+            }
+            const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + tk;
+            if (tok < p.T) {
+                float* o = p.e_out + tok * kL;
+                o[i] = e_pre;
+                o[kN + i] = e_post;
+                *reinterpret_cast<float4*>(o + 2 * kN + 4 * i) = make_float4(e0, e1, e2, e3);
+            }   // padded rows have dy = 0, hence G = 0 and every dl = 0: they add nothing to the sums above
+            __threadfence_block();
+            bar_arrive(kBarCoef + buf, kWorkerThreads + 32);
+        }
+        // fold the 8 token groups of the warp (lanes with equal i), fixed order
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc_b[k] += __shfl_xor_sync(0xffffffffu, acc_b[k], o);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], o);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc_a[k] = group_sum4(acc_a[k]);
+        if (lane < 4) {
+            float* o = p.cta_accum + (size_t)blockIdx.x * kAccum;
+            o[i] = acc_b[0];
+            o[kN + i] = acc_b[1];
+            o[2 * kN + 4 * i + 0] = acc_b[2]; o[2 * kN + 4 * i + 1] = acc_b[3];
+            o[2 * kN + 4 * i + 2] = acc_b[4]; o[2 * kN + 4 * i + 3] = acc_b[5];
+            if (i == 0) { o[kL] = acc_a[0]; o[kL + 1] = acc_a[1]; o[kL + 2] = acc_a[2]; }
+        }
+      }
+    } else {
+        // ===================================================== worker warps
+        reg_alloc<kWorkerRegs>();
+        const int w = warp, g = lane >> 2, t = lane & 3;
+        uint32_t bfrag[kN][2][3][2];
+#pragma unroll
+        for (int j = 0; j < kN; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int k0 = j * kC + 32 * w + 8 * t + 4 * q;
+                float sc[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sc[e] = __ldg(p.scale + k0 + e);
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt) {
+                    const int col = nt * 8 + g;
+                    float f[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) f[e] = __ldg(p.phi + (size_t)(k0 + e) * kL + col) * sc[e];
+                    bfrag[j][q][nt][0] = pack_bf16(f[0], f[1]);
+                    bfrag[j][q][nt][1] = pack_bf16(f[2], f[3]);
+                }
+            }
+        const int cb = w >> 1, hh = w & 1;
+        uint32_t off[kN];                                   // own 16-byte chunk of (token g, stream j)
+#pragma unroll
+        for (int j = 0; j < kN; ++j) {
+            const int row = g * kN + j;
+            off[j] = cb * kBoxBytes + row * 128 + (((4 * hh + t) ^ (row & 7)) << 4);
+        }
+        // ldmatrix lane addresses for G = dy x^T: matrix (lane>>3) of an x4 load, row (lane&7)
+        const int lm = lane >> 3, lr = lane & 7;
+        const uint32_t stage0 = smem_u32(smem);
+
+        auto finish_tile = [&](int itp) {
+            const int bufp = itp & 1;
+            const uint32_t sbase = stage0 + (itp % kStages) * kStageBytes;
+            bar_sync(kBarCoef + bufp, kWorkerThreads + 32);
+            const float* c = coef + (bufp * kTok + g) * kCoefStride;
+            const uint32_t* ew = reinterpret_cast<const uint32_t*>(c + kCoefE);
+            const uint32_t ea0 = ew[t], ea2 = ew[t + 4], eb0 = ew[t + 8];     // e[2t..], e[2t+8..], e[2t+16..]
+            const float kappa = c[kCoefKappa];
+            uint32_t dyr[kN][4];
+#pragma unroll
+            for (int ii = 0; ii < kN; ++ii) {
+                const uint4 v = lds128(sbase + kHalfBytes + off[ii]);
+                dyr[ii][0] = v.x; dyr[ii][1] = v.y; dyr[ii][2] = v.z; dyr[ii][3] = v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < kN; ++j) {
+                const float4 mt = *reinterpret_cast<const float4*>(c + 4 * j);       // M[0..3][j]
+                const uint4 xv = lds128(sbase + off[j]);
+                const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+                uint32_t out[4];
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        // dx_proj for Kidx (j, 32w + 8t + 4q + 2rr + {0,1}) of token g: e . W^T
+                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                        mma_bf16_16816(acc, ea0, 0u, ea2, 0u, movmatrix_trans(bfrag[j][q][0][rr]), movmatrix_trans(bfrag[j][q][1][rr]));
+                        mma_bf16_16816(acc, eb0, 0u, 0u, 0u, movmatrix_trans(bfrag[j][q][2][rr]), 0u);
+                        const int e = 2 * q + rr;
+                        float lo = fmaf(kappa, bf16lo(xw[e]), acc[0]);
+                        float hi = fmaf(kappa, bf16hi(xw[e]), acc[1]);
+                        lo = fmaf(mt.x, bf16lo(dyr[0][e]), lo); hi = fmaf(mt.x, bf16hi(dyr[0][e]), hi);
+                        lo = fmaf(mt.y, bf16lo(dyr[1][e]), lo); hi = fmaf(mt.y, bf16hi(dyr[1][e]), hi);
+                        lo = fmaf(mt.z, bf16lo(dyr[2][e]), lo); hi = fmaf(mt.z, bf16hi(dyr[2][e]), hi);
+                        lo = fmaf(mt.w, bf16lo(dyr[3][e]), lo); hi = fmaf(mt.w, bf16hi(dyr[3][e]), hi);
+                        out[e] = pack_bf16(lo, hi);
+                    }
+                sts128(sbase + kHalfBytes + off[j], make_uint4(out[0], out[1], out[2], out[3]));
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bar_done[itp % kStages]);
+        };
+
+        for (int it = 0; it < n_local; ++it) {
+            const int s = it % kStages;
+            const uint32_t sbase = stage0 + s * kStageBytes;
+            mbar_wait(&bar_full[s], (it / kStages) & 1);
+            // ---- raw^T = W^T x^T (tokens are the MMA N), sum x^2 on the diagonal of x x^T
+            float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, accs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < kN; ++j) {
+                const uint4 xv = lds128(sbase + off[j]);
+                mma_bf16_16816(acc0, bfrag[j][0][0][0], bfrag[j][0][1][0], bfrag[j][0][0][1], bfrag[j][0][1][1], xv.x, xv.y);
+                mma_bf16_16816(acc1, bfrag[j][0][2][0], 0u, bfrag[j][0][2][1], 0u, xv.x, xv.y);
+                mma_bf16_16816(accs, xv.x, 0u, xv.y, 0u, xv.x, xv.y);
+                mma_bf16_16816(acc0, bfrag[j][1][0][0], bfrag[j][1][1][0], bfrag[j][1][0][1], bfrag[j][1][1][1], xv.z, xv.w);
+                mma_bf16_16816(acc1, bfrag[j][1][2][0], 0u, bfrag[j][1][2][1], 0u, xv.z, xv.w);
+                mma_bf16_16816(accs, xv.z, 0u, xv.w, 0u, xv.z, xv.w);
+            }
+            // ---- G = dy x^T per token: rows (token, i) of dy against rows (token, j) of x, block diagonal
+            float gacc[2][2][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) gacc[m][h2][0] = gacc[m][h2][1] = gacc[m][h2][2] = gacc[m][h2][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint32_t bx[4][2];
+#pragma unroll
+                for (int nn = 0; nn < 4; nn += 2) {
+                    // x rows 8nn..8nn+15, chunks (4hh + 2ks), (4hh + 2ks + 1)
+                    const int row = 8 * nn + (lm >> 1) * 8 + lr;
+                    const int chunk = 4 * hh + 2 * ks + (lm & 1);
+                    ldmatrix_x4(sbase + cb * kBoxBytes + row * 128 + ((chunk ^ (row & 7)) << 4),
+                                bx[nn][0], bx[nn][1], bx[nn + 1][0], bx[nn + 1][1]);
+                }
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    uint32_t a0, a1, a2, a3;
+                    const int row = 16 * m + (lm & 1) * 8 + lr;
+                    const int chunk = 4 * hh + 2 * ks + (lm >> 1);
+                    ldmatrix_x4(sbase + kHalfBytes + cb * kBoxBytes + row * 128 + ((chunk ^ (row & 7)) << 4), a0, a1, a2, a3);
+                    mma_bf16_16816(gacc[m][0], a0, a1, a2, a3, bx[2 * m][0], bx[2 * m][1]);
+                    mma_bf16_16816(gacc[m][1], a0, a1, a2, a3, bx[2 * m + 1][0], bx[2 * m + 1][1]);
+                }
+            }
+            bar_sync(kBarPartFree, kWorkerThreads + 32);      // reducer finished reading the previous partials
+            {
+                float* pw = part + (size_t)w * kTok * kPartStride;
+                // raw^T fragments: (logit g | g+8 | 16+g, tokens 2t, 2t+1)
+                pw[(2 * t) * kPartStride + g] = acc0[0];      pw[(2 * t + 1) * kPartStride + g] = acc0[1];
+                pw[(2 * t) * kPartStride + 8 + g] = acc0[2];  pw[(2 * t + 1) * kPartStride + 8 + g] = acc0[3];
+                pw[(2 * t) * kPartStride + 16 + g] = acc1[0]; pw[(2 * t + 1) * kPartStride + 16 + g] = acc1[1];
+                if (t == (g >> 1)) pw[g * kPartStride + kL] = accs[g & 1];       // diagonal of x x^T
+                // G fragments: m-tile m rows = (token 4m + {0,1} | 4m + {2,3}, i), n-tile cols = (token, j)
+                if ((g >> 2) == (t >> 1)) {
+                    const int i = g & 3, jj = 2 * (t & 1);
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const int tokA = 4 * m + (g >> 2), tokB = 4 * m + 2 + (g >> 2);
+                        *reinterpret_cast<float2*>(pw + tokA * kPartStride + kPartG + 4 * i + jj) =
+                            make_float2(gacc[m][0][0], gacc[m][0][1]);
+                        *reinterpret_cast<float2*>(pw + tokB * kPartStride + kPartG + 4 * i + jj) =
+                            make_float2(gacc[m][1][2], gacc[m][1][3]);
+                    }
+                }
+            }
+            __threadfence_block();
+            bar_arrive(kBarPart + (it & 1), kWorkerThreads + 32);
+            if (it > 0) finish_tile(it - 1);
+        }
+        if (n_local > 0) finish_tile(n_local - 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ B2: dW = x^T E
+constexpr int kDwTok = 16;
+constexpr int kDwThreads = 512;                       // 16 MMA warps; thread 0 also issues the TMA loads
+constexpr int kDwStages = 3;
+constexpr int kDwStageBytes = kDwTok * kRowBytes;     // 64 KB, 32 boxes of [16 tokens x 64 cols]
+constexpr int kDwBoxBytes = kDwTok * 128;
+constexpr int kDwOffE = kDwStages * kDwStageBytes;    // E^T as two bf16 terms: [2 buffers][hi|lo][24][8 words]
+constexpr int kDwEWords = 2 * kL * 8;
+constexpr int kDwOffBar = kDwOffE + 2 * kDwEWords * 4;
+constexpr int kDwSmemBytes = kDwOffBar + kDwStages * 8;
+
+__global__ void __launch_bounds__(kDwThreads, 1)
+mhc_stream_dw_kernel(const __grid_constant__ CUtensorMap tmap_xt, const float* __restrict__ e_in, float* __restrict__ dw_part,
+                     int64_t T, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (smem_u32(smem) & 1023u) __trap();
+    uint32_t* et = reinterpret_cast<uint32_t*>(smem + kDwOffE);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kDwOffBar);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_local = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto load_tile = [&](int it) {
+        const int s = it % kDwStages;
+        const int tok0 = ((int)blockIdx.x + it * (int)gridDim.x) * kDwTok;
+        mbar_arrive_expect_tx(&bar_full[s], kDwStageBytes);
+        for (int b = 0; b < kRow / 64; ++b)
+            tma_load_2d(smem + s * kDwStageBytes + b * kDwBoxBytes, &tmap_xt, &bar_full[s], b * 64, tok0);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kDwStages; ++s) mbar_init(&bar_full[s], 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_xt);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (n_local > 0) load_tile(0);
+        if (n_local > 1) load_tile(1);
+    }
+    // warp w owns K rows [128w, 128w+128) -> 8 m-tiles of 16; accumulators [8][3][4]
+    const int w = warp, g = lane >> 2, t = lane & 3;
+    float acc[8][3][4];
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) acc[m][nt][0] = acc[m][nt][1] = acc[m][nt][2] = acc[m][nt][3] = 0.f;
+    const int lm = lane >> 3, lr = lane & 7;
+    const uint32_t stage0 = smem_u32(smem);
+    const int tid = threadIdx.x;
+    for (int it = 0; it < n_local; ++it) {
+        const int s = it % kDwStages, eb = it & 1;
+        const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kDwTok;
+        // E tile -> two bf16 terms, transposed to [logit][token pair]
+        if (tid < kDwTok * kL / 2) {
+            const int logit = tid % kL, pair = tid / kL;               // tokens 2*pair, 2*pair+1
+            const int64_t ta = tok0 + 2 * pair, tb = ta + 1;
+            const float va = ta < T ? __ldg(e_in + ta * kL + logit) : 0.f;
+            const float vb = tb < T ? __ldg(e_in + tb * kL + logit) : 0.f;
+            const __nv_bfloat16 ha = __float2bfloat16_rn(va), hb = __float2bfloat16_rn(vb);
+            const float la = va - __bfloat162float(ha), lb = vb - __bfloat162float(hb);
+            uint32_t* dst = et + eb * kDwEWords;
+            dst[logit * 8 + pair] = pack_bf16(__bfloat162float(ha), __bfloat162float(hb));
+            dst[kL * 8 + logit * 8 + pair] = pack_bf16(la, lb);
+        }
+        __syncthreads();            // E^T visible; every warp is done with tile it-1, so its stage is free
+        if (tid == 0 && it + 2 < n_local) load_tile(it + 2);
+        mbar_wait(&bar_full[s], (it / kDwStages) & 1);
+        const uint32_t sbase = stage0 + s * kDwStageBytes;
+        const uint32_t* ehi = et + eb * kDwEWords;
+        uint32_t bh[3][2], bl[3][2];
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+            bh[nt][0] = ehi[(nt * 8 + g) * 8 + t];            bh[nt][1] = ehi[(nt * 8 + g) * 8 + t + 4];
+            bl[nt][0] = ehi[kL * 8 + (nt * 8 + g) * 8 + t];   bl[nt][1] = ehi[kL * 8 + (nt * 8 + g) * 8 + t + 4];
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            // A = x^T: K rows 128w + 16m .. +15 (two 8-column chunks), k = 16 tokens; transposed 8x8 loads
+            const int box = 2 * w + (m >> 2), chunk = 2 * (m & 3) + (lm & 1);
+            const int row = (lm >> 1) * 8 + lr;               // token
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4_trans(sbase + box * kDwBoxBytes + row * 128 + ((chunk ^ (row & 7)) << 4), a0, a1, a2, a3);
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                mma_bf16_16816(acc[m][nt], a0, a1, a2, a3, bh[nt][0], bh[nt][1]);
+                mma_bf16_16816(acc[m][nt], a0, a1, a2, a3, bl[nt][0], bl[nt][1]);
+            }
+        }
+    }
+    float* out = dw_part + (size_t)blockIdx.x * kRow * kL;
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+            const int k0 = 128 * w + 16 * m + g;
+            *reinterpret_cast<float2*>(out + (size_t)k0 * kL + nt * 8 + 2 * t) = make_float2(acc[m][nt][0], acc[m][nt][1]);
+            *reinterpret_cast<float2*>(out + (size_t)(k0 + 8) * kL + nt * 8 + 2 * t) = make_float2(acc[m][nt][2], acc[m][nt][3]);
+        }
+}
+
+// dphi = scale * dW, dscale = sum_k phi * dW (straight-through the bf16 rounding of scale*phi),
+// dbias / dalpha from the B1 per-CTA partials.  Fixed summation order over CTAs.
+__global__ void __launch_bounds__(256)
+mhc_stream_bwd_finalize_kernel(const float* __restrict__ dw_part, int dw_ctas, const float* __restrict__ cta_accum,
+                               int acc_ctas, const float* __restrict__ phi, const float* __restrict__ scale,
+                               float* __restrict__ dphi, float* __restrict__ dscale, float* __restrict__ dbias,
+                               float* __restrict__ dalpha) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row < kRow) {
+        float dwv = 0.f;
+        if (lane < kL)
+            for (int c = 0; c < dw_ctas; ++c) dwv += dw_part[((size_t)c * kRow + row) * kL + lane];
+        float ds = lane < kL ? dwv * phi[(size_t)row * kL + lane] : 0.f;
+        if (lane < kL) dphi[(size_t)row * kL + lane] = dwv * scale[row];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        if (lane == 0) dscale[row] = ds;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < kAccum) {
+        float s0 = 0.f;
+        for (int c = 0; c < acc_ctas; ++c) s0 += cta_accum[(size_t)c * kAccum + threadIdx.x];
+        if (threadIdx.x < kL) dbias[threadIdx.x] = s0; else dalpha[threadIdx.x - kL] = s0;
+    }
+}
+
+inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct BwdWs {
+    float* e; float* dw_part; float* cta_accum;
+    size_t total;
+};
+BwdWs carve(void* base, int64_t T, int ctas) {
+    BwdWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return reinterpret_cast<uint8_t*>(base) + o; };
+    w.e = reinterpret_cast<float*>(take((size_t)T * kL * 4));
+    w.dw_part = reinterpret_cast<float*>(take((size_t)ctas * kRow * kL * 4));
+    w.cta_accum = reinterpret_cast<float*>(take((size_t)ctas * kAccum * 4));
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+}  // namespace hvs
+
+extern "C" size_t hvs_mhc_stream_bwd_workspace(int64_t T, int n, int C) {
+    using namespace hvs;
+    if (T < 0 || n != kN || C != kC) return 0;
+    return carve(nullptr, T, sm_count()).total;
+}
+
+extern "C" int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* phi, const float* bias,
+                                  const float* alpha, const float* scale, void* dx, float* dphi, float* dbias,
+                                  float* dalpha, float* dscale, int64_t T, int n, int C, int sk_iters,
+                                  float eps_rms, float eps_sk, uint32_t flags, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (T < 0) return HVS_ERR_BAD_ARG;
+    if (n != kN || C != kC || sk_iters < 0 || sk_iters > kMaxIters) return HVS_ERR_UNSUPPORTED;
+    if (flags & HVS_MHC_SPLIT_PHI) return HVS_ERR_UNSUPPORTED;
+    if (!phi || !bias || !alpha || !scale || !dphi || !dbias || !dalpha || !dscale) return HVS_ERR_BAD_ARG;
+    if (T > 0 && (!x || !dy || !dx)) return HVS_ERR_BAD_ARG;
+    if (T * kN >= (int64_t)1 << 31) return HVS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15)
+        return HVS_ERR_ALIGNMENT;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return HVS_ERR_ALIGNMENT;
+    const int sms = sm_count();
+    const BwdWs ws = carve(workspace, T, sms);
+    if (workspace_bytes < ws.total) return HVS_ERR_WORKSPACE;
+    int grid1 = 0, grid2 = 0;
+    if (T > 0) {
+        CUtensorMap tx, tdy, tdx, txt;
+        int rc = make_tmap_bf16_2d(&tx, x, (uint64_t)T * kN, kC, kTok * kN);
+        if (rc) return rc;
+        rc = make_tmap_bf16_2d(&tdy, dy, (uint64_t)T * kN, kC, kTok * kN);
+        if (rc) return rc;
+        rc = make_tmap_bf16_2d(&tdx, dx, (uint64_t)T * kN, kC, kTok * kN);
+        if (rc) return rc;
+        rc = make_tmap_bf16_2d(&txt, x, (uint64_t)T, kRow, kDwTok);
+        if (rc) return rc;
+        static bool attr_set = false;
+        if (!attr_set) {
+            HVS_CUDA_TRY(cudaFuncSetAttribute(mhc_stream_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+            HVS_CUDA_TRY(cudaFuncSetAttribute(mhc_stream_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
+            attr_set = true;
+        }
+        BwdParams p;
+        p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale;
+        p.e_out = ws.e; p.cta_accum = ws.cta_accum;
+        p.T = T;
+        p.num_tiles = (int)((T + kTok - 1) / kTok);
+        p.sk_iters = sk_iters; p.eps_rms = eps_rms; p.eps_sk = eps_sk;
+        grid1 = p.num_tiles < sms ? p.num_tiles : sms;
+        mhc_stream_bwd_kernel<<<grid1, kThreads, kSmemBytes, stream>>>(tx, tdy, tdx, p);
+        count_launch();
+        int rc2 = launch_status();
+        if (rc2) return rc2;
+        const int tiles2 = (int)((T + kDwTok - 1) / kDwTok);
+        grid2 = tiles2 < sms ? tiles2 : sms;
+        mhc_stream_dw_kernel<<<grid2, kDwThreads, kDwSmemBytes, stream>>>(txt, ws.e, ws.dw_part, T, tiles2);
+        count_launch();
+        rc2 = launch_status();
+        if (rc2) return rc2;
+    }
+    mhc_stream_bwd_finalize_kernel<<<kRow / 8, 256, 0, stream>>>(ws.dw_part, grid2, ws.cta_accum, grid1, phi, scale, dphi,
+                                                                 dscale, dbias, dalpha);
+    count_launch();
+    return launch_status();
 }

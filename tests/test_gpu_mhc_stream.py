@@ -137,3 +137,57 @@ def test_large_linearity_property():
     mag = mhc_ref.mixing_condition_magnitude(xs, ref["H_pre"], ref["H_post"], ref["H_res"])
     y32 = torch.einsum("tij,tjc->tic", ref["H_res"], xs.float()) + ref["H_post"][:, :, None] * ref["u"][:, None, :]
     assert ((y[idx.cuda()].cpu().float() - y32).abs() <= ULP_BOUND * mhc_ref.bf16_ulp(mag)).all()
+
+
+# ----------------------------------------------------------------------------- backward
+def run_bwd(x, dy, phi, bias, al, scale, **kw):
+    import hvs_b200
+    dev = "cuda:0"
+    out = hvs_b200.ops.mhc_stream_bwd(x.to(dev), dy.to(dev), phi.to(dev), bias.to(dev), al.to(dev), scale.to(dev), **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu() for k, v in out.items()}
+
+
+def check_bwd(inp, dy, got, tag=""):
+    x, phi, bias, al, scale = inp
+    ref = mhc_ref.stream_mhc_backward(x, dy, phi, bias, al, scale)
+    fwd = mhc_ref.stream_mhc_forward(x, phi, bias, al, scale)
+    # dx: bf16, error measured at the condition magnitude of the dominant term  M^T dy
+    m = fwd["H_res"] + fwd["H_post"][:, :, None] * fwd["H_pre"][:, None, :]
+    mag = torch.einsum("tij,tic->tjc", m.abs(), dy.float().abs()) + ref["dx"].abs()
+    ulps = ((got["dx"].float() - ref["dx"]).abs() / mhc_ref.bf16_ulp(mag)).max().item()
+    assert ulps <= ULP_BOUND, f"{tag} dx off by {ulps:.2f} bf16 ulp"
+    for name in ("dphi", "dbias", "dalpha", "dscale"):
+        a, b = got[name].double(), ref[name].double()
+        rel = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+        assert rel < 2e-3, f"{tag} {name} relative error {rel:.2e}"
+    return ulps
+
+
+@pytest.mark.parametrize("t", [1, 7, 8, 9, 64, 1000, 2051])
+def test_backward_matches_oracle(t):
+    inp = make_inputs(t, seed=100 + t, alpha=0.3, phistd=0.03, bstd=0.1)
+    dy = torch.randn(t, 4, 512, generator=torch.Generator().manual_seed(t)).to(torch.bfloat16)
+    got = run_bwd(*inp[:1], dy, *inp[1:])
+    check_bwd(inp, dy, got, f"T={t}")
+
+
+def test_backward_init_scale_logits():
+    inp = make_inputs(515, seed=21)          # alpha = 0.01, the microbenchmark's configuration
+    dy = torch.randn(515, 4, 512, generator=torch.Generator().manual_seed(5)).to(torch.bfloat16)
+    got = run_bwd(*inp[:1], dy, *inp[1:])
+    check_bwd(inp, dy, got, "init")
+
+
+def test_backward_deterministic_and_linear_in_dy():
+    inp = make_inputs(3000, seed=33, alpha=0.2)
+    g = torch.Generator().manual_seed(6)
+    dy = torch.randn(3000, 4, 512, generator=g).to(torch.bfloat16)
+    a = run_bwd(*inp[:1], dy, *inp[1:])
+    b = run_bwd(*inp[:1], dy, *inp[1:])
+    for k in a:
+        assert torch.equal(a[k].view(torch.int16) if a[k].dtype == torch.bfloat16 else a[k], b[k].view(torch.int16) if b[k].dtype == torch.bfloat16 else b[k]), k
+    # parameter gradients are linear in dy: doubling dy (exact in bf16) doubles them
+    c = run_bwd(*inp[:1], (dy.float() * 2).to(torch.bfloat16), *inp[1:])
+    for k in ("dphi", "dbias", "dalpha", "dscale"):
+        assert torch.allclose(c[k], 2 * a[k], rtol=1e-4, atol=1e-6 * a[k].abs().max().item()), k
