@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract for the hot path (BASELINE.json configs[1]).
+
+Workload: stream-mHC layer microbenchmark, n = 4 streams, C = 512, T = 2^20 tokens per GPU, bf16,
+forward + backward, 20 Sinkhorn iterations, synthetic inputs, random-init parameters
+(SURVEY.md section 8(d), config 2).  One "step" = one forward + one backward over the T tokens.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--tokens T] [--impl reference]
+
+N > 1 is launched by the driver with torch.distributed.run (one rank per GPU).  Tokens are sharded
+across ranks with no data-path collective ("weak": T tokens per GPU); like a DDP step, the small
+parameter gradients are all-reduced over NCCL after the backward.  Rank 0 prints ONE JSON line.
+
+value        tokens/s (whole job) with x, dy resident in HBM, CUDA-event timed, max over ranks
+e2e          the same metric through the host-buffer entry (stream_mhc_fwd_bwd_host): pinned host x, dy
+             -> H2D -> kernels -> D2H of y, dx and the parameter gradients, all inside the timed region
+roofline     dominant kernel (backward per-token kernel): algorithmic 12288 B/token over its own
+             CUDA-event duration (hvs_mhc_stream_profile hooks), against MEASURED_PEAKS.json
+cpu_baseline oracle/ (a port of the reference's PyTorch arithmetic) timed on the host cores, rank 0,
+             N = 1 only, bounded sample of the same workload
+--impl reference   times that CPU implementation alone (the reference is pure PyTorch; its own modules
+             cannot travel to the GPU box)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_STREAMS, CHANNELS, LOGITS = 4, 512, 24
+FWD_BYTES, BWD_BYTES = 8192, 12288                   # algorithmic bytes per token
+METRIC, UNIT = "mhc_layer_fwd_bwd_tokens_per_s", "tokens/s"
+FALLBACK_HBM_GBS = 6650.0                            # B200_PROFILING.md fallback
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+def load_traffic():
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(tokens: int, steps: int, warmup: int):
+    """Oracle forward+backward (fp32, all host threads) on `tokens` tokens; returns tokens/s and meta."""
+    import torch
+    from oracle import mhc_ref
+    torch.manual_seed(0)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(tokens, N_STREAMS, CHANNELS, generator=g).to(torch.bfloat16)
+    dy = torch.randn(tokens, N_STREAMS, CHANNELS, generator=g).to(torch.bfloat16)
+    phi = torch.randn(N_STREAMS * CHANNELS, LOGITS, generator=g) * 0.02
+    bias, alpha, scale = torch.zeros(LOGITS), torch.full((3,), 0.01), torch.ones(N_STREAMS * CHANNELS)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        mhc_ref.stream_mhc_backward(x, dy, phi, bias, alpha, scale)      # forward + autograd backward
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    dt = sum(ts) / len(ts)
+    return tokens / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 8192
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    tps, dt, threads = cpu_reference_run(sample, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "mHC layer microbenchmark n=4 C=512 fwd+bwd, 20 Sinkhorn iters (BASELINE configs[1])",
+                   "tokens_per_step": sample, "note": "bounded sample of the 2^20-token workload; CPU throughput is flat in T"},
+        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} tokens fwd+bwd, oracle/mhc_ref.py (torch fp32 CPU), mean of {steps} steps"},
+        "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--tokens", type=int, default=1 << 20, help="tokens per GPU")
+    ap.add_argument("--impl", default="hvs_b200", choices=["hvs_b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import hvs_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    T = args.tokens
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn(T, N_STREAMS, CHANNELS, generator=g, device=dev, dtype=torch.bfloat16)
+    dy = torch.randn(T, N_STREAMS, CHANNELS, generator=g, device=dev, dtype=torch.bfloat16)
+    gp = torch.Generator(device=dev).manual_seed(0)                      # identical parameters on every rank
+    phi = torch.randn(N_STREAMS * CHANNELS, LOGITS, generator=gp, device=dev) * 0.02
+    bias = torch.zeros(LOGITS, device=dev)
+    alpha = torch.full((3,), 0.01, device=dev)
+    scale = torch.ones(N_STREAMS * CHANNELS, device=dev)
+    y = torch.empty_like(x)
+    lib = hvs_b200.load_library()
+
+    def step():
+        hvs_b200.ops.mhc_stream_fwd(x, phi, bias, alpha, scale, out=y)
+        grads = hvs_b200.ops.mhc_stream_bwd(x, dy, phi, bias, alpha, scale)
+        if world > 1:                                                    # DDP-style parameter-gradient exchange
+            flat = torch.cat([grads[k].reshape(-1) for k in ("dphi", "dbias", "dalpha", "dscale")])
+            dist.all_reduce(flat)
+        return grads
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    launches0 = hvs_b200._lib.launch_count()
+    lib.hvs_mhc_stream_profile(1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    barrier()
+    t_wall = time.perf_counter()
+    ev0.record()
+    for i in range(args.steps):
+        step()
+        buf = (ctypes.c_float * 4)()
+        lib.hvs_mhc_stream_kernel_ms(buf)                # per-kernel event durations of this step (inputs stay in HBM)
+        kms.append(list(buf))
+    ev1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    lib.hvs_mhc_stream_profile(0)
+    launches = hvs_b200._lib.launch_count() - launches0
+    step_ms = ev0.elapsed_time(ev1) / args.steps         # exactly K steps, including the gaps between them
+    t = torch.tensor([step_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms = float(t.item())
+    value = world * T / (step_ms * 1e-3)
+
+    # ---- end to end through the host-buffer entry (pinned host memory, copies inside the timed region)
+    layer = hvs_b200.StreamMHC(device=dev)
+    with torch.no_grad():
+        layer.phi.copy_(phi); layer.bias.copy_(bias); layer.alpha.copy_(alpha); layer.rms_scale.copy_(scale)
+    del y
+    torch.cuda.empty_cache()
+    xh = x.cpu().pin_memory(); dyh = dy.cpu().pin_memory()
+    yh = torch.empty_like(xh).pin_memory(); dxh = torch.empty_like(xh).pin_memory()
+    hvs_b200.stream_mhc_fwd_bwd_host(xh[: 1 << 16], dyh[: 1 << 16], layer, yh[: 1 << 16], dxh[: 1 << 16])   # warm-up
+    barrier()
+    e2e_ts = []
+    for _ in range(args.e2e_steps):
+        t0 = time.perf_counter()
+        gh = hvs_b200.stream_mhc_fwd_bwd_host(xh, dyh, layer, yh, dxh)
+        torch.cuda.synchronize()
+        e2e_ts.append(time.perf_counter() - t0)
+    e2e_dt = sum(e2e_ts) / len(e2e_ts)
+    te = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * T / float(te.item())
+    row_bytes = N_STREAMS * CHANNELS * 2
+    grad_bytes = 4 * (N_STREAMS * CHANNELS * LOGITS + LOGITS + 3 + N_STREAMS * CHANNELS)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        fwd_ms = sum(k[0] for k in kms) / len(kms)
+        bwd_ms = sum(k[1] for k in kms) / len(kms)
+        dw_ms = sum(k[2] for k in kms) / len(kms)
+        fin_ms = sum(k[3] for k in kms) / len(kms)
+        achieved = BWD_BYTES * T / (bwd_ms * 1e-3) / 1e9
+        traffic = load_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 in/out, fp32 accumulate and Sinkhorn", "data": "synthetic",
+            "config": {"workload": "mHC layer microbenchmark n=4 C=512 bf16 fwd+bwd, 20 Sinkhorn iters (BASELINE configs[1])",
+                       "tokens_per_gpu": T, "parallelism": f"dp{world}" if world > 1 else "single",
+                       "l2": "inputs (4.3 GB each) are larger than L2; no flush needed",
+                       "params": "phi~N(0,0.02^2), bias=0, alpha=0.01, rms_scale=1"},
+            "hbm_gbs": {"fwd_bwd_algorithmic": (FWD_BYTES + BWD_BYTES) * T * world / (step_ms * 1e-3) / 1e9,
+                        "frac_of_peak": (FWD_BYTES + BWD_BYTES) * T / (step_ms * 1e-3) / 1e9 / peak, "peak": peak,
+                        "peak_source": peak_src, "frac_of_nominal_8000": (FWD_BYTES + BWD_BYTES) * T / (step_ms * 1e-3) / 1e9 / 8000.0},
+            "kernels_ms": {"mhc_stream_fwd_kernel": fwd_ms, "mhc_stream_bwd_kernel": bwd_ms, "mhc_stream_dw_kernel": dw_ms,
+                           "mhc_stream_bwd_finalize_kernel": fin_ms,
+                           "fwd_GBs": FWD_BYTES * T / (fwd_ms * 1e-3) / 1e9, "fwd_frac": FWD_BYTES * T / (fwd_ms * 1e-3) / 1e9 / peak},
+            "roofline": {"kernel": "mhc_stream_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback (B200_PROFILING.md)",
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (traffic or {}).get("mhc_stream_bwd_kernel_bytes_per_launch"),
+                         "traffic_note": (traffic or {}).get("note")},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * T * row_bytes,
+                    "d2h_bytes_per_step": 2 * T * row_bytes + grad_bytes, "ms_per_step": e2e_dt * 1e3,
+                    "api": "hvs_b200.stream_mhc_fwd_bwd_host (pinned host buffers, 3-stream chunk pipeline)"},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            tps, dt, threads = cpu_reference_run(8192, 2, 1)
+            line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "8192 tokens fwd+bwd, oracle/mhc_ref.py (torch fp32 CPU), mean of 2 steps after 1 warm-up"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,8 @@ _SIGNATURES = {
     "hvs_abi_version": (c_int, []),
     "hvs_error_string": (c_char_p, [c_int]),
     "hvs_launch_count": (c_uint64, []),
+    "hvs_mhc_stream_profile": (c_int, [c_int]),
+    "hvs_mhc_stream_kernel_ms": (c_int, [POINTER(c_float)]),
     "hvs_mhc_stream_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int64, c_int, c_int, c_int, c_float, c_float, c_uint32, c_void_p]),
     "hvs_mhc_stream_post": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),

@@ -6,6 +6,7 @@
 namespace hvs {
 
 std::atomic<uint64_t> g_launches{0};
+KernelTimer g_timer;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -45,6 +46,26 @@ extern "C" {
 int hvs_abi_version(void) { return 1; }
 
 uint64_t hvs_launch_count(void) { return hvs::g_launches.load(std::memory_order_relaxed); }
+
+int hvs_mhc_stream_profile(int enable) {
+    hvs::g_timer.enabled = enable != 0;
+    for (int i = 0; i < 4; ++i) hvs::g_timer.used[i] = false;
+    return HVS_OK;
+}
+
+int hvs_mhc_stream_kernel_ms(float* out4_host) {
+    if (!out4_host) return HVS_ERR_BAD_ARG;
+    for (int i = 0; i < 4; ++i) {
+        out4_host[i] = -1.0f;
+        if (hvs::g_timer.used[i]) {
+            cudaError_t e = cudaEventSynchronize(hvs::g_timer.end[i]);
+            if (e != cudaSuccess) return (int)e;
+            e = cudaEventElapsedTime(&out4_host[i], hvs::g_timer.beg[i], hvs::g_timer.end[i]);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    return HVS_OK;
+}
 
 const char* hvs_error_string(int code) {
     switch (code) {

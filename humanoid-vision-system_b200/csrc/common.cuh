@@ -38,6 +38,24 @@ inline int launch_status() {
     return e == cudaSuccess ? HVS_OK : (int)e;
 }
 
+// Optional event bracketing of individual launches (hvs_mhc_stream_profile).
+struct KernelTimer {
+    cudaEvent_t beg[4] = {nullptr, nullptr, nullptr, nullptr}, end[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool used[4] = {false, false, false, false};
+    bool enabled = false;
+};
+extern KernelTimer g_timer;
+inline void timer_begin(int slot, cudaStream_t s) {
+    if (!g_timer.enabled) return;
+    if (!g_timer.beg[slot]) { cudaEventCreate(&g_timer.beg[slot]); cudaEventCreate(&g_timer.end[slot]); }
+    cudaEventRecord(g_timer.beg[slot], s);
+}
+inline void timer_end(int slot, cudaStream_t s) {
+    if (!g_timer.enabled) return;
+    cudaEventRecord(g_timer.end[slot], s);
+    g_timer.used[slot] = true;
+}
+
 // 2-D bf16 tensor map: [rows][cols] row-major, box [box_rows][64 cols] (=128 B inner), 128-byte swizzle.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 

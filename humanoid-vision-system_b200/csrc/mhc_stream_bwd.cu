@@ -3,9 +3,9 @@
 // Kernel B1 (per-token, HBM-bound: reads x and dy, writes dx; 8-token tiles, 3-stage TMA ring):
 //   P1 workers (16 warps, split-K)  raw = x.W on the warp MMA path (W = bf16(scale*phi) in registers),
 //                                   sum x^2 and the per-token 4x4  G = dy x^T  as MMAs on the smem tiles
-//   reducer warp                    fixed-order sum of the 16 split-K partials
-//   coefficient warp (4 lanes/token) forward gates + Sinkhorn keeping the normalisers, then the exact
-//                                   reverse sweep through all iterations -> dlogits, e = d raw, kappa
+//   2 reducer warps                 fixed-order sum of the 16 split-K partials
+//   coefficient warp (lane/token)   forward gates + Sinkhorn in packed fp32x2 registers keeping the normalisers,
+//                                   then the exact reverse sweep through all iterations -> dlogits, e = d raw, kappa
 //   P3 workers                      dx = M^T dy  +  e W^T (MMA, W^T by movmatrix from the same registers)
 //                                        + kappa x, one rounding to bf16, in place over dy, TMA store
 //   The coefficient warp also emits E[T,24] (fp32) and per-CTA partial sums of dbias / dalpha.
@@ -25,7 +25,7 @@ namespace {
 constexpr int kTok = 8;                               // tokens per tile
 constexpr int kWorkers = 16;
 constexpr int kWorkerThreads = kWorkers * 32;
-constexpr int kThreads = (kWorkers + 4) * 32;         // + coefficient, producer, reducer, idle warps
+constexpr int kThreads = (kWorkers + 4) * 32;         // + coefficient, producer and 2 reducer warps
 constexpr int kWorkerRegs = 104, kRoleRegs = 64;
 constexpr int kStages = 3;
 constexpr int kHalfBytes = kTok * kRowBytes;          // 32 KB: x tile or dy tile
@@ -43,7 +43,9 @@ constexpr int kOffPart = kStages * kStageBytes;
 constexpr int kOffRed = kOffPart + kWorkers * kTok * kPartStride * 4;
 constexpr int kOffCoef = kOffRed + 2 * kTok * kRedStride * 4;
 constexpr int kOffSk = kOffCoef + 2 * kTok * kCoefStride * 4;
-constexpr int kOffBar = kOffSk + kTok * kMaxIters * kSkStride * 4;
+constexpr int kDlStride = 28;                         // per token: dl[24], dalpha terms[3]
+constexpr int kOffDl = kOffSk + kTok * kMaxIters * kSkStride * 4;
+constexpr int kOffBar = kOffDl + kTok * kDlStride * 4;
 constexpr int kSmemBytes = kOffBar + 2 * kStages * 8;
 static_assert(kOffBar % 8 == 0, "mbarrier alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -77,12 +79,12 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t v) {
     asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(r) : "r"(v));
     return r;
 }
-__device__ __forceinline__ float group_sum4(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    return v;
-}
-
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __global__ void __launch_bounds__(kThreads, 1)
 mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                       const __grid_constant__ CUtensorMap tmap_dx, const BwdParams p) {
@@ -92,6 +94,7 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     float* red = reinterpret_cast<float*>(smem + kOffRed);
     float* coef = reinterpret_cast<float*>(smem + kOffCoef);
     float* sk = reinterpret_cast<float*>(smem + kOffSk);
+    float* dlbuf = reinterpret_cast<float*>(smem + kOffDl);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint64_t* bar_done = bar_full + kStages;
 
@@ -141,154 +144,205 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             }
             bulk_wait<0>();
         }
-      } else if (warp == kWorkers + 2) {
-        // ===================================================== reducer: fixed-order sum of split-K partials
-        bar_arrive(kBarPartFree, kWorkerThreads + 32);              // `part` starts out free
+      } else if (warp >= kWorkers + 2) {
+        // ===================================================== 2 reducer warps: fixed-order (tree) sum of the
+        // 16 split-K partials, 4 tokens each
+        const int rw = warp - (kWorkers + 2);
+        bar_arrive(kBarPartFree, kWorkerThreads + 64);              // `part` starts out free
         for (int it = 0; it < n_local; ++it) {
             const int buf = it & 1;
-            bar_sync(kBarPart + buf, kWorkerThreads + 32);
-            for (int idx = lane; idx < kTok * kPartStride; idx += 32) {
-                const int tok = idx / kPartStride, col = idx - tok * kPartStride;
-                if (col >= kL + 1 && col < kPartG) continue;
-                float s0 = 0.f;
+            bar_sync(kBarPart + buf, kWorkerThreads + 64);
+            for (int idx = lane; idx < 4 * kPartStride; idx += 32) {
+                const int tok = 4 * rw + idx / kPartStride, col = idx % kPartStride;
+                float v[kWorkers];
 #pragma unroll
-                for (int ww = 0; ww < kWorkers; ++ww) s0 += part[(ww * kTok + tok) * kPartStride + col];
-                red[(buf * kTok + tok) * kRedStride + col] = s0;
+                for (int ww = 0; ww < kWorkers; ++ww) v[ww] = part[(ww * kTok + tok) * kPartStride + col];
+#pragma unroll
+                for (int st = 1; st < kWorkers; st <<= 1)
+#pragma unroll
+                    for (int ww = 0; ww < kWorkers; ww += 2 * st) v[ww] += v[ww + st];
+                red[(buf * kTok + tok) * kRedStride + col] = v[0];
             }
             __threadfence_block();
-            if (it + 1 < n_local) bar_arrive(kBarPartFree, kWorkerThreads + 32);   // workers may overwrite `part`
-            bar_arrive(kBarRed + buf, 64);                           // coefficient warp may read `red`
+            if (it + 1 < n_local) bar_arrive(kBarPartFree, kWorkerThreads + 64);   // workers may overwrite `part`
+            bar_arrive(kBarRed + buf, 96);                           // coefficient warp may read `red`
         }
       } else if (warp == kWorkers) {
-        // ===================================================== coefficient warp: lane (tk, i) owns row i of token tk
-        const int tk = lane >> 2, i = lane & 3, gbase = lane & ~3;
-        const float b_pre = __ldg(p.bias + i), b_post = __ldg(p.bias + kN + i);
-        const float4 b_res = __ldg(reinterpret_cast<const float4*>(p.bias + 2 * kN) + i);
+        // ===================================================== coefficient warp: one lane per token, the 4x4
+        // block in packed fp32x2 registers (rows i: R[i] = (p_i0,p_i1), S[i] = (p_i2,p_i3)); no shuffles.
+        // Lane k < 27 additionally owns component k of the dbias / dalpha sums.
+        const int tk = lane & 7;
         const float a_pre = __ldg(p.alpha + 0), a_post = __ldg(p.alpha + 1), a_res = __ldg(p.alpha + 2);
-        float acc_b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dbias: pre_i, post_i, res_i0..3
-        float acc_a[3] = {0.f, 0.f, 0.f};                  // dalpha partials of this lane
+        float my_acc = 0.f;
         float* skl = sk + tk * kMaxIters * kSkStride;
+        float* dls = dlbuf + tk * kDlStride;
         for (int it = 0; it < n_local; ++it) {
             const int buf = it & 1;
-            bar_sync(kBarRed + buf, 64);
-            const float* r = red + (buf * kTok + tk) * kRedStride;
-            const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(r[kL], 1.0f / kRow, p.eps_rms)));
-            // normalised projections z = inv_rms * raw of this lane's six logits
-            const float z_pre = r[i] * inv_rms, z_post = r[kN + i] * inv_rms;
-            const float z0 = r[2 * kN + 4 * i] * inv_rms, z1 = r[2 * kN + 4 * i + 1] * inv_rms;
-            const float z2 = r[2 * kN + 4 * i + 2] * inv_rms, z3 = r[2 * kN + 4 * i + 3] * inv_rms;
-            const float hpre = sigmoid_f32(fmaf(a_pre, z_pre, b_pre));
-            const float hpost = 2.0f * sigmoid_f32(fmaf(a_post, z_post, b_post));
-            float p0 = fmaf(a_res, z0, b_res.x), p1 = fmaf(a_res, z1, b_res.y);
-            float p2 = fmaf(a_res, z2, b_res.z), p3 = fmaf(a_res, z3, b_res.w);
-            // ---- forward Sinkhorn, remembering the normalisers (row: own; columns: all four)
-            {
-                const float mx = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
-                const float e0 = fast_exp(p0 - mx), e1 = fast_exp(p1 - mx), e2 = fast_exp(p2 - mx), e3 = fast_exp(p3 - mx);
-                const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
-                p0 = e0 * r4; p1 = e1 * r4; p2 = e2 * r4; p3 = e3 * r4;
-            }
-            const float s0 = p0, s1 = p1, s2 = p2, s3 = p3;     // softmax * 4 (start of the iteration)
-            for (int k = 0; k < p.sk_iters; ++k) {
-                const float dr = ((p0 + p1) + (p2 + p3)) + p.eps_sk;
-                const float rr = rcp_approx(dr);
-                p0 *= rr; p1 *= rr; p2 *= rr; p3 *= rr;
-                float c0 = p0 + __shfl_xor_sync(0xffffffffu, p0, 1), c1 = p1 + __shfl_xor_sync(0xffffffffu, p1, 1);
-                float c2 = p2 + __shfl_xor_sync(0xffffffffu, p2, 1), c3 = p3 + __shfl_xor_sync(0xffffffffu, p3, 1);
-                c0 += __shfl_xor_sync(0xffffffffu, c0, 2); c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
-                c2 += __shfl_xor_sync(0xffffffffu, c2, 2); c3 += __shfl_xor_sync(0xffffffffu, c3, 2);
-                c0 += p.eps_sk; c1 += p.eps_sk; c2 += p.eps_sk; c3 += p.eps_sk;
-                p0 *= rcp_approx(c0); p1 *= rcp_approx(c1); p2 *= rcp_approx(c2); p3 *= rcp_approx(c3);
-                skl[k * kSkStride + i] = dr;
-                if (i == 0) *reinterpret_cast<float4*>(skl + k * kSkStride + 4) = make_float4(c0, c1, c2, c3);
-            }
-            __syncwarp();
-            // ---- mixing matrix M = P + hpost (x) hpre, stored transposed for the dx pass
-            const float h0 = __shfl_sync(0xffffffffu, hpre, gbase + 0), h1 = __shfl_sync(0xffffffffu, hpre, gbase + 1);
-            const float h2 = __shfl_sync(0xffffffffu, hpre, gbase + 2), h3 = __shfl_sync(0xffffffffu, hpre, gbase + 3);
-            float* c = coef + (buf * kTok + tk) * kCoefStride;
-            c[0 * 4 + i] = fmaf(hpost, h0, p0);          // M^T[j][i] = M[i][j]
-            c[1 * 4 + i] = fmaf(hpost, h1, p1);
-            c[2 * 4 + i] = fmaf(hpost, h2, p2);
-            c[3 * 4 + i] = fmaf(hpost, h3, p3);
-            // ---- gradients of the coefficients from G = dy x^T (row i of G in this lane)
-            const float g0 = r[kPartG + 4 * i], g1 = r[kPartG + 4 * i + 1], g2 = r[kPartG + 4 * i + 2], g3 = r[kPartG + 4 * i + 3];
-            const float dhpost = fmaf(g3, h3, fmaf(g2, h2, fmaf(g1, h1, g0 * h0)));
-            // dhpre[j] = sum_i G[i][j] hpost[i]; lane i keeps j == i
-            const float t0 = group_sum4(g0 * hpost), t1 = group_sum4(g1 * hpost);
-            const float t2 = group_sum4(g2 * hpost), t3 = group_sum4(g3 * hpost);
-            const float dhpre = i == 0 ? t0 : i == 1 ? t1 : i == 2 ? t2 : t3;
-            const float dl_pre = dhpre * hpre * (1.0f - hpre);
-            const float dl_post = dhpost * hpost * (1.0f - 0.5f * hpost);
-            // ---- reverse sweep through the Sinkhorn iterations (dP = G)
-            float d0 = g0, d1 = g1, d2 = g2, d3 = g3;
-            for (int k = p.sk_iters - 1; k >= 0; --k) {
-                const float4 cd = *reinterpret_cast<const float4*>(skl + k * kSkStride + 4);
-                const float dr = skl[k * kSkStride + i];
-                // column step  y = x / c  (c per column):  dx = (dy - sum_rows(dy*y)) / c ;  x = y * c
-                const float q0 = group_sum4(d0 * p0), q1 = group_sum4(d1 * p1);
-                const float q2 = group_sum4(d2 * p2), q3 = group_sum4(d3 * p3);
-                d0 = (d0 - q0) * rcp_approx(cd.x); d1 = (d1 - q1) * rcp_approx(cd.y);
-                d2 = (d2 - q2) * rcp_approx(cd.z); d3 = (d3 - q3) * rcp_approx(cd.w);
-                p0 *= cd.x; p1 *= cd.y; p2 *= cd.z; p3 *= cd.w;
-                // row step  y = x / dr
-                const float qr = fmaf(d3, p3, fmaf(d2, p2, fmaf(d1, p1, d0 * p0)));
-                const float rr = rcp_approx(dr);
-                d0 = (d0 - qr) * rr; d1 = (d1 - qr) * rr; d2 = (d2 - qr) * rr; d3 = (d3 - qr) * rr;
-                p0 *= dr; p1 *= dr; p2 *= dr; p3 *= dr;
-            }
-            // softmax * 4 backward (row-local): dl = s * (d - sum(d*s)/4)
-            const float qs = 0.25f * fmaf(d3, s3, fmaf(d2, s2, fmaf(d1, s1, d0 * s0)));
-            const float dl0 = s0 * (d0 - qs), dl1 = s1 * (d1 - qs), dl2 = s2 * (d2 - qs), dl3 = s3 * (d3 - qs);
-            // ---- parameter-gradient partials, e = d raw, kappa (RMSNorm backward)
-            acc_b[0] += dl_pre; acc_b[1] += dl_post;
-            acc_b[2] += dl0; acc_b[3] += dl1; acc_b[4] += dl2; acc_b[5] += dl3;
-            acc_a[0] = fmaf(dl_pre, z_pre, acc_a[0]);
-            acc_a[1] = fmaf(dl_post, z_post, acc_a[1]);
-            acc_a[2] += fmaf(dl3, z3, fmaf(dl2, z2, fmaf(dl1, z1, dl0 * z0)));
-            const float e_pre = a_pre * dl_pre * inv_rms, e_post = a_post * dl_post * inv_rms;
-            const float e0 = a_res * dl0 * inv_rms, e1 = a_res * dl1 * inv_rms;
-            const float e2 = a_res * dl2 * inv_rms, e3 = a_res * dl3 * inv_rms;
-            // d inv_rms = sum_k dz_k raw_k = sum_k e_k raw_k / inv_rms ;  kappa = -d inv_rms * inv_rms^3 / N
-            float dsum = e_pre * r[i] + e_post * r[kN + i] +
-                         (e0 * r[2 * kN + 4 * i] + e1 * r[2 * kN + 4 * i + 1] + e2 * r[2 * kN + 4 * i + 2] + e3 * r[2 * kN + 4 * i + 3]);
-            dsum = group_sum4(dsum);
-            __nv_bfloat16* eb = reinterpret_cast<__nv_bfloat16*>(c + kCoefE);
-            eb[i] = __float2bfloat16_rn(e_pre);
-            eb[kN + i] = __float2bfloat16_rn(e_post);
-            *reinterpret_cast<uint2*>(eb + 2 * kN + 4 * i) = make_uint2(pack_bf16(e0, e1), pack_bf16(e2, e3));
-            if (i == 0) {
-                *reinterpret_cast<uint4*>(eb + kL) = make_uint4(0u, 0u, 0u, 0u);      // logits 24..31: zero pad
+            bar_sync(kBarRed + buf, 96);
+            if (lane < kTok) {
+                const float* r = red + (buf * kTok + tk) * kRedStride;
+                const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(r[kL], 1.0f / kRow, p.eps_rms)));
+                float hpre[kN], hpost[kN];
+#pragma unroll
+                for (int j = 0; j < kN; ++j) {
+                    hpre[j] = sigmoid_f32(fmaf(a_pre, r[j] * inv_rms, __ldg(p.bias + j)));
+                    hpost[j] = 2.0f * sigmoid_f32(fmaf(a_post, r[kN + j] * inv_rms, __ldg(p.bias + kN + j)));
+                }
+                u64 R[kN], S[kN];
+#pragma unroll
+                for (int i = 0; i < kN; ++i) {
+                    const float l0 = fmaf(a_res, r[2 * kN + 4 * i + 0] * inv_rms, __ldg(p.bias + 2 * kN + 4 * i + 0));
+                    const float l1 = fmaf(a_res, r[2 * kN + 4 * i + 1] * inv_rms, __ldg(p.bias + 2 * kN + 4 * i + 1));
+                    const float l2 = fmaf(a_res, r[2 * kN + 4 * i + 2] * inv_rms, __ldg(p.bias + 2 * kN + 4 * i + 2));
+                    const float l3 = fmaf(a_res, r[2 * kN + 4 * i + 3] * inv_rms, __ldg(p.bias + 2 * kN + 4 * i + 3));
+                    const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
+                    const float e0 = fast_exp(l0 - mx), e1 = fast_exp(l1 - mx), e2 = fast_exp(l2 - mx), e3 = fast_exp(l3 - mx);
+                    const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
+                    R[i] = pk2(e0 * r4, e1 * r4);
+                    S[i] = pk2(e2 * r4, e3 * r4);
+                }
+                // ---- forward Sinkhorn, normalisers kept in shared memory
+                const u64 eps2 = pk2(p.eps_sk, p.eps_sk);
+                for (int k = 0; k < p.sk_iters; ++k) {
+                    float dr[kN];
+#pragma unroll
+                    for (int i = 0; i < kN; ++i) {
+                        float a, b;
+                        upk2(add2(R[i], S[i]), a, b);
+                        dr[i] = (a + b) + p.eps_sk;
+                        const float rr = rcp_approx(dr[i]);
+                        const u64 rr2 = pk2(rr, rr);
+                        R[i] = mul2(R[i], rr2);
+                        S[i] = mul2(S[i], rr2);
+                    }
+                    const u64 c01 = add2(add2(add2(R[0], R[1]), add2(R[2], R[3])), eps2);
+                    const u64 c23 = add2(add2(add2(S[0], S[1]), add2(S[2], S[3])), eps2);
+                    float c0, c1, c2, c3;
+                    upk2(c01, c0, c1);
+                    upk2(c23, c2, c3);
+                    const u64 ci01 = pk2(rcp_approx(c0), rcp_approx(c1)), ci23 = pk2(rcp_approx(c2), rcp_approx(c3));
+#pragma unroll
+                    for (int i = 0; i < kN; ++i) { R[i] = mul2(R[i], ci01); S[i] = mul2(S[i], ci23); }
+                    *reinterpret_cast<float4*>(skl + k * kSkStride) = make_float4(dr[0], dr[1], dr[2], dr[3]);
+                    *reinterpret_cast<float4*>(skl + k * kSkStride + 4) = make_float4(c0, c1, c2, c3);
+                }
+                // ---- mixing matrix M = P + hpost (x) hpre, stored transposed (M^T[j][i]) for the dx pass
+                float* c = coef + (buf * kTok + tk) * kCoefStride;
+                {
+                    float pr[kN][kN];
+#pragma unroll
+                    for (int i = 0; i < kN; ++i) { upk2(R[i], pr[i][0], pr[i][1]); upk2(S[i], pr[i][2], pr[i][3]); }
+#pragma unroll
+                    for (int j = 0; j < kN; ++j)
+                        *reinterpret_cast<float4*>(c + 4 * j) =
+                            make_float4(fmaf(hpost[0], hpre[j], pr[0][j]), fmaf(hpost[1], hpre[j], pr[1][j]),
+                                        fmaf(hpost[2], hpre[j], pr[2][j]), fmaf(hpost[3], hpre[j], pr[3][j]));
+                }
+                // ---- gradients of the gates from G = dy x^T; D/E start as dP = G
+                u64 D[kN], E[kN];
+                float dl_pre[kN] = {0.f, 0.f, 0.f, 0.f}, dl_post[kN];
+#pragma unroll
+                for (int i = 0; i < kN; ++i) {
+                    const float g0 = r[kPartG + 4 * i], g1 = r[kPartG + 4 * i + 1], g2 = r[kPartG + 4 * i + 2], g3 = r[kPartG + 4 * i + 3];
+                    D[i] = pk2(g0, g1);
+                    E[i] = pk2(g2, g3);
+                    const float dhpost = fmaf(g3, hpre[3], fmaf(g2, hpre[2], fmaf(g1, hpre[1], g0 * hpre[0])));
+                    dl_post[i] = dhpost * hpost[i] * (1.0f - 0.5f * hpost[i]);
+                    dl_pre[0] = fmaf(g0, hpost[i], dl_pre[0]); dl_pre[1] = fmaf(g1, hpost[i], dl_pre[1]);
+                    dl_pre[2] = fmaf(g2, hpost[i], dl_pre[2]); dl_pre[3] = fmaf(g3, hpost[i], dl_pre[3]);
+                }
+#pragma unroll
+                for (int j = 0; j < kN; ++j) dl_pre[j] = dl_pre[j] * hpre[j] * (1.0f - hpre[j]);
+                // ---- exact reverse sweep through the iterations
+                for (int k = p.sk_iters - 1; k >= 0; --k) {
+                    const float4 dr = *reinterpret_cast<const float4*>(skl + k * kSkStride);
+                    const float4 cd = *reinterpret_cast<const float4*>(skl + k * kSkStride + 4);
+                    // column step y = x / c:  dx = (dy - sum_i dy*y) / c ;  x = y * c
+                    u64 q01 = mul2(D[0], R[0]), q23 = mul2(E[0], S[0]);
+#pragma unroll
+                    for (int i = 1; i < kN; ++i) { q01 = fma2(D[i], R[i], q01); q23 = fma2(E[i], S[i], q23); }
+                    const float r0 = rcp_approx(cd.x), r1 = rcp_approx(cd.y), r2 = rcp_approx(cd.z), r3 = rcp_approx(cd.w);
+                    const u64 ci01 = pk2(r0, r1), ci23 = pk2(r2, r3);
+                    const u64 nq01 = mul2(q01, pk2(-r0, -r1)), nq23 = mul2(q23, pk2(-r2, -r3));
+                    const u64 cc01 = pk2(cd.x, cd.y), cc23 = pk2(cd.z, cd.w);
+#pragma unroll
+                    for (int i = 0; i < kN; ++i) {
+                        D[i] = fma2(D[i], ci01, nq01); E[i] = fma2(E[i], ci23, nq23);
+                        R[i] = mul2(R[i], cc01);       S[i] = mul2(S[i], cc23);
+                    }
+                    // row step y = x / dr
+                    const float drv[kN] = {dr.x, dr.y, dr.z, dr.w};
+#pragma unroll
+                    for (int i = 0; i < kN; ++i) {
+                        float a, b;
+                        upk2(fma2(E[i], S[i], mul2(D[i], R[i])), a, b);
+                        const float rr = rcp_approx(drv[i]);
+                        const float nq = -(a + b) * rr;
+                        const u64 rr2 = pk2(rr, rr), nq2 = pk2(nq, nq), dd2 = pk2(drv[i], drv[i]);
+                        D[i] = fma2(D[i], rr2, nq2); E[i] = fma2(E[i], rr2, nq2);
+                        R[i] = mul2(R[i], dd2);      S[i] = mul2(S[i], dd2);
+                    }
+                }
+                // softmax * 4 backward (R,S are back at the softmax output): dl = s * (d - sum(d*s)/4)
+                float dl_res[kN][kN];
+#pragma unroll
+                for (int i = 0; i < kN; ++i) {
+                    float a, b;
+                    upk2(fma2(E[i], S[i], mul2(D[i], R[i])), a, b);
+                    const float nqs = -0.25f * (a + b);
+                    const u64 nq2 = pk2(nqs, nqs);
+                    upk2(mul2(R[i], add2(D[i], nq2)), dl_res[i][0], dl_res[i][1]);
+                    upk2(mul2(S[i], add2(E[i], nq2)), dl_res[i][2], dl_res[i][3]);
+                }
+                // ---- e = d raw, kappa (RMSNorm backward), per-token terms of dbias / dalpha
+                float dsum = 0.f, da_pre = 0.f, da_post = 0.f, da_res = 0.f;
+                float ev[kL];
+#pragma unroll
+                for (int j = 0; j < kN; ++j) {
+                    ev[j] = a_pre * dl_pre[j] * inv_rms;       dsum = fmaf(ev[j], r[j], dsum);
+                    da_pre = fmaf(dl_pre[j], r[j] * inv_rms, da_pre);
+                    ev[kN + j] = a_post * dl_post[j] * inv_rms; dsum = fmaf(ev[kN + j], r[kN + j], dsum);
+                    da_post = fmaf(dl_post[j], r[kN + j] * inv_rms, da_post);
+                }
+#pragma unroll
+                for (int i = 0; i < kN; ++i)
+#pragma unroll
+                    for (int j = 0; j < kN; ++j) {
+                        const int k = 2 * kN + 4 * i + j;
+                        ev[k] = a_res * dl_res[i][j] * inv_rms; dsum = fmaf(ev[k], r[k], dsum);
+                        da_res = fmaf(dl_res[i][j], r[k] * inv_rms, da_res);
+                    }
+                uint32_t* ew = reinterpret_cast<uint32_t*>(c + kCoefE);
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    *reinterpret_cast<uint4*>(ew + 4 * q) = make_uint4(pack_bf16(ev[8 * q], ev[8 * q + 1]), pack_bf16(ev[8 * q + 2], ev[8 * q + 3]),
+                                                                       pack_bf16(ev[8 * q + 4], ev[8 * q + 5]), pack_bf16(ev[8 * q + 6], ev[8 * q + 7]));
+                *reinterpret_cast<uint4*>(ew + 12) = make_uint4(0u, 0u, 0u, 0u);          // logits 24..31: zero pad
                 c[kCoefKappa] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
+                const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + tk;
+                if (tok < p.T) {
+                    float4* o = reinterpret_cast<float4*>(p.e_out + tok * kL);
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) o[q] = make_float4(ev[4 * q], ev[4 * q + 1], ev[4 * q + 2], ev[4 * q + 3]);
+                }
+                // padded rows have dy = 0, hence G = 0 and every dl = 0: they add nothing below
+#pragma unroll
+                for (int j = 0; j < kN; ++j) { dls[j] = dl_pre[j]; dls[kN + j] = dl_post[j]; }
+#pragma unroll
+                for (int i = 0; i < kN; ++i)
+                    *reinterpret_cast<float4*>(dls + 2 * kN + 4 * i) = make_float4(dl_res[i][0], dl_res[i][1], dl_res[i][2], dl_res[i][3]);
+                dls[kL] = da_pre; dls[kL + 1] = da_post; dls[kL + 2] = da_res;
             }
-            const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + tk;
-            if (tok < p.T) {
-                float* o = p.e_out + tok * kL;
-                o[i] = e_pre;
-                o[kN + i] = e_post;
-                *reinterpret_cast<float4*>(o + 2 * kN + 4 * i) = make_float4(e0, e1, e2, e3);
-            }   // padded rows have dy = 0, hence G = 0 and every dl = 0: they add nothing to the sums above
             __threadfence_block();
             bar_arrive(kBarCoef + buf, kWorkerThreads + 32);
+            __syncwarp();
+            if (lane < kAccum) {
+#pragma unroll
+                for (int q = 0; q < kTok; ++q) my_acc += dlbuf[q * kDlStride + lane];      // fixed order over tokens
+            }
+            __syncwarp();
         }
-        // fold the 8 token groups of the warp (lanes with equal i), fixed order
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) acc_b[k] += __shfl_xor_sync(0xffffffffu, acc_b[k], o);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], o);
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) acc_a[k] = group_sum4(acc_a[k]);
-        if (lane < 4) {
-            float* o = p.cta_accum + (size_t)blockIdx.x * kAccum;
-            o[i] = acc_b[0];
-            o[kN + i] = acc_b[1];
-            o[2 * kN + 4 * i + 0] = acc_b[2]; o[2 * kN + 4 * i + 1] = acc_b[3];
-            o[2 * kN + 4 * i + 2] = acc_b[4]; o[2 * kN + 4 * i + 3] = acc_b[5];
-            if (i == 0) { o[kL] = acc_a[0]; o[kL + 1] = acc_a[1]; o[kL + 2] = acc_a[2]; }
-        }
+        if (lane < kAccum) p.cta_accum[(size_t)blockIdx.x * kAccum + lane] = my_acc;
       }
     } else {
         // ===================================================== worker warps
@@ -410,7 +464,7 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     mma_bf16_16816(gacc[m][1], a0, a1, a2, a3, bx[2 * m + 1][0], bx[2 * m + 1][1]);
                 }
             }
-            bar_sync(kBarPartFree, kWorkerThreads + 32);      // reducer finished reading the previous partials
+            bar_sync(kBarPartFree, kWorkerThreads + 64);      // reducers finished reading the previous partials
             {
                 float* pw = part + (size_t)w * kTok * kPartStride;
                 // raw^T fragments: (logit g | g+8 | 16+g, tokens 2t, 2t+1)
@@ -432,7 +486,7 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 }
             }
             __threadfence_block();
-            bar_arrive(kBarPart + (it & 1), kWorkerThreads + 32);
+            bar_arrive(kBarPart + (it & 1), kWorkerThreads + 64);
             if (it > 0) finish_tile(it - 1);
         }
         if (n_local > 0) finish_tile(n_local - 1);
@@ -632,19 +686,25 @@ extern "C" int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* ph
         p.num_tiles = (int)((T + kTok - 1) / kTok);
         p.sk_iters = sk_iters; p.eps_rms = eps_rms; p.eps_sk = eps_sk;
         grid1 = p.num_tiles < sms ? p.num_tiles : sms;
+        timer_begin(1, stream);
         mhc_stream_bwd_kernel<<<grid1, kThreads, kSmemBytes, stream>>>(tx, tdy, tdx, p);
+        timer_end(1, stream);
         count_launch();
         int rc2 = launch_status();
         if (rc2) return rc2;
         const int tiles2 = (int)((T + kDwTok - 1) / kDwTok);
         grid2 = tiles2 < sms ? tiles2 : sms;
+        timer_begin(2, stream);
         mhc_stream_dw_kernel<<<grid2, kDwThreads, kDwSmemBytes, stream>>>(txt, ws.e, ws.dw_part, T, tiles2);
+        timer_end(2, stream);
         count_launch();
         rc2 = launch_status();
         if (rc2) return rc2;
     }
+    timer_begin(3, stream);
     mhc_stream_bwd_finalize_kernel<<<kRow / 8, 256, 0, stream>>>(ws.dw_part, grid2, ws.cta_accum, grid1, phi, scale, dphi,
                                                                  dscale, dbias, dalpha);
+    timer_end(3, stream);
     count_launch();
     return launch_status();
 }

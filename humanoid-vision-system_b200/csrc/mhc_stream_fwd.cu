@@ -390,7 +390,9 @@ extern "C" int hvs_mhc_stream_fwd(const void* x, const float* phi, const float* 
         attr_set = true;
     }
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    timer_begin(0, (cudaStream_t)stream);
     mhc_stream_fwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tx, ty, p);
+    timer_end(0, (cudaStream_t)stream);
     count_launch();
     return launch_status();
 }

@@ -1,0 +1,171 @@
+"""Detection decode / NMS modules with the reference's signatures.
+
+* ``YOLODecoder``        src/models/yolo_head.py:206-294   (forward(predictions, anchors, grid_size) -> dict)
+* ``YOLODetectionHead``  src/models/yolo_head.py:468-755   (forward / post_process / non_max_suppression /
+                         compute_iou; same sub-module names and state_dict keys)
+* ``NMSFilter``          src/inference/postprocessing.py:498-607 (apply(boxes, scores, class_ids))
+
+Repairs baked in: anchors are kept per scale as [S,A,1,1,4] and paired
+small<->finest grid (D2/D3), the decoder indexes the last dim so boxes are [B,A,H,W,4] (D4), the
+class-aware NMS compares 1-D IoUs (D9).  Decode and NMS run in libhvs_b200.so.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .mhc import ManifoldHyperConnection
+
+DEFAULT_ANCHORS = [[(10, 13), (16, 30), (33, 23)], [(30, 61), (62, 45), (59, 119)], [(116, 90), (156, 198), (373, 326)]]
+
+
+class YOLOAnchorGenerator(nn.Module):
+    """yolo_head.py:11-90; buffer ``anchors`` [S,A,1,1,4] with (w,h)/416 in slots 2:4."""
+
+    def __init__(self, anchor_sizes=None, grid_sizes=(13, 26, 52)):
+        super().__init__()
+        self.anchor_sizes = anchor_sizes if anchor_sizes is not None else DEFAULT_ANCHORS
+        self.grid_sizes = list(grid_sizes)
+        self.num_scales = len(self.anchor_sizes)
+        self.num_anchors = len(self.anchor_sizes[0])
+        wh = torch.tensor(self.anchor_sizes, dtype=torch.float32) / 416.0
+        anchors = torch.zeros(self.num_scales, self.num_anchors, 1, 1, 4)
+        anchors[..., 0, 0, 2:4] = wh
+        self.register_buffer("anchors", anchors)
+
+    def forward(self, scale_idx: int) -> torch.Tensor:
+        return self.anchors[scale_idx]
+
+    def get_num_anchors(self) -> int:
+        return self.num_anchors
+
+
+class YOLODecoder(nn.Module):
+    """YOLODecoder(image_size=416).forward(predictions [B,A,H,W,5+C], anchors [A,*,*,4], grid_size)."""
+
+    def __init__(self, image_size: int = 416):
+        super().__init__()
+        self.image_size = image_size
+
+    def forward(self, predictions: torch.Tensor, anchors: torch.Tensor, grid_size: Tuple[int, int] = None,
+                want_scores: bool = True) -> Dict[str, torch.Tensor]:
+        a = predictions.shape[1]
+        anchor_wh = anchors.reshape(a, -1, 4)[:, 0, 2:4]
+        out = ops.yolo_decode(predictions, anchor_wh, want_scores=want_scores, want_objectness=True)
+        out["raw_predictions"] = predictions
+        return out
+
+
+class YOLOPredictionHead(nn.Module):
+    """yolo_head.py:93-203: conv-BN-LeakyReLU x2 -> mHC over [B*H*W, C] -> 1x1 conv -> [B,A,H,W,5+C] view."""
+
+    def __init__(self, in_channels: int, num_classes: int = 80, num_anchors: int = 3, use_mhc: bool = True):
+        super().__init__()
+        self.in_channels, self.num_classes, self.num_anchors = in_channels, num_classes, num_anchors
+        self.output_dim = num_anchors * (5 + num_classes)
+        self.conv_layers = nn.Sequential(
+            nn.Conv2d(in_channels, in_channels * 2, 3, padding=1), nn.BatchNorm2d(in_channels * 2), nn.LeakyReLU(0.1),
+            nn.Conv2d(in_channels * 2, in_channels, 3, padding=1), nn.BatchNorm2d(in_channels), nn.LeakyReLU(0.1))
+        self.mhc_enhance = ManifoldHyperConnection(input_dim=in_channels, expansion_rate=2) if use_mhc else nn.Identity()
+        self.pred_conv = nn.Conv2d(in_channels, self.output_dim, kernel_size=1)
+        for m in self.conv_layers:
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="leaky_relu")
+                nn.init.zeros_(m.bias)
+        nn.init.normal_(self.pred_conv.weight, std=0.01)
+        nn.init.zeros_(self.pred_conv.bias)
+        with torch.no_grad():                              # :165-168
+            bias = self.pred_conv.bias.view(num_anchors, -1)
+            bias[:, 4] = -4.0
+            bias[:, 5:] = -math.log((1 - 0.01) / 0.01) / num_classes
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.conv_layers(x)
+        b, c, h, w = x.shape
+        if not isinstance(self.mhc_enhance, nn.Identity):
+            x = self.mhc_enhance(x.permute(0, 2, 3, 1).reshape(-1, c)).reshape(b, h, w, c).permute(0, 3, 1, 2)
+        pred = self.pred_conv(x)
+        # [B, A*(5+C), H, W] -> [B,A,H,W,5+C] as a VIEW: the decode kernel reads it through its strides
+        return pred.view(b, self.num_anchors, 5 + self.num_classes, h, w).permute(0, 1, 3, 4, 2)
+
+
+class YOLODetectionHead(nn.Module):
+    """YOLODetectionHead(in_channels_list, num_classes=80, anchors=None, use_mhc=True)  (yolo_head.py:468-755)."""
+
+    def __init__(self, in_channels_list: List[int], num_classes: int = 80, anchors=None, use_mhc: bool = True):
+        super().__init__()
+        self.in_channels_list = in_channels_list
+        self.num_classes = num_classes
+        self.num_scales = len(in_channels_list)
+        self.anchor_generator = YOLOAnchorGenerator(anchors)
+        self.num_anchors = self.anchor_generator.get_num_anchors()
+        self.pred_heads = nn.ModuleList([YOLOPredictionHead(c, num_classes, self.num_anchors, use_mhc) for c in in_channels_list])
+        self.decoder = YOLODecoder(image_size=416)
+
+    def forward(self, features: Dict[str, torch.Tensor], targets=None, compute_loss: bool = False,
+                want_scores: bool = True) -> Dict[str, Any]:
+        predictions, decoded = {}, {}
+        for i in range(self.num_scales):
+            key = ["scale_small", "scale_medium", "scale_large"][i]
+            if key not in features:
+                continue
+            pred = self.pred_heads[i](features[key])
+            predictions[f"scale_{i}"] = pred
+            decoded[f"scale_{i}"] = self.decoder(pred, self.anchor_generator(i), pred.shape[2:4], want_scores=want_scores)
+        return {"predictions": predictions, "decoded": decoded}
+
+    def post_process(self, decoded_outputs: Dict[str, Dict[str, torch.Tensor]], confidence_threshold: float = 0.5,
+                     iou_threshold: float = 0.5, max_detections: int = 100) -> List[Dict[str, torch.Tensor]]:
+        """yolo_head.py:571-676: per-scale thresholded NMS, concatenation, second NMS -- one batched call."""
+        scales = list(decoded_outputs.values())
+        db, ds, dl, dc = ops.post_process(scales, confidence_threshold, iou_threshold, max_detections)
+        counts = dc.cpu().tolist()                        # the only host sync: the result sizes
+        return [{"boxes": db[b, :k], "scores": ds[b, :k], "labels": dl[b, :k]} for b, k in enumerate(counts)]
+
+    def non_max_suppression(self, boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float = 0.5,
+                            max_detections: int = 100) -> torch.Tensor:
+        """yolo_head.py:678-731; returns int64 indices into the input, descending score."""
+        if boxes.numel() == 0:
+            return torch.tensor([], dtype=torch.long, device=boxes.device)
+        keep_idx, _, cnt = ops.nms(boxes, scores, None, iou_threshold, max_detections)
+        return keep_idx[0, :int(cnt[0])]
+
+    def compute_iou(self, box1: torch.Tensor, box2: torch.Tensor) -> torch.Tensor:
+        """yolo_head.py:733-755 (elementwise torch ops; not on the hot path)."""
+        ix1, iy1 = torch.max(box1[..., 0], box2[..., 0]), torch.max(box1[..., 1], box2[..., 1])
+        ix2, iy2 = torch.min(box1[..., 2], box2[..., 2]), torch.min(box1[..., 3], box2[..., 3])
+        inter = torch.clamp(ix2 - ix1, min=0) * torch.clamp(iy2 - iy1, min=0)
+        a1 = (box1[..., 2] - box1[..., 0]) * (box1[..., 3] - box1[..., 1])
+        a2 = (box2[..., 2] - box2[..., 0]) * (box2[..., 3] - box2[..., 1])
+        return inter / (a1 + a2 - inter + 1e-6)
+
+
+@dataclass
+class PostprocessingConfig:
+    """The NMS fields of src/inference/postprocessing.py:31-67."""
+    nms_iou_threshold: float = 0.45
+    nms_score_threshold: float = 0.25
+    nms_max_detections: int = 100
+    nms_method: str = "standard"
+
+
+class NMSFilter:
+    """NMSFilter(config).apply(boxes [N,4] cx,cy,w,h, scores [N], class_ids [N]) -> keep indices
+    (postprocessing.py:498-607, "standard" method)."""
+
+    def __init__(self, config: Optional[PostprocessingConfig] = None):
+        self.config = config or PostprocessingConfig()
+        if self.config.nms_method != "standard":
+            raise ValueError(f"Unknown / unsupported NMS method: {self.config.nms_method}")
+
+    def apply(self, boxes: torch.Tensor, scores: torch.Tensor, class_ids: torch.Tensor) -> torch.Tensor:
+        if len(boxes) == 0:
+            return torch.empty(0, dtype=torch.long, device=boxes.device)
+        keep_idx, _, cnt = ops.nms(boxes, scores, class_ids, self.config.nms_iou_threshold,
+                                   self.config.nms_max_detections, class_aware=True, boxes_xyxy=False)
+        return keep_idx[0, :int(cnt[0])]

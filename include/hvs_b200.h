@@ -79,6 +79,14 @@ int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* phi, const fl
                        float eps_rms, float eps_sk, uint32_t flags, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Optional per-kernel timing of the stream-mHC launches (used by bench.py for the roofline line).
+ * When enabled, each launch is bracketed by CUDA events on the launching stream;
+ * hvs_mhc_stream_kernel_ms synchronises those events and returns the durations in ms of the LAST
+ * call of each entry point: out[0] forward kernel, out[1] backward per-token kernel,
+ * out[2] backward x^T E reduction kernel, out[3] backward finalize kernel (negative = not run). */
+int hvs_mhc_stream_profile(int enable);
+int hvs_mhc_stream_kernel_ms(float* out4_host);
+
 /* ------------------------------------------------------------------------------------
  * Sinkhorn-Knopp projection, SinkhornKnoppProjection.forward (manifold_layers.py:32-93):
  * out = SK(in) for `batch` matrices of n x m fp32, row-major, contiguous.
