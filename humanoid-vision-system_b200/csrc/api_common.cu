@@ -1,5 +1,7 @@
 // ABI bookkeeping + tensor-map encode through the driver entry point (no -lcuda link).
 #include <cudaTypedefs.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -29,6 +31,9 @@ static EncodeTiledFn encode_fn() {
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return HVS_ERR_DRIVER;
+    // The encode is a driver-API call and needs the primary context current on THIS thread; a thread that
+    // has only been handed a device ordinal (e.g. PyTorch's autograd workers) has not bound it yet.
+    cudaFree(nullptr);
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {cols * 2};
     cuuint32_t box[2] = {64, box_rows};
@@ -36,6 +41,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS && getenv("HVS_DEBUG"))
+        fprintf(stderr, "[hvs_b200] cuTensorMapEncodeTiled -> CUresult %d (ptr %p rows %llu cols %llu box_rows %u)\n", (int)r,
+                gptr, (unsigned long long)rows, (unsigned long long)cols, box_rows);
     return r == CUDA_SUCCESS ? HVS_OK : HVS_ERR_DRIVER;
 }
 

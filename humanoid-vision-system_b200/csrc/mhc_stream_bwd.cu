@@ -1,14 +1,17 @@
 // K1 backward (F = identity), coefficients recomputed from x -- nothing is saved by the forward.
 //
-// Kernel B1 (per-token, HBM-bound: reads x and dy, writes dx; 8-token tiles, 3-stage TMA ring):
-//   P1 workers (16 warps, split-K)  raw = x.W on the warp MMA path (W = bf16(scale*phi) in registers),
-//                                   sum x^2 and the per-token 4x4  G = dy x^T  as MMAs on the smem tiles
-//   2 reducer warps                 fixed-order sum of the 16 split-K partials
-//   coefficient warp (lane/token)   forward gates + Sinkhorn in packed fp32x2 registers keeping the normalisers,
-//                                   then the exact reverse sweep through all iterations -> dlogits, e = d raw, kappa
-//   P3 workers                      dx = M^T dy  +  e W^T (MMA, W^T by movmatrix from the same registers)
-//                                        + kappa x, one rounding to bf16, in place over dy, TMA store
-//   The coefficient warp also emits E[T,24] (fp32) and per-CTA partial sums of dbias / dalpha.
+// Kernel B1 (per token, HBM-bound: x and dy in, dx out).  The per-token Sinkhorn forward + reverse sweep is
+// a ~14k-cycle dependent chain, far longer than a tile can stay resident in shared memory, so every 8-token
+// tile is visited TWICE by the same CTA, the second time re-loaded by TMA while it is still in the 126 MB L2:
+//   pass 1 (workers, 16 warps, split-K)  raw = x.W on the warp MMA path (W = bf16(scale*phi) in registers),
+//                                        sum x^2 and the per-token 4x4  G = dy x^T  as MMAs on the smem tiles;
+//                                        the stage is released immediately
+//   reducer warp                         fixed-order sum of the 16 split-K partials into a per-token record
+//   2 coefficient warps (lane = token,   forward gates + Sinkhorn in packed fp32x2 registers, then the exact
+//     24 tokens per pass, alternating)   reverse sweep through all iterations -> dlogits, e = d raw, kappa, M^T
+//   pass 2 (workers, two superblocks     dx = M^T dy  +  e W^T (MMA; W^T by movmatrix from the same registers)
+//     of 3 tiles later)                       + kappa x, one rounding to bf16, in place over dy, TMA store
+//   The coefficient warps also emit E[T,24] (fp32) and per-CTA partial sums of dbias / dalpha.
 // Kernel B2: dW = x^T E on the warp MMA path (x re-read once; E split into two bf16 terms), per-CTA
 //   partials; finalize: dphi = scale * dW, dscale = sum_k phi * dW, dbias, dalpha (fixed order).
 //
@@ -23,35 +26,32 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------ B1
 constexpr int kTok = 8;                               // tokens per tile
+constexpr int kSb = 3;                                // tiles per superblock = one coefficient pass (24 tokens)
+constexpr int kLag = 2;                               // superblocks between pass 1 and pass 2 of a tile
+constexpr int kRedSlots = 3;                          // record buffers: filling | in the coefficient warp | pass 2
 constexpr int kWorkers = 16;
 constexpr int kWorkerThreads = kWorkers * 32;
-constexpr int kThreads = (kWorkers + 4) * 32;         // + coefficient, producer and 2 reducer warps
+constexpr int kThreads = (kWorkers + 4) * 32;         // + coefficient warp A, producer, coefficient warp B, reducer
 constexpr int kWorkerRegs = 104, kRoleRegs = 64;
 constexpr int kStages = 3;
 constexpr int kHalfBytes = kTok * kRowBytes;          // 32 KB: x tile or dy tile
 constexpr int kStageBytes = 2 * kHalfBytes;           // x | dy
 constexpr int kBoxBytes = 32 * 128;                   // TMA box: 32 rows (8 tokens x 4 streams) x 64 bf16
-constexpr int kPartStride = 42;                       // raw[24] ss[1] pad[1] G[16]
-constexpr int kPartG = 26;
-constexpr int kRedStride = 43;                        // odd stride: conflict-free per-lane walks
-constexpr int kCoefStride = 36;                       // M^T[16] | e bf16[24 -> 16 words incl. pad] | kappa | pad
-constexpr int kCoefE = 16, kCoefKappa = 32;
-constexpr int kSkStride = 8;                          // per (iteration): row d[4], col d[4]
+// per-token record (fp32 words): pass 1 writes raw[0..23] ss[24] G[28..43]; the coefficient warp overwrites it in
+// place with e as bf16 pairs [0..11], kappa [12], M^T [28..43] for pass 2
+constexpr int kRec = 44, kRecSS = 24, kRecG = 28, kRecKappa = 12;
 constexpr int kMaxIters = 32;
 
 constexpr int kOffPart = kStages * kStageBytes;
-constexpr int kOffRed = kOffPart + kWorkers * kTok * kPartStride * 4;
-constexpr int kOffCoef = kOffRed + 2 * kTok * kRedStride * 4;
-constexpr int kOffSk = kOffCoef + 2 * kTok * kCoefStride * 4;
-constexpr int kDlStride = 28;                         // per token: dl[24], dalpha terms[3]
-constexpr int kOffDl = kOffSk + kTok * kMaxIters * kSkStride * 4;
-constexpr int kOffBar = kOffDl + kTok * kDlStride * 4;
+constexpr int kOffRed = kOffPart + kWorkers * kTok * kRec * 4;
+constexpr int kOffBar = kOffRed + kRedSlots * kSb * kTok * kRec * 4;
 constexpr int kSmemBytes = kOffBar + 2 * kStages * 8;
 static_assert(kOffBar % 8 == 0, "mbarrier alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 constexpr int kBarPartFree = 1, kBarPart = 2 /*,3*/, kBarRed = 4 /*,5*/, kBarCoef = 6 /*,7*/;
-constexpr int kAccum = kL + 3;                        // per-CTA partials: dbias[24], dalpha[3]
+constexpr int kAccum = kL + 3;                        // dbias[24], dalpha[3]
+constexpr int kSkWords = kMaxIters * 8 * 32;          // normaliser scratch per coefficient warp: [iter][8][lane]
 
 struct BwdParams {
     const float* phi;
@@ -59,7 +59,8 @@ struct BwdParams {
     const float* alpha;
     const float* scale;
     float* e_out;          // [T,24] fp32
-    float* cta_accum;      // [grid, 27]
+    float* cta_accum;      // [grid, 2, 27]
+    float* sk_scratch;     // [grid, 2, kSkWords]  (L2-resident: rewritten every pass)
     int64_t T;
     int num_tiles;
     int sk_iters;
@@ -85,6 +86,31 @@ __device__ __forceinline__ void upk2(u64 v, float& a, float& b) { asm("mov.b64 {
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// The static work order of one CTA.  Step s runs pass 1 of superblock s interleaved with pass 2 of superblock
+// s - kLag, tile by tile; every role walks the same sequence, item q lives in stage q % kStages.
+struct ItemIter {
+    int s, i, ph, n_local, nsb;
+    __device__ void init(int n) { n_local = n; nsb = (n + kSb - 1) / kSb; s = 0; i = 0; ph = -1; next(); }
+    __device__ bool valid() const { return s < nsb + kLag; }
+    __device__ int sb() const { return ph == 0 ? s : s - kLag; }
+    __device__ int tile() const { return sb() * kSb + i; }
+    __device__ void next() {
+        for (;;) {
+            if (++ph == 2) { ph = 0; if (++i == kSb) { i = 0; ++s; } }
+            if (s >= nsb + kLag) return;
+            const int b = ph == 0 ? s : s - kLag;
+            if (b < 0 || b >= nsb || b * kSb + i >= n_local) continue;
+            return;
+        }
+    }
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
 mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                       const __grid_constant__ CUtensorMap tmap_dx, const BwdParams p) {
@@ -92,15 +118,13 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (smem_u32(smem) & 1023u) __trap();
     float* part = reinterpret_cast<float*>(smem + kOffPart);
     float* red = reinterpret_cast<float*>(smem + kOffRed);
-    float* coef = reinterpret_cast<float*>(smem + kOffCoef);
-    float* sk = reinterpret_cast<float*>(smem + kOffSk);
-    float* dlbuf = reinterpret_cast<float*>(smem + kOffDl);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint64_t* bar_done = bar_full + kStages;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nsb = (n_local + kSb - 1) / kSb;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -119,9 +143,9 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             tma_prefetch_desc(&tmap_x);
             tma_prefetch_desc(&tmap_dy);
             tma_prefetch_desc(&tmap_dx);
-            auto load_tile = [&](int it) {
-                const int s = it % kStages;
-                const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * (kTok * kN);
+            auto load_item = [&](const ItemIter& w, int q) {
+                const int s = q % kStages;
+                const int row0 = ((int)blockIdx.x + w.tile() * (int)gridDim.x) * (kTok * kN);
                 uint8_t* st = smem + s * kStageBytes;
                 mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
 #pragma unroll
@@ -130,58 +154,69 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     tma_load_2d(st + kHalfBytes + cb * kBoxBytes, &tmap_dy, &bar_full[s], cb * 64, row0);
                 }
             };
-            for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
-            for (int it = 0; it < n_local; ++it) {
-                const int s = it % kStages;
-                mbar_wait(&bar_done[s], (it / kStages) & 1);
-                const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * (kTok * kN);
+            ItemIter ld, cur;
+            ld.init(n_local);
+            cur.init(n_local);
+            int q_ld = 0;
+            for (; q_ld < kStages && ld.valid(); ++q_ld, ld.next()) load_item(ld, q_ld);
+            for (int q = 0; cur.valid(); ++q, cur.next()) {
+                const int s = q % kStages;
+                mbar_wait(&bar_done[s], (q / kStages) & 1);
+                if (cur.ph == 1) {
+                    const int row0 = ((int)blockIdx.x + cur.tile() * (int)gridDim.x) * (kTok * kN);
 #pragma unroll
-                for (int cb = 0; cb < kC / 64; ++cb)
-                    tma_store_2d(&tmap_dx, smem + s * kStageBytes + kHalfBytes + cb * kBoxBytes, cb * 64, row0);
-                bulk_commit();
-                bulk_wait_read<0>();
-                if (it + kStages < n_local) load_tile(it + kStages);
+                    for (int cb = 0; cb < kC / 64; ++cb)
+                        tma_store_2d(&tmap_dx, smem + s * kStageBytes + kHalfBytes + cb * kBoxBytes, cb * 64, row0);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                }
+                if (ld.valid()) { load_item(ld, q_ld); ++q_ld; ld.next(); }
             }
             bulk_wait<0>();
         }
-      } else if (warp >= kWorkers + 2) {
-        // ===================================================== 2 reducer warps: fixed-order (tree) sum of the
-        // 16 split-K partials, 4 tokens each
-        const int rw = warp - (kWorkers + 2);
-        bar_arrive(kBarPartFree, kWorkerThreads + 64);              // `part` starts out free
+      } else if (warp == kWorkers + 3) {
+        // ===================================================== reducer: fixed-order (tree) sum of the 16 split-K
+        // partials of each pass-1 tile into the superblock's record buffer
+        if (n_local > 0) bar_arrive(kBarPartFree, kWorkerThreads + 32);      // `part` starts out free
         for (int it = 0; it < n_local; ++it) {
-            const int buf = it & 1;
-            bar_sync(kBarPart + buf, kWorkerThreads + 64);
-            for (int idx = lane; idx < 4 * kPartStride; idx += 32) {
-                const int tok = 4 * rw + idx / kPartStride, col = idx % kPartStride;
+            const int sb = it / kSb, ti = it - sb * kSb;
+            bar_sync(kBarPart + (it & 1), kWorkerThreads + 32);
+            float* dst = red + ((sb % kRedSlots) * kSb + ti) * kTok * kRec;
+            for (int idx = lane; idx < kTok * kRec; idx += 32) {
+                const int col = idx % kRec;
+                if (col > kRecSS && col < kRecG) continue;
                 float v[kWorkers];
 #pragma unroll
-                for (int ww = 0; ww < kWorkers; ++ww) v[ww] = part[(ww * kTok + tok) * kPartStride + col];
+                for (int ww = 0; ww < kWorkers; ++ww) v[ww] = part[ww * kTok * kRec + idx];
 #pragma unroll
                 for (int st = 1; st < kWorkers; st <<= 1)
 #pragma unroll
                     for (int ww = 0; ww < kWorkers; ww += 2 * st) v[ww] += v[ww + st];
-                red[(buf * kTok + tok) * kRedStride + col] = v[0];
+                dst[idx] = v[0];
             }
             __threadfence_block();
-            if (it + 1 < n_local) bar_arrive(kBarPartFree, kWorkerThreads + 64);   // workers may overwrite `part`
-            bar_arrive(kBarRed + buf, 96);                           // coefficient warp may read `red`
+            if (it + 1 < n_local) bar_arrive(kBarPartFree, kWorkerThreads + 32);
+            if (ti == kSb - 1 || it == n_local - 1) bar_arrive(kBarRed + (sb & 1), 64);
         }
-      } else if (warp == kWorkers) {
-        // ===================================================== coefficient warp: one lane per token, the 4x4
-        // block in packed fp32x2 registers (rows i: R[i] = (p_i0,p_i1), S[i] = (p_i2,p_i3)); no shuffles.
-        // Lane k < 27 additionally owns component k of the dbias / dalpha sums.
-        const int tk = lane & 7;
+      } else {
+        // ===================================================== coefficient warps A (warp 16) and B (warp 18):
+        // superblocks alternate between them; one lane per token, the 4x4 block in packed fp32x2 registers
+        // (row i: R[i] = (p_i0,p_i1), S[i] = (p_i2,p_i3)), no shuffles inside the sweeps.  Lane k < 27 also
+        // owns component k of the dbias / dalpha sums.
+        const int cw = (warp - kWorkers) >> 1;
         const float a_pre = __ldg(p.alpha + 0), a_post = __ldg(p.alpha + 1), a_res = __ldg(p.alpha + 2);
         float my_acc = 0.f;
-        float* skl = sk + tk * kMaxIters * kSkStride;
-        float* dls = dlbuf + tk * kDlStride;
-        for (int it = 0; it < n_local; ++it) {
-            const int buf = it & 1;
-            bar_sync(kBarRed + buf, 96);
-            if (lane < kTok) {
-                const float* r = red + (buf * kTok + tk) * kRedStride;
-                const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(r[kL], 1.0f / kRow, p.eps_rms)));
+        float* skl = p.sk_scratch + ((size_t)blockIdx.x * 2 + cw) * kSkWords + lane;
+        for (int sb = cw; sb < nsb; sb += 2) {
+            bar_sync(kBarRed + cw, 64);
+            const int tiles = min(kSb, n_local - sb * kSb);
+            const bool act = lane < tiles * kTok;
+            float dlv[kAccum];
+#pragma unroll
+            for (int k = 0; k < kAccum; ++k) dlv[k] = 0.f;
+            if (act) {
+                float* r = red + ((sb % kRedSlots) * kSb * kTok + lane) * kRec;
+                const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(r[kRecSS], 1.0f / kRow, p.eps_rms)));
                 float hpre[kN], hpost[kN];
 #pragma unroll
                 for (int j = 0; j < kN; ++j) {
@@ -201,16 +236,18 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     R[i] = pk2(e0 * r4, e1 * r4);
                     S[i] = pk2(e2 * r4, e3 * r4);
                 }
-                // ---- forward Sinkhorn, normalisers kept in shared memory
-                const u64 eps2 = pk2(p.eps_sk, p.eps_sk);
+                // ---- forward Sinkhorn; the normalisers go to the (L2-resident) scratch
+                const float eps = p.eps_sk;
+                const u64 eps2 = pk2(eps, eps);
                 for (int k = 0; k < p.sk_iters; ++k) {
-                    float dr[kN];
+                    float* sk = skl + k * 256;
 #pragma unroll
                     for (int i = 0; i < kN; ++i) {
                         float a, b;
                         upk2(add2(R[i], S[i]), a, b);
-                        dr[i] = (a + b) + p.eps_sk;
-                        const float rr = rcp_approx(dr[i]);
+                        const float dr = (a + b) + eps;
+                        __stcg(sk + i * 32, dr);
+                        const float rr = rcp_approx(dr);
                         const u64 rr2 = pk2(rr, rr);
                         R[i] = mul2(R[i], rr2);
                         S[i] = mul2(S[i], rr2);
@@ -220,129 +257,126 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     float c0, c1, c2, c3;
                     upk2(c01, c0, c1);
                     upk2(c23, c2, c3);
+                    __stcg(sk + 4 * 32, c0); __stcg(sk + 5 * 32, c1); __stcg(sk + 6 * 32, c2); __stcg(sk + 7 * 32, c3);
                     const u64 ci01 = pk2(rcp_approx(c0), rcp_approx(c1)), ci23 = pk2(rcp_approx(c2), rcp_approx(c3));
 #pragma unroll
                     for (int i = 0; i < kN; ++i) { R[i] = mul2(R[i], ci01); S[i] = mul2(S[i], ci23); }
-                    *reinterpret_cast<float4*>(skl + k * kSkStride) = make_float4(dr[0], dr[1], dr[2], dr[3]);
-                    *reinterpret_cast<float4*>(skl + k * kSkStride + 4) = make_float4(c0, c1, c2, c3);
                 }
-                // ---- mixing matrix M = P + hpost (x) hpre, stored transposed (M^T[j][i]) for the dx pass
-                float* c = coef + (buf * kTok + tk) * kCoefStride;
+                // ---- gradients of the gates from G = dy x^T; D/E start as dP = G
+                u64 D[kN], E[kN];
+                float dl_post[kN];
+#pragma unroll
+                for (int j = 0; j < kN; ++j) dlv[j] = 0.f;
+#pragma unroll
+                for (int i = 0; i < kN; ++i) {
+                    const float4 gq = *reinterpret_cast<const float4*>(r + kRecG + 4 * i);
+                    D[i] = pk2(gq.x, gq.y);
+                    E[i] = pk2(gq.z, gq.w);
+                    const float dhpost = fmaf(gq.w, hpre[3], fmaf(gq.z, hpre[2], fmaf(gq.y, hpre[1], gq.x * hpre[0])));
+                    dl_post[i] = dhpost * hpost[i] * (1.0f - 0.5f * hpost[i]);
+                    dlv[0] = fmaf(gq.x, hpost[i], dlv[0]); dlv[1] = fmaf(gq.y, hpost[i], dlv[1]);
+                    dlv[2] = fmaf(gq.z, hpost[i], dlv[2]); dlv[3] = fmaf(gq.w, hpost[i], dlv[3]);
+                }
+#pragma unroll
+                for (int j = 0; j < kN; ++j) { dlv[j] = dlv[j] * hpre[j] * (1.0f - hpre[j]); dlv[kN + j] = dl_post[j]; }
+                // ---- M^T[j][i] = P[i][j] + hpost[i] hpre[j] replaces G in the record (pass 2 reads it)
                 {
                     float pr[kN][kN];
 #pragma unroll
                     for (int i = 0; i < kN; ++i) { upk2(R[i], pr[i][0], pr[i][1]); upk2(S[i], pr[i][2], pr[i][3]); }
 #pragma unroll
                     for (int j = 0; j < kN; ++j)
-                        *reinterpret_cast<float4*>(c + 4 * j) =
+                        *reinterpret_cast<float4*>(r + kRecG + 4 * j) =
                             make_float4(fmaf(hpost[0], hpre[j], pr[0][j]), fmaf(hpost[1], hpre[j], pr[1][j]),
                                         fmaf(hpost[2], hpre[j], pr[2][j]), fmaf(hpost[3], hpre[j], pr[3][j]));
                 }
-                // ---- gradients of the gates from G = dy x^T; D/E start as dP = G
-                u64 D[kN], E[kN];
-                float dl_pre[kN] = {0.f, 0.f, 0.f, 0.f}, dl_post[kN];
+                // ---- exact reverse sweep through the iterations (normalisers prefetched one iteration ahead)
+                float nx[8];
+                if (p.sk_iters > 0) {
 #pragma unroll
-                for (int i = 0; i < kN; ++i) {
-                    const float g0 = r[kPartG + 4 * i], g1 = r[kPartG + 4 * i + 1], g2 = r[kPartG + 4 * i + 2], g3 = r[kPartG + 4 * i + 3];
-                    D[i] = pk2(g0, g1);
-                    E[i] = pk2(g2, g3);
-                    const float dhpost = fmaf(g3, hpre[3], fmaf(g2, hpre[2], fmaf(g1, hpre[1], g0 * hpre[0])));
-                    dl_post[i] = dhpost * hpost[i] * (1.0f - 0.5f * hpost[i]);
-                    dl_pre[0] = fmaf(g0, hpost[i], dl_pre[0]); dl_pre[1] = fmaf(g1, hpost[i], dl_pre[1]);
-                    dl_pre[2] = fmaf(g2, hpost[i], dl_pre[2]); dl_pre[3] = fmaf(g3, hpost[i], dl_pre[3]);
+                    for (int c = 0; c < 8; ++c) nx[c] = __ldcg(skl + (p.sk_iters - 1) * 256 + c * 32);
                 }
-#pragma unroll
-                for (int j = 0; j < kN; ++j) dl_pre[j] = dl_pre[j] * hpre[j] * (1.0f - hpre[j]);
-                // ---- exact reverse sweep through the iterations
                 for (int k = p.sk_iters - 1; k >= 0; --k) {
-                    const float4 dr = *reinterpret_cast<const float4*>(skl + k * kSkStride);
-                    const float4 cd = *reinterpret_cast<const float4*>(skl + k * kSkStride + 4);
+                    float cu[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) cu[c] = nx[c];
+                    if (k > 0) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) nx[c] = __ldcg(skl + (k - 1) * 256 + c * 32);
+                    }
                     // column step y = x / c:  dx = (dy - sum_i dy*y) / c ;  x = y * c
                     u64 q01 = mul2(D[0], R[0]), q23 = mul2(E[0], S[0]);
 #pragma unroll
                     for (int i = 1; i < kN; ++i) { q01 = fma2(D[i], R[i], q01); q23 = fma2(E[i], S[i], q23); }
-                    const float r0 = rcp_approx(cd.x), r1 = rcp_approx(cd.y), r2 = rcp_approx(cd.z), r3 = rcp_approx(cd.w);
+                    const float r0 = rcp_approx(cu[4]), r1 = rcp_approx(cu[5]), r2 = rcp_approx(cu[6]), r3 = rcp_approx(cu[7]);
                     const u64 ci01 = pk2(r0, r1), ci23 = pk2(r2, r3);
                     const u64 nq01 = mul2(q01, pk2(-r0, -r1)), nq23 = mul2(q23, pk2(-r2, -r3));
-                    const u64 cc01 = pk2(cd.x, cd.y), cc23 = pk2(cd.z, cd.w);
+                    const u64 cc01 = pk2(cu[4], cu[5]), cc23 = pk2(cu[6], cu[7]);
 #pragma unroll
                     for (int i = 0; i < kN; ++i) {
                         D[i] = fma2(D[i], ci01, nq01); E[i] = fma2(E[i], ci23, nq23);
                         R[i] = mul2(R[i], cc01);       S[i] = mul2(S[i], cc23);
                     }
                     // row step y = x / dr
-                    const float drv[kN] = {dr.x, dr.y, dr.z, dr.w};
 #pragma unroll
                     for (int i = 0; i < kN; ++i) {
                         float a, b;
                         upk2(fma2(E[i], S[i], mul2(D[i], R[i])), a, b);
-                        const float rr = rcp_approx(drv[i]);
+                        const float rr = rcp_approx(cu[i]);
                         const float nq = -(a + b) * rr;
-                        const u64 rr2 = pk2(rr, rr), nq2 = pk2(nq, nq), dd2 = pk2(drv[i], drv[i]);
+                        const u64 rr2 = pk2(rr, rr), nq2 = pk2(nq, nq), dd2 = pk2(cu[i], cu[i]);
                         D[i] = fma2(D[i], rr2, nq2); E[i] = fma2(E[i], rr2, nq2);
                         R[i] = mul2(R[i], dd2);      S[i] = mul2(S[i], dd2);
                     }
                 }
                 // softmax * 4 backward (R,S are back at the softmax output): dl = s * (d - sum(d*s)/4)
-                float dl_res[kN][kN];
 #pragma unroll
                 for (int i = 0; i < kN; ++i) {
                     float a, b;
                     upk2(fma2(E[i], S[i], mul2(D[i], R[i])), a, b);
                     const float nqs = -0.25f * (a + b);
                     const u64 nq2 = pk2(nqs, nqs);
-                    upk2(mul2(R[i], add2(D[i], nq2)), dl_res[i][0], dl_res[i][1]);
-                    upk2(mul2(S[i], add2(E[i], nq2)), dl_res[i][2], dl_res[i][3]);
+                    upk2(mul2(R[i], add2(D[i], nq2)), dlv[2 * kN + 4 * i + 0], dlv[2 * kN + 4 * i + 1]);
+                    upk2(mul2(S[i], add2(E[i], nq2)), dlv[2 * kN + 4 * i + 2], dlv[2 * kN + 4 * i + 3]);
                 }
-                // ---- e = d raw, kappa (RMSNorm backward), per-token terms of dbias / dalpha
-                float dsum = 0.f, da_pre = 0.f, da_post = 0.f, da_res = 0.f;
+                // ---- e = d raw, kappa (RMSNorm backward), per-token terms of dalpha; the raw logits in the
+                // record are read here for the last time and then overwritten with e (bf16 pairs) and kappa
+                float dsum = 0.f;
                 float ev[kL];
 #pragma unroll
-                for (int j = 0; j < kN; ++j) {
-                    ev[j] = a_pre * dl_pre[j] * inv_rms;       dsum = fmaf(ev[j], r[j], dsum);
-                    da_pre = fmaf(dl_pre[j], r[j] * inv_rms, da_pre);
-                    ev[kN + j] = a_post * dl_post[j] * inv_rms; dsum = fmaf(ev[kN + j], r[kN + j], dsum);
-                    da_post = fmaf(dl_post[j], r[kN + j] * inv_rms, da_post);
+                for (int k = 0; k < kL; ++k) {
+                    const float ag = k < kN ? a_pre : (k < 2 * kN ? a_post : a_res);
+                    const float rawk = r[k];
+                    ev[k] = ag * dlv[k] * inv_rms;
+                    dsum = fmaf(ev[k], rawk, dsum);
+                    const float dz = dlv[k] * rawk * inv_rms;
+                    if (k < kN) dlv[kL] += dz; else if (k < 2 * kN) dlv[kL + 1] += dz; else dlv[kL + 2] += dz;
                 }
-#pragma unroll
-                for (int i = 0; i < kN; ++i)
-#pragma unroll
-                    for (int j = 0; j < kN; ++j) {
-                        const int k = 2 * kN + 4 * i + j;
-                        ev[k] = a_res * dl_res[i][j] * inv_rms; dsum = fmaf(ev[k], r[k], dsum);
-                        da_res = fmaf(dl_res[i][j], r[k] * inv_rms, da_res);
-                    }
-                uint32_t* ew = reinterpret_cast<uint32_t*>(c + kCoefE);
+                uint32_t* ew = reinterpret_cast<uint32_t*>(r);
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                     *reinterpret_cast<uint4*>(ew + 4 * q) = make_uint4(pack_bf16(ev[8 * q], ev[8 * q + 1]), pack_bf16(ev[8 * q + 2], ev[8 * q + 3]),
                                                                        pack_bf16(ev[8 * q + 4], ev[8 * q + 5]), pack_bf16(ev[8 * q + 6], ev[8 * q + 7]));
-                *reinterpret_cast<uint4*>(ew + 12) = make_uint4(0u, 0u, 0u, 0u);          // logits 24..31: zero pad
-                c[kCoefKappa] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
-                const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + tk;
+                r[kRecKappa] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
+                const int it = sb * kSb + (lane >> 3);
+                const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + (lane & 7);
                 if (tok < p.T) {
                     float4* o = reinterpret_cast<float4*>(p.e_out + tok * kL);
 #pragma unroll
                     for (int q = 0; q < 6; ++q) o[q] = make_float4(ev[4 * q], ev[4 * q + 1], ev[4 * q + 2], ev[4 * q + 3]);
                 }
-                // padded rows have dy = 0, hence G = 0 and every dl = 0: they add nothing below
-#pragma unroll
-                for (int j = 0; j < kN; ++j) { dls[j] = dl_pre[j]; dls[kN + j] = dl_post[j]; }
-#pragma unroll
-                for (int i = 0; i < kN; ++i)
-                    *reinterpret_cast<float4*>(dls + 2 * kN + 4 * i) = make_float4(dl_res[i][0], dl_res[i][1], dl_res[i][2], dl_res[i][3]);
-                dls[kL] = da_pre; dls[kL + 1] = da_post; dls[kL + 2] = da_res;
+                // padded rows have dy = 0, hence G = 0 and every dl = 0: they add nothing to the sums below
             }
             __threadfence_block();
-            bar_arrive(kBarCoef + buf, kWorkerThreads + 32);
-            __syncwarp();
-            if (lane < kAccum) {
+            bar_arrive(kBarCoef + cw, kWorkerThreads + 32);
+            // dbias / dalpha: butterfly over the token lanes (fixed order), component k accumulates in lane k
 #pragma unroll
-                for (int q = 0; q < kTok; ++q) my_acc += dlbuf[q * kDlStride + lane];      // fixed order over tokens
+            for (int k = 0; k < kAccum; ++k) {
+                const float v = warp_sum(dlv[k]);
+                if (lane == k) my_acc += v;
             }
-            __syncwarp();
         }
-        if (lane < kAccum) p.cta_accum[(size_t)blockIdx.x * kAccum + lane] = my_acc;
+        if (lane < kAccum) p.cta_accum[((size_t)blockIdx.x * 2 + cw) * kAccum + lane] = my_acc;
       }
     } else {
         // ===================================================== worker warps
@@ -374,122 +408,119 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             const int row = g * kN + j;
             off[j] = cb * kBoxBytes + row * 128 + (((4 * hh + t) ^ (row & 7)) << 4);
         }
-        // ldmatrix lane addresses for G = dy x^T: matrix (lane>>3) of an x4 load, row (lane&7)
-        const int lm = lane >> 3, lr = lane & 7;
+        const int lm = lane >> 3, lr = lane & 7;            // ldmatrix: matrix index / row of an x4 load
         const uint32_t stage0 = smem_u32(smem);
 
-        auto finish_tile = [&](int itp) {
-            const int bufp = itp & 1;
-            const uint32_t sbase = stage0 + (itp % kStages) * kStageBytes;
-            bar_sync(kBarCoef + bufp, kWorkerThreads + 32);
-            const float* c = coef + (bufp * kTok + g) * kCoefStride;
-            const uint32_t* ew = reinterpret_cast<const uint32_t*>(c + kCoefE);
-            const uint32_t ea0 = ew[t], ea2 = ew[t + 4], eb0 = ew[t + 8];     // e[2t..], e[2t+8..], e[2t+16..]
-            const float kappa = c[kCoefKappa];
-            uint32_t dyr[kN][4];
-#pragma unroll
-            for (int ii = 0; ii < kN; ++ii) {
-                const uint4 v = lds128(sbase + kHalfBytes + off[ii]);
-                dyr[ii][0] = v.x; dyr[ii][1] = v.y; dyr[ii][2] = v.z; dyr[ii][3] = v.w;
-            }
-#pragma unroll
-            for (int j = 0; j < kN; ++j) {
-                const float4 mt = *reinterpret_cast<const float4*>(c + 4 * j);       // M[0..3][j]
-                const uint4 xv = lds128(sbase + off[j]);
-                const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-                uint32_t out[4];
-#pragma unroll
-                for (int q = 0; q < 2; ++q)
-#pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) {
-                        // dx_proj for Kidx (j, 32w + 8t + 4q + 2rr + {0,1}) of token g: e . W^T
-                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                        mma_bf16_16816(acc, ea0, 0u, ea2, 0u, movmatrix_trans(bfrag[j][q][0][rr]), movmatrix_trans(bfrag[j][q][1][rr]));
-                        mma_bf16_16816(acc, eb0, 0u, 0u, 0u, movmatrix_trans(bfrag[j][q][2][rr]), 0u);
-                        const int e = 2 * q + rr;
-                        float lo = fmaf(kappa, bf16lo(xw[e]), acc[0]);
-                        float hi = fmaf(kappa, bf16hi(xw[e]), acc[1]);
-                        lo = fmaf(mt.x, bf16lo(dyr[0][e]), lo); hi = fmaf(mt.x, bf16hi(dyr[0][e]), hi);
-                        lo = fmaf(mt.y, bf16lo(dyr[1][e]), lo); hi = fmaf(mt.y, bf16hi(dyr[1][e]), hi);
-                        lo = fmaf(mt.z, bf16lo(dyr[2][e]), lo); hi = fmaf(mt.z, bf16hi(dyr[2][e]), hi);
-                        lo = fmaf(mt.w, bf16lo(dyr[3][e]), lo); hi = fmaf(mt.w, bf16hi(dyr[3][e]), hi);
-                        out[e] = pack_bf16(lo, hi);
-                    }
-                sts128(sbase + kHalfBytes + off[j], make_uint4(out[0], out[1], out[2], out[3]));
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(&bar_done[itp % kStages]);
-        };
-
-        for (int it = 0; it < n_local; ++it) {
-            const int s = it % kStages;
+        ItemIter itx;
+        itx.init(n_local);
+        int p1_count = 0;
+        for (int q = 0; itx.valid(); ++q, itx.next()) {
+            const int s = q % kStages;
             const uint32_t sbase = stage0 + s * kStageBytes;
-            mbar_wait(&bar_full[s], (it / kStages) & 1);
-            // ---- raw^T = W^T x^T (tokens are the MMA N), sum x^2 on the diagonal of x x^T
-            float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, accs[4] = {0.f, 0.f, 0.f, 0.f};
+            mbar_wait(&bar_full[s], (q / kStages) & 1);
+            if (itx.ph == 0) {
+                // ============ pass 1: raw^T = W^T x^T (tokens are the MMA N), sum x^2 on the diagonal of x x^T
+                float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, accs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < kN; ++j) {
-                const uint4 xv = lds128(sbase + off[j]);
-                mma_bf16_16816(acc0, bfrag[j][0][0][0], bfrag[j][0][1][0], bfrag[j][0][0][1], bfrag[j][0][1][1], xv.x, xv.y);
-                mma_bf16_16816(acc1, bfrag[j][0][2][0], 0u, bfrag[j][0][2][1], 0u, xv.x, xv.y);
-                mma_bf16_16816(accs, xv.x, 0u, xv.y, 0u, xv.x, xv.y);
-                mma_bf16_16816(acc0, bfrag[j][1][0][0], bfrag[j][1][1][0], bfrag[j][1][0][1], bfrag[j][1][1][1], xv.z, xv.w);
-                mma_bf16_16816(acc1, bfrag[j][1][2][0], 0u, bfrag[j][1][2][1], 0u, xv.z, xv.w);
-                mma_bf16_16816(accs, xv.z, 0u, xv.w, 0u, xv.z, xv.w);
-            }
-            // ---- G = dy x^T per token: rows (token, i) of dy against rows (token, j) of x, block diagonal
-            float gacc[2][2][4];
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-#pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) gacc[m][h2][0] = gacc[m][h2][1] = gacc[m][h2][2] = gacc[m][h2][3] = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                uint32_t bx[4][2];
-#pragma unroll
-                for (int nn = 0; nn < 4; nn += 2) {
-                    // x rows 8nn..8nn+15, chunks (4hh + 2ks), (4hh + 2ks + 1)
-                    const int row = 8 * nn + (lm >> 1) * 8 + lr;
-                    const int chunk = 4 * hh + 2 * ks + (lm & 1);
-                    ldmatrix_x4(sbase + cb * kBoxBytes + row * 128 + ((chunk ^ (row & 7)) << 4),
-                                bx[nn][0], bx[nn][1], bx[nn + 1][0], bx[nn + 1][1]);
+                for (int j = 0; j < kN; ++j) {
+                    const uint4 xv = lds128(sbase + off[j]);
+                    mma_bf16_16816(acc0, bfrag[j][0][0][0], bfrag[j][0][1][0], bfrag[j][0][0][1], bfrag[j][0][1][1], xv.x, xv.y);
+                    mma_bf16_16816(acc1, bfrag[j][0][2][0], 0u, bfrag[j][0][2][1], 0u, xv.x, xv.y);
+                    mma_bf16_16816(accs, xv.x, 0u, xv.y, 0u, xv.x, xv.y);
+                    mma_bf16_16816(acc0, bfrag[j][1][0][0], bfrag[j][1][1][0], bfrag[j][1][0][1], bfrag[j][1][1][1], xv.z, xv.w);
+                    mma_bf16_16816(acc1, bfrag[j][1][2][0], 0u, bfrag[j][1][2][1], 0u, xv.z, xv.w);
+                    mma_bf16_16816(accs, xv.z, 0u, xv.w, 0u, xv.z, xv.w);
                 }
+                // G = dy x^T per token: rows (token, i) of dy against rows (token, j) of x, block diagonal
+                float gacc[2][2][4];
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    uint32_t a0, a1, a2, a3;
-                    const int row = 16 * m + (lm & 1) * 8 + lr;
-                    const int chunk = 4 * hh + 2 * ks + (lm >> 1);
-                    ldmatrix_x4(sbase + kHalfBytes + cb * kBoxBytes + row * 128 + ((chunk ^ (row & 7)) << 4), a0, a1, a2, a3);
-                    mma_bf16_16816(gacc[m][0], a0, a1, a2, a3, bx[2 * m][0], bx[2 * m][1]);
-                    mma_bf16_16816(gacc[m][1], a0, a1, a2, a3, bx[2 * m + 1][0], bx[2 * m + 1][1]);
-                }
-            }
-            bar_sync(kBarPartFree, kWorkerThreads + 64);      // reducers finished reading the previous partials
-            {
-                float* pw = part + (size_t)w * kTok * kPartStride;
-                // raw^T fragments: (logit g | g+8 | 16+g, tokens 2t, 2t+1)
-                pw[(2 * t) * kPartStride + g] = acc0[0];      pw[(2 * t + 1) * kPartStride + g] = acc0[1];
-                pw[(2 * t) * kPartStride + 8 + g] = acc0[2];  pw[(2 * t + 1) * kPartStride + 8 + g] = acc0[3];
-                pw[(2 * t) * kPartStride + 16 + g] = acc1[0]; pw[(2 * t + 1) * kPartStride + 16 + g] = acc1[1];
-                if (t == (g >> 1)) pw[g * kPartStride + kL] = accs[g & 1];       // diagonal of x x^T
-                // G fragments: m-tile m rows = (token 4m + {0,1} | 4m + {2,3}, i), n-tile cols = (token, j)
-                if ((g >> 2) == (t >> 1)) {
-                    const int i = g & 3, jj = 2 * (t & 1);
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) gacc[m][h2][0] = gacc[m][h2][1] = gacc[m][h2][2] = gacc[m][h2][3] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    uint32_t bx[4][2];
+#pragma unroll
+                    for (int nn = 0; nn < 4; nn += 2) {
+                        const int row = 8 * nn + (lm >> 1) * 8 + lr;
+                        const int chunk = 4 * hh + 2 * ks + (lm & 1);
+                        ldmatrix_x4(sbase + cb * kBoxBytes + row * 128 + ((chunk ^ (row & 7)) << 4),
+                                    bx[nn][0], bx[nn][1], bx[nn + 1][0], bx[nn + 1][1]);
+                    }
 #pragma unroll
                     for (int m = 0; m < 2; ++m) {
-                        const int tokA = 4 * m + (g >> 2), tokB = 4 * m + 2 + (g >> 2);
-                        *reinterpret_cast<float2*>(pw + tokA * kPartStride + kPartG + 4 * i + jj) =
-                            make_float2(gacc[m][0][0], gacc[m][0][1]);
-                        *reinterpret_cast<float2*>(pw + tokB * kPartStride + kPartG + 4 * i + jj) =
-                            make_float2(gacc[m][1][2], gacc[m][1][3]);
+                        uint32_t a0, a1, a2, a3;
+                        const int row = 16 * m + (lm & 1) * 8 + lr;
+                        const int chunk = 4 * hh + 2 * ks + (lm >> 1);
+                        ldmatrix_x4(sbase + kHalfBytes + cb * kBoxBytes + row * 128 + ((chunk ^ (row & 7)) << 4), a0, a1, a2, a3);
+                        mma_bf16_16816(gacc[m][0], a0, a1, a2, a3, bx[2 * m][0], bx[2 * m][1]);
+                        mma_bf16_16816(gacc[m][1], a0, a1, a2, a3, bx[2 * m + 1][0], bx[2 * m + 1][1]);
                     }
                 }
+                mbar_arrive(&bar_done[s]);                        // every read of the stage has landed in registers
+                bar_sync(kBarPartFree, kWorkerThreads + 32);      // reducer finished reading the previous partials
+                {
+                    float* pw = part + (size_t)w * kTok * kRec;
+                    pw[(2 * t) * kRec + g] = acc0[0];      pw[(2 * t + 1) * kRec + g] = acc0[1];
+                    pw[(2 * t) * kRec + 8 + g] = acc0[2];  pw[(2 * t + 1) * kRec + 8 + g] = acc0[3];
+                    pw[(2 * t) * kRec + 16 + g] = acc1[0]; pw[(2 * t + 1) * kRec + 16 + g] = acc1[1];
+                    if (t == (g >> 1)) pw[g * kRec + kRecSS] = accs[g & 1];       // diagonal of x x^T
+                    if ((g >> 2) == (t >> 1)) {
+                        const int i = g & 3, jj = 2 * (t & 1);
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) {
+                            const int tokA = 4 * m + (g >> 2), tokB = 4 * m + 2 + (g >> 2);
+                            *reinterpret_cast<float2*>(pw + tokA * kRec + kRecG + 4 * i + jj) = make_float2(gacc[m][0][0], gacc[m][0][1]);
+                            *reinterpret_cast<float2*>(pw + tokB * kRec + kRecG + 4 * i + jj) = make_float2(gacc[m][1][2], gacc[m][1][3]);
+                        }
+                    }
+                }
+                __threadfence_block();
+                bar_arrive(kBarPart + (p1_count & 1), kWorkerThreads + 32);
+                ++p1_count;
+            } else {
+                // ============ pass 2: dx for token g of this tile
+                const int sb = itx.sb();
+                if (itx.i == 0) bar_sync(kBarCoef + (sb & 1), kWorkerThreads + 32);     // superblock's coefficients are ready
+                const float* c = red + (((sb % kRedSlots) * kSb + itx.i) * kTok + g) * kRec;
+                const uint32_t* ew = reinterpret_cast<const uint32_t*>(c);
+                const uint32_t ea0 = ew[t], ea2 = ew[t + 4], eb0 = ew[t + 8];     // e[2t..], e[2t+8..], e[2t+16..]
+                const float kappa = c[kRecKappa];
+                uint32_t dyr[kN][4];
+#pragma unroll
+                for (int ii = 0; ii < kN; ++ii) {
+                    const uint4 v = lds128(sbase + kHalfBytes + off[ii]);
+                    dyr[ii][0] = v.x; dyr[ii][1] = v.y; dyr[ii][2] = v.z; dyr[ii][3] = v.w;
+                }
+#pragma unroll
+                for (int j = 0; j < kN; ++j) {
+                    const float4 mt = *reinterpret_cast<const float4*>(c + kRecG + 4 * j);       // M[0..3][j]
+                    const uint4 xv = lds128(sbase + off[j]);
+                    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+                    uint32_t out[4];
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq)
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            // dx_proj for K index (j, 32w + 8t + 4qq + 2rr + {0,1}) of token g: e . W^T
+                            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                            mma_bf16_16816(acc, ea0, 0u, ea2, 0u, movmatrix_trans(bfrag[j][qq][0][rr]), movmatrix_trans(bfrag[j][qq][1][rr]));
+                            mma_bf16_16816(acc, eb0, 0u, 0u, 0u, movmatrix_trans(bfrag[j][qq][2][rr]), 0u);
+                            const int e = 2 * qq + rr;
+                            float lo = fmaf(kappa, bf16lo(xw[e]), acc[0]);
+                            float hi = fmaf(kappa, bf16hi(xw[e]), acc[1]);
+                            lo = fmaf(mt.x, bf16lo(dyr[0][e]), lo); hi = fmaf(mt.x, bf16hi(dyr[0][e]), hi);
+                            lo = fmaf(mt.y, bf16lo(dyr[1][e]), lo); hi = fmaf(mt.y, bf16hi(dyr[1][e]), hi);
+                            lo = fmaf(mt.z, bf16lo(dyr[2][e]), lo); hi = fmaf(mt.z, bf16hi(dyr[2][e]), hi);
+                            lo = fmaf(mt.w, bf16lo(dyr[3][e]), lo); hi = fmaf(mt.w, bf16hi(dyr[3][e]), hi);
+                            out[e] = pack_bf16(lo, hi);
+                        }
+                    sts128(sbase + kHalfBytes + off[j], make_uint4(out[0], out[1], out[2], out[3]));
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&bar_done[s]);
             }
-            __threadfence_block();
-            bar_arrive(kBarPart + (it & 1), kWorkerThreads + 64);
-            if (it > 0) finish_tile(it - 1);
         }
-        if (n_local > 0) finish_tile(n_local - 1);
     }
 }
 
@@ -620,7 +651,7 @@ mhc_stream_bwd_finalize_kernel(const float* __restrict__ dw_part, int dw_ctas, c
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct BwdWs {
-    float* e; float* dw_part; float* cta_accum;
+    float* e; float* dw_part; float* cta_accum; float* sk_scratch;
     size_t total;
 };
 BwdWs carve(void* base, int64_t T, int ctas) {
@@ -629,7 +660,8 @@ BwdWs carve(void* base, int64_t T, int ctas) {
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return reinterpret_cast<uint8_t*>(base) + o; };
     w.e = reinterpret_cast<float*>(take((size_t)T * kL * 4));
     w.dw_part = reinterpret_cast<float*>(take((size_t)ctas * kRow * kL * 4));
-    w.cta_accum = reinterpret_cast<float*>(take((size_t)ctas * kAccum * 4));
+    w.cta_accum = reinterpret_cast<float*>(take((size_t)ctas * 2 * kAccum * 4));
+    w.sk_scratch = reinterpret_cast<float*>(take((size_t)ctas * 2 * kSkWords * 4));
     w.total = off;
     return w;
 }
@@ -681,7 +713,7 @@ extern "C" int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* ph
         }
         BwdParams p;
         p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale;
-        p.e_out = ws.e; p.cta_accum = ws.cta_accum;
+        p.e_out = ws.e; p.cta_accum = ws.cta_accum; p.sk_scratch = ws.sk_scratch;
         p.T = T;
         p.num_tiles = (int)((T + kTok - 1) / kTok);
         p.sk_iters = sk_iters; p.eps_rms = eps_rms; p.eps_sk = eps_sk;
@@ -702,7 +734,7 @@ extern "C" int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* ph
         if (rc2) return rc2;
     }
     timer_begin(3, stream);
-    mhc_stream_bwd_finalize_kernel<<<kRow / 8, 256, 0, stream>>>(ws.dw_part, grid2, ws.cta_accum, grid1, phi, scale, dphi,
+    mhc_stream_bwd_finalize_kernel<<<kRow / 8, 256, 0, stream>>>(ws.dw_part, grid2, ws.cta_accum, 2 * grid1, phi, scale, dphi,
                                                                  dscale, dbias, dalpha);
     timer_end(3, stream);
     count_launch();

@@ -111,7 +111,7 @@ def test_manifold_hyper_connection_bf16_and_grad():
     mod = hvs_b200.ManifoldHyperConnection(64, expansion_rate=4, dropout_rate=0.0).cuda().train()
     x = torch.randn(16, 64, device="cuda", requires_grad=True)
     out = mod(x)
-    out.sum().backward()
+    (out * torch.randn_like(out)).sum().backward()      # (a plain sum of a LayerNorm output has zero gradient)
     gn = x.grad.norm().item()
     assert np.isfinite(gn) and 0 < gn < 100
     assert mod.H_res_raw.grad is not None and torch.isfinite(mod.H_res_raw.grad).all()
