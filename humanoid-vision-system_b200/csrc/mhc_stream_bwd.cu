@@ -143,15 +143,18 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             tma_prefetch_desc(&tmap_x);
             tma_prefetch_desc(&tmap_dy);
             tma_prefetch_desc(&tmap_dx);
+            const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
             auto load_item = [&](const ItemIter& w, int q) {
                 const int s = q % kStages;
                 const int row0 = ((int)blockIdx.x + w.tile() * (int)gridDim.x) * (kTok * kN);
                 uint8_t* st = smem + s * kStageBytes;
                 mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
+                // pass 1 asks L2 to keep the lines (they come back kLag superblocks later), pass 2 releases them
+                const uint64_t pol = w.ph == 0 ? pol_keep : pol_drop;
 #pragma unroll
                 for (int cb = 0; cb < kC / 64; ++cb) {
-                    tma_load_2d(st + cb * kBoxBytes, &tmap_x, &bar_full[s], cb * 64, row0);
-                    tma_load_2d(st + kHalfBytes + cb * kBoxBytes, &tmap_dy, &bar_full[s], cb * 64, row0);
+                    tma_load_2d_hint(st + cb * kBoxBytes, &tmap_x, &bar_full[s], cb * 64, row0, pol);
+                    tma_load_2d_hint(st + kHalfBytes + cb * kBoxBytes, &tmap_dy, &bar_full[s], cb * 64, row0, pol);
                 }
             };
             ItemIter ld, cur;
@@ -166,7 +169,7 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     const int row0 = ((int)blockIdx.x + cur.tile() * (int)gridDim.x) * (kTok * kN);
 #pragma unroll
                     for (int cb = 0; cb < kC / 64; ++cb)
-                        tma_store_2d(&tmap_dx, smem + s * kStageBytes + kHalfBytes + cb * kBoxBytes, cb * 64, row0);
+                        tma_store_2d_hint(&tmap_dx, smem + s * kStageBytes + kHalfBytes + cb * kBoxBytes, cb * 64, row0, pol_drop);
                     bulk_commit();
                     bulk_wait_read<0>();
                 }
