@@ -1,16 +1,20 @@
 // K1 backward (F = identity), coefficients recomputed from x -- nothing is saved by the forward.
 //
-// Kernel B1 (per token, HBM-bound: x and dy in, dx out).  The per-token Sinkhorn forward + reverse sweep is
-// a ~14k-cycle dependent chain, far longer than a tile can stay resident in shared memory, so every 8-token
-// tile is visited TWICE by the same CTA, the second time re-loaded by TMA while it is still in the 126 MB L2:
-//   pass 1 (workers, 16 warps, split-K)  raw = x.W on the warp MMA path (W = bf16(scale*phi) in registers),
-//                                        sum x^2 and the per-token 4x4  G = dy x^T  as MMAs on the smem tiles;
-//                                        the stage is released immediately
-//   reducer warp                         fixed-order sum of the 16 split-K partials into a per-token record
-//   2 coefficient warps (lane = token,   forward gates + Sinkhorn in packed fp32x2 registers, then the exact
-//     24 tokens per pass, alternating)   reverse sweep through all iterations -> dlogits, e = d raw, kappa, M^T
-//   pass 2 (workers, two superblocks     dx = M^T dy  +  e W^T (MMA; W^T by movmatrix from the same registers)
-//     of 3 tiles later)                       + kappa x, one rounding to bf16, in place over dy, TMA store
+// Kernel B1 (per token, HBM-bound: x and dy in, dx out; every byte crosses HBM once).  The per-token
+// Sinkhorn forward + reverse sweep is a ~14k-cycle dependent chain, several times longer than a tile can
+// afford to occupy a shared-memory stage.  So after pass 1 each 8-token tile is PARKED IN TENSOR MEMORY
+// (256 KB per SM, unused otherwise: this kernel has no tcgen05.mma) -- every worker thread stores its own
+// 32 registers of x and dy with tcgen05.st and gets them back with tcgen05.ld -- and the shared-memory
+// stage is recycled at once.  Four tiles can be parked while two coefficient warps work on them:
+//   P1 workers (16 warps, split-K)   raw = x.W on the warp MMA path (W = bf16(scale*phi) in registers),
+//                                    sum x^2 and the per-token 4x4  G = dy x^T  as MMAs on the smem tile,
+//                                    park x, dy in TMEM, release the stage
+//                                    and fixed-order sum of the 16 split-K partials into a per-token record
+//   3 coefficient warps (lane=token, forward gates + Sinkhorn in packed fp32x2 registers, then the exact
+//     one tile each, round robin)    reverse sweep through all iterations -> dlogits, e = d raw, kappa, M^T
+//   P3 workers (4 tiles later)       dx = M^T dy  +  e W^T (MMA; W^T by movmatrix from the same registers)
+//                                        + kappa x from the parked registers, one rounding to bf16, staged in
+//                                    shared memory and TMA-stored
 //   The coefficient warps also emit E[T,24] (fp32) and per-CTA partial sums of dbias / dalpha.
 // Kernel B2: dW = x^T E on the warp MMA path (x re-read once; E split into two bf16 terms), per-CTA
 //   partials; finalize: dphi = scale * dW, dscale = sum_k phi * dW, dbias, dalpha (fixed order).
@@ -26,32 +30,36 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------ B1
 constexpr int kTok = 8;                               // tokens per tile
-constexpr int kSb = 3;                                // tiles per superblock = one coefficient pass (24 tokens)
-constexpr int kLag = 2;                               // superblocks between pass 1 and pass 2 of a tile
-constexpr int kRedSlots = 3;                          // record buffers: filling | in the coefficient warp | pass 2
+constexpr int kSlots = 4;                             // tiles parked in TMEM at a time (4 x 128 columns)
 constexpr int kWorkers = 16;
 constexpr int kWorkerThreads = kWorkers * 32;
-constexpr int kThreads = (kWorkers + 4) * 32;         // + coefficient warp A, producer, coefficient warp B, reducer
+constexpr int kThreads = (kWorkers + 4) * 32;         // + coefficient warp 0, producer, coefficient warps 1, 2
+constexpr int kCoefWarps = 3;
 constexpr int kWorkerRegs = 104, kRoleRegs = 64;
-constexpr int kStages = 3;
+constexpr int kStages = 2;                            // TMA landing stages (x | dy), held only until P1 is done
 constexpr int kHalfBytes = kTok * kRowBytes;          // 32 KB: x tile or dy tile
-constexpr int kStageBytes = 2 * kHalfBytes;           // x | dy
+constexpr int kStageBytes = 2 * kHalfBytes;
+constexpr int kDxBufs = 1;                            // dx staging for the TMA store
 constexpr int kBoxBytes = 32 * 128;                   // TMA box: 32 rows (8 tokens x 4 streams) x 64 bf16
-// per-token record (fp32 words): pass 1 writes raw[0..23] ss[24] G[28..43]; the coefficient warp overwrites it in
-// place with e as bf16 pairs [0..11], kappa [12], M^T [28..43] for pass 2
+// per-token record (fp32 words): P1 writes raw[0..23] ss[24] G[28..43]; the coefficient warp overwrites it in
+// place with e as bf16 pairs [0..11], kappa [12], M^T [28..43] for P3
 constexpr int kRec = 44, kRecSS = 24, kRecG = 28, kRecKappa = 12;
-constexpr int kMaxIters = 32;
+constexpr int kMaxIters = 24;                         // normalisers of every iteration are kept in shared memory
+constexpr uint32_t kTmemCols = 512;
 
-constexpr int kOffPart = kStages * kStageBytes;
-constexpr int kOffRed = kOffPart + kWorkers * kTok * kRec * 4;
-constexpr int kOffBar = kOffRed + kRedSlots * kSb * kTok * kRec * 4;
-constexpr int kSmemBytes = kOffBar + 2 * kStages * 8;
+constexpr int kOffDx = kStages * kStageBytes;
+constexpr int kOffPart = kOffDx + kDxBufs * kHalfBytes;
+constexpr int kOffRec = kOffPart + kWorkers * kTok * kRec * 4;
+constexpr int kSkWords = kMaxIters * 8 * 8;           // normaliser scratch per coefficient warp: [iter][8][8 lanes]
+constexpr int kOffSk = kOffRec + kSlots * kTok * kRec * 4;
+constexpr int kOffBar = kOffSk + kCoefWarps * kSkWords * 4;
+constexpr int kOffTmem = kOffBar + (2 * kStages + 2 * kDxBufs) * 8;
+constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kOffBar % 8 == 0, "mbarrier alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
-constexpr int kBarPartFree = 1, kBarPart = 2 /*,3*/, kBarRed = 4 /*,5*/, kBarCoef = 6 /*,7*/;
+constexpr int kBarW1 = 1, kBarW2 = 2, kBarRed = 4 /*,5,6*/, kBarCoef = 7 /*,8,9*/;
 constexpr int kAccum = kL + 3;                        // dbias[24], dalpha[3]
-constexpr int kSkWords = kMaxIters * 8 * 32;          // normaliser scratch per coefficient warp: [iter][8][lane]
 
 struct BwdParams {
     const float* phi;
@@ -59,8 +67,7 @@ struct BwdParams {
     const float* alpha;
     const float* scale;
     float* e_out;          // [T,24] fp32
-    float* cta_accum;      // [grid, 2, 27]
-    float* sk_scratch;     // [grid, 2, kSkWords]  (L2-resident: rewritten every pass)
+    float* cta_accum;      // [grid, 3, 27]
     int64_t T;
     int num_tiles;
     int sk_iters;
@@ -92,24 +99,27 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// The static work order of one CTA.  Step s runs pass 1 of superblock s interleaved with pass 2 of superblock
-// s - kLag, tile by tile; every role walks the same sequence, item q lives in stage q % kStages.
-struct ItemIter {
-    int s, i, ph, n_local, nsb;
-    __device__ void init(int n) { n_local = n; nsb = (n + kSb - 1) / kSb; s = 0; i = 0; ph = -1; next(); }
-    __device__ bool valid() const { return s < nsb + kLag; }
-    __device__ int sb() const { return ph == 0 ? s : s - kLag; }
-    __device__ int tile() const { return sb() * kSb + i; }
-    __device__ void next() {
-        for (;;) {
-            if (++ph == 2) { ph = 0; if (++i == kSb) { i = 0; ++s; } }
-            if (s >= nsb + kLag) return;
-            const int b = ph == 0 ? s : s - kLag;
-            if (b < 0 || b >= nsb || b * kSb + i >= n_local) continue;
-            return;
-        }
-    }
-};
+// ---- tensor memory as a register parking lot (tcgen05.st / tcgen05.ld, 32 lanes x 32 bit x N columns)
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
@@ -117,23 +127,27 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     extern __shared__ __align__(1024) uint8_t smem[];
     if (smem_u32(smem) & 1023u) __trap();
     float* part = reinterpret_cast<float*>(smem + kOffPart);
-    float* red = reinterpret_cast<float*>(smem + kOffRed);
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffBar);
-    uint64_t* bar_done = bar_full + kStages;
+    float* rec = reinterpret_cast<float*>(smem + kOffRec);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffBar);     // TMA load landed
+    uint64_t* bar_free = bar_full + kStages;                              // P1 done with the stage
+    uint64_t* bar_dx_full = bar_free + kStages;                           // dx staged by the workers
+    uint64_t* bar_dx_free = bar_dx_full + kDxBufs;                        // staged dx drained by the TMA store
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int nsb = (n_local + kSb - 1) / kSb;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_done[s], kWorkerThreads);
-        }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_free[s], kWorkerThreads); }
+        for (int s = 0; s < kDxBufs; ++s) { mbar_init(&bar_dx_full[s], kWorkerThreads); mbar_init(&bar_dx_free[s], 1); }
         fence_mbar_init();
     }
+    if (warp == kWorkers + 1) tmem_alloc(tmem_slot, kTmemCols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
 
     if (warp >= kWorkers) {
       reg_dealloc<kRoleRegs>();
@@ -143,82 +157,55 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             tma_prefetch_desc(&tmap_x);
             tma_prefetch_desc(&tmap_dy);
             tma_prefetch_desc(&tmap_dx);
-            const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
-            auto load_item = [&](const ItemIter& w, int q) {
-                const int s = q % kStages;
-                const int row0 = ((int)blockIdx.x + w.tile() * (int)gridDim.x) * (kTok * kN);
+            auto load_tile = [&](int it) {
+                const int s = it % kStages;
+                const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * (kTok * kN);
                 uint8_t* st = smem + s * kStageBytes;
                 mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
-                // pass 1 asks L2 to keep the lines (they come back kLag superblocks later), pass 2 releases them
-                const uint64_t pol = w.ph == 0 ? pol_keep : pol_drop;
 #pragma unroll
                 for (int cb = 0; cb < kC / 64; ++cb) {
-                    tma_load_2d_hint(st + cb * kBoxBytes, &tmap_x, &bar_full[s], cb * 64, row0, pol);
-                    tma_load_2d_hint(st + kHalfBytes + cb * kBoxBytes, &tmap_dy, &bar_full[s], cb * 64, row0, pol);
+                    tma_load_2d(st + cb * kBoxBytes, &tmap_x, &bar_full[s], cb * 64, row0);
+                    tma_load_2d(st + kHalfBytes + cb * kBoxBytes, &tmap_dy, &bar_full[s], cb * 64, row0);
                 }
             };
-            ItemIter ld, cur;
-            ld.init(n_local);
-            cur.init(n_local);
-            int q_ld = 0;
-            for (; q_ld < kStages && ld.valid(); ++q_ld, ld.next()) load_item(ld, q_ld);
-            for (int q = 0; cur.valid(); ++q, cur.next()) {
-                const int s = q % kStages;
-                mbar_wait(&bar_done[s], (q / kStages) & 1);
-                if (cur.ph == 1) {
-                    const int row0 = ((int)blockIdx.x + cur.tile() * (int)gridDim.x) * (kTok * kN);
+            for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
+            for (int j = 0; j < n_local + kSlots; ++j) {
+                const int k = j - kSlots;                       // tile whose dx is staged in this iteration
+                if (k >= 0) {
+                    const int b = k % kDxBufs;
+                    mbar_wait(&bar_dx_full[b], (k / kDxBufs) & 1);
+                    const int row0 = ((int)blockIdx.x + k * (int)gridDim.x) * (kTok * kN);
 #pragma unroll
                     for (int cb = 0; cb < kC / 64; ++cb)
-                        tma_store_2d_hint(&tmap_dx, smem + s * kStageBytes + kHalfBytes + cb * kBoxBytes, cb * 64, row0, pol_drop);
+                        tma_store_2d(&tmap_dx, smem + kOffDx + b * kHalfBytes + cb * kBoxBytes, cb * 64, row0);
                     bulk_commit();
                     bulk_wait_read<0>();
+                    mbar_arrive(&bar_dx_free[b]);
                 }
-                if (ld.valid()) { load_item(ld, q_ld); ++q_ld; ld.next(); }
+                if (j < n_local && j + kStages < n_local) {
+                    mbar_wait(&bar_free[j % kStages], (j / kStages) & 1);     // P1(j) has released its stage
+                    load_tile(j + kStages);
+                }
             }
             bulk_wait<0>();
         }
-      } else if (warp == kWorkers + 3) {
-        // ===================================================== reducer: fixed-order (tree) sum of the 16 split-K
-        // partials of each pass-1 tile into the superblock's record buffer
-        if (n_local > 0) bar_arrive(kBarPartFree, kWorkerThreads + 32);      // `part` starts out free
-        for (int it = 0; it < n_local; ++it) {
-            const int sb = it / kSb, ti = it - sb * kSb;
-            bar_sync(kBarPart + (it & 1), kWorkerThreads + 32);
-            float* dst = red + ((sb % kRedSlots) * kSb + ti) * kTok * kRec;
-            for (int idx = lane; idx < kTok * kRec; idx += 32) {
-                const int col = idx % kRec;
-                if (col > kRecSS && col < kRecG) continue;
-                float v[kWorkers];
-#pragma unroll
-                for (int ww = 0; ww < kWorkers; ++ww) v[ww] = part[ww * kTok * kRec + idx];
-#pragma unroll
-                for (int st = 1; st < kWorkers; st <<= 1)
-#pragma unroll
-                    for (int ww = 0; ww < kWorkers; ww += 2 * st) v[ww] += v[ww + st];
-                dst[idx] = v[0];
-            }
-            __threadfence_block();
-            if (it + 1 < n_local) bar_arrive(kBarPartFree, kWorkerThreads + 32);
-            if (ti == kSb - 1 || it == n_local - 1) bar_arrive(kBarRed + (sb & 1), 64);
-        }
       } else {
-        // ===================================================== coefficient warps A (warp 16) and B (warp 18):
-        // superblocks alternate between them; one lane per token, the 4x4 block in packed fp32x2 registers
+        // ===================================================== coefficient warps 0..2 (warps 16, 18, 19): tile k
+        // goes to warp k % 3; one lane per token (8 per pass), the 4x4 block in packed fp32x2 registers
         // (row i: R[i] = (p_i0,p_i1), S[i] = (p_i2,p_i3)), no shuffles inside the sweeps.  Lane k < 27 also
         // owns component k of the dbias / dalpha sums.
-        const int cw = (warp - kWorkers) >> 1;
+        const int cw = warp == kWorkers ? 0 : warp - (kWorkers + 1);
         const float a_pre = __ldg(p.alpha + 0), a_post = __ldg(p.alpha + 1), a_res = __ldg(p.alpha + 2);
         float my_acc = 0.f;
-        float* skl = p.sk_scratch + ((size_t)blockIdx.x * 2 + cw) * kSkWords + lane;
-        for (int sb = cw; sb < nsb; sb += 2) {
-            bar_sync(kBarRed + cw, 64);
-            const int tiles = min(kSb, n_local - sb * kSb);
-            const bool act = lane < tiles * kTok;
+        float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + (lane & 7);
+        for (int it = cw; it < n_local; it += kCoefWarps) {
+            bar_sync(kBarRed + cw, kWorkerThreads + 32);
+            const bool act = lane < kTok;
             float dlv[kAccum];
 #pragma unroll
             for (int k = 0; k < kAccum; ++k) dlv[k] = 0.f;
             if (act) {
-                float* r = red + ((sb % kRedSlots) * kSb * kTok + lane) * kRec;
+                float* r = rec + ((it % kSlots) * kTok + lane) * kRec;
                 const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(r[kRecSS], 1.0f / kRow, p.eps_rms)));
                 float hpre[kN], hpost[kN];
 #pragma unroll
@@ -239,17 +226,17 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     R[i] = pk2(e0 * r4, e1 * r4);
                     S[i] = pk2(e2 * r4, e3 * r4);
                 }
-                // ---- forward Sinkhorn; the normalisers go to the (L2-resident) scratch
+                // ---- forward Sinkhorn; the normalisers are kept for the reverse sweep
                 const float eps = p.eps_sk;
                 const u64 eps2 = pk2(eps, eps);
                 for (int k = 0; k < p.sk_iters; ++k) {
-                    float* sk = skl + k * 256;
+                    float* sk = skl + k * 64;
 #pragma unroll
                     for (int i = 0; i < kN; ++i) {
                         float a, b;
                         upk2(add2(R[i], S[i]), a, b);
                         const float dr = (a + b) + eps;
-                        __stcg(sk + i * 32, dr);
+                        sk[i * 8] = dr;
                         const float rr = rcp_approx(dr);
                         const u64 rr2 = pk2(rr, rr);
                         R[i] = mul2(R[i], rr2);
@@ -260,7 +247,7 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     float c0, c1, c2, c3;
                     upk2(c01, c0, c1);
                     upk2(c23, c2, c3);
-                    __stcg(sk + 4 * 32, c0); __stcg(sk + 5 * 32, c1); __stcg(sk + 6 * 32, c2); __stcg(sk + 7 * 32, c3);
+                    sk[4 * 8] = c0; sk[5 * 8] = c1; sk[6 * 8] = c2; sk[7 * 8] = c3;
                     const u64 ci01 = pk2(rcp_approx(c0), rcp_approx(c1)), ci23 = pk2(rcp_approx(c2), rcp_approx(c3));
 #pragma unroll
                     for (int i = 0; i < kN; ++i) { R[i] = mul2(R[i], ci01); S[i] = mul2(S[i], ci23); }
@@ -297,7 +284,7 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 float nx[8];
                 if (p.sk_iters > 0) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) nx[c] = __ldcg(skl + (p.sk_iters - 1) * 256 + c * 32);
+                    for (int c = 0; c < 8; ++c) nx[c] = skl[(p.sk_iters - 1) * 64 + c * 8];
                 }
                 for (int k = p.sk_iters - 1; k >= 0; --k) {
                     float cu[8];
@@ -305,7 +292,7 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     for (int c = 0; c < 8; ++c) cu[c] = nx[c];
                     if (k > 0) {
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) nx[c] = __ldcg(skl + (k - 1) * 256 + c * 32);
+                        for (int c = 0; c < 8; ++c) nx[c] = skl[(k - 1) * 64 + c * 8];
                     }
                     // column step y = x / c:  dx = (dy - sum_i dy*y) / c ;  x = y * c
                     u64 q01 = mul2(D[0], R[0]), q23 = mul2(E[0], S[0]);
@@ -361,8 +348,7 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     *reinterpret_cast<uint4*>(ew + 4 * q) = make_uint4(pack_bf16(ev[8 * q], ev[8 * q + 1]), pack_bf16(ev[8 * q + 2], ev[8 * q + 3]),
                                                                        pack_bf16(ev[8 * q + 4], ev[8 * q + 5]), pack_bf16(ev[8 * q + 6], ev[8 * q + 7]));
                 r[kRecKappa] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
-                const int it = sb * kSb + (lane >> 3);
-                const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + (lane & 7);
+                const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + lane;
                 if (tok < p.T) {
                     float4* o = reinterpret_cast<float4*>(p.e_out + tok * kL);
 #pragma unroll
@@ -379,7 +365,7 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 if (lane == k) my_acc += v;
             }
         }
-        if (lane < kAccum) p.cta_accum[((size_t)blockIdx.x * 2 + cw) * kAccum + lane] = my_acc;
+        if (lane < kAccum) p.cta_accum[((size_t)blockIdx.x * kCoefWarps + cw) * kAccum + lane] = my_acc;
       }
     } else {
         // ===================================================== worker warps
@@ -413,26 +399,83 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
         const int lm = lane >> 3, lr = lane & 7;            // ldmatrix: matrix index / row of an x4 load
         const uint32_t stage0 = smem_u32(smem);
+        // this thread's parking columns: TMEM lane = 32*(warp%4) + lane (the only quadrant the warp may touch),
+        // 32 columns per (slot, warp/4): x words [0,16), dy words [16,32)
+        const uint32_t tm_thread = tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)((w >> 2) * 32);
 
-        ItemIter itx;
-        itx.init(n_local);
-        int p1_count = 0;
-        for (int q = 0; itx.valid(); ++q, itx.next()) {
-            const int s = q % kStages;
-            const uint32_t sbase = stage0 + s * kStageBytes;
-            mbar_wait(&bar_full[s], (q / kStages) & 1);
-            if (itx.ph == 0) {
-                // ============ pass 1: raw^T = W^T x^T (tokens are the MMA N), sum x^2 on the diagonal of x x^T
-                float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, accs[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < n_local + kSlots; ++j) {
+            const int k = j - kSlots;
+            if (k >= 0) {
+                // ============ P3: dx for token g of tile k, operands back from tensor memory
+                bar_sync(kBarCoef + k % kCoefWarps, kWorkerThreads + 32);                // the tile's coefficients are ready
+                const float* c = rec + ((k % kSlots) * kTok + g) * kRec;
+                const uint32_t* ew = reinterpret_cast<const uint32_t*>(c);
+                const uint32_t ea0 = ew[t], ea2 = ew[t + 4], eb0 = ew[t + 8];     // e[2t..], e[2t+8..], e[2t+16..]
+                const float kappa = c[kRecKappa];
+                const uint32_t tm = tm_thread + (uint32_t)((k % kSlots) * 128);
+                uint32_t xr[16], dyr[16];
+                tmem_ld16(tm, xr);
+                tmem_ld16(tm + 16, dyr);
+                tmem_wait_ld();
+                const int b = k % kDxBufs;
+                mbar_wait(&bar_dx_free[b], ((k / kDxBufs) & 1) ^ 1);     // staging buffer drained (first use passes)
+                const uint32_t dbase = stage0 + kOffDx + b * kHalfBytes;
 #pragma unroll
-                for (int j = 0; j < kN; ++j) {
-                    const uint4 xv = lds128(sbase + off[j]);
-                    mma_bf16_16816(acc0, bfrag[j][0][0][0], bfrag[j][0][1][0], bfrag[j][0][0][1], bfrag[j][0][1][1], xv.x, xv.y);
-                    mma_bf16_16816(acc1, bfrag[j][0][2][0], 0u, bfrag[j][0][2][1], 0u, xv.x, xv.y);
-                    mma_bf16_16816(accs, xv.x, 0u, xv.y, 0u, xv.x, xv.y);
-                    mma_bf16_16816(acc0, bfrag[j][1][0][0], bfrag[j][1][1][0], bfrag[j][1][0][1], bfrag[j][1][1][1], xv.z, xv.w);
-                    mma_bf16_16816(acc1, bfrag[j][1][2][0], 0u, bfrag[j][1][2][1], 0u, xv.z, xv.w);
-                    mma_bf16_16816(accs, xv.z, 0u, xv.w, 0u, xv.z, xv.w);
+                for (int jj = 0; jj < kN; ++jj) {
+                    const float4 mt = *reinterpret_cast<const float4*>(c + kRecG + 4 * jj);       // M[0..3][jj]
+                    uint32_t out[4];
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq)
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            // dx_proj for K index (jj, 32w + 8t + 4qq + 2rr + {0,1}) of token g: e . W^T
+                            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                            mma_bf16_16816(acc, ea0, 0u, ea2, 0u, movmatrix_trans(bfrag[jj][qq][0][rr]), movmatrix_trans(bfrag[jj][qq][1][rr]));
+                            mma_bf16_16816(acc, eb0, 0u, 0u, 0u, movmatrix_trans(bfrag[jj][qq][2][rr]), 0u);
+                            const int e = 2 * qq + rr;
+                            float lo = fmaf(kappa, bf16lo(xr[4 * jj + e]), acc[0]);
+                            float hi = fmaf(kappa, bf16hi(xr[4 * jj + e]), acc[1]);
+                            lo = fmaf(mt.x, bf16lo(dyr[e]), lo);      hi = fmaf(mt.x, bf16hi(dyr[e]), hi);
+                            lo = fmaf(mt.y, bf16lo(dyr[4 + e]), lo);  hi = fmaf(mt.y, bf16hi(dyr[4 + e]), hi);
+                            lo = fmaf(mt.z, bf16lo(dyr[8 + e]), lo);  hi = fmaf(mt.z, bf16hi(dyr[8 + e]), hi);
+                            lo = fmaf(mt.w, bf16lo(dyr[12 + e]), lo); hi = fmaf(mt.w, bf16hi(dyr[12 + e]), hi);
+                            out[e] = pack_bf16(lo, hi);
+                        }
+                    sts128(dbase + off[jj], make_uint4(out[0], out[1], out[2], out[3]));
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&bar_dx_full[b]);
+            }
+            if (j < n_local) {
+                // ============ P1: raw^T = W^T x^T (tokens are the MMA N), sum x^2 on the diagonal of x x^T
+                const int s = j % kStages;
+                const uint32_t sbase = stage0 + s * kStageBytes;
+                const uint32_t tm = tm_thread + (uint32_t)((j % kSlots) * 128);
+                mbar_wait(&bar_full[s], (j / kStages) & 1);
+                float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, accs[4] = {0.f, 0.f, 0.f, 0.f};
+                {
+                    uint32_t xr[16];
+#pragma unroll
+                    for (int jj = 0; jj < kN; ++jj) {
+                        const uint4 xv = lds128(sbase + off[jj]);
+                        xr[4 * jj] = xv.x; xr[4 * jj + 1] = xv.y; xr[4 * jj + 2] = xv.z; xr[4 * jj + 3] = xv.w;
+                        mma_bf16_16816(acc0, bfrag[jj][0][0][0], bfrag[jj][0][1][0], bfrag[jj][0][0][1], bfrag[jj][0][1][1], xv.x, xv.y);
+                        mma_bf16_16816(acc1, bfrag[jj][0][2][0], 0u, bfrag[jj][0][2][1], 0u, xv.x, xv.y);
+                        mma_bf16_16816(accs, xv.x, 0u, xv.y, 0u, xv.x, xv.y);
+                        mma_bf16_16816(acc0, bfrag[jj][1][0][0], bfrag[jj][1][1][0], bfrag[jj][1][0][1], bfrag[jj][1][1][1], xv.z, xv.w);
+                        mma_bf16_16816(acc1, bfrag[jj][1][2][0], 0u, bfrag[jj][1][2][1], 0u, xv.z, xv.w);
+                        mma_bf16_16816(accs, xv.z, 0u, xv.w, 0u, xv.z, xv.w);
+                    }
+                    tmem_st16(tm, xr);                                   // park x
+                }
+                {
+                    uint32_t dyr[16];
+#pragma unroll
+                    for (int ii = 0; ii < kN; ++ii) {
+                        const uint4 v = lds128(sbase + kHalfBytes + off[ii]);
+                        dyr[4 * ii] = v.x; dyr[4 * ii + 1] = v.y; dyr[4 * ii + 2] = v.z; dyr[4 * ii + 3] = v.w;
+                    }
+                    tmem_st16(tm + 16, dyr);                             // park dy
                 }
                 // G = dy x^T per token: rows (token, i) of dy against rows (token, j) of x, block diagonal
                 float gacc[2][2][4];
@@ -460,8 +503,9 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                         mma_bf16_16816(gacc[m][1], a0, a1, a2, a3, bx[2 * m + 1][0], bx[2 * m + 1][1]);
                     }
                 }
-                mbar_arrive(&bar_done[s]);                        // every read of the stage has landed in registers
-                bar_sync(kBarPartFree, kWorkerThreads + 32);      // reducer finished reading the previous partials
+                tmem_wait_st();
+                mbar_arrive(&bar_free[s]);                        // every read of the stage has landed in registers
+                bar_sync(kBarW1, kWorkerThreads);                 // the previous tile's reduction has read `part`
                 {
                     float* pw = part + (size_t)w * kTok * kRec;
                     pw[(2 * t) * kRec + g] = acc0[0];      pw[(2 * t + 1) * kRec + g] = acc0[1];
@@ -469,62 +513,39 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     pw[(2 * t) * kRec + 16 + g] = acc1[0]; pw[(2 * t + 1) * kRec + 16 + g] = acc1[1];
                     if (t == (g >> 1)) pw[g * kRec + kRecSS] = accs[g & 1];       // diagonal of x x^T
                     if ((g >> 2) == (t >> 1)) {
-                        const int i = g & 3, jj = 2 * (t & 1);
+                        const int i = g & 3, jq = 2 * (t & 1);
 #pragma unroll
                         for (int m = 0; m < 2; ++m) {
                             const int tokA = 4 * m + (g >> 2), tokB = 4 * m + 2 + (g >> 2);
-                            *reinterpret_cast<float2*>(pw + tokA * kRec + kRecG + 4 * i + jj) = make_float2(gacc[m][0][0], gacc[m][0][1]);
-                            *reinterpret_cast<float2*>(pw + tokB * kRec + kRecG + 4 * i + jj) = make_float2(gacc[m][1][2], gacc[m][1][3]);
+                            *reinterpret_cast<float2*>(pw + tokA * kRec + kRecG + 4 * i + jq) = make_float2(gacc[m][0][0], gacc[m][0][1]);
+                            *reinterpret_cast<float2*>(pw + tokB * kRec + kRecG + 4 * i + jq) = make_float2(gacc[m][1][2], gacc[m][1][3]);
                         }
                     }
                 }
+                bar_sync(kBarW2, kWorkerThreads);
+                // fixed-order (tree) sum of the 16 split-K partials into the tile's record slot
+                if (threadIdx.x < kTok * kRec) {
+                    const int col = threadIdx.x % kRec;
+                    if (!(col > kRecSS && col < kRecG)) {
+                        float v[kWorkers];
+#pragma unroll
+                        for (int ww = 0; ww < kWorkers; ++ww) v[ww] = part[ww * kTok * kRec + threadIdx.x];
+#pragma unroll
+                        for (int st = 1; st < kWorkers; st <<= 1)
+#pragma unroll
+                            for (int ww = 0; ww < kWorkers; ww += 2 * st) v[ww] += v[ww + st];
+                        rec[(j % kSlots) * kTok * kRec + threadIdx.x] = v[0];
+                    }
+                }
                 __threadfence_block();
-                bar_arrive(kBarPart + (p1_count & 1), kWorkerThreads + 32);
-                ++p1_count;
-            } else {
-                // ============ pass 2: dx for token g of this tile
-                const int sb = itx.sb();
-                if (itx.i == 0) bar_sync(kBarCoef + (sb & 1), kWorkerThreads + 32);     // superblock's coefficients are ready
-                const float* c = red + (((sb % kRedSlots) * kSb + itx.i) * kTok + g) * kRec;
-                const uint32_t* ew = reinterpret_cast<const uint32_t*>(c);
-                const uint32_t ea0 = ew[t], ea2 = ew[t + 4], eb0 = ew[t + 8];     // e[2t..], e[2t+8..], e[2t+16..]
-                const float kappa = c[kRecKappa];
-                uint32_t dyr[kN][4];
-#pragma unroll
-                for (int ii = 0; ii < kN; ++ii) {
-                    const uint4 v = lds128(sbase + kHalfBytes + off[ii]);
-                    dyr[ii][0] = v.x; dyr[ii][1] = v.y; dyr[ii][2] = v.z; dyr[ii][3] = v.w;
-                }
-#pragma unroll
-                for (int j = 0; j < kN; ++j) {
-                    const float4 mt = *reinterpret_cast<const float4*>(c + kRecG + 4 * j);       // M[0..3][j]
-                    const uint4 xv = lds128(sbase + off[j]);
-                    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-                    uint32_t out[4];
-#pragma unroll
-                    for (int qq = 0; qq < 2; ++qq)
-#pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            // dx_proj for K index (j, 32w + 8t + 4qq + 2rr + {0,1}) of token g: e . W^T
-                            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                            mma_bf16_16816(acc, ea0, 0u, ea2, 0u, movmatrix_trans(bfrag[j][qq][0][rr]), movmatrix_trans(bfrag[j][qq][1][rr]));
-                            mma_bf16_16816(acc, eb0, 0u, 0u, 0u, movmatrix_trans(bfrag[j][qq][2][rr]), 0u);
-                            const int e = 2 * qq + rr;
-                            float lo = fmaf(kappa, bf16lo(xw[e]), acc[0]);
-                            float hi = fmaf(kappa, bf16hi(xw[e]), acc[1]);
-                            lo = fmaf(mt.x, bf16lo(dyr[0][e]), lo); hi = fmaf(mt.x, bf16hi(dyr[0][e]), hi);
-                            lo = fmaf(mt.y, bf16lo(dyr[1][e]), lo); hi = fmaf(mt.y, bf16hi(dyr[1][e]), hi);
-                            lo = fmaf(mt.z, bf16lo(dyr[2][e]), lo); hi = fmaf(mt.z, bf16hi(dyr[2][e]), hi);
-                            lo = fmaf(mt.w, bf16lo(dyr[3][e]), lo); hi = fmaf(mt.w, bf16hi(dyr[3][e]), hi);
-                            out[e] = pack_bf16(lo, hi);
-                        }
-                    sts128(sbase + kHalfBytes + off[j], make_uint4(out[0], out[1], out[2], out[3]));
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(&bar_done[s]);
+                bar_arrive(kBarRed + j % kCoefWarps, kWorkerThreads + 32);
             }
         }
     }
+    // tensor memory is released by the warp that allocated it, after every parked register has been read back
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kWorkers + 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ B2: dW = x^T E
@@ -654,7 +675,7 @@ mhc_stream_bwd_finalize_kernel(const float* __restrict__ dw_part, int dw_ctas, c
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct BwdWs {
-    float* e; float* dw_part; float* cta_accum; float* sk_scratch;
+    float* e; float* dw_part; float* cta_accum;
     size_t total;
 };
 BwdWs carve(void* base, int64_t T, int ctas) {
@@ -663,8 +684,7 @@ BwdWs carve(void* base, int64_t T, int ctas) {
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return reinterpret_cast<uint8_t*>(base) + o; };
     w.e = reinterpret_cast<float*>(take((size_t)T * kL * 4));
     w.dw_part = reinterpret_cast<float*>(take((size_t)ctas * kRow * kL * 4));
-    w.cta_accum = reinterpret_cast<float*>(take((size_t)ctas * 2 * kAccum * 4));
-    w.sk_scratch = reinterpret_cast<float*>(take((size_t)ctas * 2 * kSkWords * 4));
+    w.cta_accum = reinterpret_cast<float*>(take((size_t)ctas * kCoefWarps * kAccum * 4));
     w.total = off;
     return w;
 }
@@ -716,7 +736,7 @@ extern "C" int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* ph
         }
         BwdParams p;
         p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale;
-        p.e_out = ws.e; p.cta_accum = ws.cta_accum; p.sk_scratch = ws.sk_scratch;
+        p.e_out = ws.e; p.cta_accum = ws.cta_accum;
         p.T = T;
         p.num_tiles = (int)((T + kTok - 1) / kTok);
         p.sk_iters = sk_iters; p.eps_rms = eps_rms; p.eps_sk = eps_sk;
@@ -737,7 +757,7 @@ extern "C" int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* ph
         if (rc2) return rc2;
     }
     timer_begin(3, stream);
-    mhc_stream_bwd_finalize_kernel<<<kRow / 8, 256, 0, stream>>>(ws.dw_part, grid2, ws.cta_accum, 2 * grid1, phi, scale, dphi,
+    mhc_stream_bwd_finalize_kernel<<<kRow / 8, 256, 0, stream>>>(ws.dw_part, grid2, ws.cta_accum, kCoefWarps * grid1, phi, scale, dphi,
                                                                  dscale, dbias, dalpha);
     timer_end(3, stream);
     count_launch();
