@@ -144,7 +144,10 @@ def stream_mhc_coeffs(x: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor,
     inv_rms = 1.0 / torch.sqrt(torch.mean(xf * xf, dim=-1, keepdim=True) + eps)  # :451
     w = rms_scale.to(dtype)[:, None] * phi.to(dtype)
     if not split_phi:
-        w = w.to(torch.bfloat16).to(dtype)
+        # bf16 rounding of the operand with a straight-through gradient kept in `dtype` (a plain
+        # .to(bf16).to(dtype) would also round the GRADIENT to bf16 on its way back).  r - w is exact
+        # (Sterbenz), so w + (r - w) == r bit for bit.
+        w = w + (w.to(torch.bfloat16).to(dtype) - w).detach()
     raw = (xf @ w) * inv_rms                                  # == rms_norm(x) @ phi
     alpha = alpha.to(dtype)
     a = torch.cat([alpha[0].expand(n), alpha[1].expand(n), alpha[2].expand(n * n)])

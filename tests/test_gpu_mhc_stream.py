@@ -160,7 +160,7 @@ def check_bwd(inp, dy, got, tag=""):
     for name in ("dphi", "dbias", "dalpha", "dscale"):
         a, b = got[name].double(), ref[name].double()
         rel = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
-        assert rel < 2e-3, f"{tag} {name} relative error {rel:.2e}"
+        assert rel < 3e-4, f"{tag} {name} relative error {rel:.2e}"
     return ulps
 
 
