@@ -50,7 +50,7 @@ constexpr uint32_t kTmemCols = 512;
 constexpr int kOffDx = kStages * kStageBytes;
 constexpr int kOffPart = kOffDx + kDxBufs * kHalfBytes;
 constexpr int kOffRec = kOffPart + kWorkers * kTok * kRec * 4;
-constexpr int kSkWords = kMaxIters * 8 * 8;           // normaliser scratch per coefficient warp: [iter][8][8 lanes]
+constexpr int kSkWords = kTok * kMaxIters * 8;         // normaliser scratch per coefficient warp: [token][iter][row d x4 | col d x4]
 constexpr int kOffSk = kOffRec + kSlots * kTok * kRec * 4;
 constexpr int kOffBar = kOffSk + kCoefWarps * kSkWords * 4;
 constexpr int kOffTmem = kOffBar + (2 * kStages + 2 * kDxBufs) * 8;
@@ -191,181 +191,159 @@ mhc_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
       } else {
         // ===================================================== coefficient warps 0..2 (warps 16, 18, 19): tile k
-        // goes to warp k % 3; one lane per token (8 per pass), the 4x4 block in packed fp32x2 registers
-        // (row i: R[i] = (p_i0,p_i1), S[i] = (p_i2,p_i3)), no shuffles inside the sweeps.  Lane k < 27 also
-        // owns component k of the dbias / dalpha sums.
+        // goes to warp k % 3.  Four lanes per token: lane (tk, i) owns row i of the token's 4x4 block as two
+        // packed fp32x2 registers A = (p_i0,p_i1), B = (p_i2,p_i3) and gate i of H_pre / H_post.  Row sums are
+        // local, column sums take two xor-shuffles inside the 4-lane group.
         const int cw = warp == kWorkers ? 0 : warp - (kWorkers + 1);
+        const int tk = lane >> 2, i = lane & 3, gbase = lane & ~3;
+        const float b_pre = __ldg(p.bias + i), b_post = __ldg(p.bias + kN + i);
+        const float4 b_res = __ldg(reinterpret_cast<const float4*>(p.bias + 2 * kN) + i);
         const float a_pre = __ldg(p.alpha + 0), a_post = __ldg(p.alpha + 1), a_res = __ldg(p.alpha + 2);
-        float my_acc = 0.f;
-        float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + (lane & 7);
+        const float eps = p.eps_sk;
+        const u64 eps2 = pk2(eps, eps);
+        float acc_b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dbias: pre_i, post_i, res_i0..3
+        float acc_a[3] = {0.f, 0.f, 0.f};                  // dalpha terms of this lane
+        float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + tk * (kMaxIters * 8);
+        auto gsum2 = [](u64 v) {                           // sum over the 4 lanes of a group, both halves
+            float a, b;
+            upk2(v, a, b);
+            a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
+            return pk2(a, b);
+        };
         for (int it = cw; it < n_local; it += kCoefWarps) {
             bar_sync(kBarRed + cw, kWorkerThreads + 32);
-            const bool act = lane < kTok;
-            float dlv[kAccum];
-#pragma unroll
-            for (int k = 0; k < kAccum; ++k) dlv[k] = 0.f;
-            if (act) {
-                float* r = rec + ((it % kSlots) * kTok + lane) * kRec;
-                const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(r[kRecSS], 1.0f / kRow, p.eps_rms)));
-                float hpre[kN], hpost[kN];
-#pragma unroll
-                for (int j = 0; j < kN; ++j) {
-                    hpre[j] = sigmoid_f32(fmaf(a_pre, r[j] * inv_rms, __ldg(p.bias + j)));
-                    hpost[j] = 2.0f * sigmoid_f32(fmaf(a_post, r[kN + j] * inv_rms, __ldg(p.bias + kN + j)));
-                }
-                u64 R[kN], S[kN];
-#pragma unroll
-                for (int i = 0; i < kN; ++i) {
-                    const float l0 = fmaf(a_res, r[2 * kN + 4 * i + 0] * inv_rms, __ldg(p.bias + 2 * kN + 4 * i + 0));
-                    const float l1 = fmaf(a_res, r[2 * kN + 4 * i + 1] * inv_rms, __ldg(p.bias + 2 * kN + 4 * i + 1));
-                    const float l2 = fmaf(a_res, r[2 * kN + 4 * i + 2] * inv_rms, __ldg(p.bias + 2 * kN + 4 * i + 2));
-                    const float l3 = fmaf(a_res, r[2 * kN + 4 * i + 3] * inv_rms, __ldg(p.bias + 2 * kN + 4 * i + 3));
-                    const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
-                    const float e0 = fast_exp(l0 - mx), e1 = fast_exp(l1 - mx), e2 = fast_exp(l2 - mx), e3 = fast_exp(l3 - mx);
-                    const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
-                    R[i] = pk2(e0 * r4, e1 * r4);
-                    S[i] = pk2(e2 * r4, e3 * r4);
-                }
-                // ---- forward Sinkhorn; the normalisers are kept for the reverse sweep
-                const float eps = p.eps_sk;
-                const u64 eps2 = pk2(eps, eps);
-                for (int k = 0; k < p.sk_iters; ++k) {
-                    float* sk = skl + k * 64;
-#pragma unroll
-                    for (int i = 0; i < kN; ++i) {
-                        float a, b;
-                        upk2(add2(R[i], S[i]), a, b);
-                        const float dr = (a + b) + eps;
-                        sk[i * 8] = dr;
-                        const float rr = rcp_approx(dr);
-                        const u64 rr2 = pk2(rr, rr);
-                        R[i] = mul2(R[i], rr2);
-                        S[i] = mul2(S[i], rr2);
-                    }
-                    const u64 c01 = add2(add2(add2(R[0], R[1]), add2(R[2], R[3])), eps2);
-                    const u64 c23 = add2(add2(add2(S[0], S[1]), add2(S[2], S[3])), eps2);
-                    float c0, c1, c2, c3;
-                    upk2(c01, c0, c1);
-                    upk2(c23, c2, c3);
-                    sk[4 * 8] = c0; sk[5 * 8] = c1; sk[6 * 8] = c2; sk[7 * 8] = c3;
-                    const u64 ci01 = pk2(rcp_approx(c0), rcp_approx(c1)), ci23 = pk2(rcp_approx(c2), rcp_approx(c3));
-#pragma unroll
-                    for (int i = 0; i < kN; ++i) { R[i] = mul2(R[i], ci01); S[i] = mul2(S[i], ci23); }
-                }
-                // ---- gradients of the gates from G = dy x^T; D/E start as dP = G
-                u64 D[kN], E[kN];
-                float dl_post[kN];
-#pragma unroll
-                for (int j = 0; j < kN; ++j) dlv[j] = 0.f;
-#pragma unroll
-                for (int i = 0; i < kN; ++i) {
-                    const float4 gq = *reinterpret_cast<const float4*>(r + kRecG + 4 * i);
-                    D[i] = pk2(gq.x, gq.y);
-                    E[i] = pk2(gq.z, gq.w);
-                    const float dhpost = fmaf(gq.w, hpre[3], fmaf(gq.z, hpre[2], fmaf(gq.y, hpre[1], gq.x * hpre[0])));
-                    dl_post[i] = dhpost * hpost[i] * (1.0f - 0.5f * hpost[i]);
-                    dlv[0] = fmaf(gq.x, hpost[i], dlv[0]); dlv[1] = fmaf(gq.y, hpost[i], dlv[1]);
-                    dlv[2] = fmaf(gq.z, hpost[i], dlv[2]); dlv[3] = fmaf(gq.w, hpost[i], dlv[3]);
-                }
-#pragma unroll
-                for (int j = 0; j < kN; ++j) { dlv[j] = dlv[j] * hpre[j] * (1.0f - hpre[j]); dlv[kN + j] = dl_post[j]; }
-                // ---- M^T[j][i] = P[i][j] + hpost[i] hpre[j] replaces G in the record (pass 2 reads it)
-                {
-                    float pr[kN][kN];
-#pragma unroll
-                    for (int i = 0; i < kN; ++i) { upk2(R[i], pr[i][0], pr[i][1]); upk2(S[i], pr[i][2], pr[i][3]); }
-#pragma unroll
-                    for (int j = 0; j < kN; ++j)
-                        *reinterpret_cast<float4*>(r + kRecG + 4 * j) =
-                            make_float4(fmaf(hpost[0], hpre[j], pr[0][j]), fmaf(hpost[1], hpre[j], pr[1][j]),
-                                        fmaf(hpost[2], hpre[j], pr[2][j]), fmaf(hpost[3], hpre[j], pr[3][j]));
-                }
-                // ---- exact reverse sweep through the iterations (normalisers prefetched one iteration ahead)
-                float nx[8];
-                if (p.sk_iters > 0) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) nx[c] = skl[(p.sk_iters - 1) * 64 + c * 8];
-                }
-                for (int k = p.sk_iters - 1; k >= 0; --k) {
-                    float cu[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) cu[c] = nx[c];
-                    if (k > 0) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) nx[c] = skl[(k - 1) * 64 + c * 8];
-                    }
-                    // column step y = x / c:  dx = (dy - sum_i dy*y) / c ;  x = y * c
-                    u64 q01 = mul2(D[0], R[0]), q23 = mul2(E[0], S[0]);
-#pragma unroll
-                    for (int i = 1; i < kN; ++i) { q01 = fma2(D[i], R[i], q01); q23 = fma2(E[i], S[i], q23); }
-                    const float r0 = rcp_approx(cu[4]), r1 = rcp_approx(cu[5]), r2 = rcp_approx(cu[6]), r3 = rcp_approx(cu[7]);
-                    const u64 ci01 = pk2(r0, r1), ci23 = pk2(r2, r3);
-                    const u64 nq01 = mul2(q01, pk2(-r0, -r1)), nq23 = mul2(q23, pk2(-r2, -r3));
-                    const u64 cc01 = pk2(cu[4], cu[5]), cc23 = pk2(cu[6], cu[7]);
-#pragma unroll
-                    for (int i = 0; i < kN; ++i) {
-                        D[i] = fma2(D[i], ci01, nq01); E[i] = fma2(E[i], ci23, nq23);
-                        R[i] = mul2(R[i], cc01);       S[i] = mul2(S[i], cc23);
-                    }
-                    // row step y = x / dr
-#pragma unroll
-                    for (int i = 0; i < kN; ++i) {
-                        float a, b;
-                        upk2(fma2(E[i], S[i], mul2(D[i], R[i])), a, b);
-                        const float rr = rcp_approx(cu[i]);
-                        const float nq = -(a + b) * rr;
-                        const u64 rr2 = pk2(rr, rr), nq2 = pk2(nq, nq), dd2 = pk2(cu[i], cu[i]);
-                        D[i] = fma2(D[i], rr2, nq2); E[i] = fma2(E[i], rr2, nq2);
-                        R[i] = mul2(R[i], dd2);      S[i] = mul2(S[i], dd2);
-                    }
-                }
-                // softmax * 4 backward (R,S are back at the softmax output): dl = s * (d - sum(d*s)/4)
-#pragma unroll
-                for (int i = 0; i < kN; ++i) {
-                    float a, b;
-                    upk2(fma2(E[i], S[i], mul2(D[i], R[i])), a, b);
-                    const float nqs = -0.25f * (a + b);
-                    const u64 nq2 = pk2(nqs, nqs);
-                    upk2(mul2(R[i], add2(D[i], nq2)), dlv[2 * kN + 4 * i + 0], dlv[2 * kN + 4 * i + 1]);
-                    upk2(mul2(S[i], add2(E[i], nq2)), dlv[2 * kN + 4 * i + 2], dlv[2 * kN + 4 * i + 3]);
-                }
-                // ---- e = d raw, kappa (RMSNorm backward), per-token terms of dalpha; the raw logits in the
-                // record are read here for the last time and then overwritten with e (bf16 pairs) and kappa
-                float dsum = 0.f;
-                float ev[kL];
-#pragma unroll
-                for (int k = 0; k < kL; ++k) {
-                    const float ag = k < kN ? a_pre : (k < 2 * kN ? a_post : a_res);
-                    const float rawk = r[k];
-                    ev[k] = ag * dlv[k] * inv_rms;
-                    dsum = fmaf(ev[k], rawk, dsum);
-                    const float dz = dlv[k] * rawk * inv_rms;
-                    if (k < kN) dlv[kL] += dz; else if (k < 2 * kN) dlv[kL + 1] += dz; else dlv[kL + 2] += dz;
-                }
-                uint32_t* ew = reinterpret_cast<uint32_t*>(r);
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    *reinterpret_cast<uint4*>(ew + 4 * q) = make_uint4(pack_bf16(ev[8 * q], ev[8 * q + 1]), pack_bf16(ev[8 * q + 2], ev[8 * q + 3]),
-                                                                       pack_bf16(ev[8 * q + 4], ev[8 * q + 5]), pack_bf16(ev[8 * q + 6], ev[8 * q + 7]));
-                r[kRecKappa] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
-                const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + lane;
-                if (tok < p.T) {
-                    float4* o = reinterpret_cast<float4*>(p.e_out + tok * kL);
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) o[q] = make_float4(ev[4 * q], ev[4 * q + 1], ev[4 * q + 2], ev[4 * q + 3]);
-                }
-                // padded rows have dy = 0, hence G = 0 and every dl = 0: they add nothing to the sums below
+            float* r = rec + ((it % kSlots) * kTok + tk) * kRec;
+            const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(r[kRecSS], 1.0f / kRow, p.eps_rms)));
+            const float raw_pre = r[i], raw_post = r[kN + i];
+            const float4 raw_res = *reinterpret_cast<const float4*>(r + 2 * kN + 4 * i);
+            const float4 gq = *reinterpret_cast<const float4*>(r + kRecG + 4 * i);          // row i of G = dy x^T
+            const float hpre = sigmoid_f32(fmaf(a_pre, raw_pre * inv_rms, b_pre));
+            const float hpost = 2.0f * sigmoid_f32(fmaf(a_post, raw_post * inv_rms, b_post));
+            u64 A, B;
+            {
+                const float l0 = fmaf(a_res, raw_res.x * inv_rms, b_res.x), l1 = fmaf(a_res, raw_res.y * inv_rms, b_res.y);
+                const float l2 = fmaf(a_res, raw_res.z * inv_rms, b_res.z), l3 = fmaf(a_res, raw_res.w * inv_rms, b_res.w);
+                const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
+                const float e0 = fast_exp(l0 - mx), e1 = fast_exp(l1 - mx), e2 = fast_exp(l2 - mx), e3 = fast_exp(l3 - mx);
+                const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
+                A = pk2(e0 * r4, e1 * r4);
+                B = pk2(e2 * r4, e3 * r4);
             }
+            // ---- forward Sinkhorn, the normalisers are kept for the reverse sweep
+            for (int k = 0; k < p.sk_iters; ++k) {
+                float sa, sb;
+                upk2(add2(A, B), sa, sb);
+                const float dr = (sa + sb) + eps;
+                const float rr = rcp_approx(dr);
+                const u64 rr2 = pk2(rr, rr);
+                A = mul2(A, rr2); B = mul2(B, rr2);
+                const u64 cA = add2(gsum2(A), eps2), cB = add2(gsum2(B), eps2);
+                float c0, c1, c2, c3;
+                upk2(cA, c0, c1); upk2(cB, c2, c3);
+                A = mul2(A, pk2(rcp_approx(c0), rcp_approx(c1)));
+                B = mul2(B, pk2(rcp_approx(c2), rcp_approx(c3)));
+                skl[k * 8 + i] = dr;
+                if (i == 0) *reinterpret_cast<float4*>(skl + k * 8 + 4) = make_float4(c0, c1, c2, c3);
+            }
+            // ---- M = P + hpost (x) hpre needs every H_pre of the token; gate gradients from G
+            const float h0 = __shfl_sync(0xffffffffu, hpre, gbase + 0), h1 = __shfl_sync(0xffffffffu, hpre, gbase + 1);
+            const float h2 = __shfl_sync(0xffffffffu, hpre, gbase + 2), h3 = __shfl_sync(0xffffffffu, hpre, gbase + 3);
+            float p0, p1, p2, p3;
+            upk2(A, p0, p1); upk2(B, p2, p3);
+            const float dhpost = fmaf(gq.w, h3, fmaf(gq.z, h2, fmaf(gq.y, h1, gq.x * h0)));
+            float t0 = gq.x * hpost, t1 = gq.y * hpost, t2 = gq.z * hpost, t3 = gq.w * hpost;   // dhpre[j] = sum_i G[i][j] hpost[i]
+            t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, 1); t3 += __shfl_xor_sync(0xffffffffu, t3, 1);
+            t0 += __shfl_xor_sync(0xffffffffu, t0, 2); t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, 2); t3 += __shfl_xor_sync(0xffffffffu, t3, 2);
+            const float dhpre = i == 0 ? t0 : i == 1 ? t1 : i == 2 ? t2 : t3;
+            const float dl_pre = dhpre * hpre * (1.0f - hpre);
+            const float dl_post = dhpost * hpost * (1.0f - 0.5f * hpost);
+            __syncwarp();                                   // every lane of the group has read its G row and raw logits
+            r[kRecG + 0 * 4 + i] = fmaf(hpost, h0, p0);     // M^T[j][i] = M[i][j] replaces G in the record
+            r[kRecG + 1 * 4 + i] = fmaf(hpost, h1, p1);
+            r[kRecG + 2 * 4 + i] = fmaf(hpost, h2, p2);
+            r[kRecG + 3 * 4 + i] = fmaf(hpost, h3, p3);
+            __syncwarp();                                   // normalisers written by lane 0 of the group are visible
+            // ---- exact reverse sweep through the iterations (dP = G)
+            u64 Da = pk2(gq.x, gq.y), Db = pk2(gq.z, gq.w);
+            for (int k = p.sk_iters - 1; k >= 0; --k) {
+                const float4 cd = *reinterpret_cast<const float4*>(skl + k * 8 + 4);
+                const float dr = skl[k * 8 + i];
+                // column step y = x / c:  dx = (dy - sum_rows dy*y) / c ;  x = y * c
+                const u64 qA = gsum2(mul2(Da, A)), qB = gsum2(mul2(Db, B));
+                const float r0 = rcp_approx(cd.x), r1 = rcp_approx(cd.y), r2 = rcp_approx(cd.z), r3 = rcp_approx(cd.w);
+                Da = fma2(Da, pk2(r0, r1), mul2(qA, pk2(-r0, -r1)));
+                Db = fma2(Db, pk2(r2, r3), mul2(qB, pk2(-r2, -r3)));
+                A = mul2(A, pk2(cd.x, cd.y)); B = mul2(B, pk2(cd.z, cd.w));
+                // row step y = x / dr
+                float qa, qb;
+                upk2(fma2(Db, B, mul2(Da, A)), qa, qb);
+                const float rr = rcp_approx(dr);
+                const float nq = -(qa + qb) * rr;
+                const u64 rr2 = pk2(rr, rr), nq2 = pk2(nq, nq), dd2 = pk2(dr, dr);
+                Da = fma2(Da, rr2, nq2); Db = fma2(Db, rr2, nq2);
+                A = mul2(A, dd2); B = mul2(B, dd2);
+            }
+            // softmax * 4 backward (A,B are back at the softmax output): dl = s * (d - sum(d*s)/4)
+            float dl0, dl1, dl2, dl3;
+            {
+                float qa, qb;
+                upk2(fma2(Db, B, mul2(Da, A)), qa, qb);
+                const float nqs = -0.25f * (qa + qb);
+                const u64 nq2 = pk2(nqs, nqs);
+                upk2(mul2(A, add2(Da, nq2)), dl0, dl1);
+                upk2(mul2(B, add2(Db, nq2)), dl2, dl3);
+            }
+            // ---- e = d raw, kappa (RMSNorm backward), dbias / dalpha terms
+            acc_b[0] += dl_pre; acc_b[1] += dl_post; acc_b[2] += dl0; acc_b[3] += dl1; acc_b[4] += dl2; acc_b[5] += dl3;
+            acc_a[0] = fmaf(dl_pre, raw_pre * inv_rms, acc_a[0]);
+            acc_a[1] = fmaf(dl_post, raw_post * inv_rms, acc_a[1]);
+            acc_a[2] += fmaf(dl3, raw_res.w, fmaf(dl2, raw_res.z, fmaf(dl1, raw_res.y, dl0 * raw_res.x))) * inv_rms;
+            const float e_pre = a_pre * dl_pre * inv_rms, e_post = a_post * dl_post * inv_rms;
+            const float e0 = a_res * dl0 * inv_rms, e1 = a_res * dl1 * inv_rms;
+            const float e2 = a_res * dl2 * inv_rms, e3 = a_res * dl3 * inv_rms;
+            // d inv_rms = sum_k e_k raw_k / inv_rms ;  kappa = -d inv_rms * inv_rms^3 / N
+            float dsum = e_pre * raw_pre + e_post * raw_post + (e0 * raw_res.x + e1 * raw_res.y + e2 * raw_res.z + e3 * raw_res.w);
+            dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+            dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+            __nv_bfloat16* eb = reinterpret_cast<__nv_bfloat16*>(r);        // e as bf16 pairs over raw[0..11]
+            eb[i] = __float2bfloat16_rn(e_pre);
+            eb[kN + i] = __float2bfloat16_rn(e_post);
+            *reinterpret_cast<uint2*>(eb + 2 * kN + 4 * i) = make_uint2(pack_bf16(e0, e1), pack_bf16(e2, e3));
+            if (i == 0) r[kRecKappa] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
+            const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + tk;
+            if (tok < p.T) {
+                float* o = p.e_out + tok * kL;
+                o[i] = e_pre;
+                o[kN + i] = e_post;
+                *reinterpret_cast<float4*>(o + 2 * kN + 4 * i) = make_float4(e0, e1, e2, e3);
+            }   // padded rows have dy = 0, hence G = 0 and every dl = 0: they add nothing to the sums above
             __threadfence_block();
             bar_arrive(kBarCoef + cw, kWorkerThreads + 32);
-            // dbias / dalpha: butterfly over the token lanes (fixed order), component k accumulates in lane k
-#pragma unroll
-            for (int k = 0; k < kAccum; ++k) {
-                const float v = warp_sum(dlv[k]);
-                if (lane == k) my_acc += v;
-            }
         }
-        if (lane < kAccum) p.cta_accum[((size_t)blockIdx.x * kCoefWarps + cw) * kAccum + lane] = my_acc;
+        // fold the 8 token groups of the warp (lanes with equal i) in a fixed order, then the group for dalpha
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc_b[k] += __shfl_xor_sync(0xffffffffu, acc_b[k], o);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], o);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], 1);
+            acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], 2);
+        }
+        if (lane < 4) {
+            float* o = p.cta_accum + ((size_t)blockIdx.x * kCoefWarps + cw) * kAccum;
+            o[i] = acc_b[0];
+            o[kN + i] = acc_b[1];
+            o[2 * kN + 4 * i + 0] = acc_b[2]; o[2 * kN + 4 * i + 1] = acc_b[3];
+            o[2 * kN + 4 * i + 2] = acc_b[4]; o[2 * kN + 4 * i + 3] = acc_b[5];
+            if (i == 0) { o[kL] = acc_a[0]; o[kL + 1] = acc_a[1]; o[kL + 2] = acc_a[2]; }
+        }
       }
     } else {
         // ===================================================== worker warps
