@@ -47,6 +47,25 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
     return r == CUDA_SUCCESS ? HVS_OK : HVS_ERR_DRIVER;
 }
 
+// 3-D view of a [T, 4, 512] bf16 stream tensor as (channel, token, stream): a box of 64 channels x 8 tokens
+// x 4 streams lands in shared memory as four 1 KB swizzle atoms [stream][token][64 channels].
+int make_tmap_bf16_streams3d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return HVS_ERR_DRIVER;
+    cudaFree(nullptr);
+    cuuint64_t gdim[3] = {512, tokens, 4};
+    cuuint64_t gstride[2] = {4096, 1024};       // bytes: token stride, stream stride
+    cuuint32_t box[3] = {64, box_tokens, 4};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS && getenv("HVS_DEBUG"))
+        fprintf(stderr, "[hvs_b200] cuTensorMapEncodeTiled(3d) -> CUresult %d (ptr %p tokens %llu)\n", (int)r, gptr,
+                (unsigned long long)tokens);
+    return r == CUDA_SUCCESS ? HVS_OK : HVS_ERR_DRIVER;
+}
+
 }  // namespace hvs
 
 extern "C" {

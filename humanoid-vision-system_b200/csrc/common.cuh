@@ -58,5 +58,7 @@ inline void timer_end(int slot, cudaStream_t s) {
 
 // 2-D bf16 tensor map: [rows][cols] row-major, box [box_rows][64 cols] (=128 B inner), 128-byte swizzle.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+// 3-D (channel, token, stream) view of [T,4,512] bf16: box = 64 channels x box_tokens x 4 streams, 128-byte swizzle.
+int make_tmap_bf16_streams3d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens);
 
 }  // namespace hvs
