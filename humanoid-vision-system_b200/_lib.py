@@ -14,6 +14,7 @@ from . import build as _build
 _LIB = None
 
 HVS_MHC_SPLIT_PHI = 1
+HVS_MHC_SAVED_STRIDE = 28
 HVS_DTYPE_F32, HVS_DTYPE_F16, HVS_DTYPE_BF16 = 0, 1, 2
 HVS_NMS_AGNOSTIC, HVS_NMS_CLASS_AWARE, HVS_NMS_BOXES_XYXY = 0, 1, 16
 
@@ -26,11 +27,17 @@ _SIGNATURES = {
     "hvs_mhc_stream_kernel_ms": (c_int, [POINTER(c_float)]),
     "hvs_mhc_stream_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int64, c_int, c_int, c_int, c_float, c_float, c_uint32, c_void_p]),
+    "hvs_mhc_stream_fwd_save": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_int64, c_int, c_int, c_int, c_float, c_float, c_uint32, c_void_p]),
     "hvs_mhc_stream_post": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "hvs_mhc_stream_bwd_workspace": (c_size_t, [c_int64, c_int, c_int]),
     "hvs_mhc_stream_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_float,
                                    c_uint32, c_void_p, c_size_t, c_void_p]),
+    "hvs_mhc_stream_bwd_saved_workspace": (c_size_t, [c_int64, c_int, c_int]),
+    "hvs_mhc_stream_bwd_saved": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float,
+                                         c_float, c_uint32, c_void_p, c_size_t, c_void_p]),
     "hvs_sinkhorn": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "hvs_mhc_constrained_matrices": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                              c_int, c_float, c_void_p, c_void_p]),

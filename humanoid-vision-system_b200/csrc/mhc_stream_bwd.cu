@@ -668,6 +668,16 @@ BwdWs carve(void* base, int64_t T, int ctas) {
 }
 
 }  // namespace
+
+// shared with the fused (saved-statistics) backward in mhc_stream_bwd_fused.cu
+int launch_bwd_finalize(const float* dw_part, int dw_ctas, const float* cta_accum, int acc_ctas, const float* phi,
+                        const float* scale, float* dphi, float* dscale, float* dbias, float* dalpha, cudaStream_t stream) {
+    mhc_stream_bwd_finalize_kernel<<<kRow / 8, 256, 0, stream>>>(dw_part, dw_ctas, cta_accum, acc_ctas, phi, scale, dphi,
+                                                                 dscale, dbias, dalpha);
+    count_launch();
+    return launch_status();
+}
+
 }  // namespace hvs
 
 extern "C" size_t hvs_mhc_stream_bwd_workspace(int64_t T, int n, int C) {

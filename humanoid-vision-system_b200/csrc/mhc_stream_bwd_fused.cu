@@ -1,0 +1,604 @@
+// K1 backward for training, ONE fused kernel: dx and the parameter gradients in a single pass over x and dy
+// (every byte crosses HBM once).  The forward saved the un-normalised projection and the sum of squares per
+// token (hvs_mhc_stream_fwd_save, 112 B/token), so nothing here needs the projection operand in its forward
+// layout; the two dense contractions that remain go to the tcgen05 tensor cores with accumulators in tensor
+// memory, straight from the TMA-landed token tile:
+//   G = dy x^T (per-token 4x4)   tcgen05.mma  D[64x32] += [x rows ; dy rows] (64 x 16) * (x rows)^T, K-major operands
+//                                 (the 4x4 blocks are the token-diagonal of the dy half of D)
+//   dW = x^T E (2048 x 24)       tcgen05.mma  D[64x24] += x-atom^T (MN-major A, read in place) * [E_hi ; E_lo]
+//                                 the two bf16 terms of E ride the two halves of K = 16 against the SAME eight
+//                                 token rows of x (stride-0 K step), accumulated over the whole kernel in 384
+//                                 tensor-memory columns (32 blocks of 64 channels, two per column range)
+// Roles (640 threads, one CTA per SM, 3 stages of 8 tokens: x | dy = 64 KB each):
+//   front thread        TMA loads (3-D boxes -> [stream][token][64 ch] swizzle atoms, + the saved records),
+//                       issues every tcgen05.mma in dependency order, TMA-stores dx, recycles stages
+//   8 worker warps      read the G blocks out of tensor memory into the tile's record
+//   3 coefficient warps (one per stage, 4 lanes per token) gates + Sinkhorn forward in packed fp32x2 registers,
+//                       exact reverse sweep, e = d raw, kappa, M; write E as bf16 hi/lo in MMA operand layout
+//   16 worker warps     dx = M^T dy + kappa x + W e   (W e on the warp MMA path with scale*phi resident in 48
+//                       registers; mixing in packed fp32x2 FMAs), written IN PLACE over dy, one rounding to bf16
+// Oracle: autograd through oracle/mhc_ref.py::stream_mhc_forward (reference primitives
+// src/models/manifold_layers.py:56-77, :213-216, :449-456).
+#include "common.cuh"
+#include "mhc_stream_shared.cuh"
+#include "ptx_sm100.cuh"
+#include "umma_sm100.cuh"
+
+namespace hvs {
+
+int launch_bwd_finalize(const float* dw_part, int dw_ctas, const float* cta_accum, int acc_ctas, const float* phi,
+                        const float* scale, float* dphi, float* dscale, float* dbias, float* dalpha, cudaStream_t stream);
+
+namespace {
+
+constexpr int kTok = 8;
+constexpr int kStages = 3;
+constexpr int kWorkers = 16;
+constexpr int kWorkerThreads = kWorkers * 32;
+constexpr int kThreads = (kWorkers + 4) * 32;         // + coefficient warp 0, front warp, coefficient warps 1, 2
+constexpr int kWorkerRegs = 104, kRoleRegs = 64;
+constexpr int kStageBytes = 65536;                    // 8 channel blocks x ([x box 4 KB][dy box 4 KB]); box = 4 stream atoms of 8 tokens x 128 B
+constexpr int kSaved = HVS_MHC_SAVED_STRIDE;          // floats per token in the saved record: raw[24], sum x^2, pad
+constexpr int kMaxIters = 24;
+constexpr int kCoefWarps = 3;
+constexpr int kAccum = kL + 3;
+
+constexpr int kSavedBytes = kTok * kSaved * 4;        // 896
+constexpr int kOffSaved = kStages * kStageBytes;
+constexpr int kOffG = kOffSaved + kStages * kSavedBytes;          // [stage][token][i][j] fp32
+constexpr int kOffWrec = kOffG + kStages * 512;                   // per stage: e bf16 pairs [8][12] | M pairs [4][4][4][2] | kappa [8]
+constexpr int kWrecBytes = 1024, kWrecM = 384, kWrecK = 896;
+constexpr int kOffEt = kOffWrec + kStages * kWrecBytes;           // per stage: E tile, 24 rows x 16 K bf16, no swizzle (768 B)
+constexpr int kEtBytes = 1024;
+constexpr int kSkWords = kTok * kMaxIters * 8;
+constexpr int kOffSk = kOffEt + kStages * kEtBytes;
+constexpr int kOffBar = kOffSk + kCoefWarps * kSkWords * 4;
+constexpr int kOffTmem = kOffBar + 5 * kStages * 8;
+constexpr int kSmemBytes = kOffTmem + 16;
+static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffG % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0, "alignment");
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColDw = 0;                        // 16 column ranges x 24: blocks 2p (lanes +0) and 2p+1 (lanes +16)
+constexpr uint32_t kColGs = 384;                      // 32 columns per stage
+
+constexpr int kBarRec = 1 /*,2,3*/, kBarCoef = 4 /*,5,6*/;
+
+struct FusedParams {
+    const float* phi;
+    const float* bias;
+    const float* alpha;
+    const float* scale;
+    const float* saved;    // [T, 28]
+    float* dw_part;        // [grid, 2048, 24]
+    float* cta_accum;      // [grid, 3, 27]
+    int64_t T;
+    int num_tiles;
+    int sk_iters;
+    float eps_rms, eps_sk;
+};
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// D(16x8,f32) += A(16x8,bf16,row) * B(8x8,bf16,col)
+__device__ __forceinline__ void mma_bf16_1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                            const __grid_constant__ CUtensorMap tmap_dx, const FusedParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (smem_u32(smem) & 1023u) __trap();
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffBar);     // tile + saved records landed
+    uint64_t* bar_gs = bar_full + kStages;                                // G MMAs of the tile complete
+    uint64_t* bar_ed = bar_gs + kStages;                                  // E tile written (coefficient warp)
+    uint64_t* bar_dxr = bar_ed + kStages;                                 // dx staged by the workers
+    uint64_t* bar_dw = bar_dxr + kStages;                                 // dW MMAs of the tile complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_gs[s], 1);
+            mbar_init(&bar_ed[s], 1);
+            mbar_init(&bar_dxr[s], kWorkerThreads);
+            mbar_init(&bar_dw[s], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == kWorkers + 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // the dW accumulators start at zero: every MMA below accumulates
+    if (warp < kWorkers) {
+        const uint32_t zero[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const uint32_t tq = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + kColDw + (uint32_t)((warp >> 2) * 96);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) tmem_st16(tq + 16 * c, zero);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp >= kWorkers) {
+      reg_dealloc<kRoleRegs>();
+      if (warp == kWorkers + 1) {
+        // ===================================================== front thread: loads, MMA issue, stores
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_x);
+            tma_prefetch_desc(&tmap_dy);
+            tma_prefetch_desc(&tmap_dx);
+            const uint32_t s0 = smem_u32(smem);
+            auto load_tile = [&](int it) {
+                const int s = it % kStages;
+                const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok;
+                const int64_t left = p.T - tok0;
+                const uint32_t nvalid = left >= kTok ? kTok : (uint32_t)left;
+                uint8_t* st = smem + s * kStageBytes;
+                mbar_arrive_expect_tx(&bar_full[s], kStageBytes + nvalid * kSaved * 4);
+#pragma unroll
+                for (int cb = 0; cb < 8; ++cb) {
+                    tma_load_3d(st + cb * 8192, &tmap_x, &bar_full[s], cb * 64, (int)tok0, 0);
+                    tma_load_3d(st + cb * 8192 + 4096, &tmap_dy, &bar_full[s], cb * 64, (int)tok0, 0);
+                }
+                bulk_load_1d(smem + kOffSaved + s * kSavedBytes, p.saved + tok0 * kSaved, nvalid * kSaved * 4, &bar_full[s]);
+            };
+            const uint32_t id_gs = umma_idesc_bf16(64, 32, 0, 0);
+            const uint32_t id_dw = umma_idesc_bf16(64, 24, 1, 0);
+            auto retire = [&](int k) {
+                const int s = k % kStages;
+                const uint32_t ph = (uint32_t)(k / kStages) & 1u;
+                // dW += x^T E for the tile whose coefficients are ready
+                mbar_wait(&bar_ed[s], ph);
+                tc_fence_after();
+                const uint64_t bdesc = umma_smem_desc(s0 + kOffEt + s * kEtBytes, 384, 128, kUmmaLayoutNone);
+#pragma unroll 4
+                for (int b = 0; b < 32; ++b) {
+                    const uint32_t a = s0 + s * kStageBytes + (b >> 2) * 8192 + (b & 3) * 1024;
+                    const uint32_t d = tmem_base + ((uint32_t)((b & 1) * 16) << 16) + kColDw + (uint32_t)((b >> 1) * 24);
+                    umma_bf16_ss(d, umma_smem_desc(a, 1024, 0, kUmmaLayoutSw128), bdesc, id_dw, 1u);
+                }
+                umma_commit(&bar_dw[s]);
+                // dx of the tile (written in place over dy) -> HBM
+                mbar_wait(&bar_dxr[s], ph);
+                const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * kTok;
+#pragma unroll
+                for (int cb = 0; cb < 8; ++cb)
+                    tma_store_3d(&tmap_dx, smem + s * kStageBytes + cb * 8192 + 4096, cb * 64, (int)tok0, 0);
+                bulk_commit();
+                bulk_wait_read<0>();
+                mbar_wait(&bar_dw[s], ph);                       // the tensor core is done reading x of this stage
+                if (k + kStages < n_local) load_tile(k + kStages);
+            };
+            for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
+            for (int it = 0; it < n_local; ++it) {
+                const int s = it % kStages;
+                mbar_wait(&bar_full[s], (uint32_t)(it / kStages) & 1u);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + kColGs + 32u * s;
+#pragma unroll
+                for (int cb = 0; cb < 8; ++cb)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t a = s0 + s * kStageBytes + cb * 8192 + ks * 32;
+                        const uint64_t d64 = umma_smem_desc(a, 16, 1024, kUmmaLayoutSw128);
+                        umma_bf16_ss(dcol, d64, d64, id_gs, (uint32_t)((cb | ks) != 0));
+                    }
+                umma_commit(&bar_gs[s]);
+                if (it >= 2) retire(it - 2);
+            }
+            for (int k = n_local >= 2 ? n_local - 2 : 0; k < n_local; ++k) retire(k);
+            bulk_wait<0>();
+        }
+      } else {
+        // ===================================================== coefficient warps (warps 16, 18, 19 <-> stage 0, 1, 2)
+        // Four lanes per token: lane (tk, i) owns row i of the token's 4x4 block as two packed fp32x2 registers
+        // A = (p_i0,p_i1), B = (p_i2,p_i3) and gate i of H_pre / H_post.  Row sums are local, column sums take two
+        // xor-shuffles inside the 4-lane group.
+        const int cw = warp == kWorkers ? 0 : warp - (kWorkers + 1);
+        const int s = cw;
+        const int tk = lane >> 2, i = lane & 3, gbase = lane & ~3;
+        const float b_pre = __ldg(p.bias + i), b_post = __ldg(p.bias + kN + i);
+        const float4 b_res = __ldg(reinterpret_cast<const float4*>(p.bias + 2 * kN) + i);
+        const float a_pre = __ldg(p.alpha + 0), a_post = __ldg(p.alpha + 1), a_res = __ldg(p.alpha + 2);
+        const float eps = p.eps_sk;
+        const u64 eps2 = pk2(eps, eps);
+        float acc_b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dbias: pre_i, post_i, res_i0..3
+        float acc_a[3] = {0.f, 0.f, 0.f};                  // dalpha terms of this lane
+        float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + tk * (kMaxIters * 8);
+        const float* rs = reinterpret_cast<const float*>(smem + kOffSaved + s * kSavedBytes) + tk * kSaved;
+        const float* gs = reinterpret_cast<const float*>(smem + kOffG + s * 512) + tk * 16 + 4 * i;
+        uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
+        uint8_t* et = smem + kOffEt + s * kEtBytes;
+        auto gsum2 = [](u64 v) {                           // sum over the 4 lanes of a group, both halves
+            float a, b;
+            upk2(v, a, b);
+            a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
+            return pk2(a, b);
+        };
+        for (int it = cw; it < n_local; it += kCoefWarps) {
+            const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+            bar_sync(kBarRec + s, 8 * 32 + 32);
+            mbar_wait(&bar_full[s], ph);                   // the saved records came in with the tile
+            const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + tk;
+            const bool valid = tok < p.T;                  // rows past T: x = dy = 0 (TMA fill), records not loaded
+            const float ssq = valid ? rs[kL] : 1.0f;
+            const float raw_pre = valid ? rs[i] : 0.f, raw_post = valid ? rs[kN + i] : 0.f;
+            const float4 raw_res = valid ? *reinterpret_cast<const float4*>(rs + 2 * kN + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 gq = *reinterpret_cast<const float4*>(gs);                        // row i of G = dy x^T
+            const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(ssq, 1.0f / kRow, p.eps_rms)));
+            const float hpre = sigmoid_f32(fmaf(a_pre, raw_pre * inv_rms, b_pre));
+            const float hpost = 2.0f * sigmoid_f32(fmaf(a_post, raw_post * inv_rms, b_post));
+            u64 A, B;
+            {
+                const float l0 = fmaf(a_res, raw_res.x * inv_rms, b_res.x), l1 = fmaf(a_res, raw_res.y * inv_rms, b_res.y);
+                const float l2 = fmaf(a_res, raw_res.z * inv_rms, b_res.z), l3 = fmaf(a_res, raw_res.w * inv_rms, b_res.w);
+                const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
+                const float e0 = fast_exp(l0 - mx), e1 = fast_exp(l1 - mx), e2 = fast_exp(l2 - mx), e3 = fast_exp(l3 - mx);
+                const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
+                A = pk2(e0 * r4, e1 * r4);
+                B = pk2(e2 * r4, e3 * r4);
+            }
+            // ---- forward Sinkhorn, the normalisers are kept for the reverse sweep
+            for (int k = 0; k < p.sk_iters; ++k) {
+                float sa, sb;
+                upk2(add2(A, B), sa, sb);
+                const float dr = (sa + sb) + eps;
+                const float rr = rcp_approx(dr);
+                const u64 rr2 = pk2(rr, rr);
+                A = mul2(A, rr2); B = mul2(B, rr2);
+                const u64 cA = add2(gsum2(A), eps2), cB = add2(gsum2(B), eps2);
+                float c0, c1, c2, c3;
+                upk2(cA, c0, c1); upk2(cB, c2, c3);
+                A = mul2(A, pk2(rcp_approx(c0), rcp_approx(c1)));
+                B = mul2(B, pk2(rcp_approx(c2), rcp_approx(c3)));
+                skl[k * 8 + i] = dr;
+                if (i == 0) *reinterpret_cast<float4*>(skl + k * 8 + 4) = make_float4(c0, c1, c2, c3);
+            }
+            // ---- M = P + hpost (x) hpre needs every H_pre of the token; gate gradients from G
+            const float h0 = __shfl_sync(0xffffffffu, hpre, gbase + 0), h1 = __shfl_sync(0xffffffffu, hpre, gbase + 1);
+            const float h2 = __shfl_sync(0xffffffffu, hpre, gbase + 2), h3 = __shfl_sync(0xffffffffu, hpre, gbase + 3);
+            float p0, p1, p2, p3;
+            upk2(A, p0, p1); upk2(B, p2, p3);
+            const float dhpost = fmaf(gq.w, h3, fmaf(gq.z, h2, fmaf(gq.y, h1, gq.x * h0)));
+            float t0 = gq.x * hpost, t1 = gq.y * hpost, t2 = gq.z * hpost, t3 = gq.w * hpost;   // dhpre[j] = sum_i G[i][j] hpost[i]
+            t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, 1); t3 += __shfl_xor_sync(0xffffffffu, t3, 1);
+            t0 += __shfl_xor_sync(0xffffffffu, t0, 2); t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, 2); t3 += __shfl_xor_sync(0xffffffffu, t3, 2);
+            const float dhpre = i == 0 ? t0 : i == 1 ? t1 : i == 2 ? t2 : t3;
+            const float dl_pre = dhpre * hpre * (1.0f - hpre);
+            const float dl_post = dhpost * hpost * (1.0f - 0.5f * hpost);
+            {   // M[i][jj] for the workers, paired over the two tokens (2t, 2t+1) a worker thread owns: [tk/2][jj][i][tk&1]
+                float* mp = reinterpret_cast<float*>(wrec + kWrecM) + (tk >> 1) * 32 + i * 2 + (tk & 1);
+                mp[0] = fmaf(hpost, h0, p0);
+                mp[8] = fmaf(hpost, h1, p1);
+                mp[16] = fmaf(hpost, h2, p2);
+                mp[24] = fmaf(hpost, h3, p3);
+            }
+            __syncwarp();                                   // normalisers written by lane 0 of the group are visible
+            // ---- exact reverse sweep through the iterations (dP = G)
+            u64 Da = pk2(gq.x, gq.y), Db = pk2(gq.z, gq.w);
+            for (int k = p.sk_iters - 1; k >= 0; --k) {
+                const float4 cd = *reinterpret_cast<const float4*>(skl + k * 8 + 4);
+                const float dr = skl[k * 8 + i];
+                // column step y = x / c:  dx = (dy - sum_rows dy*y) / c ;  x = y * c
+                const u64 qA = gsum2(mul2(Da, A)), qB = gsum2(mul2(Db, B));
+                const float r0 = rcp_approx(cd.x), r1 = rcp_approx(cd.y), r2 = rcp_approx(cd.z), r3 = rcp_approx(cd.w);
+                Da = fma2(Da, pk2(r0, r1), mul2(qA, pk2(-r0, -r1)));
+                Db = fma2(Db, pk2(r2, r3), mul2(qB, pk2(-r2, -r3)));
+                A = mul2(A, pk2(cd.x, cd.y)); B = mul2(B, pk2(cd.z, cd.w));
+                // row step y = x / dr
+                float qa, qb;
+                upk2(fma2(Db, B, mul2(Da, A)), qa, qb);
+                const float rr = rcp_approx(dr);
+                const float nq = -(qa + qb) * rr;
+                const u64 rr2 = pk2(rr, rr), nq2 = pk2(nq, nq), dd2 = pk2(dr, dr);
+                Da = fma2(Da, rr2, nq2); Db = fma2(Db, rr2, nq2);
+                A = mul2(A, dd2); B = mul2(B, dd2);
+            }
+            // softmax * 4 backward (A,B are back at the softmax output): dl = s * (d - sum(d*s)/4)
+            float dl0, dl1, dl2, dl3;
+            {
+                float qa, qb;
+                upk2(fma2(Db, B, mul2(Da, A)), qa, qb);
+                const float nqs = -0.25f * (qa + qb);
+                const u64 nq2 = pk2(nqs, nqs);
+                upk2(mul2(A, add2(Da, nq2)), dl0, dl1);
+                upk2(mul2(B, add2(Db, nq2)), dl2, dl3);
+            }
+            // ---- e = d raw, kappa (RMSNorm backward), dbias / dalpha terms
+            acc_b[0] += dl_pre; acc_b[1] += dl_post; acc_b[2] += dl0; acc_b[3] += dl1; acc_b[4] += dl2; acc_b[5] += dl3;
+            acc_a[0] = fmaf(dl_pre, raw_pre * inv_rms, acc_a[0]);
+            acc_a[1] = fmaf(dl_post, raw_post * inv_rms, acc_a[1]);
+            acc_a[2] += fmaf(dl3, raw_res.w, fmaf(dl2, raw_res.z, fmaf(dl1, raw_res.y, dl0 * raw_res.x))) * inv_rms;
+            const float ev[6] = {a_pre * dl_pre * inv_rms, a_post * dl_post * inv_rms, a_res * dl0 * inv_rms,
+                                 a_res * dl1 * inv_rms, a_res * dl2 * inv_rms, a_res * dl3 * inv_rms};
+            // d inv_rms = sum_k e_k raw_k / inv_rms ;  kappa = -d inv_rms * inv_rms^3 / N
+            float dsum = ev[0] * raw_pre + ev[1] * raw_post + (ev[2] * raw_res.x + ev[3] * raw_res.y + ev[4] * raw_res.z + ev[5] * raw_res.w);
+            dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+            dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+            // bf16 hi of e for the workers' W e MMA, hi and lo for the dW MMA (operand rows = logits, K = token | 8 + token)
+            const int lg[6] = {i, kN + i, 2 * kN + 4 * i, 2 * kN + 4 * i + 1, 2 * kN + 4 * i + 2, 2 * kN + 4 * i + 3};
+            __nv_bfloat16 hi[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                hi[q] = __float2bfloat16_rn(ev[q]);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(ev[q] - __bfloat162float(hi[q]));
+                uint8_t* dst = et + (lg[q] >> 3) * 128 + (lg[q] & 7) * 16 + tk * 2;
+                *reinterpret_cast<__nv_bfloat16*>(dst) = hi[q];
+                *reinterpret_cast<__nv_bfloat16*>(dst + 384) = lo;
+            }
+            __nv_bfloat16* eb = reinterpret_cast<__nv_bfloat16*>(wrec) + tk * 24;
+            eb[i] = hi[0];
+            eb[kN + i] = hi[1];
+            *reinterpret_cast<uint2*>(eb + 2 * kN + 4 * i) =
+                make_uint2((uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16),
+                           (uint32_t)__bfloat16_as_ushort(hi[4]) | ((uint32_t)__bfloat16_as_ushort(hi[5]) << 16));
+            if (i == 0) reinterpret_cast<float*>(wrec + kWrecK)[tk] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
+            fence_proxy_async_smem();                       // the E tile is read by the tensor core (async proxy)
+            __threadfence_block();
+            bar_arrive(kBarCoef + s, kWorkerThreads + 32);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_ed[s]);
+        }
+        // fold the 8 token groups of the warp (lanes with equal i) in a fixed order, then the group for dalpha
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc_b[k] += __shfl_xor_sync(0xffffffffu, acc_b[k], o);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], o);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], 1);
+            acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], 2);
+        }
+        if (lane < 4) {
+            float* o = p.cta_accum + ((size_t)blockIdx.x * kCoefWarps + cw) * kAccum;
+            o[i] = acc_b[0];
+            o[kN + i] = acc_b[1];
+            o[2 * kN + 4 * i + 0] = acc_b[2]; o[2 * kN + 4 * i + 1] = acc_b[3];
+            o[2 * kN + 4 * i + 2] = acc_b[4]; o[2 * kN + 4 * i + 3] = acc_b[5];
+            if (i == 0) { o[kL] = acc_a[0]; o[kL + 1] = acc_a[1]; o[kL + 2] = acc_a[2]; }
+        }
+      }
+    } else {
+        // ===================================================== worker warps
+        reg_alloc<kWorkerRegs>();
+        const int w = warp, g = lane >> 2, t = lane & 3;
+        // W = bf16(scale * phi) as the A operand of  dx_proj^T = W e^T : m-tile (jj, mt) rows g / g+8 are the
+        // channel pair 32w + 4g + 2mt + {0,1} of stream jj, k = logits.  48 registers, resident for the whole kernel.
+        uint32_t wf[kN][2][6];
+#pragma unroll
+        for (int jj = 0; jj < kN; ++jj)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int ka = jj * kC + 32 * w + 4 * g + 2 * mt;
+                const float sa = __ldg(p.scale + ka), sb = __ldg(p.scale + ka + 1);
+                const float* ra = p.phi + (size_t)ka * kL;
+                const float* rb = ra + kL;
+                wf[jj][mt][0] = pack_bf16(__ldg(ra + 2 * t) * sa, __ldg(ra + 2 * t + 1) * sa);
+                wf[jj][mt][1] = pack_bf16(__ldg(rb + 2 * t) * sb, __ldg(rb + 2 * t + 1) * sb);
+                wf[jj][mt][2] = pack_bf16(__ldg(ra + 2 * t + 8) * sa, __ldg(ra + 2 * t + 9) * sa);
+                wf[jj][mt][3] = pack_bf16(__ldg(rb + 2 * t + 8) * sb, __ldg(rb + 2 * t + 9) * sb);
+                wf[jj][mt][4] = pack_bf16(__ldg(ra + 2 * t + 16) * sa, __ldg(ra + 2 * t + 17) * sa);
+                wf[jj][mt][5] = pack_bf16(__ldg(rb + 2 * t + 16) * sb, __ldg(rb + 2 * t + 17) * sb);
+            }
+        // this thread's 8 bytes (channels 32w + 4g .. +3) of (token 2t, stream jj); token 2t+1 is the next row with
+        // the swizzle bit flipped
+        const int cb = w >> 1, hh = w & 1;
+        uint32_t offa[kN];
+#pragma unroll
+        for (int jj = 0; jj < kN; ++jj)
+            offa[jj] = cb * 8192 + jj * 1024 + (2 * t) * 128 + (((4 * hh + (g >> 1)) ^ (2 * t)) << 4) + (g & 1) * 8;
+        const uint32_t stage0 = smem_u32(smem);
+        const int q = w & 3, jcol = w >> 2;               // tensor-memory lane quadrant / G column group of this warp
+        const uint32_t tm_gs = tmem_base + ((uint32_t)(32 * q) << 16) + kColGs + 8u * jcol;
+
+        for (int step = 0; step < n_local + 2; ++step) {
+            const int k = step - 2;
+            if (k >= 0) {
+                // ============ dx for tokens 2t, 2t+1 of tile k, channels 32w + 4g .. +3 of every stream
+                const int s = k % kStages;
+                bar_sync(kBarCoef + s, kWorkerThreads + 32);
+                mbar_wait(&bar_full[s], (uint32_t)(k / kStages) & 1u);
+                const uint32_t sb = stage0 + s * kStageBytes;
+                const uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
+                const uint32_t* ew = reinterpret_cast<const uint32_t*>(wrec) + g * 12;
+                const uint32_t eb0 = ew[t], eb1 = ew[t + 4], eb2 = ew[t + 8];     // e[g][2t..], e[g][2t+8..], e[g][2t+16..]
+                const float2 kp = *reinterpret_cast<const float2*>(wrec + kWrecK + 8 * t);
+                const u64 kp2 = pk2(kp.x, kp.y);
+                uint2 dya[kN], dyb[kN];
+#pragma unroll
+                for (int ii = 0; ii < kN; ++ii) {
+                    dya[ii] = lds64(sb + 4096 + offa[ii]);
+                    dyb[ii] = lds64(sb + 4096 + ((offa[ii] + 128) ^ 16));
+                }
+#pragma unroll
+                for (int jj = 0; jj < kN; ++jj) {
+                    const float4* mq = reinterpret_cast<const float4*>(wrec + kWrecM) + (t * 4 + jj) * 2;
+                    const float4 m01 = mq[0], m23 = mq[1];                        // (M_a[0],M_b[0],M_a[1],M_b[1]) (M_a[2],...)
+                    const u64 mp[kN] = {pk2(m01.x, m01.y), pk2(m01.z, m01.w), pk2(m23.x, m23.y), pk2(m23.z, m23.w)};
+                    const uint2 xa = lds64(sb + offa[jj]);
+                    const uint2 xb = lds64(sb + ((offa[jj] + 128) ^ 16));
+                    uint32_t oa[2], ob[2];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const uint32_t xwa = mt ? xa.y : xa.x, xwb = mt ? xb.y : xb.x;
+                        const u64 c01i = mul2(kp2, pk2(bf16lo(xwa), bf16lo(xwb)));
+                        const u64 c23i = mul2(kp2, pk2(bf16hi(xwa), bf16hi(xwb)));
+                        float c[4];
+                        upk2(c01i, c[0], c[1]);
+                        upk2(c23i, c[2], c[3]);
+                        mma_bf16_16816(c, wf[jj][mt][0], wf[jj][mt][1], wf[jj][mt][2], wf[jj][mt][3], eb0, eb1);
+                        mma_bf16_1688(c, wf[jj][mt][4], wf[jj][mt][5], eb2);
+                        u64 c01 = pk2(c[0], c[1]), c23 = pk2(c[2], c[3]);
+#pragma unroll
+                        for (int ii = 0; ii < kN; ++ii) {
+                            const uint32_t da = mt ? dya[ii].y : dya[ii].x, db = mt ? dyb[ii].y : dyb[ii].x;
+                            c01 = fma2(mp[ii], pk2(bf16lo(da), bf16lo(db)), c01);
+                            c23 = fma2(mp[ii], pk2(bf16hi(da), bf16hi(db)), c23);
+                        }
+                        upk2(c01, c[0], c[1]);
+                        upk2(c23, c[2], c[3]);
+                        oa[mt] = pack_bf16(c[0], c[2]);
+                        ob[mt] = pack_bf16(c[1], c[3]);
+                    }
+                    sts64(sb + 4096 + offa[jj], oa[0], oa[1]);
+                    sts64(sb + 4096 + ((offa[jj] + 128) ^ 16), ob[0], ob[1]);
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&bar_dxr[s]);
+            }
+            if (step < n_local && q >= 2) {
+                // ============ G blocks of tile `step` out of tensor memory: lanes 0..15 of quadrant q hold the
+                // dy rows (stream 2(q-2) + lane/8, token lane%8); this warp takes x stream jcol
+                const int s = step % kStages;
+                mbar_wait(&bar_gs[s], (uint32_t)(step / kStages) & 1u);
+                tc_fence_after();
+                uint32_t v[8];
+                tmem_ld8(tm_gs + 32u * s, v);
+                tmem_wait_ld();
+                const int tok = lane & 7;
+                uint32_t val = v[0];
+#pragma unroll
+                for (int c = 1; c < 8; ++c) val = tok == c ? v[c] : val;
+                if (lane < 16)
+                    reinterpret_cast<uint32_t*>(smem + kOffG + s * 512)[tok * 16 + (2 * (q - 2) + (lane >> 3)) * 4 + jcol] = val;
+                tc_fence_before();
+                __threadfence_block();
+                bar_arrive(kBarRec + s, 8 * 32 + 32);
+            }
+        }
+        // ============ dW of this CTA out of tensor memory (every MMA has been committed before the last barrier phase)
+        {
+            const int last = n_local - 1;
+            mbar_wait(&bar_dw[last % kStages], (uint32_t)(last / kStages) & 1u);
+            tc_fence_after();
+            const int half = lane >> 4, r = lane & 15;
+            float* out = p.dw_part + (size_t)blockIdx.x * kRow * kL;
+#pragma unroll
+            for (int pi = 0; pi < 4; ++pi) {
+                const int pr = (w >> 2) * 4 + pi;          // column range = block pair
+                const int b = 2 * pr + half;               // block (cb, j) = (b >> 2, b & 3), row = channel in the block
+                const int kidx = (b & 3) * kC + (b >> 2) * 64 + 16 * q + r;
+                const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + kColDw + (uint32_t)(pr * 24);
+                uint32_t v[8];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    tmem_ld8(ta + 8 * c, v);
+                    tmem_wait_ld();
+                    float4* o = reinterpret_cast<float4*>(out + (size_t)kidx * kL + 8 * c);
+                    o[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+                    o[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWorkers + 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct FusedWs {
+    float* dw_part; float* cta_accum;
+    size_t total;
+};
+FusedWs carve(void* base, int ctas) {
+    FusedWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return reinterpret_cast<uint8_t*>(base) + o; };
+    w.dw_part = reinterpret_cast<float*>(take((size_t)ctas * kRow * kL * 4));
+    w.cta_accum = reinterpret_cast<float*>(take((size_t)ctas * kCoefWarps * kAccum * 4));
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+}  // namespace hvs
+
+extern "C" size_t hvs_mhc_stream_bwd_saved_workspace(int64_t T, int n, int C) {
+    using namespace hvs;
+    if (T < 0 || n != kN || C != kC) return 0;
+    return carve(nullptr, sm_count()).total;
+}
+
+extern "C" int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const float* saved, const float* phi,
+                                        const float* bias, const float* alpha, const float* scale, void* dx,
+                                        float* dphi, float* dbias, float* dalpha, float* dscale, int64_t T, int n,
+                                        int C, int sk_iters, float eps_rms, float eps_sk, uint32_t flags,
+                                        void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (T < 0) return HVS_ERR_BAD_ARG;
+    if (n != kN || C != kC || sk_iters < 0 || sk_iters > kMaxIters) return HVS_ERR_UNSUPPORTED;
+    if (flags & HVS_MHC_SPLIT_PHI) return HVS_ERR_UNSUPPORTED;
+    if (!phi || !bias || !alpha || !scale || !dphi || !dbias || !dalpha || !dscale) return HVS_ERR_BAD_ARG;
+    if (T > 0 && (!x || !dy || !dx || !saved)) return HVS_ERR_BAD_ARG;
+    if (T >= (int64_t)1 << 31) return HVS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+         reinterpret_cast<uintptr_t>(saved)) & 15)
+        return HVS_ERR_ALIGNMENT;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return HVS_ERR_ALIGNMENT;
+    const int sms = sm_count();
+    const FusedWs ws = carve(workspace, sms);
+    if (workspace_bytes < ws.total) return HVS_ERR_WORKSPACE;
+    int grid = 0;
+    if (T > 0) {
+        CUtensorMap tx, tdy, tdx;
+        int rc = make_tmap_bf16_streams3d(&tx, x, (uint64_t)T, kTok);
+        if (rc) return rc;
+        rc = make_tmap_bf16_streams3d(&tdy, dy, (uint64_t)T, kTok);
+        if (rc) return rc;
+        rc = make_tmap_bf16_streams3d(&tdx, dx, (uint64_t)T, kTok);
+        if (rc) return rc;
+        static bool attr_set = false;
+        if (!attr_set) {
+            HVS_CUDA_TRY(cudaFuncSetAttribute(mhc_stream_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+            attr_set = true;
+        }
+        FusedParams p;
+        p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale; p.saved = saved;
+        p.dw_part = ws.dw_part; p.cta_accum = ws.cta_accum;
+        p.T = T;
+        p.num_tiles = (int)((T + kTok - 1) / kTok);
+        p.sk_iters = sk_iters; p.eps_rms = eps_rms; p.eps_sk = eps_sk;
+        grid = p.num_tiles < sms ? p.num_tiles : sms;
+        timer_begin(1, stream);
+        mhc_stream_bwd_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tx, tdy, tdx, p);
+        timer_end(1, stream);
+        count_launch();
+        const int rc2 = launch_status();
+        if (rc2) return rc2;
+    }
+    timer_begin(3, stream);
+    const int rc3 = launch_bwd_finalize(ws.dw_part, grid, ws.cta_accum, kCoefWarps * grid, phi, scale, dphi, dscale, dbias, dalpha, stream);
+    timer_end(3, stream);
+    return rc3;
+}

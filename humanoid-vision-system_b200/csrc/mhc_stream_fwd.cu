@@ -48,6 +48,7 @@ struct FwdParams {
     const float* scale;
     __nv_bfloat16* u;
     float* coeffs;
+    float* saved;          // [T, 28]: un-normalised projection raw[24], sum of squares, pad (for the fused backward)
     int64_t T;
     int num_tiles;
     int sk_iters;
@@ -155,6 +156,14 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 o[i] = hpre;
                 o[kN + i] = hpost;
                 *reinterpret_cast<float4*>(o + 2 * kN + 4 * i) = make_float4(p0, p1, p2, p3);
+            }
+            if (p.saved != nullptr && tok < p.T) {
+                float* o = p.saved + tok * HVS_MHC_SAVED_STRIDE;
+                o[i] = r[i];
+                o[kN + i] = r[kN + i];
+                *reinterpret_cast<float4*>(o + 2 * kN + 4 * i) =
+                    make_float4(r[2 * kN + 4 * i], r[2 * kN + 4 * i + 1], r[2 * kN + 4 * i + 2], r[2 * kN + 4 * i + 3]);
+                o[kL + i] = i == 0 ? r[kL] : 0.f;
             }
             __threadfence_block();
             bar_arrive(kBarCoef + buf, kWorkerThreads + 64);
@@ -360,6 +369,14 @@ mhc_stream_post_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
 extern "C" int hvs_mhc_stream_fwd(const void* x, const float* phi, const float* bias, const float* alpha,
                                   const float* scale, void* y, void* u, float* coeffs, int64_t T, int n, int C,
                                   int sk_iters, float eps_rms, float eps_sk, uint32_t flags, void* stream) {
+    return hvs_mhc_stream_fwd_save(x, phi, bias, alpha, scale, y, u, coeffs, nullptr, T, n, C, sk_iters, eps_rms, eps_sk,
+                                   flags, stream);
+}
+
+extern "C" int hvs_mhc_stream_fwd_save(const void* x, const float* phi, const float* bias, const float* alpha,
+                                       const float* scale, void* y, void* u, float* coeffs, float* saved, int64_t T,
+                                       int n, int C, int sk_iters, float eps_rms, float eps_sk, uint32_t flags,
+                                       void* stream) {
     using namespace hvs;
     if (T < 0) return HVS_ERR_BAD_ARG;
     if (n != kN || C != kC || sk_iters < 0 || sk_iters > 64) return HVS_ERR_UNSUPPORTED;
@@ -368,7 +385,7 @@ extern "C" int hvs_mhc_stream_fwd(const void* x, const float* phi, const float* 
     if (flags & HVS_MHC_SPLIT_PHI) return HVS_ERR_UNSUPPORTED;
     if (T * kN >= (int64_t)1 << 31) return HVS_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(u) |
-         reinterpret_cast<uintptr_t>(coeffs)) & 15)
+         reinterpret_cast<uintptr_t>(coeffs) | reinterpret_cast<uintptr_t>(saved)) & 15)
         return HVS_ERR_ALIGNMENT;
     if (T == 0) return HVS_OK;
     CUtensorMap tx, ty;
@@ -380,6 +397,7 @@ extern "C" int hvs_mhc_stream_fwd(const void* x, const float* phi, const float* 
     p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale;
     p.u = reinterpret_cast<__nv_bfloat16*>(u);
     p.coeffs = coeffs;
+    p.saved = saved;
     p.T = T;
     p.num_tiles = (int)((T + kTileTok - 1) / kTileTok);
     p.sk_iters = sk_iters; p.eps_rms = eps_rms; p.eps_sk = eps_sk;

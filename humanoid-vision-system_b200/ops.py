@@ -32,9 +32,11 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 def mhc_stream_fwd(x: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor, alpha: torch.Tensor,
                    scale: torch.Tensor, sk_iters: int = 20, eps_rms: float = 1e-8, eps_sk: float = 1e-8,
                    want_y: bool = True, want_u: bool = False, want_coeffs: bool = False,
-                   split_phi: bool = False, out: Optional[torch.Tensor] = None
+                   split_phi: bool = False, out: Optional[torch.Tensor] = None,
+                   saved: Optional[torch.Tensor] = None
                    ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """x [T,n,C] bf16 -> (y [T,n,C] bf16, u [T,C] bf16, coeffs [T,n*n+2n] fp32)."""
+    """x [T,n,C] bf16 -> (y [T,n,C] bf16, u [T,C] bf16, coeffs [T,n*n+2n] fp32).
+    `saved` ([T, SAVED_STRIDE] fp32, from `new_saved`) receives the statistics `mhc_stream_bwd_saved` consumes."""
     _need_cuda(x, phi, bias, alpha, scale)
     if x.dtype != torch.bfloat16 or x.dim() != 3 or not x.is_contiguous():
         raise _lib.HvsError("x must be a contiguous [T,n,C] bf16 tensor")
@@ -47,10 +49,44 @@ def mhc_stream_fwd(x: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor, alpha
     u = torch.empty((t, c), dtype=torch.bfloat16, device=x.device) if want_u else None
     co = torch.empty((t, k), dtype=torch.float32, device=x.device) if want_coeffs else None
     flags = _lib.HVS_MHC_SPLIT_PHI if split_phi else 0
-    check(_lib.load().hvs_mhc_stream_fwd(_ptr(x), _ptr(phi), _ptr(bias), _ptr(alpha), _ptr(scale), _ptr(y), _ptr(u),
-                                         _ptr(co), t, n, c, sk_iters, eps_rms, eps_sk, flags, _stream()),
-          "hvs_mhc_stream_fwd")
+    if saved is not None:
+        _need_cuda(saved)
+        if saved.dtype != torch.float32 or tuple(saved.shape) != (t, _lib.HVS_MHC_SAVED_STRIDE) or not saved.is_contiguous():
+            raise _lib.HvsError("saved must be contiguous [T, HVS_MHC_SAVED_STRIDE] fp32")
+    check(_lib.load().hvs_mhc_stream_fwd_save(_ptr(x), _ptr(phi), _ptr(bias), _ptr(alpha), _ptr(scale), _ptr(y), _ptr(u),
+                                              _ptr(co), _ptr(saved), t, n, c, sk_iters, eps_rms, eps_sk, flags, _stream()),
+          "hvs_mhc_stream_fwd_save")
     return y, u, co
+
+
+def new_saved(x: torch.Tensor) -> torch.Tensor:
+    """Buffer for the forward's per-token statistics (112 B/token)."""
+    return torch.empty((x.shape[0], _lib.HVS_MHC_SAVED_STRIDE), dtype=torch.float32, device=x.device)
+
+
+def mhc_stream_bwd_saved(x: torch.Tensor, dy: torch.Tensor, saved: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor,
+                         alpha: torch.Tensor, scale: torch.Tensor, sk_iters: int = 20, eps_rms: float = 1e-8,
+                         eps_sk: float = 1e-8, out: Optional[torch.Tensor] = None,
+                         workspace: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Fused single-pass backward (dx and every parameter gradient) from the statistics saved by the forward."""
+    _need_cuda(x, dy, saved, phi, bias, alpha, scale)
+    if dy.dtype != torch.bfloat16 or dy.shape != x.shape or not dy.is_contiguous() or not x.is_contiguous():
+        raise _lib.HvsError("dy must be contiguous bf16 with x's shape")
+    t, n, c = x.shape
+    if saved.dtype != torch.float32 or tuple(saved.shape) != (t, _lib.HVS_MHC_SAVED_STRIDE) or not saved.is_contiguous():
+        raise _lib.HvsError("saved must be contiguous [T, HVS_MHC_SAVED_STRIDE] fp32")
+    lib = _lib.load()
+    dx = out if out is not None else torch.empty_like(x)
+    dphi = torch.empty_like(phi)
+    dbias = torch.empty_like(bias)
+    dalpha = torch.empty_like(alpha)
+    dscale = torch.empty_like(scale)
+    ws_bytes = int(lib.hvs_mhc_stream_bwd_saved_workspace(t, n, c))
+    ws = workspace if workspace is not None else torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=x.device)
+    check(lib.hvs_mhc_stream_bwd_saved(_ptr(x), _ptr(dy), _ptr(saved), _ptr(phi), _ptr(bias), _ptr(alpha), _ptr(scale),
+                                       _ptr(dx), _ptr(dphi), _ptr(dbias), _ptr(dalpha), _ptr(dscale), t, n, c, sk_iters,
+                                       eps_rms, eps_sk, 0, _ptr(ws), ws.numel(), _stream()), "hvs_mhc_stream_bwd_saved")
+    return {"dx": dx, "dphi": dphi, "dbias": dbias, "dalpha": dalpha, "dscale": dscale}
 
 
 def mhc_stream_post(x: torch.Tensor, coeffs: torch.Tensor, fu: torch.Tensor) -> torch.Tensor:

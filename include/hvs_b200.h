@@ -63,6 +63,15 @@ int hvs_mhc_stream_fwd(const void* x, const float* phi, const float* bias, const
                        const float* scale, void* y, void* u, float* coeffs, int64_t T, int n, int C,
                        int sk_iters, float eps_rms, float eps_sk, uint32_t flags, void* stream);
 
+/* Training forward: the same kernel, additionally writing the per-token statistics the fused backward
+ * needs instead of recomputing them:
+ *   saved [T, HVS_MHC_SAVED_STRIDE] fp32 = raw[n*n+2n] (x . bf16(scale*phi), before the RMS factor, alpha and
+ *   bias) | sum_k x_k^2 | zero pad.  112 B/token next to the 8192 B/token of x and y. */
+#define HVS_MHC_SAVED_STRIDE 28
+int hvs_mhc_stream_fwd_save(const void* x, const float* phi, const float* bias, const float* alpha,
+                            const float* scale, void* y, void* u, float* coeffs, float* saved, int64_t T, int n,
+                            int C, int sk_iters, float eps_rms, float eps_sk, uint32_t flags, void* stream);
+
 /* y = H_res x + H_post (x) fu  with coefficients produced by hvs_mhc_stream_fwd(y=NULL);
  * fu [T, C] bf16 is the wrapped layer's output F(u). */
 int hvs_mhc_stream_post(const void* x, const float* coeffs, const void* fu, void* y, int64_t T, int n,
@@ -78,6 +87,18 @@ int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* phi, const fl
                        float* dalpha, float* dscale, int64_t T, int n, int C, int sk_iters,
                        float eps_rms, float eps_sk, uint32_t flags, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* Backward of hvs_mhc_stream_fwd_save (F = identity) in ONE fused kernel: dx and dphi/dscale/dbias/dalpha in a
+ * single pass over x and dy (12288 + 112 B/token); `saved` is the forward's [T, HVS_MHC_SAVED_STRIDE] record.
+ * The Sinkhorn forward iterations are replayed from the saved logits and differentiated exactly.
+ * Same outputs and conventions as hvs_mhc_stream_bwd.  sk_iters <= 24.
+ * workspace: hvs_mhc_stream_bwd_saved_workspace(T, n, C) bytes, 256-byte aligned. */
+size_t hvs_mhc_stream_bwd_saved_workspace(int64_t T, int n, int C);
+int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const float* saved, const float* phi,
+                             const float* bias, const float* alpha, const float* scale, void* dx, float* dphi,
+                             float* dbias, float* dalpha, float* dscale, int64_t T, int n, int C, int sk_iters,
+                             float eps_rms, float eps_sk, uint32_t flags, void* workspace, size_t workspace_bytes,
+                             void* stream);
 
 /* Optional per-kernel timing of the stream-mHC launches (used by bench.py for the roofline line).
  * When enabled, each launch is bracketed by CUDA events on the launching stream;
