@@ -36,7 +36,6 @@ constexpr int kStages = 3;
 constexpr int kWorkers = 16;
 constexpr int kWorkerThreads = kWorkers * 32;
 constexpr int kThreads = (kWorkers + 4) * 32;         // + coefficient warp 0, front warp, coefficient warps 1, 2
-constexpr int kWorkerRegs = 104, kRoleRegs = 64;
 constexpr int kStageBytes = 65536;                    // 8 channel blocks x ([x box 4 KB][dy box 4 KB]); box = 4 stream atoms of 8 tokens x 128 B
 constexpr int kSaved = HVS_MHC_SAVED_STRIDE;          // floats per token in the saved record: raw[24], sum x^2, pad
 constexpr int kMaxIters = 24;
@@ -52,7 +51,8 @@ constexpr int kOffEt = kOffWrec + kStages * kWrecBytes;           // per stage: 
 constexpr int kEtBytes = 1024;
 constexpr int kSkWords = kTok * kMaxIters * 8;
 constexpr int kOffSk = kOffEt + kStages * kEtBytes;
-constexpr int kOffBar = kOffSk + kCoefWarps * kSkWords * 4;
+constexpr int kOffBias = kOffSk + kCoefWarps * kSkWords * 4;    // bias[24] staged once (float4 broadcast reads)
+constexpr int kOffBar = kOffBias + 128;
 constexpr int kOffTmem = kOffBar + 5 * kStages * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffG % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0, "alignment");
@@ -124,6 +124,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         }
         fence_mbar_init();
     }
+    if (threadIdx.x < kL) reinterpret_cast<float*>(smem + kOffBias)[threadIdx.x] = __ldg(p.bias + threadIdx.x);
     if (warp == kWorkers + 1) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
@@ -142,7 +143,6 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     tc_fence_after();
 
     if (warp >= kWorkers) {
-      reg_dealloc<kRoleRegs>();
       if (warp == kWorkers + 1) {
         // ===================================================== front thread: loads, MMA issue, stores
         if (lane == 0) {
@@ -213,182 +213,231 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         }
       } else {
         // ===================================================== coefficient warps (warps 16, 18, 19 <-> stage 0, 1, 2)
-        // Four lanes per token: lane (tk, i) owns row i of the token's 4x4 block as two packed fp32x2 registers
-        // A = (p_i0,p_i1), B = (p_i2,p_i3) and gate i of H_pre / H_post.  Row sums are local, column sums take two
-        // xor-shuffles inside the 4-lane group.
+        // lane = token: the whole 4x4 block of token lane%8 lives in this lane's registers as packed fp32x2 rows,
+        // so the 20 forward iterations and the exact reverse sweep are one shuffle-free dependent chain with
+        // four-way instruction-level parallelism.  Lanes 8..31 repeat tokens 0..7 (lane / 8 = part) and take a
+        // quarter of the epilogue stores / accumulators each.
         const int cw = warp == kWorkers ? 0 : warp - (kWorkers + 1);
         const int s = cw;
-        const int tk = lane >> 2, i = lane & 3, gbase = lane & ~3;
-        const float b_pre = __ldg(p.bias + i), b_post = __ldg(p.bias + kN + i);
-        const float4 b_res = __ldg(reinterpret_cast<const float4*>(p.bias + 2 * kN) + i);
+        const int tk = lane & 7, part = lane >> 3;
         const float a_pre = __ldg(p.alpha + 0), a_post = __ldg(p.alpha + 1), a_res = __ldg(p.alpha + 2);
         const float eps = p.eps_sk;
         const u64 eps2 = pk2(eps, eps);
-        float acc_b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dbias: pre_i, post_i, res_i0..3
-        float acc_a[3] = {0.f, 0.f, 0.f};                  // dalpha terms of this lane
-        float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + tk * (kMaxIters * 8);
-        const float* rs = reinterpret_cast<const float*>(smem + kOffSaved + s * kSavedBytes) + tk * kSaved;
-        const float* gs = reinterpret_cast<const float*>(smem + kOffG + s * 512) + tk * 16 + 4 * i;
+        float acc_b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dbias of logits 6*part .. 6*part+5, this lane's token
+        float acc_a[3] = {0.f, 0.f, 0.f};                  // dalpha terms (part 0 lanes)
+        float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + tk * 8;     // [iter][token][dr x4 | c x4]
+        const float4* rs4 = reinterpret_cast<const float4*>(smem + kOffSaved + s * kSavedBytes + tk * (kSaved * 4));
+        const float4* gs4 = reinterpret_cast<const float4*>(smem + kOffG + s * 512 + tk * 64);
+        const float4* bs4 = reinterpret_cast<const float4*>(smem + kOffBias);
         uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
         uint8_t* et = smem + kOffEt + s * kEtBytes;
-        auto gsum2 = [](u64 v) {                           // sum over the 4 lanes of a group, both halves
-            float a, b;
-            upk2(v, a, b);
-            a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
-            a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
-            return pk2(a, b);
-        };
+        uint32_t et_off[6];                                // E-tile byte offsets of this lane's six logits
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const int r = 6 * part + q;
+            et_off[q] = (uint32_t)((r >> 3) * 128 + (r & 7) * 16 + tk * 2);
+        }
         for (int it = cw; it < n_local; it += kCoefWarps) {
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
             bar_sync(kBarRec + s, 8 * 32 + 32);
             mbar_wait(&bar_full[s], ph);                   // the saved records came in with the tile
             const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + tk;
             const bool valid = tok < p.T;                  // rows past T: x = dy = 0 (TMA fill), records not loaded
-            const float ssq = valid ? rs[kL] : 1.0f;
-            const float raw_pre = valid ? rs[i] : 0.f, raw_post = valid ? rs[kN + i] : 0.f;
-            const float4 raw_res = valid ? *reinterpret_cast<const float4*>(rs + 2 * kN + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 gq = *reinterpret_cast<const float4*>(gs);                        // row i of G = dy x^T
-            const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(ssq, 1.0f / kRow, p.eps_rms)));
-            const float hpre = sigmoid_f32(fmaf(a_pre, raw_pre * inv_rms, b_pre));
-            const float hpost = 2.0f * sigmoid_f32(fmaf(a_post, raw_post * inv_rms, b_post));
-            u64 A, B;
+            const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(valid ? rs4[6].x : 1.0f, 1.0f / kRow, p.eps_rms)));
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float hpre[4], hpost[4];
             {
-                const float l0 = fmaf(a_res, raw_res.x * inv_rms, b_res.x), l1 = fmaf(a_res, raw_res.y * inv_rms, b_res.y);
-                const float l2 = fmaf(a_res, raw_res.z * inv_rms, b_res.z), l3 = fmaf(a_res, raw_res.w * inv_rms, b_res.w);
+                const float4 rp = valid ? rs4[0] : zero4, rq = valid ? rs4[1] : zero4;
+                const float4 bp = bs4[0], bq = bs4[1];
+                hpre[0] = sigmoid_f32(fmaf(a_pre, rp.x * inv_rms, bp.x)); hpre[1] = sigmoid_f32(fmaf(a_pre, rp.y * inv_rms, bp.y));
+                hpre[2] = sigmoid_f32(fmaf(a_pre, rp.z * inv_rms, bp.z)); hpre[3] = sigmoid_f32(fmaf(a_pre, rp.w * inv_rms, bp.w));
+                hpost[0] = 2.0f * sigmoid_f32(fmaf(a_post, rq.x * inv_rms, bq.x)); hpost[1] = 2.0f * sigmoid_f32(fmaf(a_post, rq.y * inv_rms, bq.y));
+                hpost[2] = 2.0f * sigmoid_f32(fmaf(a_post, rq.z * inv_rms, bq.z)); hpost[3] = 2.0f * sigmoid_f32(fmaf(a_post, rq.w * inv_rms, bq.w));
+            }
+            u64 P[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 rr = valid ? rs4[2 + i] : zero4, bb = bs4[2 + i];
+                const float l0 = fmaf(a_res, rr.x * inv_rms, bb.x), l1 = fmaf(a_res, rr.y * inv_rms, bb.y);
+                const float l2 = fmaf(a_res, rr.z * inv_rms, bb.z), l3 = fmaf(a_res, rr.w * inv_rms, bb.w);
                 const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
                 const float e0 = fast_exp(l0 - mx), e1 = fast_exp(l1 - mx), e2 = fast_exp(l2 - mx), e3 = fast_exp(l3 - mx);
                 const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
-                A = pk2(e0 * r4, e1 * r4);
-                B = pk2(e2 * r4, e3 * r4);
+                P[i][0] = pk2(e0 * r4, e1 * r4);
+                P[i][1] = pk2(e2 * r4, e3 * r4);
             }
             // ---- forward Sinkhorn, the normalisers are kept for the reverse sweep
             for (int k = 0; k < p.sk_iters; ++k) {
-                float sa, sb;
-                upk2(add2(A, B), sa, sb);
-                const float dr = (sa + sb) + eps;
-                const float rr = rcp_approx(dr);
-                const u64 rr2 = pk2(rr, rr);
-                A = mul2(A, rr2); B = mul2(B, rr2);
-                const u64 cA = add2(gsum2(A), eps2), cB = add2(gsum2(B), eps2);
+                float dr[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float sa, sb;
+                    upk2(add2(P[i][0], P[i][1]), sa, sb);
+                    dr[i] = (sa + sb) + eps;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float rr = rcp_approx(dr[i]);
+                    const u64 rr2 = pk2(rr, rr);
+                    P[i][0] = mul2(P[i][0], rr2);
+                    P[i][1] = mul2(P[i][1], rr2);
+                }
+                const u64 c01 = add2(add2(add2(P[0][0], P[1][0]), add2(P[2][0], P[3][0])), eps2);
+                const u64 c23 = add2(add2(add2(P[0][1], P[1][1]), add2(P[2][1], P[3][1])), eps2);
                 float c0, c1, c2, c3;
-                upk2(cA, c0, c1); upk2(cB, c2, c3);
-                A = mul2(A, pk2(rcp_approx(c0), rcp_approx(c1)));
-                B = mul2(B, pk2(rcp_approx(c2), rcp_approx(c3)));
-                skl[k * 8 + i] = dr;
-                if (i == 0) *reinterpret_cast<float4*>(skl + k * 8 + 4) = make_float4(c0, c1, c2, c3);
+                upk2(c01, c0, c1); upk2(c23, c2, c3);
+                const u64 rc01 = pk2(rcp_approx(c0), rcp_approx(c1)), rc23 = pk2(rcp_approx(c2), rcp_approx(c3));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    P[i][0] = mul2(P[i][0], rc01);
+                    P[i][1] = mul2(P[i][1], rc23);
+                }
+                if (part == 0) {
+                    float4* o = reinterpret_cast<float4*>(skl + k * 64);
+                    o[0] = make_float4(dr[0], dr[1], dr[2], dr[3]);
+                    o[1] = make_float4(c0, c1, c2, c3);
+                }
             }
-            // ---- M = P + hpost (x) hpre needs every H_pre of the token; gate gradients from G
-            const float h0 = __shfl_sync(0xffffffffu, hpre, gbase + 0), h1 = __shfl_sync(0xffffffffu, hpre, gbase + 1);
-            const float h2 = __shfl_sync(0xffffffffu, hpre, gbase + 2), h3 = __shfl_sync(0xffffffffu, hpre, gbase + 3);
-            float p0, p1, p2, p3;
-            upk2(A, p0, p1); upk2(B, p2, p3);
-            const float dhpost = fmaf(gq.w, h3, fmaf(gq.z, h2, fmaf(gq.y, h1, gq.x * h0)));
-            float t0 = gq.x * hpost, t1 = gq.y * hpost, t2 = gq.z * hpost, t3 = gq.w * hpost;   // dhpre[j] = sum_i G[i][j] hpost[i]
-            t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
-            t2 += __shfl_xor_sync(0xffffffffu, t2, 1); t3 += __shfl_xor_sync(0xffffffffu, t3, 1);
-            t0 += __shfl_xor_sync(0xffffffffu, t0, 2); t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
-            t2 += __shfl_xor_sync(0xffffffffu, t2, 2); t3 += __shfl_xor_sync(0xffffffffu, t3, 2);
-            const float dhpre = i == 0 ? t0 : i == 1 ? t1 : i == 2 ? t2 : t3;
-            const float dl_pre = dhpre * hpre * (1.0f - hpre);
-            const float dl_post = dhpost * hpost * (1.0f - 0.5f * hpost);
-            {   // M[i][jj] for the workers, paired over the two tokens (2t, 2t+1) a worker thread owns: [tk/2][jj][i][tk&1]
-                float* mp = reinterpret_cast<float*>(wrec + kWrecM) + (tk >> 1) * 32 + i * 2 + (tk & 1);
-                mp[0] = fmaf(hpost, h0, p0);
-                mp[8] = fmaf(hpost, h1, p1);
-                mp[16] = fmaf(hpost, h2, p2);
-                mp[24] = fmaf(hpost, h3, p3);
-            }
-            __syncwarp();                                   // normalisers written by lane 0 of the group are visible
-            // ---- exact reverse sweep through the iterations (dP = G)
-            u64 Da = pk2(gq.x, gq.y), Db = pk2(gq.z, gq.w);
-            for (int k = p.sk_iters - 1; k >= 0; --k) {
-                const float4 cd = *reinterpret_cast<const float4*>(skl + k * 8 + 4);
-                const float dr = skl[k * 8 + i];
-                // column step y = x / c:  dx = (dy - sum_rows dy*y) / c ;  x = y * c
-                const u64 qA = gsum2(mul2(Da, A)), qB = gsum2(mul2(Db, B));
-                const float r0 = rcp_approx(cd.x), r1 = rcp_approx(cd.y), r2 = rcp_approx(cd.z), r3 = rcp_approx(cd.w);
-                Da = fma2(Da, pk2(r0, r1), mul2(qA, pk2(-r0, -r1)));
-                Db = fma2(Db, pk2(r2, r3), mul2(qB, pk2(-r2, -r3)));
-                A = mul2(A, pk2(cd.x, cd.y)); B = mul2(B, pk2(cd.z, cd.w));
-                // row step y = x / dr
-                float qa, qb;
-                upk2(fma2(Db, B, mul2(Da, A)), qa, qb);
-                const float rr = rcp_approx(dr);
-                const float nq = -(qa + qb) * rr;
-                const u64 rr2 = pk2(rr, rr), nq2 = pk2(nq, nq), dd2 = pk2(dr, dr);
-                Da = fma2(Da, rr2, nq2); Db = fma2(Db, rr2, nq2);
-                A = mul2(A, dd2); B = mul2(B, dd2);
-            }
-            // softmax * 4 backward (A,B are back at the softmax output): dl = s * (d - sum(d*s)/4)
-            float dl0, dl1, dl2, dl3;
+            // ---- M = P + hpost (x) hpre for the workers (part p writes column jj = p), gate gradients from G = dy x^T
+            u64 D[4][2];
+            float dl_pre[4], dl_post[4];
             {
+                float dhpre[4] = {0.f, 0.f, 0.f, 0.f};
+                float* mp = reinterpret_cast<float*>(wrec + kWrecM) + (tk >> 1) * 32 + part * 8 + (tk & 1);
+                const float hsel = part == 0 ? hpre[0] : part == 1 ? hpre[1] : part == 2 ? hpre[2] : hpre[3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 g = gs4[i];                                   // row i of G
+                    D[i][0] = pk2(g.x, g.y);
+                    D[i][1] = pk2(g.z, g.w);
+                    const float dhpost = fmaf(g.w, hpre[3], fmaf(g.z, hpre[2], fmaf(g.y, hpre[1], g.x * hpre[0])));
+                    dl_post[i] = dhpost * hpost[i] * (1.0f - 0.5f * hpost[i]);
+                    dhpre[0] = fmaf(g.x, hpost[i], dhpre[0]); dhpre[1] = fmaf(g.y, hpost[i], dhpre[1]);
+                    dhpre[2] = fmaf(g.z, hpost[i], dhpre[2]); dhpre[3] = fmaf(g.w, hpost[i], dhpre[3]);
+                    float p0, p1, p2, p3;
+                    upk2(P[i][0], p0, p1); upk2(P[i][1], p2, p3);
+                    const float psel = part == 0 ? p0 : part == 1 ? p1 : part == 2 ? p2 : p3;
+                    mp[i * 2] = fmaf(hpost[i], hsel, psel);                     // M[i][part]
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dl_pre[j] = dhpre[j] * hpre[j] * (1.0f - hpre[j]);
+            }
+            __syncwarp();                                   // normalisers written by the part-0 lanes are visible
+            // ---- exact reverse sweep through the iterations (dP = G)
+            for (int k = p.sk_iters - 1; k >= 0; --k) {
+                const float4 drv = *reinterpret_cast<const float4*>(skl + k * 64);
+                const float4 cv = *reinterpret_cast<const float4*>(skl + k * 64 + 4);
+                // column step y = x / c:  dx = (dy - sum_rows dy*y) / c ;  x = y * c
+                const u64 rc01 = pk2(rcp_approx(cv.x), rcp_approx(cv.y)), rc23 = pk2(rcp_approx(cv.z), rcp_approx(cv.w));
+                const u64 q01 = add2(fma2(D[2][0], P[2][0], mul2(D[0][0], P[0][0])), fma2(D[3][0], P[3][0], mul2(D[1][0], P[1][0])));
+                const u64 q23 = add2(fma2(D[2][1], P[2][1], mul2(D[0][1], P[0][1])), fma2(D[3][1], P[3][1], mul2(D[1][1], P[1][1])));
+                const u64 nq01 = mul2(q01, pk2(-rcp_approx(cv.x), -rcp_approx(cv.y)));
+                const u64 nq23 = mul2(q23, pk2(-rcp_approx(cv.z), -rcp_approx(cv.w)));
+                const u64 cc01 = pk2(cv.x, cv.y), cc23 = pk2(cv.z, cv.w);
+                const float drr[4] = {drv.x, drv.y, drv.z, drv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    D[i][0] = fma2(D[i][0], rc01, nq01);
+                    D[i][1] = fma2(D[i][1], rc23, nq23);
+                    P[i][0] = mul2(P[i][0], cc01);
+                    P[i][1] = mul2(P[i][1], cc23);
+                    // row step y = x / dr
+                    float qa, qb;
+                    upk2(fma2(D[i][1], P[i][1], mul2(D[i][0], P[i][0])), qa, qb);
+                    const float rr = rcp_approx(drr[i]);
+                    const float nq = -(qa + qb) * rr;
+                    const u64 rr2 = pk2(rr, rr), nq2 = pk2(nq, nq), dd2 = pk2(drr[i], drr[i]);
+                    D[i][0] = fma2(D[i][0], rr2, nq2);
+                    D[i][1] = fma2(D[i][1], rr2, nq2);
+                    P[i][0] = mul2(P[i][0], dd2);
+                    P[i][1] = mul2(P[i][1], dd2);
+                }
+            }
+            // ---- softmax * 4 backward (P is back at the softmax output): dl = s * (d - sum(d*s)/4); e = d raw;
+            //      kappa (RMSNorm backward); dbias / dalpha terms.  Raw values are re-read from the record.
+            float ev[24];
+            float dsum = 0.f, da_pre = 0.f, da_post = 0.f, da_res = 0.f;
+            {
+                const float4 rp = valid ? rs4[0] : zero4, rq = valid ? rs4[1] : zero4;
+                const float rpv[4] = {rp.x, rp.y, rp.z, rp.w}, rqv[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ev[j] = dl_pre[j];
+                    ev[4 + j] = dl_post[j];
+                    da_pre = fmaf(dl_pre[j], rpv[j], da_pre);
+                    da_post = fmaf(dl_post[j], rqv[j], da_post);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
                 float qa, qb;
-                upk2(fma2(Db, B, mul2(Da, A)), qa, qb);
+                upk2(fma2(D[i][1], P[i][1], mul2(D[i][0], P[i][0])), qa, qb);
                 const float nqs = -0.25f * (qa + qb);
                 const u64 nq2 = pk2(nqs, nqs);
-                upk2(mul2(A, add2(Da, nq2)), dl0, dl1);
-                upk2(mul2(B, add2(Db, nq2)), dl2, dl3);
+                upk2(mul2(P[i][0], add2(D[i][0], nq2)), ev[8 + 4 * i], ev[8 + 4 * i + 1]);
+                upk2(mul2(P[i][1], add2(D[i][1], nq2)), ev[8 + 4 * i + 2], ev[8 + 4 * i + 3]);
+                const float4 rr = valid ? rs4[2 + i] : zero4;
+                da_res = fmaf(ev[8 + 4 * i + 3], rr.w, fmaf(ev[8 + 4 * i + 2], rr.z, fmaf(ev[8 + 4 * i + 1], rr.y, fmaf(ev[8 + 4 * i], rr.x, da_res))));
             }
-            // ---- e = d raw, kappa (RMSNorm backward), dbias / dalpha terms
-            acc_b[0] += dl_pre; acc_b[1] += dl_post; acc_b[2] += dl0; acc_b[3] += dl1; acc_b[4] += dl2; acc_b[5] += dl3;
-            acc_a[0] = fmaf(dl_pre, raw_pre * inv_rms, acc_a[0]);
-            acc_a[1] = fmaf(dl_post, raw_post * inv_rms, acc_a[1]);
-            acc_a[2] += fmaf(dl3, raw_res.w, fmaf(dl2, raw_res.z, fmaf(dl1, raw_res.y, dl0 * raw_res.x))) * inv_rms;
-            const float ev[6] = {a_pre * dl_pre * inv_rms, a_post * dl_post * inv_rms, a_res * dl0 * inv_rms,
-                                 a_res * dl1 * inv_rms, a_res * dl2 * inv_rms, a_res * dl3 * inv_rms};
-            // d inv_rms = sum_k e_k raw_k / inv_rms ;  kappa = -d inv_rms * inv_rms^3 / N
-            float dsum = ev[0] * raw_pre + ev[1] * raw_post + (ev[2] * raw_res.x + ev[3] * raw_res.y + ev[4] * raw_res.z + ev[5] * raw_res.w);
-            dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
-            dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
-            // bf16 hi of e for the workers' W e MMA, hi and lo for the dW MMA (operand rows = logits, K = token | 8 + token)
-            const int lg[6] = {i, kN + i, 2 * kN + 4 * i, 2 * kN + 4 * i + 1, 2 * kN + 4 * i + 2, 2 * kN + 4 * i + 3};
-            __nv_bfloat16 hi[6];
+            // ev holds dl (d logits) here.  d inv_rms = sum_k e_k raw_k / inv_rms ;  kappa = -d inv_rms * inv_rms^3 / N
+            dsum = (a_pre * da_pre + a_post * da_post + a_res * da_res) * inv_rms;
+            if (part == 0) {
+                acc_a[0] = fmaf(da_pre, inv_rms, acc_a[0]);
+                acc_a[1] = fmaf(da_post, inv_rms, acc_a[1]);
+                acc_a[2] = fmaf(da_res, inv_rms, acc_a[2]);
+                reinterpret_cast<float*>(wrec + kWrecK)[tk] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
+            }
+            // this lane's six logits: accumulate dbias, scale to e = alpha_g * dl * inv_rms, emit bf16 hi (workers' W e
+            // MMA, dW MMA) and lo (dW MMA; operand rows = logits, K = token | 8 + token)
+            {
+                float mine[6];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                hi[q] = __float2bfloat16_rn(ev[q]);
-                const __nv_bfloat16 lo = __float2bfloat16_rn(ev[q] - __bfloat162float(hi[q]));
-                uint8_t* dst = et + (lg[q] >> 3) * 128 + (lg[q] & 7) * 16 + tk * 2;
-                *reinterpret_cast<__nv_bfloat16*>(dst) = hi[q];
-                *reinterpret_cast<__nv_bfloat16*>(dst + 384) = lo;
+                for (int q = 0; q < 6; ++q) {
+                    mine[q] = part == 0 ? ev[q] : part == 1 ? ev[6 + q] : part == 2 ? ev[12 + q] : ev[18 + q];
+                    acc_b[q] += mine[q];
+                }
+                // alpha of logit 6*part + q: part 0 -> pre,pre,pre,pre,post,post; part 1 -> post,post,res x4; parts 2,3 -> res
+                const float al_lo = part == 0 ? a_pre : part == 1 ? a_post : a_res;     // q = 0,1
+                const float al_mid = part == 0 ? a_pre : a_res;                          // q = 2,3
+                const float al_hi = part == 0 ? a_post : a_res;                          // q = 4,5
+                uint32_t words[3];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const float al = q < 2 ? al_lo : q < 4 ? al_mid : al_hi;
+                    const float e = al * mine[q] * inv_rms;
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(e);
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
+                    *reinterpret_cast<__nv_bfloat16*>(et + et_off[q]) = hi;
+                    *reinterpret_cast<__nv_bfloat16*>(et + et_off[q] + 384) = lo;
+                    if (q & 1) words[q >> 1] |= (uint32_t)__bfloat16_as_ushort(hi) << 16;
+                    else words[q >> 1] = (uint32_t)__bfloat16_as_ushort(hi);
+                }
+                uint32_t* ew = reinterpret_cast<uint32_t*>(wrec) + tk * 12 + 3 * part;
+                ew[0] = words[0]; ew[1] = words[1]; ew[2] = words[2];
             }
-            __nv_bfloat16* eb = reinterpret_cast<__nv_bfloat16*>(wrec) + tk * 24;
-            eb[i] = hi[0];
-            eb[kN + i] = hi[1];
-            *reinterpret_cast<uint2*>(eb + 2 * kN + 4 * i) =
-                make_uint2((uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16),
-                           (uint32_t)__bfloat16_as_ushort(hi[4]) | ((uint32_t)__bfloat16_as_ushort(hi[5]) << 16));
-            if (i == 0) reinterpret_cast<float*>(wrec + kWrecK)[tk] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
             fence_proxy_async_smem();                       // the E tile is read by the tensor core (async proxy)
             __threadfence_block();
             bar_arrive(kBarCoef + s, kWorkerThreads + 32);
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_ed[s]);
         }
-        // fold the 8 token groups of the warp (lanes with equal i) in a fixed order, then the group for dalpha
+        // dbias: sum the 8 tokens of the warp (lanes with equal part) in a fixed order; dalpha likewise over part 0
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
+        for (int o = 1; o < 8; o <<= 1) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) acc_b[k] += __shfl_xor_sync(0xffffffffu, acc_b[k], o);
 #pragma unroll
             for (int k = 0; k < 3; ++k) acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], o);
         }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], 1);
-            acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], 2);
-        }
-        if (lane < 4) {
+        if (tk == 0) {
             float* o = p.cta_accum + ((size_t)blockIdx.x * kCoefWarps + cw) * kAccum;
-            o[i] = acc_b[0];
-            o[kN + i] = acc_b[1];
-            o[2 * kN + 4 * i + 0] = acc_b[2]; o[2 * kN + 4 * i + 1] = acc_b[3];
-            o[2 * kN + 4 * i + 2] = acc_b[4]; o[2 * kN + 4 * i + 3] = acc_b[5];
-            if (i == 0) { o[kL] = acc_a[0]; o[kL + 1] = acc_a[1]; o[kL + 2] = acc_a[2]; }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) o[6 * part + q] = acc_b[q];
+            if (part == 0) { o[kL] = acc_a[0]; o[kL + 1] = acc_a[1]; o[kL + 2] = acc_a[2]; }
         }
       }
     } else {
         // ===================================================== worker warps
-        reg_alloc<kWorkerRegs>();
         const int w = warp, g = lane >> 2, t = lane & 3;
         // W = bf16(scale * phi) as the A operand of  dx_proj^T = W e^T : m-tile (jj, mt) rows g / g+8 are the
         // channel pair 32w + 4g + 2mt + {0,1} of stream jj, k = logits.  48 registers, resident for the whole kernel.
@@ -419,8 +468,34 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         const int q = w & 3, jcol = w >> 2;               // tensor-memory lane quadrant / G column group of this warp
         const uint32_t tm_gs = tmem_base + ((uint32_t)(32 * q) << 16) + kColGs + 8u * jcol;
 
+        // G blocks of a tile out of tensor memory: lanes 0..15 of quadrant q hold the dy rows (stream 2(q-2) + lane/8,
+        // token lane%8); this warp takes x stream jcol.  Warps of quadrants 2 and 3 only.
+        auto readout = [&](int tile) {
+            const int s = tile % kStages;
+            mbar_wait(&bar_gs[s], (uint32_t)(tile / kStages) & 1u);
+            tc_fence_after();
+            uint32_t v[8];
+            tmem_ld8(tm_gs + 32u * s, v);
+            tmem_wait_ld();
+            const int tok = lane & 7;
+            uint32_t val = v[0];
+#pragma unroll
+            for (int c = 1; c < 8; ++c) val = tok == c ? v[c] : val;
+            if (lane < 16)
+                reinterpret_cast<uint32_t*>(smem + kOffG + s * 512)[tok * 16 + (2 * (q - 2) + (lane >> 3)) * 4 + jcol] = val;
+            tc_fence_before();
+            __threadfence_block();
+            bar_arrive(kBarRec + s, 8 * 32 + 32);
+        };
         for (int step = 0; step < n_local + 2; ++step) {
             const int k = step - 2;
+            // the next tile's G is read out as soon as its MMAs are done: before this step's dx if they already are
+            const bool ro = step < n_local && q >= 2;
+            bool ro_done = false;
+            if (ro && __all_sync(0xffffffffu, mbar_test_wait(&bar_gs[step % kStages], (uint32_t)(step / kStages) & 1u))) {
+                readout(step);
+                ro_done = true;
+            }
             if (k >= 0) {
                 // ============ dx for tokens 2t, 2t+1 of tile k, channels 32w + 4g .. +3 of every stream
                 const int s = k % kStages;
@@ -474,25 +549,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_dxr[s]);
             }
-            if (step < n_local && q >= 2) {
-                // ============ G blocks of tile `step` out of tensor memory: lanes 0..15 of quadrant q hold the
-                // dy rows (stream 2(q-2) + lane/8, token lane%8); this warp takes x stream jcol
-                const int s = step % kStages;
-                mbar_wait(&bar_gs[s], (uint32_t)(step / kStages) & 1u);
-                tc_fence_after();
-                uint32_t v[8];
-                tmem_ld8(tm_gs + 32u * s, v);
-                tmem_wait_ld();
-                const int tok = lane & 7;
-                uint32_t val = v[0];
-#pragma unroll
-                for (int c = 1; c < 8; ++c) val = tok == c ? v[c] : val;
-                if (lane < 16)
-                    reinterpret_cast<uint32_t*>(smem + kOffG + s * 512)[tok * 16 + (2 * (q - 2) + (lane >> 3)) * 4 + jcol] = val;
-                tc_fence_before();
-                __threadfence_block();
-                bar_arrive(kBarRec + s, 8 * 32 + 32);
-            }
+            if (ro && !ro_done) readout(step);
         }
         // ============ dW of this CTA out of tensor memory (every MMA has been committed before the last barrier phase)
         {

@@ -40,4 +40,21 @@ try:
     res["bwd_GBs_med"] = 12288 * T / med / 1e6
 except Exception as e:
     res["bwd"] = str(e)
+try:
+    saved = hvs_b200.ops.new_saved(x)
+    dx = torch.empty_like(x)
+    ws = torch.empty(int(hvs_b200._lib.load().hvs_mhc_stream_bwd_saved_workspace(T, 4, 512)), dtype=torch.uint8, device=dev)
+    def fwd_s():
+        hvs_b200.ops.mhc_stream_fwd(x, phi, bias, alpha, scale, out=y, saved=saved)
+    def bwd_s():
+        hvs_b200.ops.mhc_stream_bwd_saved(x, dy, saved, phi, bias, alpha, scale, out=dx, workspace=ws)
+    med, mn = timeit(fwd_s, iters)
+    res["fwd_save_ms_med"] = med; res["fwd_save_GBs"] = (8192 + 112) * T / med / 1e6
+    med, mn = timeit(bwd_s, iters)
+    res["bwd_fused_ms_med"] = med; res["bwd_fused_ms_min"] = mn
+    res["bwd_fused_GBs_med"] = (12288 + 112) * T / med / 1e6
+    res["fwd_bwd_fused_ms"] = res["fwd_save_ms_med"] + med
+    res["fwd_bwd_frac_of_6548.8"] = 20480 * T / (res["fwd_bwd_fused_ms"]) / 1e6 / 6548.8
+except Exception as e:
+    res["bwd_fused"] = str(e)
 print(json.dumps(res))
