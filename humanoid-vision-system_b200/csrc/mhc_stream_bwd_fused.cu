@@ -46,23 +46,26 @@ constexpr int kSavedBytes = kTok * kSaved * 4;        // 896
 constexpr int kOffSaved = kStages * kStageBytes;
 constexpr int kOffG = kOffSaved + kStages * kSavedBytes;          // [stage][token][i][j] fp32
 constexpr int kOffWrec = kOffG + kStages * 512;                   // per stage: e bf16 pairs [8][12] | M pairs [4][4][4][2] | kappa [8]
-constexpr int kWrecBytes = 1024, kWrecM = 384, kWrecK = 896;
+                                                                  //            | alpha_g * inv_rms [8][3] | d logits [8][24]
+constexpr int kWrecBytes = 1792, kWrecM = 384, kWrecK = 896, kWrecS = 928, kWrecDl = 1024;
 constexpr int kOffEt = kOffWrec + kStages * kWrecBytes;           // per stage: E tile, 24 rows x 16 K bf16, no swizzle (768 B)
-constexpr int kEtBytes = 1024;
+constexpr int kEtBytes = 768;
+constexpr int kOffInit = kOffEt + kStages * kEtBytes;             // per stage: Sinkhorn start P0 [8][16] | H_pre, H_post [8][8] | inv_rms [8]
+constexpr int kInitBytes = 800, kInitH = 512, kInitR = 768;
 constexpr int kSkWords = kTok * kMaxIters * 8;
-constexpr int kOffSk = kOffEt + kStages * kEtBytes;
+constexpr int kOffSk = kOffInit + kStages * kInitBytes;
 constexpr int kOffBias = kOffSk + kCoefWarps * kSkWords * 4;    // bias[24] staged once (float4 broadcast reads)
 constexpr int kOffBar = kOffBias + 128;
 constexpr int kOffTmem = kOffBar + 5 * kStages * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
-static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffG % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0, "alignment");
+static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffG % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0 && kOffInit % 16 == 0 && kOffSk % 16 == 0, "alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColDw = 0;                        // 16 column ranges x 24: blocks 2p (lanes +0) and 2p+1 (lanes +16)
 constexpr uint32_t kColGs = 384;                      // 32 columns per stage
 
-constexpr int kBarRec = 1 /*,2,3*/, kBarCoef = 4 /*,5,6*/;
+constexpr int kBarRec = 1 /*,2,3*/, kBarCoef = 4 /*,5,6*/, kBarW = 7;
 
 struct FusedParams {
     const float* phi;
@@ -220,51 +223,51 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         const int cw = warp == kWorkers ? 0 : warp - (kWorkers + 1);
         const int s = cw;
         const int tk = lane & 7, part = lane >> 3;
+        const int tk4 = lane >> 2, i4 = lane & 3;          // prologue layout: four lanes per token, lane i4 owns row i4
         const float a_pre = __ldg(p.alpha + 0), a_post = __ldg(p.alpha + 1), a_res = __ldg(p.alpha + 2);
+        const float b_pre4 = __ldg(p.bias + i4), b_post4 = __ldg(p.bias + kN + i4);
+        const float4 b_res4 = __ldg(reinterpret_cast<const float4*>(p.bias + 2 * kN) + i4);
         const float eps = p.eps_sk;
         const u64 eps2 = pk2(eps, eps);
-        float acc_b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dbias of logits 6*part .. 6*part+5, this lane's token
         float acc_a[3] = {0.f, 0.f, 0.f};                  // dalpha terms (part 0 lanes)
         float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + tk * 8;     // [iter][token][dr x4 | c x4]
-        const float4* rs4 = reinterpret_cast<const float4*>(smem + kOffSaved + s * kSavedBytes + tk * (kSaved * 4));
+        const float* rsv = reinterpret_cast<const float*>(smem + kOffSaved + s * kSavedBytes);
+        const float4* rs4 = reinterpret_cast<const float4*>(rsv + tk * kSaved);
         const float4* gs4 = reinterpret_cast<const float4*>(smem + kOffG + s * 512 + tk * 64);
-        const float4* bs4 = reinterpret_cast<const float4*>(smem + kOffBias);
         uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
-        uint8_t* et = smem + kOffEt + s * kEtBytes;
-        uint32_t et_off[6];                                // E-tile byte offsets of this lane's six logits
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            const int r = 6 * part + q;
-            et_off[q] = (uint32_t)((r >> 3) * 128 + (r & 7) * 16 + tk * 2);
-        }
+        float* init = reinterpret_cast<float*>(smem + kOffInit + s * kInitBytes);
         for (int it = cw; it < n_local; it += kCoefWarps) {
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-            bar_sync(kBarRec + s, 8 * 32 + 32);
             mbar_wait(&bar_full[s], ph);                   // the saved records came in with the tile
-            const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok + tk;
-            const bool valid = tok < p.T;                  // rows past T: x = dy = 0 (TMA fill), records not loaded
-            const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(valid ? rs4[6].x : 1.0f, 1.0f / kRow, p.eps_rms)));
-            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            float hpre[4], hpost[4];
+            const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok;
+            // ---- prologue, four lanes per token: inverse RMS, gates, softmax start of row i4 -> shared memory.
+            // Rows past T: x = dy = 0 (TMA fill) and the records were not loaded; they run on zeros.
             {
-                const float4 rp = valid ? rs4[0] : zero4, rq = valid ? rs4[1] : zero4;
-                const float4 bp = bs4[0], bq = bs4[1];
-                hpre[0] = sigmoid_f32(fmaf(a_pre, rp.x * inv_rms, bp.x)); hpre[1] = sigmoid_f32(fmaf(a_pre, rp.y * inv_rms, bp.y));
-                hpre[2] = sigmoid_f32(fmaf(a_pre, rp.z * inv_rms, bp.z)); hpre[3] = sigmoid_f32(fmaf(a_pre, rp.w * inv_rms, bp.w));
-                hpost[0] = 2.0f * sigmoid_f32(fmaf(a_post, rq.x * inv_rms, bq.x)); hpost[1] = 2.0f * sigmoid_f32(fmaf(a_post, rq.y * inv_rms, bq.y));
-                hpost[2] = 2.0f * sigmoid_f32(fmaf(a_post, rq.z * inv_rms, bq.z)); hpost[3] = 2.0f * sigmoid_f32(fmaf(a_post, rq.w * inv_rms, bq.w));
-            }
-            u64 P[4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 rr = valid ? rs4[2 + i] : zero4, bb = bs4[2 + i];
-                const float l0 = fmaf(a_res, rr.x * inv_rms, bb.x), l1 = fmaf(a_res, rr.y * inv_rms, bb.y);
-                const float l2 = fmaf(a_res, rr.z * inv_rms, bb.z), l3 = fmaf(a_res, rr.w * inv_rms, bb.w);
+                const bool v4 = tok0 + tk4 < p.T;
+                const float* r = rsv + tk4 * kSaved;
+                const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(v4 ? r[kL] : 1.0f, 1.0f / kRow, p.eps_rms)));
+                const float raw_pre = v4 ? r[i4] : 0.f, raw_post = v4 ? r[kN + i4] : 0.f;
+                const float4 rr = v4 ? *reinterpret_cast<const float4*>(r + 2 * kN + 4 * i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float l0 = fmaf(a_res, rr.x * inv_rms, b_res4.x), l1 = fmaf(a_res, rr.y * inv_rms, b_res4.y);
+                const float l2 = fmaf(a_res, rr.z * inv_rms, b_res4.z), l3 = fmaf(a_res, rr.w * inv_rms, b_res4.w);
                 const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
                 const float e0 = fast_exp(l0 - mx), e1 = fast_exp(l1 - mx), e2 = fast_exp(l2 - mx), e3 = fast_exp(l3 - mx);
                 const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
-                P[i][0] = pk2(e0 * r4, e1 * r4);
-                P[i][1] = pk2(e2 * r4, e3 * r4);
+                *reinterpret_cast<float4*>(init + tk4 * 16 + 4 * i4) = make_float4(e0 * r4, e1 * r4, e2 * r4, e3 * r4);
+                init[kInitH / 4 + tk4 * 8 + i4] = sigmoid_f32(fmaf(a_pre, raw_pre * inv_rms, b_pre4));
+                init[kInitH / 4 + tk4 * 8 + kN + i4] = 2.0f * sigmoid_f32(fmaf(a_post, raw_post * inv_rms, b_post4));
+                if (i4 == 0) init[kInitR / 4 + tk4] = inv_rms;
+            }
+            __syncwarp();
+            // ---- lane = token from here on
+            const bool valid = tok0 + tk < p.T;
+            const float inv_rms = init[kInitR / 4 + tk];
+            u64 P[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(init + tk * 16 + 4 * i);
+                P[i][0] = pk2(v.x, v.y);
+                P[i][1] = pk2(v.z, v.w);
             }
             // ---- forward Sinkhorn, the normalisers are kept for the reverse sweep
             for (int k = 0; k < p.sk_iters; ++k) {
@@ -298,10 +301,15 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     o[1] = make_float4(c0, c1, c2, c3);
                 }
             }
-            // ---- M = P + hpost (x) hpre for the workers (part p writes column jj = p), gate gradients from G = dy x^T
+            // ---- G = dy x^T of the tile (read out of tensor memory by the workers)
+            bar_sync(kBarRec + s, 8 * 32 + 32);
+            // ---- M = P + hpost (x) hpre for the workers (part p writes column jj = p), gate gradients from G
             u64 D[4][2];
-            float dl_pre[4], dl_post[4];
+            float dl[24];
             {
+                const float4 hp = *reinterpret_cast<const float4*>(init + kInitH / 4 + tk * 8);
+                const float4 hq = *reinterpret_cast<const float4*>(init + kInitH / 4 + tk * 8 + 4);
+                const float hpre[4] = {hp.x, hp.y, hp.z, hp.w}, hpost[4] = {hq.x, hq.y, hq.z, hq.w};
                 float dhpre[4] = {0.f, 0.f, 0.f, 0.f};
                 float* mp = reinterpret_cast<float*>(wrec + kWrecM) + (tk >> 1) * 32 + part * 8 + (tk & 1);
                 const float hsel = part == 0 ? hpre[0] : part == 1 ? hpre[1] : part == 2 ? hpre[2] : hpre[3];
@@ -311,7 +319,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     D[i][0] = pk2(g.x, g.y);
                     D[i][1] = pk2(g.z, g.w);
                     const float dhpost = fmaf(g.w, hpre[3], fmaf(g.z, hpre[2], fmaf(g.y, hpre[1], g.x * hpre[0])));
-                    dl_post[i] = dhpost * hpost[i] * (1.0f - 0.5f * hpost[i]);
+                    dl[4 + i] = dhpost * hpost[i] * (1.0f - 0.5f * hpost[i]);
                     dhpre[0] = fmaf(g.x, hpost[i], dhpre[0]); dhpre[1] = fmaf(g.y, hpost[i], dhpre[1]);
                     dhpre[2] = fmaf(g.z, hpost[i], dhpre[2]); dhpre[3] = fmaf(g.w, hpost[i], dhpre[3]);
                     float p0, p1, p2, p3;
@@ -320,120 +328,110 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     mp[i * 2] = fmaf(hpost[i], hsel, psel);                     // M[i][part]
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dl_pre[j] = dhpre[j] * hpre[j] * (1.0f - hpre[j]);
+                for (int j = 0; j < 4; ++j) dl[j] = dhpre[j] * hpre[j] * (1.0f - hpre[j]);
             }
-            __syncwarp();                                   // normalisers written by the part-0 lanes are visible
-            // ---- exact reverse sweep through the iterations (dP = G)
-            for (int k = p.sk_iters - 1; k >= 0; --k) {
-                const float4 drv = *reinterpret_cast<const float4*>(skl + k * 64);
-                const float4 cv = *reinterpret_cast<const float4*>(skl + k * 64 + 4);
-                // column step y = x / c:  dx = (dy - sum_rows dy*y) / c ;  x = y * c
-                const u64 rc01 = pk2(rcp_approx(cv.x), rcp_approx(cv.y)), rc23 = pk2(rcp_approx(cv.z), rcp_approx(cv.w));
-                const u64 q01 = add2(fma2(D[2][0], P[2][0], mul2(D[0][0], P[0][0])), fma2(D[3][0], P[3][0], mul2(D[1][0], P[1][0])));
-                const u64 q23 = add2(fma2(D[2][1], P[2][1], mul2(D[0][1], P[0][1])), fma2(D[3][1], P[3][1], mul2(D[1][1], P[1][1])));
-                const u64 nq01 = mul2(q01, pk2(-rcp_approx(cv.x), -rcp_approx(cv.y)));
-                const u64 nq23 = mul2(q23, pk2(-rcp_approx(cv.z), -rcp_approx(cv.w)));
-                const u64 cc01 = pk2(cv.x, cv.y), cc23 = pk2(cv.z, cv.w);
-                const float drr[4] = {drv.x, drv.y, drv.z, drv.w};
+            // ---- exact reverse sweep through the iterations (dP = G); the normalisers of the next iteration and
+            //      their reciprocals are fetched while the current one runs
+            {
+                float4 drn = make_float4(1.f, 1.f, 1.f, 1.f), cn = drn;
+                if (p.sk_iters > 0) {
+                    drn = *reinterpret_cast<const float4*>(skl + (p.sk_iters - 1) * 64);
+                    cn = *reinterpret_cast<const float4*>(skl + (p.sk_iters - 1) * 64 + 4);
+                }
+                float rrn[4] = {rcp_approx(drn.x), rcp_approx(drn.y), rcp_approx(drn.z), rcp_approx(drn.w)};
+                float rcn[4] = {rcp_approx(cn.x), rcp_approx(cn.y), rcp_approx(cn.z), rcp_approx(cn.w)};
+                for (int k = p.sk_iters - 1; k >= 0; --k) {
+                    const float drr[4] = {drn.x, drn.y, drn.z, drn.w};
+                    const float rrc[4] = {rrn[0], rrn[1], rrn[2], rrn[3]};
+                    const u64 cc01 = pk2(cn.x, cn.y), cc23 = pk2(cn.z, cn.w);
+                    const u64 rc01 = pk2(rcn[0], rcn[1]), rc23 = pk2(rcn[2], rcn[3]);
+                    const u64 nrc01 = pk2(-rcn[0], -rcn[1]), nrc23 = pk2(-rcn[2], -rcn[3]);
+                    if (k > 0) {
+                        drn = *reinterpret_cast<const float4*>(skl + (k - 1) * 64);
+                        cn = *reinterpret_cast<const float4*>(skl + (k - 1) * 64 + 4);
+                        rrn[0] = rcp_approx(drn.x); rrn[1] = rcp_approx(drn.y); rrn[2] = rcp_approx(drn.z); rrn[3] = rcp_approx(drn.w);
+                        rcn[0] = rcp_approx(cn.x); rcn[1] = rcp_approx(cn.y); rcn[2] = rcp_approx(cn.z); rcn[3] = rcp_approx(cn.w);
+                    }
+                    // column step y = x / c:  dx = (dy - sum_rows dy*y) / c ;  x = y * c
+                    const u64 q01 = add2(fma2(D[2][0], P[2][0], mul2(D[0][0], P[0][0])), fma2(D[3][0], P[3][0], mul2(D[1][0], P[1][0])));
+                    const u64 q23 = add2(fma2(D[2][1], P[2][1], mul2(D[0][1], P[0][1])), fma2(D[3][1], P[3][1], mul2(D[1][1], P[1][1])));
+                    const u64 nq01 = mul2(q01, nrc01), nq23 = mul2(q23, nrc23);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        D[i][0] = fma2(D[i][0], rc01, nq01);
+                        D[i][1] = fma2(D[i][1], rc23, nq23);
+                        P[i][0] = mul2(P[i][0], cc01);
+                        P[i][1] = mul2(P[i][1], cc23);
+                        // row step y = x / dr
+                        float qa, qb;
+                        upk2(fma2(D[i][1], P[i][1], mul2(D[i][0], P[i][0])), qa, qb);
+                        const float nq = -(qa + qb) * rrc[i];
+                        const u64 rr2 = pk2(rrc[i], rrc[i]), nq2 = pk2(nq, nq), dd2 = pk2(drr[i], drr[i]);
+                        D[i][0] = fma2(D[i][0], rr2, nq2);
+                        D[i][1] = fma2(D[i][1], rr2, nq2);
+                        P[i][0] = mul2(P[i][0], dd2);
+                        P[i][1] = mul2(P[i][1], dd2);
+                    }
+                }
+            }
+            // ---- softmax * 4 backward (P is back at the softmax output): dl = s * (d - sum(d*s)/4); the sums for
+            //      kappa (RMSNorm backward) and dalpha.  Raw values are re-read from the record.
+            float da_pre = 0.f, da_post = 0.f, da_res = 0.f;
+            {
+                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 rp = valid ? rs4[0] : zero4, rq = valid ? rs4[1] : zero4;
+                da_pre = fmaf(dl[3], rp.w, fmaf(dl[2], rp.z, fmaf(dl[1], rp.y, dl[0] * rp.x)));
+                da_post = fmaf(dl[7], rq.w, fmaf(dl[6], rq.z, fmaf(dl[5], rq.y, dl[4] * rq.x)));
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    D[i][0] = fma2(D[i][0], rc01, nq01);
-                    D[i][1] = fma2(D[i][1], rc23, nq23);
-                    P[i][0] = mul2(P[i][0], cc01);
-                    P[i][1] = mul2(P[i][1], cc23);
-                    // row step y = x / dr
                     float qa, qb;
                     upk2(fma2(D[i][1], P[i][1], mul2(D[i][0], P[i][0])), qa, qb);
-                    const float rr = rcp_approx(drr[i]);
-                    const float nq = -(qa + qb) * rr;
-                    const u64 rr2 = pk2(rr, rr), nq2 = pk2(nq, nq), dd2 = pk2(drr[i], drr[i]);
-                    D[i][0] = fma2(D[i][0], rr2, nq2);
-                    D[i][1] = fma2(D[i][1], rr2, nq2);
-                    P[i][0] = mul2(P[i][0], dd2);
-                    P[i][1] = mul2(P[i][1], dd2);
+                    const float nqs = -0.25f * (qa + qb);
+                    const u64 nq2 = pk2(nqs, nqs);
+                    upk2(mul2(P[i][0], add2(D[i][0], nq2)), dl[8 + 4 * i], dl[8 + 4 * i + 1]);
+                    upk2(mul2(P[i][1], add2(D[i][1], nq2)), dl[8 + 4 * i + 2], dl[8 + 4 * i + 3]);
+                    const float4 rr = valid ? rs4[2 + i] : zero4;
+                    const float part_sum = fmaf(dl[8 + 4 * i + 3], rr.w, fmaf(dl[8 + 4 * i + 2], rr.z, fmaf(dl[8 + 4 * i + 1], rr.y, dl[8 + 4 * i] * rr.x)));
+                    da_res += part_sum;
                 }
             }
-            // ---- softmax * 4 backward (P is back at the softmax output): dl = s * (d - sum(d*s)/4); e = d raw;
-            //      kappa (RMSNorm backward); dbias / dalpha terms.  Raw values are re-read from the record.
-            float ev[24];
-            float dsum = 0.f, da_pre = 0.f, da_post = 0.f, da_res = 0.f;
-            {
-                const float4 rp = valid ? rs4[0] : zero4, rq = valid ? rs4[1] : zero4;
-                const float rpv[4] = {rp.x, rp.y, rp.z, rp.w}, rqv[4] = {rq.x, rq.y, rq.z, rq.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ev[j] = dl_pre[j];
-                    ev[4 + j] = dl_post[j];
-                    da_pre = fmaf(dl_pre[j], rpv[j], da_pre);
-                    da_post = fmaf(dl_post[j], rqv[j], da_post);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float qa, qb;
-                upk2(fma2(D[i][1], P[i][1], mul2(D[i][0], P[i][0])), qa, qb);
-                const float nqs = -0.25f * (qa + qb);
-                const u64 nq2 = pk2(nqs, nqs);
-                upk2(mul2(P[i][0], add2(D[i][0], nq2)), ev[8 + 4 * i], ev[8 + 4 * i + 1]);
-                upk2(mul2(P[i][1], add2(D[i][1], nq2)), ev[8 + 4 * i + 2], ev[8 + 4 * i + 3]);
-                const float4 rr = valid ? rs4[2 + i] : zero4;
-                da_res = fmaf(ev[8 + 4 * i + 3], rr.w, fmaf(ev[8 + 4 * i + 2], rr.z, fmaf(ev[8 + 4 * i + 1], rr.y, fmaf(ev[8 + 4 * i], rr.x, da_res))));
-            }
-            // ev holds dl (d logits) here.  d inv_rms = sum_k e_k raw_k / inv_rms ;  kappa = -d inv_rms * inv_rms^3 / N
-            dsum = (a_pre * da_pre + a_post * da_post + a_res * da_res) * inv_rms;
+            // d inv_rms = sum_k e_k raw_k / inv_rms with e = alpha_g * dl * inv_rms ;  kappa = -d inv_rms * inv_rms^3 / N
             if (part == 0) {
+                const float dsum = (a_pre * da_pre + a_post * da_post + a_res * da_res) * inv_rms;
                 acc_a[0] = fmaf(da_pre, inv_rms, acc_a[0]);
                 acc_a[1] = fmaf(da_post, inv_rms, acc_a[1]);
                 acc_a[2] = fmaf(da_res, inv_rms, acc_a[2]);
                 reinterpret_cast<float*>(wrec + kWrecK)[tk] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
+                float* sc = reinterpret_cast<float*>(wrec + kWrecS) + tk * 3;
+                sc[0] = a_pre * inv_rms; sc[1] = a_post * inv_rms; sc[2] = a_res * inv_rms;
             }
-            // this lane's six logits: accumulate dbias, scale to e = alpha_g * dl * inv_rms, emit bf16 hi (workers' W e
-            // MMA, dW MMA) and lo (dW MMA; operand rows = logits, K = token | 8 + token)
+            // d logits of the token for the workers (they scale to e, split into bf16 hi/lo and build the E tile):
+            // part p stores quad p, parts 0 and 1 also quads 4 and 5
             {
-                float mine[6];
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    mine[q] = part == 0 ? ev[q] : part == 1 ? ev[6 + q] : part == 2 ? ev[12 + q] : ev[18 + q];
-                    acc_b[q] += mine[q];
-                }
-                // alpha of logit 6*part + q: part 0 -> pre,pre,pre,pre,post,post; part 1 -> post,post,res x4; parts 2,3 -> res
-                const float al_lo = part == 0 ? a_pre : part == 1 ? a_post : a_res;     // q = 0,1
-                const float al_mid = part == 0 ? a_pre : a_res;                          // q = 2,3
-                const float al_hi = part == 0 ? a_post : a_res;                          // q = 4,5
-                uint32_t words[3];
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const float al = q < 2 ? al_lo : q < 4 ? al_mid : al_hi;
-                    const float e = al * mine[q] * inv_rms;
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(e);
-                    const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
-                    *reinterpret_cast<__nv_bfloat16*>(et + et_off[q]) = hi;
-                    *reinterpret_cast<__nv_bfloat16*>(et + et_off[q] + 384) = lo;
-                    if (q & 1) words[q >> 1] |= (uint32_t)__bfloat16_as_ushort(hi) << 16;
-                    else words[q >> 1] = (uint32_t)__bfloat16_as_ushort(hi);
-                }
-                uint32_t* ew = reinterpret_cast<uint32_t*>(wrec) + tk * 12 + 3 * part;
-                ew[0] = words[0]; ew[1] = words[1]; ew[2] = words[2];
+                float4* dq = reinterpret_cast<float4*>(wrec + kWrecDl) + tk * 6;
+                float4 a, b;
+                a.x = part == 0 ? dl[0] : part == 1 ? dl[4] : part == 2 ? dl[8] : dl[12];
+                a.y = part == 0 ? dl[1] : part == 1 ? dl[5] : part == 2 ? dl[9] : dl[13];
+                a.z = part == 0 ? dl[2] : part == 1 ? dl[6] : part == 2 ? dl[10] : dl[14];
+                a.w = part == 0 ? dl[3] : part == 1 ? dl[7] : part == 2 ? dl[11] : dl[15];
+                b.x = part == 0 ? dl[16] : dl[20]; b.y = part == 0 ? dl[17] : dl[21];
+                b.z = part == 0 ? dl[18] : dl[22]; b.w = part == 0 ? dl[19] : dl[23];
+                dq[part] = a;
+                if (part < 2) dq[4 + part] = b;
             }
-            fence_proxy_async_smem();                       // the E tile is read by the tensor core (async proxy)
             __threadfence_block();
             bar_arrive(kBarCoef + s, kWorkerThreads + 32);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_ed[s]);
         }
-        // dbias: sum the 8 tokens of the warp (lanes with equal part) in a fixed order; dalpha likewise over part 0
+        // dalpha: sum the 8 tokens of the warp (part 0 lanes) in a fixed order; dbias comes from the workers
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) acc_b[k] += __shfl_xor_sync(0xffffffffu, acc_b[k], o);
-#pragma unroll
             for (int k = 0; k < 3; ++k) acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], o);
         }
-        if (tk == 0) {
+        {
             float* o = p.cta_accum + ((size_t)blockIdx.x * kCoefWarps + cw) * kAccum;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) o[6 * part + q] = acc_b[q];
-            if (part == 0) { o[kL] = acc_a[0]; o[kL + 1] = acc_a[1]; o[kL + 2] = acc_a[2]; }
+            if (lane == 0) { o[kL] = acc_a[0]; o[kL + 1] = acc_a[1]; o[kL + 2] = acc_a[2]; }
+            if (cw != 0 && lane < kL) o[lane] = 0.f;       // dbias of the CTA goes to row 0 (workers)
         }
       }
     } else {
@@ -465,6 +463,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         for (int jj = 0; jj < kN; ++jj)
             offa[jj] = cb * 8192 + jj * 1024 + (2 * t) * 128 + (((4 * hh + (g >> 1)) ^ (2 * t)) << 4) + (g & 1) * 8;
         const uint32_t stage0 = smem_u32(smem);
+        float acc_db = 0.f;                               // dbias of logit tid % 24 over tokens tid / 24 (threads < 192)
         const int q = w & 3, jcol = w >> 2;               // tensor-memory lane quadrant / G column group of this warp
         const uint32_t tm_gs = tmem_base + ((uint32_t)(32 * q) << 16) + kColGs + 8u * jcol;
 
@@ -502,7 +501,26 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 bar_sync(kBarCoef + s, kWorkerThreads + 32);
                 mbar_wait(&bar_full[s], (uint32_t)(k / kStages) & 1u);
                 const uint32_t sb = stage0 + s * kStageBytes;
-                const uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
+                uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
+                if (threadIdx.x < kTok * kL) {
+                    // e = alpha_g * inv_rms * d logit of (token, logit) = (tid / 24, tid % 24): bf16 hi for the W e MMA,
+                    // hi and lo into the E tile of the dW MMA (rows = logits, K = token | 8 + token); dbias in registers
+                    const int etok = threadIdx.x / kL, er = threadIdx.x - etok * kL;
+                    const float dlv = reinterpret_cast<const float*>(wrec + kWrecDl)[threadIdx.x];
+                    const float e = dlv * reinterpret_cast<const float*>(wrec + kWrecS)[etok * 3 + (er < kN ? 0 : er < 2 * kN ? 1 : 2)];
+                    acc_db += dlv;
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(e);
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
+                    uint8_t* dst = smem + kOffEt + s * kEtBytes + (er >> 3) * 128 + (er & 7) * 16 + etok * 2;
+                    *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+                    *reinterpret_cast<__nv_bfloat16*>(dst + 384) = lo;
+                    const uint32_t hb = __bfloat16_as_ushort(hi);
+                    const uint32_t nb = __shfl_down_sync(0xffffffffu, hb, 1);
+                    if (!(er & 1)) reinterpret_cast<uint32_t*>(wrec)[etok * 12 + (er >> 1)] = hb | (nb << 16);
+                    fence_proxy_async_smem();               // the E tile is read by the tensor core (async proxy)
+                }
+                bar_sync(kBarW, kWorkerThreads);
+                if (threadIdx.x == 0) mbar_arrive(&bar_ed[s]);
                 const uint32_t* ew = reinterpret_cast<const uint32_t*>(wrec) + g * 12;
                 const uint32_t eb0 = ew[t], eb1 = ew[t + 4], eb2 = ew[t + 8];     // e[g][2t..], e[g][2t+8..], e[g][2t+16..]
                 const float2 kp = *reinterpret_cast<const float2*>(wrec + kWrecK + 8 * t);
@@ -550,6 +568,18 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 mbar_arrive(&bar_dxr[s]);
             }
             if (ro && !ro_done) readout(step);
+        }
+        // ============ dbias of this CTA: fold the 8 tokens in a fixed order
+        {
+            float* red = reinterpret_cast<float*>(smem + kOffG);
+            if (threadIdx.x < kTok * kL) red[threadIdx.x] = acc_db;
+            bar_sync(kBarW, kWorkerThreads);
+            if (threadIdx.x < kL) {
+                float v = 0.f;
+#pragma unroll
+                for (int tt = 0; tt < kTok; ++tt) v += red[tt * kL + threadIdx.x];
+                p.cta_accum[(size_t)blockIdx.x * kCoefWarps * kAccum + threadIdx.x] = v;
+            }
         }
         // ============ dW of this CTA out of tensor memory (every MMA has been committed before the last barrier phase)
         {
