@@ -75,6 +75,8 @@ struct FusedParams {
     const float* saved;    // [T, 28]
     float* dw_part;        // [grid, 2048, 24]
     float* cta_accum;      // [grid, 3, 27]
+    long long* dbg;        // optional [grid, 4, 8] cycle counters: coefficient warps 0..2, front thread (development aid)
+    int dbg_mode;          // development aid: 1 = workers skip the dx math (timing experiments only)
     int64_t T;
     int num_tiles;
     int sk_iters;
@@ -167,6 +169,9 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 }
                 bulk_load_1d(smem + kOffSaved + s * kSavedBytes, p.saved + tok0 * kSaved, nvalid * kSaved * 4, &bar_full[s]);
             };
+            long long facc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            long long fprev = clock64();
+#define HVS_FTICK(slot) do { if (p.dbg) { const long long tn = clock64(); facc[slot] += tn - fprev; fprev = tn; } } while (0)
             const uint32_t id_gs = umma_idesc_bf16(64, 32, 0, 0);
             const uint32_t id_dw = umma_idesc_bf16(64, 24, 1, 0);
             auto retire = [&](int k) {
@@ -174,6 +179,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 const uint32_t ph = (uint32_t)(k / kStages) & 1u;
                 // dW += x^T E for the tile whose coefficients are ready
                 mbar_wait(&bar_ed[s], ph);
+                HVS_FTICK(2);
                 tc_fence_after();
                 const uint64_t bdesc = umma_smem_desc(s0 + kOffEt + s * kEtBytes, 384, 128, kUmmaLayoutNone);
 #pragma unroll 4
@@ -184,20 +190,26 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 }
                 umma_commit(&bar_dw[s]);
                 // dx of the tile (written in place over dy) -> HBM
+                HVS_FTICK(3);
                 mbar_wait(&bar_dxr[s], ph);
+                HVS_FTICK(4);
                 const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * kTok;
 #pragma unroll
                 for (int cb = 0; cb < 8; ++cb)
                     tma_store_3d(&tmap_dx, smem + s * kStageBytes + cb * 8192 + 4096, cb * 64, (int)tok0, 0);
                 bulk_commit();
                 bulk_wait_read<0>();
+                HVS_FTICK(5);
                 mbar_wait(&bar_dw[s], ph);                       // the tensor core is done reading x of this stage
+                HVS_FTICK(6);
                 if (k + kStages < n_local) load_tile(k + kStages);
+                HVS_FTICK(7);
             };
             for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
             for (int it = 0; it < n_local; ++it) {
                 const int s = it % kStages;
                 mbar_wait(&bar_full[s], (uint32_t)(it / kStages) & 1u);
+                HVS_FTICK(0);
                 tc_fence_after();
                 const uint32_t dcol = tmem_base + kColGs + 32u * s;
 #pragma unroll
@@ -209,10 +221,12 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                         umma_bf16_ss(dcol, d64, d64, id_gs, (uint32_t)((cb | ks) != 0));
                     }
                 umma_commit(&bar_gs[s]);
+                HVS_FTICK(1);
                 if (it >= 2) retire(it - 2);
             }
             for (int k = n_local >= 2 ? n_local - 2 : 0; k < n_local; ++k) retire(k);
             bulk_wait<0>();
+            if (p.dbg) for (int q = 0; q < 8; ++q) p.dbg[((size_t)blockIdx.x * 4 + 3) * 8 + q] = facc[q];
         }
       } else {
         // ===================================================== coefficient warps (warps 16, 18, 19 <-> stage 0, 1, 2)
@@ -236,9 +250,13 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         const float4* gs4 = reinterpret_cast<const float4*>(smem + kOffG + s * 512 + tk * 64);
         uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
         float* init = reinterpret_cast<float*>(smem + kOffInit + s * kInitBytes);
+        long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tprev = clock64();
+#define HVS_TICK(slot) do { if (p.dbg) { const long long tn = clock64(); tacc[slot] += tn - tprev; tprev = tn; } } while (0)
         for (int it = cw; it < n_local; it += kCoefWarps) {
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
             mbar_wait(&bar_full[s], ph);                   // the saved records came in with the tile
+            HVS_TICK(0);
             const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok;
             // ---- prologue, four lanes per token: inverse RMS, gates, softmax start of row i4 -> shared memory.
             // Rows past T: x = dy = 0 (TMA fill) and the records were not loaded; they run on zeros.
@@ -259,6 +277,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 if (i4 == 0) init[kInitR / 4 + tk4] = inv_rms;
             }
             __syncwarp();
+            HVS_TICK(1);
             // ---- lane = token from here on
             const bool valid = tok0 + tk < p.T;
             const float inv_rms = init[kInitR / 4 + tk];
@@ -301,8 +320,10 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     o[1] = make_float4(c0, c1, c2, c3);
                 }
             }
+            HVS_TICK(2);
             // ---- G = dy x^T of the tile (read out of tensor memory by the workers)
             bar_sync(kBarRec + s, 8 * 32 + 32);
+            HVS_TICK(3);
             // ---- M = P + hpost (x) hpre for the workers (part p writes column jj = p), gate gradients from G
             u64 D[4][2];
             float dl[24];
@@ -330,6 +351,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dl[j] = dhpre[j] * hpre[j] * (1.0f - hpre[j]);
             }
+            HVS_TICK(4);
             // ---- exact reverse sweep through the iterations (dP = G); the normalisers of the next iteration and
             //      their reciprocals are fetched while the current one runs
             {
@@ -374,6 +396,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     }
                 }
             }
+            HVS_TICK(5);
             // ---- softmax * 4 backward (P is back at the softmax output): dl = s * (d - sum(d*s)/4); the sums for
             //      kappa (RMSNorm backward) and dalpha.  Raw values are re-read from the record.
             float da_pre = 0.f, da_post = 0.f, da_res = 0.f;
@@ -421,7 +444,10 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             }
             __threadfence_block();
             bar_arrive(kBarCoef + s, kWorkerThreads + 32);
+            HVS_TICK(6);
         }
+        if (p.dbg && lane == 0)
+            for (int q = 0; q < 8; ++q) p.dbg[((size_t)blockIdx.x * 4 + cw) * 8 + q] = tacc[q];
         // dalpha: sum the 8 tokens of the warp (part 0 lanes) in a fixed order; dbias comes from the workers
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {
@@ -526,6 +552,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 const float2 kp = *reinterpret_cast<const float2*>(wrec + kWrecK + 8 * t);
                 const u64 kp2 = pk2(kp.x, kp.y);
                 uint2 dya[kN], dyb[kN];
+                if (!(p.dbg_mode & 1)) {
 #pragma unroll
                 for (int ii = 0; ii < kN; ++ii) {
                     dya[ii] = lds64(sb + 4096 + offa[ii]);
@@ -563,6 +590,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     }
                     sts64(sb + 4096 + offa[jj], oa[0], oa[1]);
                     sts64(sb + 4096 + ((offa[jj] + 128) ^ 16), ob[0], ob[1]);
+                }
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_dxr[s]);
@@ -611,6 +639,9 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     if (warp == kWorkers + 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+long long* g_fused_dbg = nullptr;
+int g_fused_dbg_mode = 0;
+
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct FusedWs {
@@ -629,6 +660,13 @@ FusedWs carve(void* base, int ctas) {
 
 }  // namespace
 }  // namespace hvs
+
+// development aid: device buffer [SMs, 3, 8] int64 receiving the coefficient warps' cycle counters (NULL = off)
+extern "C" int hvs_debug_fused_timing(void* device_buffer, int mode) {
+    hvs::g_fused_dbg = reinterpret_cast<long long*>(device_buffer);
+    hvs::g_fused_dbg_mode = mode;
+    return HVS_OK;
+}
 
 extern "C" size_t hvs_mhc_stream_bwd_saved_workspace(int64_t T, int n, int C) {
     using namespace hvs;
@@ -673,6 +711,8 @@ extern "C" int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const flo
         FusedParams p;
         p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale; p.saved = saved;
         p.dw_part = ws.dw_part; p.cta_accum = ws.cta_accum;
+        p.dbg = g_fused_dbg;
+        p.dbg_mode = g_fused_dbg_mode;
         p.T = T;
         p.num_tiles = (int)((T + kTok - 1) / kTok);
         p.sk_iters = sk_iters; p.eps_rms = eps_rms; p.eps_sk = eps_sk;
