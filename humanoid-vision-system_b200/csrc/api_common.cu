@@ -66,6 +66,25 @@ int make_tmap_bf16_streams3d(CUtensorMap* out, const void* gptr, uint64_t tokens
     return r == CUDA_SUCCESS ? HVS_OK : HVS_ERR_DRIVER;
 }
 
+// 4-D view of [T, 4, 512] bf16 as (channel in a 64-channel block, token, block, stream): ONE box of
+// 64 x box_tokens x 8 x 4 lands as 32 swizzle atoms [stream][block][token][64 channels] (32 KB for 8 tokens).
+int make_tmap_bf16_streams4d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return HVS_ERR_DRIVER;
+    cudaFree(nullptr);
+    cuuint64_t gdim[4] = {64, tokens, 8, 4};
+    cuuint64_t gstride[3] = {4096, 128, 1024};  // bytes: token, 64-channel block, stream
+    cuuint32_t box[4] = {64, box_tokens, 8, 4};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS && getenv("HVS_DEBUG"))
+        fprintf(stderr, "[hvs_b200] cuTensorMapEncodeTiled(4d) -> CUresult %d (ptr %p tokens %llu)\n", (int)r, gptr,
+                (unsigned long long)tokens);
+    return r == CUDA_SUCCESS ? HVS_OK : HVS_ERR_DRIVER;
+}
+
 }  // namespace hvs
 
 extern "C" {

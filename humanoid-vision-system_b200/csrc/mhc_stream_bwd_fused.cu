@@ -36,34 +36,34 @@ constexpr int kStages = 3;
 constexpr int kWorkers = 16;
 constexpr int kWorkerThreads = kWorkers * 32;
 constexpr int kThreads = (kWorkers + 4) * 32;         // + coefficient warp 0, front warp, coefficient warps 1, 2
-constexpr int kStageBytes = 65536;                    // 8 channel blocks x ([x box 4 KB][dy box 4 KB]); box = 4 stream atoms of 8 tokens x 128 B
+constexpr int kStageBytes = 65536;                    // [x 32 KB][dy 32 KB]; each = 32 swizzle atoms (stream j, 64-channel block cb) of 8 tokens x 128 B
+constexpr int kHalf = 32768;
 constexpr int kSaved = HVS_MHC_SAVED_STRIDE;          // floats per token in the saved record: raw[24], sum x^2, pad
-constexpr int kMaxIters = 24;
+constexpr int kMaxIters = 20;                        // normalisers of every iteration are kept in shared memory
 constexpr int kCoefWarps = 3;
 constexpr int kAccum = kL + 3;
 
 constexpr int kSavedBytes = kTok * kSaved * 4;        // 896
 constexpr int kOffSaved = kStages * kStageBytes;
-constexpr int kOffG = kOffSaved + kStages * kSavedBytes;          // [stage][token][i][j] fp32
-constexpr int kOffWrec = kOffG + kStages * 512;                   // per stage: e bf16 pairs [8][12] | M pairs [4][4][4][2] | kappa [8]
+constexpr int kOffWrec = kOffSaved + kStages * kSavedBytes;       // per stage: e bf16 pairs [8][12] | M pairs [4][4][4][2] | kappa [8]
                                                                   //            | alpha_g * inv_rms [8][3] | d logits [8][24]
-constexpr int kWrecBytes = 1792, kWrecM = 384, kWrecK = 896, kWrecS = 928, kWrecDl = 1024;
-constexpr int kOffEt = kOffWrec + kStages * kWrecBytes;           // per stage: E tile, 24 rows x 16 K bf16, no swizzle (768 B)
-constexpr int kEtBytes = 768;
-constexpr int kOffInit = kOffEt + kStages * kEtBytes;             // per stage: Sinkhorn start P0 [8][16] | H_pre, H_post [8][8] | inv_rms [8]
-constexpr int kInitBytes = 800, kInitH = 512, kInitR = 768;
+constexpr int kWrecBytes = 1024, kWrecM = 384, kWrecK = 896, kWrecS = 928;   // G [8][16] fp32 overlays bytes [0, 512) until M is written
+constexpr int kOffEt = kOffWrec + kStages * kWrecBytes;           // per stage: E tile, 32 rows (24 logits + 8 zero) x 16 K bf16, no swizzle
+constexpr int kEtBytes = 1024;
+constexpr int kOffInit = kOffEt + kStages * kEtBytes;             // per stage: Sinkhorn start P0 [8][16] | H_pre, H_post [8][8] | inv_rms [8];
+constexpr int kInitBytes = 800, kInitH = 512, kInitR = 768;       //            the d logits [8][24] overlay P0 / H once those are dead
 constexpr int kSkWords = kTok * kMaxIters * 8;
 constexpr int kOffSk = kOffInit + kStages * kInitBytes;
-constexpr int kOffBias = kOffSk + kCoefWarps * kSkWords * 4;    // bias[24] staged once (float4 broadcast reads)
+constexpr int kOffPart = kOffSk + kCoefWarps * kSkWords * 4;      // split-K partials of G: [16 warps][8 tokens][16] fp32
+constexpr int kOffBias = kOffPart + kWorkers * kTok * 16 * 4;     // bias[24] staged once (float4 broadcast reads)
 constexpr int kOffBar = kOffBias + 128;
-constexpr int kOffTmem = kOffBar + 5 * kStages * 8;
+constexpr int kOffTmem = kOffBar + 4 * kStages * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
-static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffG % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0 && kOffInit % 16 == 0 && kOffSk % 16 == 0, "alignment");
+static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0 && kOffInit % 16 == 0 && kOffSk % 16 == 0, "alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColDw = 0;                        // 16 column ranges x 24: blocks 2p (lanes +0) and 2p+1 (lanes +16)
-constexpr uint32_t kColGs = 384;                      // 32 columns per stage
+                                                      // dW accumulators: block (j, 128-channel quarter) at columns 32 * (4j + quarter)
 
 constexpr int kBarRec = 1 /*,2,3*/, kBarCoef = 4 /*,5,6*/, kBarW = 7;
 
@@ -97,6 +97,10 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
 // D(16x8,f32) += A(16x8,bf16,row) * B(8x8,bf16,col)
 __device__ __forceinline__ void mma_bf16_1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
@@ -109,8 +113,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     extern __shared__ __align__(1024) uint8_t smem[];
     if (smem_u32(smem) & 1023u) __trap();
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffBar);     // tile + saved records landed
-    uint64_t* bar_gs = bar_full + kStages;                                // G MMAs of the tile complete
-    uint64_t* bar_ed = bar_gs + kStages;                                  // E tile written (coefficient warp)
+    uint64_t* bar_ed = bar_full + kStages;                                // E tile written (worker warps)
     uint64_t* bar_dxr = bar_ed + kStages;                                 // dx staged by the workers
     uint64_t* bar_dw = bar_dxr + kStages;                                 // dW MMAs of the tile complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
@@ -122,7 +125,6 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_gs[s], 1);
             mbar_init(&bar_ed[s], 1);
             mbar_init(&bar_dxr[s], kWorkerThreads);
             mbar_init(&bar_dw[s], 1);
@@ -135,14 +137,16 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // the dW accumulators start at zero: every MMA below accumulates
+    // the dW accumulators start at zero (every MMA below accumulates); so do the 8 padding rows of the E tiles
+    for (int i = threadIdx.x; i < kStages * kEtBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(smem + kOffEt)[i] = 0u;
     if (warp < kWorkers) {
         const uint32_t zero[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        const uint32_t tq = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + kColDw + (uint32_t)((warp >> 2) * 96);
+        const uint32_t tq = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 128);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) tmem_st16(tq + 16 * c, zero);
+        for (int c = 0; c < 8; ++c) tmem_st16(tq + 16 * c, zero);
         tmem_wait_st();
     }
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -162,31 +166,28 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 const uint32_t nvalid = left >= kTok ? kTok : (uint32_t)left;
                 uint8_t* st = smem + s * kStageBytes;
                 mbar_arrive_expect_tx(&bar_full[s], kStageBytes + nvalid * kSaved * 4);
-#pragma unroll
-                for (int cb = 0; cb < 8; ++cb) {
-                    tma_load_3d(st + cb * 8192, &tmap_x, &bar_full[s], cb * 64, (int)tok0, 0);
-                    tma_load_3d(st + cb * 8192 + 4096, &tmap_dy, &bar_full[s], cb * 64, (int)tok0, 0);
-                }
+                tma_load_4d(st, &tmap_x, &bar_full[s], 0, (int)tok0, 0, 0);                 // one 32 KB box each
+                tma_load_4d(st + kHalf, &tmap_dy, &bar_full[s], 0, (int)tok0, 0, 0);
                 bulk_load_1d(smem + kOffSaved + s * kSavedBytes, p.saved + tok0 * kSaved, nvalid * kSaved * 4, &bar_full[s]);
             };
             long long facc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long fprev = clock64();
 #define HVS_FTICK(slot) do { if (p.dbg) { const long long tn = clock64(); facc[slot] += tn - fprev; fprev = tn; } } while (0)
-            const uint32_t id_gs = umma_idesc_bf16(64, 32, 0, 0);
-            const uint32_t id_dw = umma_idesc_bf16(64, 24, 1, 0);
-            auto retire = [&](int k) {
+            const uint32_t id_dw = umma_idesc_bf16(128, 32, 1, 0);
+            for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
+            for (int k = 0; k < n_local; ++k) {
                 const int s = k % kStages;
                 const uint32_t ph = (uint32_t)(k / kStages) & 1u;
-                // dW += x^T E for the tile whose coefficients are ready
+                // dW += x^T E for the tile whose coefficients are ready: 16 blocks of 128 channels (two atoms along M),
+                // K = 16 = the 8 token rows twice (stride 0) against [E_hi ; E_lo]
                 mbar_wait(&bar_ed[s], ph);
                 HVS_FTICK(2);
                 tc_fence_after();
-                const uint64_t bdesc = umma_smem_desc(s0 + kOffEt + s * kEtBytes, 384, 128, kUmmaLayoutNone);
+                const uint64_t bdesc = umma_smem_desc(s0 + kOffEt + s * kEtBytes, 512, 128, kUmmaLayoutNone);
 #pragma unroll 4
-                for (int b = 0; b < 32; ++b) {
-                    const uint32_t a = s0 + s * kStageBytes + (b >> 2) * 8192 + (b & 3) * 1024;
-                    const uint32_t d = tmem_base + ((uint32_t)((b & 1) * 16) << 16) + kColDw + (uint32_t)((b >> 1) * 24);
-                    umma_bf16_ss(d, umma_smem_desc(a, 1024, 0, kUmmaLayoutSw128), bdesc, id_dw, 1u);
+                for (int b = 0; b < 16; ++b) {
+                    const uint32_t a = s0 + s * kStageBytes + b * 2048;          // atoms (j, 2q), (j, 2q+1): b = 4j + q
+                    umma_bf16_ss(tmem_base + 32u * b, umma_smem_desc(a, 1024, 0, kUmmaLayoutSw128), bdesc, id_dw, 1u);
                 }
                 umma_commit(&bar_dw[s]);
                 // dx of the tile (written in place over dy) -> HBM
@@ -194,9 +195,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 mbar_wait(&bar_dxr[s], ph);
                 HVS_FTICK(4);
                 const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * kTok;
-#pragma unroll
-                for (int cb = 0; cb < 8; ++cb)
-                    tma_store_3d(&tmap_dx, smem + s * kStageBytes + cb * 8192 + 4096, cb * 64, (int)tok0, 0);
+                tma_store_4d(&tmap_dx, smem + s * kStageBytes + kHalf, 0, (int)tok0, 0, 0);
                 bulk_commit();
                 bulk_wait_read<0>();
                 HVS_FTICK(5);
@@ -204,27 +203,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 HVS_FTICK(6);
                 if (k + kStages < n_local) load_tile(k + kStages);
                 HVS_FTICK(7);
-            };
-            for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
-            for (int it = 0; it < n_local; ++it) {
-                const int s = it % kStages;
-                mbar_wait(&bar_full[s], (uint32_t)(it / kStages) & 1u);
-                HVS_FTICK(0);
-                tc_fence_after();
-                const uint32_t dcol = tmem_base + kColGs + 32u * s;
-#pragma unroll
-                for (int cb = 0; cb < 8; ++cb)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t a = s0 + s * kStageBytes + cb * 8192 + ks * 32;
-                        const uint64_t d64 = umma_smem_desc(a, 16, 1024, kUmmaLayoutSw128);
-                        umma_bf16_ss(dcol, d64, d64, id_gs, (uint32_t)((cb | ks) != 0));
-                    }
-                umma_commit(&bar_gs[s]);
-                HVS_FTICK(1);
-                if (it >= 2) retire(it - 2);
             }
-            for (int k = n_local >= 2 ? n_local - 2 : 0; k < n_local; ++k) retire(k);
             bulk_wait<0>();
             if (p.dbg) for (int q = 0; q < 8; ++q) p.dbg[((size_t)blockIdx.x * 4 + 3) * 8 + q] = facc[q];
         }
@@ -247,7 +226,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + tk * 8;     // [iter][token][dr x4 | c x4]
         const float* rsv = reinterpret_cast<const float*>(smem + kOffSaved + s * kSavedBytes);
         const float4* rs4 = reinterpret_cast<const float4*>(rsv + tk * kSaved);
-        const float4* gs4 = reinterpret_cast<const float4*>(smem + kOffG + s * 512 + tk * 64);
+        const float4* gs4 = reinterpret_cast<const float4*>(smem + kOffWrec + s * kWrecBytes + tk * 64);
         uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
         float* init = reinterpret_cast<float*>(smem + kOffInit + s * kInitBytes);
         long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -322,7 +301,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             }
             HVS_TICK(2);
             // ---- G = dy x^T of the tile (read out of tensor memory by the workers)
-            bar_sync(kBarRec + s, 8 * 32 + 32);
+            bar_sync(kBarRec + s, kWorkerThreads + 32);
             HVS_TICK(3);
             // ---- M = P + hpost (x) hpre for the workers (part p writes column jj = p), gate gradients from G
             u64 D[4][2];
@@ -332,11 +311,13 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 const float4 hq = *reinterpret_cast<const float4*>(init + kInitH / 4 + tk * 8 + 4);
                 const float hpre[4] = {hp.x, hp.y, hp.z, hp.w}, hpost[4] = {hq.x, hq.y, hq.z, hq.w};
                 float dhpre[4] = {0.f, 0.f, 0.f, 0.f};
+                const float4 grow[4] = {gs4[0], gs4[1], gs4[2], gs4[3]};
+                __syncwarp();                               // every lane has its G rows: M may overwrite the record
                 float* mp = reinterpret_cast<float*>(wrec + kWrecM) + (tk >> 1) * 32 + part * 8 + (tk & 1);
                 const float hsel = part == 0 ? hpre[0] : part == 1 ? hpre[1] : part == 2 ? hpre[2] : hpre[3];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 g = gs4[i];                                   // row i of G
+                    const float4 g = grow[i];                                  // row i of G
                     D[i][0] = pk2(g.x, g.y);
                     D[i][1] = pk2(g.z, g.w);
                     const float dhpost = fmaf(g.w, hpre[3], fmaf(g.z, hpre[2], fmaf(g.y, hpre[1], g.x * hpre[0])));
@@ -431,7 +412,8 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             // d logits of the token for the workers (they scale to e, split into bf16 hi/lo and build the E tile):
             // part p stores quad p, parts 0 and 1 also quads 4 and 5
             {
-                float4* dq = reinterpret_cast<float4*>(wrec + kWrecDl) + tk * 6;
+                __syncwarp();
+                float4* dq = reinterpret_cast<float4*>(init) + tk * 6;     // overlays P0 / H (dead by now)
                 float4 a, b;
                 a.x = part == 0 ? dl[0] : part == 1 ? dl[4] : part == 2 ? dl[8] : dl[12];
                 a.y = part == 0 ? dl[1] : part == 1 ? dl[5] : part == 2 ? dl[9] : dl[13];
@@ -487,40 +469,68 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         uint32_t offa[kN];
 #pragma unroll
         for (int jj = 0; jj < kN; ++jj)
-            offa[jj] = cb * 8192 + jj * 1024 + (2 * t) * 128 + (((4 * hh + (g >> 1)) ^ (2 * t)) << 4) + (g & 1) * 8;
+            offa[jj] = (jj * 8 + cb) * 1024 + (2 * t) * 128 + (((4 * hh + (g >> 1)) ^ (2 * t)) << 4) + (g & 1) * 8;
         const uint32_t stage0 = smem_u32(smem);
         float acc_db = 0.f;                               // dbias of logit tid % 24 over tokens tid / 24 (threads < 192)
-        const int q = w & 3, jcol = w >> 2;               // tensor-memory lane quadrant / G column group of this warp
-        const uint32_t tm_gs = tmem_base + ((uint32_t)(32 * q) << 16) + kColGs + 8u * jcol;
+        const int q = w & 3;                              // tensor-memory lane quadrant of this warp
+        const int lm = lane >> 3, lr = lane & 7;          // ldmatrix: matrix index / row of an x4 load
+        float* part = reinterpret_cast<float*>(smem + kOffPart);
 
-        // G blocks of a tile out of tensor memory: lanes 0..15 of quadrant q hold the dy rows (stream 2(q-2) + lane/8,
-        // token lane%8); this warp takes x stream jcol.  Warps of quadrants 2 and 3 only.
-        auto readout = [&](int tile) {
+        // G = dy x^T of a tile, per token 4x4, on the warp MMA path: fragment rows / columns are (token, stream) pairs
+        // gathered from the [stream][block][token] atoms, this warp contracts its 32 channels; only the token-diagonal
+        // 4x4 blocks are kept.  Split-K partials go through shared memory, fixed-order sum into the tile's record.
+        auto g_tile = [&](int tile) {
             const int s = tile % kStages;
-            mbar_wait(&bar_gs[s], (uint32_t)(tile / kStages) & 1u);
-            tc_fence_after();
-            uint32_t v[8];
-            tmem_ld8(tm_gs + 32u * s, v);
-            tmem_wait_ld();
-            const int tok = lane & 7;
-            uint32_t val = v[0];
+            mbar_wait(&bar_full[s], (uint32_t)(tile / kStages) & 1u);
+            const uint32_t sb = stage0 + s * kStageBytes;
+            float gacc[2][2][4];
 #pragma unroll
-            for (int c = 1; c < 8; ++c) val = tok == c ? v[c] : val;
-            if (lane < 16)
-                reinterpret_cast<uint32_t*>(smem + kOffG + s * 512)[tok * 16 + (2 * (q - 2) + (lane >> 3)) * 4 + jcol] = val;
-            tc_fence_before();
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) gacc[m][h2][0] = gacc[m][h2][1] = gacc[m][h2][2] = gacc[m][h2][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint32_t bx[4][2];
+#pragma unroll
+                for (int nn = 0; nn < 4; nn += 2) {
+                    const int row = 8 * nn + (lm >> 1) * 8 + lr, chunk = 4 * hh + 2 * ks + (lm & 1);
+                    ldmatrix_x4(sb + ((row & 3) * 8 + cb) * 1024 + (row >> 2) * 128 + ((chunk ^ (row >> 2)) << 4),
+                                bx[nn][0], bx[nn][1], bx[nn + 1][0], bx[nn + 1][1]);
+                }
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    uint32_t a0, a1, a2, a3;
+                    const int row = 16 * m + (lm & 1) * 8 + lr, chunk = 4 * hh + 2 * ks + (lm >> 1);
+                    ldmatrix_x4(sb + kHalf + ((row & 3) * 8 + cb) * 1024 + (row >> 2) * 128 + ((chunk ^ (row >> 2)) << 4), a0, a1, a2, a3);
+                    mma_bf16_16816(gacc[m][0], a0, a1, a2, a3, bx[2 * m][0], bx[2 * m][1]);
+                    mma_bf16_16816(gacc[m][1], a0, a1, a2, a3, bx[2 * m + 1][0], bx[2 * m + 1][1]);
+                }
+            }
+            if ((g >> 2) == (t >> 1)) {
+                float* pw = part + w * (kTok * 16) + 4 * (g & 3) + 2 * (t & 1);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    *reinterpret_cast<float2*>(pw + (4 * m + (g >> 2)) * 16) = make_float2(gacc[m][0][0], gacc[m][0][1]);
+                    *reinterpret_cast<float2*>(pw + (4 * m + 2 + (g >> 2)) * 16) = make_float2(gacc[m][1][2], gacc[m][1][3]);
+                }
+            }
+            bar_sync(kBarW, kWorkerThreads);
+            if (threadIdx.x < kTok * 16) {
+                float v[kWorkers];
+#pragma unroll
+                for (int ww = 0; ww < kWorkers; ++ww) v[ww] = part[ww * (kTok * 16) + threadIdx.x];
+#pragma unroll
+                for (int st = 1; st < kWorkers; st <<= 1)
+#pragma unroll
+                    for (int ww = 0; ww < kWorkers; ww += 2 * st) v[ww] += v[ww + st];
+                reinterpret_cast<float*>(smem + kOffWrec + s * kWrecBytes)[threadIdx.x] = v[0];
+            }
             __threadfence_block();
-            bar_arrive(kBarRec + s, 8 * 32 + 32);
+            bar_arrive(kBarRec + s, kWorkerThreads + 32);
         };
         for (int step = 0; step < n_local + 2; ++step) {
             const int k = step - 2;
-            // the next tile's G is read out as soon as its MMAs are done: before this step's dx if they already are
-            const bool ro = step < n_local && q >= 2;
-            bool ro_done = false;
-            if (ro && __all_sync(0xffffffffu, mbar_test_wait(&bar_gs[step % kStages], (uint32_t)(step / kStages) & 1u))) {
-                readout(step);
-                ro_done = true;
-            }
+            if (k < 0) bar_sync(kBarW, kWorkerThreads);    // (later steps: the E-tile barrier below separates the uses of `part`)
             if (k >= 0) {
                 // ============ dx for tokens 2t, 2t+1 of tile k, channels 32w + 4g .. +3 of every stream
                 const int s = k % kStages;
@@ -532,14 +542,14 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     // e = alpha_g * inv_rms * d logit of (token, logit) = (tid / 24, tid % 24): bf16 hi for the W e MMA,
                     // hi and lo into the E tile of the dW MMA (rows = logits, K = token | 8 + token); dbias in registers
                     const int etok = threadIdx.x / kL, er = threadIdx.x - etok * kL;
-                    const float dlv = reinterpret_cast<const float*>(wrec + kWrecDl)[threadIdx.x];
+                    const float dlv = reinterpret_cast<const float*>(smem + kOffInit + s * kInitBytes)[threadIdx.x];
                     const float e = dlv * reinterpret_cast<const float*>(wrec + kWrecS)[etok * 3 + (er < kN ? 0 : er < 2 * kN ? 1 : 2)];
                     acc_db += dlv;
                     const __nv_bfloat16 hi = __float2bfloat16_rn(e);
                     const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
                     uint8_t* dst = smem + kOffEt + s * kEtBytes + (er >> 3) * 128 + (er & 7) * 16 + etok * 2;
                     *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
-                    *reinterpret_cast<__nv_bfloat16*>(dst + 384) = lo;
+                    *reinterpret_cast<__nv_bfloat16*>(dst + 512) = lo;
                     const uint32_t hb = __bfloat16_as_ushort(hi);
                     const uint32_t nb = __shfl_down_sync(0xffffffffu, hb, 1);
                     if (!(er & 1)) reinterpret_cast<uint32_t*>(wrec)[etok * 12 + (er >> 1)] = hb | (nb << 16);
@@ -555,8 +565,8 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 if (!(p.dbg_mode & 1)) {
 #pragma unroll
                 for (int ii = 0; ii < kN; ++ii) {
-                    dya[ii] = lds64(sb + 4096 + offa[ii]);
-                    dyb[ii] = lds64(sb + 4096 + ((offa[ii] + 128) ^ 16));
+                    dya[ii] = lds64(sb + kHalf + offa[ii]);
+                    dyb[ii] = lds64(sb + kHalf + ((offa[ii] + 128) ^ 16));
                 }
 #pragma unroll
                 for (int jj = 0; jj < kN; ++jj) {
@@ -588,18 +598,18 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                         oa[mt] = pack_bf16(c[0], c[2]);
                         ob[mt] = pack_bf16(c[1], c[3]);
                     }
-                    sts64(sb + 4096 + offa[jj], oa[0], oa[1]);
-                    sts64(sb + 4096 + ((offa[jj] + 128) ^ 16), ob[0], ob[1]);
+                    sts64(sb + kHalf + offa[jj], oa[0], oa[1]);
+                    sts64(sb + kHalf + ((offa[jj] + 128) ^ 16), ob[0], ob[1]);
                 }
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_dxr[s]);
             }
-            if (ro && !ro_done) readout(step);
+            if (step < n_local) g_tile(step);
         }
         // ============ dbias of this CTA: fold the 8 tokens in a fixed order
         {
-            float* red = reinterpret_cast<float*>(smem + kOffG);
+            float* red = reinterpret_cast<float*>(smem + kOffPart);
             if (threadIdx.x < kTok * kL) red[threadIdx.x] = acc_db;
             bar_sync(kBarW, kWorkerThreads);
             if (threadIdx.x < kL) {
@@ -614,14 +624,12 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             const int last = n_local - 1;
             mbar_wait(&bar_dw[last % kStages], (uint32_t)(last / kStages) & 1u);
             tc_fence_after();
-            const int half = lane >> 4, r = lane & 15;
             float* out = p.dw_part + (size_t)blockIdx.x * kRow * kL;
 #pragma unroll
             for (int pi = 0; pi < 4; ++pi) {
-                const int pr = (w >> 2) * 4 + pi;          // column range = block pair
-                const int b = 2 * pr + half;               // block (cb, j) = (b >> 2, b & 3), row = channel in the block
-                const int kidx = (b & 3) * kC + (b >> 2) * 64 + 16 * q + r;
-                const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + kColDw + (uint32_t)(pr * 24);
+                const int b = (w >> 2) * 4 + pi;           // block = (stream b / 4, 128-channel quarter b % 4); lane = channel
+                const int kidx = (b >> 2) * kC + (b & 3) * 128 + 32 * q + lane;
+                const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * 32);
                 uint32_t v[8];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -697,11 +705,11 @@ extern "C" int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const flo
     int grid = 0;
     if (T > 0) {
         CUtensorMap tx, tdy, tdx;
-        int rc = make_tmap_bf16_streams3d(&tx, x, (uint64_t)T, kTok);
+        int rc = make_tmap_bf16_streams4d(&tx, x, (uint64_t)T, kTok);
         if (rc) return rc;
-        rc = make_tmap_bf16_streams3d(&tdy, dy, (uint64_t)T, kTok);
+        rc = make_tmap_bf16_streams4d(&tdy, dy, (uint64_t)T, kTok);
         if (rc) return rc;
-        rc = make_tmap_bf16_streams3d(&tdx, dx, (uint64_t)T, kTok);
+        rc = make_tmap_bf16_streams4d(&tdx, dx, (uint64_t)T, kTok);
         if (rc) return rc;
         static bool attr_set = false;
         if (!attr_set) {
