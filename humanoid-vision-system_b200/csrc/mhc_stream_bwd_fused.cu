@@ -57,7 +57,7 @@ constexpr int kOffSk = kOffInit + kStages * kInitBytes;
 constexpr int kOffPart = kOffSk + kCoefWarps * kSkWords * 4;      // split-K partials of G: [16 warps][8 tokens][16] fp32
 constexpr int kOffBias = kOffPart + kWorkers * kTok * 16 * 4;     // bias[24] staged once (float4 broadcast reads)
 constexpr int kOffBar = kOffBias + 128;
-constexpr int kOffTmem = kOffBar + 4 * kStages * 8;
+constexpr int kOffTmem = kOffBar + 5 * kStages * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0 && kOffInit % 16 == 0 && kOffSk % 16 == 0, "alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -116,6 +116,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     uint64_t* bar_ed = bar_full + kStages;                                // E tile written (worker warps)
     uint64_t* bar_dxr = bar_ed + kStages;                                 // dx staged by the workers
     uint64_t* bar_dw = bar_dxr + kStages;                                 // dW MMAs of the tile complete
+    uint64_t* bar_sv = bar_dw + kStages;                                  // saved records of the stage's next tile landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
     const int warp = threadIdx.x >> 5;
@@ -128,6 +129,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             mbar_init(&bar_ed[s], 1);
             mbar_init(&bar_dxr[s], kWorkerThreads);
             mbar_init(&bar_dw[s], 1);
+            mbar_init(&bar_sv[s], 1);
         }
         fence_mbar_init();
     }
@@ -162,13 +164,10 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             auto load_tile = [&](int it) {
                 const int s = it % kStages;
                 const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok;
-                const int64_t left = p.T - tok0;
-                const uint32_t nvalid = left >= kTok ? kTok : (uint32_t)left;
                 uint8_t* st = smem + s * kStageBytes;
-                mbar_arrive_expect_tx(&bar_full[s], kStageBytes + nvalid * kSaved * 4);
+                mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
                 tma_load_4d(st, &tmap_x, &bar_full[s], 0, (int)tok0, 0, 0);                 // one 32 KB box each
                 tma_load_4d(st + kHalf, &tmap_dy, &bar_full[s], 0, (int)tok0, 0, 0);
-                bulk_load_1d(smem + kOffSaved + s * kSavedBytes, p.saved + tok0 * kSaved, nvalid * kSaved * 4, &bar_full[s]);
             };
             long long facc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long fprev = clock64();
@@ -209,10 +208,15 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         }
       } else {
         // ===================================================== coefficient warps (warps 16, 18, 19 <-> stage 0, 1, 2)
-        // lane = token: the whole 4x4 block of token lane%8 lives in this lane's registers as packed fp32x2 rows,
-        // so the 20 forward iterations and the exact reverse sweep are one shuffle-free dependent chain with
-        // four-way instruction-level parallelism.  Lanes 8..31 repeat tokens 0..7 (lane / 8 = part) and take a
-        // quarter of the epilogue stores / accumulators each.
+        // lane = token: the whole 4x4 block of token lane%8 lives in this lane's registers as packed fp32x2 rows, so
+        // the forward iterations and the reverse sweep are shuffle-free chains with four-way instruction-level
+        // parallelism.  Lanes 8..31 repeat tokens 0..7 (lane / 8 = part) and take a quarter of the stores each.
+        //   forward  (reference arithmetic, P / (sum + eps)) runs AHEAD of the tile: it needs only the saved record,
+        //            which this warp fetches itself; it also tracks the cumulative scalings u, v with
+        //            P_k = diag(u_k) K diag(v_k), K = the softmax start
+        //   backward differentiates that scaling form exactly: u_k = 1 / (K v_{k-1}), v_k = 1 / (K^T u_k)  (the eps of
+        //            the reference, 1e-8 against sums of 1, is below fp32 resolution), so the sweep needs neither
+        //            reciprocals nor a reconstruction of P: per iteration four 4x4 mat-vecs / rank-1 updates.
         const int cw = warp == kWorkers ? 0 : warp - (kWorkers + 1);
         const int s = cw;
         const int tk = lane & 7, part = lane >> 3;
@@ -223,18 +227,26 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         const float eps = p.eps_sk;
         const u64 eps2 = pk2(eps, eps);
         float acc_a[3] = {0.f, 0.f, 0.f};                  // dalpha terms (part 0 lanes)
-        float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + tk * 8;     // [iter][token][dr x4 | c x4]
+        float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + tk * 8;     // [iter][token][u x4 | v x4]
         const float* rsv = reinterpret_cast<const float*>(smem + kOffSaved + s * kSavedBytes);
         const float4* rs4 = reinterpret_cast<const float4*>(rsv + tk * kSaved);
         const float4* gs4 = reinterpret_cast<const float4*>(smem + kOffWrec + s * kWrecBytes + tk * 64);
         uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
         float* init = reinterpret_cast<float*>(smem + kOffInit + s * kInitBytes);
+        auto fetch_saved = [&](int it) {                   // lane 0: the 8 saved records of tile `it` -> shared memory
+            const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok;
+            const int64_t left = p.T - tok0;
+            const uint32_t bytes = (left >= kTok ? kTok : (uint32_t)left) * kSaved * 4;
+            mbar_arrive_expect_tx(&bar_sv[s], bytes);
+            bulk_load_1d(smem + kOffSaved + s * kSavedBytes, p.saved + tok0 * kSaved, bytes, &bar_sv[s]);
+        };
+        if (lane == 0 && cw < n_local) fetch_saved(cw);
         long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         long long tprev = clock64();
 #define HVS_TICK(slot) do { if (p.dbg) { const long long tn = clock64(); tacc[slot] += tn - tprev; tprev = tn; } } while (0)
         for (int it = cw; it < n_local; it += kCoefWarps) {
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-            mbar_wait(&bar_full[s], ph);                   // the saved records came in with the tile
+            mbar_wait(&bar_sv[s], ph);
             HVS_TICK(0);
             const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok;
             // ---- prologue, four lanes per token: inverse RMS, gates, softmax start of row i4 -> shared memory.
@@ -267,59 +279,66 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 P[i][0] = pk2(v.x, v.y);
                 P[i][1] = pk2(v.z, v.w);
             }
-            // ---- forward Sinkhorn, the normalisers are kept for the reverse sweep
-            for (int k = 0; k < p.sk_iters; ++k) {
-                float dr[4];
+            // ---- forward Sinkhorn; the cumulative scalings after every iteration are kept for the reverse sweep
+            {
+                u64 U01 = pk2(1.f, 1.f), U23 = U01, V01 = U01, V23 = U01;
+                for (int k = 0; k < p.sk_iters; ++k) {
+                    float rr[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float sa, sb;
-                    upk2(add2(P[i][0], P[i][1]), sa, sb);
-                    dr[i] = (sa + sb) + eps;
-                }
+                    for (int i = 0; i < 4; ++i) {
+                        float sa, sb;
+                        upk2(add2(P[i][0], P[i][1]), sa, sb);
+                        rr[i] = rcp_approx((sa + sb) + eps);
+                    }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float rr = rcp_approx(dr[i]);
-                    const u64 rr2 = pk2(rr, rr);
-                    P[i][0] = mul2(P[i][0], rr2);
-                    P[i][1] = mul2(P[i][1], rr2);
-                }
-                const u64 c01 = add2(add2(add2(P[0][0], P[1][0]), add2(P[2][0], P[3][0])), eps2);
-                const u64 c23 = add2(add2(add2(P[0][1], P[1][1]), add2(P[2][1], P[3][1])), eps2);
-                float c0, c1, c2, c3;
-                upk2(c01, c0, c1); upk2(c23, c2, c3);
-                const u64 rc01 = pk2(rcp_approx(c0), rcp_approx(c1)), rc23 = pk2(rcp_approx(c2), rcp_approx(c3));
+                    for (int i = 0; i < 4; ++i) {
+                        const u64 rr2 = pk2(rr[i], rr[i]);
+                        P[i][0] = mul2(P[i][0], rr2);
+                        P[i][1] = mul2(P[i][1], rr2);
+                    }
+                    U01 = mul2(U01, pk2(rr[0], rr[1]));
+                    U23 = mul2(U23, pk2(rr[2], rr[3]));
+                    const u64 c01 = add2(add2(add2(P[0][0], P[1][0]), add2(P[2][0], P[3][0])), eps2);
+                    const u64 c23 = add2(add2(add2(P[0][1], P[1][1]), add2(P[2][1], P[3][1])), eps2);
+                    float c0, c1, c2, c3;
+                    upk2(c01, c0, c1); upk2(c23, c2, c3);
+                    const u64 rc01 = pk2(rcp_approx(c0), rcp_approx(c1)), rc23 = pk2(rcp_approx(c2), rcp_approx(c3));
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    P[i][0] = mul2(P[i][0], rc01);
-                    P[i][1] = mul2(P[i][1], rc23);
-                }
-                if (part == 0) {
-                    float4* o = reinterpret_cast<float4*>(skl + k * 64);
-                    o[0] = make_float4(dr[0], dr[1], dr[2], dr[3]);
-                    o[1] = make_float4(c0, c1, c2, c3);
+                    for (int i = 0; i < 4; ++i) {
+                        P[i][0] = mul2(P[i][0], rc01);
+                        P[i][1] = mul2(P[i][1], rc23);
+                    }
+                    V01 = mul2(V01, rc01);
+                    V23 = mul2(V23, rc23);
+                    if (part == 0) {
+                        float u0, u1, u2, u3, v0, v1, v2, v3;
+                        upk2(U01, u0, u1); upk2(U23, u2, u3); upk2(V01, v0, v1); upk2(V23, v2, v3);
+                        float4* o = reinterpret_cast<float4*>(skl + k * 64);
+                        o[0] = make_float4(u0, u1, u2, u3);
+                        o[1] = make_float4(v0, v1, v2, v3);
+                    }
                 }
             }
             HVS_TICK(2);
-            // ---- G = dy x^T of the tile (read out of tensor memory by the workers)
+            // ---- G = dy x^T of the tile (split-K sums by the workers; also: the tile has landed)
             bar_sync(kBarRec + s, kWorkerThreads + 32);
             HVS_TICK(3);
             // ---- M = P + hpost (x) hpre for the workers (part p writes column jj = p), gate gradients from G
-            u64 D[4][2];
             float dl[24];
+            float4 grow[4];
             {
                 const float4 hp = *reinterpret_cast<const float4*>(init + kInitH / 4 + tk * 8);
                 const float4 hq = *reinterpret_cast<const float4*>(init + kInitH / 4 + tk * 8 + 4);
                 const float hpre[4] = {hp.x, hp.y, hp.z, hp.w}, hpost[4] = {hq.x, hq.y, hq.z, hq.w};
                 float dhpre[4] = {0.f, 0.f, 0.f, 0.f};
-                const float4 grow[4] = {gs4[0], gs4[1], gs4[2], gs4[3]};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) grow[i] = gs4[i];
                 __syncwarp();                               // every lane has its G rows: M may overwrite the record
                 float* mp = reinterpret_cast<float*>(wrec + kWrecM) + (tk >> 1) * 32 + part * 8 + (tk & 1);
                 const float hsel = part == 0 ? hpre[0] : part == 1 ? hpre[1] : part == 2 ? hpre[2] : hpre[3];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 g = grow[i];                                  // row i of G
-                    D[i][0] = pk2(g.x, g.y);
-                    D[i][1] = pk2(g.z, g.w);
                     const float dhpost = fmaf(g.w, hpre[3], fmaf(g.z, hpre[2], fmaf(g.y, hpre[1], g.x * hpre[0])));
                     dl[4 + i] = dhpost * hpost[i] * (1.0f - 0.5f * hpost[i]);
                     dhpre[0] = fmaf(g.x, hpost[i], dhpre[0]); dhpre[1] = fmaf(g.y, hpost[i], dhpre[1]);
@@ -333,55 +352,106 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 for (int j = 0; j < 4; ++j) dl[j] = dhpre[j] * hpre[j] * (1.0f - hpre[j]);
             }
             HVS_TICK(4);
-            // ---- exact reverse sweep through the iterations (dP = G); the normalisers of the next iteration and
-            //      their reciprocals are fetched while the current one runs
+            // ---- reverse sweep in the scaling form.  K by rows (Kr) and by columns (Kc), both packed; dK accumulates
+            //      by rows; ub / vb are the adjoints of the current u / v.
+            u64 dK[4][2];
             {
-                float4 drn = make_float4(1.f, 1.f, 1.f, 1.f), cn = drn;
-                if (p.sk_iters > 0) {
-                    drn = *reinterpret_cast<const float4*>(skl + (p.sk_iters - 1) * 64);
-                    cn = *reinterpret_cast<const float4*>(skl + (p.sk_iters - 1) * 64 + 4);
-                }
-                float rrn[4] = {rcp_approx(drn.x), rcp_approx(drn.y), rcp_approx(drn.z), rcp_approx(drn.w)};
-                float rcn[4] = {rcp_approx(cn.x), rcp_approx(cn.y), rcp_approx(cn.z), rcp_approx(cn.w)};
-                for (int k = p.sk_iters - 1; k >= 0; --k) {
-                    const float drr[4] = {drn.x, drn.y, drn.z, drn.w};
-                    const float rrc[4] = {rrn[0], rrn[1], rrn[2], rrn[3]};
-                    const u64 cc01 = pk2(cn.x, cn.y), cc23 = pk2(cn.z, cn.w);
-                    const u64 rc01 = pk2(rcn[0], rcn[1]), rc23 = pk2(rcn[2], rcn[3]);
-                    const u64 nrc01 = pk2(-rcn[0], -rcn[1]), nrc23 = pk2(-rcn[2], -rcn[3]);
-                    if (k > 0) {
-                        drn = *reinterpret_cast<const float4*>(skl + (k - 1) * 64);
-                        cn = *reinterpret_cast<const float4*>(skl + (k - 1) * 64 + 4);
-                        rrn[0] = rcp_approx(drn.x); rrn[1] = rcp_approx(drn.y); rrn[2] = rcp_approx(drn.z); rrn[3] = rcp_approx(drn.w);
-                        rcn[0] = rcp_approx(cn.x); rcn[1] = rcp_approx(cn.y); rcn[2] = rcp_approx(cn.z); rcn[3] = rcp_approx(cn.w);
-                    }
-                    // column step y = x / c:  dx = (dy - sum_rows dy*y) / c ;  x = y * c
-                    const u64 q01 = add2(fma2(D[2][0], P[2][0], mul2(D[0][0], P[0][0])), fma2(D[3][0], P[3][0], mul2(D[1][0], P[1][0])));
-                    const u64 q23 = add2(fma2(D[2][1], P[2][1], mul2(D[0][1], P[0][1])), fma2(D[3][1], P[3][1], mul2(D[1][1], P[1][1])));
-                    const u64 nq01 = mul2(q01, nrc01), nq23 = mul2(q23, nrc23);
+                u64 Kr[4][2], Kc[4][2];
+                {
+                    float kv[4][4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        D[i][0] = fma2(D[i][0], rc01, nq01);
-                        D[i][1] = fma2(D[i][1], rc23, nq23);
-                        P[i][0] = mul2(P[i][0], cc01);
-                        P[i][1] = mul2(P[i][1], cc23);
-                        // row step y = x / dr
-                        float qa, qb;
-                        upk2(fma2(D[i][1], P[i][1], mul2(D[i][0], P[i][0])), qa, qb);
-                        const float nq = -(qa + qb) * rrc[i];
-                        const u64 rr2 = pk2(rrc[i], rrc[i]), nq2 = pk2(nq, nq), dd2 = pk2(drr[i], drr[i]);
-                        D[i][0] = fma2(D[i][0], rr2, nq2);
-                        D[i][1] = fma2(D[i][1], rr2, nq2);
-                        P[i][0] = mul2(P[i][0], dd2);
-                        P[i][1] = mul2(P[i][1], dd2);
+                        const float4 v = *reinterpret_cast<const float4*>(init + tk * 16 + 4 * i);
+                        kv[i][0] = v.x; kv[i][1] = v.y; kv[i][2] = v.z; kv[i][3] = v.w;
+                        Kr[i][0] = pk2(v.x, v.y);
+                        Kr[i][1] = pk2(v.z, v.w);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        Kc[j][0] = pk2(kv[0][j], kv[1][j]);
+                        Kc[j][1] = pk2(kv[2][j], kv[3][j]);
                     }
                 }
-            }
-            HVS_TICK(5);
-            // ---- softmax * 4 backward (P is back at the softmax output): dl = s * (d - sum(d*s)/4); the sums for
-            //      kappa (RMSNorm backward) and dalpha.  Raw values are re-read from the record.
-            float da_pre = 0.f, da_post = 0.f, da_res = 0.f;
-            {
+                const int last = p.sk_iters - 1;
+                float4 un = make_float4(1.f, 1.f, 1.f, 1.f), vn = un;           // u_k, v_k of the iteration being undone
+                if (last >= 0) {
+                    un = *reinterpret_cast<const float4*>(skl + last * 64);
+                    vn = *reinterpret_cast<const float4*>(skl + last * 64 + 4);
+                }
+                // adjoints of the output P = diag(u) K diag(v):  dK = G u v^T,  ub_i = sum_j G_ij K_ij v_j,  vb_j = sum_i G_ij K_ij u_i
+                u64 ub01, ub23, vb01, vb23;
+                {
+                    const u64 v01 = pk2(vn.x, vn.y), v23 = pk2(vn.z, vn.w);
+                    const float uu[4] = {un.x, un.y, un.z, un.w};
+                    float ubs[4];
+                    vb01 = pk2(0.f, 0.f); vb23 = vb01;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const u64 g0 = pk2(grow[i].x, grow[i].y), g1 = pk2(grow[i].z, grow[i].w);
+                        const u64 gk0 = mul2(g0, Kr[i][0]), gk1 = mul2(g1, Kr[i][1]);
+                        const u64 ui = pk2(uu[i], uu[i]);
+                        float sa, sb;
+                        upk2(fma2(gk1, v23, mul2(gk0, v01)), sa, sb);
+                        ubs[i] = sa + sb;
+                        vb01 = fma2(gk0, ui, vb01);
+                        vb23 = fma2(gk1, ui, vb23);
+                        dK[i][0] = mul2(mul2(g0, v01), ui);
+                        dK[i][1] = mul2(mul2(g1, v23), ui);
+                    }
+                    ub01 = pk2(ubs[0], ubs[1]); ub23 = pk2(ubs[2], ubs[3]);
+                }
+                for (int k = last; k >= 0; --k) {
+                    const float uu[4] = {un.x, un.y, un.z, un.w};
+                    const u64 u01 = pk2(un.x, un.y), u23 = pk2(un.z, un.w), nu01 = pk2(-un.x, -un.y), nu23 = pk2(-un.z, -un.w);
+                    const u64 v01 = pk2(vn.x, vn.y), v23 = pk2(vn.z, vn.w), nv01 = pk2(-vn.x, -vn.y), nv23 = pk2(-vn.z, -vn.w);
+                    if (k > 0) {                                                // u_{k-1}, v_{k-1}
+                        un = *reinterpret_cast<const float4*>(skl + (k - 1) * 64);
+                        vn = *reinterpret_cast<const float4*>(skl + (k - 1) * 64 + 4);
+                    } else {
+                        vn = make_float4(1.f, 1.f, 1.f, 1.f);                   // v_0
+                    }
+                    const u64 vp01 = pk2(vn.x, vn.y), vp23 = pk2(vn.z, vn.w);
+                    // v_k = 1 / (K^T u_k):  tb = -vb v_k^2 ;  ub += K tb ;  dK += u_k tb^T
+                    const u64 tb01 = mul2(mul2(vb01, v01), nv01), tb23 = mul2(mul2(vb23, v23), nv23);
+                    float tb[4];
+                    upk2(tb01, tb[0], tb[1]); upk2(tb23, tb[2], tb[3]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const u64 tj = pk2(tb[j], tb[j]);
+                        ub01 = fma2(Kc[j][0], tj, ub01);
+                        ub23 = fma2(Kc[j][1], tj, ub23);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const u64 ui = pk2(uu[i], uu[i]);
+                        dK[i][0] = fma2(tb01, ui, dK[i][0]);
+                        dK[i][1] = fma2(tb23, ui, dK[i][1]);
+                    }
+                    // u_k = 1 / (K v_{k-1}):  sb = -ub u_k^2 ;  vb = K^T sb ;  dK += sb v_{k-1}^T ;  ub = 0
+                    const u64 sb01 = mul2(mul2(ub01, u01), nu01), sb23 = mul2(mul2(ub23, u23), nu23);
+                    float sb[4];
+                    upk2(sb01, sb[0], sb[1]); upk2(sb23, sb[2], sb[3]);
+                    {
+                        const u64 s0 = pk2(sb[0], sb[0]);
+                        vb01 = mul2(Kr[0][0], s0);
+                        vb23 = mul2(Kr[0][1], s0);
+                        dK[0][0] = fma2(vp01, s0, dK[0][0]);
+                        dK[0][1] = fma2(vp23, s0, dK[0][1]);
+                    }
+#pragma unroll
+                    for (int i = 1; i < 4; ++i) {
+                        const u64 si = pk2(sb[i], sb[i]);
+                        vb01 = fma2(Kr[i][0], si, vb01);
+                        vb23 = fma2(Kr[i][1], si, vb23);
+                        dK[i][0] = fma2(vp01, si, dK[i][0]);
+                        dK[i][1] = fma2(vp23, si, dK[i][1]);
+                    }
+                    ub01 = pk2(0.f, 0.f); ub23 = ub01;
+                }
+                HVS_TICK(5);
+                // ---- softmax * 4 backward: dl = K (dK - sum_j(dK K) / 4); the sums for kappa (RMSNorm backward) and
+                //      dalpha.  Raw values are re-read from the record.
+                float da_pre = 0.f, da_post = 0.f, da_res = 0.f;
                 const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 rp = valid ? rs4[0] : zero4, rq = valid ? rs4[1] : zero4;
                 da_pre = fmaf(dl[3], rp.w, fmaf(dl[2], rp.z, fmaf(dl[1], rp.y, dl[0] * rp.x)));
@@ -389,25 +459,24 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float qa, qb;
-                    upk2(fma2(D[i][1], P[i][1], mul2(D[i][0], P[i][0])), qa, qb);
+                    upk2(fma2(dK[i][1], Kr[i][1], mul2(dK[i][0], Kr[i][0])), qa, qb);
                     const float nqs = -0.25f * (qa + qb);
                     const u64 nq2 = pk2(nqs, nqs);
-                    upk2(mul2(P[i][0], add2(D[i][0], nq2)), dl[8 + 4 * i], dl[8 + 4 * i + 1]);
-                    upk2(mul2(P[i][1], add2(D[i][1], nq2)), dl[8 + 4 * i + 2], dl[8 + 4 * i + 3]);
+                    upk2(mul2(Kr[i][0], add2(dK[i][0], nq2)), dl[8 + 4 * i], dl[8 + 4 * i + 1]);
+                    upk2(mul2(Kr[i][1], add2(dK[i][1], nq2)), dl[8 + 4 * i + 2], dl[8 + 4 * i + 3]);
                     const float4 rr = valid ? rs4[2 + i] : zero4;
-                    const float part_sum = fmaf(dl[8 + 4 * i + 3], rr.w, fmaf(dl[8 + 4 * i + 2], rr.z, fmaf(dl[8 + 4 * i + 1], rr.y, dl[8 + 4 * i] * rr.x)));
-                    da_res += part_sum;
+                    da_res += fmaf(dl[8 + 4 * i + 3], rr.w, fmaf(dl[8 + 4 * i + 2], rr.z, fmaf(dl[8 + 4 * i + 1], rr.y, dl[8 + 4 * i] * rr.x)));
                 }
-            }
-            // d inv_rms = sum_k e_k raw_k / inv_rms with e = alpha_g * dl * inv_rms ;  kappa = -d inv_rms * inv_rms^3 / N
-            if (part == 0) {
-                const float dsum = (a_pre * da_pre + a_post * da_post + a_res * da_res) * inv_rms;
-                acc_a[0] = fmaf(da_pre, inv_rms, acc_a[0]);
-                acc_a[1] = fmaf(da_post, inv_rms, acc_a[1]);
-                acc_a[2] = fmaf(da_res, inv_rms, acc_a[2]);
-                reinterpret_cast<float*>(wrec + kWrecK)[tk] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
-                float* sc = reinterpret_cast<float*>(wrec + kWrecS) + tk * 3;
-                sc[0] = a_pre * inv_rms; sc[1] = a_post * inv_rms; sc[2] = a_res * inv_rms;
+                // d inv_rms = sum_k e_k raw_k / inv_rms with e = alpha_g * dl * inv_rms ;  kappa = -d inv_rms * inv_rms^3 / N
+                if (part == 0) {
+                    const float dsum = (a_pre * da_pre + a_post * da_post + a_res * da_res) * inv_rms;
+                    acc_a[0] = fmaf(da_pre, inv_rms, acc_a[0]);
+                    acc_a[1] = fmaf(da_post, inv_rms, acc_a[1]);
+                    acc_a[2] = fmaf(da_res, inv_rms, acc_a[2]);
+                    reinterpret_cast<float*>(wrec + kWrecK)[tk] = -dsum * inv_rms * inv_rms * (1.0f / kRow);
+                    float* sc = reinterpret_cast<float*>(wrec + kWrecS) + tk * 3;
+                    sc[0] = a_pre * inv_rms; sc[1] = a_post * inv_rms; sc[2] = a_res * inv_rms;
+                }
             }
             // d logits of the token for the workers (they scale to e, split into bf16 hi/lo and build the E tile):
             // part p stores quad p, parts 0 and 1 also quads 4 and 5
@@ -423,6 +492,12 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 b.z = part == 0 ? dl[18] : dl[22]; b.w = part == 0 ? dl[19] : dl[23];
                 dq[part] = a;
                 if (part < 2) dq[4 + part] = b;
+            }
+            __syncwarp();
+            // every lane is done with this tile's record: fetch the next one into the same buffer
+            if (lane == 0 && it + kCoefWarps < n_local) {
+                fence_proxy_async_smem();
+                fetch_saved(it + kCoefWarps);
             }
             __threadfence_block();
             bar_arrive(kBarCoef + s, kWorkerThreads + 32);
