@@ -47,7 +47,7 @@ constexpr int kSavedBytes = kTok * kSaved * 4;        // 896
 constexpr int kOffSaved = kStages * kStageBytes;
 constexpr int kOffWrec = kOffSaved + kStages * kSavedBytes;       // per stage: e bf16 pairs [8][12] | M pairs [4][4][4][2] | kappa [8]
                                                                   //            | alpha_g * inv_rms [8][3] | d logits [8][24]
-constexpr int kWrecBytes = 1024, kWrecM = 384, kWrecK = 896, kWrecS = 928;   // G [8][16] fp32 overlays bytes [0, 512) until M is written
+constexpr int kWrecBytes = 1152, kWrecM = 384, kWrecK = 960, kWrecS = 992, kMpStride = 36;   // M pairs: 4 token pairs x (32 + 4 pad) floats   // G [8][16] fp32 overlays bytes [0, 512) until M is written
 constexpr int kOffEt = kOffWrec + kStages * kWrecBytes;           // per stage: E tile, 32 rows (24 logits + 8 zero) x 16 K bf16, no swizzle
 constexpr int kEtBytes = 1024;
 constexpr int kOffInit = kOffEt + kStages * kEtBytes;             // per stage: Sinkhorn start P0 [8][16] | H_pre, H_post [8][8] | inv_rms [8];
@@ -334,7 +334,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
 #pragma unroll
                 for (int i = 0; i < 4; ++i) grow[i] = gs4[i];
                 __syncwarp();                               // every lane has its G rows: M may overwrite the record
-                float* mp = reinterpret_cast<float*>(wrec + kWrecM) + (tk >> 1) * 32 + part * 8 + (tk & 1);
+                float* mp = reinterpret_cast<float*>(wrec + kWrecM) + (tk >> 1) * kMpStride + part * 8 + (tk & 1);
                 const float hsel = part == 0 ? hpre[0] : part == 1 ? hpre[1] : part == 2 ? hpre[2] : hpre[3];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -558,36 +558,40 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             const int s = tile % kStages;
             mbar_wait(&bar_full[s], (uint32_t)(tile / kStages) & 1u);
             const uint32_t sb = stage0 + s * kStageBytes;
-            float gacc[2][2][4];
+            // fragment row / column r = 8 * stream + token: every 8x8 ldmatrix tile is one swizzle atom (conflict-free);
+            // G[token][i][j] is the token-diagonal of the (i, j) 8x8 block of  D = dy_rows x_rows^T
+            float gacc[2][4][4];
 #pragma unroll
             for (int m = 0; m < 2; ++m)
 #pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) gacc[m][h2][0] = gacc[m][h2][1] = gacc[m][h2][2] = gacc[m][h2][3] = 0.f;
+                for (int n = 0; n < 4; ++n) gacc[m][n][0] = gacc[m][n][1] = gacc[m][n][2] = gacc[m][n][3] = 0.f;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 uint32_t bx[4][2];
 #pragma unroll
-                for (int nn = 0; nn < 4; nn += 2) {
-                    const int row = 8 * nn + (lm >> 1) * 8 + lr, chunk = 4 * hh + 2 * ks + (lm & 1);
-                    ldmatrix_x4(sb + ((row & 3) * 8 + cb) * 1024 + (row >> 2) * 128 + ((chunk ^ (row >> 2)) << 4),
+                for (int nn = 0; nn < 4; nn += 2) {     // matrices: (stream nn, k lo), (nn, k hi), (nn+1, k lo), (nn+1, k hi)
+                    const int chunk = 4 * hh + 2 * ks + (lm & 1);
+                    ldmatrix_x4(sb + ((nn + (lm >> 1)) * 8 + cb) * 1024 + lr * 128 + ((chunk ^ lr) << 4),
                                 bx[nn][0], bx[nn][1], bx[nn + 1][0], bx[nn + 1][1]);
                 }
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
+                for (int m = 0; m < 2; ++m) {           // matrices: (stream 2m, k lo), (2m+1, k lo), (2m, k hi), (2m+1, k hi)
                     uint32_t a0, a1, a2, a3;
-                    const int row = 16 * m + (lm & 1) * 8 + lr, chunk = 4 * hh + 2 * ks + (lm >> 1);
-                    ldmatrix_x4(sb + kHalf + ((row & 3) * 8 + cb) * 1024 + (row >> 2) * 128 + ((chunk ^ (row >> 2)) << 4), a0, a1, a2, a3);
-                    mma_bf16_16816(gacc[m][0], a0, a1, a2, a3, bx[2 * m][0], bx[2 * m][1]);
-                    mma_bf16_16816(gacc[m][1], a0, a1, a2, a3, bx[2 * m + 1][0], bx[2 * m + 1][1]);
+                    const int chunk = 4 * hh + 2 * ks + (lm >> 1);
+                    ldmatrix_x4(sb + kHalf + ((2 * m + (lm & 1)) * 8 + cb) * 1024 + lr * 128 + ((chunk ^ lr) << 4), a0, a1, a2, a3);
+#pragma unroll
+                    for (int n = 0; n < 4; ++n) mma_bf16_16816(gacc[m][n], a0, a1, a2, a3, bx[n][0], bx[n][1]);
                 }
             }
-            if ((g >> 2) == (t >> 1)) {
-                float* pw = part + w * (kTok * 16) + 4 * (g & 3) + 2 * (t & 1);
+            if ((g >> 1) == t) {                        // this thread holds column token g of rows (2m, g) and (2m+1, g)
+                float* pw = part + w * (kTok * 16) + g * 16;
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    *reinterpret_cast<float2*>(pw + (4 * m + (g >> 2)) * 16) = make_float2(gacc[m][0][0], gacc[m][0][1]);
-                    *reinterpret_cast<float2*>(pw + (4 * m + 2 + (g >> 2)) * 16) = make_float2(gacc[m][1][2], gacc[m][1][3]);
-                }
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int n = 0; n < 4; ++n) {
+                        pw[(2 * m) * 4 + n] = (g & 1) ? gacc[m][n][1] : gacc[m][n][0];
+                        pw[(2 * m + 1) * 4 + n] = (g & 1) ? gacc[m][n][3] : gacc[m][n][2];
+                    }
             }
             bar_sync(kBarW, kWorkerThreads);
             if (threadIdx.x < kTok * 16) {
@@ -645,7 +649,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 }
 #pragma unroll
                 for (int jj = 0; jj < kN; ++jj) {
-                    const float4* mq = reinterpret_cast<const float4*>(wrec + kWrecM) + (t * 4 + jj) * 2;
+                    const float4* mq = reinterpret_cast<const float4*>(wrec + kWrecM + t * (kMpStride * 4)) + jj * 2;
                     const float4 m01 = mq[0], m23 = mq[1];                        // (M_a[0],M_b[0],M_a[1],M_b[1]) (M_a[2],...)
                     const u64 mp[kN] = {pk2(m01.x, m01.y), pk2(m01.z, m01.w), pk2(m23.x, m23.y), pk2(m23.z, m23.w)};
                     const uint2 xa = lds64(sb + offa[jj]);
