@@ -57,13 +57,15 @@ constexpr int kOffSk = kOffInit + kStages * kInitBytes;
 constexpr int kOffPart = kOffSk + kCoefWarps * kSkWords * 4;      // split-K partials of G: [16 warps][8 tokens][16] fp32
 constexpr int kOffBias = kOffPart + kWorkers * kTok * 16 * 4;     // bias[24] staged once (float4 broadcast reads)
 constexpr int kOffBar = kOffBias + 128;
-constexpr int kOffTmem = kOffBar + 5 * kStages * 8;
+constexpr int kOffTmem = kOffBar + 7 * kStages * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0 && kOffInit % 16 == 0 && kOffSk % 16 == 0, "alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 constexpr uint32_t kTmemCols = 512;
-                                                      // dW accumulators: block (j, 128-channel quarter) at columns 32 * (4j + quarter)
+constexpr uint32_t kColDw = 0;                        // dW: 32 blocks (stream j, 64-channel block cb) of M = 64, b = 8j + cb; blocks 2p / 2p+1
+                                                      //     share columns [24p, 24p+24) at lane offsets 0 / 16
+constexpr uint32_t kColGs = 384;                      // [x ; dy] x^T of a tile: 32 columns per stage
 
 constexpr int kBarRec = 1 /*,2,3*/, kBarCoef = 4 /*,5,6*/, kBarW = 7;
 
@@ -82,6 +84,9 @@ struct FusedParams {
     int sk_iters;
     float eps_rms, eps_sk;
 };
+
+// development aid: per-tile event timestamps of CTA 0 (first 64 tiles) behind the cycle counters in p.dbg
+#define HVS_TR(tile, ev) do { if (p.dbg && blockIdx.x == 0 && (tile) < 64) p.dbg[148 * 4 * 8 + (tile) * 12 + (ev)] = clock64(); } while (0)
 
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
@@ -117,6 +122,9 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     uint64_t* bar_dxr = bar_ed + kStages;                                 // dx staged by the workers
     uint64_t* bar_dw = bar_dxr + kStages;                                 // dW MMAs of the tile complete
     uint64_t* bar_sv = bar_dw + kStages;                                  // saved records of the stage's next tile landed
+    uint64_t* bar_cd = bar_sv + kStages;                                  // coefficients of the tile written (coefficient warp)
+    uint64_t* bar_gs = bar_cd + kStages;                                  // G MMAs of the tile complete
+    volatile int* next_action = reinterpret_cast<volatile int*>(smem + kOffTmem + 8);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
     const int warp = threadIdx.x >> 5;
@@ -130,6 +138,8 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             mbar_init(&bar_dxr[s], kWorkerThreads);
             mbar_init(&bar_dw[s], 1);
             mbar_init(&bar_sv[s], 1);
+            mbar_init(&bar_cd[s], 32);
+            mbar_init(&bar_gs[s], 1);
         }
         fence_mbar_init();
     }
@@ -143,9 +153,9 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     for (int i = threadIdx.x; i < kStages * kEtBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(smem + kOffEt)[i] = 0u;
     if (warp < kWorkers) {
         const uint32_t zero[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        const uint32_t tq = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 128);
+        const uint32_t tq = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + kColDw + (uint32_t)((warp >> 2) * 96);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) tmem_st16(tq + 16 * c, zero);
+        for (int c = 0; c < 6; ++c) tmem_st16(tq + 16 * c, zero);
         tmem_wait_st();
     }
     fence_proxy_async_smem();
@@ -155,56 +165,92 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
 
     if (warp >= kWorkers) {
       if (warp == kWorkers + 1) {
-        // ===================================================== front thread: loads, MMA issue, stores
-        if (lane == 0) {
-            tma_prefetch_desc(&tmap_x);
-            tma_prefetch_desc(&tmap_dy);
-            tma_prefetch_desc(&tmap_dx);
+        // ===================================================== front warp: loads, MMA issue, stores.  The whole warp runs
+        // the loop (every address / descriptor stays warp-uniform, i.e. in uniform registers); lane 0 issues the
+        // asynchronous operations.
+        {
+            const bool leader = lane == 0;
+            if (leader) {
+                tma_prefetch_desc(&tmap_x);
+                tma_prefetch_desc(&tmap_dy);
+                tma_prefetch_desc(&tmap_dx);
+            }
             const uint32_t s0 = smem_u32(smem);
             auto load_tile = [&](int it) {
                 const int s = it % kStages;
-                const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok;
+                const int tok0 = ((int)blockIdx.x + it * (int)gridDim.x) * kTok;
                 uint8_t* st = smem + s * kStageBytes;
-                mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
-                tma_load_4d(st, &tmap_x, &bar_full[s], 0, (int)tok0, 0, 0);                 // one 32 KB box each
-                tma_load_4d(st + kHalf, &tmap_dy, &bar_full[s], 0, (int)tok0, 0, 0);
+                if (leader) {
+                    mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
+                    tma_load_4d(st, &tmap_x, &bar_full[s], 0, tok0, 0, 0);                  // one 32 KB box each
+                    tma_load_4d(st + kHalf, &tmap_dy, &bar_full[s], 0, tok0, 0, 0);
+                    HVS_TR(it, 0);
+                }
             };
             long long facc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long fprev = clock64();
 #define HVS_FTICK(slot) do { if (p.dbg) { const long long tn = clock64(); facc[slot] += tn - fprev; fprev = tn; } } while (0)
-            const uint32_t id_dw = umma_idesc_bf16(128, 32, 1, 0);
-            for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
-            for (int k = 0; k < n_local; ++k) {
+            const uint32_t id_gs = umma_idesc_bf16(64, 32, 0, 0);
+            const uint32_t id_dw = umma_idesc_bf16(64, 24, 1, 0);
+            auto retire = [&](int k) {
                 const int s = k % kStages;
                 const uint32_t ph = (uint32_t)(k / kStages) & 1u;
-                // dW += x^T E for the tile whose coefficients are ready: 16 blocks of 128 channels (two atoms along M),
+                // dW += x^T E for the tile whose coefficients are ready: 32 blocks of 64 channels (one atom each),
                 // K = 16 = the 8 token rows twice (stride 0) against [E_hi ; E_lo]
                 mbar_wait(&bar_ed[s], ph);
+                if (leader) HVS_TR(k, 9);
                 HVS_FTICK(2);
                 tc_fence_after();
                 const uint64_t bdesc = umma_smem_desc(s0 + kOffEt + s * kEtBytes, 512, 128, kUmmaLayoutNone);
-#pragma unroll 4
-                for (int b = 0; b < 16; ++b) {
-                    const uint32_t a = s0 + s * kStageBytes + b * 2048;          // atoms (j, 2q), (j, 2q+1): b = 4j + q
-                    umma_bf16_ss(tmem_base + 32u * b, umma_smem_desc(a, 1024, 0, kUmmaLayoutSw128), bdesc, id_dw, 1u);
-                }
-                umma_commit(&bar_dw[s]);
+                const uint64_t adesc0 = umma_smem_desc(s0 + s * kStageBytes, 1024, 0, kUmmaLayoutSw128);
+#pragma unroll
+                for (int b = 0; b < 32; ++b)           // atom b = 8j + cb at +1 KB each (= +64 in the address field)
+                    if (leader)
+                        umma_bf16_ss(tmem_base + ((uint32_t)((b & 1) * 16) << 16) + kColDw + (uint32_t)((b >> 1) * 24),
+                                     adesc0 + (uint64_t)(b * 64), bdesc, id_dw, 1u);
+                if (leader) umma_commit(&bar_dw[s]);
                 // dx of the tile (written in place over dy) -> HBM
                 HVS_FTICK(3);
                 mbar_wait(&bar_dxr[s], ph);
+                if (leader) HVS_TR(k, 10);
                 HVS_FTICK(4);
-                const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * kTok;
-                tma_store_4d(&tmap_dx, smem + s * kStageBytes + kHalf, 0, (int)tok0, 0, 0);
-                bulk_commit();
-                bulk_wait_read<0>();
+                const int tok0 = ((int)blockIdx.x + k * (int)gridDim.x) * kTok;
+                if (leader) {
+                    tma_store_4d(&tmap_dx, smem + s * kStageBytes + kHalf, 0, tok0, 0, 0);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                }
+                __syncwarp();
                 HVS_FTICK(5);
                 mbar_wait(&bar_dw[s], ph);                       // the tensor core is done reading x of this stage
+                if (leader) HVS_TR(k, 11);
                 HVS_FTICK(6);
                 if (k + kStages < n_local) load_tile(k + kStages);
                 HVS_FTICK(7);
+            };
+            for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
+            for (int it = 0; it < n_local; ++it) {
+                const int s = it % kStages;
+                // G of the landed tile: D[64 x 32] = [x rows ; dy rows] (x rows)^T over the 512 channels; the 8-row groups
+                // (stream atoms of one 64-channel block) sit 8 KB apart, x then dy
+                mbar_wait(&bar_full[s], (uint32_t)(it / kStages) & 1u);
+                HVS_FTICK(0);
+                tc_fence_after();
+                const uint64_t gdesc0 = umma_smem_desc(s0 + s * kStageBytes, 16, 8192, kUmmaLayoutSw128);
+#pragma unroll
+                for (int cb = 0; cb < 8; ++cb)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t d64 = gdesc0 + (uint64_t)(cb * 64 + ks * 2);      // +1 KB per block, +32 B per K step
+                        if (leader) umma_bf16_ss(tmem_base + kColGs + 32u * s, d64, d64, id_gs, (uint32_t)((cb | ks) != 0));
+                    }
+                if (leader) umma_commit(&bar_gs[s]);
+                HVS_FTICK(1);
+                if (it >= 2) retire(it - 2);
             }
-            bulk_wait<0>();
-            if (p.dbg) for (int q = 0; q < 8; ++q) p.dbg[((size_t)blockIdx.x * 4 + 3) * 8 + q] = facc[q];
+            for (int k = n_local >= 2 ? n_local - 2 : 0; k < n_local; ++k) retire(k);
+            if (leader) bulk_wait<0>();
+            if (p.dbg && leader) for (int q = 0; q < 8; ++q) p.dbg[((size_t)blockIdx.x * 4 + 3) * 8 + q] = facc[q];
         }
       } else {
         // ===================================================== coefficient warps (warps 16, 18, 19 <-> stage 0, 1, 2)
@@ -247,6 +293,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         for (int it = cw; it < n_local; it += kCoefWarps) {
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
             mbar_wait(&bar_sv[s], ph);
+            if (lane == 0) HVS_TR(it, 3);
             HVS_TICK(0);
             const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok;
             // ---- prologue, four lanes per token: inverse RMS, gates, softmax start of row i4 -> shared memory.
@@ -319,9 +366,11 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     }
                 }
             }
+            if (lane == 0) HVS_TR(it, 4);
             HVS_TICK(2);
             // ---- G = dy x^T of the tile (split-K sums by the workers; also: the tile has landed)
-            bar_sync(kBarRec + s, kWorkerThreads + 32);
+            bar_sync(kBarRec + s, 8 * 32 + 32);
+            mbar_wait(&bar_full[s], ph);
             HVS_TICK(3);
             // ---- M = P + hpost (x) hpre for the workers (part p writes column jj = p), gate gradients from G
             float dl[24];
@@ -351,86 +400,72 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dl[j] = dhpre[j] * hpre[j] * (1.0f - hpre[j]);
             }
+            if (lane == 0) HVS_TR(it, 5);
             HVS_TICK(4);
             // ---- reverse sweep in the scaling form.  K by rows (Kr) and by columns (Kc), both packed; dK accumulates
             //      by rows; ub / vb are the adjoints of the current u / v.
             u64 dK[4][2];
             {
-                u64 Kr[4][2], Kc[4][2];
-                {
-                    float kv[4][4];
+                u64 Kr[4][2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 v = *reinterpret_cast<const float4*>(init + tk * 16 + 4 * i);
-                        kv[i][0] = v.x; kv[i][1] = v.y; kv[i][2] = v.z; kv[i][3] = v.w;
-                        Kr[i][0] = pk2(v.x, v.y);
-                        Kr[i][1] = pk2(v.z, v.w);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        Kc[j][0] = pk2(kv[0][j], kv[1][j]);
-                        Kc[j][1] = pk2(kv[2][j], kv[3][j]);
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = *reinterpret_cast<const float4*>(init + tk * 16 + 4 * i);
+                    Kr[i][0] = pk2(v.x, v.y);
+                    Kr[i][1] = pk2(v.z, v.w);
                 }
                 const int last = p.sk_iters - 1;
-                float4 un = make_float4(1.f, 1.f, 1.f, 1.f), vn = un;           // u_k, v_k of the iteration being undone
+                const float* skp = skl + last * 64;                             // u_k | v_k of the iteration being undone
+                float4 un = make_float4(1.f, 1.f, 1.f, 1.f), vn = un;
                 if (last >= 0) {
-                    un = *reinterpret_cast<const float4*>(skl + last * 64);
-                    vn = *reinterpret_cast<const float4*>(skl + last * 64 + 4);
+                    un = *reinterpret_cast<const float4*>(skp);
+                    vn = *reinterpret_cast<const float4*>(skp + 4);
                 }
-                // adjoints of the output P = diag(u) K diag(v):  dK = G u v^T,  ub_i = sum_j G_ij K_ij v_j,  vb_j = sum_i G_ij K_ij u_i
-                u64 ub01, ub23, vb01, vb23;
+                // adjoints of the output P = diag(u) K diag(v):  dK = G u v^T,  ub_i = sum_j G_ij K_ij v_j,  vb_j = sum_i G_ij K_ij u_i.
+                // ub is kept as one packed partial-sum pair per row (its two halves are added when it is consumed).
+                u64 ubp[4], vb01, vb23;
                 {
                     const u64 v01 = pk2(vn.x, vn.y), v23 = pk2(vn.z, vn.w);
                     const float uu[4] = {un.x, un.y, un.z, un.w};
-                    float ubs[4];
                     vb01 = pk2(0.f, 0.f); vb23 = vb01;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const u64 g0 = pk2(grow[i].x, grow[i].y), g1 = pk2(grow[i].z, grow[i].w);
                         const u64 gk0 = mul2(g0, Kr[i][0]), gk1 = mul2(g1, Kr[i][1]);
                         const u64 ui = pk2(uu[i], uu[i]);
-                        float sa, sb;
-                        upk2(fma2(gk1, v23, mul2(gk0, v01)), sa, sb);
-                        ubs[i] = sa + sb;
+                        ubp[i] = fma2(gk1, v23, mul2(gk0, v01));
                         vb01 = fma2(gk0, ui, vb01);
                         vb23 = fma2(gk1, ui, vb23);
                         dK[i][0] = mul2(mul2(g0, v01), ui);
                         dK[i][1] = mul2(mul2(g1, v23), ui);
                     }
-                    ub01 = pk2(ubs[0], ubs[1]); ub23 = pk2(ubs[2], ubs[3]);
                 }
                 for (int k = last; k >= 0; --k) {
                     const float uu[4] = {un.x, un.y, un.z, un.w};
-                    const u64 u01 = pk2(un.x, un.y), u23 = pk2(un.z, un.w), nu01 = pk2(-un.x, -un.y), nu23 = pk2(-un.z, -un.w);
                     const u64 v01 = pk2(vn.x, vn.y), v23 = pk2(vn.z, vn.w), nv01 = pk2(-vn.x, -vn.y), nv23 = pk2(-vn.z, -vn.w);
+                    skp -= 64;
                     if (k > 0) {                                                // u_{k-1}, v_{k-1}
-                        un = *reinterpret_cast<const float4*>(skl + (k - 1) * 64);
-                        vn = *reinterpret_cast<const float4*>(skl + (k - 1) * 64 + 4);
+                        un = *reinterpret_cast<const float4*>(skp);
+                        vn = *reinterpret_cast<const float4*>(skp + 4);
                     } else {
                         vn = make_float4(1.f, 1.f, 1.f, 1.f);                   // v_0
                     }
                     const u64 vp01 = pk2(vn.x, vn.y), vp23 = pk2(vn.z, vn.w);
                     // v_k = 1 / (K^T u_k):  tb = -vb v_k^2 ;  ub += K tb ;  dK += u_k tb^T
                     const u64 tb01 = mul2(mul2(vb01, v01), nv01), tb23 = mul2(mul2(vb23, v23), nv23);
-                    float tb[4];
-                    upk2(tb01, tb[0], tb[1]); upk2(tb23, tb[2], tb[3]);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const u64 tj = pk2(tb[j], tb[j]);
-                        ub01 = fma2(Kc[j][0], tj, ub01);
-                        ub23 = fma2(Kc[j][1], tj, ub23);
-                    }
+                    float sb[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const u64 ui = pk2(uu[i], uu[i]);
+                        ubp[i] = fma2(Kr[i][1], tb23, fma2(Kr[i][0], tb01, ubp[i]));
                         dK[i][0] = fma2(tb01, ui, dK[i][0]);
                         dK[i][1] = fma2(tb23, ui, dK[i][1]);
+                        // u_k = 1 / (K v_{k-1}):  sb = -ub u_k^2
+                        float ua, ub_;
+                        upk2(ubp[i], ua, ub_);
+                        sb[i] = -(ua + ub_) * (uu[i] * uu[i]);
+                        ubp[i] = pk2(0.f, 0.f);
                     }
-                    // u_k = 1 / (K v_{k-1}):  sb = -ub u_k^2 ;  vb = K^T sb ;  dK += sb v_{k-1}^T ;  ub = 0
-                    const u64 sb01 = mul2(mul2(ub01, u01), nu01), sb23 = mul2(mul2(ub23, u23), nu23);
-                    float sb[4];
-                    upk2(sb01, sb[0], sb[1]); upk2(sb23, sb[2], sb[3]);
+                    // vb = K^T sb ;  dK += sb v_{k-1}^T
                     {
                         const u64 s0 = pk2(sb[0], sb[0]);
                         vb01 = mul2(Kr[0][0], s0);
@@ -446,7 +481,6 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                         dK[i][0] = fma2(vp01, si, dK[i][0]);
                         dK[i][1] = fma2(vp23, si, dK[i][1]);
                     }
-                    ub01 = pk2(0.f, 0.f); ub23 = ub01;
                 }
                 HVS_TICK(5);
                 // ---- softmax * 4 backward: dl = K (dK - sum_j(dK K) / 4); the sums for kappa (RMSNorm backward) and
@@ -499,8 +533,8 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 fence_proxy_async_smem();
                 fetch_saved(it + kCoefWarps);
             }
-            __threadfence_block();
-            bar_arrive(kBarCoef + s, kWorkerThreads + 32);
+            mbar_arrive(&bar_cd[s]);                        // release: every lane's stores above are visible to the waiter
+            if (lane == 0) HVS_TR(it, 6);
             HVS_TICK(6);
         }
         if (p.dbg && lane == 0)
@@ -547,74 +581,57 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             offa[jj] = (jj * 8 + cb) * 1024 + (2 * t) * 128 + (((4 * hh + (g >> 1)) ^ (2 * t)) << 4) + (g & 1) * 8;
         const uint32_t stage0 = smem_u32(smem);
         float acc_db = 0.f;                               // dbias of logit tid % 24 over tokens tid / 24 (threads < 192)
-        const int q = w & 3;                              // tensor-memory lane quadrant of this warp
-        const int lm = lane >> 3, lr = lane & 7;          // ldmatrix: matrix index / row of an x4 load
-        float* part = reinterpret_cast<float*>(smem + kOffPart);
+        const int q = w & 3, jcol = w >> 2;               // tensor-memory lane quadrant / G column group of this warp
+        const uint32_t tm_gs = tmem_base + ((uint32_t)(32 * q) << 16) + kColGs + 8u * jcol;
 
-        // G = dy x^T of a tile, per token 4x4, on the warp MMA path: fragment rows / columns are (token, stream) pairs
-        // gathered from the [stream][block][token] atoms, this warp contracts its 32 channels; only the token-diagonal
-        // 4x4 blocks are kept.  Split-K partials go through shared memory, fixed-order sum into the tile's record.
+        // G blocks of a tile out of tensor memory into its record: lanes 0..15 of quadrants 2 and 3 hold the dy rows
+        // (stream 2(q-2) + lane/8, token lane%8); a warp takes the columns of x stream jcol and keeps the token diagonal.
         auto g_tile = [&](int tile) {
             const int s = tile % kStages;
-            mbar_wait(&bar_full[s], (uint32_t)(tile / kStages) & 1u);
-            const uint32_t sb = stage0 + s * kStageBytes;
-            // fragment row / column r = 8 * stream + token: every 8x8 ldmatrix tile is one swizzle atom (conflict-free);
-            // G[token][i][j] is the token-diagonal of the (i, j) 8x8 block of  D = dy_rows x_rows^T
-            float gacc[2][4][4];
+            if (q >= 2) {
+                mbar_wait(&bar_gs[s], (uint32_t)(tile / kStages) & 1u);
+                tc_fence_after();
+                uint32_t v[8];
+                tmem_ld8(tm_gs + 32u * s, v);
+                tmem_wait_ld();
+                const int tok = lane & 7;
+                uint32_t val = v[0];
 #pragma unroll
-            for (int m = 0; m < 2; ++m)
-#pragma unroll
-                for (int n = 0; n < 4; ++n) gacc[m][n][0] = gacc[m][n][1] = gacc[m][n][2] = gacc[m][n][3] = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                uint32_t bx[4][2];
-#pragma unroll
-                for (int nn = 0; nn < 4; nn += 2) {     // matrices: (stream nn, k lo), (nn, k hi), (nn+1, k lo), (nn+1, k hi)
-                    const int chunk = 4 * hh + 2 * ks + (lm & 1);
-                    ldmatrix_x4(sb + ((nn + (lm >> 1)) * 8 + cb) * 1024 + lr * 128 + ((chunk ^ lr) << 4),
-                                bx[nn][0], bx[nn][1], bx[nn + 1][0], bx[nn + 1][1]);
-                }
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {           // matrices: (stream 2m, k lo), (2m+1, k lo), (2m, k hi), (2m+1, k hi)
-                    uint32_t a0, a1, a2, a3;
-                    const int chunk = 4 * hh + 2 * ks + (lm >> 1);
-                    ldmatrix_x4(sb + kHalf + ((2 * m + (lm & 1)) * 8 + cb) * 1024 + lr * 128 + ((chunk ^ lr) << 4), a0, a1, a2, a3);
-#pragma unroll
-                    for (int n = 0; n < 4; ++n) mma_bf16_16816(gacc[m][n], a0, a1, a2, a3, bx[n][0], bx[n][1]);
-                }
+                for (int c = 1; c < 8; ++c) val = tok == c ? v[c] : val;
+                if (lane < 16)
+                    reinterpret_cast<uint32_t*>(smem + kOffWrec + s * kWrecBytes)[tok * 16 + (2 * (q - 2) + (lane >> 3)) * 4 + jcol] = val;
+                tc_fence_before();
+                __threadfence_block();
+                bar_arrive(kBarRec + s, 8 * 32 + 32);
             }
-            if ((g >> 1) == t) {                        // this thread holds column token g of rows (2m, g) and (2m+1, g)
-                float* pw = part + w * (kTok * 16) + g * 16;
-#pragma unroll
-                for (int m = 0; m < 2; ++m)
-#pragma unroll
-                    for (int n = 0; n < 4; ++n) {
-                        pw[(2 * m) * 4 + n] = (g & 1) ? gacc[m][n][1] : gacc[m][n][0];
-                        pw[(2 * m + 1) * 4 + n] = (g & 1) ? gacc[m][n][3] : gacc[m][n][2];
-                    }
+            if (threadIdx.x == 0) HVS_TR(tile, 2);
+        };
+        // Worker schedule: whichever is ready first -- G of the next landed tile (it unblocks that tile's coefficient
+        // chain) or dx of the next tile whose coefficients are done.  Thread 0 polls the two mbarriers and publishes
+        // the choice, so all 16 warps take the same branch (both actions contain worker-wide barriers).
+        int g_next = 0, d_next = 0;
+        while (d_next < n_local) {
+            if (threadIdx.x == 0) {
+                int act = 0;
+                while (act == 0) {
+                    if (g_next < n_local && mbar_test_wait(&bar_gs[g_next % kStages], (uint32_t)(g_next / kStages) & 1u)) act = 1;
+                    else if (mbar_test_wait(&bar_cd[d_next % kStages], (uint32_t)(d_next / kStages) & 1u)) act = 2;
+                }
+                *next_action = act;
             }
             bar_sync(kBarW, kWorkerThreads);
-            if (threadIdx.x < kTok * 16) {
-                float v[kWorkers];
-#pragma unroll
-                for (int ww = 0; ww < kWorkers; ++ww) v[ww] = part[ww * (kTok * 16) + threadIdx.x];
-#pragma unroll
-                for (int st = 1; st < kWorkers; st <<= 1)
-#pragma unroll
-                    for (int ww = 0; ww < kWorkers; ww += 2 * st) v[ww] += v[ww + st];
-                reinterpret_cast<float*>(smem + kOffWrec + s * kWrecBytes)[threadIdx.x] = v[0];
+            const int act = *next_action;
+            if (act == 1) {
+                g_tile(g_next);
+                ++g_next;
+                continue;
             }
-            __threadfence_block();
-            bar_arrive(kBarRec + s, kWorkerThreads + 32);
-        };
-        for (int step = 0; step < n_local + 2; ++step) {
-            const int k = step - 2;
-            if (k < 0) bar_sync(kBarW, kWorkerThreads);    // (later steps: the E-tile barrier below separates the uses of `part`)
-            if (k >= 0) {
+            {
                 // ============ dx for tokens 2t, 2t+1 of tile k, channels 32w + 4g .. +3 of every stream
+                const int k = d_next++;
                 const int s = k % kStages;
-                bar_sync(kBarCoef + s, kWorkerThreads + 32);
-                mbar_wait(&bar_full[s], (uint32_t)(k / kStages) & 1u);
+                mbar_wait(&bar_cd[s], (uint32_t)(k / kStages) & 1u);          // acquire the coefficient warp's stores
+                if (threadIdx.x == 0) HVS_TR(k, 7);
                 const uint32_t sb = stage0 + s * kStageBytes;
                 uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
                 if (threadIdx.x < kTok * kL) {
@@ -683,8 +700,8 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_dxr[s]);
+                if (threadIdx.x == 0) HVS_TR(k, 8);
             }
-            if (step < n_local) g_tile(step);
         }
         // ============ dbias of this CTA: fold the 8 tokens in a fixed order
         {
@@ -703,12 +720,14 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             const int last = n_local - 1;
             mbar_wait(&bar_dw[last % kStages], (uint32_t)(last / kStages) & 1u);
             tc_fence_after();
+            const int half = lane >> 4, r = lane & 15;
             float* out = p.dw_part + (size_t)blockIdx.x * kRow * kL;
 #pragma unroll
             for (int pi = 0; pi < 4; ++pi) {
-                const int b = (w >> 2) * 4 + pi;           // block = (stream b / 4, 128-channel quarter b % 4); lane = channel
-                const int kidx = (b >> 2) * kC + (b & 3) * 128 + 32 * q + lane;
-                const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * 32);
+                const int pr = (w >> 2) * 4 + pi;          // column range = block pair
+                const int b = 2 * pr + half;               // block (j, cb) = (b >> 3, b & 7), row = channel in the block
+                const int kidx = (b >> 3) * kC + (b & 7) * 64 + 16 * q + r;
+                const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + kColDw + (uint32_t)(pr * 24);
                 uint32_t v[8];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {

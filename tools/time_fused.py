@@ -13,7 +13,7 @@ hvs_b200.ops.mhc_stream_fwd(x, phi, bias, alpha, scale, out=y, saved=saved)
 lib = hvs_b200._lib.load()
 lib.hvs_debug_fused_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
 mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-buf = torch.zeros(148 * 4 * 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(148 * 4 * 8 + 64 * 12, dtype=torch.int64, device=dev)
 hvs_b200.ops.mhc_stream_bwd_saved(x, dy, saved, phi, bias, alpha, scale)
 lib.hvs_debug_fused_timing(buf.data_ptr(), mode)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -21,7 +21,7 @@ a.record(); hvs_b200.ops.mhc_stream_bwd_saved(x, dy, saved, phi, bias, alpha, sc
 torch.cuda.synchronize()
 lib.hvs_debug_fused_timing(None, 0)
 ms = a.elapsed_time(b)
-tt = buf.view(148, 4, 8).double()
+tt = buf[:148 * 4 * 8].view(148, 4, 8).double()
 t = tt[:, :3]
 tiles_per_warp = (T / 8) / 148 / 3
 names = ["wait_full", "prologue", "fwd_loop", "wait_G", "mid(M,gates)", "bwd_loop", "epilogue", "-"]
@@ -36,3 +36,11 @@ print("front thread, cycles per tile:")
 for i, n in enumerate(fn):
     print(f"  {n:14s} {tt[:, 3, i].mean().item() / tiles:9.0f}")
 print("  total", tt[:, 3].sum(-1).mean().item() / tiles)
+
+tr = buf[148 * 4 * 8:].view(64, 12).cpu().numpy()
+base = tr[20, 0]
+ev = ["load", "Gstart", "Gend", "fwd0", "fwd1", "Ggot", "cdone", "P3s", "P3e", "ed", "store", "freed"]
+print("trace CTA 0, tiles 20..31, kcycles relative to load(20):")
+print("tile " + " ".join(f"{e:>7s}" for e in ev))
+for k in range(20, 32):
+    print(f"{k:4d} " + " ".join(f"{(tr[k, e] - base) / 1000:7.1f}" for e in range(12)))
