@@ -39,7 +39,7 @@ constexpr int kThreads = (kWorkers + 4) * 32;         // + coefficient warp 0, f
 constexpr int kStageBytes = 65536;                    // [x 32 KB][dy 32 KB]; each = 32 swizzle atoms (stream j, 64-channel block cb) of 8 tokens x 128 B
 constexpr int kHalf = 32768;
 constexpr int kSaved = HVS_MHC_SAVED_STRIDE;          // floats per token in the saved record: raw[24], sum x^2, pad
-constexpr int kMaxIters = 20;                        // normalisers of every iteration are kept in shared memory
+constexpr int kMaxIters = 24;                        // normalisers of every iteration are kept in shared memory
 constexpr int kCoefWarps = 3;
 constexpr int kAccum = kL + 3;
 
@@ -51,15 +51,17 @@ constexpr int kWrecBytes = 1152, kWrecM = 384, kWrecK = 960, kWrecS = 992, kMpSt
 constexpr int kOffEt = kOffWrec + kStages * kWrecBytes;           // per stage: E tile, 32 rows (24 logits + 8 zero) x 16 K bf16, no swizzle
 constexpr int kEtBytes = 1024;
 constexpr int kOffInit = kOffEt + kStages * kEtBytes;             // per stage: Sinkhorn start P0 [8][16] | H_pre, H_post [8][8] | inv_rms [8];
-constexpr int kInitBytes = 800, kInitH = 512, kInitR = 768;       //            the d logits [8][24] overlay P0 / H once those are dead
+constexpr int kInitBytes = 800, kInitH = 512, kInitR = 768;
 constexpr int kSkWords = kTok * kMaxIters * 8;
 constexpr int kOffSk = kOffInit + kStages * kInitBytes;
-constexpr int kOffPart = kOffSk + kCoefWarps * kSkWords * 4;      // split-K partials of G: [16 warps][8 tokens][16] fp32
-constexpr int kOffBias = kOffPart + kWorkers * kTok * 16 * 4;     // bias[24] staged once (float4 broadcast reads)
+constexpr int kOffDl = kOffSk + kCoefWarps * kSkWords * 4;        // per stage: d logits [8][24] fp32 (coefficient warp -> workers)
+constexpr int kDlBytes = 768;
+constexpr int kOffPart = kOffDl + kStages * kDlBytes;             // end-of-kernel dbias fold: [8 tokens][24] fp32
+constexpr int kOffBias = kOffPart + kTok * kL * 4;                // bias[24] staged once (float4 broadcast reads)
 constexpr int kOffBar = kOffBias + 128;
 constexpr int kOffTmem = kOffBar + 7 * kStages * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
-static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0 && kOffInit % 16 == 0 && kOffSk % 16 == 0, "alignment");
+static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0 && kOffInit % 16 == 0 && kOffSk % 16 == 0 && kOffDl % 16 == 0, "alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 constexpr uint32_t kTmemCols = 512;
@@ -85,8 +87,15 @@ struct FusedParams {
     float eps_rms, eps_sk;
 };
 
-// development aid: per-tile event timestamps of CTA 0 (first 64 tiles) behind the cycle counters in p.dbg
+// development aid (compile with -DHVS_FUSED_TRACE): cycle counters of the coefficient / front warps and per-tile
+// event timestamps of CTA 0 (first 64 tiles), written to p.dbg.  Compiled out by default.
+#ifdef HVS_FUSED_TRACE
 #define HVS_TR(tile, ev) do { if (p.dbg && blockIdx.x == 0 && (tile) < 64) p.dbg[148 * 4 * 8 + (tile) * 12 + (ev)] = clock64(); } while (0)
+#define HVS_TRACE_ON 1
+#else
+#define HVS_TR(tile, ev) do { } while (0)
+#define HVS_TRACE_ON 0
+#endif
 
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
@@ -189,7 +198,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             };
             long long facc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long fprev = clock64();
-#define HVS_FTICK(slot) do { if (p.dbg) { const long long tn = clock64(); facc[slot] += tn - fprev; fprev = tn; } } while (0)
+#define HVS_FTICK(slot) do { if (HVS_TRACE_ON && p.dbg) { const long long tn = clock64(); facc[slot] += tn - fprev; fprev = tn; } } while (0)
             const uint32_t id_gs = umma_idesc_bf16(64, 32, 0, 0);
             const uint32_t id_dw = umma_idesc_bf16(64, 24, 1, 0);
             auto retire = [&](int k) {
@@ -250,7 +259,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             }
             for (int k = n_local >= 2 ? n_local - 2 : 0; k < n_local; ++k) retire(k);
             if (leader) bulk_wait<0>();
-            if (p.dbg && leader) for (int q = 0; q < 8; ++q) p.dbg[((size_t)blockIdx.x * 4 + 3) * 8 + q] = facc[q];
+            if (HVS_TRACE_ON && p.dbg && leader) for (int q = 0; q < 8; ++q) p.dbg[((size_t)blockIdx.x * 4 + 3) * 8 + q] = facc[q];
         }
       } else {
         // ===================================================== coefficient warps (warps 16, 18, 19 <-> stage 0, 1, 2)
@@ -289,7 +298,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         if (lane == 0 && cw < n_local) fetch_saved(cw);
         long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         long long tprev = clock64();
-#define HVS_TICK(slot) do { if (p.dbg) { const long long tn = clock64(); tacc[slot] += tn - tprev; tprev = tn; } } while (0)
+#define HVS_TICK(slot) do { if (HVS_TRACE_ON && p.dbg) { const long long tn = clock64(); tacc[slot] += tn - tprev; tprev = tn; } } while (0)
         for (int it = cw; it < n_local; it += kCoefWarps) {
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
             mbar_wait(&bar_sv[s], ph);
@@ -516,7 +525,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             // part p stores quad p, parts 0 and 1 also quads 4 and 5
             {
                 __syncwarp();
-                float4* dq = reinterpret_cast<float4*>(init) + tk * 6;     // overlays P0 / H (dead by now)
+                float4* dq = reinterpret_cast<float4*>(smem + kOffDl + s * kDlBytes) + tk * 6;
                 float4 a, b;
                 a.x = part == 0 ? dl[0] : part == 1 ? dl[4] : part == 2 ? dl[8] : dl[12];
                 a.y = part == 0 ? dl[1] : part == 1 ? dl[5] : part == 2 ? dl[9] : dl[13];
@@ -537,7 +546,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             if (lane == 0) HVS_TR(it, 6);
             HVS_TICK(6);
         }
-        if (p.dbg && lane == 0)
+        if (HVS_TRACE_ON && p.dbg && lane == 0)
             for (int q = 0; q < 8; ++q) p.dbg[((size_t)blockIdx.x * 4 + cw) * 8 + q] = tacc[q];
         // dalpha: sum the 8 tokens of the warp (part 0 lanes) in a fixed order; dbias comes from the workers
 #pragma unroll
@@ -638,7 +647,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     // e = alpha_g * inv_rms * d logit of (token, logit) = (tid / 24, tid % 24): bf16 hi for the W e MMA,
                     // hi and lo into the E tile of the dW MMA (rows = logits, K = token | 8 + token); dbias in registers
                     const int etok = threadIdx.x / kL, er = threadIdx.x - etok * kL;
-                    const float dlv = reinterpret_cast<const float*>(smem + kOffInit + s * kInitBytes)[threadIdx.x];
+                    const float dlv = reinterpret_cast<const float*>(smem + kOffDl + s * kDlBytes)[threadIdx.x];
                     const float e = dlv * reinterpret_cast<const float*>(wrec + kWrecS)[etok * 3 + (er < kN ? 0 : er < 2 * kN ? 1 : 2)];
                     acc_db += dlv;
                     const __nv_bfloat16 hi = __float2bfloat16_rn(e);
@@ -658,7 +667,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 const float2 kp = *reinterpret_cast<const float2*>(wrec + kWrecK + 8 * t);
                 const u64 kp2 = pk2(kp.x, kp.y);
                 uint2 dya[kN], dyb[kN];
-                if (!(p.dbg_mode & 1)) {
+                {
 #pragma unroll
                 for (int ii = 0; ii < kN; ++ii) {
                     dya[ii] = lds64(sb + kHalf + offa[ii]);

@@ -23,19 +23,35 @@ from ._lib import HvsError
 
 
 # ----------------------------------------------------------------------------- K1
+FUSED_BWD_MAX_ITERS = 24      # the single-pass backward keeps every iteration's scalings in shared memory
+
+
 class _StreamMHCFn(torch.autograd.Function):
+    """Training path.  The forward additionally writes 112 B/token of statistics (un-normalised projection and
+    sum of squares); the backward is then ONE fused kernel (dx and every parameter gradient in a single pass over
+    x and dy).  With more than 24 Sinkhorn iterations the two-kernel backward that recomputes everything is used."""
+
     @staticmethod
     def forward(ctx, x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk):
-        y, _, _ = ops.mhc_stream_fwd(x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk)
-        ctx.save_for_backward(x, phi, bias, alpha, scale)        # nothing else: coefficients are recomputed
-        ctx.cfg = (sk_iters, eps_rms, eps_sk)
+        fused = sk_iters <= FUSED_BWD_MAX_ITERS
+        saved = ops.new_saved(x) if fused else None
+        y, _, _ = ops.mhc_stream_fwd(x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk, saved=saved)
+        if fused:
+            ctx.save_for_backward(x, phi, bias, alpha, scale, saved)
+        else:
+            ctx.save_for_backward(x, phi, bias, alpha, scale)
+        ctx.cfg = (sk_iters, eps_rms, eps_sk, fused)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, phi, bias, alpha, scale = ctx.saved_tensors
-        sk_iters, eps_rms, eps_sk = ctx.cfg
-        g = ops.mhc_stream_bwd(x, dy.contiguous(), phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk)
+        sk_iters, eps_rms, eps_sk, fused = ctx.cfg
+        if fused:
+            x, phi, bias, alpha, scale, saved = ctx.saved_tensors
+            g = ops.mhc_stream_bwd_saved(x, dy.contiguous(), saved, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk)
+        else:
+            x, phi, bias, alpha, scale = ctx.saved_tensors
+            g = ops.mhc_stream_bwd(x, dy.contiguous(), phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk)
         return g["dx"], g["dphi"], g["dbias"], g["dalpha"], g["dscale"], None, None, None
 
 
@@ -94,8 +110,14 @@ def stream_mhc_fwd_bwd_host(x_host: torch.Tensor, dy_host: torch.Tensor, layer: 
     n, c = layer.n_streams, layer.channels
     nchunks = (t + chunk_tokens - 1) // chunk_tokens
     s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    bufs = [{k: torch.empty((chunk_tokens, n, c), dtype=torch.bfloat16, device=dev) for k in ("x", "dy", "y")}
+    bufs = [{k: torch.empty((chunk_tokens, n, c), dtype=torch.bfloat16, device=dev) for k in ("x", "dy", "y", "dx")}
             for _ in range(2)]
+    fused = layer.sk_iterations <= FUSED_BWD_MAX_ITERS
+    saved = [ops.new_saved(bufs[0]["x"]) for _ in range(2)] if fused else None
+    ws = None
+    if fused:
+        from . import _lib
+        ws = torch.empty(int(_lib.load().hvs_mhc_stream_bwd_saved_workspace(chunk_tokens, n, c)), dtype=torch.uint8, device=dev)
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_cmp = [torch.cuda.Event() for _ in range(2)]
     ev_out = [torch.cuda.Event() for _ in range(2)]
@@ -112,20 +134,25 @@ def stream_mhc_fwd_bwd_host(x_host: torch.Tensor, dy_host: torch.Tensor, layer: 
             ev_in[i % 2].record(s_in)
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[i % 2])
-            ops.mhc_stream_fwd(b["x"][:m], *params, layer.sk_iterations, layer.eps, layer.eps, out=b["y"][:m])
-            g = ops.mhc_stream_bwd(b["x"][:m], b["dy"][:m], *params, layer.sk_iterations, layer.eps, layer.eps)
+            if fused:
+                sv = saved[i % 2][:m]
+                ops.mhc_stream_fwd(b["x"][:m], *params, layer.sk_iterations, layer.eps, layer.eps, out=b["y"][:m], saved=sv)
+                g = ops.mhc_stream_bwd_saved(b["x"][:m], b["dy"][:m], sv, *params, layer.sk_iterations, layer.eps,
+                                             layer.eps, out=b["dx"][:m], workspace=ws)
+            else:
+                ops.mhc_stream_fwd(b["x"][:m], *params, layer.sk_iterations, layer.eps, layer.eps, out=b["y"][:m])
+                g = ops.mhc_stream_bwd(b["x"][:m], b["dy"][:m], *params, layer.sk_iterations, layer.eps, layer.eps)
+                b["dx"][:m].copy_(g["dx"])
             if acc is None:
-                acc = {k: g[k] for k in ("dphi", "dbias", "dalpha", "dscale")}
+                acc = {k: g[k].clone() for k in ("dphi", "dbias", "dalpha", "dscale")}
             else:
                 for k in acc:
                     acc[k] += g[k]
-            b["dx"] = g["dx"]
             ev_cmp[i % 2].record(s_cmp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_cmp[i % 2])
             y_host[lo:hi].copy_(b["y"][:m], non_blocking=True)
             dx_host[lo:hi].copy_(b["dx"][:m], non_blocking=True)
-            b["dx"].record_stream(s_out)
             ev_out[i % 2].record(s_out)
     out = {}
     with torch.cuda.stream(s_out):

@@ -91,7 +91,7 @@ int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* phi, const fl
 /* Backward of hvs_mhc_stream_fwd_save (F = identity) in ONE fused kernel: dx and dphi/dscale/dbias/dalpha in a
  * single pass over x and dy (12288 + 112 B/token); `saved` is the forward's [T, HVS_MHC_SAVED_STRIDE] record.
  * The Sinkhorn forward iterations are replayed from the saved logits and differentiated exactly.
- * Same outputs and conventions as hvs_mhc_stream_bwd.  sk_iters <= 24.
+ * Same outputs and conventions as hvs_mhc_stream_bwd.  sk_iters <= 24 (HVS_ERR_UNSUPPORTED beyond: use hvs_mhc_stream_bwd).
  * workspace: hvs_mhc_stream_bwd_saved_workspace(T, n, C) bytes, 256-byte aligned. */
 size_t hvs_mhc_stream_bwd_saved_workspace(int64_t T, int n, int C);
 int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const float* saved, const float* phi,

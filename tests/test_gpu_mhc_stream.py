@@ -191,3 +191,129 @@ def test_backward_deterministic_and_linear_in_dy():
     c = run_bwd(*inp[:1], (dy.float() * 2).to(torch.bfloat16), *inp[1:])
     for k in ("dphi", "dbias", "dalpha", "dscale"):
         assert torch.allclose(c[k], 2 * a[k], rtol=1e-4, atol=1e-6 * a[k].abs().max().item()), k
+
+
+# ----------------------------------------------------------------------------- fused backward (saved statistics)
+def run_bwd_saved(x, dy, phi, bias, al, scale, sk_iters=20):
+    import hvs_b200
+    dev = "cuda:0"
+    xd = x.to(dev)
+    P = [p.to(dev) for p in (phi, bias, al, scale)]
+    saved = hvs_b200.ops.new_saved(xd)
+    y, _, _ = hvs_b200.ops.mhc_stream_fwd(xd, *P, sk_iters=sk_iters, saved=saved)
+    out = hvs_b200.ops.mhc_stream_bwd_saved(xd, dy.to(dev), saved, *P, sk_iters=sk_iters)
+    torch.cuda.synchronize()
+    res = {k: v.cpu() for k, v in out.items()}
+    res["saved"] = saved.cpu()
+    res["y"] = y.cpu()
+    return res
+
+
+def test_forward_saved_statistics():
+    """The training forward writes raw = x . bf16(scale*phi) and sum x^2 (what the fused backward consumes)."""
+    inp = make_inputs(300, seed=7, alpha=0.3, phistd=0.03, bstd=0.1)
+    x, phi, bias, al, scale = inp
+    got = run_bwd_saved(x, torch.zeros_like(x), phi, bias, al, scale)
+    w = (phi * scale[:, None]).to(torch.bfloat16).double()
+    raw = x.reshape(300, -1).double() @ w
+    ss = (x.double() ** 2).sum((1, 2))
+    assert torch.allclose(got["saved"][:, :24].double(), raw, rtol=1e-5, atol=1e-4)
+    assert torch.allclose(got["saved"][:, 24].double(), ss, rtol=1e-5)
+    assert (got["saved"][:, 25:] == 0).all()
+    # the saved variant computes the same y as the plain forward
+    import hvs_b200
+    y0, _, _ = hvs_b200.ops.mhc_stream_fwd(x.cuda(), phi.cuda(), bias.cuda(), al.cuda(), scale.cuda())
+    assert torch.equal(y0.cpu().view(torch.int16), got["y"].view(torch.int16))
+
+
+@pytest.mark.parametrize("t", [1, 7, 8, 9, 24, 25, 64, 1000, 2051])
+def test_fused_backward_matches_oracle(t):
+    inp = make_inputs(t, seed=200 + t, alpha=0.3, phistd=0.03, bstd=0.1)
+    dy = torch.randn(t, 4, 512, generator=torch.Generator().manual_seed(t)).to(torch.bfloat16)
+    got = run_bwd_saved(*inp[:1], dy, *inp[1:])
+    check_bwd(inp, dy, got, f"fused T={t}")
+
+
+def test_fused_backward_hot_logits_and_init_scale():
+    """Warm logits (std ~0.7: Sinkhorn still converges to 5e-7, the scaling-form reverse sweep is exercised far from
+    the uniform matrix) and the microbenchmark's alpha = 0.01 configuration against the oracle; hot logits (std > 2,
+    20 iterations leave a 3e-2 row error) against the oracle for the parameter gradients and against the two-kernel
+    backward for dx -- there the bf16 rounding of e in the W e MMA, common to both kernels, exceeds the 2-ulp
+    metric, which only accounts for the mixing term."""
+    inp = make_inputs(777, seed=41, alpha=0.5, phistd=0.03, bstd=0.3)
+    dy = torch.randn(777, 4, 512, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16)
+    check_bwd(inp, dy, run_bwd_saved(*inp[:1], dy, *inp[1:]), "fused warm")
+    inp = make_inputs(515, seed=21)
+    dy = torch.randn(515, 4, 512, generator=torch.Generator().manual_seed(5)).to(torch.bfloat16)
+    check_bwd(inp, dy, run_bwd_saved(*inp[:1], dy, *inp[1:]), "fused init")
+    inp = make_inputs(777, seed=41, alpha=1.0, phistd=0.05, bstd=0.5)
+    x, phi, bias, al, scale = inp
+    dy = torch.randn(777, 4, 512, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16)
+    got, two = run_bwd_saved(x, dy, phi, bias, al, scale), run_bwd(x, dy, phi, bias, al, scale)
+    ref = mhc_ref.stream_mhc_backward(x, dy, phi, bias, al, scale)
+    for name in ("dphi", "dbias", "dalpha", "dscale"):
+        a, b = got[name].double(), ref[name].double()
+        assert ((a - b).norm() / b.norm()).item() < 3e-4, name
+    d = got["dx"].float() - two["dx"].float()
+    assert (d.norm() / two["dx"].float().norm()).item() < 2.0 ** -8            # bf16 output rounding level
+    assert d.abs().max().item() <= 2.0 ** -6 * two["dx"].float().abs().max().item()
+    assert ((got["dx"].float() - ref["dx"]).norm() / ref["dx"].norm()).item() < 2.0 ** -7
+
+
+@pytest.mark.parametrize("iters", [0, 1, 5, 20, 24])
+def test_fused_backward_iteration_counts(iters):
+    import hvs_b200
+    inp = make_inputs(130, seed=50 + iters, alpha=0.4, phistd=0.03, bstd=0.2)
+    x, phi, bias, al, scale = inp
+    dy = torch.randn(130, 4, 512, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+    got = run_bwd_saved(x, dy, phi, bias, al, scale, sk_iters=iters)
+    old = hvs_b200.ops.mhc_stream_bwd(x.cuda(), dy.cuda(), phi.cuda(), bias.cuda(), al.cuda(), scale.cuda(), sk_iters=iters)
+    for k in ("dphi", "dbias", "dalpha", "dscale"):
+        a, b = got[k].double(), old[k].cpu().double()
+        assert ((a - b).norm() / b.norm().clamp_min(1e-30)).item() < 3e-4, (iters, k)
+    d = (got["dx"].float() - old["dx"].cpu().float()).abs().max().item()
+    assert d <= 2 * 2.0 ** -7 * old["dx"].float().abs().max().item(), (iters, d)
+
+
+def test_fused_backward_limits_and_determinism():
+    import hvs_b200
+    from hvs_b200._lib import HvsError
+    inp = make_inputs(3000, seed=33, alpha=0.2)
+    dy = torch.randn(3000, 4, 512, generator=torch.Generator().manual_seed(6)).to(torch.bfloat16)
+    a = run_bwd_saved(*inp[:1], dy, *inp[1:])
+    b = run_bwd_saved(*inp[:1], dy, *inp[1:])
+    for k in ("dx", "dphi", "dbias", "dalpha", "dscale"):
+        va = a[k].view(torch.int16) if a[k].dtype == torch.bfloat16 else a[k]
+        vb = b[k].view(torch.int16) if b[k].dtype == torch.bfloat16 else b[k]
+        assert torch.equal(va, vb), k
+    x = inp[0].cuda()
+    P = [p.cuda() for p in inp[1:]]
+    saved = hvs_b200.ops.new_saved(x)
+    with pytest.raises(HvsError):      # more iterations than the shared-memory history holds: caller must use mhc_stream_bwd
+        hvs_b200.ops.mhc_stream_bwd_saved(x, dy.cuda(), saved, *P, sk_iters=25)
+    # T = 0 is a no-op that still writes zero parameter gradients
+    e = hvs_b200.ops.mhc_stream_bwd_saved(x[:0], dy.cuda()[:0], saved[:0], *P)
+    assert e["dx"].numel() == 0 and float(e["dphi"].abs().max()) == 0.0 and float(e["dbias"].abs().max()) == 0.0
+
+
+def test_fused_backward_full_size_properties():
+    """2^18 tokens: parameter gradients are linear in dy; dx of zero dy is exactly zero."""
+    import hvs_b200
+    t = 1 << 18
+    g = torch.Generator(device="cuda:0").manual_seed(11)
+    x = torch.randn(t, 4, 512, generator=g, device="cuda:0", dtype=torch.bfloat16)
+    dy = torch.randn(t, 4, 512, generator=g, device="cuda:0", dtype=torch.bfloat16)
+    _, phi, bias, al, scale = make_inputs(1)
+    P = [p.cuda() for p in (phi, bias, al, scale)]
+    saved = hvs_b200.ops.new_saved(x)
+    hvs_b200.ops.mhc_stream_fwd(x, *P, saved=saved)
+    a = hvs_b200.ops.mhc_stream_bwd_saved(x, dy, saved, *P)
+    c = hvs_b200.ops.mhc_stream_bwd_saved(x, (dy.float() * 2).to(torch.bfloat16), saved, *P)
+    for k in ("dphi", "dbias", "dalpha", "dscale"):
+        assert torch.allclose(c[k], 2 * a[k], rtol=2e-4, atol=1e-6 * a[k].abs().max().item()), k
+    z = hvs_b200.ops.mhc_stream_bwd_saved(x, torch.zeros_like(dy), saved, *P)
+    assert float(z["dx"].float().abs().max()) == 0.0 and float(z["dphi"].abs().max()) == 0.0
+    # spot-check against the two-kernel backward
+    old = hvs_b200.ops.mhc_stream_bwd(x, dy, *P)
+    assert ((a["dphi"] - old["dphi"]).norm() / old["dphi"].norm()).item() < 1e-4
+    assert (a["dx"].float() - old["dx"].float()).abs().max().item() <= 2.0 ** -6 * old["dx"].float().abs().max().item()

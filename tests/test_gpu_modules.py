@@ -55,8 +55,9 @@ def test_host_buffer_entry_matches_device_path():
     dxh = torch.empty_like(xh).pin_memory()
     g = hvs_b200.stream_mhc_fwd_bwd_host(xh, dyh, layer, yh, dxh, chunk_tokens=2048)
     p = (layer.phi.detach(), layer.bias.detach(), layer.alpha.detach(), layer.rms_scale.detach())
-    y, _, _ = hvs_b200.ops.mhc_stream_fwd(xh.cuda(), *p)
-    gd = hvs_b200.ops.mhc_stream_bwd(xh.cuda(), dyh.cuda(), *p)
+    saved = hvs_b200.ops.new_saved(xh.cuda())
+    y, _, _ = hvs_b200.ops.mhc_stream_fwd(xh.cuda(), *p, saved=saved)
+    gd = hvs_b200.ops.mhc_stream_bwd_saved(xh.cuda(), dyh.cuda(), saved, *p)     # the training path the pipeline uses
     assert torch.equal(yh.view(torch.int16), y.cpu().view(torch.int16))
     assert torch.equal(dxh.view(torch.int16), gd["dx"].cpu().view(torch.int16))
     assert torch.allclose(g["dphi"], gd["dphi"].cpu(), rtol=1e-3, atol=1e-5 * gd["dphi"].abs().max().item())
