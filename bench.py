@@ -14,8 +14,10 @@ parameter gradients are all-reduced over NCCL after the backward.  Rank 0 prints
 value        tokens/s (whole job) with x, dy resident in HBM, CUDA-event timed, max over ranks
 e2e          the same metric through the host-buffer entry (stream_mhc_fwd_bwd_host): pinned host x, dy
              -> H2D -> kernels -> D2H of y, dx and the parameter gradients, all inside the timed region
-roofline     dominant kernel (backward per-token kernel): algorithmic 12288 B/token over its own
-             CUDA-event duration (hvs_mhc_stream_profile hooks), against MEASURED_PEAKS.json
+roofline     dominant kernel (the fused single-pass backward, dx + every parameter gradient): algorithmic
+             12288 B/token over its own CUDA-event duration (hvs_mhc_stream_profile hooks), against
+             MEASURED_PEAKS.json.  The training forward also writes, and the backward reads, 112 B/token of
+             saved statistics (1.1 % on top of the 20480 B/token; not counted in the algorithmic figure)
 cpu_baseline oracle/ (a port of the reference's PyTorch arithmetic) timed on the host cores, rank 0,
              N = 1 only, bounded sample of the same workload
 --impl reference   times that CPU implementation alone (the reference is pure PyTorch; its own modules
@@ -190,11 +192,14 @@ def main():
     alpha = torch.full((3,), 0.01, device=dev)
     scale = torch.ones(N_STREAMS * CHANNELS, device=dev)
     y = torch.empty_like(x)
+    dx = torch.empty_like(x)
+    saved = hvs_b200.ops.new_saved(x)
     lib = hvs_b200.load_library()
+    ws = torch.empty(int(lib.hvs_mhc_stream_bwd_saved_workspace(T, N_STREAMS, CHANNELS)), dtype=torch.uint8, device=dev)
 
-    def step():
-        hvs_b200.ops.mhc_stream_fwd(x, phi, bias, alpha, scale, out=y)
-        grads = hvs_b200.ops.mhc_stream_bwd(x, dy, phi, bias, alpha, scale)
+    def step():                                                          # the training path of hvs_b200.StreamMHC
+        hvs_b200.ops.mhc_stream_fwd(x, phi, bias, alpha, scale, out=y, saved=saved)
+        grads = hvs_b200.ops.mhc_stream_bwd_saved(x, dy, saved, phi, bias, alpha, scale, out=dx, workspace=ws)
         if world > 1:                                                    # DDP-style parameter-gradient exchange
             flat = torch.cat([grads[k].reshape(-1) for k in ("dphi", "dbias", "dalpha", "dscale")])
             dist.all_reduce(flat)
@@ -240,7 +245,7 @@ def main():
     layer = hvs_b200.StreamMHC(device=dev)
     with torch.no_grad():
         layer.phi.copy_(phi); layer.bias.copy_(bias); layer.alpha.copy_(alpha); layer.rms_scale.copy_(scale)
-    del y
+    del y, dx, ws
     torch.cuda.empty_cache()
     xh = x.cpu().pin_memory(); dyh = dy.cpu().pin_memory()
     yh = torch.empty_like(xh).pin_memory(); dxh = torch.empty_like(xh).pin_memory()
@@ -264,7 +269,6 @@ def main():
         peak, peak_src = load_peaks()
         fwd_ms = sum(k[0] for k in kms) / len(kms)
         bwd_ms = sum(k[1] for k in kms) / len(kms)
-        dw_ms = sum(k[2] for k in kms) / len(kms)
         fin_ms = sum(k[3] for k in kms) / len(kms)
         achieved = BWD_BYTES * T / (bwd_ms * 1e-3) / 1e9
         traffic = load_traffic()
@@ -275,17 +279,18 @@ def main():
             "config": {"workload": "mHC layer microbenchmark n=4 C=512 bf16 fwd+bwd, 20 Sinkhorn iters (BASELINE configs[1])",
                        "tokens_per_gpu": T, "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "inputs (4.3 GB each) are larger than L2; no flush needed",
-                       "params": "phi~N(0,0.02^2), bias=0, alpha=0.01, rms_scale=1"},
+                       "params": "phi~N(0,0.02^2), bias=0, alpha=0.01, rms_scale=1",
+                       "path": "training path: forward saves 112 B/token of statistics, backward = one fused kernel (dx + all parameter gradients) + a 2048-row finalize"},
             "hbm_gbs": {"fwd_bwd_algorithmic": (FWD_BYTES + BWD_BYTES) * T * world / (step_ms * 1e-3) / 1e9,
                         "frac_of_peak": (FWD_BYTES + BWD_BYTES) * T / (step_ms * 1e-3) / 1e9 / peak, "peak": peak,
                         "peak_source": peak_src, "frac_of_nominal_8000": (FWD_BYTES + BWD_BYTES) * T / (step_ms * 1e-3) / 1e9 / 8000.0},
-            "kernels_ms": {"mhc_stream_fwd_kernel": fwd_ms, "mhc_stream_bwd_kernel": bwd_ms, "mhc_stream_dw_kernel": dw_ms,
+            "kernels_ms": {"mhc_stream_fwd_kernel": fwd_ms, "mhc_stream_bwd_fused_kernel": bwd_ms,
                            "mhc_stream_bwd_finalize_kernel": fin_ms,
                            "fwd_GBs": FWD_BYTES * T / (fwd_ms * 1e-3) / 1e9, "fwd_frac": FWD_BYTES * T / (fwd_ms * 1e-3) / 1e9 / peak},
-            "roofline": {"kernel": "mhc_stream_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "mhc_stream_bwd_fused_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback (B200_PROFILING.md)",
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (traffic or {}).get("mhc_stream_bwd_kernel_bytes_per_launch"),
+                         "traffic": (traffic or {}).get("mhc_stream_bwd_fused_kernel_bytes_per_launch"),
                          "traffic_note": (traffic or {}).get("note")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * T * row_bytes,
                     "d2h_bytes_per_step": 2 * T * row_bytes + grad_bytes, "ms_per_step": e2e_dt * 1e3,
