@@ -257,7 +257,7 @@ def main():
         gh = hvs_b200.stream_mhc_fwd_bwd_host(xh, dyh, layer, yh, dxh)
         torch.cuda.synchronize()
         e2e_ts.append(time.perf_counter() - t0)
-    e2e_dt = sum(e2e_ts) / len(e2e_ts)
+    e2e_dt = sum(e2e_ts) / len(e2e_ts) if e2e_ts else float('nan')
     te = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

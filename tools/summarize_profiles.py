@@ -74,22 +74,28 @@ if __name__ == "__main__":
             "r1_bwd_v1.ncu-rep": ("r01_bwd_v1_smem_resident.txt", "backward v1: tiles resident in shared memory, 1 coefficient warp (T=262144)"),
             "r1_bwd_v3.ncu-rep": ("r01_bwd_v3_two_pass_l2.txt", "backward v3: two passes per tile, second re-loaded through L2 (T=262144)"),
             "r1_bwd_v5.ncu-rep": ("r01_bwd_v5_tmem.txt", "backward v5 (shipped): tiles parked in tensor memory, 3 coefficient warps (T=262144)"),
-            "r1_bench_kernels.ncu-rep": ("r01_bench_kernels_T1M.txt", "bench.py kernels at the benchmark size T=2^20 (one launch each)")}
+            "r1_bench_kernels.ncu-rep": ("r01_bench_kernels_T1M.txt", "two-kernel backward era: bench.py kernels at the benchmark size T=2^20 (one launch each)"),
+            "r1_fused_v1.ncu-rep": ("r01_fused_v1_front_thread_bound.txt", "fused backward v1: 64 small tcgen05.mma per tile issued by one divergent thread, 4-lane coefficient chain (T=262144)"),
+            "r1_fused_v5.ncu-rep": ("r01_fused_v5_bank_conflicts.txt", "fused backward v5: G on the warp MMA path with 4-way conflicting ldmatrix rows + unpadded M-pair rows (T=262144)"),
+            "r1_fused_v6.ncu-rep": ("r01_fused_v6.txt", "fused backward v6: conflicts fixed, scaling-form reverse sweep, early forward (T=262144)"),
+            "r1b_bench_kernels.ncu-rep": ("r01b_bench_kernels_T1M.txt", "SHIPPED training path: forward (saving statistics) + fused single-pass backward + finalize at T=2^20")}
     traffic = {}
     for rep, (out, note) in reps.items():
         path = os.path.join(g, rep)
         if not os.path.exists(path):
             continue
         res = summarize(path, out, note)
-        if rep == "r1_bench_kernels.ncu-rep":
+        if rep == "r1b_bench_kernels.ncu-rep":
             for short, d in res:
                 def gb(k):
                     v, u = d[k]
                     return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
                 traffic[short + "_bytes_per_launch"] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
     if traffic:
-        traffic["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, T=2^20 (profiles/r01_bench_kernels_T1M.txt)"
+        traffic["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, T=2^20 (profiles/r01b_bench_kernels_T1M.txt)"
         json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
     if os.path.exists(os.path.join(g, "r1_launches.csv")):
         launch_list(os.path.join(g, "r1_launches.csv"), "r01_launch_list.txt")
+    if os.path.exists(os.path.join(g, "r1b_launches.csv")):
+        launch_list(os.path.join(g, "r1b_launches.csv"), "r01b_launch_list.txt")
     print(open(os.path.join(OUT, "traffic.json")).read() if traffic else "no traffic")
