@@ -51,7 +51,9 @@ def is_fresh() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into one shared library.  Returns its path."""
+    """Compile every .cu under csrc/ into one shared library.  Returns its path.
+    HVS_FUSED_TRACE=1 in the environment adds the cycle-counter instrumentation of the fused backward
+    (development aid, tools/time_fused.py)."""
     if not force and is_fresh():
         return LIB_PATH
     nvcc = _nvcc()
@@ -66,6 +68,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(obj)
         cmd = [nvcc, *NVCC_FLAGS, "-c", spath, "-o", obj]
+        if os.environ.get("HVS_FUSED_TRACE"):
+            cmd.insert(1, "-DHVS_FUSED_TRACE")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

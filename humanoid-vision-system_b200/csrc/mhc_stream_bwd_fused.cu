@@ -1,22 +1,22 @@
 // K1 backward for training, ONE fused kernel: dx and the parameter gradients in a single pass over x and dy
 // (every byte crosses HBM once).  The forward saved the un-normalised projection and the sum of squares per
-// token (hvs_mhc_stream_fwd_save, 112 B/token), so nothing here needs the projection operand in its forward
-// layout; the two dense contractions that remain go to the tcgen05 tensor cores with accumulators in tensor
-// memory, straight from the TMA-landed token tile:
+// token (hvs_mhc_stream_fwd_save, 112 B/token).  The two dense contractions go to the tcgen05 tensor cores with
+// accumulators in tensor memory, operands straight from the TMA-landed token tile:
 //   G = dy x^T (per-token 4x4)   tcgen05.mma  D[64x32] += [x rows ; dy rows] (64 x 16) * (x rows)^T, K-major operands
-//                                 (the 4x4 blocks are the token-diagonal of the dy half of D)
+//                                 (the 4x4 blocks are the token diagonal of the dy half of D)
 //   dW = x^T E (2048 x 24)       tcgen05.mma  D[64x24] += x-atom^T (MN-major A, read in place) * [E_hi ; E_lo]
 //                                 the two bf16 terms of E ride the two halves of K = 16 against the SAME eight
 //                                 token rows of x (stride-0 K step), accumulated over the whole kernel in 384
 //                                 tensor-memory columns (32 blocks of 64 channels, two per column range)
-// Roles (640 threads, one CTA per SM, 3 stages of 8 tokens: x | dy = 64 KB each):
-//   front thread        TMA loads (3-D boxes -> [stream][token][64 ch] swizzle atoms, + the saved records),
-//                       issues every tcgen05.mma in dependency order, TMA-stores dx, recycles stages
-//   8 worker warps      read the G blocks out of tensor memory into the tile's record
-//   3 coefficient warps (one per stage, 4 lanes per token) gates + Sinkhorn forward in packed fp32x2 registers,
-//                       exact reverse sweep, e = d raw, kappa, M; write E as bf16 hi/lo in MMA operand layout
-//   16 worker warps     dx = M^T dy + kappa x + W e   (W e on the warp MMA path with scale*phi resident in 48
-//                       registers; mixing in packed fp32x2 FMAs), written IN PLACE over dy, one rounding to bf16
+// Roles (640 threads, one CTA per SM, 3 stages of 8 tokens: x | dy = 64 KB each, one 4-D TMA box per tensor):
+//   front warp          (convergent; lane 0 issues) TMA loads, every tcgen05.mma in dependency order, TMA stores of
+//                       dx, stage recycling
+//   3 coefficient warps (one per stage, lane = token) forward Sinkhorn AHEAD of the tile from the saved record
+//                       (fetched by the warp itself), tracking the cumulative scalings; once G is there: gate
+//                       gradients, reverse sweep in the scaling form (no reciprocals), softmax / RMSNorm backward
+//   16 worker warps     G blocks out of tensor memory; e = d raw as bf16 hi/lo into the E operand tile, dbias;
+//                       dx = M^T dy + kappa x + W e   (W e on the warp MMA path, scale*phi resident in 48 registers
+//                       in A-fragment order; mixing in packed fp32x2 FMAs), written IN PLACE over dy, one rounding
 // Oracle: autograd through oracle/mhc_ref.py::stream_mhc_forward (reference primitives
 // src/models/manifold_layers.py:56-77, :213-216, :449-456).
 #include "common.cuh"
