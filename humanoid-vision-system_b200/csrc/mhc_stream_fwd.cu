@@ -57,6 +57,12 @@ struct FwdParams {
     int has_y;
 };
 
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 __device__ __forceinline__ float sum_sq8(uint4 v) {
     float s = 0.f, a;
     a = bf16lo(v.x); s = fmaf(a, a, s); a = bf16hi(v.x); s = fmaf(a, a, s);
@@ -229,16 +235,15 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                         uint32_t y0[4], y1[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float l0 = bf16lo(xr[0][e]), h0 = bf16hi(xr[0][e]);
-                            const float l1 = bf16lo(xr[1][e]), h1 = bf16hi(xr[1][e]);
-                            const float l2 = bf16lo(xr[2][e]), h2 = bf16hi(xr[2][e]);
-                            const float l3 = bf16lo(xr[3][e]), h3 = bf16hi(xr[3][e]);
-                            const float a0 = fmaf(m0.w, l3, fmaf(m0.z, l2, fmaf(m0.y, l1, m0.x * l0)));
-                            const float b0 = fmaf(m0.w, h3, fmaf(m0.z, h2, fmaf(m0.y, h1, m0.x * h0)));
-                            const float a1 = fmaf(m1.w, l3, fmaf(m1.z, l2, fmaf(m1.y, l1, m1.x * l0)));
-                            const float b1 = fmaf(m1.w, h3, fmaf(m1.z, h2, fmaf(m1.y, h1, m1.x * h0)));
-                            y0[e] = pack_bf16(a0, b0);
-                            y1[e] = pack_bf16(a1, b1);
+                            // the (lo, hi) channel pair of a bf16x2 word rides one packed fp32x2 FMA per stream
+                            const u64 x0 = pk2(bf16lo(xr[0][e]), bf16hi(xr[0][e])), x1 = pk2(bf16lo(xr[1][e]), bf16hi(xr[1][e]));
+                            const u64 x2 = pk2(bf16lo(xr[2][e]), bf16hi(xr[2][e])), x3 = pk2(bf16lo(xr[3][e]), bf16hi(xr[3][e]));
+                            const u64 a = fma2(x3, pk2(m0.w, m0.w), fma2(x2, pk2(m0.z, m0.z), fma2(x1, pk2(m0.y, m0.y), mul2(x0, pk2(m0.x, m0.x)))));
+                            const u64 b = fma2(x3, pk2(m1.w, m1.w), fma2(x2, pk2(m1.z, m1.z), fma2(x1, pk2(m1.y, m1.y), mul2(x0, pk2(m1.x, m1.x)))));
+                            float al, ah, bl, bh;
+                            upk2(a, al, ah); upk2(b, bl, bh);
+                            y0[e] = pack_bf16(al, ah);
+                            y1[e] = pack_bf16(bl, bh);
                         }
                         sts128(sbase + off[ip] + half * 4096, make_uint4(y0[0], y0[1], y0[2], y0[3]));
                         sts128(sbase + off[ip + 1] + half * 4096, make_uint4(y1[0], y1[1], y1[2], y1[3]));
