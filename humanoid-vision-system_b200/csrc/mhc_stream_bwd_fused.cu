@@ -584,10 +584,9 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         // this thread's 8 bytes (channels 32w + 4g .. +3) of (token 2t, stream jj); token 2t+1 is the next row with
         // the swizzle bit flipped
         const int cb = w >> 1, hh = w & 1;
-        uint32_t offa[kN];
-#pragma unroll
-        for (int jj = 0; jj < kN; ++jj)
-            offa[jj] = (jj * 8 + cb) * 1024 + (2 * t) * 128 + (((4 * hh + (g >> 1)) ^ (2 * t)) << 4) + (g & 1) * 8;
+        // (stream jj adds the constant 8 KB * jj: an immediate in the load / store)
+        const uint32_t offa0 = cb * 1024 + (2 * t) * 128 + (((4 * hh + (g >> 1)) ^ (2 * t)) << 4) + (g & 1) * 8;
+        const uint32_t offb0 = (offa0 + 128) ^ 16;
         const uint32_t stage0 = smem_u32(smem);
         float acc_db = 0.f;                               // dbias of logit tid % 24 over tokens tid / 24 (threads < 192)
         const int q = w & 3, jcol = w >> 2;               // tensor-memory lane quadrant / G column group of this warp
@@ -622,19 +621,19 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         while (d_next < n_local) {
             if (threadIdx.x == 0) {
                 int act = 0;
-                while (act == 0) {
-                    if (g_next < n_local && mbar_test_wait(&bar_gs[g_next % kStages], (uint32_t)(g_next / kStages) & 1u)) act = 1;
-                    else if (mbar_test_wait(&bar_cd[d_next % kStages], (uint32_t)(d_next / kStages) & 1u)) act = 2;
+                while (act == 0) {                                       // bit 0: a tile's G is ready, bit 1: a tile's coefficients are
+                    if (g_next < n_local && mbar_test_wait(&bar_gs[g_next % kStages], (uint32_t)(g_next / kStages) & 1u)) act |= 1;
+                    if (mbar_test_wait(&bar_cd[d_next % kStages], (uint32_t)(d_next / kStages) & 1u)) act |= 2;
                 }
                 *next_action = act;
             }
             bar_sync(kBarW, kWorkerThreads);
             const int act = *next_action;
-            if (act == 1) {
+            if (act & 1) {
                 g_tile(g_next);
                 ++g_next;
-                continue;
             }
+            if (!(act & 2)) continue;
             {
                 // ============ dx for tokens 2t, 2t+1 of tile k, channels 32w + 4g .. +3 of every stream
                 const int k = d_next++;
@@ -670,16 +669,16 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 {
 #pragma unroll
                 for (int ii = 0; ii < kN; ++ii) {
-                    dya[ii] = lds64(sb + kHalf + offa[ii]);
-                    dyb[ii] = lds64(sb + kHalf + ((offa[ii] + 128) ^ 16));
+                    dya[ii] = lds64(sb + kHalf + offa0 + ii * 8192);
+                    dyb[ii] = lds64(sb + kHalf + offb0 + ii * 8192);
                 }
 #pragma unroll
                 for (int jj = 0; jj < kN; ++jj) {
                     const float4* mq = reinterpret_cast<const float4*>(wrec + kWrecM + t * (kMpStride * 4)) + jj * 2;
                     const float4 m01 = mq[0], m23 = mq[1];                        // (M_a[0],M_b[0],M_a[1],M_b[1]) (M_a[2],...)
                     const u64 mp[kN] = {pk2(m01.x, m01.y), pk2(m01.z, m01.w), pk2(m23.x, m23.y), pk2(m23.z, m23.w)};
-                    const uint2 xa = lds64(sb + offa[jj]);
-                    const uint2 xb = lds64(sb + ((offa[jj] + 128) ^ 16));
+                    const uint2 xa = lds64(sb + offa0 + jj * 8192);
+                    const uint2 xb = lds64(sb + offb0 + jj * 8192);
                     uint32_t oa[2], ob[2];
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
@@ -703,8 +702,8 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                         oa[mt] = pack_bf16(c[0], c[2]);
                         ob[mt] = pack_bf16(c[1], c[3]);
                     }
-                    sts64(sb + kHalf + offa[jj], oa[0], oa[1]);
-                    sts64(sb + kHalf + ((offa[jj] + 128) ^ 16), ob[0], ob[1]);
+                    sts64(sb + kHalf + offa0 + jj * 8192, oa[0], oa[1]);
+                    sts64(sb + kHalf + offb0 + jj * 8192, ob[0], ob[1]);
                 }
                 }
                 fence_proxy_async_smem();
