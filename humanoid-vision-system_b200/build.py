@@ -37,7 +37,7 @@ def _fingerprint() -> str:
     files.append(os.path.abspath(__file__))
     for f in files:
         if os.path.isfile(f):
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())     # content + name, not the checkout path: the stamp travels with the tree
             with open(f, "rb") as fh:
                 h.update(fh.read())
     return h.hexdigest()
@@ -59,6 +59,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     obj_dir = os.path.join(PKG_DIR, "build")
     os.makedirs(obj_dir, exist_ok=True)
+    # one builder at a time (several ranks may import the package at once); the others find a fresh library
+    import fcntl
+    lock = open(os.path.join(obj_dir, ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and is_fresh():
+            return LIB_PATH
+        return _build_locked(nvcc, obj_dir, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc: str, obj_dir: str, verbose: bool) -> str:
     procs = []
     objs = []
     for src in SOURCES:
@@ -83,10 +97,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out)
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    link = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, LIB_PATH)                          # atomic: a concurrent loader sees the old or the new library, never half of one
     with open(STAMP, "w") as f:
         f.write(_fingerprint())
     return LIB_PATH
