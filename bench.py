@@ -176,9 +176,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries ONE JSON line: everything libraries print (NCCL's version banner, ...) goes to stderr
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     T = args.tokens
@@ -301,7 +302,8 @@ def main():
             tps, dt, threads = cpu_reference_run(8192, 2, 1)
             line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "8192 tokens fwd+bwd, oracle/mhc_ref.py (torch fp32 CPU), mean of 2 steps after 1 warm-up"}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
