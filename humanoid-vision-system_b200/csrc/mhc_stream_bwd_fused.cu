@@ -80,7 +80,6 @@ struct FusedParams {
     float* dw_part;        // [grid, 2048, 24]
     float* cta_accum;      // [grid, 3, 27]
     long long* dbg;        // optional [grid, 4, 8] cycle counters: coefficient warps 0..2, front thread (development aid)
-    int dbg_mode;          // development aid: 1 = workers skip the dx math (timing experiments only)
     int64_t T;
     int num_tiles;
     int sk_iters;
@@ -754,7 +753,6 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
 }
 
 long long* g_fused_dbg = nullptr;
-int g_fused_dbg_mode = 0;
 
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
@@ -778,7 +776,7 @@ FusedWs carve(void* base, int ctas) {
 // development aid: device buffer [SMs, 3, 8] int64 receiving the coefficient warps' cycle counters (NULL = off)
 extern "C" int hvs_debug_fused_timing(void* device_buffer, int mode) {
     hvs::g_fused_dbg = reinterpret_cast<long long*>(device_buffer);
-    hvs::g_fused_dbg_mode = mode;
+    (void)mode;
     return HVS_OK;
 }
 
@@ -826,7 +824,6 @@ extern "C" int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const flo
         p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale; p.saved = saved;
         p.dw_part = ws.dw_part; p.cta_accum = ws.cta_accum;
         p.dbg = g_fused_dbg;
-        p.dbg_mode = g_fused_dbg_mode;
         p.T = T;
         p.num_tiles = (int)((T + kTok - 1) / kTok);
         p.sk_iters = sk_iters; p.eps_rms = eps_rms; p.eps_sk = eps_sk;
