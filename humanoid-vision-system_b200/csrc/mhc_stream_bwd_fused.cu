@@ -59,7 +59,7 @@ constexpr int kDlBytes = 768;
 constexpr int kOffPart = kOffDl + kStages * kDlBytes;             // end-of-kernel dbias fold: [8 tokens][24] fp32
 constexpr int kOffBias = kOffPart + kTok * kL * 4;                // bias[24] staged once (float4 broadcast reads)
 constexpr int kOffBar = kOffBias + 128;
-constexpr int kOffTmem = kOffBar + 7 * kStages * 8;
+constexpr int kOffTmem = kOffBar + 8 * kStages * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0 && kOffInit % 16 == 0 && kOffSk % 16 == 0 && kOffDl % 16 == 0, "alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -67,7 +67,9 @@ static_assert(kSmemBytes <= 232448, "shared memory budget");
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColDw = 0;                        // dW: 32 blocks (stream j, 64-channel block cb) of M = 64, b = 8j + cb; blocks 2p / 2p+1
                                                       //     share columns [24p, 24p+24) at lane offsets 0 / 16
-constexpr uint32_t kColGs = 384;                      // [x ; dy] x^T of a tile: 32 columns per stage
+constexpr uint32_t kColGs = 384;                      // [x ; dy] x^T of a tile: 32 columns, two buffers (tile parity)
+constexpr uint32_t kColW = 448;                       // 64 columns = 16 registers per worker thread: the K = 8 step of its W
+                                                      //     fragments lives here instead of spilling (no L1 to speak of)
 
 constexpr int kBarRec = 1 /*,2,3*/, kBarCoef = 4 /*,5,6*/, kBarW = 7;
 
@@ -132,6 +134,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     uint64_t* bar_sv = bar_dw + kStages;                                  // saved records of the stage's next tile landed
     uint64_t* bar_cd = bar_sv + kStages;                                  // coefficients of the tile written (coefficient warp)
     uint64_t* bar_gs = bar_cd + kStages;                                  // G MMAs of the tile complete
+    uint64_t* bar_gr = bar_gs + kStages;                                  // [2] G buffer read out by the 8 read-out warps
     volatile int* next_action = reinterpret_cast<volatile int*>(smem + kOffTmem + 8);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
@@ -148,6 +151,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             mbar_init(&bar_sv[s], 1);
             mbar_init(&bar_cd[s], 32);
             mbar_init(&bar_gs[s], 1);
+            if (s < 2) mbar_init(&bar_gr[s], 8);
         }
         fence_mbar_init();
     }
@@ -243,6 +247,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 // (stream atoms of one 64-channel block) sit 8 KB apart, x then dy
                 mbar_wait(&bar_full[s], (uint32_t)(it / kStages) & 1u);
                 HVS_FTICK(0);
+                if (it >= 2) mbar_wait(&bar_gr[it & 1], (uint32_t)((it >> 1) - 1) & 1u);   // buffer read out (tile it - 2)
                 tc_fence_after();
                 const uint64_t gdesc0 = umma_smem_desc(s0 + s * kStageBytes, 16, 8192, kUmmaLayoutSw128);
 #pragma unroll
@@ -250,7 +255,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t d64 = gdesc0 + (uint64_t)(cb * 64 + ks * 2);      // +1 KB per block, +32 B per K step
-                        if (leader) umma_bf16_ss(tmem_base + kColGs + 32u * s, d64, d64, id_gs, (uint32_t)((cb | ks) != 0));
+                        if (leader) umma_bf16_ss(tmem_base + kColGs + 32u * (it & 1), d64, d64, id_gs, (uint32_t)((cb | ks) != 0));
                     }
                 if (leader) umma_commit(&bar_gs[s]);
                 HVS_FTICK(1);
@@ -564,7 +569,8 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         const int w = warp, g = lane >> 2, t = lane & 3;
         // W = bf16(scale * phi) as the A operand of  dx_proj^T = W e^T : m-tile (jj, mt) rows g / g+8 are the
         // channel pair 32w + 4g + 2mt + {0,1} of stream jj, k = logits.  48 registers, resident for the whole kernel.
-        uint32_t wf[kN][2][6];
+        uint32_t wf[kN][2][4];
+        uint32_t wk[16];
 #pragma unroll
         for (int jj = 0; jj < kN; ++jj)
 #pragma unroll
@@ -577,9 +583,14 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 wf[jj][mt][1] = pack_bf16(__ldg(rb + 2 * t) * sb, __ldg(rb + 2 * t + 1) * sb);
                 wf[jj][mt][2] = pack_bf16(__ldg(ra + 2 * t + 8) * sa, __ldg(ra + 2 * t + 9) * sa);
                 wf[jj][mt][3] = pack_bf16(__ldg(rb + 2 * t + 8) * sb, __ldg(rb + 2 * t + 9) * sb);
-                wf[jj][mt][4] = pack_bf16(__ldg(ra + 2 * t + 16) * sa, __ldg(ra + 2 * t + 17) * sa);
-                wf[jj][mt][5] = pack_bf16(__ldg(rb + 2 * t + 16) * sb, __ldg(rb + 2 * t + 17) * sb);
+                wk[(jj * 2 + mt) * 2] = pack_bf16(__ldg(ra + 2 * t + 16) * sa, __ldg(ra + 2 * t + 17) * sa);
+                wk[(jj * 2 + mt) * 2 + 1] = pack_bf16(__ldg(rb + 2 * t + 16) * sb, __ldg(rb + 2 * t + 17) * sb);
             }
+        // the K = 8 step (logits 16..23) of the fragments is parked in tensor memory: 4 registers per stream are
+        // fetched when needed (tcgen05.ld), 32 registers stay resident
+        const uint32_t tm_w = tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + kColW + 16u * (uint32_t)(w >> 2);
+        tmem_st16(tm_w, wk);
+        tmem_wait_st();
         // this thread's 8 bytes (channels 32w + 4g .. +3) of (token 2t, stream jj); token 2t+1 is the next row with
         // the swizzle bit flipped
         const int cb = w >> 1, hh = w & 1;
@@ -599,8 +610,11 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 mbar_wait(&bar_gs[s], (uint32_t)(tile / kStages) & 1u);
                 tc_fence_after();
                 uint32_t v[8];
-                tmem_ld8(tm_gs + 32u * s, v);
+                tmem_ld8(tm_gs + 32u * (tile & 1), v);
                 tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_gr[tile & 1]);
                 const int tok = lane & 7;
                 uint32_t val = v[0];
 #pragma unroll
@@ -676,6 +690,8 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     const float4* mq = reinterpret_cast<const float4*>(wrec + kWrecM + t * (kMpStride * 4)) + jj * 2;
                     const float4 m01 = mq[0], m23 = mq[1];                        // (M_a[0],M_b[0],M_a[1],M_b[1]) (M_a[2],...)
                     const u64 mp[kN] = {pk2(m01.x, m01.y), pk2(m01.z, m01.w), pk2(m23.x, m23.y), pk2(m23.z, m23.w)};
+                    uint32_t w8[4];
+                    tmem_ld4(tm_w + 4u * jj, w8);
                     const uint2 xa = lds64(sb + offa0 + jj * 8192);
                     const uint2 xb = lds64(sb + offb0 + jj * 8192);
                     uint32_t oa[2], ob[2];
@@ -688,7 +704,8 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                         upk2(c01i, c[0], c[1]);
                         upk2(c23i, c[2], c[3]);
                         mma_bf16_16816(c, wf[jj][mt][0], wf[jj][mt][1], wf[jj][mt][2], wf[jj][mt][3], eb0, eb1);
-                        mma_bf16_1688(c, wf[jj][mt][4], wf[jj][mt][5], eb2);
+                        if (mt == 0) tmem_wait_ld();
+                        mma_bf16_1688(c, w8[2 * mt], w8[2 * mt + 1], eb2);
                         u64 c01 = pk2(c[0], c[1]), c23 = pk2(c[2], c[3]);
 #pragma unroll
                         for (int ii = 0; ii < kN; ++ii) {
