@@ -48,8 +48,9 @@ constexpr int kOffSaved = kStages * kStageBytes;
 constexpr int kOffWrec = kOffSaved + kStages * kSavedBytes;       // per stage: e bf16 pairs [8][12] | M pairs [4][4][4][2] | kappa [8]
                                                                   //            | alpha_g * inv_rms [8][3] | d logits [8][24]
 constexpr int kWrecBytes = 1152, kWrecM = 384, kWrecK = 960, kWrecS = 992, kMpStride = 36;   // M pairs: 4 token pairs x (32 + 4 pad) floats   // G [8][16] fp32 overlays bytes [0, 512) until M is written
-constexpr int kOffEt = kOffWrec + kStages * kWrecBytes;           // per stage: E tile, 32 rows (24 logits + 8 zero) x 16 K bf16, no swizzle
-constexpr int kEtBytes = 1024;
+constexpr int kOffEt = kOffWrec + kStages * kWrecBytes;           // per stage: E tile, no swizzle: two K chunks (bf16 hi | lo of e over the 8 tokens) of
+                                                                  // 5 row groups (8 rows x 16 B): zero | logits 0-7 | 8-15 | 16-23 | zero
+constexpr int kEtBytes = 1280, kEtChunk = 640, kEtRow0 = 128;
 constexpr int kOffInit = kOffEt + kStages * kEtBytes;             // per stage: Sinkhorn start P0 [8][16] | H_pre, H_post [8][8] | inv_rms [8];
 constexpr int kInitBytes = 800, kInitH = 512, kInitR = 768;
 constexpr int kSkWords = kTok * kMaxIters * 8;
@@ -65,9 +66,8 @@ static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffWrec % 16 == 0 && k
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColDw = 0;                        // dW: 32 blocks (stream j, 64-channel block cb) of M = 64, b = 8j + cb; blocks 2p / 2p+1
-                                                      //     share columns [24p, 24p+24) at lane offsets 0 / 16
-constexpr uint32_t kColGs = 384;                      // [x ; dy] x^T of a tile: 32 columns, two buffers (tile parity)
+constexpr uint32_t kColDw = 0;                        // dW: 16 blocks of 128 channels (lane = channel in the block), block p in columns [24p, 24p+24)
+constexpr uint32_t kColGs = 384;                      // dy x^T of a tile in two channel halves: 64 columns
 constexpr uint32_t kColW = 448;                       // 64 columns = 16 registers per worker thread: the K = 8 step of its W
                                                       //     fragments lives here instead of spilling (no L1 to speak of)
 
@@ -98,7 +98,25 @@ struct FusedParams {
 #define HVS_TRACE_ON 0
 #endif
 
+#ifndef HVS_WAIT_NS
+#define HVS_WAIT_NS 1000
+#endif
+#ifndef HVS_POLL_NS
+#define HVS_POLL_NS 100
+#endif
+__device__ __forceinline__ void mbar_wait_q(uint64_t* bar, uint32_t parity) {          // quiet wait (see mbar_try_wait_ns)
+#if HVS_WAIT_NS > 0
+    mbar_wait_ns(bar, parity, HVS_WAIT_NS);
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 typedef unsigned long long u64;
+__device__ __forceinline__ uint32_t sel32(uint32_t a, uint32_t b, uint32_t c) {       // c != 0 ? a : b, kept out of the optimiser's sight
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.b32 %0, %1, %2, p;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 __device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void upk2(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
@@ -134,8 +152,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     uint64_t* bar_sv = bar_dw + kStages;                                  // saved records of the stage's next tile landed
     uint64_t* bar_cd = bar_sv + kStages;                                  // coefficients of the tile written (coefficient warp)
     uint64_t* bar_gs = bar_cd + kStages;                                  // G MMAs of the tile complete
-    uint64_t* bar_gr = bar_gs + kStages;                                  // [2] G buffer read out by the 8 read-out warps
-    volatile int* next_action = reinterpret_cast<volatile int*>(smem + kOffTmem + 8);
+    uint64_t* bar_gr = bar_gs + kStages;                                  // G buffer read out by the 16 worker warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
     const int warp = threadIdx.x >> 5;
@@ -151,7 +168,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             mbar_init(&bar_sv[s], 1);
             mbar_init(&bar_cd[s], 32);
             mbar_init(&bar_gs[s], 1);
-            if (s < 2) mbar_init(&bar_gr[s], 8);
+            if (s < 1) mbar_init(&bar_gr[s], kWorkers);
         }
         fence_mbar_init();
     }
@@ -177,9 +194,10 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
 
     if (warp >= kWorkers) {
       if (warp == kWorkers + 1) {
-        // ===================================================== front warp: loads, MMA issue, stores.  The whole warp runs
-        // the loop (every address / descriptor stays warp-uniform, i.e. in uniform registers); lane 0 issues the
-        // asynchronous operations.
+        // ===================================================== front warp: loads, dW MMA issue, stores.  The whole warp
+        // runs the loop (every address / descriptor stays warp-uniform, i.e. in uniform registers); lane 0 issues the
+        // asynchronous operations.  (The G MMAs of a tile are issued by that tile's coefficient warp, which is the
+        // one waiting for them: a tcgen05.mma costs its issuer ~55 cycles, 64 of them per tile are too many for one warp.)
         {
             const bool leader = lane == 0;
             if (leader) {
@@ -202,28 +220,36 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             long long facc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long fprev = clock64();
 #define HVS_FTICK(slot) do { if (HVS_TRACE_ON && p.dbg) { const long long tn = clock64(); facc[slot] += tn - fprev; fprev = tn; } } while (0)
-            const uint32_t id_gs = umma_idesc_bf16(64, 32, 0, 0);
-            const uint32_t id_dw = umma_idesc_bf16(64, 24, 1, 0);
+            const uint32_t id_dw = umma_idesc_bf16(128, 32, 1, 0);
             auto retire = [&](int k) {
                 const int s = k % kStages;
                 const uint32_t ph = (uint32_t)(k / kStages) & 1u;
-                // dW += x^T E for the tile whose coefficients are ready: 32 blocks of 64 channels (one atom each),
+                // dW += x^T E for the tile whose coefficients are ready: 16 blocks of 128 channels,
                 // K = 16 = the 8 token rows twice (stride 0) against [E_hi ; E_lo]
-                mbar_wait(&bar_ed[s], ph);
+                mbar_wait_q(&bar_ed[s], ph);
                 if (leader) HVS_TR(k, 9);
                 HVS_FTICK(2);
                 tc_fence_after();
-                const uint64_t bdesc = umma_smem_desc(s0 + kOffEt + s * kEtBytes, 512, 128, kUmmaLayoutNone);
+                // M = 128 channels (two atoms, 1 KB apart), N = 32 = 24 logits + 8 zero rows: the accumulators sit 24 columns
+                // apart, so the 8 extra columns add 0 to the next block's first columns (same issuer, in order).  The last
+                // block puts the zero rows first instead (E tile one row group earlier, accumulator 8 columns lower).
+                const uint32_t et = s0 + kOffEt + s * kEtBytes;
+                const uint64_t bdesc = umma_smem_desc(et + kEtRow0, kEtChunk, 128, kUmmaLayoutNone);
+                const uint64_t bdesc_last = umma_smem_desc(et, kEtChunk, 128, kUmmaLayoutNone);
                 const uint64_t adesc0 = umma_smem_desc(s0 + s * kStageBytes, 1024, 0, kUmmaLayoutSw128);
 #pragma unroll
-                for (int b = 0; b < 32; ++b)           // atom b = 8j + cb at +1 KB each (= +64 in the address field)
+                for (int b = 0; b < 16; ++b)           // block b = atoms 2b, 2b+1 at +2 KB each (= +128 in the address field)
+#ifndef HVS_EXP_NODW
                     if (leader)
-                        umma_bf16_ss(tmem_base + ((uint32_t)((b & 1) * 16) << 16) + kColDw + (uint32_t)((b >> 1) * 24),
-                                     adesc0 + (uint64_t)(b * 64), bdesc, id_dw, 1u);
+#else
+                    if (leader && b < 0)
+#endif
+                        umma_bf16_ss(tmem_base + kColDw + (uint32_t)(b * 24 - (b == 15 ? 8 : 0)), adesc0 + (uint64_t)(b * 128),
+                                     b == 15 ? bdesc_last : bdesc, id_dw, 1u);
                 if (leader) umma_commit(&bar_dw[s]);
                 // dx of the tile (written in place over dy) -> HBM
                 HVS_FTICK(3);
-                mbar_wait(&bar_dxr[s], ph);
+                mbar_wait_q(&bar_dxr[s], ph);
                 if (leader) HVS_TR(k, 10);
                 HVS_FTICK(4);
                 const int tok0 = ((int)blockIdx.x + k * (int)gridDim.x) * kTok;
@@ -234,34 +260,14 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 }
                 __syncwarp();
                 HVS_FTICK(5);
-                mbar_wait(&bar_dw[s], ph);                       // the tensor core is done reading x of this stage
+                mbar_wait_q(&bar_dw[s], ph);                       // the tensor core is done reading x of this stage
                 if (leader) HVS_TR(k, 11);
                 HVS_FTICK(6);
                 if (k + kStages < n_local) load_tile(k + kStages);
                 HVS_FTICK(7);
             };
             for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
-            for (int it = 0; it < n_local; ++it) {
-                const int s = it % kStages;
-                // G of the landed tile: D[64 x 32] = [x rows ; dy rows] (x rows)^T over the 512 channels; the 8-row groups
-                // (stream atoms of one 64-channel block) sit 8 KB apart, x then dy
-                mbar_wait(&bar_full[s], (uint32_t)(it / kStages) & 1u);
-                HVS_FTICK(0);
-                if (it >= 2) mbar_wait(&bar_gr[it & 1], (uint32_t)((it >> 1) - 1) & 1u);   // buffer read out (tile it - 2)
-                tc_fence_after();
-                const uint64_t gdesc0 = umma_smem_desc(s0 + s * kStageBytes, 16, 8192, kUmmaLayoutSw128);
-#pragma unroll
-                for (int cb = 0; cb < 8; ++cb)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t d64 = gdesc0 + (uint64_t)(cb * 64 + ks * 2);      // +1 KB per block, +32 B per K step
-                        if (leader) umma_bf16_ss(tmem_base + kColGs + 32u * (it & 1), d64, d64, id_gs, (uint32_t)((cb | ks) != 0));
-                    }
-                if (leader) umma_commit(&bar_gs[s]);
-                HVS_FTICK(1);
-                if (it >= 2) retire(it - 2);
-            }
-            for (int k = n_local >= 2 ? n_local - 2 : 0; k < n_local; ++k) retire(k);
+            for (int k = 0; k < n_local; ++k) retire(k);
             if (leader) bulk_wait<0>();
             if (HVS_TRACE_ON && p.dbg && leader) for (int q = 0; q < 8; ++q) p.dbg[((size_t)blockIdx.x * 4 + 3) * 8 + q] = facc[q];
         }
@@ -285,6 +291,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         const float4 b_res4 = __ldg(reinterpret_cast<const float4*>(p.bias + 2 * kN) + i4);
         const float eps = p.eps_sk;
         const u64 eps2 = pk2(eps, eps);
+        const uint32_t id_gs = umma_idesc_bf16(64, 64, 0, 0);
         float acc_a[3] = {0.f, 0.f, 0.f};                  // dalpha terms (part 0 lanes)
         float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + tk * 8;     // [iter][token][u x4 | v x4]
         const float* rsv = reinterpret_cast<const float*>(smem + kOffSaved + s * kSavedBytes);
@@ -305,7 +312,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
 #define HVS_TICK(slot) do { if (HVS_TRACE_ON && p.dbg) { const long long tn = clock64(); tacc[slot] += tn - tprev; tprev = tn; } } while (0)
         for (int it = cw; it < n_local; it += kCoefWarps) {
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-            mbar_wait(&bar_sv[s], ph);
+            mbar_wait_q(&bar_sv[s], ph);
             if (lane == 0) HVS_TR(it, 3);
             HVS_TICK(0);
             const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok;
@@ -381,9 +388,36 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             }
             if (lane == 0) HVS_TR(it, 4);
             HVS_TICK(2);
-            // ---- G = dy x^T of the tile (split-K sums by the workers; also: the tile has landed)
-            bar_sync(kBarRec + s, 8 * 32 + 32);
-            mbar_wait(&bar_full[s], ph);
+            // ---- G = dy x^T of the landed tile on the tensor core.  Every tcgen05.mma costs ~55 cycles whatever its shape,
+            //      so the 512 channels go in as two halves side by side: A rows = (stream, half, token) of dy, B rows = the
+            //      same of x (row groups 4 KB apart), K = the 256 channels of a half: 16 MMAs of 64 x 64; the read-out adds
+            //      the two (half, half) diagonal blocks.  This warp issues them (lane 0; descriptors warp-uniform); the 16
+            //      worker warps read the token diagonal out of tensor memory into the tile's record.
+            mbar_wait_q(&bar_full[s], ph);
+            if (it >= 1) {
+                // one G buffer, three issuing warps: strictly in tile order.  (G of tile it - 1 complete first -- only then
+                // is the parity wait on the read-out barrier unambiguous.)
+                mbar_wait_q(&bar_gs[(it - 1) % kStages], (uint32_t)((it - 1) / kStages) & 1u);
+                mbar_wait_q(&bar_gr[0], (uint32_t)(it - 1) & 1u);                      // buffer read out (tile it - 1)
+            }
+            if (lane == 0) HVS_TR(it, 1);
+            tc_fence_after();
+            {
+                const uint32_t st = smem_u32(smem) + s * kStageBytes;
+                const uint64_t xdesc0 = umma_smem_desc(st, 16, 4096, kUmmaLayoutSw128);
+                const uint64_t ydesc0 = umma_smem_desc(st + kHalf, 16, 4096, kUmmaLayoutSw128);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t o = (uint64_t)(c4 * 64 + ks * 2);                 // +1 KB per block, +32 B per K step
+#ifndef HVS_EXP_NOGS
+                        if (lane == 0) umma_bf16_ss(tmem_base + kColGs, ydesc0 + o, xdesc0 + o, id_gs, (uint32_t)((c4 | ks) != 0));
+#endif
+                    }
+                if (lane == 0) umma_commit(&bar_gs[s]);
+            }
+            bar_sync(kBarRec + s, kWorkerThreads + 32);
             HVS_TICK(3);
             // ---- M = P + hpost (x) hpre for the workers (part p writes column jj = p), gate gradients from G
             float dl[24];
@@ -600,58 +634,52 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         const uint32_t stage0 = smem_u32(smem);
         float acc_db = 0.f;                               // dbias of logit tid % 24 over tokens tid / 24 (threads < 192)
         const int q = w & 3, jcol = w >> 2;               // tensor-memory lane quadrant / G column group of this warp
-        const uint32_t tm_gs = tmem_base + ((uint32_t)(32 * q) << 16) + kColGs + 8u * jcol;
+        const uint32_t tm_gs = tmem_base + ((uint32_t)(32 * q) << 16) + kColGs + 16u * jcol;
 
-        // G blocks of a tile out of tensor memory into its record: lanes 0..15 of quadrants 2 and 3 hold the dy rows
-        // (stream 2(q-2) + lane/8, token lane%8); a warp takes the columns of x stream jcol and keeps the token diagonal.
+        // G of a tile out of tensor memory into its record: lanes 0..15 of quadrant q hold the rows (dy stream q, half
+        // lane / 8, token lane % 8); a warp takes the columns of x stream jcol (both halves), keeps the (half, token)
+        // diagonal and adds the halves.
         auto g_tile = [&](int tile) {
             const int s = tile % kStages;
-            if (q >= 2) {
-                mbar_wait(&bar_gs[s], (uint32_t)(tile / kStages) & 1u);
-                tc_fence_after();
-                uint32_t v[8];
-                tmem_ld8(tm_gs + 32u * (tile & 1), v);
-                tmem_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_gr[tile & 1]);
-                const int tok = lane & 7;
-                uint32_t val = v[0];
-#pragma unroll
-                for (int c = 1; c < 8; ++c) val = tok == c ? v[c] : val;
-                if (lane < 16)
-                    reinterpret_cast<uint32_t*>(smem + kOffWrec + s * kWrecBytes)[tok * 16 + (2 * (q - 2) + (lane >> 3)) * 4 + jcol] = val;
-                tc_fence_before();
-                __threadfence_block();
-                bar_arrive(kBarRec + s, 8 * 32 + 32);
-            }
-            if (threadIdx.x == 0) HVS_TR(tile, 2);
+            tc_fence_after();
+            // column lane % 16 of this lane's row, 8 columns at a time (a select tree on the lane bits; an indexed array
+            // would go to the stack, and the stack is an L2 round trip away)
+            const uint32_t b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
+            uint32_t v[8];
+            tmem_ld8(tm_gs, v);
+            tmem_wait_ld();
+            const uint32_t lo8 = sel32(sel32(sel32(v[7], v[6], b0), sel32(v[5], v[4], b0), b1),
+                                       sel32(sel32(v[3], v[2], b0), sel32(v[1], v[0], b0), b1), b2);
+            tmem_ld8(tm_gs + 8, v);
+            tmem_wait_ld();
+            const uint32_t hi8 = sel32(sel32(sel32(v[7], v[6], b0), sel32(v[5], v[4], b0), b1),
+                                       sel32(sel32(v[3], v[2], b0), sel32(v[1], v[0], b0), b1), b2);
+            const uint32_t val = sel32(hi8, lo8, b3);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_gr[0]);
+            const float sum = __uint_as_float(val) + __shfl_xor_sync(0xffffffffu, __uint_as_float(val), 8);
+            if (lane < 8) reinterpret_cast<float*>(smem + kOffWrec + s * kWrecBytes)[lane * 16 + q * 4 + jcol] = sum;
+            __threadfence_block();
+            bar_arrive(kBarRec + s, kWorkerThreads + 32);
+            if (threadIdx.x == 64) HVS_TR(tile, 2);
         };
-        // Worker schedule: whichever is ready first -- G of the next landed tile (it unblocks that tile's coefficient
-        // chain) or dx of the next tile whose coefficients are done.  Thread 0 polls the two mbarriers and publishes
-        // the choice, so all 16 warps take the same branch (both actions contain worker-wide barriers).
-        int g_next = 0, d_next = 0;
-        while (d_next < n_local) {
-            if (threadIdx.x == 0) {
-                int act = 0;
-                while (act == 0) {                                       // bit 0: a tile's G is ready, bit 1: a tile's coefficients are
-                    if (g_next < n_local && mbar_test_wait(&bar_gs[g_next % kStages], (uint32_t)(g_next / kStages) & 1u)) act |= 1;
-                    if (mbar_test_wait(&bar_cd[d_next % kStages], (uint32_t)(d_next / kStages) & 1u)) act |= 2;
-                }
-                *next_action = act;
-            }
-            bar_sync(kBarW, kWorkerThreads);
-            const int act = *next_action;
-            if (act & 1) {
+        // Worker schedule: dx of tile k as soon as its coefficients are done.  Every warp also moves its part of a
+        // finished G out of tensor memory the moment it completes -- while they wait, and between
+        // the four stream steps of a dx pass -- because that read-out heads the next tiles' coefficient chains.
+        int g_next = 0;
+        auto g_poll = [&]() {
+            if (g_next < n_local && mbar_test_wait(&bar_gs[g_next % kStages], (uint32_t)(g_next / kStages) & 1u)) {
                 g_tile(g_next);
                 ++g_next;
             }
-            if (!(act & 2)) continue;
+        };
+        for (int d_next = 0; d_next < n_local;) {
             {
                 // ============ dx for tokens 2t, 2t+1 of tile k, channels 32w + 4g .. +3 of every stream
                 const int k = d_next++;
                 const int s = k % kStages;
-                mbar_wait(&bar_cd[s], (uint32_t)(k / kStages) & 1u);          // acquire the coefficient warp's stores
+                while (!mbar_try_wait_ns(&bar_cd[s], (uint32_t)(k / kStages) & 1u, HVS_POLL_NS)) g_poll();   // (acquires the coefficient warp's stores)
                 if (threadIdx.x == 0) HVS_TR(k, 7);
                 const uint32_t sb = stage0 + s * kStageBytes;
                 uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
@@ -664,9 +692,9 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     acc_db += dlv;
                     const __nv_bfloat16 hi = __float2bfloat16_rn(e);
                     const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
-                    uint8_t* dst = smem + kOffEt + s * kEtBytes + (er >> 3) * 128 + (er & 7) * 16 + etok * 2;
+                    uint8_t* dst = smem + kOffEt + s * kEtBytes + kEtRow0 + (er >> 3) * 128 + (er & 7) * 16 + etok * 2;
                     *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
-                    *reinterpret_cast<__nv_bfloat16*>(dst + 512) = lo;
+                    *reinterpret_cast<__nv_bfloat16*>(dst + kEtChunk) = lo;
                     const uint32_t hb = __bfloat16_as_ushort(hi);
                     const uint32_t nb = __shfl_down_sync(0xffffffffu, hb, 1);
                     if (!(er & 1)) reinterpret_cast<uint32_t*>(wrec)[etok * 12 + (er >> 1)] = hb | (nb << 16);
@@ -687,11 +715,18 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 }
 #pragma unroll
                 for (int jj = 0; jj < kN; ++jj) {
+#ifndef HVS_EXP_NOPOLL
+                    g_poll();
+#endif
                     const float4* mq = reinterpret_cast<const float4*>(wrec + kWrecM + t * (kMpStride * 4)) + jj * 2;
                     const float4 m01 = mq[0], m23 = mq[1];                        // (M_a[0],M_b[0],M_a[1],M_b[1]) (M_a[2],...)
                     const u64 mp[kN] = {pk2(m01.x, m01.y), pk2(m01.z, m01.w), pk2(m23.x, m23.y), pk2(m23.z, m23.w)};
                     uint32_t w8[4];
+#ifdef HVS_EXP_NOWLD
+                    w8[0] = w8[1] = w8[2] = w8[3] = 0u;
+#else
                     tmem_ld4(tm_w + 4u * jj, w8);
+#endif
                     const uint2 xa = lds64(sb + offa0 + jj * 8192);
                     const uint2 xb = lds64(sb + offb0 + jj * 8192);
                     uint32_t oa[2], ob[2];
@@ -742,15 +777,13 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         // ============ dW of this CTA out of tensor memory (every MMA has been committed before the last barrier phase)
         {
             const int last = n_local - 1;
-            mbar_wait(&bar_dw[last % kStages], (uint32_t)(last / kStages) & 1u);
+            mbar_wait_q(&bar_dw[last % kStages], (uint32_t)(last / kStages) & 1u);
             tc_fence_after();
-            const int half = lane >> 4, r = lane & 15;
             float* out = p.dw_part + (size_t)blockIdx.x * kRow * kL;
 #pragma unroll
             for (int pi = 0; pi < 4; ++pi) {
-                const int pr = (w >> 2) * 4 + pi;          // column range = block pair
-                const int b = 2 * pr + half;               // block (j, cb) = (b >> 3, b & 7), row = channel in the block
-                const int kidx = (b >> 3) * kC + (b & 7) * 64 + 16 * q + r;
+                const int pr = (w >> 2) * 4 + pi;          // 128-channel block; this lane's row = channel 32q + lane of it
+                const int kidx = pr * 128 + 32 * q + lane;
                 const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + kColDw + (uint32_t)(pr * 24);
                 uint32_t v[8];
 #pragma unroll

@@ -1,6 +1,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, hvs_b200
+from variants import use_variant; use_variant()
 t = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
 g = torch.Generator(device="cuda:0").manual_seed(11)
 x = torch.randn(t, 4, 512, generator=g, device="cuda:0", dtype=torch.bfloat16)

@@ -3,6 +3,7 @@ import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import hvs_b200
+from variants import use_variant; use_variant()
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20

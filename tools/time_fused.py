@@ -1,6 +1,7 @@
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, hvs_b200
+from variants import use_variant; use_variant()
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(0)
@@ -44,3 +45,8 @@ print("trace CTA 0, tiles 20..31, kcycles relative to load(20):")
 print("tile " + " ".join(f"{e:>7s}" for e in ev))
 for k in range(20, 32):
     print(f"{k:4d} " + " ".join(f"{(tr[k, e] - base) / 1000:7.1f}" for e in range(12)))
+import numpy as np
+sl = tr[8:60].astype(np.float64)
+def dm(a, b): return float(np.mean(sl[:, b] - sl[:, a]))
+print(f"SUMMARY {os.environ.get('HVS_VARIANT','')} kernel {ms:.3f} ms period {float(np.mean(np.diff(sl[:, 8]))):.0f} | load->Gstart {dm(0,1):.0f} Gstart->Gend {dm(1,2):.0f} Gend->Ggot {dm(2,5):.0f} "
+      f"Ggot->cdone {dm(5,6):.0f} cdone->P3s {dm(6,7):.0f} P3 {dm(7,8):.0f} P3e->store {dm(8,10):.0f} store->freed {dm(10,11):.0f} fwd {dm(3,4):.0f}")
