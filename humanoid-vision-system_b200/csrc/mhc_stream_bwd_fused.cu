@@ -51,10 +51,8 @@ constexpr int kWrecBytes = 1152, kWrecM = 384, kWrecK = 960, kWrecS = 992, kMpSt
 constexpr int kOffEt = kOffWrec + kStages * kWrecBytes;           // per stage: E tile, no swizzle: two K chunks (bf16 hi | lo of e over the 8 tokens) of
                                                                   // 5 row groups (8 rows x 16 B): zero | logits 0-7 | 8-15 | 16-23 | zero
 constexpr int kEtBytes = 1280, kEtChunk = 640, kEtRow0 = 128;
-constexpr int kOffInit = kOffEt + kStages * kEtBytes;             // per stage: Sinkhorn start P0 [8][16] | H_pre, H_post [8][8] | inv_rms [8];
-constexpr int kInitBytes = 800, kInitH = 512, kInitR = 768;
 constexpr int kSkWords = kTok * kMaxIters * 8;
-constexpr int kOffSk = kOffInit + kStages * kInitBytes;
+constexpr int kOffSk = kOffEt + kStages * kEtBytes;                 // per coefficient warp: scalings u | v of every Sinkhorn iteration
 constexpr int kOffDl = kOffSk + kCoefWarps * kSkWords * 4;        // per stage: d logits [8][24] fp32 (coefficient warp -> workers)
 constexpr int kDlBytes = 768;
 constexpr int kOffPart = kOffDl + kStages * kDlBytes;             // end-of-kernel dbias fold: [8 tokens][24] fp32
@@ -62,7 +60,7 @@ constexpr int kOffBias = kOffPart + kTok * kL * 4;                // bias[24] st
 constexpr int kOffBar = kOffBias + 128;
 constexpr int kOffTmem = kOffBar + 8 * kStages * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
-static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0 && kOffInit % 16 == 0 && kOffSk % 16 == 0 && kOffDl % 16 == 0, "alignment");
+static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0 && kOffSk % 16 == 0 && kOffDl % 16 == 0, "alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 constexpr uint32_t kTmemCols = 512;
@@ -71,7 +69,7 @@ constexpr uint32_t kColGs = 384;                      // dy x^T of a tile in two
 constexpr uint32_t kColW = 448;                       // 64 columns = 16 registers per worker thread: the K = 8 step of its W
                                                       //     fragments lives here instead of spilling (no L1 to speak of)
 
-constexpr int kBarRec = 1 /*,2,3*/, kBarCoef = 4 /*,5,6*/, kBarW = 7;
+constexpr int kBarRec = 1 /*,2,3*/, kBarW = 4;
 
 struct FusedParams {
     const float* phi;
@@ -98,19 +96,6 @@ struct FusedParams {
 #define HVS_TRACE_ON 0
 #endif
 
-#ifndef HVS_WAIT_NS
-#define HVS_WAIT_NS 1000
-#endif
-#ifndef HVS_POLL_NS
-#define HVS_POLL_NS 100
-#endif
-__device__ __forceinline__ void mbar_wait_q(uint64_t* bar, uint32_t parity) {          // quiet wait (see mbar_try_wait_ns)
-#if HVS_WAIT_NS > 0
-    mbar_wait_ns(bar, parity, HVS_WAIT_NS);
-#else
-    mbar_wait(bar, parity);
-#endif
-}
 typedef unsigned long long u64;
 __device__ __forceinline__ uint32_t sel32(uint32_t a, uint32_t b, uint32_t c) {       // c != 0 ? a : b, kept out of the optimiser's sight
     uint32_t r;
@@ -129,10 +114,6 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 }
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
 // D(16x8,f32) += A(16x8,bf16,row) * B(8x8,bf16,col)
 __device__ __forceinline__ void mma_bf16_1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
@@ -156,6 +137,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
     const int warp = threadIdx.x >> 5;
+    const int wtid = threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -206,16 +188,21 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 tma_prefetch_desc(&tmap_dx);
             }
             const uint32_t s0 = smem_u32(smem);
-            auto load_tile = [&](int it) {
+            // a tile = two 32 KB boxes on one mbarrier; the x half of a stage is free as soon as the dx pass and the dW MMAs
+            // are done with it, the dy half only once the dx store has read it
+            auto load_x = [&](int it) {
                 const int s = it % kStages;
                 const int tok0 = ((int)blockIdx.x + it * (int)gridDim.x) * kTok;
-                uint8_t* st = smem + s * kStageBytes;
                 if (leader) {
                     mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
-                    tma_load_4d(st, &tmap_x, &bar_full[s], 0, tok0, 0, 0);                  // one 32 KB box each
-                    tma_load_4d(st + kHalf, &tmap_dy, &bar_full[s], 0, tok0, 0, 0);
+                    tma_load_4d(smem + s * kStageBytes, &tmap_x, &bar_full[s], 0, tok0, 0, 0);
                     HVS_TR(it, 0);
                 }
+            };
+            auto load_dy = [&](int it) {
+                const int s = it % kStages;
+                const int tok0 = ((int)blockIdx.x + it * (int)gridDim.x) * kTok;
+                if (leader) tma_load_4d(smem + s * kStageBytes + kHalf, &tmap_dy, &bar_full[s], 0, tok0, 0, 0);
             };
             long long facc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long fprev = clock64();
@@ -224,9 +211,10 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             auto retire = [&](int k) {
                 const int s = k % kStages;
                 const uint32_t ph = (uint32_t)(k / kStages) & 1u;
+                const int tok0 = ((int)blockIdx.x + k * (int)gridDim.x) * kTok;
                 // dW += x^T E for the tile whose coefficients are ready: 16 blocks of 128 channels,
                 // K = 16 = the 8 token rows twice (stride 0) against [E_hi ; E_lo]
-                mbar_wait_q(&bar_ed[s], ph);
+                mbar_wait(&bar_ed[s], ph);
                 if (leader) HVS_TR(k, 9);
                 HVS_FTICK(2);
                 tc_fence_after();
@@ -239,66 +227,61 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 const uint64_t adesc0 = umma_smem_desc(s0 + s * kStageBytes, 1024, 0, kUmmaLayoutSw128);
 #pragma unroll
                 for (int b = 0; b < 16; ++b)           // block b = atoms 2b, 2b+1 at +2 KB each (= +128 in the address field)
-#ifndef HVS_EXP_NODW
                     if (leader)
-#else
-                    if (leader && b < 0)
-#endif
                         umma_bf16_ss(tmem_base + kColDw + (uint32_t)(b * 24 - (b == 15 ? 8 : 0)), adesc0 + (uint64_t)(b * 128),
                                      b == 15 ? bdesc_last : bdesc, id_dw, 1u);
                 if (leader) umma_commit(&bar_dw[s]);
-                // dx of the tile (written in place over dy) -> HBM
                 HVS_FTICK(3);
-                mbar_wait_q(&bar_dxr[s], ph);
-                if (leader) HVS_TR(k, 10);
-                HVS_FTICK(4);
-                const int tok0 = ((int)blockIdx.x + k * (int)gridDim.x) * kTok;
+                // dx of the tile (written in place over dy) -> HBM
+                mbar_wait(&bar_dxr[s], ph);
                 if (leader) {
+                    HVS_TR(k, 10);
                     tma_store_4d(&tmap_dx, smem + s * kStageBytes + kHalf, 0, tok0, 0, 0);
                     bulk_commit();
-                    bulk_wait_read<0>();
                 }
-                __syncwarp();
-                HVS_FTICK(5);
-                mbar_wait_q(&bar_dw[s], ph);                       // the tensor core is done reading x of this stage
-                if (leader) HVS_TR(k, 11);
+                HVS_FTICK(4);
+                mbar_wait(&bar_dw[s], ph);                       // the tensor core is done reading x of this stage
+                if (k + kStages < n_local) load_x(k + kStages);
                 HVS_FTICK(6);
-                if (k + kStages < n_local) load_tile(k + kStages);
+                if (leader) bulk_wait_read<0>();
+                __syncwarp();
+                if (leader) HVS_TR(k, 11);
+                HVS_FTICK(5);
+                if (k + kStages < n_local) load_dy(k + kStages);
                 HVS_FTICK(7);
             };
-            for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
+            for (int it = 0; it < kStages && it < n_local; ++it) { load_x(it); load_dy(it); }
             for (int k = 0; k < n_local; ++k) retire(k);
             if (leader) bulk_wait<0>();
             if (HVS_TRACE_ON && p.dbg && leader) for (int q = 0; q < 8; ++q) p.dbg[((size_t)blockIdx.x * 4 + 3) * 8 + q] = facc[q];
         }
       } else {
         // ===================================================== coefficient warps (warps 16, 18, 19 <-> stage 0, 1, 2)
-        // lane = token: the whole 4x4 block of token lane%8 lives in this lane's registers as packed fp32x2 rows, so
-        // the forward iterations and the reverse sweep are shuffle-free chains with four-way instruction-level
-        // parallelism.  Lanes 8..31 repeat tokens 0..7 (lane / 8 = part) and take a quarter of the stores each.
+        // Four lanes per token: lane 4 tk + i owns row i of the token's 4x4 blocks as two packed fp32x2 registers, so
+        // row sums / row dot products are local and column sums are two xor-shuffle steps inside the quad.  These warps
+        // share their scheduler with four worker warps each, so what counts is the number of instructions per
+        // iteration (about half of a lane-per-token layout, whose other 24 lanes only repeat work).
         //   forward  (reference arithmetic, P / (sum + eps)) runs AHEAD of the tile: it needs only the saved record,
         //            which this warp fetches itself; it also tracks the cumulative scalings u, v with
         //            P_k = diag(u_k) K diag(v_k), K = the softmax start
         //   backward differentiates that scaling form exactly: u_k = 1 / (K v_{k-1}), v_k = 1 / (K^T u_k)  (the eps of
         //            the reference, 1e-8 against sums of 1, is below fp32 resolution), so the sweep needs neither
         //            reciprocals nor a reconstruction of P: per iteration four 4x4 mat-vecs / rank-1 updates.
-        const int cw = warp == kWorkers ? 0 : warp - (kWorkers + 1);
+        const int cw = warp == kWorkers ? 0 : warp - (kWorkers + 1);     // warps 16, 18, 19 -> 0, 1, 2
         const int s = cw;
-        const int tk = lane & 7, part = lane >> 3;
-        const int tk4 = lane >> 2, i4 = lane & 3;          // prologue layout: four lanes per token, lane i4 owns row i4
+        const int tk = lane >> 2, i4 = lane & 3, qb = lane & ~3;
         const float a_pre = __ldg(p.alpha + 0), a_post = __ldg(p.alpha + 1), a_res = __ldg(p.alpha + 2);
         const float b_pre4 = __ldg(p.bias + i4), b_post4 = __ldg(p.bias + kN + i4);
         const float4 b_res4 = __ldg(reinterpret_cast<const float4*>(p.bias + 2 * kN) + i4);
         const float eps = p.eps_sk;
         const u64 eps2 = pk2(eps, eps);
         const uint32_t id_gs = umma_idesc_bf16(64, 64, 0, 0);
-        float acc_a[3] = {0.f, 0.f, 0.f};                  // dalpha terms (part 0 lanes)
-        float* skl = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + tk * 8;     // [iter][token][u x4 | v x4]
+        float acc_a[3] = {0.f, 0.f, 0.f};                  // dalpha terms (row-0 lanes)
+        // scalings of every iteration: [iter][ u: 32 floats, lane-indexed | v: 8 tokens x 4 ]
+        float* sku = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + lane;
+        float* skv = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + 32 + tk * 4;
         const float* rsv = reinterpret_cast<const float*>(smem + kOffSaved + s * kSavedBytes);
-        const float4* rs4 = reinterpret_cast<const float4*>(rsv + tk * kSaved);
-        const float4* gs4 = reinterpret_cast<const float4*>(smem + kOffWrec + s * kWrecBytes + tk * 64);
         uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
-        float* init = reinterpret_cast<float*>(smem + kOffInit + s * kInitBytes);
         auto fetch_saved = [&](int it) {                   // lane 0: the 8 saved records of tile `it` -> shared memory
             const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok;
             const int64_t left = p.T - tok0;
@@ -306,83 +289,66 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             mbar_arrive_expect_tx(&bar_sv[s], bytes);
             bulk_load_1d(smem + kOffSaved + s * kSavedBytes, p.saved + tok0 * kSaved, bytes, &bar_sv[s]);
         };
+        auto quad_sum2 = [](u64 v) {                       // sum over the four lanes of a token, identical in all four
+            v = add2(v, __shfl_xor_sync(0xffffffffu, v, 1));
+            return add2(v, __shfl_xor_sync(0xffffffffu, v, 2));
+        };
         if (lane == 0 && cw < n_local) fetch_saved(cw);
         long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         long long tprev = clock64();
 #define HVS_TICK(slot) do { if (HVS_TRACE_ON && p.dbg) { const long long tn = clock64(); tacc[slot] += tn - tprev; tprev = tn; } } while (0)
         for (int it = cw; it < n_local; it += kCoefWarps) {
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-            mbar_wait_q(&bar_sv[s], ph);
+            mbar_wait(&bar_sv[s], ph);
             if (lane == 0) HVS_TR(it, 3);
             HVS_TICK(0);
             const int64_t tok0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTok;
-            // ---- prologue, four lanes per token: inverse RMS, gates, softmax start of row i4 -> shared memory.
+            // ---- prologue: inverse RMS, gates, softmax start of row i4.
             // Rows past T: x = dy = 0 (TMA fill) and the records were not loaded; they run on zeros.
+            const bool valid = tok0 + tk < p.T;
+            const float* r = rsv + tk * kSaved;
+            const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(valid ? r[kL] : 1.0f, 1.0f / kRow, p.eps_rms)));
+            const float raw_pre = valid ? r[i4] : 0.f, raw_post = valid ? r[kN + i4] : 0.f;
+            const float4 rr = valid ? *reinterpret_cast<const float4*>(r + 2 * kN + 4 * i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            u64 K01, K23;                                  // row i4 of K = 4 softmax(logits): the Sinkhorn start
             {
-                const bool v4 = tok0 + tk4 < p.T;
-                const float* r = rsv + tk4 * kSaved;
-                const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(v4 ? r[kL] : 1.0f, 1.0f / kRow, p.eps_rms)));
-                const float raw_pre = v4 ? r[i4] : 0.f, raw_post = v4 ? r[kN + i4] : 0.f;
-                const float4 rr = v4 ? *reinterpret_cast<const float4*>(r + 2 * kN + 4 * i4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float l0 = fmaf(a_res, rr.x * inv_rms, b_res4.x), l1 = fmaf(a_res, rr.y * inv_rms, b_res4.y);
                 const float l2 = fmaf(a_res, rr.z * inv_rms, b_res4.z), l3 = fmaf(a_res, rr.w * inv_rms, b_res4.w);
                 const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
                 const float e0 = fast_exp(l0 - mx), e1 = fast_exp(l1 - mx), e2 = fast_exp(l2 - mx), e3 = fast_exp(l3 - mx);
                 const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
-                *reinterpret_cast<float4*>(init + tk4 * 16 + 4 * i4) = make_float4(e0 * r4, e1 * r4, e2 * r4, e3 * r4);
-                init[kInitH / 4 + tk4 * 8 + i4] = sigmoid_f32(fmaf(a_pre, raw_pre * inv_rms, b_pre4));
-                init[kInitH / 4 + tk4 * 8 + kN + i4] = 2.0f * sigmoid_f32(fmaf(a_post, raw_post * inv_rms, b_post4));
-                if (i4 == 0) init[kInitR / 4 + tk4] = inv_rms;
+                K01 = pk2(e0 * r4, e1 * r4);
+                K23 = pk2(e2 * r4, e3 * r4);
             }
-            __syncwarp();
+            const float hpre = sigmoid_f32(fmaf(a_pre, raw_pre * inv_rms, b_pre4));
+            const float hpost = 2.0f * sigmoid_f32(fmaf(a_post, raw_post * inv_rms, b_post4));
             HVS_TICK(1);
-            // ---- lane = token from here on
-            const bool valid = tok0 + tk < p.T;
-            const float inv_rms = init[kInitR / 4 + tk];
-            u64 P[4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 v = *reinterpret_cast<const float4*>(init + tk * 16 + 4 * i);
-                P[i][0] = pk2(v.x, v.y);
-                P[i][1] = pk2(v.z, v.w);
-            }
             // ---- forward Sinkhorn; the cumulative scalings after every iteration are kept for the reverse sweep
+            u64 P01 = K01, P23 = K23;
             {
-                u64 U01 = pk2(1.f, 1.f), U23 = U01, V01 = U01, V23 = U01;
+                float ui = 1.f;
+                u64 V01 = pk2(1.f, 1.f), V23 = V01;
                 for (int k = 0; k < p.sk_iters; ++k) {
-                    float rr[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float sa, sb;
-                        upk2(add2(P[i][0], P[i][1]), sa, sb);
-                        rr[i] = rcp_approx((sa + sb) + eps);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const u64 rr2 = pk2(rr[i], rr[i]);
-                        P[i][0] = mul2(P[i][0], rr2);
-                        P[i][1] = mul2(P[i][1], rr2);
-                    }
-                    U01 = mul2(U01, pk2(rr[0], rr[1]));
-                    U23 = mul2(U23, pk2(rr[2], rr[3]));
-                    const u64 c01 = add2(add2(add2(P[0][0], P[1][0]), add2(P[2][0], P[3][0])), eps2);
-                    const u64 c23 = add2(add2(add2(P[0][1], P[1][1]), add2(P[2][1], P[3][1])), eps2);
+                    float sa, sb;
+                    upk2(add2(P01, P23), sa, sb);
+                    const float rw = rcp_approx((sa + sb) + eps);
+                    const u64 rw2 = pk2(rw, rw);
+                    P01 = mul2(P01, rw2);
+                    P23 = mul2(P23, rw2);
+                    ui *= rw;
+                    const u64 c01 = add2(quad_sum2(P01), eps2), c23 = add2(quad_sum2(P23), eps2);
                     float c0, c1, c2, c3;
                     upk2(c01, c0, c1); upk2(c23, c2, c3);
                     const u64 rc01 = pk2(rcp_approx(c0), rcp_approx(c1)), rc23 = pk2(rcp_approx(c2), rcp_approx(c3));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        P[i][0] = mul2(P[i][0], rc01);
-                        P[i][1] = mul2(P[i][1], rc23);
-                    }
+                    P01 = mul2(P01, rc01);
+                    P23 = mul2(P23, rc23);
                     V01 = mul2(V01, rc01);
                     V23 = mul2(V23, rc23);
-                    if (part == 0) {
-                        float u0, u1, u2, u3, v0, v1, v2, v3;
-                        upk2(U01, u0, u1); upk2(U23, u2, u3); upk2(V01, v0, v1); upk2(V23, v2, v3);
-                        float4* o = reinterpret_cast<float4*>(skl + k * 64);
-                        o[0] = make_float4(u0, u1, u2, u3);
-                        o[1] = make_float4(v0, v1, v2, v3);
+                    sku[k * 64] = ui;
+                    if (i4 == 0) {
+                        float v0, v1, v2, v3;
+                        upk2(V01, v0, v1); upk2(V23, v2, v3);
+                        *reinterpret_cast<float4*>(skv + k * 64) = make_float4(v0, v1, v2, v3);
                     }
                 }
             }
@@ -393,12 +359,12 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             //      same of x (row groups 4 KB apart), K = the 256 channels of a half: 16 MMAs of 64 x 64; the read-out adds
             //      the two (half, half) diagonal blocks.  This warp issues them (lane 0; descriptors warp-uniform); the 16
             //      worker warps read the token diagonal out of tensor memory into the tile's record.
-            mbar_wait_q(&bar_full[s], ph);
+            mbar_wait(&bar_full[s], ph);
             if (it >= 1) {
                 // one G buffer, three issuing warps: strictly in tile order.  (G of tile it - 1 complete first -- only then
                 // is the parity wait on the read-out barrier unambiguous.)
-                mbar_wait_q(&bar_gs[(it - 1) % kStages], (uint32_t)((it - 1) / kStages) & 1u);
-                mbar_wait_q(&bar_gr[0], (uint32_t)(it - 1) & 1u);                      // buffer read out (tile it - 1)
+                mbar_wait(&bar_gs[(it - 1) % kStages], (uint32_t)((it - 1) / kStages) & 1u);
+                mbar_wait(&bar_gr[0], (uint32_t)(it - 1) & 1u);                      // buffer read out (tile it - 1)
             }
             if (lane == 0) HVS_TR(it, 1);
             tc_fence_after();
@@ -411,145 +377,106 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t o = (uint64_t)(c4 * 64 + ks * 2);                 // +1 KB per block, +32 B per K step
-#ifndef HVS_EXP_NOGS
                         if (lane == 0) umma_bf16_ss(tmem_base + kColGs, ydesc0 + o, xdesc0 + o, id_gs, (uint32_t)((c4 | ks) != 0));
-#endif
                     }
                 if (lane == 0) umma_commit(&bar_gs[s]);
             }
             bar_sync(kBarRec + s, kWorkerThreads + 32);
             HVS_TICK(3);
-            // ---- M = P + hpost (x) hpre for the workers (part p writes column jj = p), gate gradients from G
-            float dl[24];
-            float4 grow[4];
+            // ---- M = P + hpost (x) hpre for the workers, gate gradients from G (row i4 of the token's G)
+            const float4 g = *reinterpret_cast<const float4*>(wrec + lane * 16);
+            __syncwarp();                                   // every lane has its G row: M may overwrite the record
+            float dl_pre, dl_post;
             {
-                const float4 hp = *reinterpret_cast<const float4*>(init + kInitH / 4 + tk * 8);
-                const float4 hq = *reinterpret_cast<const float4*>(init + kInitH / 4 + tk * 8 + 4);
-                const float hpre[4] = {hp.x, hp.y, hp.z, hp.w}, hpost[4] = {hq.x, hq.y, hq.z, hq.w};
-                float dhpre[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) grow[i] = gs4[i];
-                __syncwarp();                               // every lane has its G rows: M may overwrite the record
-                float* mp = reinterpret_cast<float*>(wrec + kWrecM) + (tk >> 1) * kMpStride + part * 8 + (tk & 1);
-                const float hsel = part == 0 ? hpre[0] : part == 1 ? hpre[1] : part == 2 ? hpre[2] : hpre[3];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 g = grow[i];                                  // row i of G
-                    const float dhpost = fmaf(g.w, hpre[3], fmaf(g.z, hpre[2], fmaf(g.y, hpre[1], g.x * hpre[0])));
-                    dl[4 + i] = dhpost * hpost[i] * (1.0f - 0.5f * hpost[i]);
-                    dhpre[0] = fmaf(g.x, hpost[i], dhpre[0]); dhpre[1] = fmaf(g.y, hpost[i], dhpre[1]);
-                    dhpre[2] = fmaf(g.z, hpost[i], dhpre[2]); dhpre[3] = fmaf(g.w, hpost[i], dhpre[3]);
-                    float p0, p1, p2, p3;
-                    upk2(P[i][0], p0, p1); upk2(P[i][1], p2, p3);
-                    const float psel = part == 0 ? p0 : part == 1 ? p1 : part == 2 ? p2 : p3;
-                    mp[i * 2] = fmaf(hpost[i], hsel, psel);                     // M[i][part]
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dl[j] = dhpre[j] * hpre[j] * (1.0f - hpre[j]);
+                const float hp0 = __shfl_sync(0xffffffffu, hpre, qb), hp1 = __shfl_sync(0xffffffffu, hpre, qb + 1);
+                const float hp2 = __shfl_sync(0xffffffffu, hpre, qb + 2), hp3 = __shfl_sync(0xffffffffu, hpre, qb + 3);
+                const float dhpost = fmaf(g.w, hp3, fmaf(g.z, hp2, fmaf(g.y, hp1, g.x * hp0)));
+                dl_post = dhpost * hpost * (1.0f - 0.5f * hpost);
+                const u64 hq2 = pk2(hpost, hpost);
+                const u64 d01 = quad_sum2(mul2(pk2(g.x, g.y), hq2)), d23 = quad_sum2(mul2(pk2(g.z, g.w), hq2));
+                float d0, d1, d2, d3;
+                upk2(d01, d0, d1); upk2(d23, d2, d3);
+                const float dhpre = i4 == 0 ? d0 : i4 == 1 ? d1 : i4 == 2 ? d2 : d3;
+                dl_pre = dhpre * hpre * (1.0f - hpre);
+                float p0, p1, p2, p3;
+                upk2(P01, p0, p1); upk2(P23, p2, p3);
+                float* mp = reinterpret_cast<float*>(wrec + kWrecM) + (tk >> 1) * kMpStride + i4 * 2 + (tk & 1);
+                mp[0] = fmaf(hpost, hp0, p0);               // M[i4][j] at j * 8
+                mp[8] = fmaf(hpost, hp1, p1);
+                mp[16] = fmaf(hpost, hp2, p2);
+                mp[24] = fmaf(hpost, hp3, p3);
             }
             if (lane == 0) HVS_TR(it, 5);
             HVS_TICK(4);
-            // ---- reverse sweep in the scaling form.  K by rows (Kr) and by columns (Kc), both packed; dK accumulates
-            //      by rows; ub / vb are the adjoints of the current u / v.
-            u64 dK[4][2];
+            // ---- reverse sweep in the scaling form; dK accumulates row i4; ub / vb are the adjoints of the current u / v
+            u64 dK0, dK1;
             {
-                u64 Kr[4][2];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 v = *reinterpret_cast<const float4*>(init + tk * 16 + 4 * i);
-                    Kr[i][0] = pk2(v.x, v.y);
-                    Kr[i][1] = pk2(v.z, v.w);
-                }
                 const int last = p.sk_iters - 1;
-                const float* skp = skl + last * 64;                             // u_k | v_k of the iteration being undone
-                float4 un = make_float4(1.f, 1.f, 1.f, 1.f), vn = un;
+                float un = 1.f;
+                float4 vn = make_float4(1.f, 1.f, 1.f, 1.f);
                 if (last >= 0) {
-                    un = *reinterpret_cast<const float4*>(skp);
-                    vn = *reinterpret_cast<const float4*>(skp + 4);
+                    un = sku[last * 64];
+                    vn = *reinterpret_cast<const float4*>(skv + last * 64);
                 }
                 // adjoints of the output P = diag(u) K diag(v):  dK = G u v^T,  ub_i = sum_j G_ij K_ij v_j,  vb_j = sum_i G_ij K_ij u_i.
-                // ub is kept as one packed partial-sum pair per row (its two halves are added when it is consumed).
-                u64 ubp[4], vb01, vb23;
+                // ub is kept as a packed partial-sum pair (its two halves are added when it is consumed).
+                u64 ubp, vb01, vb23;
                 {
-                    const u64 v01 = pk2(vn.x, vn.y), v23 = pk2(vn.z, vn.w);
-                    const float uu[4] = {un.x, un.y, un.z, un.w};
-                    vb01 = pk2(0.f, 0.f); vb23 = vb01;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const u64 g0 = pk2(grow[i].x, grow[i].y), g1 = pk2(grow[i].z, grow[i].w);
-                        const u64 gk0 = mul2(g0, Kr[i][0]), gk1 = mul2(g1, Kr[i][1]);
-                        const u64 ui = pk2(uu[i], uu[i]);
-                        ubp[i] = fma2(gk1, v23, mul2(gk0, v01));
-                        vb01 = fma2(gk0, ui, vb01);
-                        vb23 = fma2(gk1, ui, vb23);
-                        dK[i][0] = mul2(mul2(g0, v01), ui);
-                        dK[i][1] = mul2(mul2(g1, v23), ui);
-                    }
+                    const u64 v01 = pk2(vn.x, vn.y), v23 = pk2(vn.z, vn.w), ui = pk2(un, un);
+                    const u64 g0 = pk2(g.x, g.y), g1 = pk2(g.z, g.w);
+                    const u64 gk0 = mul2(g0, K01), gk1 = mul2(g1, K23);
+                    ubp = fma2(gk1, v23, mul2(gk0, v01));
+                    vb01 = quad_sum2(mul2(gk0, ui));
+                    vb23 = quad_sum2(mul2(gk1, ui));
+                    dK0 = mul2(mul2(g0, v01), ui);
+                    dK1 = mul2(mul2(g1, v23), ui);
                 }
                 for (int k = last; k >= 0; --k) {
-                    const float uu[4] = {un.x, un.y, un.z, un.w};
+                    const float uu = un;
                     const u64 v01 = pk2(vn.x, vn.y), v23 = pk2(vn.z, vn.w), nv01 = pk2(-vn.x, -vn.y), nv23 = pk2(-vn.z, -vn.w);
-                    skp -= 64;
                     if (k > 0) {                                                // u_{k-1}, v_{k-1}
-                        un = *reinterpret_cast<const float4*>(skp);
-                        vn = *reinterpret_cast<const float4*>(skp + 4);
+                        un = sku[(k - 1) * 64];
+                        vn = *reinterpret_cast<const float4*>(skv + (k - 1) * 64);
                     } else {
                         vn = make_float4(1.f, 1.f, 1.f, 1.f);                   // v_0
                     }
                     const u64 vp01 = pk2(vn.x, vn.y), vp23 = pk2(vn.z, vn.w);
                     // v_k = 1 / (K^T u_k):  tb = -vb v_k^2 ;  ub += K tb ;  dK += u_k tb^T
                     const u64 tb01 = mul2(mul2(vb01, v01), nv01), tb23 = mul2(mul2(vb23, v23), nv23);
-                    float sb[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const u64 ui = pk2(uu[i], uu[i]);
-                        ubp[i] = fma2(Kr[i][1], tb23, fma2(Kr[i][0], tb01, ubp[i]));
-                        dK[i][0] = fma2(tb01, ui, dK[i][0]);
-                        dK[i][1] = fma2(tb23, ui, dK[i][1]);
-                        // u_k = 1 / (K v_{k-1}):  sb = -ub u_k^2
-                        float ua, ub_;
-                        upk2(ubp[i], ua, ub_);
-                        sb[i] = -(ua + ub_) * (uu[i] * uu[i]);
-                        ubp[i] = pk2(0.f, 0.f);
-                    }
+                    const u64 ui = pk2(uu, uu);
+                    ubp = fma2(K23, tb23, fma2(K01, tb01, ubp));
+                    dK0 = fma2(tb01, ui, dK0);
+                    dK1 = fma2(tb23, ui, dK1);
+                    // u_k = 1 / (K v_{k-1}):  sb = -ub u_k^2
+                    float ua, ub_;
+                    upk2(ubp, ua, ub_);
+                    const float sb = -(ua + ub_) * (uu * uu);
+                    ubp = pk2(0.f, 0.f);
                     // vb = K^T sb ;  dK += sb v_{k-1}^T
-                    {
-                        const u64 s0 = pk2(sb[0], sb[0]);
-                        vb01 = mul2(Kr[0][0], s0);
-                        vb23 = mul2(Kr[0][1], s0);
-                        dK[0][0] = fma2(vp01, s0, dK[0][0]);
-                        dK[0][1] = fma2(vp23, s0, dK[0][1]);
-                    }
-#pragma unroll
-                    for (int i = 1; i < 4; ++i) {
-                        const u64 si = pk2(sb[i], sb[i]);
-                        vb01 = fma2(Kr[i][0], si, vb01);
-                        vb23 = fma2(Kr[i][1], si, vb23);
-                        dK[i][0] = fma2(vp01, si, dK[i][0]);
-                        dK[i][1] = fma2(vp23, si, dK[i][1]);
-                    }
+                    const u64 s2 = pk2(sb, sb);
+                    vb01 = quad_sum2(mul2(K01, s2));
+                    vb23 = quad_sum2(mul2(K23, s2));
+                    dK0 = fma2(vp01, s2, dK0);
+                    dK1 = fma2(vp23, s2, dK1);
                 }
-                HVS_TICK(5);
-                // ---- softmax * 4 backward: dl = K (dK - sum_j(dK K) / 4); the sums for kappa (RMSNorm backward) and
-                //      dalpha.  Raw values are re-read from the record.
-                float da_pre = 0.f, da_post = 0.f, da_res = 0.f;
-                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 rp = valid ? rs4[0] : zero4, rq = valid ? rs4[1] : zero4;
-                da_pre = fmaf(dl[3], rp.w, fmaf(dl[2], rp.z, fmaf(dl[1], rp.y, dl[0] * rp.x)));
-                da_post = fmaf(dl[7], rq.w, fmaf(dl[6], rq.z, fmaf(dl[5], rq.y, dl[4] * rq.x)));
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float qa, qb;
-                    upk2(fma2(dK[i][1], Kr[i][1], mul2(dK[i][0], Kr[i][0])), qa, qb);
-                    const float nqs = -0.25f * (qa + qb);
-                    const u64 nq2 = pk2(nqs, nqs);
-                    upk2(mul2(Kr[i][0], add2(dK[i][0], nq2)), dl[8 + 4 * i], dl[8 + 4 * i + 1]);
-                    upk2(mul2(Kr[i][1], add2(dK[i][1], nq2)), dl[8 + 4 * i + 2], dl[8 + 4 * i + 3]);
-                    const float4 rr = valid ? rs4[2 + i] : zero4;
-                    da_res += fmaf(dl[8 + 4 * i + 3], rr.w, fmaf(dl[8 + 4 * i + 2], rr.z, fmaf(dl[8 + 4 * i + 1], rr.y, dl[8 + 4 * i] * rr.x)));
-                }
+            }
+            HVS_TICK(5);
+            // ---- softmax * 4 backward: dl = K (dK - sum_j(dK K) / 4); the sums for kappa (RMSNorm backward) and dalpha
+            {
+                float qa, qb_;
+                upk2(fma2(dK1, K23, mul2(dK0, K01)), qa, qb_);
+                const float nqs = -0.25f * (qa + qb_);
+                const u64 nq2 = pk2(nqs, nqs);
+                float d0, d1, d2, d3;
+                upk2(mul2(K01, add2(dK0, nq2)), d0, d1);
+                upk2(mul2(K23, add2(dK1, nq2)), d2, d3);
+                const u64 sums = quad_sum2(pk2(dl_pre * raw_pre, dl_post * raw_post));
+                const u64 sumr = quad_sum2(pk2(fmaf(d3, rr.w, fmaf(d2, rr.z, fmaf(d1, rr.y, d0 * rr.x))), 0.f));
+                float da_pre, da_post, da_res, unused;
+                upk2(sums, da_pre, da_post);
+                upk2(sumr, da_res, unused);
                 // d inv_rms = sum_k e_k raw_k / inv_rms with e = alpha_g * dl * inv_rms ;  kappa = -d inv_rms * inv_rms^3 / N
-                if (part == 0) {
+                if (i4 == 0) {
                     const float dsum = (a_pre * da_pre + a_post * da_post + a_res * da_res) * inv_rms;
                     acc_a[0] = fmaf(da_pre, inv_rms, acc_a[0]);
                     acc_a[1] = fmaf(da_post, inv_rms, acc_a[1]);
@@ -558,21 +485,11 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     float* sc = reinterpret_cast<float*>(wrec + kWrecS) + tk * 3;
                     sc[0] = a_pre * inv_rms; sc[1] = a_post * inv_rms; sc[2] = a_res * inv_rms;
                 }
-            }
-            // d logits of the token for the workers (they scale to e, split into bf16 hi/lo and build the E tile):
-            // part p stores quad p, parts 0 and 1 also quads 4 and 5
-            {
-                __syncwarp();
-                float4* dq = reinterpret_cast<float4*>(smem + kOffDl + s * kDlBytes) + tk * 6;
-                float4 a, b;
-                a.x = part == 0 ? dl[0] : part == 1 ? dl[4] : part == 2 ? dl[8] : dl[12];
-                a.y = part == 0 ? dl[1] : part == 1 ? dl[5] : part == 2 ? dl[9] : dl[13];
-                a.z = part == 0 ? dl[2] : part == 1 ? dl[6] : part == 2 ? dl[10] : dl[14];
-                a.w = part == 0 ? dl[3] : part == 1 ? dl[7] : part == 2 ? dl[11] : dl[15];
-                b.x = part == 0 ? dl[16] : dl[20]; b.y = part == 0 ? dl[17] : dl[21];
-                b.z = part == 0 ? dl[18] : dl[22]; b.w = part == 0 ? dl[19] : dl[23];
-                dq[part] = a;
-                if (part < 2) dq[4 + part] = b;
+                // d logits of the token for the workers (they scale to e, split into bf16 hi/lo and build the E tile)
+                float* dq = reinterpret_cast<float*>(smem + kOffDl + s * kDlBytes) + tk * kL;
+                dq[i4] = dl_pre;
+                dq[kN + i4] = dl_post;
+                *reinterpret_cast<float4*>(dq + 2 * kN + 4 * i4) = make_float4(d0, d1, d2, d3);
             }
             __syncwarp();
             // every lane is done with this tile's record: fetch the next one into the same buffer
@@ -586,9 +503,9 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         }
         if (HVS_TRACE_ON && p.dbg && lane == 0)
             for (int q = 0; q < 8; ++q) p.dbg[((size_t)blockIdx.x * 4 + cw) * 8 + q] = tacc[q];
-        // dalpha: sum the 8 tokens of the warp (part 0 lanes) in a fixed order; dbias comes from the workers
+        // dalpha: sum the 8 tokens of the warp (row-0 lanes; the others hold 0) in a fixed order; dbias comes from the workers
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
+        for (int o = 4; o < 32; o <<= 1) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], o);
         }
@@ -662,7 +579,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             if (lane < 8) reinterpret_cast<float*>(smem + kOffWrec + s * kWrecBytes)[lane * 16 + q * 4 + jcol] = sum;
             __threadfence_block();
             bar_arrive(kBarRec + s, kWorkerThreads + 32);
-            if (threadIdx.x == 64) HVS_TR(tile, 2);
+            if (wtid == 64) HVS_TR(tile, 2);
         };
         // Worker schedule: dx of tile k as soon as its coefficients are done.  Every warp also moves its part of a
         // finished G out of tensor memory the moment it completes -- while they wait, and between
@@ -679,15 +596,15 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 // ============ dx for tokens 2t, 2t+1 of tile k, channels 32w + 4g .. +3 of every stream
                 const int k = d_next++;
                 const int s = k % kStages;
-                while (!mbar_try_wait_ns(&bar_cd[s], (uint32_t)(k / kStages) & 1u, HVS_POLL_NS)) g_poll();   // (acquires the coefficient warp's stores)
-                if (threadIdx.x == 0) HVS_TR(k, 7);
+                while (!mbar_try_wait(&bar_cd[s], (uint32_t)(k / kStages) & 1u)) g_poll();   // (acquires the coefficient warp's stores)
+                if (wtid == 0) HVS_TR(k, 7);
                 const uint32_t sb = stage0 + s * kStageBytes;
                 uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
-                if (threadIdx.x < kTok * kL) {
+                if (wtid < kTok * kL) {
                     // e = alpha_g * inv_rms * d logit of (token, logit) = (tid / 24, tid % 24): bf16 hi for the W e MMA,
                     // hi and lo into the E tile of the dW MMA (rows = logits, K = token | 8 + token); dbias in registers
-                    const int etok = threadIdx.x / kL, er = threadIdx.x - etok * kL;
-                    const float dlv = reinterpret_cast<const float*>(smem + kOffDl + s * kDlBytes)[threadIdx.x];
+                    const int etok = wtid / kL, er = wtid - etok * kL;
+                    const float dlv = reinterpret_cast<const float*>(smem + kOffDl + s * kDlBytes)[wtid];
                     const float e = dlv * reinterpret_cast<const float*>(wrec + kWrecS)[etok * 3 + (er < kN ? 0 : er < 2 * kN ? 1 : 2)];
                     acc_db += dlv;
                     const __nv_bfloat16 hi = __float2bfloat16_rn(e);
@@ -701,7 +618,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     fence_proxy_async_smem();               // the E tile is read by the tensor core (async proxy)
                 }
                 bar_sync(kBarW, kWorkerThreads);
-                if (threadIdx.x == 0) mbar_arrive(&bar_ed[s]);
+                if (wtid == 0) mbar_arrive(&bar_ed[s]);
                 const uint32_t* ew = reinterpret_cast<const uint32_t*>(wrec) + g * 12;
                 const uint32_t eb0 = ew[t], eb1 = ew[t + 4], eb2 = ew[t + 8];     // e[g][2t..], e[g][2t+8..], e[g][2t+16..]
                 const float2 kp = *reinterpret_cast<const float2*>(wrec + kWrecK + 8 * t);
@@ -715,18 +632,12 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 }
 #pragma unroll
                 for (int jj = 0; jj < kN; ++jj) {
-#ifndef HVS_EXP_NOPOLL
                     g_poll();
-#endif
                     const float4* mq = reinterpret_cast<const float4*>(wrec + kWrecM + t * (kMpStride * 4)) + jj * 2;
                     const float4 m01 = mq[0], m23 = mq[1];                        // (M_a[0],M_b[0],M_a[1],M_b[1]) (M_a[2],...)
                     const u64 mp[kN] = {pk2(m01.x, m01.y), pk2(m01.z, m01.w), pk2(m23.x, m23.y), pk2(m23.z, m23.w)};
                     uint32_t w8[4];
-#ifdef HVS_EXP_NOWLD
-                    w8[0] = w8[1] = w8[2] = w8[3] = 0u;
-#else
                     tmem_ld4(tm_w + 4u * jj, w8);
-#endif
                     const uint2 xa = lds64(sb + offa0 + jj * 8192);
                     const uint2 xb = lds64(sb + offb0 + jj * 8192);
                     uint32_t oa[2], ob[2];
@@ -759,25 +670,25 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_dxr[s]);
-                if (threadIdx.x == 0) HVS_TR(k, 8);
+                if (wtid == 0) HVS_TR(k, 8);
             }
         }
         // ============ dbias of this CTA: fold the 8 tokens in a fixed order
         {
             float* red = reinterpret_cast<float*>(smem + kOffPart);
-            if (threadIdx.x < kTok * kL) red[threadIdx.x] = acc_db;
+            if (wtid < kTok * kL) red[wtid] = acc_db;
             bar_sync(kBarW, kWorkerThreads);
-            if (threadIdx.x < kL) {
+            if (wtid < kL) {
                 float v = 0.f;
 #pragma unroll
-                for (int tt = 0; tt < kTok; ++tt) v += red[tt * kL + threadIdx.x];
-                p.cta_accum[(size_t)blockIdx.x * kCoefWarps * kAccum + threadIdx.x] = v;
+                for (int tt = 0; tt < kTok; ++tt) v += red[tt * kL + wtid];
+                p.cta_accum[(size_t)blockIdx.x * kCoefWarps * kAccum + wtid] = v;
             }
         }
         // ============ dW of this CTA out of tensor memory (every MMA has been committed before the last barrier phase)
         {
             const int last = n_local - 1;
-            mbar_wait_q(&bar_dw[last % kStages], (uint32_t)(last / kStages) & 1u);
+            mbar_wait(&bar_dw[last % kStages], (uint32_t)(last / kStages) & 1u);
             tc_fence_after();
             float* out = p.dw_part + (size_t)blockIdx.x * kRow * kL;
 #pragma unroll
