@@ -215,7 +215,6 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 // dW += x^T E for the tile whose coefficients are ready: 16 blocks of 128 channels,
                 // K = 16 = the 8 token rows twice (stride 0) against [E_hi ; E_lo]
                 mbar_wait(&bar_ed[s], ph);
-                if (leader) HVS_TR(k, 9);
                 HVS_FTICK(2);
                 tc_fence_after();
                 // M = 128 channels (two atoms, 1 KB apart), N = 32 = 24 logits + 8 zero rows: the accumulators sit 24 columns
@@ -354,6 +353,15 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             }
             if (lane == 0) HVS_TR(it, 4);
             HVS_TICK(2);
+            // gathered while the tile is still in flight: all four rows of K (this lane's own among them) and the four H_pre
+            u64 KR[4][2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                KR[k][0] = __shfl_sync(0xffffffffu, K01, qb + k);
+                KR[k][1] = __shfl_sync(0xffffffffu, K23, qb + k);
+            }
+            const float hp0 = __shfl_sync(0xffffffffu, hpre, qb), hp1 = __shfl_sync(0xffffffffu, hpre, qb + 1);
+            const float hp2 = __shfl_sync(0xffffffffu, hpre, qb + 2), hp3 = __shfl_sync(0xffffffffu, hpre, qb + 3);
             // ---- G = dy x^T of the landed tile on the tensor core.  Every tcgen05.mma costs ~55 cycles whatever its shape,
             //      so the 512 channels go in as two halves side by side: A rows = (stream, half, token) of dy, B rows = the
             //      same of x (row groups 4 KB apart), K = the 256 channels of a half: 16 MMAs of 64 x 64; the read-out adds
@@ -380,6 +388,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                         if (lane == 0) umma_bf16_ss(tmem_base + kColGs, ydesc0 + o, xdesc0 + o, id_gs, (uint32_t)((c4 | ks) != 0));
                     }
                 if (lane == 0) umma_commit(&bar_gs[s]);
+                if (lane == 0) HVS_TR(it, 9);
             }
             bar_sync(kBarRec + s, kWorkerThreads + 32);
             HVS_TICK(3);
@@ -388,8 +397,6 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             __syncwarp();                                   // every lane has its G row: M may overwrite the record
             float dl_pre, dl_post;
             {
-                const float hp0 = __shfl_sync(0xffffffffu, hpre, qb), hp1 = __shfl_sync(0xffffffffu, hpre, qb + 1);
-                const float hp2 = __shfl_sync(0xffffffffu, hpre, qb + 2), hp3 = __shfl_sync(0xffffffffu, hpre, qb + 3);
                 const float dhpost = fmaf(g.w, hp3, fmaf(g.z, hp2, fmaf(g.y, hp1, g.x * hp0)));
                 dl_post = dhpost * hpost * (1.0f - 0.5f * hpost);
                 const u64 hq2 = pk2(hpost, hpost);
@@ -452,10 +459,17 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     upk2(ubp, ua, ub_);
                     const float sb = -(ua + ub_) * (uu * uu);
                     ubp = pk2(0.f, 0.f);
-                    // vb = K^T sb ;  dK += sb v_{k-1}^T
+                    // vb = K^T sb ;  dK += sb v_{k-1}^T.  The four sb of the token are gathered in ONE shuffle step (independent
+                    // shuffles) and every lane forms the whole column sum from its copy of K -- the two dependent steps of a
+                    // butterfly sum were the longest link of the iteration.
                     const u64 s2 = pk2(sb, sb);
-                    vb01 = quad_sum2(mul2(K01, s2));
-                    vb23 = quad_sum2(mul2(K23, s2));
+                    {
+                        const float t0 = __shfl_sync(0xffffffffu, sb, qb), t1 = __shfl_sync(0xffffffffu, sb, qb + 1);
+                        const float t2 = __shfl_sync(0xffffffffu, sb, qb + 2), t3 = __shfl_sync(0xffffffffu, sb, qb + 3);
+                        const u64 q0 = pk2(t0, t0), q1 = pk2(t1, t1), q2 = pk2(t2, t2), q3 = pk2(t3, t3);
+                        vb01 = add2(fma2(KR[1][0], q1, mul2(KR[0][0], q0)), fma2(KR[3][0], q3, mul2(KR[2][0], q2)));
+                        vb23 = add2(fma2(KR[1][1], q1, mul2(KR[0][1], q0)), fma2(KR[3][1], q3, mul2(KR[2][1], q2)));
+                    }
                     dK0 = fma2(vp01, s2, dK0);
                     dK1 = fma2(vp23, s2, dK1);
                 }
