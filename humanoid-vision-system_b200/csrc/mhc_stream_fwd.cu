@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "mhc_stream_shared.cuh"
 #include "ptx_sm100.cuh"
+#include "umma_sm100.cuh"
 
 namespace hvs {
 namespace {
@@ -34,7 +35,9 @@ constexpr int kOffPart = kStages * kStageBytes;
 constexpr int kOffRed = kOffPart + kWorkers * kTileTok * kPartStride * 4;
 constexpr int kOffCoef = kOffRed + 2 * kTileTok * kRedStride * 4;
 constexpr int kOffBar = kOffCoef + 2 * kTileTok * kCoefStride * 4;
-constexpr int kSmemBytes = kOffBar + 2 * kStages * 8;
+constexpr int kOffTmem = kOffBar + 2 * kStages * 8;
+constexpr int kSmemBytes = kOffTmem + 16;
+constexpr uint32_t kTmemCols = 128;                // 32 columns per worker thread: half of its projection fragments (below)
 static_assert(kOffBar % 8 == 0, "mbarrier alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
@@ -62,6 +65,52 @@ __device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {
 __device__ __forceinline__ void upk2(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// Sinkhorn-Knopp on a 4x4 block spread over 4 adjacent lanes (this lane: row i = lane & 3, logits in p0..p3, result
+// in p0..p3), iterated on the SCALINGS: P_k = diag(u_k) K diag(v_k) with K = 4 softmax(logits),
+//   u_k = 1 / (K v_{k-1} + eps),  v_k = 1 / (K^T u_k + eps)
+// which is the reference's P / (sum + eps) up to eps * (1/u - 1) ~ 1e-8 relative.  Each lane keeps all of K (gathered
+// once), so an iteration needs ONE shuffle step (the four u) instead of the two dependent steps of a butterfly column
+// sum -- the chain of 20 iterations is what bounds the forward kernel.
+__device__ __forceinline__ void sinkhorn_row_lane_scaled(float& p0, float& p1, float& p2, float& p3, int iters, float eps) {
+    const int gbase = (threadIdx.x & 31) & ~3;
+    u64 K01, K23;
+    {
+        const float mx = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
+        const float e0 = fast_exp(p0 - mx), e1 = fast_exp(p1 - mx), e2 = fast_exp(p2 - mx), e3 = fast_exp(p3 - mx);
+        const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
+        K01 = pk2(e0 * r4, e1 * r4);
+        K23 = pk2(e2 * r4, e3 * r4);
+    }
+    u64 KR[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        KR[k][0] = __shfl_sync(0xffffffffu, K01, gbase + k);
+        KR[k][1] = __shfl_sync(0xffffffffu, K23, gbase + k);
+    }
+    const u64 eps2 = pk2(eps, eps);
+    u64 v01 = pk2(1.f, 1.f), v23 = v01;
+    float u = 1.f;
+    for (int it = 0; it < iters; ++it) {
+        float ra, rb;
+        upk2(fma2(K23, v23, mul2(K01, v01)), ra, rb);
+        u = rcp_approx((ra + rb) + eps);
+        const float u0 = __shfl_sync(0xffffffffu, u, gbase), u1 = __shfl_sync(0xffffffffu, u, gbase + 1);
+        const float u2 = __shfl_sync(0xffffffffu, u, gbase + 2), u3 = __shfl_sync(0xffffffffu, u, gbase + 3);
+        const u64 q0 = pk2(u0, u0), q1 = pk2(u1, u1), q2 = pk2(u2, u2), q3 = pk2(u3, u3);
+        const u64 c01 = add2(add2(fma2(KR[1][0], q1, mul2(KR[0][0], q0)), fma2(KR[3][0], q3, mul2(KR[2][0], q2))), eps2);
+        const u64 c23 = add2(add2(fma2(KR[1][1], q1, mul2(KR[0][1], q0)), fma2(KR[3][1], q3, mul2(KR[2][1], q2))), eps2);
+        float c0, c1, c2, c3;
+        upk2(c01, c0, c1); upk2(c23, c2, c3);
+        v01 = pk2(rcp_approx(c0), rcp_approx(c1));
+        v23 = pk2(rcp_approx(c2), rcp_approx(c3));
+    }
+    const u64 uu = pk2(u, u);
+    upk2(mul2(mul2(K01, v01), uu), p0, p1);
+    upk2(mul2(mul2(K23, v23), uu), p2, p3);
+}
 
 __device__ __forceinline__ float sum_sq8(uint4 v) {
     float s = 0.f, a;
@@ -94,7 +143,12 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
         fence_mbar_init();
     }
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+    if (warp == kWorkers + 3) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
 
     if (warp >= kWorkers) {
       // one warpgroup: coefficient warp, producer warp, two idle warps; hands registers to the workers
@@ -128,6 +182,7 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             }
             bulk_wait<0>();
         }
+        __syncwarp();                                  // the warp reaches the closing barrier as one
       } else if (warp == kWorkers || warp == kWorkers + 2) {
         // ===================================================== 2 coefficient warps, 8 tokens each,
         // 4 lanes per token: lane i of a group owns row i of the 4x4 block (and gate i of H_pre / H_post).
@@ -147,7 +202,7 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             float p1 = fmaf(a_res, r[2 * kN + 4 * i + 1] * inv_rms, b_res.y);
             float p2 = fmaf(a_res, r[2 * kN + 4 * i + 2] * inv_rms, b_res.z);
             float p3 = fmaf(a_res, r[2 * kN + 4 * i + 3] * inv_rms, b_res.w);
-            sinkhorn_row_lane(p0, p1, p2, p3, p.sk_iters, p.eps_sk);
+            sinkhorn_row_lane_scaled(p0, p1, p2, p3, p.sk_iters, p.eps_sk);
             // M = H_res + H_post (x) H_pre needs all four H_pre of the token
             const int gbase = lane & ~3;
             const float h0 = __shfl_sync(0xffffffffu, hpre, gbase + 0), h1 = __shfl_sync(0xffffffffu, hpre, gbase + 1);
@@ -156,6 +211,12 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             *reinterpret_cast<float4*>(c + 4 * i) =
                 make_float4(fmaf(hpost, h0, p0), fmaf(hpost, h1, p1), fmaf(hpost, h2, p2), fmaf(hpost, h3, p3));
             c[16 + i] = hpre;
+            // the raw statistics of the record are re-read before the hand-off (the buffer is the workers' again after
+            // it); the global stores come after it: the workers are waiting
+            const float sv_pre = r[i], sv_post = r[kN + i], sv_ss = r[kL];
+            const float4 sv_res = make_float4(r[2 * kN + 4 * i], r[2 * kN + 4 * i + 1], r[2 * kN + 4 * i + 2], r[2 * kN + 4 * i + 3]);
+            __threadfence_block();
+            bar_arrive(kBarCoef + buf, kWorkerThreads + 64);
             const int64_t tok = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTileTok + tl;
             if (p.coeffs != nullptr && tok < p.T) {
                 float* o = p.coeffs + tok * kL;
@@ -165,14 +226,11 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             }
             if (p.saved != nullptr && tok < p.T) {
                 float* o = p.saved + tok * HVS_MHC_SAVED_STRIDE;
-                o[i] = r[i];
-                o[kN + i] = r[kN + i];
-                *reinterpret_cast<float4*>(o + 2 * kN + 4 * i) =
-                    make_float4(r[2 * kN + 4 * i], r[2 * kN + 4 * i + 1], r[2 * kN + 4 * i + 2], r[2 * kN + 4 * i + 3]);
-                o[kL + i] = i == 0 ? r[kL] : 0.f;
+                o[i] = sv_pre;
+                o[kN + i] = sv_post;
+                *reinterpret_cast<float4*>(o + 2 * kN + 4 * i) = sv_res;
+                o[kL + i] = i == 0 ? sv_ss : 0.f;
             }
-            __threadfence_block();
-            bar_arrive(kBarCoef + buf, kWorkerThreads + 64);
         }
       }
     } else {
@@ -200,6 +258,17 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     bfrag[j][q][nt][1] = pack_bf16(f[2], f[3]);
                 }
             }
+        // The second k-step of every stream (24 of the 48 registers) is parked in tensor memory and fetched when needed
+        // (tcgen05.ld, 8 columns per stream): with the shared-memory carve-out there is no L1, so the 18 registers the
+        // compiler would otherwise spill cost an L2 round trip per tile.
+        const uint32_t tm_b = tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + 32u * (uint32_t)(w >> 2);
+#pragma unroll
+        for (int j = 0; j < kN; ++j) {
+            const uint32_t v[8] = {bfrag[j][1][0][0], bfrag[j][1][0][1], bfrag[j][1][1][0], bfrag[j][1][1][1],
+                                   bfrag[j][1][2][0], bfrag[j][1][2][1], 0u, 0u};
+            tmem_st8(tm_b + 8 * j, v);
+        }
+        tmem_wait_st();
         // swizzled byte offsets of this thread's 16-byte chunk in rows (token g, stream j); token g+8: +4096
         const int cb = w >> 1, hh = w & 1;
         uint32_t off[kN];
@@ -280,13 +349,15 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             for (int j = 0; j < kN; ++j) {
                 const uint4 xa = lds128(sbase + off[j]);
                 const uint4 xb = lds128(sbase + off[j] + 4096);
+                uint32_t bq[8];
+                tmem_ld8(tm_b + 8 * j, bq);
                 ssa += sum_sq8(xa);
                 ssb += sum_sq8(xb);
 #pragma unroll
-                for (int nt = 0; nt < 3; ++nt) {
-                    mma_bf16_16816(acc[nt], xa.x, xb.x, xa.y, xb.y, bfrag[j][0][nt][0], bfrag[j][0][nt][1]);
-                    mma_bf16_16816(acc[nt], xa.z, xb.z, xa.w, xb.w, bfrag[j][1][nt][0], bfrag[j][1][nt][1]);
-                }
+                for (int nt = 0; nt < 3; ++nt) mma_bf16_16816(acc[nt], xa.x, xb.x, xa.y, xb.y, bfrag[j][0][nt][0], bfrag[j][0][nt][1]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt) mma_bf16_16816(acc[nt], xa.z, xb.z, xa.w, xb.w, bq[2 * nt], bq[2 * nt + 1]);
             }
             ssa += __shfl_xor_sync(0xffffffffu, ssa, 1); ssa += __shfl_xor_sync(0xffffffffu, ssa, 2);
             ssb += __shfl_xor_sync(0xffffffffu, ssb, 1); ssb += __shfl_xor_sync(0xffffffffu, ssb, 2);
@@ -320,6 +391,9 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
         if (n_local > 0) mix_tile(n_local - 1);
     }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWorkers + 3) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------
