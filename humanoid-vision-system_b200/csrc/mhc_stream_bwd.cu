@@ -625,27 +625,39 @@ mhc_stream_dw_kernel(const __grid_constant__ CUtensorMap tmap_xt, const float* _
 }
 
 // dphi = scale * dW, dscale = sum_k phi * dW (straight-through the bf16 rounding of scale*phi),
-// dbias / dalpha from the B1 per-CTA partials.  Fixed summation order over CTAs.
-__global__ void __launch_bounds__(256)
+// dphi / dscale from the per-CTA dW partials, dbias / dalpha from the per-CTA accumulators.  Fixed summation order
+// (eight interleaved partial sums over the CTAs, combined pairwise), so the result is bitwise reproducible.
+// One CTA = 8 rows x 24 columns, one element per thread: every load of a warp is 128 contiguous bytes.
+constexpr int kFinRows = 8;
+__global__ void __launch_bounds__(kFinRows * kL)
 mhc_stream_bwd_finalize_kernel(const float* __restrict__ dw_part, int dw_ctas, const float* __restrict__ cta_accum,
                                int acc_ctas, const float* __restrict__ phi, const float* __restrict__ scale,
                                float* __restrict__ dphi, float* __restrict__ dscale, float* __restrict__ dbias,
                                float* __restrict__ dalpha) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row < kRow) {
-        float dwv = 0.f;
-        if (lane < kL)
-            for (int c = 0; c < dw_ctas; ++c) dwv += dw_part[((size_t)c * kRow + row) * kL + lane];
-        float ds = lane < kL ? dwv * phi[(size_t)row * kL + lane] : 0.f;
-        if (lane < kL) dphi[(size_t)row * kL + lane] = dwv * scale[row];
+    __shared__ float prod[kFinRows * kL];
+    const size_t idx = (size_t)blockIdx.x * (kFinRows * kL) + threadIdx.x;      // element of the [2048, 24] matrix
+    const float* src = dw_part + idx;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int c = 0;
+    for (; c + 8 <= dw_ctas; c += 8) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
-        if (lane == 0) dscale[row] = ds;
+        for (int u = 0; u < 8; ++u) acc[u] += src[(size_t)(c + u) * kRow * kL];
+    }
+    for (int u = 0; c < dw_ctas; ++c, ++u) acc[u] += src[(size_t)c * kRow * kL];
+    const float dwv = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    const int row = (int)(idx / kL);
+    dphi[idx] = dwv * scale[row];
+    prod[threadIdx.x] = dwv * phi[idx];
+    __syncthreads();
+    if (threadIdx.x < kFinRows) {
+        float ds = 0.f;
+#pragma unroll
+        for (int l = 0; l < kL; ++l) ds += prod[threadIdx.x * kL + l];
+        dscale[blockIdx.x * kFinRows + threadIdx.x] = ds;
     }
     if (blockIdx.x == 0 && threadIdx.x < kAccum) {
         float s0 = 0.f;
-        for (int c = 0; c < acc_ctas; ++c) s0 += cta_accum[(size_t)c * kAccum + threadIdx.x];
+        for (int k = 0; k < acc_ctas; ++k) s0 += cta_accum[(size_t)k * kAccum + threadIdx.x];
         if (threadIdx.x < kL) dbias[threadIdx.x] = s0; else dalpha[threadIdx.x - kL] = s0;
     }
 }
@@ -672,7 +684,7 @@ BwdWs carve(void* base, int64_t T, int ctas) {
 // shared with the fused (saved-statistics) backward in mhc_stream_bwd_fused.cu
 int launch_bwd_finalize(const float* dw_part, int dw_ctas, const float* cta_accum, int acc_ctas, const float* phi,
                         const float* scale, float* dphi, float* dscale, float* dbias, float* dalpha, cudaStream_t stream) {
-    mhc_stream_bwd_finalize_kernel<<<kRow / 8, 256, 0, stream>>>(dw_part, dw_ctas, cta_accum, acc_ctas, phi, scale, dphi,
+    mhc_stream_bwd_finalize_kernel<<<kRow / kFinRows, kFinRows * kL, 0, stream>>>(dw_part, dw_ctas, cta_accum, acc_ctas, phi, scale, dphi,
                                                                  dscale, dbias, dalpha);
     count_launch();
     return launch_status();
@@ -745,7 +757,7 @@ extern "C" int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* ph
         if (rc2) return rc2;
     }
     timer_begin(3, stream);
-    mhc_stream_bwd_finalize_kernel<<<kRow / 8, 256, 0, stream>>>(ws.dw_part, grid2, ws.cta_accum, kCoefWarps * grid1, phi, scale, dphi,
+    mhc_stream_bwd_finalize_kernel<<<kRow / kFinRows, kFinRows * kL, 0, stream>>>(ws.dw_part, grid2, ws.cta_accum, kCoefWarps * grid1, phi, scale, dphi,
                                                                  dscale, dbias, dalpha);
     timer_end(3, stream);
     count_launch();

@@ -90,18 +90,18 @@ __device__ __forceinline__ void sinkhorn_row_lane_scaled(float& p0, float& p1, f
         KR[k][0] = __shfl_sync(0xffffffffu, K01, gbase + k);
         KR[k][1] = __shfl_sync(0xffffffffu, K23, gbase + k);
     }
-    const u64 eps2 = pk2(eps, eps);
+    const u64 eps2 = pk2(eps, eps), eps0 = pk2(eps, 0.f);
     u64 v01 = pk2(1.f, 1.f), v23 = v01;
     float u = 1.f;
     for (int it = 0; it < iters; ++it) {
         float ra, rb;
-        upk2(fma2(K23, v23, mul2(K01, v01)), ra, rb);
-        u = rcp_approx((ra + rb) + eps);
+        upk2(fma2(K23, v23, fma2(K01, v01, eps0)), ra, rb);                 // eps rides the first product (one dependent add less)
+        u = rcp_approx(ra + rb);
         const float u0 = __shfl_sync(0xffffffffu, u, gbase), u1 = __shfl_sync(0xffffffffu, u, gbase + 1);
         const float u2 = __shfl_sync(0xffffffffu, u, gbase + 2), u3 = __shfl_sync(0xffffffffu, u, gbase + 3);
         const u64 q0 = pk2(u0, u0), q1 = pk2(u1, u1), q2 = pk2(u2, u2), q3 = pk2(u3, u3);
-        const u64 c01 = add2(add2(fma2(KR[1][0], q1, mul2(KR[0][0], q0)), fma2(KR[3][0], q3, mul2(KR[2][0], q2))), eps2);
-        const u64 c23 = add2(add2(fma2(KR[1][1], q1, mul2(KR[0][1], q0)), fma2(KR[3][1], q3, mul2(KR[2][1], q2))), eps2);
+        const u64 c01 = add2(fma2(KR[1][0], q1, fma2(KR[0][0], q0, eps2)), fma2(KR[3][0], q3, mul2(KR[2][0], q2)));
+        const u64 c23 = add2(fma2(KR[1][1], q1, fma2(KR[0][1], q0, eps2)), fma2(KR[3][1], q3, mul2(KR[2][1], q2)));
         float c0, c1, c2, c3;
         upk2(c01, c0, c1); upk2(c23, c2, c3);
         v01 = pk2(rcp_approx(c0), rcp_approx(c1));
