@@ -95,20 +95,28 @@ uint64_t hvs_launch_count(void) { return hvs::g_launches.load(std::memory_order_
 
 int hvs_mhc_stream_profile(int enable) {
     hvs::g_timer.enabled = enable != 0;
-    for (int i = 0; i < 4; ++i) hvs::g_timer.used[i] = false;
+    if (enable)
+        for (int i = 0; i < 4; ++i) hvs::g_timer.count[i] = 0;
     return HVS_OK;
 }
 
 int hvs_mhc_stream_kernel_ms(float* out4_host) {
     if (!out4_host) return HVS_ERR_BAD_ARG;
+    using hvs::KernelTimer;
     for (int i = 0; i < 4; ++i) {
         out4_host[i] = -1.0f;
-        if (hvs::g_timer.used[i]) {
-            cudaError_t e = cudaEventSynchronize(hvs::g_timer.end[i]);
+        const int n = hvs::g_timer.count[i] < KernelTimer::kRing ? hvs::g_timer.count[i] : KernelTimer::kRing;
+        if (n == 0) continue;
+        double sum = 0.0;
+        for (int k = 0; k < n; ++k) {
+            cudaError_t e = cudaEventSynchronize(hvs::g_timer.end[i][k]);
             if (e != cudaSuccess) return (int)e;
-            e = cudaEventElapsedTime(&out4_host[i], hvs::g_timer.beg[i], hvs::g_timer.end[i]);
+            float ms = 0.f;
+            e = cudaEventElapsedTime(&ms, hvs::g_timer.beg[i][k], hvs::g_timer.end[i][k]);
             if (e != cudaSuccess) return (int)e;
+            sum += ms;
         }
+        out4_host[i] = (float)(sum / n);
     }
     return HVS_OK;
 }

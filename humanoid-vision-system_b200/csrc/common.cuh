@@ -38,22 +38,25 @@ inline int launch_status() {
     return e == cudaSuccess ? HVS_OK : (int)e;
 }
 
-// Optional event bracketing of individual launches (hvs_mhc_stream_profile).
+// Optional event bracketing of individual launches (hvs_mhc_stream_profile): a ring of event pairs per kernel slot,
+// read back (one synchronisation) by hvs_mhc_stream_kernel_ms -- the host never waits inside the profiled region.
 struct KernelTimer {
-    cudaEvent_t beg[4] = {nullptr, nullptr, nullptr, nullptr}, end[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool used[4] = {false, false, false, false};
+    static constexpr int kRing = 128;
+    cudaEvent_t beg[4][kRing] = {}, end[4][kRing] = {};
+    int count[4] = {0, 0, 0, 0};                       // launches recorded since profiling was switched on
     bool enabled = false;
 };
 extern KernelTimer g_timer;
 inline void timer_begin(int slot, cudaStream_t s) {
     if (!g_timer.enabled) return;
-    if (!g_timer.beg[slot]) { cudaEventCreate(&g_timer.beg[slot]); cudaEventCreate(&g_timer.end[slot]); }
-    cudaEventRecord(g_timer.beg[slot], s);
+    const int i = g_timer.count[slot] % KernelTimer::kRing;
+    if (!g_timer.beg[slot][i]) { cudaEventCreate(&g_timer.beg[slot][i]); cudaEventCreate(&g_timer.end[slot][i]); }
+    cudaEventRecord(g_timer.beg[slot][i], s);
 }
 inline void timer_end(int slot, cudaStream_t s) {
     if (!g_timer.enabled) return;
-    cudaEventRecord(g_timer.end[slot], s);
-    g_timer.used[slot] = true;
+    cudaEventRecord(g_timer.end[slot][g_timer.count[slot] % KernelTimer::kRing], s);
+    ++g_timer.count[slot];
 }
 
 // 2-D bf16 tensor map: [rows][cols] row-major, box [box_rows][64 cols] (=128 B inner), 128-byte swizzle.

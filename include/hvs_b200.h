@@ -101,10 +101,12 @@ int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const float* saved, 
                              void* stream);
 
 /* Optional per-kernel timing of the stream-mHC launches (used by bench.py for the roofline line).
- * When enabled, each launch is bracketed by CUDA events on the launching stream;
- * hvs_mhc_stream_kernel_ms synchronises those events and returns the durations in ms of the LAST
- * call of each entry point: out[0] forward kernel, out[1] backward per-token kernel,
- * out[2] backward x^T E reduction kernel, out[3] backward finalize kernel (negative = not run). */
+ * When enabled, each launch is bracketed by CUDA events on the launching stream (a ring of 128 event
+ * pairs per kernel; enabling resets it).  Nothing waits on the host while launches are recorded;
+ * hvs_mhc_stream_kernel_ms synchronises the recorded events and returns the MEAN duration in ms of
+ * the (last 128) launches of each kernel since profiling was enabled: out[0] forward kernel,
+ * out[1] backward per-token / fused kernel, out[2] backward x^T E reduction kernel (two-kernel
+ * path), out[3] backward finalize kernel (negative = not run). */
 int hvs_mhc_stream_profile(int enable);
 int hvs_mhc_stream_kernel_ms(float* out4_host);
 
