@@ -68,13 +68,13 @@ int make_tmap_bf16_streams3d(CUtensorMap* out, const void* gptr, uint64_t tokens
 
 // 4-D view of [T, 4, 512] bf16 as (channel in a 64-channel block, token, block, stream): ONE box of
 // 64 x box_tokens x 8 x 4 lands as 32 swizzle atoms [stream][block][token][64 channels] (32 KB for 8 tokens).
-int make_tmap_bf16_streams4d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens) {
+int make_tmap_bf16_streams4d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens, uint32_t box_streams) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return HVS_ERR_DRIVER;
     cudaFree(nullptr);
     cuuint64_t gdim[4] = {64, tokens, 8, 4};
     cuuint64_t gstride[3] = {4096, 128, 1024};  // bytes: token, 64-channel block, stream
-    cuuint32_t box[4] = {64, box_tokens, 8, 4};
+    cuuint32_t box[4] = {64, box_tokens, 8, box_streams};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gptr), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

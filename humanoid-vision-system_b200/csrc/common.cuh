@@ -63,7 +63,7 @@ inline void timer_end(int slot, cudaStream_t s) {
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 // 3-D (channel, token, stream) view of [T,4,512] bf16: box = 64 channels x box_tokens x 4 streams, 128-byte swizzle.
 int make_tmap_bf16_streams3d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens);
-// 4-D (channel-in-block, token, block, stream) view: one box = 64 x box_tokens x 8 blocks x 4 streams.
-int make_tmap_bf16_streams4d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens);
+// 4-D (channel-in-block, token, block, stream) view: one box = 64 x box_tokens x 8 blocks x box_streams streams.
+int make_tmap_bf16_streams4d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens, uint32_t box_streams = 4);
 
 }  // namespace hvs

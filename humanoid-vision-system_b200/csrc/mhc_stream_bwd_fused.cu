@@ -58,7 +58,7 @@ constexpr int kDlBytes = 768;
 constexpr int kOffPart = kOffDl + kStages * kDlBytes;             // end-of-kernel dbias fold: [8 tokens][24] fp32
 constexpr int kOffBias = kOffPart + kTok * kL * 4;                // bias[24] staged once (float4 broadcast reads)
 constexpr int kOffBar = kOffBias + 128;
-constexpr int kOffTmem = kOffBar + 8 * kStages * 8;
+constexpr int kOffTmem = kOffBar + (7 * kStages + 4 * kStages + 1) * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kOffBar % 8 == 0 && kOffSaved % 16 == 0 && kOffWrec % 16 == 0 && kOffEt % 128 == 0 && kOffSk % 16 == 0 && kOffDl % 16 == 0, "alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -128,8 +128,8 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     if (smem_u32(smem) & 1023u) __trap();
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffBar);     // tile + saved records landed
     uint64_t* bar_ed = bar_full + kStages;                                // E tile written (worker warps)
-    uint64_t* bar_dxr = bar_ed + kStages;                                 // dx staged by the workers
-    uint64_t* bar_dw = bar_dxr + kStages;                                 // dW MMAs of the tile complete
+    uint64_t* bar_dxr = bar_ed + kStages;                                 // [stage][stream] dx of one output stream staged by the workers
+    uint64_t* bar_dw = bar_dxr + kN * kStages;                            // dW MMAs of the tile complete
     uint64_t* bar_sv = bar_dw + kStages;                                  // saved records of the stage's next tile landed
     uint64_t* bar_cd = bar_sv + kStages;                                  // coefficients of the tile written (coefficient warp)
     uint64_t* bar_gs = bar_cd + kStages;                                  // G MMAs of the tile complete
@@ -145,7 +145,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_ed[s], 1);
-            mbar_init(&bar_dxr[s], kWorkerThreads);
+            for (int j = 0; j < kN; ++j) mbar_init(&bar_dxr[s * kN + j], kWorkerThreads);
             mbar_init(&bar_dw[s], 1);
             mbar_init(&bar_sv[s], 1);
             mbar_init(&bar_cd[s], 32);
@@ -231,12 +231,16 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                                      b == 15 ? bdesc_last : bdesc, id_dw, 1u);
                 if (leader) umma_commit(&bar_dw[s]);
                 HVS_FTICK(3);
-                // dx of the tile (written in place over dy) -> HBM
-                mbar_wait(&bar_dxr[s], ph);
-                if (leader) {
-                    HVS_TR(k, 10);
-                    tma_store_4d(&tmap_dx, smem + s * kStageBytes + kHalf, 0, tok0, 0, 0);
-                    bulk_commit();
+                // dx of the tile (written in place over dy) -> HBM, one output stream at a time while the dx pass is still
+                // working on the next: when the pass ends only the last 8 KB are left to drain before dy can be re-loaded
+#pragma unroll
+                for (int j = 0; j < kN; ++j) {
+                    mbar_wait(&bar_dxr[s * kN + j], ph);
+                    if (leader) {
+                        if (j == kN - 1) HVS_TR(k, 10);
+                        tma_store_4d(&tmap_dx, smem + s * kStageBytes + kHalf + j * 8192, 0, tok0, 0, j);
+                        bulk_commit();
+                    }
                 }
                 HVS_FTICK(4);
                 mbar_wait(&bar_dw[s], ph);                       // the tensor core is done reading x of this stage
@@ -680,10 +684,10 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     }
                     sts64(sb + kHalf + offa0 + jj * 8192, oa[0], oa[1]);
                     sts64(sb + kHalf + offb0 + jj * 8192, ob[0], ob[1]);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&bar_dxr[s * kN + jj]);
                 }
                 }
-                fence_proxy_async_smem();
-                mbar_arrive(&bar_dxr[s]);
                 if (wtid == 0) HVS_TR(k, 8);
             }
         }
@@ -788,7 +792,7 @@ extern "C" int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const flo
         if (rc) return rc;
         rc = make_tmap_bf16_streams4d(&tdy, dy, (uint64_t)T, kTok);
         if (rc) return rc;
-        rc = make_tmap_bf16_streams4d(&tdx, dx, (uint64_t)T, kTok);
+        rc = make_tmap_bf16_streams4d(&tdx, dx, (uint64_t)T, kTok, 1);      // dx leaves one stream (8 KB) at a time
         if (rc) return rc;
         static bool attr_set = false;
         if (!attr_set) {
