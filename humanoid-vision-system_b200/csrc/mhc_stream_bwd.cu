@@ -626,28 +626,37 @@ mhc_stream_dw_kernel(const __grid_constant__ CUtensorMap tmap_xt, const float* _
 
 // dphi = scale * dW, dscale = sum_k phi * dW (straight-through the bf16 rounding of scale*phi),
 // dphi / dscale from the per-CTA dW partials, dbias / dalpha from the per-CTA accumulators.  Fixed summation order
-// (eight interleaved partial sums over the CTAs, combined pairwise), so the result is bitwise reproducible.
-// One CTA = 8 rows x 24 columns, one element per thread: every load of a warp is 128 contiguous bytes.
-constexpr int kFinRows = 8;
-__global__ void __launch_bounds__(kFinRows * kL)
+// (four thread groups take a quarter of the CTAs each, eight interleaved partial sums per thread, combined pairwise),
+// so the result is bitwise reproducible.  One CTA = 8 rows x 24 columns x 4 groups; every load of a warp is 128
+// contiguous bytes and 32 loads per element are in flight (the kernel is latency-bound: 29 MB behind 148-deep sums).
+constexpr int kFinRows = 8, kFinGroups = 4;
+__global__ void __launch_bounds__(kFinRows * kL * kFinGroups)
 mhc_stream_bwd_finalize_kernel(const float* __restrict__ dw_part, int dw_ctas, const float* __restrict__ cta_accum,
                                int acc_ctas, const float* __restrict__ phi, const float* __restrict__ scale,
                                float* __restrict__ dphi, float* __restrict__ dscale, float* __restrict__ dbias,
                                float* __restrict__ dalpha) {
+    __shared__ float part[kFinGroups][kFinRows * kL];
     __shared__ float prod[kFinRows * kL];
-    const size_t idx = (size_t)blockIdx.x * (kFinRows * kL) + threadIdx.x;      // element of the [2048, 24] matrix
+    const int e = threadIdx.x % (kFinRows * kL), grp = threadIdx.x / (kFinRows * kL);
+    const size_t idx = (size_t)blockIdx.x * (kFinRows * kL) + e;               // element of the [2048, 24] matrix
+    const int per = (dw_ctas + kFinGroups - 1) / kFinGroups;
+    const int c0 = grp * per, c1 = min(dw_ctas, c0 + per);
     const float* src = dw_part + idx;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int c = 0;
-    for (; c + 8 <= dw_ctas; c += 8) {
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc[u] += src[(size_t)(c + u) * kRow * kL];
     }
-    for (int u = 0; c < dw_ctas; ++c, ++u) acc[u] += src[(size_t)c * kRow * kL];
-    const float dwv = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-    const int row = (int)(idx / kL);
-    dphi[idx] = dwv * scale[row];
-    prod[threadIdx.x] = dwv * phi[idx];
+    for (int u = 0; c < c1; ++c, ++u) acc[u] += src[(size_t)c * kRow * kL];
+    part[grp][e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    __syncthreads();
+    if (grp == 0) {
+        const float dwv = (part[0][e] + part[1][e]) + (part[2][e] + part[3][e]);
+        const int row = (int)(idx / kL);
+        dphi[idx] = dwv * scale[row];
+        prod[e] = dwv * phi[idx];
+    }
     __syncthreads();
     if (threadIdx.x < kFinRows) {
         float ds = 0.f;
@@ -684,7 +693,7 @@ BwdWs carve(void* base, int64_t T, int ctas) {
 // shared with the fused (saved-statistics) backward in mhc_stream_bwd_fused.cu
 int launch_bwd_finalize(const float* dw_part, int dw_ctas, const float* cta_accum, int acc_ctas, const float* phi,
                         const float* scale, float* dphi, float* dscale, float* dbias, float* dalpha, cudaStream_t stream) {
-    mhc_stream_bwd_finalize_kernel<<<kRow / kFinRows, kFinRows * kL, 0, stream>>>(dw_part, dw_ctas, cta_accum, acc_ctas, phi, scale, dphi,
+    mhc_stream_bwd_finalize_kernel<<<kRow / kFinRows, kFinRows * kL * kFinGroups, 0, stream>>>(dw_part, dw_ctas, cta_accum, acc_ctas, phi, scale, dphi,
                                                                  dscale, dbias, dalpha);
     count_launch();
     return launch_status();
@@ -757,7 +766,7 @@ extern "C" int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* ph
         if (rc2) return rc2;
     }
     timer_begin(3, stream);
-    mhc_stream_bwd_finalize_kernel<<<kRow / kFinRows, kFinRows * kL, 0, stream>>>(ws.dw_part, grid2, ws.cta_accum, kCoefWarps * grid1, phi, scale, dphi,
+    mhc_stream_bwd_finalize_kernel<<<kRow / kFinRows, kFinRows * kL * kFinGroups, 0, stream>>>(ws.dw_part, grid2, ws.cta_accum, kCoefWarps * grid1, phi, scale, dphi,
                                                                  dscale, dbias, dalpha);
     timer_end(3, stream);
     count_launch();
