@@ -1,22 +1,27 @@
 // K1 backward for training, ONE fused kernel: dx and the parameter gradients in a single pass over x and dy
 // (every byte crosses HBM once).  The forward saved the un-normalised projection and the sum of squares per
 // token (hvs_mhc_stream_fwd_save, 112 B/token).  The two dense contractions go to the tcgen05 tensor cores with
-// accumulators in tensor memory, operands straight from the TMA-landed token tile:
-//   G = dy x^T (per-token 4x4)   tcgen05.mma  D[64x32] += [x rows ; dy rows] (64 x 16) * (x rows)^T, K-major operands
-//                                 (the 4x4 blocks are the token diagonal of the dy half of D)
-//   dW = x^T E (2048 x 24)       tcgen05.mma  D[64x24] += x-atom^T (MN-major A, read in place) * [E_hi ; E_lo]
-//                                 the two bf16 terms of E ride the two halves of K = 16 against the SAME eight
-//                                 token rows of x (stride-0 K step), accumulated over the whole kernel in 384
-//                                 tensor-memory columns (32 blocks of 64 channels, two per column range)
+// accumulators in tensor memory, operands straight from the TMA-landed token tile.  A small tcgen05.mma occupies
+// the tensor pipe ~55 cycles whatever its shape (tools/micro/umma.cu), so they are few and big, 32 per tile:
+//   G = dy x^T (per-token 4x4)   16 x tcgen05.mma D[64x64] += dy rows * (x rows)^T: the 512 channels as two halves side
+//                                 by side (rows = (stream, half, token), K = the 256 channels of a half); the read-out
+//                                 keeps the (half, token) diagonal and adds the halves
+//   dW = x^T E (2048 x 24)       16 x tcgen05.mma D[128x32] += x-atoms^T (MN-major A, read in place) * [E_hi ; E_lo]:
+//                                 the two bf16 terms of E ride the two halves of K = 16 against the SAME eight token
+//                                 rows of x (stride-0 K step); accumulated over the whole kernel in 384 tensor-memory
+//                                 columns (16 blocks of 128 channels, 24 columns apart: the 8 spare columns of N = 32
+//                                 add zeros to the neighbour)
 // Roles (640 threads, one CTA per SM, 3 stages of 8 tokens: x | dy = 64 KB each, one 4-D TMA box per tensor):
-//   front warp          (convergent; lane 0 issues) TMA loads, every tcgen05.mma in dependency order, TMA stores of
-//                       dx, stage recycling
-//   3 coefficient warps (one per stage, lane = token) forward Sinkhorn AHEAD of the tile from the saved record
-//                       (fetched by the warp itself), tracking the cumulative scalings; once G is there: gate
-//                       gradients, reverse sweep in the scaling form (no reciprocals), softmax / RMSNorm backward
-//   16 worker warps     G blocks out of tensor memory; e = d raw as bf16 hi/lo into the E operand tile, dbias;
-//                       dx = M^T dy + kappa x + W e   (W e on the warp MMA path, scale*phi resident in 48 registers
-//                       in A-fragment order; mixing in packed fp32x2 FMAs), written IN PLACE over dy, one rounding
+//   front warp          (convergent; lane 0 issues) TMA loads, the dW MMAs, TMA stores of dx (one output stream at
+//                       a time, during the dx pass), stage recycling
+//   3 coefficient warps (one per stage, four lanes per token) forward Sinkhorn AHEAD of the tile from the saved
+//                       record (fetched by the warp itself), tracking the cumulative scalings; the G MMAs when the tile
+//                       has landed; once G is there: gate gradients, reverse sweep in the scaling form (no reciprocals,
+//                       one shuffle step per iteration), softmax / RMSNorm backward
+//   16 worker warps     G out of tensor memory the moment it completes; e = d raw as bf16 hi/lo into the E operand
+//                       tile, dbias; dx = M^T dy + kappa x + W e   (W e on the warp MMA path, scale*phi in A-fragment
+//                       order: 32 registers + 16 parked in tensor memory; mixing in packed fp32x2 FMAs), written IN
+//                       PLACE over dy, one rounding
 // Oracle: autograd through oracle/mhc_ref.py::stream_mhc_forward (reference primitives
 // src/models/manifold_layers.py:56-77, :213-216, :449-456).
 #include "common.cuh"
