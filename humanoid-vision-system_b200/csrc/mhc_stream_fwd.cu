@@ -35,7 +35,7 @@ constexpr int kOffPart = kStages * kStageBytes;
 constexpr int kOffRed = kOffPart + kWorkers * kTileTok * kPartStride * 4;
 constexpr int kOffCoef = kOffRed + 2 * kTileTok * kRedStride * 4;
 constexpr int kOffBar = kOffCoef + 2 * kTileTok * kCoefStride * 4;
-constexpr int kOffTmem = kOffBar + 2 * kStages * 8;
+constexpr int kOffTmem = kOffBar + 3 * kStages * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 constexpr uint32_t kTmemCols = 128;                // 32 columns per worker thread: half of its projection fragments (below)
 static_assert(kOffBar % 8 == 0, "mbarrier alignment");
@@ -130,7 +130,7 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     float* red = reinterpret_cast<float*>(smem + kOffRed);
     float* coef = reinterpret_cast<float*>(smem + kOffCoef);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffBar);
-    uint64_t* bar_done = bar_full + kStages;          // workers finished with a stage (y written in place)
+    uint64_t* bar_done = bar_full + kStages;          // [stage][half] workers finished with 8 tokens of a stage (y written in place)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -139,7 +139,8 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_done[s], kWorkerThreads);
+            mbar_init(&bar_done[2 * s], kWorkerThreads);
+            mbar_init(&bar_done[2 * s + 1], kWorkerThreads);
         }
         fence_mbar_init();
     }
@@ -169,15 +170,19 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             for (int it = 0; it < kStages && it < n_local; ++it) load_tile(it);
             for (int it = 0; it < n_local; ++it) {
                 const int s = it % kStages;
-                mbar_wait(&bar_done[s], (it / kStages) & 1);
-                if (p.has_y) {
-                    const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * (kTileTok * kN);
+                // y leaves in two halves of 8 tokens (boxes of 32 rows): the first drains while the workers mix the second
+                const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * (kTileTok * kN);
 #pragma unroll
-                    for (int cb = 0; cb < kC / 64; ++cb)
-                        tma_store_2d(&tmap_y, smem + s * kStageBytes + cb * kBoxBytes, cb * 64, row0);
-                    bulk_commit();
-                    bulk_wait_read<0>();
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait(&bar_done[2 * s + half], (it / kStages) & 1);
+                    if (p.has_y) {
+#pragma unroll
+                        for (int cb = 0; cb < kC / 64; ++cb)
+                            tma_store_2d(&tmap_y, smem + s * kStageBytes + cb * kBoxBytes + half * 4096, cb * 64, row0 + half * 32);
+                        bulk_commit();
+                    }
                 }
+                if (p.has_y) bulk_wait_read<0>();
                 if (it + kStages < n_local) load_tile(it + kStages);
             }
             bulk_wait<0>();
@@ -331,9 +336,9 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     }
                     *reinterpret_cast<uint4*>(p.u + (tok0 + tl) * kC + 32 * w + 8 * t) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
                 }
+                if (p.has_y) fence_proxy_async_smem();
+                mbar_arrive(&bar_done[2 * (itp % kStages) + half]);
             }
-            if (p.has_y) fence_proxy_async_smem();
-            mbar_arrive(&bar_done[itp % kStages]);
         };
 
         for (int it = 0; it < n_local; ++it) {
@@ -470,7 +475,7 @@ extern "C" int hvs_mhc_stream_fwd_save(const void* x, const float* phi, const fl
     CUtensorMap tx, ty;
     int rc = make_tmap_bf16_2d(&tx, x, (uint64_t)T * kN, kC, 64);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(&ty, y ? y : x, (uint64_t)T * kN, kC, 64);
+    rc = make_tmap_bf16_2d(&ty, y ? y : x, (uint64_t)T * kN, kC, 32);      // y is stored in half tiles
     if (rc) return rc;
     FwdParams p;
     p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale;
