@@ -317,3 +317,33 @@ def test_fused_backward_full_size_properties():
     old = hvs_b200.ops.mhc_stream_bwd(x, dy, *P)
     assert ((a["dphi"] - old["dphi"]).norm() / old["dphi"].norm()).item() < 1e-4
     assert (a["dx"].float() - old["dx"].float()).abs().max().item() <= 2.0 ** -6 * old["dx"].float().abs().max().item()
+
+
+def test_kernel_timing_hooks():
+    """hvs_mhc_stream_profile / hvs_mhc_stream_kernel_ms: mean duration per kernel over the launches recorded since
+    profiling was enabled, read without waiting inside the profiled region; -1 for kernels that did not run."""
+    import ctypes
+    import hvs_b200
+    lib = hvs_b200._lib.load()
+    t = 1 << 14
+    x, phi, bias, al, scale = make_inputs(t)
+    X = x.cuda()
+    P = [p.cuda() for p in (phi, bias, al, scale)]
+    dy = torch.randn(t, 4, 512, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).cuda()
+    saved = hvs_b200.ops.new_saved(X)
+    assert lib.hvs_mhc_stream_profile(1) == 0
+    try:
+        for _ in range(3):
+            hvs_b200.ops.mhc_stream_fwd(X, *P, saved=saved)
+            hvs_b200.ops.mhc_stream_bwd_saved(X, dy, saved, *P)
+        buf = (ctypes.c_float * 4)()
+        assert lib.hvs_mhc_stream_kernel_ms(buf) == 0
+        fwd_ms, bwd_ms, dw_ms, fin_ms = list(buf)
+        assert 0.0 < fwd_ms < 5.0 and 0.0 < bwd_ms < 5.0 and 0.0 < fin_ms < 5.0
+        assert dw_ms == -1.0                       # the x^T E reduction kernel belongs to the two-kernel backward
+        # enabling again resets the ring
+        assert lib.hvs_mhc_stream_profile(1) == 0
+        assert lib.hvs_mhc_stream_kernel_ms(buf) == 0
+        assert list(buf) == [-1.0, -1.0, -1.0, -1.0]
+    finally:
+        lib.hvs_mhc_stream_profile(0)
