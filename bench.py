@@ -15,11 +15,13 @@ value        tokens/s (whole job) with x, dy resident in HBM, CUDA-event timed, 
 e2e          the same metric through the host-buffer entry (stream_mhc_fwd_bwd_host): pinned host x, dy
              -> H2D -> kernels -> D2H of y, dx and the parameter gradients, all inside the timed region
 roofline     dominant kernel (the fused single-pass backward, dx + every parameter gradient): algorithmic
-             12288 B/token over its own CUDA-event duration (hvs_mhc_stream_profile hooks), against
+             12288 B/token over its mean CUDA-event duration across the timed steps (hvs_mhc_stream_profile
+             hooks: events on the launching stream, read back after the timed region), against
              MEASURED_PEAKS.json.  The training forward also writes, and the backward reads, 112 B/token of
              saved statistics (1.1 % on top of the 20480 B/token; not counted in the algorithmic figure)
 cpu_baseline oracle/ (a port of the reference's PyTorch arithmetic) timed on the host cores, rank 0,
              N = 1 only, bounded sample of the same workload
+clocks       SM clock and throttle reasons sampled through NVML every 2 ms inside the timed region
 --impl reference   times that CPU implementation alone (the reference is pure PyTorch; its own modules
              cannot travel to the GPU box)
 """
