@@ -72,10 +72,11 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0,
 // in p0..p3), iterated on the SCALINGS: P_k = diag(u_k) K diag(v_k) with K = 4 softmax(logits),
 //   u_k = 1 / (K v_{k-1} + eps),  v_k = 1 / (K^T u_k + eps)
 // which is the reference's P / (sum + eps) up to eps * (1/u - 1) ~ 1e-8 relative.  Each lane keeps all of K (gathered
-// once), so an iteration needs ONE shuffle step (the four u) instead of the two dependent steps of a butterfly column
-// sum -- the chain of 20 iterations is what bounds the forward kernel.
+// once) and iterates the whole 4 + 4 scalings itself, so the loop has no cross-lane step at all -- the chain of 20
+// iterations is what bounds the forward kernel, and it shares its scheduler and the shuffle / shared-memory pipe
+// with four worker warps.  The lanes only differ in the row they start from and the row of P they return.
 __device__ __forceinline__ void sinkhorn_row_lane_scaled(float& p0, float& p1, float& p2, float& p3, int iters, float eps) {
-    const int gbase = (threadIdx.x & 31) & ~3;
+    const int gbase = (threadIdx.x & 31) & ~3, i = threadIdx.x & 3;
     u64 K01, K23;
     {
         const float mx = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
@@ -92,14 +93,17 @@ __device__ __forceinline__ void sinkhorn_row_lane_scaled(float& p0, float& p1, f
     }
     const u64 eps2 = pk2(eps, eps), eps0 = pk2(eps, 0.f);
     u64 v01 = pk2(1.f, 1.f), v23 = v01;
-    float u = 1.f;
+    float us[4] = {1.f, 1.f, 1.f, 1.f};
     for (int it = 0; it < iters; ++it) {
-        float ra, rb;
-        upk2(fma2(K23, v23, fma2(K01, v01, eps0)), ra, rb);                 // eps rides the first product (one dependent add less)
-        u = rcp_approx(ra + rb);
-        const float u0 = __shfl_sync(0xffffffffu, u, gbase), u1 = __shfl_sync(0xffffffffu, u, gbase + 1);
-        const float u2 = __shfl_sync(0xffffffffu, u, gbase + 2), u3 = __shfl_sync(0xffffffffu, u, gbase + 3);
-        const u64 q0 = pk2(u0, u0), q1 = pk2(u1, u1), q2 = pk2(u2, u2), q3 = pk2(u3, u3);
+        // every lane forms all four u from its copy of K (eps rides the first product): four reciprocals instead of one,
+        // but NO shuffle inside the loop -- under the workers' shared-memory traffic a shuffle step was the slowest link
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            float ra, rb;
+            upk2(fma2(KR[m][1], v23, fma2(KR[m][0], v01, eps0)), ra, rb);
+            us[m] = rcp_approx(ra + rb);
+        }
+        const u64 q0 = pk2(us[0], us[0]), q1 = pk2(us[1], us[1]), q2 = pk2(us[2], us[2]), q3 = pk2(us[3], us[3]);
         const u64 c01 = add2(fma2(KR[1][0], q1, fma2(KR[0][0], q0, eps2)), fma2(KR[3][0], q3, mul2(KR[2][0], q2)));
         const u64 c23 = add2(fma2(KR[1][1], q1, fma2(KR[0][1], q0, eps2)), fma2(KR[3][1], q3, mul2(KR[2][1], q2)));
         float c0, c1, c2, c3;
@@ -107,6 +111,7 @@ __device__ __forceinline__ void sinkhorn_row_lane_scaled(float& p0, float& p1, f
         v01 = pk2(rcp_approx(c0), rcp_approx(c1));
         v23 = pk2(rcp_approx(c2), rcp_approx(c3));
     }
+    const float u = i == 0 ? us[0] : i == 1 ? us[1] : i == 2 ? us[2] : us[3];
     const u64 uu = pk2(u, u);
     upk2(mul2(mul2(K01, v01), uu), p0, p1);
     upk2(mul2(mul2(K23, v23), uu), p2, p3);
@@ -200,7 +205,7 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             const int buf = it & 1;
             bar_sync(kBarRed + buf, kWorkerThreads + 64);
             const float* r = red + (buf * kTileTok + tl) * kRedStride;
-            const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(r[kL], 1.0f / kRow, p.eps_rms)));
+            const float inv_rms = rsqrtf(fmaf(r[kL], 1.0f / kRow, p.eps_rms));    // MUFU.RSQ: 2 ulp, far inside the 1e-5 budget
             const float hpre = sigmoid_f32(fmaf(a_pre, r[i] * inv_rms, b_pre));
             const float hpost = 2.0f * sigmoid_f32(fmaf(a_post, r[kN + i] * inv_rms, b_post));
             float p0 = fmaf(a_res, r[2 * kN + 4 * i + 0] * inv_rms, b_res.x);
