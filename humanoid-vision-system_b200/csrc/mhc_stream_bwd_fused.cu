@@ -56,7 +56,7 @@ constexpr int kWrecBytes = 1152, kWrecM = 384, kWrecK = 960, kWrecS = 992, kMpSt
 constexpr int kOffEt = kOffWrec + kStages * kWrecBytes;           // per stage: E tile, no swizzle: two K chunks (bf16 hi | lo of e over the 8 tokens) of
                                                                   // 5 row groups (8 rows x 16 B): zero | logits 0-7 | 8-15 | 16-23 | zero
 constexpr int kEtBytes = 1280, kEtChunk = 640, kEtRow0 = 128;
-constexpr int kSkWords = kTok * kMaxIters * 8;
+constexpr int kSkWords = kTok * (kMaxIters + 1) * 8;     // slot 0 = the scalings before the first iteration (ones)
 constexpr int kOffSk = kOffEt + kStages * kEtBytes;                 // per coefficient warp: scalings u | v of every Sinkhorn iteration
 constexpr int kOffDl = kOffSk + kCoefWarps * kSkWords * 4;        // per stage: d logits [8][24] fp32 (coefficient warp -> workers)
 constexpr int kDlBytes = 768;
@@ -288,6 +288,9 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         // scalings of every iteration: [iter][ u: 32 floats, lane-indexed | v: 8 tokens x 4 ]
         float* sku = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + lane;
         float* skv = reinterpret_cast<float*>(smem + kOffSk) + cw * kSkWords + 32 + tk * 4;
+        sku[0] = 1.f;                                      // slot 0: u_0 = v_0 = 1 (iteration k writes slot k + 1)
+        if (i4 == 0) *reinterpret_cast<float4*>(skv) = make_float4(1.f, 1.f, 1.f, 1.f);
+        __syncwarp();
         const float* rsv = reinterpret_cast<const float*>(smem + kOffSaved + s * kSavedBytes);
         uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
         auto fetch_saved = [&](int it) {                   // lane 0: the 8 saved records of tile `it` -> shared memory
@@ -352,11 +355,11 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     P23 = mul2(P23, rc23);
                     V01 = mul2(V01, rc01);
                     V23 = mul2(V23, rc23);
-                    sku[k * 64] = ui;
+                    sku[(k + 1) * 64] = ui;
                     if (i4 == 0) {
                         float v0, v1, v2, v3;
                         upk2(V01, v0, v1); upk2(V23, v2, v3);
-                        *reinterpret_cast<float4*>(skv + k * 64) = make_float4(v0, v1, v2, v3);
+                        *reinterpret_cast<float4*>(skv + (k + 1) * 64) = make_float4(v0, v1, v2, v3);
                     }
                 }
             }
@@ -424,24 +427,25 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             }
             if (lane == 0) HVS_TR(it, 5);
             HVS_TICK(4);
-            // ---- reverse sweep in the scaling form; dK accumulates row i4; ub / vb are the adjoints of the current u / v
+            // ---- reverse sweep in the scaling form; dK accumulates row i4; ub / vb are the adjoints of the current u / v.
+            //      This loop is the longest serial piece of a tile's life and its warp is short of issue slots, so it is
+            //      written for instruction count: the history is walked with two pointers (slot 0 holds the ones before the
+            //      first iteration: no special case for k = 0), and the signs are folded (tn = vb v^2 = -tb, ubn = -ub).
             u64 dK0, dK1;
             {
                 const int last = p.sk_iters - 1;
-                float un = 1.f;
-                float4 vn = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (last >= 0) {
-                    un = sku[last * 64];
-                    vn = *reinterpret_cast<const float4*>(skv + last * 64);
-                }
+                const float* pu = sku + (last + 1) * 64;                        // u_k | v_k of the iteration being undone
+                const float* pv = skv + (last + 1) * 64;
+                float un = *pu;
+                float4 vn = *reinterpret_cast<const float4*>(pv);
                 // adjoints of the output P = diag(u) K diag(v):  dK = G u v^T,  ub_i = sum_j G_ij K_ij v_j,  vb_j = sum_i G_ij K_ij u_i.
-                // ub is kept as a packed partial-sum pair (its two halves are added when it is consumed).
-                u64 ubp, vb01, vb23;
+                // ubn is kept as a packed partial-sum pair (its two halves are added when it is consumed).
+                u64 ubn, vb01, vb23;
                 {
                     const u64 v01 = pk2(vn.x, vn.y), v23 = pk2(vn.z, vn.w), ui = pk2(un, un);
                     const u64 g0 = pk2(g.x, g.y), g1 = pk2(g.z, g.w);
                     const u64 gk0 = mul2(g0, K01), gk1 = mul2(g1, K23);
-                    ubp = fma2(gk1, v23, mul2(gk0, v01));
+                    ubn = mul2(fma2(gk1, v23, mul2(gk0, v01)), pk2(-1.f, -1.f));
                     vb01 = quad_sum2(mul2(gk0, ui));
                     vb23 = quad_sum2(mul2(gk1, ui));
                     dK0 = mul2(mul2(g0, v01), ui);
@@ -449,25 +453,22 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 }
                 for (int k = last; k >= 0; --k) {
                     const float uu = un;
-                    const u64 v01 = pk2(vn.x, vn.y), v23 = pk2(vn.z, vn.w), nv01 = pk2(-vn.x, -vn.y), nv23 = pk2(-vn.z, -vn.w);
-                    if (k > 0) {                                                // u_{k-1}, v_{k-1}
-                        un = sku[(k - 1) * 64];
-                        vn = *reinterpret_cast<const float4*>(skv + (k - 1) * 64);
-                    } else {
-                        vn = make_float4(1.f, 1.f, 1.f, 1.f);                   // v_0
-                    }
+                    const u64 v01 = pk2(vn.x, vn.y), v23 = pk2(vn.z, vn.w);
+                    pu -= 64; pv -= 64;
+                    un = *pu;                                                   // u_{k-1}, v_{k-1}
+                    vn = *reinterpret_cast<const float4*>(pv);
                     const u64 vp01 = pk2(vn.x, vn.y), vp23 = pk2(vn.z, vn.w);
-                    // v_k = 1 / (K^T u_k):  tb = -vb v_k^2 ;  ub += K tb ;  dK += u_k tb^T
-                    const u64 tb01 = mul2(mul2(vb01, v01), nv01), tb23 = mul2(mul2(vb23, v23), nv23);
-                    const u64 ui = pk2(uu, uu);
-                    ubp = fma2(K23, tb23, fma2(K01, tb01, ubp));
-                    dK0 = fma2(tb01, ui, dK0);
-                    dK1 = fma2(tb23, ui, dK1);
-                    // u_k = 1 / (K v_{k-1}):  sb = -ub u_k^2
+                    // v_k = 1 / (K^T u_k):  tb = -vb v_k^2 = -tn ;  ub += K tb ;  dK += u_k tb^T
+                    const u64 tn01 = mul2(mul2(vb01, v01), v01), tn23 = mul2(mul2(vb23, v23), v23);
+                    const u64 nui = pk2(-uu, -uu);
+                    ubn = fma2(K23, tn23, fma2(K01, tn01, ubn));
+                    dK0 = fma2(tn01, nui, dK0);
+                    dK1 = fma2(tn23, nui, dK1);
+                    // u_k = 1 / (K v_{k-1}):  sb = -ub u_k^2 = ubn u_k^2
                     float ua, ub_;
-                    upk2(ubp, ua, ub_);
-                    const float sb = -(ua + ub_) * (uu * uu);
-                    ubp = pk2(0.f, 0.f);
+                    upk2(ubn, ua, ub_);
+                    const float sb = (ua + ub_) * (uu * uu);
+                    ubn = pk2(0.f, 0.f);
                     // vb = K^T sb ;  dK += sb v_{k-1}^T.  The four sb of the token are gathered in ONE shuffle step (independent
                     // shuffles) and every lane forms the whole column sum from its copy of K -- the two dependent steps of a
                     // butterfly sum were the longest link of the iteration.
