@@ -141,7 +141,9 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     uint64_t* bar_gr = bar_gs + kStages;                                  // G buffer read out by the 16 worker warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
-    const int warp = threadIdx.x >> 5;
+    // (the shuffle tells the compiler that the warp index is warp-uniform: everything derived from it -- stage addresses,
+    // tensor-core descriptors -- then lives in uniform registers instead of going through an elect / R2UR loop per MMA)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int wtid = threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
