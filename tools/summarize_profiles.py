@@ -84,21 +84,22 @@ if __name__ == "__main__":
             "r1d_bench_kernels.ncu-rep": ("r01d_bench_kernels_T1M.txt", "one step earlier than r01e: before the per-stream dx stores and the coalesced finalize; T=2^20"),
             "r1e_bench_kernels.ncu-rep": ("r01e_bench_kernels_T1M.txt", "one step earlier than r01f (forward before the half-tile y stores, finalize before the 4-group split); T=2^20"),
             "r1f_bench_kernels.ncu-rep": ("r01f_bench_kernels_T1M.txt", "one step earlier than r01g (forward with one shuffle step per Sinkhorn iteration, 1.60 ms); T=2^20"),
-            "r1g_bench_kernels.ncu-rep": ("r01g_bench_kernels_T1M.txt", "SHIPPED training path at T=2^20: forward (saving statistics; shuffle-free Sinkhorn on scalings, fragments parked in tensor memory, y in half tiles), fused single-pass backward, finalize")}
+            "r1g_bench_kernels.ncu-rep": ("r01g_bench_kernels_T1M.txt", "one step earlier than r01h (backward before the lean reverse sweep and the uniform warp index, 2.86 ms); T=2^20"),
+            "r1h_bench_kernels.ncu-rep": ("r01h_bench_kernels_T1M.txt", "SHIPPED training path at T=2^20: forward (saving statistics; shuffle-free Sinkhorn on scalings, fragments parked in tensor memory, y in half tiles), fused single-pass backward, finalize")}
     traffic = {}
     for rep, (out, note) in reps.items():
         path = os.path.join(g, rep)
         if not os.path.exists(path):
             continue
         res = summarize(path, out, note)
-        if rep == "r1g_bench_kernels.ncu-rep":
+        if rep == "r1h_bench_kernels.ncu-rep":
             for short, d in res:
                 def gb(k):
                     v, u = d[k]
                     return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
                 traffic[short + "_bytes_per_launch"] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
     if traffic:
-        traffic["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, T=2^20 (profiles/r01g_bench_kernels_T1M.txt)"
+        traffic["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, T=2^20 (profiles/r01h_bench_kernels_T1M.txt)"
         json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
     if os.path.exists(os.path.join(g, "r1_launches.csv")):
         launch_list(os.path.join(g, "r1_launches.csv"), "r01_launch_list.txt")
@@ -114,4 +115,6 @@ if __name__ == "__main__":
         launch_list(os.path.join(g, "r1f_launches.csv"), "r01f_launch_list.txt")
     if os.path.exists(os.path.join(g, "r1g_launches.csv")):
         launch_list(os.path.join(g, "r1g_launches.csv"), "r01g_launch_list.txt")
+    if os.path.exists(os.path.join(g, "r1h_launches.csv")):
+        launch_list(os.path.join(g, "r1h_launches.csv"), "r01h_launch_list.txt")
     print(open(os.path.join(OUT, "traffic.json")).read() if traffic else "no traffic")
