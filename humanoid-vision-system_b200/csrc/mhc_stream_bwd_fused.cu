@@ -323,6 +323,13 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             const float inv_rms = __fdiv_rn(1.0f, __fsqrt_rn(fmaf(valid ? r[kL] : 1.0f, 1.0f / kRow, p.eps_rms)));
             const float raw_pre = valid ? r[i4] : 0.f, raw_post = valid ? r[kN + i4] : 0.f;
             const float4 rr = valid ? *reinterpret_cast<const float4*>(r + 2 * kN + 4 * i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // the record now lives in registers: fetch the next tile's into the same buffer right away, a whole tile ahead of
+            // its use (fetched at the end of the tile it cost this warp 1.5 k cycles of HBM latency per tile)
+            __syncwarp();
+            if (lane == 0 && it + kCoefWarps < n_local) {
+                fence_proxy_async_smem();
+                fetch_saved(it + kCoefWarps);
+            }
             u64 K01, K23;                                  // row i4 of K = 4 softmax(logits): the Sinkhorn start
             {
                 const float l0 = fmaf(a_res, rr.x * inv_rms, b_res4.x), l1 = fmaf(a_res, rr.y * inv_rms, b_res4.y);
@@ -518,11 +525,6 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 *reinterpret_cast<float4*>(dq + 2 * kN + 4 * i4) = make_float4(d0, d1, d2, d3);
             }
             __syncwarp();
-            // every lane is done with this tile's record: fetch the next one into the same buffer
-            if (lane == 0 && it + kCoefWarps < n_local) {
-                fence_proxy_async_smem();
-                fetch_saved(it + kCoefWarps);
-            }
             mbar_arrive(&bar_cd[s]);                        // release: every lane's stores above are visible to the waiter
             if (lane == 0) HVS_TR(it, 6);
             HVS_TICK(6);
