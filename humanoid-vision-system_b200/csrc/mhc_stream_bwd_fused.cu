@@ -584,8 +584,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         // G of a tile out of tensor memory into its record: lanes 0..15 of quadrant q hold the rows (dy stream q, half
         // lane / 8, token lane % 8); a warp takes the columns of x stream jcol (both halves), keeps the (half, token)
         // diagonal and adds the halves.
-        auto g_tile = [&](int tile) {
-            const int s = tile % kStages;
+        auto g_tile = [&](int tile, int s) {
             tc_fence_after();
             // column lane % 16 of this lane's row, 8 columns at a time (a select tree on the lane bits; an indexed array
             // would go to the stack, and the stack is an L2 round trip away)
@@ -612,11 +611,15 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         // Worker schedule: dx of tile k as soon as its coefficients are done.  Every warp also moves its part of a
         // finished G out of tensor memory the moment it completes -- while they wait, and between
         // the four stream steps of a dx pass -- because that read-out heads the next tiles' coefficient chains.
-        int g_next = 0;
+        // (the poll sits in the dx pass's inner loop: barrier address and parity of the next tile are carried along
+        // instead of being derived from the tile index every time)
+        int g_next = 0, g_stage = 0;
+        uint32_t g_par = 0;
         auto g_poll = [&]() {
-            if (g_next < n_local && mbar_test_wait(&bar_gs[g_next % kStages], (uint32_t)(g_next / kStages) & 1u)) {
-                g_tile(g_next);
+            if (g_next < n_local && mbar_test_wait(&bar_gs[g_stage], g_par)) {
+                g_tile(g_next, g_stage);
                 ++g_next;
+                if (++g_stage == kStages) { g_stage = 0; g_par ^= 1u; }
             }
         };
         for (int d_next = 0; d_next < n_local;) {
