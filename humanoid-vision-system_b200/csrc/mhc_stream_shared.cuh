@@ -53,26 +53,6 @@ __device__ __forceinline__ void sinkhorn4x4(float (&pm)[16], int iters, float ep
     }
 }
 
-// The same projection with the 4x4 block spread over 4 adjacent lanes: this lane holds row i = lane & 3
-// (p0..p3).  Row sums are local, column sums take two xor-shuffles inside the 4-lane group.
-__device__ __forceinline__ void sinkhorn_row_lane(float& p0, float& p1, float& p2, float& p3, int iters, float eps) {
-    {
-        const float mx = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
-        const float e0 = fast_exp(p0 - mx), e1 = fast_exp(p1 - mx), e2 = fast_exp(p2 - mx), e3 = fast_exp(p3 - mx);
-        const float r4 = 4.0f * rcp_approx((e0 + e1) + (e2 + e3));
-        p0 = e0 * r4; p1 = e1 * r4; p2 = e2 * r4; p3 = e3 * r4;
-    }
-    for (int it = 0; it < iters; ++it) {
-        const float r = rcp_approx(((p0 + p1) + (p2 + p3)) + eps);
-        p0 *= r; p1 *= r; p2 *= r; p3 *= r;
-        float c0 = p0 + __shfl_xor_sync(0xffffffffu, p0, 1), c1 = p1 + __shfl_xor_sync(0xffffffffu, p1, 1);
-        float c2 = p2 + __shfl_xor_sync(0xffffffffu, p2, 1), c3 = p3 + __shfl_xor_sync(0xffffffffu, p3, 1);
-        c0 += __shfl_xor_sync(0xffffffffu, c0, 2); c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
-        c2 += __shfl_xor_sync(0xffffffffu, c2, 2); c3 += __shfl_xor_sync(0xffffffffu, c3, 2);
-        p0 *= rcp_approx(c0 + eps); p1 *= rcp_approx(c1 + eps); p2 *= rcp_approx(c2 + eps); p3 *= rcp_approx(c3 + eps);
-    }
-}
-
 // raw[24] = x . (scale*phi) un-normalised;  logits = alpha_g * (inv_rms * raw) + bias.
 __device__ __forceinline__ void coefficients_from_raw(const float (&raw)[kL], float inv_rms, const float (&bias)[kL],
                                                       float a_pre, float a_post, float a_res, int iters, float eps,

@@ -55,24 +55,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
-// try_wait that may stay suspended for up to `ns` nanoseconds (it still wakes as soon as the phase completes);
-// without the hint the suspension is so short that a waiting warp spins through its issue slots
-__device__ __forceinline__ bool mbar_try_wait_ns(uint64_t* bar, uint32_t parity, uint32_t ns) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, uint32_t ns) {
-    while (!mbar_try_wait_ns(bar, parity, ns)) {
-    }
-}
-
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
