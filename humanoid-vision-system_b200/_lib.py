@@ -17,6 +17,23 @@ HVS_MHC_SPLIT_PHI = 1
 HVS_MHC_SAVED_STRIDE = 28
 HVS_DTYPE_F32, HVS_DTYPE_F16, HVS_DTYPE_BF16 = 0, 1, 2
 HVS_NMS_AGNOSTIC, HVS_NMS_CLASS_AWARE, HVS_NMS_BOXES_XYXY = 0, 1, 16
+HVS_GEMM_EPI_NONE, HVS_GEMM_EPI_BIAS_GELU, HVS_GEMM_EPI_LAYERNORM = 0, 1, 2
+
+
+class CoeffJob(ctypes.Structure):
+    """struct hvs_coeff_job (include/hvs_b200.h)."""
+    _fields_ = [("h_pre_raw", c_void_p), ("h_post_raw", c_void_p), ("h_res_raw", c_void_p),
+                ("h_pre", c_void_p), ("h_post", c_void_p), ("h_res", c_void_p),
+                ("h_pre_t", c_void_p), ("h_post_t", c_void_p), ("h_res_t", c_void_p),
+                ("uv_history", c_void_p), ("convergence", c_void_p),
+                ("D", c_int32), ("H", c_int32), ("Dp", c_int32), ("reserved", c_int32)]
+
+
+class CoeffGrad(ctypes.Structure):
+    """struct hvs_coeff_grad."""
+    _fields_ = [("d_h_pre", c_void_p), ("d_h_post", c_void_p), ("d_h_res", c_void_p),
+                ("d_h_pre_raw", c_void_p), ("d_h_post_raw", c_void_p), ("d_h_res_raw", c_void_p)]
+
 
 # name -> (restype, argtypes); mirrors include/hvs_b200.h one to one
 _SIGNATURES = {
@@ -41,6 +58,19 @@ _SIGNATURES = {
     "hvs_sinkhorn": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "hvs_mhc_constrained_matrices": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                              c_int, c_float, c_void_p, c_void_p]),
+    "hvs_rmsnorm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_void_p]),
+    "hvs_rmsnorm_bwd_workspace": (c_size_t, [c_int64, c_int]),
+    "hvs_rmsnorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p,
+                                c_size_t, c_void_p]),
+    "hvs_layernorm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int,
+                                  c_int, c_float, c_void_p]),
+    "hvs_mhc_static_coeffs_workspace": (c_size_t, [POINTER(CoeffJob), c_int, c_int, c_int]),
+    "hvs_mhc_static_coeffs": (c_int, [POINTER(CoeffJob), c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "hvs_mhc_static_coeffs_bwd": (c_int, [POINTER(CoeffJob), POINTER(CoeffGrad), c_int, c_int, c_float, c_void_p, c_size_t,
+                                          c_void_p]),
+    "hvs_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p,
+                              c_void_p, c_float, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "hvs_profile_kernel_ms": (c_int, [POINTER(c_float)]),
     "hvs_yolo_decode": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hvs_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_int, c_int,
@@ -70,10 +100,18 @@ def load(build_if_missing: bool = True):
     path = _build.LIB_PATH
     if build_if_missing and not _build.is_fresh():
         try:
-            _build.build()
-        except Exception as exc:  # no nvcc on this box: use the prebuilt library if there is one
+            _build.have_nvcc()
+        except RuntimeError as exc:
+            # no compiler on this box: a prebuilt library that travelled with the tree is all there is
             if not os.path.exists(path):
                 raise HvsError(f"libhvs_b200.so is not built and cannot be built here: {exc}") from exc
+            import warnings
+            warnings.warn("hvs_b200: nvcc not found, loading the prebuilt libhvs_b200.so without a freshness check")
+        else:
+            try:
+                _build.build()                      # a compile error must surface, never fall back to a stale .so
+            except Exception as exc:
+                raise HvsError(f"building libhvs_b200.so failed: {exc}") from exc
     if not os.path.exists(path):
         raise HvsError(f"{path} not found; run `python -m hvs_b200.build`")
     lib = ctypes.CDLL(path)

@@ -12,7 +12,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhvs_b200.so")
 STAMP = os.path.join(PKG_DIR, "build", "sources.sha256")
 
-SOURCES = ["api_common.cu", "mhc_stream_fwd.cu", "mhc_stream_bwd.cu", "mhc_stream_bwd_fused.cu", "sinkhorn.cu", "yolo_decode.cu", "nms.cu", "umma_probe.cu"]
+SOURCES = ["api_common.cu", "mhc_stream_fwd.cu", "mhc_stream_bwd.cu", "mhc_stream_bwd_fused.cu", "sinkhorn.cu", "yolo_decode.cu", "nms.cu", "norm.cu", "k2_gemm.cu", "k2_coeffs.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -27,6 +27,11 @@ def _nvcc() -> str:
         if cand and os.path.exists(cand):
             return cand
     raise RuntimeError("nvcc not found")
+
+
+def have_nvcc() -> str:
+    """Path of nvcc, or RuntimeError when there is none."""
+    return _nvcc()
 
 
 def _fingerprint() -> str:

@@ -15,16 +15,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // function-local static: initialised exactly once, thread-safe (C++11), so a second thread (e.g. an autograd
+    // worker) can never observe a half-initialised lookup
+    static const EncodeTiledFn fn = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
+            return reinterpret_cast<EncodeTiledFn>(p);
+        return (EncodeTiledFn) nullptr;
+    }();
     return fn;
 }
 
@@ -44,6 +44,23 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
     if (r != CUDA_SUCCESS && getenv("HVS_DEBUG"))
         fprintf(stderr, "[hvs_b200] cuTensorMapEncodeTiled -> CUresult %d (ptr %p rows %llu cols %llu box_rows %u)\n", (int)r,
                 gptr, (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    return r == CUDA_SUCCESS ? HVS_OK : HVS_ERR_DRIVER;
+}
+
+int make_tmap_bf16_2d_ld(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return HVS_ERR_DRIVER;
+    cudaFree(nullptr);
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS && getenv("HVS_DEBUG"))
+        fprintf(stderr, "[hvs_b200] cuTensorMapEncodeTiled(ld) -> CUresult %d (ptr %p rows %llu cols %llu ld %llu box_rows %u)\n",
+                (int)r, gptr, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
     return r == CUDA_SUCCESS ? HVS_OK : HVS_ERR_DRIVER;
 }
 
@@ -94,16 +111,22 @@ int hvs_abi_version(void) { return 1; }
 uint64_t hvs_launch_count(void) { return hvs::g_launches.load(std::memory_order_relaxed); }
 
 int hvs_mhc_stream_profile(int enable) {
-    hvs::g_timer.enabled = enable != 0;
+    std::lock_guard<std::mutex> lock(hvs::g_timer.mu);
+    hvs::g_timer.enabled.store(enable != 0);
     if (enable)
-        for (int i = 0; i < 4; ++i) hvs::g_timer.count[i] = 0;
+        for (int i = 0; i < hvs::KernelTimer::kSlots; ++i) hvs::g_timer.count[i] = 0;
     return HVS_OK;
 }
 
-int hvs_mhc_stream_kernel_ms(float* out4_host) {
+static int kernel_ms(float* out_host, int slots);
+int hvs_mhc_stream_kernel_ms(float* out4_host) { return kernel_ms(out4_host, 4); }
+int hvs_profile_kernel_ms(float* out8_host) { return kernel_ms(out8_host, hvs::KernelTimer::kSlots); }
+
+static int kernel_ms(float* out4_host, int slots) {
     if (!out4_host) return HVS_ERR_BAD_ARG;
     using hvs::KernelTimer;
-    for (int i = 0; i < 4; ++i) {
+    std::lock_guard<std::mutex> lock(hvs::g_timer.mu);
+    for (int i = 0; i < slots; ++i) {
         out4_host[i] = -1.0f;
         const int n = hvs::g_timer.count[i] < KernelTimer::kRing ? hvs::g_timer.count[i] : KernelTimer::kRing;
         if (n == 0) continue;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "../../include/hvs_b200.h"
 
@@ -32,6 +33,25 @@ inline int sm_count() {
         if (_e != cudaSuccess) return (int)_e;  \
     } while (0)
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory ONCE PER DEVICE (the attribute is per device, and a
+// process may drive several GPUs).  `done` is the call site's own static flag array.
+template <class Kernel>
+inline int set_max_smem_once(Kernel kernel, int bytes, std::atomic<bool> (&done)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+    if (dev >= 0 && dev < 64 && done[dev].load(std::memory_order_acquire)) return HVS_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release);
+    return HVS_OK;
+}
+#define HVS_SET_MAX_SMEM(kernel, bytes)                                   \
+    do {                                                                  \
+        static std::atomic<bool> _hvs_done[64];                           \
+        const int _rc = hvs::set_max_smem_once(kernel, bytes, _hvs_done); \
+        if (_rc) return _rc;                                              \
+    } while (0)
+
 // Returns the launch status without clearing a sticky error of an earlier kernel.
 inline int launch_status() {
     cudaError_t e = cudaGetLastError();
@@ -42,25 +62,36 @@ inline int launch_status() {
 // read back (one synchronisation) by hvs_mhc_stream_kernel_ms -- the host never waits inside the profiled region.
 struct KernelTimer {
     static constexpr int kRing = 128;
-    cudaEvent_t beg[4][kRing] = {}, end[4][kRing] = {};
-    int count[4] = {0, 0, 0, 0};                       // launches recorded since profiling was switched on
-    bool enabled = false;
+    static constexpr int kSlots = 8;
+    cudaEvent_t beg[kSlots][kRing] = {}, end[kSlots][kRing] = {};
+    int count[kSlots] = {};                            // launches recorded since profiling was switched on
+    std::atomic<bool> enabled{false};
+    std::mutex mu;                                     // launches may come from several host threads / streams
 };
 extern KernelTimer g_timer;
+// begin reserves a ring entry under the lock and remembers it for this thread's matching timer_end
+inline int& timer_slot_index(int slot) {
+    thread_local int idx[KernelTimer::kSlots];
+    return idx[slot];
+}
 inline void timer_begin(int slot, cudaStream_t s) {
-    if (!g_timer.enabled) return;
-    const int i = g_timer.count[slot] % KernelTimer::kRing;
+    if (!g_timer.enabled.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_timer.mu);
+    const int i = g_timer.count[slot]++ % KernelTimer::kRing;
     if (!g_timer.beg[slot][i]) { cudaEventCreate(&g_timer.beg[slot][i]); cudaEventCreate(&g_timer.end[slot][i]); }
+    timer_slot_index(slot) = i;
     cudaEventRecord(g_timer.beg[slot][i], s);
 }
 inline void timer_end(int slot, cudaStream_t s) {
-    if (!g_timer.enabled) return;
-    cudaEventRecord(g_timer.end[slot][g_timer.count[slot] % KernelTimer::kRing], s);
-    ++g_timer.count[slot];
+    if (!g_timer.enabled.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_timer.mu);
+    cudaEventRecord(g_timer.end[slot][timer_slot_index(slot)], s);
 }
 
 // 2-D bf16 tensor map: [rows][cols] row-major, box [box_rows][64 cols] (=128 B inner), 128-byte swizzle.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+// same with an explicit row stride `ld` (elements) and any box height up to 256
+int make_tmap_bf16_2d_ld(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 // 3-D (channel, token, stream) view of [T,4,512] bf16: box = 64 channels x box_tokens x 4 streams, 128-byte swizzle.
 int make_tmap_bf16_streams3d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens);
 // 4-D (channel-in-block, token, block, stream) view: one box = 64 x box_tokens x 8 blocks x box_streams streams.

@@ -732,12 +732,8 @@ extern "C" int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* ph
         if (rc) return rc;
         rc = make_tmap_bf16_2d(&txt, x, (uint64_t)T, kRow, kDwTok);
         if (rc) return rc;
-        static bool attr_set = false;
-        if (!attr_set) {
-            HVS_CUDA_TRY(cudaFuncSetAttribute(mhc_stream_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-            HVS_CUDA_TRY(cudaFuncSetAttribute(mhc_stream_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
-            attr_set = true;
-        }
+        HVS_SET_MAX_SMEM(mhc_stream_bwd_kernel, kSmemBytes);
+        HVS_SET_MAX_SMEM(mhc_stream_dw_kernel, kDwSmemBytes);
         BwdParams p;
         p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale;
         p.e_out = ws.e; p.cta_accum = ws.cta_accum;

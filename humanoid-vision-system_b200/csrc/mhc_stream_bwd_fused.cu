@@ -765,12 +765,15 @@ FusedWs carve(void* base, int ctas) {
 }  // namespace
 }  // namespace hvs
 
-// development aid: device buffer [SMs, 3, 8] int64 receiving the coefficient warps' cycle counters (NULL = off)
+#ifdef HVS_FUSED_TRACE
+// development aid (trace builds only, tools/time_fused.py): device buffer [SMs, 3, 8] int64 receiving the
+// coefficient warps' cycle counters (NULL = off).  Not part of the shipped ABI.
 extern "C" int hvs_debug_fused_timing(void* device_buffer, int mode) {
     hvs::g_fused_dbg = reinterpret_cast<long long*>(device_buffer);
     (void)mode;
     return HVS_OK;
 }
+#endif
 
 extern "C" size_t hvs_mhc_stream_bwd_saved_workspace(int64_t T, int n, int C) {
     using namespace hvs;
@@ -807,11 +810,7 @@ extern "C" int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const flo
         if (rc) return rc;
         rc = make_tmap_bf16_streams4d(&tdx, dx, (uint64_t)T, kTok, 1);      // dx leaves one stream (8 KB) at a time
         if (rc) return rc;
-        static bool attr_set = false;
-        if (!attr_set) {
-            HVS_CUDA_TRY(cudaFuncSetAttribute(mhc_stream_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-            attr_set = true;
-        }
+        HVS_SET_MAX_SMEM(mhc_stream_bwd_fused_kernel, kSmemBytes);
         FusedParams p;
         p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale; p.saved = saved;
         p.dw_part = ws.dw_part; p.cta_accum = ws.cta_accum;

@@ -491,11 +491,7 @@ extern "C" int hvs_mhc_stream_fwd_save(const void* x, const float* phi, const fl
     p.num_tiles = (int)((T + kTileTok - 1) / kTileTok);
     p.sk_iters = sk_iters; p.eps_rms = eps_rms; p.eps_sk = eps_sk;
     p.has_y = y != nullptr;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HVS_CUDA_TRY(cudaFuncSetAttribute(mhc_stream_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_set = true;
-    }
+    HVS_SET_MAX_SMEM(mhc_stream_fwd_kernel, kSmemBytes);
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     timer_begin(0, (cudaStream_t)stream);
     mhc_stream_fwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tx, ty, p);

@@ -173,11 +173,7 @@ int launch_nms(const NmsArgs& a, int num_problems, int64_t max_n, cudaStream_t s
     if (max_n <= 4096) {
         nms_kernel<256><<<num_problems, 256, smem, stream>>>(a);
     } else {
-        static bool attr = false;
-        if (!attr) {
-            HVS_CUDA_TRY(cudaFuncSetAttribute(nms_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 * 4));
-            attr = true;
-        }
+        HVS_SET_MAX_SMEM(nms_kernel<1024>, 49152 * 4);
         nms_kernel<1024><<<num_problems, 1024, smem, stream>>>(a);
     }
     count_launch();

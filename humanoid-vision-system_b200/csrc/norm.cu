@@ -1,0 +1,211 @@
+// Row normalisations of the mHC path, one warp per row (rows are 32...4096 elements, i.e. L1-resident):
+//   RMSNorm.forward                         src/models/manifold_layers.py:449-456   x / sqrt(mean(x^2) + eps) * scale
+//   nn.LayerNorm around the module's token path (norm_pre :250, norm_post :267)
+// Statistics and arithmetic are fp32 whatever the storage type; the mean and the variance are two separate
+// passes over the (cached) row, so no E[x^2] - mean^2 cancellation.  Cross-row reductions (dscale) are two-stage
+// with a fixed order: bitwise reproducible.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace hvs {
+namespace {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p, int64_t i);
+template <> __device__ __forceinline__ float ldf<float>(const float* p, int64_t i) { return p[i]; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+template <typename T> __device__ __forceinline__ void stf(T* p, int64_t i, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, int64_t i, float v) { p[i] = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------------------- RMSNorm
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+rmsnorm_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ scale, TO* __restrict__ out, int64_t rows,
+                   int dim, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const TI* xr = x + r * dim;
+        float ss = 0.f;
+        for (int j = lane; j < dim; j += 32) { const float v = ldf(xr, j); ss = fmaf(v, v, ss); }
+        ss = wsum(ss);
+        const float rms = sqrtf(ss / (float)dim + eps);                 // :451
+        for (int j = lane; j < dim; j += 32) stf(out + r * dim, j, __fdiv_rn(ldf(xr, j), rms) * scale[j]);   // :454
+    }
+}
+
+// dx = scale*dy/rms - x * sum_j(dy_j scale_j x_j) / (dim rms^3);  dscale partial per CTA (fixed order inside the CTA)
+template <typename TI, typename TG>
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_kernel(const TI* __restrict__ x, const float* __restrict__ scale, const TG* __restrict__ dy,
+                   TG* __restrict__ dx, float* __restrict__ dscale_part, int64_t rows, int dim, float eps) {
+    extern __shared__ float sm_ds[];                                    // [8 warps][dim]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* mine = sm_ds + (size_t)w * dim;
+    for (int j = lane; j < dim; j += 32) mine[j] = 0.f;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + w;
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const TI* xr = x + r * dim;
+        const TG* gr = dy + r * dim;
+        float ss = 0.f, dot = 0.f;
+        for (int j = lane; j < dim; j += 32) {
+            const float v = ldf(xr, j);
+            ss = fmaf(v, v, ss);
+            dot = fmaf(ldf(gr, j) * scale[j], v, dot);
+        }
+        ss = wsum(ss);
+        dot = wsum(dot);
+        const float ms = ss / (float)dim + eps;
+        const float inv = rsqrtf(ms);
+        const float k = dot * inv / ((float)dim * ms);
+        for (int j = lane; j < dim; j += 32) {
+            const float v = ldf(xr, j), g = ldf(gr, j);
+            stf(dx + r * dim, j, g * scale[j] * inv - v * k);
+            mine[j] += g * v * inv;
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += sm_ds[(size_t)k * dim + j];
+        dscale_part[(size_t)blockIdx.x * dim + j] = s;
+    }
+}
+
+__global__ void colsum_finalize_kernel(const float* __restrict__ part, float* __restrict__ out, int parts, int dim) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    float s = 0.f;
+    for (int p = 0; p < parts; ++p) s += part[(size_t)p * dim + j];
+    out[j] = s;
+}
+
+// ---------------------------------------------------------------------------- LayerNorm (forward, K2 prologue / epilogue)
+// out = (x - mean) / sqrt(var + eps) * w + b; optionally also a plain bf16 copy of x (the A operand of x @ H_res),
+// both written into rows padded to `out_ld` / `copy_ld` elements (pad columns zero-filled so they can sit in a GEMM K).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                     TO* __restrict__ out, __nv_bfloat16* __restrict__ copy, int64_t rows, int dim, int out_ld,
+                     int copy_ld, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const TI* xr = x + r * dim;
+        float s = 0.f;
+        for (int j = lane; j < dim; j += 32) s += ldf(xr, j);
+        const float mean = wsum(s) / (float)dim;
+        float q = 0.f;
+        for (int j = lane; j < dim; j += 32) { const float d = ldf(xr, j) - mean; q = fmaf(d, d, q); }
+        const float inv = rsqrtf(wsum(q) / (float)dim + eps);
+        TO* o = out + r * out_ld;
+        for (int j = lane; j < out_ld; j += 32)
+            stf(o, j, j < dim ? (ldf(xr, j) - mean) * inv * w[j] + b[j] : 0.f);
+        if (copy != nullptr) {
+            __nv_bfloat16* c = copy + r * copy_ld;
+            for (int j = lane; j < copy_ld; j += 32) c[j] = __float2bfloat16_rn(j < dim ? ldf(xr, j) : 0.f);
+        }
+    }
+}
+
+inline int grid_for_rows(int64_t rows) {
+    int64_t blocks = (rows + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+}  // namespace hvs
+
+extern "C" int hvs_rmsnorm_fwd(const void* x, int x_dtype, const float* scale, void* out, int out_dtype, int64_t rows,
+                               int dim, float eps, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (rows < 0 || dim <= 0 || !scale) return HVS_ERR_BAD_ARG;
+    if (rows == 0) return HVS_OK;
+    if (!x || !out) return HVS_ERR_BAD_ARG;
+    const int g = grid_for_rows(rows);
+    if (x_dtype == HVS_DTYPE_F32 && out_dtype == HVS_DTYPE_F32)
+        rmsnorm_fwd_kernel<float, float><<<g, 256, 0, stream>>>((const float*)x, scale, (float*)out, rows, dim, eps);
+    else if (x_dtype == HVS_DTYPE_BF16 && out_dtype == HVS_DTYPE_BF16)
+        rmsnorm_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, scale, (__nv_bfloat16*)out, rows, dim, eps);
+    else if (x_dtype == HVS_DTYPE_BF16 && out_dtype == HVS_DTYPE_F32)
+        rmsnorm_fwd_kernel<__nv_bfloat16, float><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, scale, (float*)out, rows, dim, eps);
+    else if (x_dtype == HVS_DTYPE_F32 && out_dtype == HVS_DTYPE_BF16)
+        rmsnorm_fwd_kernel<float, __nv_bfloat16><<<g, 256, 0, stream>>>((const float*)x, scale, (__nv_bfloat16*)out, rows, dim, eps);
+    else
+        return HVS_ERR_UNSUPPORTED;
+    count_launch();
+    return launch_status();
+}
+
+extern "C" size_t hvs_rmsnorm_bwd_workspace(int64_t rows, int dim) {
+    if (rows < 0 || dim <= 0) return 0;
+    int64_t blocks = (rows + 7) / 8;
+    const int64_t cap = (int64_t)hvs::sm_count() * 2;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (size_t)blocks * dim * sizeof(float);
+}
+
+extern "C" int hvs_rmsnorm_bwd(const void* x, int dtype, const float* scale, const void* dy, void* dx, float* dscale,
+                               int64_t rows, int dim, float eps, void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (rows < 0 || dim <= 0 || !scale || !dscale) return HVS_ERR_BAD_ARG;
+    if (dim > 6144) return HVS_ERR_UNSUPPORTED;                       // 8 warps x dim floats of shared memory
+    if (rows > 0 && (!x || !dy || !dx)) return HVS_ERR_BAD_ARG;
+    const size_t need = hvs_rmsnorm_bwd_workspace(rows, dim);
+    if (!workspace || workspace_bytes < need) return HVS_ERR_WORKSPACE;
+    const int blocks = (int)(need / ((size_t)dim * sizeof(float)));
+    const int smem = 8 * dim * (int)sizeof(float);
+    float* part = (float*)workspace;
+    if (dtype == HVS_DTYPE_F32) {
+        HVS_SET_MAX_SMEM((rmsnorm_bwd_kernel<float, float>), 8 * 6144 * 4);
+        rmsnorm_bwd_kernel<float, float><<<blocks, 256, smem, stream>>>((const float*)x, scale, (const float*)dy, (float*)dx, part, rows, dim, eps);
+    } else if (dtype == HVS_DTYPE_BF16) {
+        HVS_SET_MAX_SMEM((rmsnorm_bwd_kernel<__nv_bfloat16, __nv_bfloat16>), 8 * 6144 * 4);
+        rmsnorm_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, smem, stream>>>((const __nv_bfloat16*)x, scale, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, part, rows, dim, eps);
+    } else {
+        return HVS_ERR_UNSUPPORTED;
+    }
+    colsum_finalize_kernel<<<(dim + 127) / 128, 128, 0, stream>>>(part, dscale, blocks, dim);
+    count_launch(2);
+    return launch_status();
+}
+
+extern "C" int hvs_layernorm_fwd(const void* x, int x_dtype, const float* weight, const float* bias, void* out, int out_dtype,
+                                 void* x_bf16_copy, int64_t rows, int dim, int out_ld, int copy_ld, float eps, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (rows < 0 || dim <= 0 || !weight || !bias || out_ld < dim || (x_bf16_copy && copy_ld < dim)) return HVS_ERR_BAD_ARG;
+    if (rows == 0) return HVS_OK;
+    if (!x || !out) return HVS_ERR_BAD_ARG;
+    const int g = grid_for_rows(rows);
+    __nv_bfloat16* cp = (__nv_bfloat16*)x_bf16_copy;
+    if (x_dtype == HVS_DTYPE_F32 && out_dtype == HVS_DTYPE_BF16)
+        layernorm_fwd_kernel<float, __nv_bfloat16><<<g, 256, 0, stream>>>((const float*)x, weight, bias, (__nv_bfloat16*)out, cp, rows, dim, out_ld, copy_ld, eps);
+    else if (x_dtype == HVS_DTYPE_BF16 && out_dtype == HVS_DTYPE_BF16)
+        layernorm_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, weight, bias, (__nv_bfloat16*)out, cp, rows, dim, out_ld, copy_ld, eps);
+    else if (x_dtype == HVS_DTYPE_F32 && out_dtype == HVS_DTYPE_F32)
+        layernorm_fwd_kernel<float, float><<<g, 256, 0, stream>>>((const float*)x, weight, bias, (float*)out, cp, rows, dim, out_ld, copy_ld, eps);
+    else if (x_dtype == HVS_DTYPE_BF16 && out_dtype == HVS_DTYPE_F32)
+        layernorm_fwd_kernel<__nv_bfloat16, float><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, weight, bias, (float*)out, cp, rows, dim, out_ld, copy_ld, eps);
+    else
+        return HVS_ERR_UNSUPPORTED;
+    count_launch();
+    return launch_status();
+}

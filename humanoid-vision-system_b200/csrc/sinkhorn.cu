@@ -4,8 +4,8 @@
 //   ManifoldHyperConnection.constrained_matrices                      :205-221
 // Two shapes of work: many tiny blocks (a warp per matrix, columns in lanes, rows in registers) and
 // one large D x D matrix per layer (a CTA per matrix, iterating in place on the L2-resident output).
-// Divisions are IEEE (the reference divides); reductions have a fixed order, so results are
-// bitwise reproducible run to run.
+// Divisions are IEEE (the reference divides); the reductions that produce `out` have a fixed order, so `out` is
+// bitwise reproducible run to run (the small-block convergence history, a diagnostic, sums with fp32 atomics).
 #include <math.h>
 
 #include "common.cuh"

@@ -23,17 +23,28 @@ from ._lib import HvsError
 
 
 # ----------------------------------------------------------------------------- K1
-FUSED_BWD_MAX_ITERS = 24      # the single-pass backward keeps every iteration's scalings in shared memory
+FUSED_BWD_MAX_ITERS = 24      # both backward kernels keep every iteration's scalings in shared memory
+FWD_MAX_ITERS = 64
+
+
+def _check_trainable_iters(sk_iters: int):
+    """The forward kernel takes up to 64 Sinkhorn iterations; the backward kernels (fused single-pass and the
+    two-kernel recompute form alike) differentiate at most 24.  Reject a training call up front instead of
+    failing inside autograd after the forward has run."""
+    if sk_iters > FUSED_BWD_MAX_ITERS:
+        raise HvsError(f"stream mHC training supports sk_iterations <= {FUSED_BWD_MAX_ITERS} "
+                       f"(got {sk_iters}); inference (no grad) supports up to {FWD_MAX_ITERS}")
 
 
 class _StreamMHCFn(torch.autograd.Function):
     """Training path.  The forward additionally writes 112 B/token of statistics (un-normalised projection and
     sum of squares); the backward is then ONE fused kernel (dx and every parameter gradient in a single pass over
-    x and dy).  With more than 24 Sinkhorn iterations the two-kernel backward that recomputes everything is used."""
+    x and dy).  sk_iters <= 24 (checked before the forward runs)."""
 
     @staticmethod
     def forward(ctx, x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk):
-        fused = sk_iters <= FUSED_BWD_MAX_ITERS
+        _check_trainable_iters(sk_iters)
+        fused = True
         saved = ops.new_saved(x) if fused else None
         y, _, _ = ops.mhc_stream_fwd(x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk, saved=saved)
         if fused:
@@ -86,7 +97,11 @@ class StreamMHC(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         shape = x.shape
         xf = x.reshape(-1, self.n_streams, self.channels).contiguous()
-        if self.fn is None:
+        needs_grad = torch.is_grad_enabled() and (xf.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if self.fn is None and not needs_grad:
+            y, _, _ = ops.mhc_stream_fwd(xf, self.phi, self.bias, self.alpha, self.rms_scale, self.sk_iterations,
+                                         self.eps, self.eps)
+        elif self.fn is None:
             y = _StreamMHCFn.apply(xf, self.phi, self.bias, self.alpha, self.rms_scale, self.sk_iterations,
                                    self.eps, self.eps)
         else:
@@ -108,13 +123,19 @@ def stream_mhc_fwd_bwd_host(x_host: torch.Tensor, dy_host: torch.Tensor, layer: 
     measured best on a B200 box: 181 ms for 2^20 tokens = 47.5 GB/s each way, against 49.9 GB/s for bare concurrent
     H2D + D2H copies of the same buffers (tools/e2e_sweep.py)."""
     dev = device or layer.phi.device
+    _check_trainable_iters(layer.sk_iterations)
     t = x_host.shape[0]
     n, c = layer.n_streams, layer.channels
     nchunks = (t + chunk_tokens - 1) // chunk_tokens
+    cur = torch.cuda.current_stream(dev)
     s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    # the caller may just have written the parameters (optimizer step) or be using memory the staging buffers
+    # will be carved from on its own stream: order the three side streams after it
+    for side in (s_in, s_cmp, s_out):
+        side.wait_stream(cur)
     bufs = [{k: torch.empty((chunk_tokens, n, c), dtype=torch.bfloat16, device=dev) for k in ("x", "dy", "y", "dx")}
             for _ in range(2)]
-    fused = layer.sk_iterations <= FUSED_BWD_MAX_ITERS
+    fused = True
     saved = [ops.new_saved(bufs[0]["x"]) for _ in range(2)] if fused else None
     ws = None
     if fused:
@@ -162,14 +183,49 @@ def stream_mhc_fwd_bwd_host(x_host: torch.Tensor, dy_host: torch.Tensor, layer: 
         for k, v in (acc or {}).items():
             out[k] = v.to("cpu", non_blocking=False)
     s_out.synchronize()
+    cur.wait_stream(s_out)                                   # staging buffers return to the caller's pool in order
     return out
 
 
 # ----------------------------------------------------------------------------- reference-signature modules
+def _pad64(v: int) -> int:
+    return (v + 63) // 64 * 64
+
+
+class _SquareSinkhornFn(torch.autograd.Function):
+    """Differentiable D x D projection: forward and backward are the batched static-coefficient kernels
+    (hvs_mhc_static_coeffs / _bwd) with a single job; no unrolled autograd graph."""
+
+    @staticmethod
+    def forward(ctx, raw, iters, eps, history):
+        d = raw.shape[0]
+        raw = raw.contiguous()
+        out = torch.empty_like(raw)
+        uv = torch.empty((iters + 1, 2, d), dtype=torch.float32, device=raw.device)
+        dummy = raw.new_zeros((d, 1))
+        ops.static_coeffs([{"h_pre_raw": dummy, "h_post_raw": None, "h_res_raw": raw, "h_res": out, "uv_history": uv,
+                            "convergence": history}], iters, eps)
+        ctx.save_for_backward(raw, uv)
+        ctx.cfg = (iters, eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        raw, uv = ctx.saved_tensors
+        iters, eps = ctx.cfg
+        d_raw = torch.empty_like(raw)
+        dummy = raw.new_zeros((raw.shape[0], 1))
+        ops.static_coeffs_bwd([{"h_pre_raw": dummy, "h_res_raw": raw, "h_res": d_raw, "uv_history": uv}],
+                              [{"d_h_res": g.contiguous().float(), "d_h_res_raw": d_raw}], iters, eps)
+        return d_raw, None, None, None
+
+
 class SinkhornKnoppProjection(nn.Module):
     """SinkhornKnoppProjection(num_iterations=20, epsilon=1e-8, tau=1.0)  (manifold_layers.py:25-101).
     ``forward`` runs hvs_sinkhorn; the ``convergence_history`` buffer is filled on the device without
-    the reference's 3 host synchronisations per iteration."""
+    the reference's 3 host synchronisations per iteration.  A square 2-D input that requires grad goes through
+    the static-coefficient kernels (forward + exact reverse sweep); only batched / non-square inputs that require
+    grad -- which no model in the reference has -- use the torch-op restatement below."""
 
     def __init__(self, num_iterations: int = 20, epsilon: float = 1e-8, tau: float = 1.0):
         super().__init__()
@@ -178,7 +234,10 @@ class SinkhornKnoppProjection(nn.Module):
 
     def forward(self, matrix: torch.Tensor, return_history: bool = False):
         if torch.is_grad_enabled() and matrix.requires_grad:
-            out = _sinkhorn_autograd(matrix, self.num_iterations, self.epsilon, self.tau)
+            if matrix.dim() == 2 and matrix.shape[0] == matrix.shape[1] and self.tau == 1.0 and matrix.dtype == torch.float32:
+                out = _SquareSinkhornFn.apply(matrix, self.num_iterations, self.epsilon, self.convergence_history)
+            else:
+                out = _sinkhorn_autograd(matrix, self.num_iterations, self.epsilon, self.tau)
         else:
             out = ops.sinkhorn(matrix.detach().float(), self.num_iterations, self.epsilon, self.tau,
                                history=self.convergence_history)
@@ -196,9 +255,8 @@ class SinkhornKnoppProjection(nn.Module):
 
 
 def _sinkhorn_autograd(matrix, iters, eps, tau):
-    """Differentiable D x D projection for TRAINING of the reference-literal module: same arithmetic in
-    torch device ops so autograd can unroll it.  (The fused CUDA backward exists for the per-token K1
-    path; a D x D backward kernel is listed as next work in DESIGN.md.)"""
+    """Batched / non-square projection that requires grad (not on any model's path): the reference arithmetic in
+    torch device ops."""
     squeeze = matrix.dim() == 2
     p = matrix.unsqueeze(0) if squeeze else matrix
     m = p.shape[-1]
@@ -209,8 +267,22 @@ def _sinkhorn_autograd(matrix, iters, eps, tau):
     return p.squeeze(0) if squeeze else p
 
 
+class _RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale, eps):
+        ctx.save_for_backward(x, scale)
+        ctx.eps = eps
+        return ops.rmsnorm_fwd(x, scale, eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale = ctx.saved_tensors
+        dx, dscale = ops.rmsnorm_bwd(x, scale, dy.to(x.dtype), ctx.eps)
+        return dx, dscale, None
+
+
 class RMSNorm(nn.Module):
-    """RMSNorm(dim, eps=1e-8) (manifold_layers.py:437-456)."""
+    """RMSNorm(dim, eps=1e-8) (manifold_layers.py:437-456); hvs_rmsnorm_fwd / _bwd (fp32 or bf16 data, fp32 stats)."""
 
     def __init__(self, dim: int, eps: float = 1e-8):
         super().__init__()
@@ -218,8 +290,89 @@ class RMSNorm(nn.Module):
         self.eps = eps
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        rms = torch.sqrt(torch.mean(x.pow(2), dim=-1, keepdim=True) + self.eps)
-        return x / rms * self.scale
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        if torch.is_grad_enabled() and (x.requires_grad or self.scale.requires_grad):
+            return _RMSNormFn.apply(x, self.scale, self.eps)
+        return ops.rmsnorm_fwd(x, self.scale.detach(), self.eps)
+
+
+class _CoeffState:
+    """Per-module device buffers of the static coefficient path (fp32 matrices, their bf16 transposed copies for the
+    GEMM B operands, the scaling history the backward consumes, bf16 copies of the MLP weights)."""
+
+    def __init__(self, mod: "ManifoldHyperConnection"):
+        d, h, dev = mod.input_dim, mod.hidden_dim, mod.H_res_raw.device
+        dp = _pad64(d)
+        it = mod.sinkhorn.num_iterations
+        f32, bf = torch.float32, torch.bfloat16
+        self.h_pre = torch.empty((d, h), dtype=f32, device=dev)
+        self.h_post = torch.empty((h, d), dtype=f32, device=dev)
+        self.h_res = torch.empty((d, d), dtype=f32, device=dev)
+        self.h_pre_t = torch.zeros((h, dp), dtype=bf, device=dev)
+        self.h_post_t = torch.zeros((d, h), dtype=bf, device=dev)
+        self.h_res_t = torch.zeros((d, dp), dtype=bf, device=dev)
+        self.uv_history = torch.empty((it + 1, 2, d), dtype=f32, device=dev)
+        self.w1 = self.w2 = None
+        self.key = None
+        self.wkey = None
+
+    def job(self, mod) -> Dict[str, Optional[torch.Tensor]]:
+        return {"h_pre_raw": mod.H_pre_raw.detach(), "h_post_raw": mod.H_post_raw.detach(), "h_res_raw": mod.H_res_raw.detach(),
+                "h_pre": self.h_pre, "h_post": self.h_post, "h_res": self.h_res, "h_pre_t": self.h_pre_t,
+                "h_post_t": self.h_post_t, "h_res_t": self.h_res_t, "uv_history": self.uv_history,
+                "convergence": mod.sinkhorn.convergence_history}
+
+
+def refresh_static_coefficients(model: nn.Module, force: bool = False) -> int:
+    """constrained_matrices (:205-221) of EVERY ManifoldHyperConnection under `model` whose parameters changed since
+    the last refresh, in ONE kernel launch (the reference recomputes each layer's, with 60 host syncs, on every
+    forward).  Returns the number of layers refreshed.  Called by the hybrid_vision harness before a forward / at the
+    top of a training step; a module whose cache is stale when its own forward runs refreshes itself."""
+    mods = [m for m in model.modules() if isinstance(m, ManifoldHyperConnection) and m.H_res_raw.is_cuda]
+    todo = [m for m in mods if force or m._state is None or m._state.key != m._key()]
+    groups: Dict[Tuple[Any, int, float], list] = {}
+    for m in todo:
+        groups.setdefault((m.H_res_raw.device, m.sinkhorn.num_iterations, m.sinkhorn.epsilon), []).append(m)
+    for (_, iters, eps), ms in groups.items():
+        jobs = []
+        for m in ms:
+            if m._state is None:
+                m._state = _CoeffState(m)
+            jobs.append(m._state.job(m))
+        ops.static_coeffs(jobs, iters, eps)
+        for m in ms:
+            m._state.key = m._key()
+    return len(todo)
+
+
+class _CoeffFn(torch.autograd.Function):
+    """(H_pre_raw, H_post_raw, H_res_raw) -> (H_pre, H_post, H_res) for training: forward reads the module's
+    (batched-refreshed) state, backward is hvs_mhc_static_coeffs_bwd."""
+
+    @staticmethod
+    def forward(ctx, mod, pre_raw, post_raw, res_raw):
+        st = mod._fresh_state()
+        ctx.mod = mod
+        ctx.uv = st.uv_history.clone()                 # the state may be refreshed (optimizer step) before backward runs
+        ctx.save_for_backward(pre_raw, post_raw, res_raw)
+        return st.h_pre.clone(), st.h_post.clone(), st.h_res.clone()
+
+    @staticmethod
+    def backward(ctx, d_pre, d_post, d_res):
+        pre_raw, post_raw, res_raw = ctx.saved_tensors
+        mod = ctx.mod
+        g = {"d_h_pre": None, "d_h_post": None, "d_h_res": None, "d_h_pre_raw": None, "d_h_post_raw": None, "d_h_res_raw": None}
+        outs = [None, None, None]
+        for i, (name, d, raw) in enumerate((("pre", d_pre, pre_raw), ("post", d_post, post_raw), ("res", d_res, res_raw))):
+            if d is not None and ctx.needs_input_grad[i + 1]:
+                g[f"d_h_{name}"] = d.contiguous().float()
+                outs[i] = torch.empty_like(raw, memory_format=torch.contiguous_format)
+                g[f"d_h_{name}_raw"] = outs[i]
+        job = {"h_pre_raw": pre_raw.detach().contiguous(), "h_post_raw": post_raw.detach().contiguous(),
+               "h_res_raw": res_raw.detach().contiguous(), "h_res": mod._state.h_res, "uv_history": ctx.uv}
+        ops.static_coeffs_bwd([job], [g], mod.sinkhorn.num_iterations, mod.sinkhorn.epsilon)
+        return None, outs[0], outs[1], outs[2]
 
 
 class ManifoldHyperConnection(nn.Module):
@@ -227,11 +380,17 @@ class ManifoldHyperConnection(nn.Module):
 
     Same constructor, parameters, buffers and state_dict keys (H_pre_raw, H_post_raw, H_res_raw,
     gradient_norms, eigenvalues, signal_ratio_history, sinkhorn.convergence_history, mlp.{0,3}.*,
-    norm_pre.*, norm_post.*).  Differences, all behind the same interface:
-      * the constrained matrices come from hvs_mhc_constrained_matrices and are cached until a
-        parameter changes (the reference recomputes them, with 60 host syncs, on every forward);
-      * stability monitoring (:282-316) is computed on demand in get_stability_metrics instead of an
-        eigvalsh inside every training forward.
+    norm_pre.*, norm_post.*).  What runs where:
+      * constrained_matrices: hvs_mhc_static_coeffs (all layers of a model in one launch through
+        ``refresh_static_coefficients``), cached until a parameter changes; its backward is
+        hvs_mhc_static_coeffs_bwd (no unrolled Sinkhorn graph);
+      * inference forward (no grad): hvs_layernorm_fwd -> four hvs_gemm_bf16 launches (tcgen05, fused bias+GELU and
+        residual + LayerNorm epilogues) under the reference's CUDA-autocast convention (bf16 operands, fp32
+        accumulation, fp32 output);
+      * training forward (grad): the same token path in torch ops so autograd sees it (the K2 backward GEMMs are
+        library calls), with the coefficient kernels above;
+      * stability monitoring (:282-316) is computed on demand in get_stability_metrics instead of an eigvalsh inside
+        every training forward.
     """
 
     def __init__(self, input_dim: int, expansion_rate: int = 4, hidden_dim: Optional[int] = None, alpha: float = 0.01,
@@ -255,8 +414,8 @@ class ManifoldHyperConnection(nn.Module):
         self.register_buffer("signal_ratio_history", torch.zeros(1000))
         self.signal_ratio_idx = 0
         self.dtype = torch.bfloat16 if use_mixed_precision else torch.float32
-        self._cache = None
-        self._cache_key = None
+        self._state: Optional[_CoeffState] = None
+        self.monitor_signal_ratio = True
         self._initialize_weights()
 
     def _initialize_weights(self):                       # :191-203
@@ -270,20 +429,60 @@ class ManifoldHyperConnection(nn.Module):
     def _key(self):
         return tuple((p.data_ptr(), p._version, p.device) for p in (self.H_pre_raw, self.H_post_raw, self.H_res_raw))
 
+    def _fresh_state(self) -> _CoeffState:
+        if self._state is None or self._state.key != self._key():
+            refresh_static_coefficients(self)
+        return self._state
+
     def constrained_matrices(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:      # :205-221
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in (self.H_pre_raw, self.H_post_raw, self.H_res_raw))
         if needs_grad:
-            return (torch.sigmoid(self.H_pre_raw), 2 * torch.sigmoid(self.H_post_raw), self.sinkhorn(self.H_res_raw))
-        key = self._key()
-        if self._cache is None or self._cache_key != key:
-            self._cache = ops.constrained_matrices(self.H_pre_raw.detach(), self.H_post_raw.detach(), self.H_res_raw.detach(),
-                                                   self.sinkhorn.num_iterations, self.sinkhorn.epsilon,
-                                                   history=self.sinkhorn.convergence_history)
-            self._cache_key = key
-        return self._cache
+            return _CoeffFn.apply(self, self.H_pre_raw, self.H_post_raw, self.H_res_raw)
+        st = self._fresh_state()
+        return st.h_pre, st.h_post, st.h_res
+
+    # ------------------------------------------------------------------ inference token path (K2 kernels)
+    def fused_supported(self) -> bool:
+        d, h = self.input_dim, self.hidden_dim
+        return (self.use_mixed_precision and d % 32 == 0 and h % 64 == 0 and (d <= 256 or d % 256 == 0)
+                and (h <= 256 or h % 256 == 0) and (2 * h <= 256 or (2 * h) % 256 == 0))
+
+    def _mlp_bf16(self):
+        st = self._state
+        w1, w2 = self.mlp[0].weight, self.mlp[3].weight
+        key = (w1.data_ptr(), w1._version, w2.data_ptr(), w2._version)
+        if st.wkey != key:
+            st.w1 = w1.detach().to(torch.bfloat16).contiguous()
+            st.w2 = w2.detach().to(torch.bfloat16).contiguous()
+            st.wkey = key
+        return st.w1, st.w2
+
+    def _forward_fused(self, x2: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """x2 [T, D] fp32 / bf16 -> [T, D] (:248-267, eval mode: dropout is the identity)."""
+        from . import _lib
+        st = self._fresh_state()
+        w1, w2 = self._mlp_bf16()
+        d = self.input_dim
+        dp = _pad64(d)
+        xn, xb = ops.layernorm_fwd(x2, self.norm_pre.weight.detach(), self.norm_pre.bias.detach(), self.norm_pre.eps,
+                                   out_dtype=torch.bfloat16, out_ld=dp, want_copy=True, copy_ld=dp)        # :250
+        z = ops.gemm_bf16(xn, st.h_pre_t)                                                                 # :253
+        z = ops.gemm_bf16(z, w1, bias=self.mlp[0].bias.detach(), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU)     # :164-165
+        z = ops.gemm_bf16(z, w2, bias=self.mlp[3].bias.detach(), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU)     # :167-168
+        if d <= 512:
+            return ops.gemm_bf16(z, st.h_post_t, xb, st.h_res_t, ln_weight=self.norm_post.weight.detach(),
+                                 ln_bias=self.norm_post.bias.detach(), ln_eps=self.norm_post.eps,
+                                 epilogue=_lib.HVS_GEMM_EPI_LAYERNORM, out_dtype=out_dtype)                # :259-267
+        pre = ops.gemm_bf16(z, st.h_post_t, xb, st.h_res_t, out_dtype=torch.float32)
+        out, _ = ops.layernorm_fwd(pre, self.norm_post.weight.detach(), self.norm_post.bias.detach(), self.norm_post.eps,
+                                   out_dtype=out_dtype)
+        return out
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:  # :223-280
         shape = x.shape
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if x.is_cuda and not needs_grad and not self.training and self.fused_supported() and x.dtype in (torch.float32, torch.bfloat16):
+            return self._forward_fused(x.reshape(-1, shape[-1])).reshape(shape)
         if x.dim() > 2:
             x = x.reshape(shape[0], -1, shape[-1])
         x_in = x
@@ -296,17 +495,25 @@ class ManifoldHyperConnection(nn.Module):
             out = torch.matmul(x_in, h_res) + z
             out = self.norm_post(out)
             out = self.dropout(out)
-        if self.training:
+        if self.training and self.monitor_signal_ratio:
             with torch.no_grad():                        # :295-303, without the per-call eigvalsh
                 ratio = torch.norm(out.float(), dim=-1).mean() / (torch.norm(x_in.float(), dim=-1).mean() + 1e-8)
                 self.signal_ratio_history[self.signal_ratio_idx % 1000] = ratio
                 self.signal_ratio_idx += 1
         return out.reshape(shape)
 
-    def get_stability_metrics(self) -> Dict[str, Any]:   # :318-341
+    def record_gradient_norms(self):
+        """Fill the reference's ``gradient_norms`` buffer (:153) from the current .grad of the three raw matrices
+        (call after backward; one small device op, no host sync)."""
         with torch.no_grad():
-            _, _, h_res = self.constrained_matrices()
-            h = h_res.detach().float()
+            for i, p in enumerate((self.H_pre_raw, self.H_post_raw, self.H_res_raw)):
+                if p.grad is not None:
+                    self.gradient_norms[i] = p.grad.norm()
+
+    def get_stability_metrics(self) -> Dict[str, Any]:   # :318-341 (values as _monitor_stability :282-316 computes them)
+        with torch.no_grad():
+            st = self._fresh_state()
+            h = st.h_res.detach().float()
             eig = torch.linalg.eigvalsh((h + h.T) / 2)
             self.eigenvalues.copy_(eig)
             metrics = {"max_eigenvalue": eig.max().item(), "min_eigenvalue": eig.min().item(),

@@ -6,6 +6,7 @@ libhvs_b200.so.  CPU tensors are rejected (no fallback).
 from __future__ import annotations
 
 import ctypes
+import functools
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -16,6 +17,30 @@ from ._lib import check
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_device(fn):
+    """Run the wrapped op with the first tensor argument's device current, so the stream, the SM count and the
+    per-device kernel attributes the library looks up are those of the device that owns the data."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor):
+                dev = a.device
+                break
+            if isinstance(a, (list, tuple)) and a and isinstance(a[0], dict):
+                for v in a[0].values():
+                    if isinstance(v, torch.Tensor):
+                        dev = v.device
+                        break
+                if dev is not None:
+                    break
+        if dev is None or dev.type != "cuda":
+            return fn(*args, **kwargs)            # the op itself rejects CPU tensors
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def _need_cuda(*tensors: Optional[torch.Tensor]):
@@ -29,6 +54,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 # ----------------------------------------------------------------------------- K1 stream mHC
+@_on_device
 def mhc_stream_fwd(x: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor, alpha: torch.Tensor,
                    scale: torch.Tensor, sk_iters: int = 20, eps_rms: float = 1e-8, eps_sk: float = 1e-8,
                    want_y: bool = True, want_u: bool = False, want_coeffs: bool = False,
@@ -64,6 +90,7 @@ def new_saved(x: torch.Tensor) -> torch.Tensor:
     return torch.empty((x.shape[0], _lib.HVS_MHC_SAVED_STRIDE), dtype=torch.float32, device=x.device)
 
 
+@_on_device
 def mhc_stream_bwd_saved(x: torch.Tensor, dy: torch.Tensor, saved: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor,
                          alpha: torch.Tensor, scale: torch.Tensor, sk_iters: int = 20, eps_rms: float = 1e-8,
                          eps_sk: float = 1e-8, out: Optional[torch.Tensor] = None,
@@ -89,6 +116,7 @@ def mhc_stream_bwd_saved(x: torch.Tensor, dy: torch.Tensor, saved: torch.Tensor,
     return {"dx": dx, "dphi": dphi, "dbias": dbias, "dalpha": dalpha, "dscale": dscale}
 
 
+@_on_device
 def mhc_stream_post(x: torch.Tensor, coeffs: torch.Tensor, fu: torch.Tensor) -> torch.Tensor:
     _need_cuda(x, coeffs, fu)
     t, n, c = x.shape
@@ -102,6 +130,7 @@ def mhc_stream_post(x: torch.Tensor, coeffs: torch.Tensor, fu: torch.Tensor) -> 
     return y
 
 
+@_on_device
 def mhc_stream_bwd(x: torch.Tensor, dy: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor, alpha: torch.Tensor,
                    scale: torch.Tensor, sk_iters: int = 20, eps_rms: float = 1e-8, eps_sk: float = 1e-8,
                    split_phi: bool = False) -> Dict[str, torch.Tensor]:
@@ -126,12 +155,18 @@ def mhc_stream_bwd(x: torch.Tensor, dy: torch.Tensor, phi: torch.Tensor, bias: t
 
 
 # ----------------------------------------------------------------------------- Sinkhorn / static coefficients
+@_on_device
 def sinkhorn(matrix: torch.Tensor, iters: int = 20, eps: float = 1e-8, tau: float = 1.0,
              history: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(matrix, history)
     if matrix.dtype != torch.float32:
         raise _lib.HvsError("sinkhorn expects fp32")
     m = matrix.contiguous()
+    if m.dim() == 2 and m.shape[0] == m.shape[1] and m.shape[0] > 32 and tau == 1.0:
+        # one large square matrix (a layer's D x D H_res_raw): the multi-CTA slab kernel, not one CTA walking it
+        out = torch.empty_like(m)
+        static_coeffs([{"h_pre_raw": m.new_zeros((m.shape[0], 1)), "h_res_raw": m, "h_res": out, "convergence": history}], iters, eps)
+        return out
     if m.dim() == 2:
         batch, n, mm = 1, m.shape[0], m.shape[1]
     else:
@@ -143,6 +178,7 @@ def sinkhorn(matrix: torch.Tensor, iters: int = 20, eps: float = 1e-8, tau: floa
     return out
 
 
+@_on_device
 def constrained_matrices(h_pre_raw: torch.Tensor, h_post_raw: torch.Tensor, h_res_raw: torch.Tensor,
                          iters: int = 20, eps: float = 1e-8, history: Optional[torch.Tensor] = None):
     _need_cuda(h_pre_raw, h_post_raw, h_res_raw)
@@ -156,10 +192,148 @@ def constrained_matrices(h_pre_raw: torch.Tensor, h_post_raw: torch.Tensor, h_re
     return h_pre, h_post, h_res
 
 
+# ----------------------------------------------------------------------------- row norms
+_NORM_DTYPES = {torch.float32: _lib.HVS_DTYPE_F32, torch.bfloat16: _lib.HVS_DTYPE_BF16}
+
+
+@_on_device
+def rmsnorm_fwd(x: torch.Tensor, scale: torch.Tensor, eps: float = 1e-8, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """RMSNorm over the last axis (manifold_layers.py:449-456); x fp32 / bf16, any leading shape."""
+    _need_cuda(x, scale)
+    if x.dtype not in _NORM_DTYPES or scale.dtype != torch.float32:
+        raise _lib.HvsError("rmsnorm expects fp32 / bf16 data and an fp32 scale")
+    dim = x.shape[-1]
+    xc = x.contiguous()
+    out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    check(_lib.load().hvs_rmsnorm_fwd(_ptr(xc), _NORM_DTYPES[xc.dtype], _ptr(scale.contiguous()), _ptr(out),
+                                      _NORM_DTYPES[out.dtype], xc.numel() // max(dim, 1), dim, eps, _stream()), "hvs_rmsnorm_fwd")
+    return out
+
+
+@_on_device
+def rmsnorm_bwd(x: torch.Tensor, scale: torch.Tensor, dy: torch.Tensor, eps: float = 1e-8) -> Tuple[torch.Tensor, torch.Tensor]:
+    _need_cuda(x, scale, dy)
+    if x.dtype not in _NORM_DTYPES or dy.dtype != x.dtype:
+        raise _lib.HvsError("rmsnorm_bwd expects x and dy of the same fp32 / bf16 dtype")
+    dim = x.shape[-1]
+    rows = x.numel() // max(dim, 1)
+    xc, dyc = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(xc)
+    dscale = torch.empty(dim, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    nb = int(lib.hvs_rmsnorm_bwd_workspace(rows, dim))
+    ws = torch.empty(max(nb, 256), dtype=torch.uint8, device=x.device)
+    check(lib.hvs_rmsnorm_bwd(_ptr(xc), _NORM_DTYPES[xc.dtype], _ptr(scale.contiguous()), _ptr(dyc), _ptr(dx), _ptr(dscale),
+                              rows, dim, eps, _ptr(ws), ws.numel(), _stream()), "hvs_rmsnorm_bwd")
+    return dx, dscale
+
+
+@_on_device
+def layernorm_fwd(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
+                  out_dtype: torch.dtype = torch.float32, out_ld: Optional[int] = None, want_copy: bool = False,
+                  copy_ld: Optional[int] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """LayerNorm over the last axis of x [rows, dim] -> out [rows, out_ld] (pad columns zero); optionally bf16(x)."""
+    _need_cuda(x, weight, bias)
+    rows, dim = x.shape
+    out_ld = out_ld or dim
+    copy_ld = copy_ld or out_ld
+    out = torch.empty((rows, out_ld), dtype=out_dtype, device=x.device)
+    cp = torch.empty((rows, copy_ld), dtype=torch.bfloat16, device=x.device) if want_copy else None
+    xc = x.contiguous()
+    check(_lib.load().hvs_layernorm_fwd(_ptr(xc), _NORM_DTYPES[xc.dtype], _ptr(weight), _ptr(bias), _ptr(out),
+                                        _NORM_DTYPES[out_dtype], _ptr(cp), rows, dim, out_ld, copy_ld, eps, _stream()),
+          "hvs_layernorm_fwd")
+    return out, cp
+
+
+# ----------------------------------------------------------------------------- K2: batched static coefficients, GEMMs
+def _coeff_arrays(jobs: Sequence[Dict[str, Optional[torch.Tensor]]]):
+    arr = (_lib.CoeffJob * len(jobs))()
+    for a, j in zip(arr, jobs):
+        for k in ("h_pre_raw", "h_post_raw", "h_res_raw", "h_pre", "h_post", "h_res", "h_pre_t", "h_post_t", "h_res_t",
+                  "uv_history", "convergence"):
+            setattr(a, k, _ptr(j.get(k)))
+        a.D, a.H = j["h_res_raw"].shape[0], j["h_pre_raw"].shape[1]
+        a.Dp = j["h_res_t"].shape[1] if j.get("h_res_t") is not None else (j["h_pre_t"].shape[1] if j.get("h_pre_t") is not None else a.D)
+    return arr
+
+
+@_on_device
+def static_coeffs(jobs: Sequence[Dict[str, Optional[torch.Tensor]]], iters: int = 20, eps: float = 1e-8) -> None:
+    """constrained_matrices of MANY layers in one launch.  Each job is a dict of tensors named after
+    struct hvs_coeff_job's fields; outputs are written in place."""
+    if not jobs:
+        return
+    for j in jobs:
+        _need_cuda(*[t for t in j.values() if isinstance(t, torch.Tensor)])
+    lib = _lib.load()
+    arr = _coeff_arrays(jobs)
+    dev = jobs[0]["h_res_raw"].device
+    nb = int(lib.hvs_mhc_static_coeffs_workspace(arr, len(jobs), iters, 0))
+    if nb == 0:
+        raise _lib.HvsError("hvs_mhc_static_coeffs: unsupported job list")
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    check(lib.hvs_mhc_static_coeffs(arr, len(jobs), iters, eps, _ptr(ws), nb, _stream()), "hvs_mhc_static_coeffs")
+
+
+@_on_device
+def static_coeffs_bwd(jobs: Sequence[Dict[str, Optional[torch.Tensor]]], grads: Sequence[Dict[str, Optional[torch.Tensor]]],
+                      iters: int = 20, eps: float = 1e-8) -> None:
+    """Backward of static_coeffs: grads[i] has d_h_pre / d_h_post / d_h_res (inputs, may be None) and
+    d_h_pre_raw / d_h_post_raw / d_h_res_raw (outputs)."""
+    if not jobs:
+        return
+    lib = _lib.load()
+    arr = _coeff_arrays(jobs)
+    garr = (_lib.CoeffGrad * len(jobs))()
+    for g, d in zip(garr, grads):
+        for k in ("d_h_pre", "d_h_post", "d_h_res", "d_h_pre_raw", "d_h_post_raw", "d_h_res_raw"):
+            t = d.get(k)
+            if t is not None:
+                _need_cuda(t)
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise _lib.HvsError(f"{k} must be contiguous fp32")
+            setattr(g, k, _ptr(t))
+    dev = jobs[0]["h_res_raw"].device
+    nb = int(lib.hvs_mhc_static_coeffs_workspace(arr, len(jobs), iters, 1))
+    if nb == 0:
+        raise _lib.HvsError("hvs_mhc_static_coeffs_bwd: unsupported job list")
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    check(lib.hvs_mhc_static_coeffs_bwd(arr, garr, len(jobs), iters, eps, _ptr(ws), nb, _stream()), "hvs_mhc_static_coeffs_bwd")
+
+
+@_on_device
+def gemm_bf16(a0: torch.Tensor, b0: torch.Tensor, a1: Optional[torch.Tensor] = None, b1: Optional[torch.Tensor] = None,
+              bias: Optional[torch.Tensor] = None, ln_weight: Optional[torch.Tensor] = None,
+              ln_bias: Optional[torch.Tensor] = None, ln_eps: float = 1e-5, epilogue: int = _lib.HVS_GEMM_EPI_NONE,
+              out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = epilogue(a0 @ b0^T (+ a1 @ b1^T)); a*: [M,K*] bf16 (row stride may exceed K*), b*: [N,K*] bf16."""
+    _need_cuda(a0, b0, a1, b1, bias, ln_weight, ln_bias, out)
+    for t in (a0, b0, a1, b1):
+        if t is not None and (t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1):
+            raise _lib.HvsError("gemm operands must be 2-D bf16 with unit inner stride")
+    m, k0 = a0.shape
+    n = b0.shape[0]
+    if b0.shape[1] != k0 or not b0.is_contiguous():
+        raise _lib.HvsError("b0 must be contiguous [N, K0]")
+    k1 = 0
+    if a1 is not None:
+        k1 = a1.shape[1]
+        if b1 is None or tuple(b1.shape) != (n, k1) or not b1.is_contiguous() or a1.shape[0] != m:
+            raise _lib.HvsError("second operand pair must be a1 [M,K1], b1 [N,K1]")
+    if out is None:
+        out = torch.empty((m, n), dtype=out_dtype, device=a0.device)
+    check(_lib.load().hvs_gemm_bf16(_ptr(a0), a0.stride(0), _ptr(b0), k0, _ptr(a1), a1.stride(0) if a1 is not None else 0,
+                                    _ptr(b1), k1, _ptr(bias), _ptr(ln_weight), _ptr(ln_bias), ln_eps, _ptr(out),
+                                    _NORM_DTYPES[out.dtype], out.stride(0), m, n, epilogue, _stream()), "hvs_gemm_bf16")
+    return out
+
+
 # ----------------------------------------------------------------------------- detection
 _DTYPES = {torch.float32: _lib.HVS_DTYPE_F32, torch.float16: _lib.HVS_DTYPE_F16, torch.bfloat16: _lib.HVS_DTYPE_BF16}
 
 
+@_on_device
 def yolo_decode(pred: torch.Tensor, anchor_wh: torch.Tensor, want_scores: bool = False,
                 want_objectness: bool = True) -> Dict[str, torch.Tensor]:
     """pred [B,A,H,W,5+C] (any strides, fp32/fp16/bf16), anchor_wh [A,2] fp32."""
@@ -186,6 +360,7 @@ def yolo_decode(pred: torch.Tensor, anchor_wh: torch.Tensor, want_scores: bool =
     return out
 
 
+@_on_device
 def nms(boxes: torch.Tensor, scores: torch.Tensor, classes: Optional[torch.Tensor] = None,
         iou_threshold: float = 0.5, max_detections: int = 100, score_threshold: float = float("-inf"),
         class_aware: bool = False, boxes_xyxy: bool = True, offsets: Optional[torch.Tensor] = None,
@@ -217,6 +392,7 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, classes: Optional[torch.Tenso
     return keep_idx, keep_src, keep_cnt
 
 
+@_on_device
 def post_process(decoded: Sequence[Dict[str, torch.Tensor]], confidence_threshold: float = 0.5,
                  iou_threshold: float = 0.5, max_detections: int = 100):
     """Two-stage multi-scale NMS for a batch.  decoded: per-scale dicts from yolo_decode.

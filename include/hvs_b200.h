@@ -80,6 +80,7 @@ int hvs_mhc_stream_post(const void* x, const float* coeffs, const void* fu, void
 /* Backward of hvs_mhc_stream_fwd (F = identity), coefficients recomputed.
  *   dy [T,n,C] bf16 -> dx [T,n,C] bf16, dphi [n*C, n*n+2n] fp32, dbias [n*n+2n], dalpha [3],
  *   dscale [n*C]  (parameter gradients are OVERWRITTEN, not accumulated).
+ * sk_iters <= 24 (HVS_ERR_UNSUPPORTED beyond; the forward alone takes up to 64).
  * workspace: hvs_mhc_stream_bwd_workspace(T, n, C) bytes, 256-byte aligned. */
 size_t hvs_mhc_stream_bwd_workspace(int64_t T, int n, int C);
 int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* phi, const float* bias,
@@ -91,7 +92,7 @@ int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* phi, const fl
 /* Backward of hvs_mhc_stream_fwd_save (F = identity) in ONE fused kernel: dx and dphi/dscale/dbias/dalpha in a
  * single pass over x and dy (12288 + 112 B/token); `saved` is the forward's [T, HVS_MHC_SAVED_STRIDE] record.
  * The Sinkhorn forward iterations are replayed from the saved logits and differentiated exactly.
- * Same outputs and conventions as hvs_mhc_stream_bwd.  sk_iters <= 24 (HVS_ERR_UNSUPPORTED beyond: use hvs_mhc_stream_bwd).
+ * Same outputs and conventions as hvs_mhc_stream_bwd.  sk_iters <= 24 (HVS_ERR_UNSUPPORTED beyond).
  * workspace: hvs_mhc_stream_bwd_saved_workspace(T, n, C) bytes, 256-byte aligned. */
 size_t hvs_mhc_stream_bwd_saved_workspace(int64_t T, int n, int C);
 int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const float* saved, const float* phi,
@@ -115,8 +116,10 @@ int hvs_mhc_stream_kernel_ms(float* out4_host);
  * out = SK(in) for `batch` matrices of n x m fp32, row-major, contiguous.
  * `history` (may be NULL) receives |mean(row_sum) - 1| per iteration ([iters] fp32), the
  * reference's convergence_history buffer (:76-77).
- * Supported: n*m <= 64 per matrix for batch > 1 ("per-token" blocks), or batch == 1 with
- * n, m <= 2048 (a layer's D x D H_res_raw).
+ * Supported: n, m <= 32 for any batch ("per-token" blocks, a warp per matrix), or larger matrices with
+ * n, m <= 4096 (a layer's D x D H_res_raw; `history` then only with batch == 1).
+ * `out` is bitwise reproducible run to run; the `history` diagnostic of the small-block path accumulates
+ * with fp32 atomics and may differ in its last bits.
  * ---------------------------------------------------------------------------------- */
 int hvs_sinkhorn(const float* in, float* out, int64_t batch, int n, int m, int iters, float eps,
                  float tau, float* history, void* stream);
@@ -127,6 +130,88 @@ int hvs_sinkhorn(const float* in, float* out, int64_t batch, int n, int m, int i
 int hvs_mhc_constrained_matrices(const float* h_pre_raw, const float* h_post_raw, const float* h_res_raw,
                                  float* h_pre, float* h_post, float* h_res, int D, int hidden, int iters,
                                  float eps, float* history, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Row normalisations of the path.
+ * RMSNorm.forward (src/models/manifold_layers.py:449-456): out = x / sqrt(mean(x^2, -1) + eps) * scale,
+ * rows x dim, contiguous; x / out dtypes HVS_DTYPE_F32 or HVS_DTYPE_BF16 (statistics always fp32).
+ * hvs_rmsnorm_bwd: dy -> dx (same dtype as x) and dscale [dim] fp32 (overwritten; two-stage fixed-order
+ * reduction through `workspace`, hvs_rmsnorm_bwd_workspace bytes).  dim <= 6144.
+ * hvs_layernorm_fwd: nn.LayerNorm over the last axis as the module applies it before / after the token path
+ * (manifold_layers.py:250, :267).  out has row stride out_ld >= dim (columns [dim, out_ld) are zero-filled so
+ * the row can feed a GEMM whose K is padded); x_bf16_copy (may be NULL) receives bf16(x) with row stride copy_ld.
+ * ---------------------------------------------------------------------------------- */
+int hvs_rmsnorm_fwd(const void* x, int x_dtype, const float* scale, void* out, int out_dtype, int64_t rows,
+                    int dim, float eps, void* stream);
+size_t hvs_rmsnorm_bwd_workspace(int64_t rows, int dim);
+int hvs_rmsnorm_bwd(const void* x, int dtype, const float* scale, const void* dy, void* dx, float* dscale,
+                    int64_t rows, int dim, float eps, void* workspace, size_t workspace_bytes, void* stream);
+int hvs_layernorm_fwd(const void* x, int x_dtype, const float* weight, const float* bias, void* out, int out_dtype,
+                      void* x_bf16_copy, int64_t rows, int dim, int out_ld, int copy_ld, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2, the reference-literal module: static coefficients of MANY layers in one launch.
+ * ManifoldHyperConnection.constrained_matrices (manifold_layers.py:205-221) for every job:
+ *   H_pre = sigmoid(H_pre_raw) [D,H], H_post = 2 sigmoid(H_post_raw) [H,D], H_res = SK(H_res_raw) [D,D]
+ * plus the bf16, transposed copies the token-path GEMMs take as B operands ([N,K] row-major, K padded to Dp):
+ *   h_pre_t [H,Dp] = H_pre^T, h_post_t [D,H] = H_post^T, h_res_t [D,Dp] = H_res^T.
+ * One cooperative kernel; a large D x D matrix is iterated by many CTAs (row slabs).  D <= 4096.
+ * uv_history [(iters+1), 2, D] fp32 (scalings u_k | v_k, k = 0..iters) is what the backward consumes;
+ * convergence [iters] = the reference's convergence_history buffer (:76-77).  Any output pointer except
+ * h_res may be NULL.  Job arrays live in HOST memory (the call copies its tables into the workspace).
+ * ---------------------------------------------------------------------------------- */
+typedef struct hvs_coeff_job {
+    const float* h_pre_raw;
+    const float* h_post_raw;
+    const float* h_res_raw;
+    float* h_pre;
+    float* h_post;
+    float* h_res;
+    void* h_pre_t;
+    void* h_post_t;
+    void* h_res_t;
+    float* uv_history;
+    float* convergence;
+    int32_t D, H, Dp, reserved;
+} hvs_coeff_job;
+
+/* gradients for hvs_mhc_static_coeffs_bwd: d_h_* are dL/dH (inputs, may be NULL), d_*_raw the parameter
+ * gradients (outputs, overwritten). */
+typedef struct hvs_coeff_grad {
+    const float* d_h_pre;
+    const float* d_h_post;
+    const float* d_h_res;
+    float* d_h_pre_raw;
+    float* d_h_post_raw;
+    float* d_h_res_raw;
+} hvs_coeff_grad;
+
+size_t hvs_mhc_static_coeffs_workspace(const hvs_coeff_job* jobs_host, int num_jobs, int iters, int backward);
+int hvs_mhc_static_coeffs(const hvs_coeff_job* jobs_host, int num_jobs, int iters, float eps, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* Backward through the gates and the Sinkhorn iterations (exact reverse sweep of the scaling form; jobs must
+ * carry the uv_history written by the forward with the same raw parameters). */
+int hvs_mhc_static_coeffs_bwd(const hvs_coeff_job* jobs_host, const hvs_coeff_grad* grads_host, int num_jobs,
+                              int iters, float eps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* K2 token path (manifold_layers.py:248-270) as tcgen05 GEMMs with fused epilogues:
+ *   out[M,N] = epilogue( A0[M,K0] B0[N,K0]^T + A1[M,K1] B1[N,K1]^T )        (second pair optional: K1 = 0)
+ * A*: bf16 row-major, row stride lda* elements (multiple of 8); B*: bf16 [N,K*] row-major contiguous (the
+ * nn.Linear weight layout).  K0, K1 multiples of 64; N a multiple of 32, and of 256 when N > 256.
+ *   HVS_GEMM_EPI_NONE       out = acc (+ bias if given)                        z = LN(x) @ H_pre          (:253)
+ *   HVS_GEMM_EPI_BIAS_GELU  out = gelu_erf(acc + bias[n])                      mlp Linear + GELU          (:164-168)
+ *   HVS_GEMM_EPI_LAYERNORM  out = LayerNorm_N(acc) * ln_w + ln_b, N <= 512     norm_post(z@H_post + x@H_res) (:259-267)
+ * out: fp32 or bf16 (out_dtype), row stride ldo elements (multiple of 8). */
+#define HVS_GEMM_EPI_NONE 0
+#define HVS_GEMM_EPI_BIAS_GELU 1
+#define HVS_GEMM_EPI_LAYERNORM 2
+int hvs_gemm_bf16(const void* a0, int64_t lda0, const void* b0, int K0, const void* a1, int64_t lda1,
+                  const void* b1, int K1, const float* bias, const float* ln_w, const float* ln_b, float ln_eps,
+                  void* out, int out_dtype, int64_t ldo, int64_t M, int N, int epilogue, void* stream);
+
+/* Mean duration in ms of the (last 128) launches per kernel slot since hvs_mhc_stream_profile(1):
+ * 0-3 as hvs_mhc_stream_kernel_ms, 4 = K2 GEMM, 5 = decode, 6 = NMS, 7 = static coefficients; negative = not run. */
+int hvs_profile_kernel_ms(float* out8_host);
 
 /* ------------------------------------------------------------------------------------
  * YOLODecoder.forward (src/models/yolo_head.py:220-294), one scale.

@@ -17,7 +17,8 @@ def declared_symbols():
 def test_header_declares_the_hot_path():
     syms = declared_symbols()
     for need in ("hvs_mhc_stream_fwd", "hvs_mhc_stream_bwd", "hvs_sinkhorn", "hvs_yolo_decode", "hvs_nms",
-                 "hvs_post_process", "hvs_mhc_constrained_matrices"):
+                 "hvs_post_process", "hvs_mhc_constrained_matrices", "hvs_mhc_static_coeffs", "hvs_mhc_static_coeffs_bwd",
+                 "hvs_gemm_bf16", "hvs_layernorm_fwd", "hvs_rmsnorm_fwd", "hvs_rmsnorm_bwd"):
         assert need in syms
 
 
@@ -28,6 +29,11 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(raw, s), f"{s} declared in hvs_b200.h but not exported"
     assert set(hvs_b200._lib.EXPORTED_SYMBOLS) == set(declared_symbols())
+    # and the other direction: the shipped library exports NOTHING the header does not declare (no debug probes)
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", hvs_b200._lib.lib_path()], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln and ln.split()[-1].startswith("hvs_")}
+    assert exported == set(declared_symbols()), exported ^ set(declared_symbols())
     assert lib.hvs_abi_version() == 1
     assert b"not supported" in lib.hvs_error_string(-2)
 

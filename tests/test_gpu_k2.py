@@ -1,0 +1,350 @@
+"""K2, the reference-literal ManifoldHyperConnection (src/models/manifold_layers.py:104-346) on the CUDA kernels:
+batched static coefficients (+ their backward), row norms, the tcgen05 GEMMs with fused epilogues, and the module's
+fused inference path -- each through the C ABI, against the CPU oracle / golden vectors.
+
+Tolerances: fp32 coefficient work 1e-5 relative (north_star); the GEMM path follows the reference's CUDA-autocast
+convention (bf16 operands, fp32 accumulate), so it is compared (i) tightly with a torch fp32 reference fed the SAME
+bf16-rounded operands and (ii) with the fp32 oracle at a bf16-operand tolerance (2^-7 of the LayerNorm-ed output scale)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mhc_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand(*shape, seed=0, std=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * std
+
+
+# ----------------------------------------------------------------------------- row norms
+def test_rmsnorm_kernel_golden_and_backward(golden):
+    import hvs_b200
+    g = golden("rmsnorm")
+    x, scale, want = (torch.from_numpy(g[k]) for k in ("x", "scale", "out"))
+    mod = hvs_b200.RMSNorm(2048).to(DEV)
+    with torch.no_grad():
+        mod.scale.copy_(scale)
+        got = mod(x.to(DEV))
+    assert ((got.cpu() - want).abs() / want.abs().clamp_min(1e-3)).max() < 1e-5
+    # bf16 data, fp32 statistics
+    xb = x.to(torch.bfloat16)
+    with torch.no_grad():
+        gb = mod(xb.to(DEV))
+    ref = mhc_ref.rms_norm(xb.float(), scale)
+    assert gb.dtype == torch.bfloat16 and (gb.cpu().float() - ref).abs().max() <= 2.0 ** -7 * ref.abs().max()
+    # backward vs autograd through the oracle; deterministic
+    for rows, dim in ((37, 256), (1000, 2048), (3, 96)):
+        xx = _rand(rows, dim, seed=rows).requires_grad_(True)
+        sc = (1 + 0.1 * _rand(dim, seed=dim)).requires_grad_(True)
+        dy = _rand(rows, dim, seed=7)
+        mhc_ref.rms_norm(xx, sc).backward(dy)
+        m2 = hvs_b200.RMSNorm(dim).to(DEV)
+        with torch.no_grad():
+            m2.scale.copy_(sc.detach())
+        xg = xx.detach().to(DEV).requires_grad_(True)
+        m2(xg).backward(dy.to(DEV))
+        assert torch.allclose(xg.grad.cpu(), xx.grad, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(m2.scale.grad.cpu(), sc.grad, rtol=1e-4, atol=1e-4)
+        dx2, ds2 = hvs_b200.ops.rmsnorm_bwd(xx.detach().to(DEV), sc.detach().to(DEV), dy.to(DEV))
+        assert torch.equal(dx2, xg.grad) and torch.equal(ds2, m2.scale.grad)
+
+
+def test_layernorm_kernel_with_padding_and_copy():
+    import hvs_b200
+    for rows, dim, ld in ((100, 32, 64), (7, 512, 512), (33, 1792, 1792), (5, 96, 128)):
+        x = _rand(rows, dim, seed=dim) * 3 + 1.5
+        w, b = 1 + 0.1 * _rand(dim, seed=1), 0.1 * _rand(dim, seed=2)
+        want = torch.nn.functional.layer_norm(x, (dim,), w, b)
+        out, cp = hvs_b200.ops.layernorm_fwd(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5, torch.float32, ld, True, ld)
+        assert torch.allclose(out[:, :dim].cpu(), want, rtol=1e-5, atol=2e-6)
+        assert (out[:, dim:] == 0).all() and (cp[:, dim:] == 0).all()
+        assert torch.equal(cp[:, :dim].cpu(), x.to(torch.bfloat16))
+        ob, _ = hvs_b200.ops.layernorm_fwd(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5, torch.bfloat16, ld)
+        assert torch.equal(ob[:, :dim].cpu(), out[:, :dim].cpu().to(torch.bfloat16))
+
+
+# ----------------------------------------------------------------------------- batched static coefficients
+def _jobs(dims, iters=20, hidden_mult=2, seed=0, std=0.3):
+    import hvs_b200
+    jobs, raws = [], []
+    for i, d in enumerate(dims):
+        h = max(64, d * hidden_mult)
+        dp = (d + 63) // 64 * 64
+        raw = [_rand(d, h, seed=seed + 3 * i, std=std), _rand(h, d, seed=seed + 3 * i + 1, std=std), _rand(d, d, seed=seed + 3 * i + 2, std=std)]
+        raws.append(raw)
+        f32, bf = dict(dtype=torch.float32, device=DEV), dict(dtype=torch.bfloat16, device=DEV)
+        jobs.append({"h_pre_raw": raw[0].to(DEV), "h_post_raw": raw[1].to(DEV), "h_res_raw": raw[2].to(DEV),
+                     "h_pre": torch.empty(d, h, **f32), "h_post": torch.empty(h, d, **f32), "h_res": torch.empty(d, d, **f32),
+                     "h_pre_t": torch.full((h, dp), 7.0, **bf), "h_post_t": torch.empty(d, h, **bf), "h_res_t": torch.full((d, dp), 7.0, **bf),
+                     "uv_history": torch.empty(iters + 1, 2, d, **f32), "convergence": torch.empty(iters, **f32)})
+    return jobs, raws
+
+
+def test_static_coeffs_all_layers_one_launch_vs_oracle():
+    """Every D the model has, including the 1024 and 1792 the single-CTA path never tested, in ONE
+    launch: 1e-5 relative to the oracle, row / column sums, transposed bf16 copies, convergence history."""
+    import hvs_b200
+    dims = [32, 64, 128, 256, 256, 512, 1024, 1792, 3, 48]
+    jobs, raws = _jobs(dims)
+    before = hvs_b200._lib.launch_count()
+    hvs_b200.ops.static_coeffs(jobs, 20, 1e-8)
+    torch.cuda.synchronize()
+    assert hvs_b200._lib.launch_count() == before + 1
+    for d, j, raw in zip(dims, jobs, raws):
+        hp, hq, hr = mhc_ref.constrained_matrices(*raw)
+        want, hist = mhc_ref.sinkhorn_knopp(raw[2], 20, return_history=True)
+        got = j["h_res"].cpu()
+        assert ((got - hr).abs() / hr.abs()).max() < 1e-5, d
+        assert (got.sum(0) - 1).abs().max() < 1e-4 and (got.sum(1) - 1).abs().max() < 1e-4, d
+        assert ((j["h_pre"].cpu() - hp).abs() / hp.abs()).max() < 1e-5 and ((j["h_post"].cpu() - hq).abs() / hq.abs()).max() < 1e-5
+        assert torch.allclose(j["convergence"].cpu(), hist, atol=3e-6), d
+        assert torch.equal(j["h_res_t"][:, :d].cpu(), got.t().to(torch.bfloat16))
+        assert torch.equal(j["h_pre_t"][:, :d].cpu(), j["h_pre"].cpu().t().to(torch.bfloat16))
+        assert torch.equal(j["h_post_t"].cpu(), j["h_post"].cpu().t().to(torch.bfloat16))
+        assert (j["h_res_t"][:, d:] == 0).all() and (j["h_pre_t"][:, d:] == 0).all()
+        # the scalings reproduce the projection: P = diag(u_n) K diag(v_n)
+        k = torch.softmax(raw[2], -1) * d
+        uv = j["uv_history"].cpu()
+        assert torch.allclose(uv[20, 0][:, None] * k * uv[20, 1][None, :], got, rtol=1e-5, atol=1e-9)
+    jobs2, _ = _jobs(dims)
+    hvs_b200.ops.static_coeffs(jobs2, 20, 1e-8)
+    for a, b in zip(jobs, jobs2):
+        assert torch.equal(a["h_res"], b["h_res"]) and torch.equal(a["convergence"], b["convergence"])
+
+
+def test_static_coeffs_hot_logits_and_iteration_counts():
+    import hvs_b200
+    for iters in (0, 1, 5, 20):
+        jobs, raws = _jobs([64, 200], iters=iters, std=1.0, seed=11)
+        hvs_b200.ops.static_coeffs(jobs, iters, 1e-8)
+        for j, raw in zip(jobs, raws):
+            want = mhc_ref.sinkhorn_knopp(raw[2], iters)
+            assert ((j["h_res"].cpu() - want).abs() / want.abs()).max() < 1e-5, iters
+
+
+@pytest.mark.parametrize("dims", [[16, 64], [256], [1024, 32]])
+def test_static_coeffs_backward_vs_oracle_autograd(dims):
+    import hvs_b200
+    jobs, raws = _jobs(dims, seed=5, std=0.5)
+    hvs_b200.ops.static_coeffs(jobs, 20, 1e-8)
+    grads, want = [], []
+    for d, j, raw in zip(dims, jobs, raws):
+        h = raw[0].shape[1]
+        g = [_rand(d, h, seed=d + 1), _rand(h, d, seed=d + 2), _rand(d, d, seed=d + 3)]
+        leaf = [r.clone().requires_grad_(True) for r in raw]
+        hp, hq, hr = mhc_ref.constrained_matrices(*leaf)
+        (hp * g[0]).sum().backward(); (hq * g[1]).sum().backward(); (hr * g[2]).sum().backward()
+        want.append([t.grad for t in leaf])
+        grads.append({"d_h_pre": g[0].to(DEV), "d_h_post": g[1].to(DEV), "d_h_res": g[2].to(DEV),
+                      "d_h_pre_raw": torch.empty(d, h, device=DEV), "d_h_post_raw": torch.empty(h, d, device=DEV),
+                      "d_h_res_raw": torch.empty(d, d, device=DEV)})
+    hvs_b200.ops.static_coeffs_bwd(jobs, grads, 20, 1e-8)
+    for d, gr, w in zip(dims, grads, want):
+        for name, ref in zip(("d_h_pre_raw", "d_h_post_raw", "d_h_res_raw"), w):
+            got = gr[name].cpu().double()
+            rel = ((got - ref.double()).norm() / ref.double().norm()).item()
+            assert rel < 1e-5, (d, name, rel)
+        assert (gr["d_h_res_raw"].cpu() - w[2]).abs().max() <= 1e-4 * w[2].abs().max() + 1e-9
+
+
+def test_sinkhorn_module_square_grad_uses_kernel_backward():
+    import hvs_b200
+    sk = hvs_b200.SinkhornKnoppProjection(20).to(DEV)
+    w = torch.nn.Parameter(_rand(48, 48, seed=9, std=0.4).to(DEV))
+    tgt = _rand(48, 48, seed=10).to(DEV)
+    before = hvs_b200._lib.launch_count()
+    (sk(w) * tgt).sum().backward()
+    assert hvs_b200._lib.launch_count() == before + 2              # one forward, one backward launch: nothing unrolled
+    leaf = w.detach().cpu().clone().requires_grad_(True)
+    (mhc_ref.sinkhorn_knopp(leaf, 20) * tgt.cpu()).sum().backward()
+    assert ((w.grad.cpu() - leaf.grad).norm() / leaf.grad.norm()) < 1e-5
+
+
+# ----------------------------------------------------------------------------- tcgen05 GEMM + epilogues
+def _gemm_ref(a0, b0, a1=None, b1=None, bias=None):
+    acc = a0.double() @ b0.double().t()
+    if a1 is not None:
+        acc = acc + a1.double() @ b1.double().t()
+    if bias is not None:
+        acc = acc + bias.double()
+    return acc
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (1, 32, 64), (300, 96, 128), (1000, 512, 2048), (4099, 1792, 256),
+                                   (257, 2048, 512), (129, 64, 4096)])
+def test_gemm_plain_and_gelu(m, n, k):
+    import hvs_b200
+    from hvs_b200 import _lib
+    a = _rand(m, k, seed=m).to(torch.bfloat16)
+    b = (_rand(n, k, seed=n) / k ** 0.5).to(torch.bfloat16)
+    bias = 0.1 * _rand(n, seed=3)
+    out = hvs_b200.ops.gemm_bf16(a.to(DEV), b.to(DEV), out_dtype=torch.float32).cpu()
+    ref = _gemm_ref(a, b)
+    assert (out.double() - ref).abs().max() <= 2e-5 * ref.abs().max() + 1e-6        # fp32 accumulation of exact bf16 products
+    outb = hvs_b200.ops.gemm_bf16(a.to(DEV), b.to(DEV)).cpu()
+    assert outb.dtype == torch.bfloat16 and torch.equal(outb, out.to(torch.bfloat16))
+    g = hvs_b200.ops.gemm_bf16(a.to(DEV), b.to(DEV), bias=bias.to(DEV), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU, out_dtype=torch.float32).cpu()
+    gref = torch.nn.functional.gelu(_gemm_ref(a, b, bias=bias))
+    assert (g.double() - gref).abs().max() <= 2e-5 * gref.abs().max() + 2e-6
+
+
+@pytest.mark.parametrize("m,n,k0,k1", [(500, 64, 256, 64), (128, 512, 2048, 512), (1000, 256, 512, 256), (77, 32, 128, 64),
+                                       (260, 96, 192, 128)])
+def test_gemm_two_operand_pairs_layernorm_epilogue(m, n, k0, k1):
+    import hvs_b200
+    from hvs_b200 import _lib
+    a0, b0 = _rand(m, k0, seed=1).to(torch.bfloat16), (_rand(n, k0, seed=2) / k0 ** 0.5).to(torch.bfloat16)
+    a1, b1 = (_rand(m, k1, seed=3) + 0.5).to(torch.bfloat16), (_rand(n, k1, seed=4) / k1 ** 0.5).to(torch.bfloat16)
+    w, b = 1 + 0.1 * _rand(n, seed=5), 0.1 * _rand(n, seed=6)
+    pre = _gemm_ref(a0, b0, a1, b1)
+    ref = torch.nn.functional.layer_norm(pre, (n,), w.double(), b.double())
+    # padded A rows (row stride > K) exercise the lda path
+    a1p = torch.zeros(m, k1 + 64, dtype=torch.bfloat16)
+    a1p[:, :k1] = a1
+    out = hvs_b200.ops.gemm_bf16(a0.to(DEV), b0.to(DEV), a1p.to(DEV)[:, :k1], b1.to(DEV), ln_weight=w.to(DEV), ln_bias=b.to(DEV),
+                                 epilogue=_lib.HVS_GEMM_EPI_LAYERNORM, out_dtype=torch.float32).cpu()
+    assert (out.double() - ref).abs().max() < 5e-5
+    raw = hvs_b200.ops.gemm_bf16(a0.to(DEV), b0.to(DEV), a1.to(DEV), b1.to(DEV), out_dtype=torch.float32).cpu()
+    assert (raw.double() - pre).abs().max() <= 2e-5 * pre.abs().max() + 1e-6
+    again = hvs_b200.ops.gemm_bf16(a0.to(DEV), b0.to(DEV), a1p.to(DEV)[:, :k1], b1.to(DEV), ln_weight=w.to(DEV), ln_bias=b.to(DEV),
+                                   epilogue=_lib.HVS_GEMM_EPI_LAYERNORM, out_dtype=torch.float32).cpu()
+    assert torch.equal(out, again)
+
+
+def test_gemm_rejects_bad_shapes():
+    import hvs_b200
+    from hvs_b200._lib import HvsError
+    a, b = torch.zeros(8, 48, dtype=torch.bfloat16, device=DEV), torch.zeros(32, 48, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(HvsError):
+        hvs_b200.ops.gemm_bf16(a, b)                                # K not a multiple of 64
+    with pytest.raises(HvsError):
+        hvs_b200.ops.gemm_bf16(torch.zeros(8, 64, dtype=torch.bfloat16, device=DEV), torch.zeros(40, 64, dtype=torch.bfloat16, device=DEV))
+    assert hvs_b200.ops.gemm_bf16(torch.zeros(0, 64, dtype=torch.bfloat16, device=DEV), torch.zeros(32, 64, dtype=torch.bfloat16, device=DEV)).shape == (0, 32)
+
+
+# ----------------------------------------------------------------------------- the module's fused inference path
+def _module_pair(d, n, hidden=None, seed=0):
+    import hvs_b200
+    torch.manual_seed(seed)
+    mod = hvs_b200.ManifoldHyperConnection(d, expansion_rate=n, hidden_dim=hidden)
+    with torch.no_grad():                                           # non-trivial norms / biases
+        for p in (mod.norm_pre.weight, mod.norm_post.weight):
+            p.add_(0.1 * torch.randn_like(p))
+        for p in (mod.norm_pre.bias, mod.norm_post.bias, mod.mlp[0].bias, mod.mlp[3].bias):
+            p.add_(0.05 * torch.randn_like(p))
+    params = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    return mod.to(DEV).eval(), params
+
+
+def _bf16_convention_reference(x, p):
+    """The reference's CUDA-autocast arithmetic in fp64 on bf16-rounded operands (what the kernels compute up to fp32
+    accumulation order): LN fp32 -> bf16, every matmul operand bf16, intermediate activations bf16."""
+    r = lambda t: t.to(torch.bfloat16).double()
+    hp, hq, hr = mhc_ref.constrained_matrices(p["H_pre_raw"], p["H_post_raw"], p["H_res_raw"])
+    d = x.shape[-1]
+    xn = r(torch.nn.functional.layer_norm(x.float(), (d,), p["norm_pre.weight"], p["norm_pre.bias"]))
+    z = r((xn @ r(hp)).float())
+    z = r(torch.nn.functional.gelu(z @ r(p["mlp.0.weight"]).t() + p["mlp.0.bias"].double()).float())
+    z = r(torch.nn.functional.gelu(z @ r(p["mlp.3.weight"]).t() + p["mlp.3.bias"].double()).float())
+    pre = z @ r(hq) + r(x) @ r(hr)
+    return torch.nn.functional.layer_norm(pre, (d,), p["norm_post.weight"].double(), p["norm_post.bias"].double())
+
+
+@pytest.mark.parametrize("d,n,hidden,t", [(64, 4, None, 1000), (32, 4, None, 4099), (256, 2, None, 401), (512, 4, None, 300),
+                                          (256, 2, 1024, 257), (1024, 2, None, 130), (1792, 2, None, 1), (128, 4, None, 77)])
+def test_module_fused_forward_vs_oracle(d, n, hidden, t):
+    import hvs_b200
+    mod, p = _module_pair(d, n, hidden, seed=d + n)
+    assert mod.fused_supported()
+    x = _rand(t, d, seed=t) * 1.5 + 0.2
+    before = hvs_b200._lib.launch_count()
+    with torch.no_grad():
+        y = mod(x.to(DEV))
+    launches = hvs_b200._lib.launch_count() - before
+    assert launches == (7 if d > 512 else 6)                        # coefficients (1, first call only) + LN + 4 GEMMs (+ LN)
+    assert y.dtype == torch.float32 and y.shape == x.shape
+    tight = _bf16_convention_reference(x, p)
+    assert (y.cpu().double() - tight).abs().max() < 2e-2           # bf16 re-rounding of intermediates may flip an ulp
+    assert (y.cpu().double() - tight).abs().mean() < 1e-3
+    oracle = mhc_ref.mhc_module_forward(x, p)                       # fp32 oracle (the reference's CPU arithmetic)
+    err = (y.cpu() - oracle).abs()
+    assert err.max() < 2.0 ** -4 and err.mean() < 2.0 ** -7, (err.max().item(), err.mean().item())
+    with torch.no_grad():
+        y2 = mod(x.to(DEV))
+    assert torch.equal(y, y2)
+    assert hvs_b200._lib.launch_count() - before == launches + launches - 1      # cached coefficients: no second refresh
+
+
+def test_module_fused_forward_golden_and_shapes(golden):
+    import hvs_b200
+    g = golden("mhc_module")
+    for tag, (d, n) in {"d64n4": (64, 4), "d32n2": (32, 2)}.items():
+        mod = hvs_b200.ManifoldHyperConnection(d, expansion_rate=n).to(DEV).eval()
+        keys = {k.split("/p/")[1] for k in g.files if k.startswith(tag + "/p/")}
+        mod.load_state_dict({k: torch.from_numpy(g[f"{tag}/p/{k}"]) for k in keys})
+        x = torch.from_numpy(g[f"{tag}/x"])
+        with torch.no_grad():
+            y = mod(x.to(DEV))
+        want = torch.from_numpy(g[f"{tag}/y"])
+        assert y.shape == want.shape
+        err = (y.cpu() - want).abs()
+        assert err.max() < 2.0 ** -4 and err.mean() < 2.0 ** -7
+        hr = mod.constrained_matrices()[2].cpu()
+        assert ((hr - torch.from_numpy(g[f"{tag}/H_res"])).abs() / torch.from_numpy(g[f"{tag}/H_res"])).max() < 1e-5
+    # bf16 input, empty input
+    mod, p = _module_pair(64, 4)
+    with torch.no_grad():
+        xb = (_rand(50, 64, seed=1)).to(torch.bfloat16)
+        yb = mod(xb.to(DEV))
+        assert (yb.cpu() - mhc_ref.mhc_module_forward(xb.float(), p)).abs().max() < 2.0 ** -4
+        assert mod(torch.zeros(0, 64, device=DEV)).shape == (0, 64)
+
+
+def test_refresh_static_coefficients_batches_all_modules():
+    import hvs_b200
+    from hvs_b200.mhc import refresh_static_coefficients
+    torch.manual_seed(0)
+    net = torch.nn.ModuleList([hvs_b200.ManifoldHyperConnection(d, expansion_rate=2) for d in (32, 64, 256, 512, 1792)]).to(DEV).eval()
+    before = hvs_b200._lib.launch_count()
+    assert refresh_static_coefficients(net) == 5
+    assert hvs_b200._lib.launch_count() == before + 1               # five layers, one launch
+    assert refresh_static_coefficients(net) == 0
+    with torch.no_grad():
+        net[1].H_res_raw.mul_(1.5)
+    assert refresh_static_coefficients(net) == 1
+    for m in net:
+        hp, hq, hr = mhc_ref.constrained_matrices(m.H_pre_raw.detach().cpu(), m.H_post_raw.detach().cpu(), m.H_res_raw.detach().cpu())
+        got = m.constrained_matrices()
+        assert ((got[2].cpu() - hr).abs() / hr).max() < 1e-5 and ((got[0].cpu() - hp).abs() / hp).max() < 1e-5
+
+
+def test_module_training_path_gradients_vs_oracle():
+    """Training (grad mode): coefficient forward/backward on the kernels, token path in torch ops under bf16 autocast.
+    Gradients against autograd through the fp32 oracle at the bf16-operand tolerance."""
+    import hvs_b200
+    mod, p = _module_pair(64, 4, seed=3)
+    mod.train()
+    mod.dropout.p = 0.0
+    for m in mod.mlp:
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    x = _rand(200, 64, seed=8)
+    dy = _rand(200, 64, seed=9)
+    xg = x.to(DEV).requires_grad_(True)
+    mod(xg).backward(dy.to(DEV))
+    leaf = {k: v.clone().requires_grad_(True) if v.dtype == torch.float32 and "history" not in k and k not in ("gradient_norms", "eigenvalues") else v
+            for k, v in p.items()}
+    xl = x.clone().requires_grad_(True)
+    mhc_ref.mhc_module_forward(xl, leaf).backward(dy)
+    def rel(a, b):
+        return ((a.cpu().double() - b.double()).norm() / b.double().norm()).item()
+    assert rel(xg.grad, xl.grad) < 3e-2
+    assert rel(mod.H_res_raw.grad, leaf["H_res_raw"].grad) < 3e-2
+    assert rel(mod.H_pre_raw.grad, leaf["H_pre_raw"].grad) < 3e-2
+    assert rel(mod.H_post_raw.grad, leaf["H_post_raw"].grad) < 3e-2
+    assert rel(mod.mlp[0].weight.grad, leaf["mlp.0.weight"].grad) < 3e-2
+    mod.record_gradient_norms()
+    assert torch.allclose(mod.gradient_norms.cpu(), torch.stack([mod.H_pre_raw.grad.norm(), mod.H_post_raw.grad.norm(), mod.H_res_raw.grad.norm()]).cpu())

@@ -234,7 +234,7 @@ def test_fused_backward_matches_oracle(t):
     check_bwd(inp, dy, got, f"fused T={t}")
 
 
-def test_fused_backward_hot_logits_and_init_scale():
+def test_fused_backward_warm_and_init_2ulp_hot_logits_looser_norm_bound():
     """Warm logits (std ~0.7: Sinkhorn still converges to 5e-7, the scaling-form reverse sweep is exercised far from
     the uniform matrix) and the microbenchmark's alpha = 0.01 configuration against the oracle; hot logits (std > 2,
     20 iterations leave a 3e-2 row error) against the oracle for the parameter gradients and against the two-kernel
@@ -289,8 +289,10 @@ def test_fused_backward_limits_and_determinism():
     x = inp[0].cuda()
     P = [p.cuda() for p in inp[1:]]
     saved = hvs_b200.ops.new_saved(x)
-    with pytest.raises(HvsError):      # more iterations than the shared-memory history holds: caller must use mhc_stream_bwd
+    with pytest.raises(HvsError):      # more iterations than the shared-memory history holds
         hvs_b200.ops.mhc_stream_bwd_saved(x, dy.cuda(), saved, *P, sk_iters=25)
+    with pytest.raises(HvsError):      # the two-kernel backward has the same limit
+        hvs_b200.ops.mhc_stream_bwd(x, dy.cuda(), *P, sk_iters=25)
     # T = 0 is a no-op that still writes zero parameter gradients
     e = hvs_b200.ops.mhc_stream_bwd_saved(x[:0], dy.cuda()[:0], saved[:0], *P)
     assert e["dx"].numel() == 0 and float(e["dphi"].abs().max()) == 0.0 and float(e["dbias"].abs().max()) == 0.0
@@ -347,3 +349,82 @@ def test_kernel_timing_hooks():
         assert list(buf) == [-1.0, -1.0, -1.0, -1.0]
     finally:
         lib.hvs_mhc_stream_profile(0)
+
+
+def test_more_than_24_iterations_is_inference_only():
+    """The forward takes up to 64 Sinkhorn iterations; training (either backward kernel) at most 24.  A training
+    call with more must be rejected BEFORE the forward runs, not inside autograd.backward."""
+    import hvs_b200
+    from hvs_b200._lib import HvsError
+    x, phi, bias, al, scale = make_inputs(64, seed=3, alpha=0.3)
+    layer = hvs_b200.StreamMHC(sk_iterations=25).cuda()
+    with torch.no_grad():
+        layer.phi.copy_(phi); layer.bias.copy_(bias); layer.alpha.copy_(al); layer.rms_scale.copy_(scale)
+        y = layer(x.cuda())                                       # inference: fine
+    ref = mhc_ref.stream_mhc_forward(x, phi, bias, al, scale, sk_iterations=25)
+    mag = mhc_ref.mixing_condition_magnitude(x, ref["H_pre"], ref["H_post"], ref["H_res"])
+    assert ((y.cpu().float() - ref["y"].float()).abs() <= ULP_BOUND * mhc_ref.bf16_ulp(mag)).all()
+    before = hvs_b200._lib.launch_count()
+    with pytest.raises(HvsError, match="sk_iterations"):
+        layer(x.cuda().requires_grad_(True))
+    assert hvs_b200._lib.launch_count() == before                # nothing was launched
+    xh = x.pin_memory()
+    with pytest.raises(HvsError, match="sk_iterations"):
+        hvs_b200.stream_mhc_fwd_bwd_host(xh, xh, layer, torch.empty_like(xh).pin_memory(), torch.empty_like(xh).pin_memory())
+
+
+def test_bench_configuration_full_size_against_oracle():
+    """BASELINE configs[1] as benchmarked: T = 2^20, n = 4, C = 512, bench.py's parameters.  Forward y / coefficients
+    and the FUSED backward's dx are compared with the oracle on 4 608 tokens taken from the first, middle and LAST
+    tiles (plus the tokens straddling the 2^31-element boundary of the flat index); parameter gradients are compared
+    with the oracle on one 2^16-token slice (they are sums over tokens), and the full-size gradients must equal the
+    sum of the 16 slices' gradients."""
+    import hvs_b200
+    t = 1 << 20
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(t, 4, 512, generator=g, device=dev, dtype=torch.bfloat16)
+    dy = torch.randn(t, 4, 512, generator=g, device=dev, dtype=torch.bfloat16)
+    gp = torch.Generator().manual_seed(0)
+    phi = torch.randn(2048, 24, generator=gp) * 0.02
+    bias, al, scale = torch.zeros(24), torch.full((3,), 0.01), torch.ones(2048)
+    P = [p.to(dev) for p in (phi, bias, al, scale)]
+    saved = hvs_b200.ops.new_saved(x)
+    y, _, co = hvs_b200.ops.mhc_stream_fwd(x, *P, want_coeffs=True, saved=saved)
+    full = hvs_b200.ops.mhc_stream_bwd_saved(x, dy, saved, *P)
+    torch.cuda.synchronize()
+    mid = t // 2
+    edge = (1 << 31) // 2048                                      # token whose first element has flat index 2^31
+    idx = torch.cat([torch.arange(0, 1536), torch.arange(mid - 512, mid + 512), torch.arange(edge - 256, edge + 256),
+                     torch.arange(t - 1536, t)])
+    assert idx.numel() == 4608
+    xs, dys = x[idx.to(dev)].cpu(), dy[idx.to(dev)].cpu()
+    ys, cos = y[idx.to(dev)].cpu(), co[idx.to(dev)].cpu()
+    check_against_oracle(xs, phi, bias, al, scale, ys, torch.einsum("tj,tjc->tc", cos[:, :4], xs.float()).to(torch.bfloat16), cos)
+    ref = mhc_ref.stream_mhc_backward(xs, dys, phi, bias, al, scale)
+    fwd = mhc_ref.stream_mhc_forward(xs, phi, bias, al, scale)
+    m = fwd["H_res"] + fwd["H_post"][:, :, None] * fwd["H_pre"][:, None, :]
+    mag = torch.einsum("tij,tic->tjc", m.abs(), dys.float().abs()) + ref["dx"].abs()
+    ulps = ((full["dx"][idx.to(dev)].cpu().float() - ref["dx"]).abs() / mhc_ref.bf16_ulp(mag)).max().item()
+    assert ulps <= ULP_BOUND, f"full-size fused dx off by {ulps:.2f} bf16 ulp"
+    # parameter gradients: additivity over 16 slices, and one slice (the LAST) against the oracle
+    sl = t // 16
+    acc = None
+    last = None
+    for k in range(16):
+        lo, hi = k * sl, (k + 1) * sl
+        part = hvs_b200.ops.mhc_stream_bwd_saved(x[lo:hi], dy[lo:hi], saved[lo:hi], *P)
+        acc = {n: part[n].double() for n in PARAM_KEYS} if acc is None else {n: acc[n] + part[n].double() for n in PARAM_KEYS}
+        last = part
+    for n in PARAM_KEYS:
+        rel = ((full[n].double() - acc[n]).norm() / acc[n].norm().clamp_min(1e-30)).item()
+        assert rel < 1e-4, f"{n}: full-size gradient != sum of slices ({rel:.2e})"
+    lo = t - sl
+    ref_sl = mhc_ref.stream_mhc_backward(x[lo:].cpu(), dy[lo:].cpu(), phi, bias, al, scale)
+    for n in PARAM_KEYS:
+        a, b = last[n].cpu().double(), ref_sl[n].double()
+        rel = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+        assert rel < 3e-4, f"{n} on the last 2^16-token slice: relative error {rel:.2e}"
+
+
+PARAM_KEYS = ("dphi", "dbias", "dalpha", "dscale")

@@ -22,7 +22,8 @@ def test_sinkhorn_golden(golden):
         assert (out >= 0).all()
 
 
-@pytest.mark.parametrize("shape", [(1000, 4, 4), (7, 8, 8), (3, 16, 12), (2, 32, 32), (64, 64), (257, 257), (512, 512)])
+@pytest.mark.parametrize("shape", [(1000, 4, 4), (7, 8, 8), (3, 16, 12), (2, 32, 32), (64, 64), (257, 257), (512, 512), (1024, 1024),
+                                   (1792, 1792), (40, 1300)])
 def test_sinkhorn_shapes(shape):
     import hvs_b200
     torch.manual_seed(sum(shape))
