@@ -88,10 +88,96 @@ class YOLOPredictionHead(nn.Module):
         x = self.conv_layers(x)
         b, c, h, w = x.shape
         if not isinstance(self.mhc_enhance, nn.Identity):
+            # [B*H*W, C] token view: free (no copy) when x is channels_last, as in hybrid_vision.mhc_over_pixels
             x = self.mhc_enhance(x.permute(0, 2, 3, 1).reshape(-1, c)).reshape(b, h, w, c).permute(0, 3, 1, 2)
         pred = self.pred_conv(x)
+        if not pred.is_contiguous():
+            pred = pred.contiguous()                    # channels_last conv output: the [B,A,5+C,H,W] view below needs NCHW strides
         # [B, A*(5+C), H, W] -> [B,A,H,W,5+C] as a VIEW: the decode kernel reads it through its strides
         return pred.view(b, self.num_anchors, 5 + self.num_classes, h, w).permute(0, 1, 3, 4, 2)
+
+
+class YOLOLoss(nn.Module):
+    """YOLOLoss(num_classes, anchors, image_size, lambda_coord=5, lambda_noobj=.5, lambda_obj=1, lambda_cls=1)
+    (yolo_head.py:297-465).  predictions {scale_i: [B,A,H,W,5+C]}, targets [per scale [B,A,H,W,5+C]] -> dict with
+    'coord_loss', 'obj_loss', 'noobj_loss', 'cls_loss', 'total_loss'.
+
+    Same arithmetic -- squared error on the 4 box slots and BCE-with-logits on objectness / classes, summed over the
+    cells with target objectness > 0.5 (no-object term over the cells < 0.5), every term divided by the scale's object
+    count, a scale without objects contributing nothing (:411-413) -- written with masks instead of boolean indexing,
+    so the loss has NO host synchronisation (the reference does five .item() per scale) and can be captured in a CUDA
+    graph.  The four component entries are detached 0-dim tensors (the reference returns Python floats)."""
+
+    def __init__(self, num_classes: int = 80, anchors=None, image_size: int = 416, lambda_coord: float = 5.0,
+                 lambda_noobj: float = 0.5, lambda_obj: float = 1.0, lambda_cls: float = 1.0):
+        super().__init__()
+        self.num_classes, self.image_size = num_classes, image_size
+        self.lambda_coord, self.lambda_noobj, self.lambda_obj, self.lambda_cls = lambda_coord, lambda_noobj, lambda_obj, lambda_cls
+        self.anchors = anchors if anchors is not None else DEFAULT_ANCHORS
+        self.num_scales = len(self.anchors)
+
+    @staticmethod
+    def compute_iou(box1: torch.Tensor, box2: torch.Tensor) -> torch.Tensor:      # :341-372
+        ix1, iy1 = torch.max(box1[..., 0], box2[..., 0]), torch.max(box1[..., 1], box2[..., 1])
+        ix2, iy2 = torch.min(box1[..., 2], box2[..., 2]), torch.min(box1[..., 3], box2[..., 3])
+        inter = torch.clamp(ix2 - ix1, min=0) * torch.clamp(iy2 - iy1, min=0)
+        a1 = (box1[..., 2] - box1[..., 0]) * (box1[..., 3] - box1[..., 1])
+        a2 = (box2[..., 2] - box2[..., 0]) * (box2[..., 3] - box2[..., 1])
+        return inter / (a1 + a2 - inter + 1e-6)
+
+    def forward(self, predictions: Dict[str, torch.Tensor], targets: Sequence[torch.Tensor]) -> Dict[str, torch.Tensor]:
+        bce = nn.functional.binary_cross_entropy_with_logits
+        total = None
+        parts = {"coord_loss": 0.0, "obj_loss": 0.0, "noobj_loss": 0.0, "cls_loss": 0.0}
+        for i in range(self.num_scales):
+            key = f"scale_{i}"
+            if key not in predictions:
+                continue
+            pred = predictions[key].float()
+            tgt = targets[i].to(pred.dtype)
+            t_obj = tgt[..., 4]
+            obj = (t_obj > 0.5).to(pred.dtype)
+            noobj = (t_obj < 0.5).to(pred.dtype)
+            n = obj.sum()
+            has = (n > 0).to(pred.dtype)
+            coord = (((pred[..., :4] - tgt[..., :4]) ** 2).sum(-1) * obj).sum()
+            e_obj = bce(pred[..., 4], t_obj, reduction="none")
+            l_obj, l_noobj = (e_obj * obj).sum(), (e_obj * noobj).sum()
+            l_cls = (bce(pred[..., 5:], tgt[..., 5:], reduction="none").sum(-1) * obj).sum()
+            term = (self.lambda_coord * coord + self.lambda_obj * l_obj + self.lambda_noobj * l_noobj + self.lambda_cls * l_cls)
+            term = has * term / n.clamp_min(1.0)
+            total = term if total is None else total + term
+            for k, v in (("coord_loss", coord), ("obj_loss", l_obj), ("noobj_loss", l_noobj), ("cls_loss", l_cls)):
+                parts[k] = parts[k] + (has * v).detach()
+        out: Dict[str, Any] = dict(parts)
+        out["total_loss"] = total if total is not None else 0.0
+        return out
+
+
+def dense_targets_from_boxes(boxes: Sequence[torch.Tensor], labels: Sequence[torch.Tensor], grid_sizes: Sequence[Tuple[int, int]],
+                             num_classes: int = 80, anchors=None, device=None) -> List[torch.Tensor]:
+    """Padded-box annotations -> the dense per-scale targets [B,A,H,W,5+C] YOLOLoss consumes.  The reference has no
+    assigner anywhere; this is the rule SURVEY section 8(d) cfg 4 fixes: a box (cx,cy,w,h
+    normalised) goes to the cell floor(cx*W), floor(cy*H) of EVERY scale, on the anchor of that scale with the best
+    width/height IoU against anchors/416; slots 0:4 = (cx,cy,w,h), 4 = 1, 5+class = 1."""
+    anchors = anchors if anchors is not None else DEFAULT_ANCHORS
+    b = len(boxes)
+    out = []
+    for s, (h, w) in enumerate(grid_sizes):
+        a_wh = torch.tensor(anchors[s], dtype=torch.float32) / 416.0
+        t = torch.zeros(b, len(anchors[s]), h, w, 5 + num_classes)
+        for i in range(b):
+            bx = boxes[i].detach().float().cpu().reshape(-1, 4)
+            lb = labels[i].detach().cpu().reshape(-1).long()
+            for (cx, cy, bw, bh), c in zip(bx.tolist(), lb.tolist()):
+                inter = torch.minimum(a_wh[:, 0], torch.tensor(bw)) * torch.minimum(a_wh[:, 1], torch.tensor(bh))
+                a = int(torch.argmax(inter / (a_wh[:, 0] * a_wh[:, 1] + bw * bh - inter)))
+                gx, gy = min(int(cx * w), w - 1), min(int(cy * h), h - 1)
+                t[i, a, gy, gx, 0:4] = torch.tensor([cx, cy, bw, bh])
+                t[i, a, gy, gx, 4] = 1.0
+                t[i, a, gy, gx, 5 + c] = 1.0
+        out.append(t.to(device) if device is not None else t)
+    return out
 
 
 class YOLODetectionHead(nn.Module):
@@ -106,9 +192,14 @@ class YOLODetectionHead(nn.Module):
         self.num_anchors = self.anchor_generator.get_num_anchors()
         self.pred_heads = nn.ModuleList([YOLOPredictionHead(c, num_classes, self.num_anchors, use_mhc) for c in in_channels_list])
         self.decoder = YOLODecoder(image_size=416)
+        self.loss_fn = YOLOLoss(num_classes=num_classes, anchors=anchors)        # :505-508
+        self.grid_sizes = [(13, 13), (26, 26), (52, 52)]                          # :511 (informational: the decoder uses the actual H, W)
+        self.want_scores = True      # full [B,A,H,W,C] obj*cls tensor (the reference's 'scores'); post_process does not need it
 
     def forward(self, features: Dict[str, torch.Tensor], targets=None, compute_loss: bool = False,
-                want_scores: bool = True) -> Dict[str, Any]:
+                want_scores: Optional[bool] = None) -> Dict[str, Any]:
+        """yolo_head.py:515-569.  With compute_loss and targets the result carries 'loss' (:556-563)."""
+        want_scores = self.want_scores if want_scores is None else want_scores
         predictions, decoded = {}, {}
         for i in range(self.num_scales):
             key = ["scale_small", "scale_medium", "scale_large"][i]
@@ -116,8 +207,12 @@ class YOLODetectionHead(nn.Module):
                 continue
             pred = self.pred_heads[i](features[key])
             predictions[f"scale_{i}"] = pred
-            decoded[f"scale_{i}"] = self.decoder(pred, self.anchor_generator(i), pred.shape[2:4], want_scores=want_scores)
-        return {"predictions": predictions, "decoded": decoded}
+            with torch.no_grad():                       # decode is an inference product; the loss works on raw predictions
+                decoded[f"scale_{i}"] = self.decoder(pred.detach(), self.anchor_generator(i), pred.shape[2:4], want_scores=want_scores)
+        out = {"predictions": predictions, "decoded": decoded}
+        if compute_loss and targets is not None:
+            out["loss"] = self.loss_fn(predictions, targets)
+        return out
 
     def post_process(self, decoded_outputs: Dict[str, Dict[str, torch.Tensor]], confidence_threshold: float = 0.5,
                      iou_threshold: float = 0.5, max_detections: int = 100) -> List[Dict[str, torch.Tensor]]:
@@ -132,8 +227,8 @@ class YOLODetectionHead(nn.Module):
         """yolo_head.py:678-731; returns int64 indices into the input, descending score."""
         if boxes.numel() == 0:
             return torch.tensor([], dtype=torch.long, device=boxes.device)
-        keep_idx, _, cnt = ops.nms(boxes, scores, None, iou_threshold, max_detections)
-        return keep_idx[0, :int(cnt[0])]
+        _, keep_src, cnt = ops.nms(boxes, scores, None, iou_threshold, max_detections)
+        return keep_src[0, :int(cnt[0])]              # indices into the INPUT (differs from the compacted index when a score is NaN / -inf)
 
     def compute_iou(self, box1: torch.Tensor, box2: torch.Tensor) -> torch.Tensor:
         """yolo_head.py:733-755 (elementwise torch ops; not on the hot path)."""
@@ -166,6 +261,6 @@ class NMSFilter:
     def apply(self, boxes: torch.Tensor, scores: torch.Tensor, class_ids: torch.Tensor) -> torch.Tensor:
         if len(boxes) == 0:
             return torch.empty(0, dtype=torch.long, device=boxes.device)
-        keep_idx, _, cnt = ops.nms(boxes, scores, class_ids, self.config.nms_iou_threshold,
+        _, keep_src, cnt = ops.nms(boxes, scores, class_ids, self.config.nms_iou_threshold,
                                    self.config.nms_max_detections, class_aware=True, boxes_xyxy=False)
-        return keep_idx[0, :int(cnt[0])]
+        return keep_src[0, :int(cnt[0])]

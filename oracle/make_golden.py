@@ -275,6 +275,84 @@ def gen_nms(ref, head):
     np.savez_compressed(os.path.join(GOLDEN, "nms.npz"), **out)
 
 
+def gen_stability(ref):
+    """_monitor_stability / get_stability_metrics (manifold_layers.py:282-341): the reference module in TRAIN mode
+    (dropout 0) records eigenvalues of sym(H_res), the signal ratio and the row / column sum errors."""
+    out = {}
+    for tag, (d, n, t) in {"d48n2": (48, 2, 64), "d64n4": (64, 4, 33)}.items():
+        torch.manual_seed(106)
+        mod = ref.ManifoldHyperConnection(d, expansion_rate=n, dropout_rate=0.0).train()
+        with torch.no_grad():
+            mod.H_res_raw.normal_(0, 0.7)
+        xs = [torch.randn(t, d) * (1 + i) for i in range(3)]
+        with torch.no_grad():
+            for x in xs:
+                mod(x)
+        m = mod.get_stability_metrics()
+        for k, v in mod.state_dict().items():
+            out[f"{tag}/p/{k}"] = v.detach().numpy()
+        for i, x in enumerate(xs):
+            out[f"{tag}/x{i}"] = x.numpy()
+        for k in ("max_eigenvalue", "min_eigenvalue", "eigenvalue_range", "signal_ratio_mean", "signal_ratio_std",
+                  "signal_ratio_min", "signal_ratio_max", "signal_ratio", "row_sum_error", "col_sum_error"):
+            out[f"{tag}/m/{k}"] = np.float64(m[k])
+        out[f"{tag}/m/final_convergence"] = np.float64(m["sk_convergence"]["final_convergence"])
+        say(f"stability[{tag}]: reference metrics recorded (max eig {m['max_eigenvalue']:.6f}, signal ratio {m['signal_ratio']:.4f})")
+    np.savez_compressed(os.path.join(GOLDEN, "stability.npz"), **out)
+
+
+def gen_loss(ref):
+    """YOLOLoss (yolo_head.py:374-465) on dense targets, including a scale without objects."""
+    g = torch.Generator().manual_seed(107)
+    loss = ref.yolo_head.YOLOLoss(num_classes=80)
+    preds, tgts = {}, []
+    for s, hw in enumerate((8, 4, 2)):
+        preds[f"scale_{s}"] = torch.randn(2, 3, hw, hw, 85, generator=g)
+        t = torch.zeros(2, 3, hw, hw, 85)
+        if s != 1:                                          # scale 1 has no object: contributes nothing (:411-413)
+            for _ in range(5):
+                b, a, y, x = (int(torch.randint(0, m, (1,), generator=g)) for m in (2, 3, hw, hw))
+                t[b, a, y, x, :4] = torch.rand(4, generator=g)
+                t[b, a, y, x, 4] = 1.0
+                t[b, a, y, x, 5 + int(torch.randint(0, 80, (1,), generator=g))] = 1.0
+        tgts.append(t)
+    want = loss(preds, tgts)
+    out = {f"pred{s}": preds[f"scale_{s}"].numpy() for s in range(3)}
+    out.update({f"tgt{s}": tgts[s].numpy() for s in range(3)})
+    for k, v in want.items():
+        out[k] = np.float64(float(v))
+    say(f"yolo_loss: reference total {float(want['total_loss']):.6f} (coord {want['coord_loss']:.4f} obj {want['obj_loss']:.4f} "
+        f"noobj {want['noobj_loss']:.4f} cls {want['cls_loss']:.4f})")
+    np.savez_compressed(os.path.join(GOLDEN, "yolo_loss.npz"), **out)
+
+
+def gen_hybrid():
+    """Whole model: the reference's HybridVisionSystem (repairs R1-R8, reference_repaired.load_full_model) with
+    name-seeded parameters on a 2 x 3 x 128 x 128 input.  The fixture holds the state_dict key / shape table and the
+    outputs; the GPU test rebuilds the same parameters by name in hvs_b200's host model."""
+    import json
+    model = reference_repaired.load_full_model().eval()
+    table = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in model.state_dict().items()}
+    with open(os.path.join(GOLDEN, "hybrid_vision_keys.json"), "w") as f:
+        json.dump(table, f, indent=0, sort_keys=True)
+    reference_repaired.fill_by_name(model, 0)
+    x = torch.randn(2, 3, 128, 128, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        res = model(x)
+    out = {"x": x.numpy(), "final_features": res["final_features"].numpy(), "vit_features_mean": res["vit_features"].mean((2, 3)).numpy()}
+    for s in range(3):
+        out[f"pred{s}"] = res["predictions"][f"scale_{s}"].numpy()
+    for k in ("fused_small", "fused_medium", "fused_large"):
+        out[f"{k}_chanmean"] = res["fused_features"][k].mean((2, 3)).numpy()
+    for k in ("scale_small", "scale_medium"):
+        out[f"backbone_{k}_chanmean"] = res["backbone_features"][k].mean((2, 3)).numpy()
+    n_mhc = sum(1 for m in model.modules() if type(m).__name__ == "ManifoldHyperConnection")
+    say(f"hybrid_vision: reference model ({sum(p.numel() for p in model.parameters()) / 1e6:.1f} M parameters, {n_mhc} mHC modules, "
+        f"{len(table)} state_dict entries) forward at 2x3x128x128 with name-seeded parameters: predictions std "
+        f"{[round(float(out[f'pred{s}'].std()), 4) for s in range(3)]}")
+    np.savez_compressed(os.path.join(GOLDEN, "hybrid_vision.npz"), **out)
+
+
 def main():
     torch.set_num_threads(1)        # fixed reduction order -> reproducible fixtures
     os.makedirs(GOLDEN, exist_ok=True)
@@ -286,6 +364,9 @@ def main():
     gen_stream(ref)
     head = gen_decode(ref)
     gen_nms(ref, head)
+    gen_stability(ref)
+    gen_loss(ref)
+    gen_hybrid()
     with open(os.path.join(GOLDEN, "PINNING.txt"), "w") as f:
         f.write(_report.getvalue())
     say("golden fixtures written to tests/golden/")

@@ -1,0 +1,146 @@
+"""Whole-model checks on the GPU: hvs_b200's host model (hybrid_vision.py) with the CUDA modules dropped in, against the
+fixture written by the REFERENCE's HybridVisionSystem (oracle/make_golden.py::gen_hybrid, name-seeded parameters).
+
+* fp32 mode (every mHC with use_mixed_precision=False, TF32 off): the model must reproduce the reference's CPU outputs
+  -- pins composition + coefficient kernels + decode inside the real model;
+* default mode (bf16 tcgen05 token path, the reference's CUDA-autocast convention): agreement at bf16-operand level
+  (the fixture's coefficients are trained-like, i.e. well conditioned, see tests/test_gpu_k2.py);
+* channels_last (layout fold, row a10) changes nothing; detect() end to end; CUDA-graph replay is bitwise stable."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import detect_ref, reference_repaired
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def model():
+    import hvs_b200
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = hvs_b200.HybridVisionSystem({"num_classes": 80, "image_size": 640}).eval()
+    reference_repaired.fill_by_name(m, 0)                   # pure torch helper: same weights as the fixture's model
+    return m.to(DEV)
+
+
+def _set_mixed(model, mixed):
+    import hvs_b200
+    for m in model.modules():
+        if isinstance(m, hvs_b200.ManifoldHyperConnection):
+            m.use_mixed_precision = mixed
+
+
+def test_fp32_mode_reproduces_reference_outputs(model, golden):
+    import hvs_b200
+    g = golden("hybrid_vision")
+    _set_mixed(model, False)
+    try:
+        before = hvs_b200._lib.launch_count()
+        with torch.no_grad():
+            out = model(torch.from_numpy(g["x"]).to(DEV))
+        assert hvs_b200._lib.launch_count() - before >= 1 + 3       # one coefficient launch for all 76 layers + 3 decodes
+    finally:
+        _set_mixed(model, True)
+    for s in range(3):
+        got, want = out["predictions"][f"scale_{s}"].cpu(), torch.from_numpy(g[f"pred{s}"])
+        assert torch.allclose(got, want, rtol=5e-3, atol=5e-3), (s, (got - want).abs().max())
+    assert torch.allclose(out["final_features"].cpu(), torch.from_numpy(g["final_features"]), rtol=5e-3, atol=5e-3)
+    assert torch.allclose(out["vit_features"].mean((2, 3)).cpu(), torch.from_numpy(g["vit_features_mean"]), rtol=5e-3, atol=5e-3)
+    for k in ("fused_small", "fused_medium", "fused_large"):
+        assert torch.allclose(out["fused_features"][k].mean((2, 3)).cpu(), torch.from_numpy(g[f"{k}_chanmean"]), rtol=5e-3, atol=5e-3)
+    # decode inside the model: boxes of the GPU kernel == oracle decode of the same raw predictions
+    for s in range(3):
+        d = detect_ref.yolo_decode(out["predictions"][f"scale_{s}"].cpu(), detect_ref.anchors_wh(s))
+        assert torch.allclose(out["decoded"][f"scale_{s}"]["boxes"].cpu(), d["boxes"], rtol=1e-5, atol=1e-6)
+        assert torch.equal(out["decoded"][f"scale_{s}"]["class_indices"].cpu(), d["class_indices"])
+
+
+def test_bf16_kernel_path_tracks_reference_and_uses_the_k2_kernels(model, golden):
+    import hvs_b200
+    g = golden("hybrid_vision")
+    x = torch.from_numpy(g["x"]).to(DEV)
+    with torch.no_grad():
+        model(x)
+        before = hvs_b200._lib.launch_count()
+        out = model(x)
+    launches = hvs_b200._lib.launch_count() - before
+    # 76 layers x (LN + 4 GEMMs) (+1 LN for D > 512), 14 RMSNorms, 3 decodes; coefficients cached: no refresh launch
+    assert launches == 76 * 5 + 2 + 14 + 3, launches
+    for s in range(3):
+        got, want = out["predictions"][f"scale_{s}"].cpu(), torch.from_numpy(g[f"pred{s}"])
+        rel = ((got - want).norm() / want.norm()).item()
+        print(f"[hybrid bf16] scale {s}: relative error of raw predictions vs the reference's fp32 CPU forward {rel:.3e}")
+        assert rel < 0.15, (s, rel)
+    ff, want = out["final_features"].cpu(), torch.from_numpy(g["final_features"])
+    assert ((ff - want).norm() / want.norm()) < 0.15
+
+
+def test_channels_last_is_a_free_layout_fold(model, golden):
+    g = golden("hybrid_vision")
+    x = torch.from_numpy(g["x"]).to(DEV)
+    with torch.no_grad():
+        a = model(x)["predictions"]
+        model.to(memory_format=torch.channels_last)
+        try:
+            b = model(x.contiguous(memory_format=torch.channels_last))["predictions"]
+        finally:
+            model.to(memory_format=torch.contiguous_format)
+    for s in range(3):
+        rel = ((a[f"scale_{s}"] - b[f"scale_{s}"]).norm() / a[f"scale_{s}"].norm()).item()
+        assert rel < 2e-2, rel                                      # cuDNN picks other conv algorithms; same math
+
+
+def test_detect_and_graph_replay_are_deterministic(model):
+    x = torch.randn(1, 3, 256, 256, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    with torch.no_grad():
+        dets = model.detect(x, confidence_threshold=0.25, iou_threshold=0.45, max_detections=100)
+        assert len(dets) == 1 and dets[0]["boxes"].shape[1] == 4 and dets[0]["boxes"].shape[0] <= 100
+        assert dets[0]["labels"].dtype == torch.int64
+        # whole forward under a CUDA graph (streaming config 5): replay == eager, and replays are bitwise identical
+        model.detection_head.want_scores = False
+        static_x = x.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                model(static_x)
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = model(static_x)
+        eager = {k: v.clone() for k, v in model(x)["predictions"].items()}
+        graph.replay()
+        first = {k: v.clone() for k, v in out["predictions"].items()}
+        graph.replay()
+        for k in first:
+            assert torch.equal(first[k], out["predictions"][k])
+            assert torch.equal(first[k], eager[k])
+        model.detection_head.want_scores = True
+
+
+def test_stability_metrics_match_reference_values(golden):
+    """Row a5: get_stability_metrics / the monitoring the reference does inside its training forward
+    (manifold_layers.py:282-341) against the values the reference module produced."""
+    import hvs_b200
+    g = golden("stability")
+    for tag, (d, n) in {"d48n2": (48, 2), "d64n4": (64, 4)}.items():
+        mod = hvs_b200.ManifoldHyperConnection(d, expansion_rate=n, dropout_rate=0.0, use_mixed_precision=False)
+        keys = {k.split("/p/")[1] for k in g.files if k.startswith(tag + "/p/")}
+        sd = {k: torch.from_numpy(g[f"{tag}/p/{k}"]) for k in keys}
+        for k in ("signal_ratio_history", "eigenvalues", "gradient_norms", "sinkhorn.convergence_history"):
+            sd[k] = torch.zeros_like(sd[k])                         # the module has not run yet
+        mod.load_state_dict(sd)
+        mod = mod.to(DEV).train()
+        with torch.no_grad():
+            for i in range(3):
+                mod(torch.from_numpy(g[f"{tag}/x{i}"]).to(DEV))
+        m = mod.get_stability_metrics()
+        for k in ("max_eigenvalue", "min_eigenvalue", "eigenvalue_range", "signal_ratio_mean", "signal_ratio_std",
+                  "signal_ratio_min", "signal_ratio_max", "signal_ratio", "row_sum_error", "col_sum_error"):
+            want = float(g[f"{tag}/m/{k}"])
+            assert abs(m[k] - want) <= 2e-4 * max(abs(want), 1e-2), (tag, k, m[k], want)
+        assert abs(m["sk_convergence"]["final_convergence"] - float(g[f"{tag}/m/final_convergence"])) < 2e-6
+        assert torch.allclose(mod.eigenvalues.cpu(), torch.from_numpy(g[f"{tag}/p/eigenvalues"]), atol=2e-5)

@@ -226,7 +226,15 @@ def test_gemm_rejects_bad_shapes():
 
 
 # ----------------------------------------------------------------------------- the module's fused inference path
-def _module_pair(d, n, hidden=None, seed=0):
+# Conditioning.  At the reference's initialisation (xavier, gain 0.1: H_pre ~ 0.5, H_post ~ 1, H_res ~ 1/D everywhere) the
+# input of norm_post is a per-token CONSTANT plus a variation of relative size ~1e-2...1e-4, and LayerNorm divides by
+# that variation.  Under the reference's own CUDA convention (torch.cuda.amp.autocast(bfloat16), :248) the matrices are
+# rounded to bf16 (relative step 2^-8), which is as large as the variation: the module's output is then dominated by
+# rounding and ANY two correct bf16 implementations (this one, cuBLAS under autocast) differ by O(1) after the norm.
+# So parity is asserted (a) on the LayerNorm INPUT at bf16-operand accuracy for the reference's init, (b) on the module
+# output for well-conditioned ("trained-like", raw std 1) coefficients, and (c) on the output for the reference's init
+# with the bound scaled by the row's condition number max|pre| / std(pre).
+def _module_pair(d, n, hidden=None, seed=0, raw_std=None):
     import hvs_b200
     torch.manual_seed(seed)
     mod = hvs_b200.ManifoldHyperConnection(d, expansion_rate=n, hidden_dim=hidden)
@@ -235,14 +243,17 @@ def _module_pair(d, n, hidden=None, seed=0):
             p.add_(0.1 * torch.randn_like(p))
         for p in (mod.norm_pre.bias, mod.norm_post.bias, mod.mlp[0].bias, mod.mlp[3].bias):
             p.add_(0.05 * torch.randn_like(p))
+        if raw_std is not None:
+            for p in (mod.H_pre_raw, mod.H_post_raw, mod.H_res_raw):
+                p.normal_(0, raw_std)
     params = {k: v.detach().clone() for k, v in mod.state_dict().items()}
     return mod.to(DEV).eval(), params
 
 
-def _bf16_convention_reference(x, p):
-    """The reference's CUDA-autocast arithmetic in fp64 on bf16-rounded operands (what the kernels compute up to fp32
-    accumulation order): LN fp32 -> bf16, every matmul operand bf16, intermediate activations bf16."""
-    r = lambda t: t.to(torch.bfloat16).double()
+def _oracle_pre_and_out(x, p, bf16_operands):
+    """LayerNorm input and module output of the reference arithmetic (:248-267), in fp64; with bf16_operands the
+    reference's CUDA-autocast convention (LN fp32 -> bf16, every matmul operand and intermediate activation bf16)."""
+    r = (lambda t: t.to(torch.bfloat16).double()) if bf16_operands else (lambda t: t.double())
     hp, hq, hr = mhc_ref.constrained_matrices(p["H_pre_raw"], p["H_post_raw"], p["H_res_raw"])
     d = x.shape[-1]
     xn = r(torch.nn.functional.layer_norm(x.float(), (d,), p["norm_pre.weight"], p["norm_pre.bias"]))
@@ -250,14 +261,33 @@ def _bf16_convention_reference(x, p):
     z = r(torch.nn.functional.gelu(z @ r(p["mlp.0.weight"]).t() + p["mlp.0.bias"].double()).float())
     z = r(torch.nn.functional.gelu(z @ r(p["mlp.3.weight"]).t() + p["mlp.3.bias"].double()).float())
     pre = z @ r(hq) + r(x) @ r(hr)
-    return torch.nn.functional.layer_norm(pre, (d,), p["norm_post.weight"].double(), p["norm_post.bias"].double())
+    return pre, torch.nn.functional.layer_norm(pre, (d,), p["norm_post.weight"].double(), p["norm_post.bias"].double())
 
 
-@pytest.mark.parametrize("d,n,hidden,t", [(64, 4, None, 1000), (32, 4, None, 4099), (256, 2, None, 401), (512, 4, None, 300),
-                                          (256, 2, 1024, 257), (1024, 2, None, 130), (1792, 2, None, 1), (128, 4, None, 77)])
-def test_module_fused_forward_vs_oracle(d, n, hidden, t):
+def _fused_pre(mod, x):
+    """The fused path's LayerNorm input (same launches as _forward_fused with the last epilogue switched off)."""
     import hvs_b200
-    mod, p = _module_pair(d, n, hidden, seed=d + n)
+    from hvs_b200 import _lib
+    from hvs_b200.mhc import _pad64
+    st = mod._fresh_state()
+    w1, w2 = mod._mlp_bf16()
+    dp = _pad64(mod.input_dim)
+    xn, xb = hvs_b200.ops.layernorm_fwd(x, mod.norm_pre.weight.detach(), mod.norm_pre.bias.detach(), mod.norm_pre.eps,
+                                        out_dtype=torch.bfloat16, out_ld=dp, want_copy=True, copy_ld=dp)
+    z = hvs_b200.ops.gemm_bf16(xn, st.h_pre_t)
+    z = hvs_b200.ops.gemm_bf16(z, w1, bias=mod.mlp[0].bias.detach(), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU)
+    z = hvs_b200.ops.gemm_bf16(z, w2, bias=mod.mlp[3].bias.detach(), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU)
+    return hvs_b200.ops.gemm_bf16(z, st.h_post_t, xb, st.h_res_t, out_dtype=torch.float32)
+
+
+SHAPES = [(64, 4, None, 1000), (32, 4, None, 4099), (256, 2, None, 401), (512, 4, None, 300), (256, 2, 1024, 257),
+          (1024, 2, None, 130), (1792, 2, None, 1), (128, 4, None, 77)]
+
+
+@pytest.mark.parametrize("d,n,hidden,t", SHAPES)
+def test_module_fused_forward_trained_like_coefficients(d, n, hidden, t):
+    import hvs_b200
+    mod, p = _module_pair(d, n, hidden, seed=d + n, raw_std=1.0)
     assert mod.fused_supported()
     x = _rand(t, d, seed=t) * 1.5 + 0.2
     before = hvs_b200._lib.launch_count()
@@ -266,16 +296,41 @@ def test_module_fused_forward_vs_oracle(d, n, hidden, t):
     launches = hvs_b200._lib.launch_count() - before
     assert launches == (7 if d > 512 else 6)                        # coefficients (1, first call only) + LN + 4 GEMMs (+ LN)
     assert y.dtype == torch.float32 and y.shape == x.shape
-    tight = _bf16_convention_reference(x, p)
-    assert (y.cpu().double() - tight).abs().max() < 2e-2           # bf16 re-rounding of intermediates may flip an ulp
-    assert (y.cpu().double() - tight).abs().mean() < 1e-3
-    oracle = mhc_ref.mhc_module_forward(x, p)                       # fp32 oracle (the reference's CPU arithmetic)
-    err = (y.cpu() - oracle).abs()
-    assert err.max() < 2.0 ** -4 and err.mean() < 2.0 ** -7, (err.max().item(), err.mean().item())
+    _, tight = _oracle_pre_and_out(x, p, True)
+    _, exact = _oracle_pre_and_out(x, p, False)
+    e_tight = (y.cpu().double() - tight).abs()
+    e_exact = (y.cpu().double() - exact).abs()
+    print(f"[k2 trained-like d={d} n={n} t={t}] vs bf16-convention ref max {e_tight.max():.2e} mean {e_tight.mean():.2e}; "
+          f"vs fp32 oracle max {e_exact.max():.2e} mean {e_exact.mean():.2e}")
+    assert e_tight.max() < 3e-2 and e_tight.mean() < 1e-3          # same operands: only accumulation order / 1-ulp re-rounding
+    assert e_exact.max() < 2.0 ** -3 and e_exact.mean() < 2.0 ** -6   # bf16 operands vs the fp32 oracle, output scale ~1
     with torch.no_grad():
         y2 = mod(x.to(DEV))
     assert torch.equal(y, y2)
     assert hvs_b200._lib.launch_count() - before == launches + launches - 1      # cached coefficients: no second refresh
+
+
+@pytest.mark.parametrize("d,n,hidden,t", SHAPES)
+def test_module_fused_forward_reference_init(d, n, hidden, t):
+    """The reference's own initialisation: LayerNorm input at bf16-operand accuracy; output within the bound scaled by
+    the row's conditioning (see the note above)."""
+    mod, p = _module_pair(d, n, hidden, seed=d + n)
+    x = _rand(t, d, seed=t) * 1.5 + 0.2
+    with torch.no_grad():
+        y = mod(x.to(DEV)).cpu().double()
+        pre = _fused_pre(mod, x.to(DEV)).cpu().double()
+    pre_c, out_c = _oracle_pre_and_out(x, p, True)
+    pre_o, out_o = _oracle_pre_and_out(x, p, False)
+    scale = pre_o.abs().amax(-1, keepdim=True)
+    e_c = ((pre - pre_c).abs() / scale).max().item()
+    e_o = ((pre - pre_o).abs() / scale).max().item()
+    cond = (scale / pre_o.std(-1, keepdim=True).clamp_min(1e-30))
+    out_err = ((y - out_c).abs() / cond).max().item()
+    print(f"[k2 reference-init d={d} t={t}] LN input rel err: vs convention {e_c:.2e}, vs fp32 oracle {e_o:.2e}; "
+          f"median condition {cond.median().item():.1f}; output err / condition {out_err:.2e}; raw output err {(y - out_o).abs().max():.2e}")
+    assert e_c < 1e-5                                               # same bf16 operands: fp32 accumulation order only
+    assert e_o < 2.0 ** -6                                          # bf16 operand rounding relative to the row's magnitude
+    assert out_err < 2e-5 * 4
 
 
 def test_module_fused_forward_golden_and_shapes(golden):
@@ -284,22 +339,29 @@ def test_module_fused_forward_golden_and_shapes(golden):
     for tag, (d, n) in {"d64n4": (64, 4), "d32n2": (32, 2)}.items():
         mod = hvs_b200.ManifoldHyperConnection(d, expansion_rate=n).to(DEV).eval()
         keys = {k.split("/p/")[1] for k in g.files if k.startswith(tag + "/p/")}
-        mod.load_state_dict({k: torch.from_numpy(g[f"{tag}/p/{k}"]) for k in keys})
+        p = {k: torch.from_numpy(g[f"{tag}/p/{k}"]) for k in keys}
+        mod.load_state_dict(p)
         x = torch.from_numpy(g[f"{tag}/x"])
+        x2 = x.reshape(-1, d)
         with torch.no_grad():
             y = mod(x.to(DEV))
-        want = torch.from_numpy(g[f"{tag}/y"])
-        assert y.shape == want.shape
-        err = (y.cpu() - want).abs()
-        assert err.max() < 2.0 ** -4 and err.mean() < 2.0 ** -7
+            pre = _fused_pre(mod, x2.to(DEV)).cpu().double()
+        assert y.shape == x.shape
+        pre_o, out_o = _oracle_pre_and_out(x2, p, False)
+        assert (out_o.float().reshape(x.shape) - torch.from_numpy(g[f"{tag}/y"])).abs().max() < 1e-4     # the fixture is this arithmetic
+        scale = pre_o.abs().amax(-1, keepdim=True)
+        assert ((pre - pre_o).abs() / scale).max() < 2.0 ** -6
+        _, out_c = _oracle_pre_and_out(x2, p, True)
+        cond = scale / pre_o.std(-1, keepdim=True)
+        assert ((y.cpu().double().reshape(-1, d) - out_c).abs() / cond).max() < 8e-5
         hr = mod.constrained_matrices()[2].cpu()
         assert ((hr - torch.from_numpy(g[f"{tag}/H_res"])).abs() / torch.from_numpy(g[f"{tag}/H_res"])).max() < 1e-5
     # bf16 input, empty input
-    mod, p = _module_pair(64, 4)
+    mod, p = _module_pair(64, 4, raw_std=1.0)
     with torch.no_grad():
         xb = (_rand(50, 64, seed=1)).to(torch.bfloat16)
         yb = mod(xb.to(DEV))
-        assert (yb.cpu() - mhc_ref.mhc_module_forward(xb.float(), p)).abs().max() < 2.0 ** -4
+        assert (yb.cpu() - mhc_ref.mhc_module_forward(xb.float(), p)).abs().max() < 2.0 ** -3
         assert mod(torch.zeros(0, 64, device=DEV)).shape == (0, 64)
 
 
@@ -322,29 +384,36 @@ def test_refresh_static_coefficients_batches_all_modules():
 
 
 def test_module_training_path_gradients_vs_oracle():
-    """Training (grad mode): coefficient forward/backward on the kernels, token path in torch ops under bf16 autocast.
-    Gradients against autograd through the fp32 oracle at the bf16-operand tolerance."""
+    """Training (grad mode): coefficient forward / backward on the kernels (hvs_mhc_static_coeffs[_bwd]), token path in
+    torch ops.  fp32 token path (use_mixed_precision=False) against autograd through the fp32 oracle at 1e-3; the bf16
+    autocast path on trained-like coefficients at the bf16-operand tolerance."""
     import hvs_b200
-    mod, p = _module_pair(64, 4, seed=3)
-    mod.train()
-    mod.dropout.p = 0.0
-    for m in mod.mlp:
-        if isinstance(m, torch.nn.Dropout):
-            m.p = 0.0
-    x = _rand(200, 64, seed=8)
-    dy = _rand(200, 64, seed=9)
-    xg = x.to(DEV).requires_grad_(True)
-    mod(xg).backward(dy.to(DEV))
-    leaf = {k: v.clone().requires_grad_(True) if v.dtype == torch.float32 and "history" not in k and k not in ("gradient_norms", "eigenvalues") else v
-            for k, v in p.items()}
-    xl = x.clone().requires_grad_(True)
-    mhc_ref.mhc_module_forward(xl, leaf).backward(dy)
-    def rel(a, b):
-        return ((a.cpu().double() - b.double()).norm() / b.double().norm()).item()
-    assert rel(xg.grad, xl.grad) < 3e-2
-    assert rel(mod.H_res_raw.grad, leaf["H_res_raw"].grad) < 3e-2
-    assert rel(mod.H_pre_raw.grad, leaf["H_pre_raw"].grad) < 3e-2
-    assert rel(mod.H_post_raw.grad, leaf["H_post_raw"].grad) < 3e-2
-    assert rel(mod.mlp[0].weight.grad, leaf["mlp.0.weight"].grad) < 3e-2
-    mod.record_gradient_norms()
-    assert torch.allclose(mod.gradient_norms.cpu(), torch.stack([mod.H_pre_raw.grad.norm(), mod.H_post_raw.grad.norm(), mod.H_res_raw.grad.norm()]).cpu())
+    for mixed, raw_std, tol in ((False, None, 2e-3), (False, 1.0, 2e-3), (True, 1.0, 6e-2)):
+        mod, p = _module_pair(64, 4, seed=3, raw_std=raw_std)
+        mod.use_mixed_precision = mixed
+        mod.train()
+        mod.dropout.p = 0.0
+        for m in mod.mlp:
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        x = _rand(200, 64, seed=8)
+        dy = _rand(200, 64, seed=9)
+        xg = x.to(DEV).requires_grad_(True)
+        before = hvs_b200._lib.launch_count()
+        mod(xg).backward(dy.to(DEV))
+        assert hvs_b200._lib.launch_count() - before == 2           # coefficients forward + backward: nothing unrolled
+        grad_keys = ("H_pre_raw", "H_post_raw", "H_res_raw", "mlp.0.weight", "mlp.0.bias", "mlp.3.weight", "mlp.3.bias",
+                     "norm_pre.weight", "norm_pre.bias", "norm_post.weight", "norm_post.bias")
+        leaf = {k: (v.clone().requires_grad_(True) if k in grad_keys else v) for k, v in p.items()}
+        xl = x.clone().requires_grad_(True)
+        mhc_ref.mhc_module_forward(xl, leaf).backward(dy)
+
+        def rel(a, b):
+            return ((a.cpu().double() - b.double()).norm() / b.double().norm()).item()
+        got = dict(mod.named_parameters())
+        errs = {k: rel(got[k].grad, leaf[k].grad) for k in grad_keys}
+        errs["x"] = rel(xg.grad, xl.grad)
+        print(f"[k2 training mixed={mixed} raw_std={raw_std}] " + " ".join(f"{k}:{v:.1e}" for k, v in errs.items()))
+        assert max(errs.values()) < tol, errs
+        mod.record_gradient_norms()
+        assert torch.allclose(mod.gradient_norms.cpu(), torch.stack([mod.H_pre_raw.grad.norm(), mod.H_post_raw.grad.norm(), mod.H_res_raw.grad.norm()]).cpu())

@@ -376,7 +376,7 @@ def test_more_than_24_iterations_is_inference_only():
 def test_bench_configuration_full_size_against_oracle():
     """BASELINE configs[1] as benchmarked: T = 2^20, n = 4, C = 512, bench.py's parameters.  Forward y / coefficients
     and the FUSED backward's dx are compared with the oracle on 4 608 tokens taken from the first, middle and LAST
-    tiles (plus the tokens straddling the 2^31-element boundary of the flat index); parameter gradients are compared
+    tiles (the middle slice straddles the 2^31-byte offset); parameter gradients are compared
     with the oracle on one 2^16-token slice (they are sums over tokens), and the full-size gradients must equal the
     sum of the 16 slices' gradients."""
     import hvs_b200
@@ -393,9 +393,9 @@ def test_bench_configuration_full_size_against_oracle():
     y, _, co = hvs_b200.ops.mhc_stream_fwd(x, *P, want_coeffs=True, saved=saved)
     full = hvs_b200.ops.mhc_stream_bwd_saved(x, dy, saved, *P)
     torch.cuda.synchronize()
-    mid = t // 2
-    edge = (1 << 31) // 2048                                      # token whose first element has flat index 2^31
-    idx = torch.cat([torch.arange(0, 1536), torch.arange(mid - 512, mid + 512), torch.arange(edge - 256, edge + 256),
+    mid = t // 2                                                  # byte offset 2^31 of x / y / dy / dx falls here
+    q = 3 * t // 4 + 5
+    idx = torch.cat([torch.arange(0, 1536), torch.arange(mid - 512, mid + 512), torch.arange(q - 256, q + 256),
                      torch.arange(t - 1536, t)])
     assert idx.numel() == 4608
     xs, dys = x[idx.to(dev)].cpu(), dy[idx.to(dev)].cpu()
