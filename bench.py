@@ -21,6 +21,13 @@ roofline     dominant kernel (the fused single-pass backward, dx + every paramet
              saved statistics (1.1 % on top of the 20480 B/token; not counted in the algorithmic figure)
 cpu_baseline oracle/ (a port of the reference's PyTorch arithmetic) timed on the host cores, rank 0,
              N = 1 only, bounded sample of the same workload
+k2           BASELINE.md's second reading of configs[1]: ManifoldHyperConnection(512, expansion_rate=4) on [2^20, 512]
+             bf16 (tensor-core bound): TFLOP/s of the fused tcgen05 path and of the same module's library path
+detect       decode + two-stage NMS at batch 64 / 640x640 grids (SURVEY D18 worst case and objectness bias -4)
+hybrid_vision  the other half of BASELINE.json's metric ("hybrid_vision img/s at 1/2/4/8 B200"): configs[2] batch-64
+             inference sharded 64/N with no collective, configs[3] bf16 DDP training at 16 images / GPU (gradient
+             all-reduce over NCCL), configs[4] streaming batch-1 p50 / p99 under a CUDA graph; configs[0] (the CPU
+             forward) is its cpu_baseline.  --skip-hybrid / --skip-extras leave these legs out
 clocks       SM clock and throttle reasons sampled through NVML every 2 ms inside the timed region
 --impl reference   times that CPU implementation alone (the reference is pure PyTorch; its own modules
              cannot travel to the GPU box)
@@ -180,6 +187,102 @@ def cpu_reference_run(tokens: int, steps: int, warmup: int):
     return tokens / dt, dt, torch.get_num_threads()
 
 
+def cpu_hybrid_baseline():
+    """BASELINE configs[0]: whole-model CPU forward (+ decode + two-stage NMS), batch 1 at 640x640, fp32, all host
+    threads -- the oracle port of the reference path (oracle/hybrid_ref.py)."""
+    import torch
+    from oracle import hybrid_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    ips, dt, threads = hybrid_ref.cpu_inference_img_per_s(batch=1, image=640, steps=2, warmup=1)
+    return {"value": ips, "unit": "img/s", "cores": threads, "kind": "port", "s_per_image": dt,
+            "sample": "hybrid_vision forward + decode + two-stage NMS, batch 1, 640x640, fp32 (BASELINE configs[0]); host wiring of "
+                      "hvs_b200/hybrid_vision.py with oracle/ CPU leaves, mean of 2 after 1 warm-up"}
+
+
+def cpu_detect_baseline():
+    import torch
+    from oracle import detect_ref
+    g = torch.Generator().manual_seed(0)
+    preds = [torch.randn(2, 3, hw, hw, 85, generator=g) * 0.5 for hw in (80, 40, 20)]
+    t0 = time.perf_counter()
+    dec = [detect_ref.yolo_decode(p, detect_ref.anchors_wh(s)) for s, p in enumerate(preds)]
+    detect_ref.post_process(dec, 0.25, 0.45, 100)
+    dt = (time.perf_counter() - t0) / 2
+    return {"value": 1.0 / dt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "decode + two-stage NMS on 2 images (D18 worst case), oracle/detect_ref.py"}
+
+
+def run_extras(args, dev, world, rank):
+    """K2 microbenchmark, detection tail, and the hybrid_vision configurations (every rank runs them; sharded legs take
+    the max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from hvs_b200 import harness
+
+    def rank_max(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    tf_burst = float(peaks.get("bf16_tflops", 1590.0))
+    out = {}
+    k2 = harness.k2_microbench(dev)
+    k2["frac_of_bf16_sustained"] = k2["tflops_fused"] / tf_sus
+    k2["frac_of_bf16_burst"] = k2["tflops_fused"] / tf_burst
+    k2["peak_tflops"] = {"sustained": tf_sus, "burst": tf_burst, "source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}
+    k2["speedup_vs_library_path"] = k2["ms_library_path"] / k2["ms_fused"]
+    out["k2"] = k2
+    worst = harness.detect_tail(dev, 64, 0.0)
+    real = harness.detect_tail(dev, 64, -4.0)
+    hbm = load_peaks()[0]
+    for d in (worst, real):
+        d["decode_frac_of_hbm"] = d["decode_GBps"] / hbm
+    out["detect"] = {"worst_case_D18": worst, "objectness_bias_-4": real}
+    torch.cuda.empty_cache()
+    if args.skip_hybrid:
+        return out
+    model = harness.build_model(dev, seed=0)
+    per = 64 // world
+    inf = harness.inference_sharded(model, dev, world, rank, 64, 640)
+    inf_real = harness.inference_sharded(model, dev, world, rank, 64, 640, objectness_bias=-4.0, steps=3, warmup=1)
+    inf_e2e = harness.inference_sharded(model, dev, world, rank, 64, 640, steps=3, warmup=1, host_input=True)
+    ms_inf, ms_real, ms_e2e = rank_max(inf["ms_per_step"]), rank_max(inf_real["ms_per_step"]), rank_max(inf_e2e["ms_per_step"])
+    ips = 64 / (ms_inf * 1e-3)
+    hv = {"inference": {"workload": "BASELINE configs[2]: batch 64 at 640x640, bf16 autocast + channels_last, decode + two-stage NMS (conf 0.25, iou 0.45, max 100), sharded 64/N, no collective (strong scaling)",
+                        "img_per_s": ips, "ms_per_batch": ms_inf, "images_per_gpu": per,
+                        "model_tflops": ips * harness.FWD_GFLOP_PER_IMAGE_640 / 1e3,
+                        "frac_of_bf16_sustained_per_gpu": ips * harness.FWD_GFLOP_PER_IMAGE_640 / 1e3 / world / tf_sus,
+                        "img_per_s_objectness_bias_-4": 64 / (ms_real * 1e-3), "mean_detections": inf["mean_detections"],
+                        "hvs_launches_per_step": inf["hvs_launches_per_step"],
+                        "e2e": {"img_per_s": 64 / (ms_e2e * 1e-3), "ms_per_batch": ms_e2e, "h2d_bytes_per_step": inf_e2e["h2d_bytes_per_step"],
+                                "d2h_bytes_per_step": inf_e2e["d2h_bytes_per_step"], "note": "per rank: pinned host images -> H2D -> forward -> decode -> NMS -> detections D2H, all timed"}}}
+    torch.cuda.empty_cache()
+    stream = harness.streaming_latency(model, dev, frames=args.stream_frames)
+    hv["streaming"] = dict(stream, workload="BASELINE configs[4]: batch-1 640x640 frames, whole forward + decode + NMS in one CUDA graph")
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats(dev)
+    tr = harness.training_ddp(model, dev, world, rank, args.train_batch, 640)
+    ms_tr = rank_max(tr["ms_per_step"])
+    tips = world * tr["batch_per_gpu"] / (ms_tr * 1e-3)
+    hv["training"] = dict(tr, workload="BASELINE configs[3]: bf16 autocast training, synthetic COCO-shaped dense targets, YOLOLoss, AdamW, "
+                                       "DistributedDataParallel gradient all-reduce over NCCL (weak scaling)",
+                          ms_per_step=ms_tr, img_per_s=tips, model_tflops=tips * 3 * harness.FWD_GFLOP_PER_IMAGE_640 / 1e3,
+                          frac_of_bf16_sustained_per_gpu=tips * 3 * harness.FWD_GFLOP_PER_IMAGE_640 / 1e3 / world / tf_sus)
+    out["hybrid_vision"] = hv
+    out["hybrid_vision_img_per_s"] = ips
+    out["hybrid_vision_train_img_per_s"] = tips
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -198,6 +301,10 @@ def run_reference(args):
         "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.skip_extras and not args.skip_hybrid:
+        hb = cpu_hybrid_baseline()
+        line["hybrid_vision"] = {"cpu_baseline": hb, "inference": {"img_per_s": hb["value"], "workload": hb["sample"]}}
+        line["hybrid_vision_img_per_s"] = hb["value"]
     print(json.dumps(line))
 
 
@@ -210,6 +317,10 @@ def main():
     ap.add_argument("--impl", default="hvs_b200", choices=["hvs_b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="no k2 / detect / hybrid_vision legs")
+    ap.add_argument("--skip-hybrid", action="store_true", help="no hybrid_vision legs")
+    ap.add_argument("--stream-frames", type=int, default=300)
+    ap.add_argument("--train-batch", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -314,6 +425,11 @@ def main():
     e2e_value = world * T / float(te.item())
     row_bytes = N_STREAMS * CHANNELS * 2
     grad_bytes = 4 * (N_STREAMS * CHANNELS * LOGITS + LOGITS + 3 + N_STREAMS * CHANNELS)
+    del x, dy, xh, dyh, yh, dxh, saved
+    torch.cuda.empty_cache()
+    extras = {}
+    if not args.skip_extras:
+        extras = run_extras(args, dev, world, rank)
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -351,6 +467,11 @@ def main():
             tps, dt, threads = cpu_reference_run(8192, 2, 1)
             line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "8192 tokens fwd+bwd, oracle/mhc_ref.py (torch fp32 CPU), mean of 2 steps after 1 warm-up"}
+        line.update(extras)
+        if world == 1 and not args.no_cpu_baseline and "hybrid_vision" in line:
+            line["hybrid_vision"]["cpu_baseline"] = cpu_hybrid_baseline()
+            if "detect" in line:
+                line["detect"]["cpu_baseline"] = cpu_detect_baseline()
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if world > 1:

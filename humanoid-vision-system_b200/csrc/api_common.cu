@@ -14,6 +14,18 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// The encode is a driver-API call and needs the primary context current on THIS thread; a thread that has only been
+// handed a device ordinal (e.g. PyTorch's autograd workers) has not bound it yet.  cudaFree(nullptr) binds it -- once
+// per thread, because it is not allowed while a stream of the thread is being captured into a CUDA graph (the warm-up
+// run every capture needs has then already done it).
+static void bind_primary_context_once() {
+    thread_local bool bound = false;
+    if (!bound) {
+        bind_primary_context_once();
+        bound = true;
+    }
+}
+
 static EncodeTiledFn encode_fn() {
     // function-local static: initialised exactly once, thread-safe (C++11), so a second thread (e.g. an autograd
     // worker) can never observe a half-initialised lookup
@@ -31,9 +43,7 @@ static EncodeTiledFn encode_fn() {
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return HVS_ERR_DRIVER;
-    // The encode is a driver-API call and needs the primary context current on THIS thread; a thread that
-    // has only been handed a device ordinal (e.g. PyTorch's autograd workers) has not bound it yet.
-    cudaFree(nullptr);
+    bind_primary_context_once();
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {cols * 2};
     cuuint32_t box[2] = {64, box_rows};
@@ -50,7 +60,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
 int make_tmap_bf16_2d_ld(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return HVS_ERR_DRIVER;
-    cudaFree(nullptr);
+    bind_primary_context_once();
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {ld * 2};
     cuuint32_t box[2] = {64, box_rows};
@@ -69,7 +79,7 @@ int make_tmap_bf16_2d_ld(CUtensorMap* out, const void* gptr, uint64_t rows, uint
 int make_tmap_bf16_streams3d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return HVS_ERR_DRIVER;
-    cudaFree(nullptr);
+    bind_primary_context_once();
     cuuint64_t gdim[3] = {512, tokens, 4};
     cuuint64_t gstride[2] = {4096, 1024};       // bytes: token stride, stream stride
     cuuint32_t box[3] = {64, box_tokens, 4};
@@ -88,7 +98,7 @@ int make_tmap_bf16_streams3d(CUtensorMap* out, const void* gptr, uint64_t tokens
 int make_tmap_bf16_streams4d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens, uint32_t box_streams) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return HVS_ERR_DRIVER;
-    cudaFree(nullptr);
+    bind_primary_context_once();
     cuuint64_t gdim[4] = {64, tokens, 8, 4};
     cuuint64_t gstride[3] = {4096, 128, 1024};  // bytes: token, 64-channel block, stream
     cuuint32_t box[4] = {64, box_tokens, 8, box_streams};

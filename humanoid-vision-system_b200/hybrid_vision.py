@@ -42,6 +42,15 @@ def mhc_over_pixels(mhc: nn.Module, x: torch.Tensor) -> torch.Tensor:
     return y.reshape(b, h, w, c).permute(0, 3, 1, 2)
 
 
+def to_channels_last(model: nn.Module) -> nn.Module:
+    """Put every convolution weight in channels_last (nn.Module.to(memory_format=...) would also try the 5-D anchor
+    buffer).  Activations follow the input's format through cuDNN, BatchNorm and the elementwise ops."""
+    for m in model.modules():
+        if isinstance(m, nn.Conv2d):
+            m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+    return model
+
+
 class ConvMHCLayer(nn.Module):
     """conv -> BN -> act -> mHC over pixels -> squeeze-excite gate -> (+ identity)   (vision_backbone.py:10-134)."""
 

@@ -416,6 +416,7 @@ class ManifoldHyperConnection(nn.Module):
         self.dtype = torch.bfloat16 if use_mixed_precision else torch.float32
         self._state: Optional[_CoeffState] = None
         self.monitor_signal_ratio = True
+        self.output_dtype: Optional[torch.dtype] = None      # None: fp32 like the reference (its last op is a LayerNorm under autocast)
         self._initialize_weights()
 
     def _initialize_weights(self):                       # :191-203
@@ -457,9 +458,10 @@ class ManifoldHyperConnection(nn.Module):
             st.wkey = key
         return st.w1, st.w2
 
-    def _forward_fused(self, x2: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    def _forward_fused(self, x2: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
         """x2 [T, D] fp32 / bf16 -> [T, D] (:248-267, eval mode: dropout is the identity)."""
         from . import _lib
+        out_dtype = out_dtype or self.output_dtype or torch.float32
         st = self._fresh_state()
         w1, w2 = self._mlp_bf16()
         d = self.input_dim
@@ -483,6 +485,13 @@ class ManifoldHyperConnection(nn.Module):
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if x.is_cuda and not needs_grad and not self.training and self.fused_supported() and x.dtype in (torch.float32, torch.bfloat16):
             return self._forward_fused(x.reshape(-1, shape[-1])).reshape(shape)
+        return self.forward_library(x)
+
+    def forward_library(self, x: torch.Tensor) -> torch.Tensor:
+        """The token path in torch ops (library GEMMs under bf16 autocast, exactly the reference's CUDA execution):
+        the training path (autograd sees it), the path for shapes the kernels do not take, and the baseline the fused
+        path is benchmarked against."""
+        shape = x.shape
         if x.dim() > 2:
             x = x.reshape(shape[0], -1, shape[-1])
         x_in = x
