@@ -29,6 +29,11 @@ class CoeffJob(ctypes.Structure):
                 ("D", c_int32), ("H", c_int32), ("Dp", c_int32), ("reserved", c_int32)]
 
 
+class GradTensor(ctypes.Structure):
+    """struct hvs_grad_tensor."""
+    _fields_ = [("grad", c_void_p), ("numel", c_int64), ("group", c_int32), ("reserved", c_int32)]
+
+
 class CoeffGrad(ctypes.Structure):
     """struct hvs_coeff_grad."""
     _fields_ = [("d_h_pre", c_void_p), ("d_h_post", c_void_p), ("d_h_res", c_void_p),
@@ -71,6 +76,10 @@ _SIGNATURES = {
     "hvs_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p,
                               c_void_p, c_float, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p]),
     "hvs_profile_kernel_ms": (c_int, [POINTER(c_float)]),
+    "hvs_grad_clip_dual_workspace": (c_size_t, [POINTER(GradTensor), c_int]),
+    "hvs_grad_clip_dual": (c_int, [POINTER(GradTensor), c_int, c_float, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hvs_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_int,
+                                  POINTER(c_float), POINTER(c_float), c_void_p]),
     "hvs_yolo_decode": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hvs_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_int, c_int,

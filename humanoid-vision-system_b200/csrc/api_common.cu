@@ -21,7 +21,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static void bind_primary_context_once() {
     thread_local bool bound = false;
     if (!bound) {
-        bind_primary_context_once();
+        cudaFree(nullptr);
         bound = true;
     }
 }

@@ -1,0 +1,221 @@
+// Training-side and input-side helpers on the edges of the hot path.
+//
+// hvs_grad_clip_dual   ManifoldConstrainedTrainer._apply_manifold_gradient_clipping
+//                      (src/training/mhc_trainer.py:342-383): the gradients of the mHC parameters are clipped to
+//                      mhc_max_norm (0.5), all others to max_grad_norm (1.0), each by torch's clip_grad_norm_ rule
+//                      (coef = max_norm / (norm + 1e-6), applied only when < 1).  The reference does this with two
+//                      foreach norms, two .item() host syncs and two foreach multiplies; here it is three launches over
+//                      a table of tensors, no host synchronisation, fixed-order (bitwise reproducible) reductions.
+// hvs_preprocess_u8    ImagePreprocessor "accurate" path (src/inference/preprocessing.py:252-273): HWC uint8 frame ->
+//                      bilinear resize (cv2.INTER_LINEAR sampling: half-pixel centres, edge clamp) -> optional BGR->RGB
+//                      (:199-203) -> / 255 -> (x - mean) / std -> CHW tensor, one kernel, for the streaming config.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace hvs {
+namespace {
+
+constexpr int kClipThreads = 256;
+constexpr int kChunk = 1 << 16;          // elements per work item
+
+struct ClipTable {
+    const hvs_grad_tensor* tensors;      // device copy
+    const int* chunk_tensor;             // [nchunks] tensor index of each chunk
+    const int* chunk_first;              // [ntensors] first chunk of each tensor
+    float* partial;                      // [nchunks]
+    float* result;                       // [4]: norm group 0, norm group 1, coef 0, coef 1
+    int ntensors, nchunks;
+    float max_norm0, max_norm1;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < kClipThreads / 32 ? sm[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    __syncthreads();
+    return t;                            // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kClipThreads) clip_sumsq_kernel(const ClipTable tb) {
+    __shared__ float sm[kClipThreads / 32];
+    for (int c = blockIdx.x; c < tb.nchunks; c += gridDim.x) {
+        const int t = tb.chunk_tensor[c];
+        const hvs_grad_tensor g = tb.tensors[t];
+        const int64_t lo = (int64_t)(c - tb.chunk_first[t]) * kChunk;
+        const int64_t hi = lo + kChunk < g.numel ? lo + kChunk : g.numel;
+        float s = 0.f;
+        for (int64_t i = lo + threadIdx.x; i < hi; i += kClipThreads) { const float v = g.grad[i]; s = fmaf(v, v, s); }
+        s = block_sum(s, sm);
+        if (threadIdx.x == 0) tb.partial[c] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kClipThreads) clip_finalize_kernel(const ClipTable tb) {
+    __shared__ float sm[kClipThreads / 32];
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = threadIdx.x; c < tb.nchunks; c += kClipThreads) {      // fixed assignment, fixed order
+        const float v = tb.partial[c];
+        if (tb.tensors[tb.chunk_tensor[c]].group == 0) s0 += v; else s1 += v;
+    }
+    s0 = block_sum(s0, sm);
+    s1 = block_sum(s1, sm);
+    if (threadIdx.x == 0) {
+        const float n0 = sqrtf(s0), n1 = sqrtf(s1);
+        const float c0 = tb.max_norm0 / (n0 + 1e-6f), c1 = tb.max_norm1 / (n1 + 1e-6f);
+        tb.result[0] = n0; tb.result[1] = n1;
+        tb.result[2] = c0 < 1.f ? c0 : 1.f;
+        tb.result[3] = c1 < 1.f ? c1 : 1.f;
+    }
+}
+
+__global__ void __launch_bounds__(kClipThreads) clip_scale_kernel(const ClipTable tb) {
+    const float c0 = tb.result[2], c1 = tb.result[3];
+    if (c0 == 1.f && c1 == 1.f) return;
+    for (int c = blockIdx.x; c < tb.nchunks; c += gridDim.x) {
+        const int t = tb.chunk_tensor[c];
+        const hvs_grad_tensor g = tb.tensors[t];
+        const float k = g.group == 0 ? c0 : c1;
+        if (k == 1.f) continue;
+        const int64_t lo = (int64_t)(c - tb.chunk_first[t]) * kChunk;
+        const int64_t hi = lo + kChunk < g.numel ? lo + kChunk : g.numel;
+        for (int64_t i = lo + threadIdx.x; i < hi; i += kClipThreads) g.grad[i] *= k;
+    }
+}
+
+inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct ClipLayout { size_t off_t, off_ct, off_cf, off_part, table_bytes, total; int nchunks; };
+
+ClipLayout clip_layout(const hvs_grad_tensor* t, int n) {
+    ClipLayout L{};
+    int64_t chunks = 0;
+    for (int i = 0; i < n; ++i) chunks += (t[i].numel + kChunk - 1) / kChunk;
+    L.nchunks = (int)chunks;
+    size_t off = 0;
+    L.off_t = off; off += up256((size_t)n * sizeof(hvs_grad_tensor));
+    L.off_ct = off; off += up256((size_t)chunks * 4);
+    L.off_cf = off; off += up256((size_t)n * 4);
+    L.table_bytes = off;
+    L.off_part = off; off += up256((size_t)chunks * 4);
+    L.total = off;
+    return L;
+}
+
+// ---------------------------------------------------------------------------- preprocessing
+template <typename TO> __device__ __forceinline__ TO cvt_out(float v);
+template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+struct PreParams {
+    const uint8_t* src; int sh, sw, sc; int64_t src_pitch;       // HWC, channels 1 or 3
+    int dh, dw; int swap_rb; float mean[3], inv_std[3]; float scale;
+};
+
+template <typename TO>
+__global__ void preprocess_kernel(const PreParams p, TO* __restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= p.dw) return;
+    const float fy = ((float)y + 0.5f) * ((float)p.sh / (float)p.dh) - 0.5f;
+    const float fx = ((float)x + 0.5f) * ((float)p.sw / (float)p.dw) - 0.5f;
+    int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+    const float wy = fy - (float)y0, wx = fx - (float)x0;
+    const int y1 = min(max(y0 + 1, 0), p.sh - 1), x1 = min(max(x0 + 1, 0), p.sw - 1);
+    y0 = min(max(y0, 0), p.sh - 1); x0 = min(max(x0, 0), p.sw - 1);
+    const uint8_t* r0 = p.src + (int64_t)y0 * p.src_pitch;
+    const uint8_t* r1 = p.src + (int64_t)y1 * p.src_pitch;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int sc = p.sc == 1 ? 0 : (p.swap_rb ? 2 - c : c);
+        const float a = r0[x0 * p.sc + sc], b = r0[x1 * p.sc + sc], d = r1[x0 * p.sc + sc], e = r1[x1 * p.sc + sc];
+        const float top = a + (b - a) * wx, bot = d + (e - d) * wx;
+        const float v = (top + (bot - top) * wy) * p.scale;
+        dst[((int64_t)c * p.dh + y) * p.dw + x] = cvt_out<TO>((v - p.mean[c]) * p.inv_std[c]);
+    }
+}
+
+}  // namespace
+}  // namespace hvs
+
+extern "C" size_t hvs_grad_clip_dual_workspace(const hvs_grad_tensor* tensors_host, int num_tensors) {
+    if (!tensors_host || num_tensors <= 0) return 256;
+    return hvs::clip_layout(tensors_host, num_tensors).total;
+}
+
+extern "C" int hvs_grad_clip_dual(const hvs_grad_tensor* tensors_host, int num_tensors, float max_norm_group0,
+                                  float max_norm_group1, float* result4, void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (num_tensors < 0 || !result4 || (num_tensors > 0 && !tensors_host)) return HVS_ERR_BAD_ARG;
+    if (num_tensors == 0) return (int)cudaMemsetAsync(result4, 0, 16, stream);
+    for (int i = 0; i < num_tensors; ++i)
+        if (!tensors_host[i].grad || tensors_host[i].numel < 0 || (tensors_host[i].group != 0 && tensors_host[i].group != 1)) return HVS_ERR_BAD_ARG;
+    const ClipLayout L = clip_layout(tensors_host, num_tensors);
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return HVS_ERR_ALIGNMENT;
+    if (workspace_bytes < L.total) return HVS_ERR_WORKSPACE;
+    std::vector<uint8_t> tab(L.table_bytes, 0);
+    memcpy(tab.data() + L.off_t, tensors_host, (size_t)num_tensors * sizeof(hvs_grad_tensor));
+    int* ct = reinterpret_cast<int*>(tab.data() + L.off_ct);
+    int* cf = reinterpret_cast<int*>(tab.data() + L.off_cf);
+    int c = 0;
+    for (int i = 0; i < num_tensors; ++i) {
+        cf[i] = c;
+        const int n = (int)((tensors_host[i].numel + kChunk - 1) / kChunk);
+        for (int k = 0; k < n; ++k) ct[c++] = i;
+    }
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    HVS_CUDA_TRY(cudaMemcpyAsync(ws, tab.data(), L.table_bytes, cudaMemcpyHostToDevice, stream));
+    ClipTable tb{};
+    tb.tensors = reinterpret_cast<const hvs_grad_tensor*>(ws + L.off_t);
+    tb.chunk_tensor = reinterpret_cast<const int*>(ws + L.off_ct);
+    tb.chunk_first = reinterpret_cast<const int*>(ws + L.off_cf);
+    tb.partial = reinterpret_cast<float*>(ws + L.off_part);
+    tb.result = result4;
+    tb.ntensors = num_tensors; tb.nchunks = L.nchunks;
+    tb.max_norm0 = max_norm_group0; tb.max_norm1 = max_norm_group1;
+    if (L.nchunks == 0) return (int)cudaMemsetAsync(result4, 0, 16, stream);
+    int grid = sm_count() * 8;
+    if (grid > L.nchunks) grid = L.nchunks;
+    clip_sumsq_kernel<<<grid, kClipThreads, 0, stream>>>(tb);
+    clip_finalize_kernel<<<1, kClipThreads, 0, stream>>>(tb);
+    clip_scale_kernel<<<grid, kClipThreads, 0, stream>>>(tb);
+    count_launch(3);
+    return launch_status();
+}
+
+extern "C" int hvs_preprocess_u8(const void* src, int src_h, int src_w, int src_channels, int64_t src_pitch_bytes, void* dst,
+                                 int dst_dtype, int dst_h, int dst_w, int swap_rb, const float* mean3_host,
+                                 const float* std3_host, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!src || !dst || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0) return HVS_ERR_BAD_ARG;
+    if (src_channels != 1 && src_channels != 3) return HVS_ERR_UNSUPPORTED;
+    if (src_pitch_bytes < (int64_t)src_w * src_channels) return HVS_ERR_BAD_ARG;
+    PreParams p{};
+    p.src = (const uint8_t*)src; p.sh = src_h; p.sw = src_w; p.sc = src_channels; p.src_pitch = src_pitch_bytes;
+    p.dh = dst_h; p.dw = dst_w; p.swap_rb = swap_rb; p.scale = 1.0f / 255.0f;
+    for (int c = 0; c < 3; ++c) {
+        p.mean[c] = mean3_host ? mean3_host[c] : 0.f;
+        p.inv_std[c] = std3_host ? 1.0f / std3_host[c] : 1.f;
+    }
+    dim3 grid((dst_w + 127) / 128, dst_h);
+    if (dst_dtype == HVS_DTYPE_F32) preprocess_kernel<float><<<grid, 128, 0, stream>>>(p, (float*)dst);
+    else if (dst_dtype == HVS_DTYPE_F16) preprocess_kernel<__half><<<grid, 128, 0, stream>>>(p, (__half*)dst);
+    else if (dst_dtype == HVS_DTYPE_BF16) preprocess_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(p, (__nv_bfloat16*)dst);
+    else return HVS_ERR_UNSUPPORTED;
+    count_launch();
+    return launch_status();
+}

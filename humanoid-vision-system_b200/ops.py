@@ -329,6 +329,59 @@ def gemm_bf16(a0: torch.Tensor, b0: torch.Tensor, a1: Optional[torch.Tensor] = N
     return out
 
 
+# ----------------------------------------------------------------------------- edges of the path: grad clipping, frame preprocessing
+def is_mhc_parameter(name: str) -> bool:
+    """The reference's grouping rule (mhc_trainer.py:357-359)."""
+    return "mhc" in name.lower() or "H_" in name
+
+
+def clip_grad_dual(named_parameters, max_grad_norm: float = 1.0, mhc_max_norm: float = 0.5) -> torch.Tensor:
+    """_apply_manifold_gradient_clipping (mhc_trainer.py:342-383) without host synchronisation: clips the mHC
+    parameters' gradients to mhc_max_norm and the others to max_grad_norm IN PLACE; returns a device tensor
+    [norm_mhc, norm_other, coef_mhc, coef_other] (total norm = hypot of the first two)."""
+    items = [(n, p) for n, p in named_parameters if p.grad is not None]
+    if not items:
+        return torch.zeros(4)
+    dev = items[0][1].grad.device
+    with torch.cuda.device(dev):
+        arr = (_lib.GradTensor * len(items))()
+        for a, (n, p) in zip(arr, items):
+            g = p.grad
+            _need_cuda(g)
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                raise _lib.HvsError(f"gradient of {n} must be contiguous fp32")
+            a.grad, a.numel, a.group = g.data_ptr(), g.numel(), 0 if is_mhc_parameter(n) else 1
+        lib = _lib.load()
+        nb = int(lib.hvs_grad_clip_dual_workspace(arr, len(items)))
+        ws = torch.empty(max(nb, 256), dtype=torch.uint8, device=dev)
+        res = torch.empty(4, dtype=torch.float32, device=dev)
+        check(lib.hvs_grad_clip_dual(arr, len(items), mhc_max_norm, max_grad_norm, _ptr(res), _ptr(ws), ws.numel(), _stream()),
+              "hvs_grad_clip_dual")
+    return res
+
+
+_PRE_DTYPES = {torch.float32: _lib.HVS_DTYPE_F32, torch.float16: _lib.HVS_DTYPE_F16, torch.bfloat16: _lib.HVS_DTYPE_BF16}
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+@_on_device
+def preprocess_frame(frame_u8: torch.Tensor, height: int, width: int, bgr_to_rgb: bool = True, mean=IMAGENET_MEAN, std=IMAGENET_STD,
+                     out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """HWC (or HW) uint8 frame on the device -> normalised CHW tensor [3, height, width] (preprocessing.py:181-273)."""
+    _need_cuda(frame_u8, out)
+    if frame_u8.dtype != torch.uint8 or frame_u8.dim() not in (2, 3) or not frame_u8.is_contiguous():
+        raise _lib.HvsError("frame must be a contiguous uint8 HW or HWC tensor")
+    h, w = frame_u8.shape[:2]
+    c = 1 if frame_u8.dim() == 2 else frame_u8.shape[2]
+    if out is None:
+        out = torch.empty((3, height, width), dtype=out_dtype, device=frame_u8.device)
+    m3 = (ctypes.c_float * 3)(*mean) if mean is not None else None
+    s3 = (ctypes.c_float * 3)(*std) if std is not None else None
+    check(_lib.load().hvs_preprocess_u8(_ptr(frame_u8), h, w, c, w * c, _ptr(out), _PRE_DTYPES[out.dtype], height, width,
+                                        1 if bgr_to_rgb else 0, m3, s3, _stream()), "hvs_preprocess_u8")
+    return out
+
+
 # ----------------------------------------------------------------------------- detection
 _DTYPES = {torch.float32: _lib.HVS_DTYPE_F32, torch.float16: _lib.HVS_DTYPE_F16, torch.bfloat16: _lib.HVS_DTYPE_BF16}
 

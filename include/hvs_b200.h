@@ -214,6 +214,33 @@ int hvs_gemm_bf16(const void* a0, int64_t lda0, const void* b0, int K0, const vo
 int hvs_profile_kernel_ms(float* out8_host);
 
 /* ------------------------------------------------------------------------------------
+ * Edges of the path.
+ * hvs_grad_clip_dual: ManifoldConstrainedTrainer._apply_manifold_gradient_clipping
+ * (src/training/mhc_trainer.py:342-383).  tensors_host: fp32 gradient tensors (device pointers) tagged with a group
+ * (0 = mHC parameters: name contains "mhc" or "H_", 1 = others).  Per group, torch's clip_grad_norm_ rule:
+ * coef = max_norm / (norm_2 + 1e-6), gradients multiplied by coef when coef < 1.  result4 (device) receives
+ * {norm group 0, norm group 1, applied coef 0, applied coef 1}.  No host synchronisation; fixed-order reductions.
+ * ---------------------------------------------------------------------------------- */
+typedef struct hvs_grad_tensor {
+    float* grad;
+    int64_t numel;
+    int32_t group;
+    int32_t reserved;
+} hvs_grad_tensor;
+size_t hvs_grad_clip_dual_workspace(const hvs_grad_tensor* tensors_host, int num_tensors);
+int hvs_grad_clip_dual(const hvs_grad_tensor* tensors_host, int num_tensors, float max_norm_group0,
+                       float max_norm_group1, float* result4, void* workspace, size_t workspace_bytes, void* stream);
+
+/* hvs_preprocess_u8: ImagePreprocessor "accurate" path (src/inference/preprocessing.py:252-273, colour swap :199-203):
+ * src HWC uint8 frame (device memory, 1 or 3 channels, row pitch in bytes) -> bilinear resize with cv2.INTER_LINEAR
+ * sampling (half-pixel centres, edge clamp; arithmetic in fp32, without cv2's intermediate rounding to uint8) ->
+ * swap_rb (BGR -> RGB) -> / 255 -> (x - mean) / std -> dst CHW [3, dst_h, dst_w] fp32 / fp16 / bf16.  mean3 / std3 are
+ * HOST arrays (NULL = 0 / 1). */
+int hvs_preprocess_u8(const void* src, int src_h, int src_w, int src_channels, int64_t src_pitch_bytes, void* dst,
+                      int dst_dtype, int dst_h, int dst_w, int swap_rb, const float* mean3_host, const float* std3_host,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
  * YOLODecoder.forward (src/models/yolo_head.py:220-294), one scale.
  *   pred      [B, A, H, W, 5+C] viewed through element strides pred_stride[5]
  *             (the head's permuted NCHW conv output is read in place), fp32 / fp16 / bf16

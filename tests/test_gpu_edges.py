@@ -1,0 +1,75 @@
+"""Edges of the path: the fused dual-threshold gradient clipping against torch's
+clip_grad_norm_ applied the way the reference trainer applies it (mhc_trainer.py:342-383), and the frame preprocessing
+kernel against cv2 + torch (preprocessing.py:252-273)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _named_grads(seed, scale):
+    g = torch.Generator().manual_seed(seed)
+    shapes = {"backbone.stem.0.mhc.H_pre_raw": (32, 128), "backbone.stem.0.mhc.mlp.0.weight": (256, 128), "backbone.stem.0.conv.weight": (32, 3, 3, 3),
+              "final_fusion.H_res_raw": (300, 300), "vit.blocks.0.mlp.0.bias": (1024,), "head.pred_conv.weight": (255, 256, 1, 1),
+              "big.weight": (70000, 3), "nograd.weight": (4, 4)}
+    params = []
+    for n, s in shapes.items():
+        p = torch.nn.Parameter(torch.zeros(s))
+        if not n.startswith("nograd"):
+            p.grad = torch.randn(s, generator=g) * scale
+        params.append((n, p))
+    return params
+
+
+@pytest.mark.parametrize("scale", [1e-4, 0.01, 1.0])
+def test_grad_clip_dual_matches_reference_rule(scale):
+    import hvs_b200
+    cpu = _named_grads(3, scale)
+    gpu = [(n, torch.nn.Parameter(p.detach().to(DEV))) for n, p in cpu]
+    for (n, p), (_, q) in zip(cpu, gpu):
+        if p.grad is not None:
+            q.grad = p.grad.to(DEV)
+    mhc = [p for n, p in cpu if p.grad is not None and hvs_b200.ops.is_mhc_parameter(n)]
+    oth = [p for n, p in cpu if p.grad is not None and not hvs_b200.ops.is_mhc_parameter(n)]
+    assert len(mhc) == 3 and len(oth) == 4
+    n_mhc = torch.nn.utils.clip_grad_norm_(mhc, max_norm=0.5, norm_type=2)
+    n_oth = torch.nn.utils.clip_grad_norm_(oth, max_norm=1.0, norm_type=2)
+    before = hvs_b200._lib.launch_count()
+    res = hvs_b200.ops.clip_grad_dual(gpu, max_grad_norm=1.0, mhc_max_norm=0.5)
+    assert hvs_b200._lib.launch_count() - before == 3
+    r = res.cpu()
+    assert abs(r[0] - n_mhc) <= 1e-5 * n_mhc and abs(r[1] - n_oth) <= 1e-5 * n_oth
+    for (n, p), (_, q) in zip(cpu, gpu):
+        if p.grad is not None:
+            assert torch.allclose(q.grad.cpu(), p.grad, rtol=2e-6, atol=1e-12), n
+    # deterministic
+    gpu2 = [(n, torch.nn.Parameter(p.detach().to(DEV))) for n, p in _named_grads(3, scale)]
+    for (n, p), (_, q) in zip(_named_grads(3, scale), gpu2):
+        if p.grad is not None:
+            q.grad = p.grad.to(DEV)
+    assert torch.equal(hvs_b200.ops.clip_grad_dual(gpu2, 1.0, 0.5), res)
+
+
+@pytest.mark.parametrize("shape,out", [((480, 640, 3), (640, 640)), ((1080, 1920, 3), (640, 640)), ((100, 77, 3), (64, 96)), ((640, 640, 3), (640, 640)),
+                                       ((50, 60), (32, 32))])
+def test_preprocess_frame_matches_cv2_pipeline(shape, out):
+    import cv2
+    import hvs_b200
+    rng = np.random.default_rng(sum(shape))
+    frame = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    h, w = out
+    # the reference pipeline: colour conversion (preprocessing.py:199-213), cv2.resize INTER_LINEAR (:255-259), /255, normalise (:262-271)
+    rgb = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB) if frame.ndim == 3 else cv2.cvtColor(frame, cv2.COLOR_GRAY2RGB)
+    resized = cv2.resize(rgb, (w, h), interpolation=cv2.INTER_LINEAR)
+    want = torch.from_numpy(resized).permute(2, 0, 1).float() / 255.0
+    mean, std = torch.tensor(hvs_b200.ops.IMAGENET_MEAN).view(3, 1, 1), torch.tensor(hvs_b200.ops.IMAGENET_STD).view(3, 1, 1)
+    want = (want - mean) / std
+    got = hvs_b200.ops.preprocess_frame(torch.from_numpy(frame).to(DEV), h, w).cpu()
+    # cv2 interpolates uint8 in fixed point and rounds to uint8; the kernel interpolates in fp32: at most one grey level apart
+    assert ((got - want).abs() * std).max() <= 1.01 / 255.0
+    if shape[:2] == out:
+        assert ((got - want).abs() * std).max() < 1e-6             # no resampling: identical
+    g16 = hvs_b200.ops.preprocess_frame(torch.from_numpy(frame).to(DEV), h, w, out_dtype=torch.bfloat16)
+    assert torch.equal(g16.cpu(), got.to(torch.bfloat16))
