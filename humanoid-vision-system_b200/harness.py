@@ -229,6 +229,9 @@ def k2_microbench(device, tokens: int = 1 << 20, dim: int = 512, expansion: int 
     module's library path (torch ops under bf16 autocast = the reference's own CUDA execution)."""
     torch.manual_seed(0)
     mod = ManifoldHyperConnection(dim, expansion_rate=expansion).to(device).eval()
+    with torch.no_grad():                               # trained-like coefficients: at the xavier(0.1) init the module is so
+        for p in (mod.H_pre_raw, mod.H_post_raw, mod.H_res_raw):   # ill-conditioned under bf16 that two correct paths differ by O(1)
+            p.normal_(0, 1.0)                           # (tests/test_gpu_k2.py); timing does not depend on the values
     mod.output_dtype = torch.bfloat16
     h = mod.hidden_dim
     flop_per_token = 2.0 * (2 * dim * h + 4 * h * h + dim * dim)

@@ -79,8 +79,21 @@ def test_bf16_kernel_path_tracks_reference_and_uses_the_k2_kernels(model, golden
 
 
 def test_channels_last_is_a_free_layout_fold(model, golden):
+    """Row a10: in channels_last the NCHW -> [B*H*W, C] hop is a view (no copy) and the model computes the same thing.
+    Compared in fp32 mode (in the bf16 mode 76 layers of re-rounding amplify cuDNN's algorithm choice to ~8 %)."""
     g = golden("hybrid_vision")
     x = torch.from_numpy(g["x"]).to(DEV)
+    xc = x.contiguous(memory_format=torch.channels_last)
+    t = xc.permute(0, 2, 3, 1)
+    assert t.is_contiguous() and t.reshape(-1, 3).data_ptr() == xc.data_ptr()       # the token view aliases the tensor
+    _set_mixed(model, False)
+    try:
+        _channels_last_body(model, x)
+    finally:
+        _set_mixed(model, True)
+
+
+def _channels_last_body(model, x):
     with torch.no_grad():
         a = model(x)["predictions"]
         from hvs_b200.hybrid_vision import to_channels_last
@@ -93,7 +106,7 @@ def test_channels_last_is_a_free_layout_fold(model, golden):
                     m.weight.data = m.weight.data.contiguous()
     for s in range(3):
         rel = ((a[f"scale_{s}"] - b[f"scale_{s}"]).norm() / a[f"scale_{s}"].norm()).item()
-        assert rel < 2e-2, rel                                      # cuDNN picks other conv algorithms; same math
+        assert rel < 2e-3, rel                                      # cuDNN picks other conv algorithms; same math
 
 
 def test_detect_and_graph_replay_are_deterministic(model):
