@@ -248,7 +248,12 @@ def run_extras(args, dev, world, rank):
     torch.cuda.empty_cache()
     if args.skip_hybrid:
         return out
-    model = harness.build_model(dev, seed=0)
+    import copy
+    from hvs_b200.hybrid_vision import to_channels_last
+    train_model = harness.build_model(dev, seed=0)
+    model = copy.deepcopy(train_model)                     # inference copy: eval-mode BatchNorm folded into the convolutions
+    folded = harness.fold_batchnorm_for_inference(model.eval())
+    to_channels_last(model)
     per = 64 // world
     inf = harness.inference_sharded(model, dev, world, rank, 64, 640)
     inf_real = harness.inference_sharded(model, dev, world, rank, 64, 640, objectness_bias=-4.0, steps=3, warmup=1)
@@ -260,14 +265,16 @@ def run_extras(args, dev, world, rank):
                         "model_tflops": ips * harness.FWD_GFLOP_PER_IMAGE_640 / 1e3,
                         "frac_of_bf16_sustained_per_gpu": ips * harness.FWD_GFLOP_PER_IMAGE_640 / 1e3 / world / tf_sus,
                         "img_per_s_objectness_bias_-4": 64 / (ms_real * 1e-3), "mean_detections": inf["mean_detections"],
-                        "hvs_launches_per_step": inf["hvs_launches_per_step"],
+                        "hvs_launches_per_step": inf["hvs_launches_per_step"], "conv_bn_pairs_folded": folded,
                         "e2e": {"img_per_s": 64 / (ms_e2e * 1e-3), "ms_per_batch": ms_e2e, "h2d_bytes_per_step": inf_e2e["h2d_bytes_per_step"],
                                 "d2h_bytes_per_step": inf_e2e["d2h_bytes_per_step"], "note": "per rank: pinned host images -> H2D -> forward -> decode -> NMS -> detections D2H, all timed"}}}
     torch.cuda.empty_cache()
     stream = harness.streaming_latency(model, dev, frames=args.stream_frames)
     hv["streaming"] = dict(stream, workload="BASELINE configs[4]: batch-1 640x640 frames, whole forward + decode + NMS in one CUDA graph")
+    del model
     torch.cuda.empty_cache()
     torch.cuda.reset_peak_memory_stats(dev)
+    model = train_model
     tr = harness.training_ddp(model, dev, world, rank, args.train_batch, 640)
     ms_tr = rank_max(tr["ms_per_step"])
     tips = world * tr["batch_per_gpu"] / (ms_tr * 1e-3)

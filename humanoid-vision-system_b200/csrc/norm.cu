@@ -120,6 +120,108 @@ layernorm_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, cons
     }
 }
 
+// Small rows (D = 32 ... 512, the widths of the backbone's mHC layers, where T is in the millions): D / 8 lanes per row
+// (16 for D = 512 with two vectors each), every lane holds 8 (16) consecutive elements from one 16-byte load, statistics
+// by xor-shuffles inside the lane group, 16-byte stores.  The warp-per-row kernel above moves 64 bytes per warp
+// instruction at D = 32; this one moves 512.
+template <typename TI> struct Load8;
+template <> struct Load8<__nv_bfloat16> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&f)[8]) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+        f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+        f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+        f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+    }
+};
+template <> struct Load8<float> {
+    static __device__ __forceinline__ void ld(const float* p, float (&f)[8]) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+};
+__device__ __forceinline__ uint4 pack8_bf16(const float (&f)[8]) {
+    uint4 o;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(f[1]), "f"(f[0]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(f[3]), "f"(f[2]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(f[5]), "f"(f[4]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(f[7]), "f"(f[6]));
+    return o;
+}
+
+template <typename TI, int D>
+__global__ void __launch_bounds__(256)
+layernorm_small_rows_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                            __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ copy, int64_t rows, float eps) {
+    constexpr int kVec = D >= 512 ? D / 256 : 1;            // 8-element vectors per lane
+    constexpr int kLanes = D / (8 * kVec);                  // lanes per row (4 ... 32)
+    constexpr int kRowsPerWarp = 32 / kLanes;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / kLanes, l = lane % kLanes;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float wv[kVec][8], bv[kVec][8];
+#pragma unroll
+    for (int v = 0; v < kVec; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { wv[v][j] = w[(v * kLanes + l) * 8 + j]; bv[v][j] = b[(v * kLanes + l) * 8 + j]; }
+    for (int64_t r0 = warp * kRowsPerWarp; r0 < rows; r0 += nwarps * kRowsPerWarp) {
+        const int64_t r = r0 + sub;
+        const bool ok = r < rows;
+        float f[kVec][8];
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < kVec; ++v) {
+            if (ok) Load8<TI>::ld(x + r * D + (v * kLanes + l) * 8, f[v]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[v][j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += f[v][j];
+        }
+#pragma unroll
+        for (int o = kLanes / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / (float)D);
+        float q = 0.f;
+#pragma unroll
+        for (int v = 0; v < kVec; ++v)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = f[v][j] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+        for (int o = kLanes / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float inv = rsqrtf(q * (1.0f / (float)D) + eps);
+        if (ok) {
+#pragma unroll
+            for (int v = 0; v < kVec; ++v) {
+                if (copy != nullptr) *reinterpret_cast<uint4*>(copy + r * D + (v * kLanes + l) * 8) = pack8_bf16(f[v]);
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = (f[v][j] - mean) * inv * wv[v][j] + bv[v][j];
+                *reinterpret_cast<uint4*>(out + r * D + (v * kLanes + l) * 8) = pack8_bf16(y);
+            }
+        }
+    }
+}
+
+template <typename TI>
+bool launch_small_rows(const TI* x, const float* w, const float* b, __nv_bfloat16* out, __nv_bfloat16* copy, int64_t rows, int dim,
+                       float eps, cudaStream_t stream) {
+    int64_t blocks = (rows * (dim >= 512 ? 32 : dim / 8) / 32 + 7) / 8;      // 8 warps per block
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const int g = (int)blocks;
+    switch (dim) {
+        case 32: layernorm_small_rows_kernel<TI, 32><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
+        case 64: layernorm_small_rows_kernel<TI, 64><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
+        case 128: layernorm_small_rows_kernel<TI, 128><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
+        case 256: layernorm_small_rows_kernel<TI, 256><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
+        case 512: layernorm_small_rows_kernel<TI, 512><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
+        default: return false;
+    }
+}
+
 inline int grid_for_rows(int64_t rows) {
     int64_t blocks = (rows + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -196,6 +298,17 @@ extern "C" int hvs_layernorm_fwd(const void* x, int x_dtype, const float* weight
     if (!x || !out) return HVS_ERR_BAD_ARG;
     const int g = grid_for_rows(rows);
     __nv_bfloat16* cp = (__nv_bfloat16*)x_bf16_copy;
+    const bool dense = out_ld == dim && (cp == nullptr || copy_ld == dim) && out_dtype == HVS_DTYPE_BF16 &&
+                       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(cp)) & 15) == 0;
+    if (dense) {
+        bool done = false;
+        if (x_dtype == HVS_DTYPE_BF16) done = launch_small_rows((const __nv_bfloat16*)x, weight, bias, (__nv_bfloat16*)out, cp, rows, dim, eps, stream);
+        else if (x_dtype == HVS_DTYPE_F32) done = launch_small_rows((const float*)x, weight, bias, (__nv_bfloat16*)out, cp, rows, dim, eps, stream);
+        if (done) {
+            count_launch();
+            return launch_status();
+        }
+    }
     if (x_dtype == HVS_DTYPE_F32 && out_dtype == HVS_DTYPE_BF16)
         layernorm_fwd_kernel<float, __nv_bfloat16><<<g, 256, 0, stream>>>((const float*)x, weight, bias, (__nv_bfloat16*)out, cp, rows, dim, out_ld, copy_ld, eps);
     else if (x_dtype == HVS_DTYPE_BF16 && out_dtype == HVS_DTYPE_BF16)

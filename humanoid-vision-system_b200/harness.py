@@ -40,6 +40,28 @@ def build_model(device, seed: int = 0, channels_last: bool = True, bf16_activati
     return model
 
 
+def fold_batchnorm_for_inference(model: nn.Module) -> int:
+    """Eval-mode conv + BatchNorm pairs of the host model (ConvMHCLayer.conv/.bn, the FPN and head conv stacks) folded into
+    one convolution with bias: y = conv(x) * g / sqrt(var + eps) + (b - mean * g / sqrt(var + eps)).  A caller-side
+    inference optimisation (the standard torch.nn.utils.fusion recipe), numerically the same function; the BatchNorm
+    module is replaced by Identity, so use it on a model that will only run inference.  Returns the number of pairs."""
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    n = 0
+    for mod in list(model.modules()):
+        if hasattr(mod, "conv") and hasattr(mod, "bn") and isinstance(mod.conv, nn.Conv2d) and isinstance(mod.bn, nn.BatchNorm2d):
+            mod.conv = fuse_conv_bn_eval(mod.conv.eval(), mod.bn.eval())
+            mod.bn = nn.Identity()
+            n += 1
+        if isinstance(mod, nn.Sequential):
+            kids = list(mod.named_children())
+            for (na, a), (nb, b) in zip(kids, kids[1:]):
+                if isinstance(a, nn.Conv2d) and isinstance(b, nn.BatchNorm2d):
+                    setattr(mod, na, fuse_conv_bn_eval(a.eval(), b.eval()))
+                    setattr(mod, nb, nn.Identity())
+                    n += 1
+    return n
+
+
 def _time_steps(fn, steps: int, warmup: int) -> float:
     for _ in range(warmup):
         fn()

@@ -197,7 +197,8 @@ int hvs_mhc_static_coeffs_bwd(const hvs_coeff_job* jobs_host, const hvs_coeff_gr
 /* K2 token path (manifold_layers.py:248-270) as tcgen05 GEMMs with fused epilogues:
  *   out[M,N] = epilogue( A0[M,K0] B0[N,K0]^T + A1[M,K1] B1[N,K1]^T )        (second pair optional: K1 = 0)
  * A*: bf16 row-major, row stride lda* elements (multiple of 8); B*: bf16 [N,K*] row-major contiguous (the
- * nn.Linear weight layout).  K0, K1 multiples of 64; N a multiple of 32, and of 256 when N > 256.
+ * nn.Linear weight layout).  K0, K1 multiples of 8 (TMA zero-fills a partial last 64-element stage); N a multiple of 32,
+ * and of 256 when N > 256; bias 16-byte aligned.
  *   HVS_GEMM_EPI_NONE       out = acc (+ bias if given)                        z = LN(x) @ H_pre          (:253)
  *   HVS_GEMM_EPI_BIAS_GELU  out = gelu_erf(acc + bias[n])                      mlp Linear + GELU          (:164-168)
  *   HVS_GEMM_EPI_LAYERNORM  out = LayerNorm_N(acc) * ln_w + ln_b, N <= 512     norm_post(z@H_post + x@H_res) (:259-267)

@@ -66,6 +66,32 @@ def test_layernorm_kernel_with_padding_and_copy():
         assert torch.equal(ob[:, :dim].cpu(), out[:, :dim].cpu().to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("rows,dim", [(4099, 32), (1000, 64), (333, 128), (77, 256), (130, 512), (1, 32)])
+def test_layernorm_small_row_kernel(rows, dim):
+    """The vectorised D/8-lanes-per-row kernel (dense bf16 output, D in {32...512}) for bf16 and fp32 inputs."""
+    import hvs_b200
+    w, b = (1 + 0.1 * _rand(dim, seed=1)).to(DEV), (0.1 * _rand(dim, seed=2)).to(DEV)
+    for dt in (torch.bfloat16, torch.float32):
+        x = (_rand(rows, dim, seed=rows) * 2 + 0.7).to(dt)
+        want = torch.nn.functional.layer_norm(x.float(), (dim,), w.cpu(), b.cpu())
+        out, cp = hvs_b200.ops.layernorm_fwd(x.to(DEV), w, b, 1e-5, torch.bfloat16, dim, True, dim)
+        assert (out.cpu().float() - want).abs().max() <= 2.0 ** -8 * want.abs().max() + 1e-6
+        assert torch.equal(out.cpu(), want.to(torch.bfloat16)) or (out.cpu().float() - want).abs().max() < 0.02
+        assert torch.equal(cp.cpu(), x.to(torch.bfloat16))
+        out2, none = hvs_b200.ops.layernorm_fwd(x.to(DEV), w, b, 1e-5, torch.bfloat16, dim)
+        assert none is None and torch.equal(out2, out)
+
+
+def test_gemm_partial_k_stage_is_zero_filled():
+    """K = 32 / 96 / 160 (not multiples of the 64-element stage): TMA zero-fills the rest of the box on both operands."""
+    import hvs_b200
+    for m, n, k in ((300, 64, 32), (129, 96, 96), (1000, 256, 160)):
+        a, b = _rand(m, k, seed=k).to(torch.bfloat16), (_rand(n, k, seed=n) / k ** 0.5).to(torch.bfloat16)
+        out = hvs_b200.ops.gemm_bf16(a.to(DEV), b.to(DEV), out_dtype=torch.float32).cpu()
+        ref = a.double() @ b.double().t()
+        assert (out.double() - ref).abs().max() <= 2e-5 * ref.abs().max() + 1e-6, (m, n, k)
+
+
 # ----------------------------------------------------------------------------- batched static coefficients
 def _jobs(dims, iters=20, hidden_mult=2, seed=0, std=0.3):
     import hvs_b200
@@ -188,7 +214,9 @@ def test_gemm_plain_and_gelu(m, n, k):
     assert outb.dtype == torch.bfloat16 and torch.equal(outb, out.to(torch.bfloat16))
     g = hvs_b200.ops.gemm_bf16(a.to(DEV), b.to(DEV), bias=bias.to(DEV), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU, out_dtype=torch.float32).cpu()
     gref = torch.nn.functional.gelu(_gemm_ref(a, b, bias=bias))
-    assert (g.double() - gref).abs().max() <= 2e-5 * gref.abs().max() + 2e-6
+    assert (g.double() - gref).abs().max() <= 2e-5 * gref.abs().max() + 2e-6    # fp32-output path: erff
+    gb = hvs_b200.ops.gemm_bf16(a.to(DEV), b.to(DEV), bias=bias.to(DEV), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU).cpu()
+    assert (gb.float().double() - gref).abs().max() <= 2.0 ** -8 * gref.abs().max() + 4e-6   # bf16-output path: packed A&S erf (6e-7) + one rounding
 
 
 @pytest.mark.parametrize("m,n,k0,k1", [(500, 64, 256, 64), (128, 512, 2048, 512), (1000, 256, 512, 256), (77, 32, 128, 64),
@@ -217,9 +245,9 @@ def test_gemm_two_operand_pairs_layernorm_epilogue(m, n, k0, k1):
 def test_gemm_rejects_bad_shapes():
     import hvs_b200
     from hvs_b200._lib import HvsError
-    a, b = torch.zeros(8, 48, dtype=torch.bfloat16, device=DEV), torch.zeros(32, 48, dtype=torch.bfloat16, device=DEV)
+    a, b = torch.zeros(8, 44, dtype=torch.bfloat16, device=DEV), torch.zeros(32, 44, dtype=torch.bfloat16, device=DEV)
     with pytest.raises(HvsError):
-        hvs_b200.ops.gemm_bf16(a, b)                                # K not a multiple of 64
+        hvs_b200.ops.gemm_bf16(a, b)                                # K not a multiple of 8 (rows must be 16-byte multiples)
     with pytest.raises(HvsError):
         hvs_b200.ops.gemm_bf16(torch.zeros(8, 64, dtype=torch.bfloat16, device=DEV), torch.zeros(40, 64, dtype=torch.bfloat16, device=DEV))
     assert hvs_b200.ops.gemm_bf16(torch.zeros(0, 64, dtype=torch.bfloat16, device=DEV), torch.zeros(32, 64, dtype=torch.bfloat16, device=DEV)).shape == (0, 32)
