@@ -372,7 +372,7 @@ def test_module_fused_forward_reference_init(d, n, hidden, t):
           f"median row condition {cond.median().item():.0f}; output err / condition {out_err:.2e}")
     assert e_c < 2.0 ** -6
     assert e_o < 0.25                                               # what bf16 operands cost at this init (H_pre = 0.5 +- 0.01 has ~3 significant bits of signal)
-    assert ((y - out_c).abs() <= 3e-2 + 1e-4 * cond).all()
+    assert ((y - out_c).abs() <= 6e-2 + 1e-4 * cond).all()
 
 
 def test_module_fused_forward_golden_and_shapes(golden):
@@ -395,7 +395,7 @@ def test_module_fused_forward_golden_and_shapes(golden):
         cmag = _condition_magnitude(x2, p)
         assert ((pre - pre_c).abs() / cmag).max() < 2.0 ** -6 and ((pre - pre_o).abs() / cmag).max() < 0.25
         cond = pre_c.abs().amax(-1, keepdim=True) / pre_c.std(-1, keepdim=True)
-        assert ((y.cpu().double().reshape(-1, d) - out_c).abs() <= 3e-2 + 1e-4 * cond).all()      # bf16 re-rounding floor + conditioning
+        assert ((y.cpu().double().reshape(-1, d) - out_c).abs() <= 6e-2 + 1e-4 * cond).all()      # bf16 re-rounding floor + conditioning
         hr = mod.constrained_matrices()[2].cpu()
         assert ((hr - torch.from_numpy(g[f"{tag}/H_res"])).abs() / torch.from_numpy(g[f"{tag}/H_res"])).max() < 1e-5
     # bf16 input, empty input, bf16 output on request

@@ -11,6 +11,10 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 train = len(sys.argv) > 2 and sys.argv[2] == "train"
 dev = torch.device("cuda", 0)
 model = harness.build_model(dev)
+if not train and os.environ.get("HVS_FOLD_BN", "1") == "1":
+    from hvs_b200.hybrid_vision import to_channels_last
+    harness.fold_batchnorm_for_inference(model.eval())
+    to_channels_last(model)
 x = torch.randn(batch, 3, 640, 640, device=dev).to(torch.bfloat16 if not train else torch.float32).contiguous(memory_format=torch.channels_last)
 if train:
     model.train()
