@@ -419,6 +419,7 @@ class ManifoldHyperConnection(nn.Module):
         self._state: Optional[_CoeffState] = None
         self.monitor_signal_ratio = True
         self.output_dtype: Optional[torch.dtype] = None      # None: fp32 like the reference (its last op is a LayerNorm under autocast)
+        self.use_chain_kernel = True                          # (D, H) = (32, 128) / (64, 256), bf16 input: hvs_mhc_module_fwd
         self._initialize_weights()
 
     def _initialize_weights(self):                       # :191-203
@@ -469,6 +470,11 @@ class ManifoldHyperConnection(nn.Module):
         d = self.input_dim
         dp = _pad64(d)
         x2 = x2.contiguous()
+        if self.use_chain_kernel and x2.dtype == torch.bfloat16 and ops.mhc_module_fwd_supported(d, self.hidden_dim):
+            # small widths: the whole path in ONE kernel per token tile, no intermediate in HBM
+            return ops.mhc_module_fwd(x2, st.h_pre_t, w1, self.mlp[0].bias.detach(), w2, self.mlp[3].bias.detach(), st.h_post_t,
+                                      st.h_res_t, (self.norm_pre.weight.detach(), self.norm_pre.bias.detach(), self.norm_pre.eps),
+                                      (self.norm_post.weight.detach(), self.norm_post.bias.detach(), self.norm_post.eps), out_dtype)
         reuse = x2.dtype == torch.bfloat16 and dp == d           # bf16 activations: x itself is the A operand of x @ H_res
         xn, xb = ops.layernorm_fwd(x2, self.norm_pre.weight.detach(), self.norm_pre.bias.detach(), self.norm_pre.eps,
                                    out_dtype=torch.bfloat16, out_ld=dp, want_copy=not reuse, copy_ld=dp)   # :250

@@ -329,6 +329,31 @@ def gemm_bf16(a0: torch.Tensor, b0: torch.Tensor, a1: Optional[torch.Tensor] = N
     return out
 
 
+def mhc_module_fwd_supported(d: int, h: int) -> bool:
+    return bool(_lib.load().hvs_mhc_module_fwd_supported(d, h))
+
+
+@_on_device
+def mhc_module_fwd(x: torch.Tensor, h_pre_t: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+                   h_post_t: torch.Tensor, h_res_t: torch.Tensor, ln_pre: Tuple[torch.Tensor, torch.Tensor, float],
+                   ln_post: Tuple[torch.Tensor, torch.Tensor, float], out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """The whole token path of the module (:248-267) in one kernel; x [T, D] bf16, (D, H) in {(32, 128), (64, 256)}."""
+    _need_cuda(x, h_pre_t, w1, b1, w2, b2, h_post_t, h_res_t)
+    t, d = x.shape
+    h = h_pre_t.shape[0]
+    if x.dtype != torch.bfloat16 or not x.is_contiguous():
+        raise _lib.HvsError("mhc_module_fwd expects contiguous bf16 x")
+    for name, ten, shape in (("h_pre_t", h_pre_t, (h, d)), ("w1", w1, (2 * h, h)), ("w2", w2, (h, 2 * h)), ("h_post_t", h_post_t, (d, h)),
+                             ("h_res_t", h_res_t, (d, d))):
+        if ten.dtype != torch.bfloat16 or tuple(ten.shape) != shape or not ten.is_contiguous():
+            raise _lib.HvsError(f"{name} must be contiguous bf16 {shape}")
+    out = torch.empty((t, d), dtype=out_dtype, device=x.device)
+    check(_lib.load().hvs_mhc_module_fwd(_ptr(x), _ptr(h_pre_t), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(h_post_t), _ptr(h_res_t),
+                                         _ptr(ln_pre[0]), _ptr(ln_pre[1]), ln_pre[2], _ptr(ln_post[0]), _ptr(ln_post[1]), ln_post[2],
+                                         _ptr(out), _NORM_DTYPES[out_dtype], t, d, h, _stream()), "hvs_mhc_module_fwd")
+    return out
+
+
 # ----------------------------------------------------------------------------- edges of the path: grad clipping, frame preprocessing
 def is_mhc_parameter(name: str) -> bool:
     """The reference's grouping rule (mhc_trainer.py:357-359)."""

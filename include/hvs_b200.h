@@ -210,8 +210,21 @@ int hvs_gemm_bf16(const void* a0, int64_t lda0, const void* b0, int K0, const vo
                   const void* b1, int K1, const float* bias, const float* ln_w, const float* ln_b, float ln_eps,
                   void* out, int out_dtype, int64_t ldo, int64_t M, int N, int epilogue, void* stream);
 
+/* The whole token path (manifold_layers.py:248-267, eval mode) in ONE kernel per 128-token tile -- LayerNorm_pre in the
+ * prologue, the five GEMMs chained through tensor memory and shared memory, GELU / residual / LayerNorm_post in the
+ * epilogues -- for the widths whose five-launch path is bound by its HBM round trips (the backbone's first stages):
+ * (D, H) = (32, 128) or (64, 256), see hvs_mhc_module_fwd_supported.
+ *   x [T, D] bf16 contiguous; h_pre_t [H, D], h_post_t [D, H], h_res_t [D, D] bf16 (hvs_mhc_static_coeffs outputs);
+ *   w1 [2H, H], w2 [H, 2H] bf16 (mlp.0 / mlp.3 weights), b1 [2H], b2 [H] fp32; LayerNorm weights / biases [D] fp32;
+ *   out [T, D] fp32 or bf16.  All pointers 16-byte aligned. */
+int hvs_mhc_module_fwd_supported(int D, int H);
+int hvs_mhc_module_fwd(const void* x, const void* h_pre_t, const void* w1, const float* b1, const void* w2,
+                       const float* b2, const void* h_post_t, const void* h_res_t, const float* ln_pre_w,
+                       const float* ln_pre_b, float ln_pre_eps, const float* ln_post_w, const float* ln_post_b,
+                       float ln_post_eps, void* out, int out_dtype, int64_t T, int D, int H, void* stream);
+
 /* Mean duration in ms of the (last 128) launches per kernel slot since hvs_mhc_stream_profile(1):
- * 0-3 as hvs_mhc_stream_kernel_ms, 4 = K2 GEMM, 5 = decode, 6 = NMS, 7 = static coefficients; negative = not run. */
+ * 0-3 as hvs_mhc_stream_kernel_ms, 4 = K2 GEMM, 5 = decode, 6 = fused K2 module kernel, 7 = static coefficients; negative = not run. */
 int hvs_profile_kernel_ms(float* out8_host);
 
 /* ------------------------------------------------------------------------------------

@@ -412,6 +412,39 @@ def test_module_fused_forward_golden_and_shapes(golden):
         assert (lib.float() - yb).abs().max() < 0.1 and (lib.float() - yb).abs().mean() < 1e-2
 
 
+@pytest.mark.parametrize("d,n", [(32, 4), (64, 4)])
+def test_module_single_kernel_chain_path(d, n):
+    """hvs_mhc_module_fwd: the whole token path in ONE launch (no intermediate in HBM) for (D, H) = (32, 128) / (64, 256)
+    and bf16 input -- against the five-launch path on the same input (same operands, same K order: differences only
+    from the LayerNorm statistics' summation order) and against the oracle at the bf16-operand tolerance."""
+    import hvs_b200
+    mod, p = _module_pair(d, n, seed=7 + d, raw_std=1.0)
+    assert hvs_b200.ops.mhc_module_fwd_supported(d, mod.hidden_dim)
+    for t in (1, 127, 128, 129, 1000, 40000):
+        x = (_rand(t, d, seed=t) * 1.5 + 0.2).to(torch.bfloat16)
+        with torch.no_grad():
+            mod.use_chain_kernel = True
+            mod(x[:1].to(DEV))
+            before = hvs_b200._lib.launch_count()
+            y = mod(x.to(DEV))
+            assert hvs_b200._lib.launch_count() - before == 1           # one kernel for the whole module
+            mod.use_chain_kernel = False
+            y5 = mod(x.to(DEV))
+            mod.use_chain_kernel = True
+            y_again = mod(x.to(DEV))
+        assert y.dtype == torch.float32 and y.shape == (t, d)
+        assert torch.equal(y, y_again)
+        diff = (y - y5).abs()
+        assert diff.max() < 2e-2 and diff.mean() < 1e-4, (t, diff.max().item(), diff.mean().item())
+        exact = mhc_ref.mhc_module_forward(x.float(), p)
+        err = (y.cpu() - exact).abs()
+        assert err.max() < 2.0 ** -3 and err.mean() < 2.0 ** -6, (t, err.max().item(), err.mean().item())
+    with torch.no_grad():
+        mod.output_dtype = torch.bfloat16
+        yb = mod(x.to(DEV))
+        assert yb.dtype == torch.bfloat16 and torch.equal(yb, y.to(torch.bfloat16))
+
+
 def test_refresh_static_coefficients_batches_all_modules():
     import hvs_b200
     from hvs_b200.mhc import refresh_static_coefficients
