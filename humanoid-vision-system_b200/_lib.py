@@ -76,6 +76,8 @@ _SIGNATURES = {
     "hvs_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p,
                               c_void_p, c_float, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p]),
     "hvs_profile_kernel_ms": (c_int, [POINTER(c_float)]),
+    "hvs_head_decode_fused": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_int, c_int, c_int, c_void_p]),
     "hvs_mhc_module_fwd_supported": (c_int, [c_int, c_int]),
     "hvs_mhc_module_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_float, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),

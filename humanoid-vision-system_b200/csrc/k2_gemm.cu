@@ -48,7 +48,17 @@ struct GemmParams {
     float ln_eps;
     int num_tiles;          // m_tiles * n_outer
     int n_outer;            // N / (BN * n_sub)
+    // HVS_GEMM_EPI_YOLO_DECODE (fused prediction conv + decode): outputs in hvs_yolo_decode's layout
+    const float* anchor_wh; // [3, 2]
+    float* dec_boxes;       // [B, 3, H, W, 4]
+    float* dec_scores;      // [B, 3, H, W]
+    int64_t* dec_cls;       // [B, 3, H, W]
+    float* dec_obj;         // [B, 3, H, W] or null
+    int grid_h, grid_w;
 };
+
+constexpr int kEpiYoloDecode = 100;      // internal epilogue id (entered through hvs_head_decode_fused)
+__device__ __forceinline__ float sigmoidf_rn(float v) { return __fdiv_rn(1.0f, 1.0f + expf(-v)); }
 
 // ---- packed fp32x2 arithmetic (one instruction for two accumulator columns): the GELU epilogue is ISSUE-bound -- at
 // K <= 256 a tile's 32768 activations cost more issue slots than its MMAs take cycles -- so instructions per element
@@ -194,6 +204,59 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 mbar_wait(&acc_full[it & 1u], (it >> 1) & 1u);
             }
             tc_fence_after();
+            if (p.epilogue == kEpiYoloDecode) {
+                // ---- YOLODecoder.forward (yolo_head.py:241-285) on the accumulator row: a row is one pixel, its 255 columns are
+                // 3 anchors x (tx, ty, tw, th, obj, 80 classes).  Same arithmetic and order as yolo_decode.cu; the raw
+                // predictions never reach HBM.  Half 0 of the warp pair takes anchors 0 and 1, half 1 anchor 2.
+                const uint32_t t0 = tmem_base + lane_base + (it0 & 1u) * kMaxBN;
+                const int hw = p.grid_h * p.grid_w;
+                const int b = (int)(row / hw), rem = (int)(row % hw);
+                const int gy = rem / p.grid_w, gx = rem % p.grid_w;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    if ((a == 2) != (half == 1)) continue;
+                    const int lo = 85 * a;
+                    float tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, obj = 0.f, best = -INFINITY;
+                    int besti = 0;
+#pragma unroll
+                    for (int c = lo / 32; c <= (lo + 84) / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld32(t0 + (uint32_t)(c * 32), v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = 32 * c + j, slot = col - lo;
+                            if (slot < 0 || slot >= 85) continue;
+                            const float x = __uint_as_float(v[j]) + __ldg(p.bias + col);
+                            if (slot == 0) tx = x;
+                            else if (slot == 1) ty = x;
+                            else if (slot == 2) tw = x;
+                            else if (slot == 3) th = x;
+                            else if (slot == 4) obj = sigmoidf_rn(x);
+                            else {
+                                const float sc = obj * sigmoidf_rn(x);
+                                if (slot == 5 || sc > best) { best = sc; besti = slot - 5; }
+                            }
+                        }
+                    }
+                    if (row_ok) {
+                        const int64_t cell = (((int64_t)b * 3 + a) * p.grid_h + gy) * p.grid_w + gx;
+                        const float bx = __fdiv_rn((float)gx + sigmoidf_rn(tx), (float)p.grid_w);
+                        const float by = __fdiv_rn((float)gy + sigmoidf_rn(ty), (float)p.grid_h);
+                        const float bw = __ldg(p.anchor_wh + 2 * a) * expf(tw), bh = __ldg(p.anchor_wh + 2 * a + 1) * expf(th);
+                        const float hx = bw * 0.5f, hy = bh * 0.5f;
+                        reinterpret_cast<float4*>(p.dec_boxes)[cell] = make_float4(bx - hx, by - hy, bx + hx, by + hy);
+                        p.dec_scores[cell] = best;
+                        p.dec_cls[cell] = besti;
+                        if (p.dec_obj != nullptr) p.dec_obj[cell] = obj;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[it0 & 1u]);
+                acc_it += 1u;
+                continue;
+            }
             float mean = 0.f, inv = 0.f;
             if (p.epilogue == HVS_GEMM_EPI_LAYERNORM) {
                 // statistics over the whole row (both accumulators), shifted by the row's first element
@@ -347,6 +410,46 @@ extern "C" int hvs_gemm_bf16(const void* a0, int64_t lda0, const void* b0, int K
     timer_begin(4, stream);
     k2_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta0, tb0, ta1, tb1, p);
     timer_end(4, stream);
+    count_launch();
+    return launch_status();
+}
+
+// Fused YOLOPredictionHead tail: the 1x1 prediction convolution (yolo_head.py:193-194) as a
+// tcgen05 GEMM over the head's token view [B*H*W, C_in] with YOLODecoder.forward (:241-285) as its epilogue.  The raw
+// [B, 3, H, W, 85] predictions (548 MB per batch of 64 at 640 x 640 in fp32) are never written: per pixel the kernel emits
+// 3 x (box, score, class).  The score threshold and the order-preserving compaction of the survivors happen where the
+// reference does them (yolo_head.py:600-622), inside hvs_post_process's NMS kernel, which reads these dense outputs.
+extern "C" int hvs_head_decode_fused(const void* tokens, int64_t ld_tokens, const void* weight256, const float* bias256,
+                                     const float* anchor_wh, float* boxes, float* class_scores, int64_t* class_idx,
+                                     float* objectness, int B, int H, int W, int C_in, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (B < 0 || H <= 0 || W <= 0 || C_in <= 0) return HVS_ERR_BAD_ARG;
+    if (B == 0) return HVS_OK;
+    if (!tokens || !weight256 || !bias256 || !anchor_wh || !boxes || !class_scores || !class_idx) return HVS_ERR_BAD_ARG;
+    if (C_in % 8 || ld_tokens % 8 || ld_tokens < C_in) return HVS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(tokens) | reinterpret_cast<uintptr_t>(weight256) | reinterpret_cast<uintptr_t>(boxes)) & 15) return HVS_ERR_ALIGNMENT;
+    const int64_t M = (int64_t)B * H * W;
+    if (M >= ((int64_t)1 << 31)) return HVS_ERR_UNSUPPORTED;
+    GemmParams p{};
+    p.bias = bias256; p.M = M; p.N = 256; p.BN = 256; p.n_sub = 1; p.n_outer = 1;
+    p.kb0 = (C_in + kBK - 1) / kBK; p.kb1 = 0;
+    p.stages = kStageBudget / (kABytes + p.BN * 128);
+    p.epilogue = kEpiYoloDecode;
+    p.num_tiles = (int)((M + kBM - 1) / kBM);
+    p.anchor_wh = anchor_wh; p.dec_boxes = boxes; p.dec_scores = class_scores; p.dec_cls = class_idx; p.dec_obj = objectness;
+    p.grid_h = H; p.grid_w = W;
+    CUtensorMap ta, tb;
+    int rc = make_tmap_bf16_2d_ld(&ta, tokens, (uint64_t)M, (uint64_t)C_in, (uint64_t)ld_tokens, kBM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d_ld(&tb, weight256, 256, (uint64_t)C_in, (uint64_t)C_in, 256);
+    if (rc) return rc;
+    HVS_SET_MAX_SMEM(k2_gemm_kernel, kSmemBytes);
+    const int sms = sm_count();
+    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    timer_begin(5, stream);
+    k2_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, ta, tb, p);
+    timer_end(5, stream);
     count_launch();
     return launch_status();
 }

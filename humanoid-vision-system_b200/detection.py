@@ -84,6 +84,30 @@ class YOLOPredictionHead(nn.Module):
             bias[:, 4] = -4.0
             bias[:, 5:] = -math.log((1 - 0.01) / 0.01) / num_classes
 
+    def _pred_operands(self):
+        """pred_conv as a GEMM B operand: [256, C_in] bf16 (255 real rows + one zero row) and the padded fp32 bias, cached
+        until the parameters change."""
+        wt, bs = self.pred_conv.weight, self.pred_conv.bias
+        key = (wt.data_ptr(), wt._version, bs.data_ptr(), bs._version)
+        if getattr(self, "_pred_key", None) != key:
+            w256 = torch.zeros((256, self.in_channels), dtype=torch.bfloat16, device=wt.device)
+            w256[: self.output_dim] = wt.detach().reshape(self.output_dim, self.in_channels).to(torch.bfloat16)
+            b256 = torch.zeros(256, dtype=torch.float32, device=wt.device)
+            b256[: self.output_dim] = bs.detach().float()
+            self._pred_w256, self._pred_b256, self._pred_key = w256, b256, key
+        return self._pred_w256, self._pred_b256
+
+    def forward_decoded(self, x: torch.Tensor, anchor_wh: torch.Tensor, want_objectness: bool = False) -> Dict[str, torch.Tensor]:
+        """Inference tail without the raw prediction tensor: conv stack -> mHC over the pixel tokens -> ONE kernel doing the
+        1x1 prediction convolution and the decode (hvs_head_decode_fused).  3 anchors x 85."""
+        x = self.conv_layers(x)
+        b, c, h, w = x.shape
+        tok = x.permute(0, 2, 3, 1).reshape(-1, c)
+        if not isinstance(self.mhc_enhance, nn.Identity):
+            tok = self.mhc_enhance(tok)
+        w256, b256 = self._pred_operands()
+        return ops.head_decode_fused(tok.to(torch.bfloat16).contiguous(), w256, b256, anchor_wh, b, h, w, want_objectness)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = self.conv_layers(x)
         b, c, h, w = x.shape
@@ -197,15 +221,21 @@ class YOLODetectionHead(nn.Module):
         self.loss_fn = YOLOLoss(num_classes=num_classes, anchors=anchors)        # :505-508
         self.grid_sizes = [(13, 13), (26, 26), (52, 52)]                          # :511 (informational: the decoder uses the actual H, W)
         self.want_scores = True      # full [B,A,H,W,C] obj*cls tensor (the reference's 'scores'); post_process does not need it
+        self.fuse_pred_decode = False  # inference only: prediction conv + decode in one kernel, 'predictions' left empty
 
     def forward(self, features: Dict[str, torch.Tensor], targets=None, compute_loss: bool = False,
                 want_scores: Optional[bool] = None) -> Dict[str, Any]:
         """yolo_head.py:515-569.  With compute_loss and targets the result carries 'loss' (:556-563)."""
         want_scores = self.want_scores if want_scores is None else want_scores
         predictions, decoded = {}, {}
+        fused = (self.fuse_pred_decode and not compute_loss and not torch.is_grad_enabled() and not self.training
+                 and self.num_anchors == 3 and self.num_classes == 80)
         for i in range(self.num_scales):
             key = ["scale_small", "scale_medium", "scale_large"][i]
             if key not in features:
+                continue
+            if fused and features[key].is_cuda:
+                decoded[f"scale_{i}"] = self.pred_heads[i].forward_decoded(features[key], self.anchor_generator(i).reshape(3, -1, 4)[:, 0, 2:4])
                 continue
             pred = self.pred_heads[i](features[key])
             predictions[f"scale_{i}"] = pred

@@ -78,7 +78,7 @@ def _time_steps(fn, steps: int, warmup: int) -> float:
 # ----------------------------------------------------------------------------------------------- config 3
 def inference_sharded(model: HybridVisionSystem, device, world: int = 1, rank: int = 0, global_batch: int = 64,
                       image: int = 640, steps: int = 5, warmup: int = 3, objectness_bias: Optional[float] = None,
-                      host_input: bool = False) -> Dict[str, Any]:
+                      host_input: bool = False, fuse_head: bool = True) -> Dict[str, Any]:
     """Each rank takes global_batch / world images (strong scaling, no collective): forward under bf16 autocast,
     decode, two-stage NMS (conf 0.25, iou 0.45, max 100).  host_input=True also copies the shard from pinned host memory
     and reads the detections back inside the timed region (the e2e reading)."""
@@ -95,6 +95,7 @@ def inference_sharded(model: HybridVisionSystem, device, world: int = 1, rank: i
             for h in head.pred_heads:
                 h.pred_conv.bias.view(head.num_anchors, -1)[:, 4] = objectness_bias
     head.want_scores = False
+    head.fuse_pred_decode = fuse_head
     result = {}
 
     def step():
@@ -113,6 +114,7 @@ def inference_sharded(model: HybridVisionSystem, device, world: int = 1, rank: i
         launches = (_lib.launch_count() - launches0) // (steps + warmup)
     finally:
         head.want_scores = True
+        head.fuse_pred_decode = False
         if saved_bias is not None:
             with torch.no_grad():
                 for h, b in zip(head.pred_heads, saved_bias):
@@ -194,6 +196,7 @@ def streaming_latency(model: HybridVisionSystem, device, frames: int = 300, imag
     model.eval()
     head = model.detection_head
     head.want_scores = False
+    head.fuse_pred_decode = True
     try:
         g = torch.Generator(device="cpu").manual_seed(3000)
         pool = [torch.randn(1, 3, image, image, generator=g).to(torch.bfloat16).to(device).contiguous(memory_format=torch.channels_last)
@@ -243,6 +246,7 @@ def streaming_latency(model: HybridVisionSystem, device, frames: int = 300, imag
                 "latency_scope": "frame resident in HBM -> detections on host (CUDA graph replay + D2H of [100,4]+[100]+[100]+count); H2D of the frame excluded"}
     finally:
         head.want_scores = True
+        head.fuse_pred_decode = False
 
 
 # ----------------------------------------------------------------------------------------------- K2 microbenchmark

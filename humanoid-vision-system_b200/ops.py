@@ -439,6 +439,30 @@ def yolo_decode(pred: torch.Tensor, anchor_wh: torch.Tensor, want_scores: bool =
 
 
 @_on_device
+def head_decode_fused(tokens: torch.Tensor, weight256: torch.Tensor, bias256: torch.Tensor, anchor_wh: torch.Tensor, b: int, h: int,
+                      w: int, want_objectness: bool = False) -> Dict[str, torch.Tensor]:
+    """1x1 prediction conv + decode in one kernel.  tokens [B*H*W, C_in] bf16 (pixel-major), weight256 [256, C_in] bf16."""
+    _need_cuda(tokens, weight256, bias256, anchor_wh)
+    if tokens.dtype != torch.bfloat16 or tokens.dim() != 2 or tokens.stride(1) != 1 or tokens.shape[0] != b * h * w:
+        raise _lib.HvsError("tokens must be [B*H*W, C_in] bf16 with unit inner stride")
+    c_in = tokens.shape[1]
+    if weight256.dtype != torch.bfloat16 or tuple(weight256.shape) != (256, c_in) or not weight256.is_contiguous():
+        raise _lib.HvsError("weight256 must be contiguous bf16 [256, C_in]")
+    dev = tokens.device
+    boxes = torch.empty((b, 3, h, w, 4), dtype=torch.float32, device=dev)
+    cs = torch.empty((b, 3, h, w), dtype=torch.float32, device=dev)
+    ci = torch.empty((b, 3, h, w), dtype=torch.int64, device=dev)
+    obj = torch.empty((b, 3, h, w, 1), dtype=torch.float32, device=dev) if want_objectness else None
+    awh = anchor_wh.to(device=dev, dtype=torch.float32).contiguous()
+    check(_lib.load().hvs_head_decode_fused(_ptr(tokens), tokens.stride(0), _ptr(weight256), _ptr(bias256.contiguous()), _ptr(awh),
+                                            _ptr(boxes), _ptr(cs), _ptr(ci), _ptr(obj), b, h, w, c_in, _stream()), "hvs_head_decode_fused")
+    out = {"boxes": boxes, "class_scores": cs, "class_indices": ci}
+    if obj is not None:
+        out["objectness"] = obj
+    return out
+
+
+@_on_device
 def nms(boxes: torch.Tensor, scores: torch.Tensor, classes: Optional[torch.Tensor] = None,
         iou_threshold: float = 0.5, max_detections: int = 100, score_threshold: float = float("-inf"),
         class_aware: bool = False, boxes_xyxy: bool = True, offsets: Optional[torch.Tensor] = None,

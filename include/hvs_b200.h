@@ -271,6 +271,18 @@ int hvs_yolo_decode(const void* pred, int pred_dtype, const int64_t* pred_stride
                     float* boxes, float* class_scores, int64_t* class_idx, float* objectness, float* scores,
                     int B, int A, int H, int W, int C, void* stream);
 
+/* Fused YOLOPredictionHead tail: the 1x1 prediction convolution (yolo_head.py:193-194) as a tcgen05 GEMM over the
+ * head's token view, with YOLODecoder.forward (:241-285) as its epilogue -- the raw [B,3,H,W,85] predictions are never
+ * written.  For the model's head: 3 anchors x (5 + 80) = 255 output channels.
+ *   tokens    [B*H*W, C_in] bf16 (pixel-major = channels_last feature map), row stride ld_tokens elements
+ *   weight256 [256, C_in] bf16 = pred_conv.weight[:, :, 0, 0] with one zero row appended; bias256 [256] fp32 likewise
+ *   outputs as hvs_yolo_decode (boxes, class_scores, class_idx, optional objectness; no per-class score tensor).
+ * Score thresholding and the order-preserving compaction of survivors (yolo_head.py:600-622) stay where the reference
+ * has them, in hvs_post_process, which consumes these outputs directly. */
+int hvs_head_decode_fused(const void* tokens, int64_t ld_tokens, const void* weight256, const float* bias256,
+                          const float* anchor_wh, float* boxes, float* class_scores, int64_t* class_idx,
+                          float* objectness, int B, int H, int W, int C_in, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Greedy NMS over `num_problems` independent candidate sets (one CTA each).
  *   boxes   [sum N, 4] fp32; scores [sum N] fp32; classes [sum N] int64 (class-aware only)

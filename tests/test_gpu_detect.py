@@ -164,3 +164,54 @@ def test_post_process_full_size_worst_case():
         assert k == len(want[b]["scores"])
         assert np.array_equal(db[b, :k].cpu().numpy(), want[b]["boxes"])
         assert np.array_equal(dl[b, :k].cpu().numpy(), want[b]["labels"])
+
+
+def test_fused_prediction_conv_decode_matches_oracle():
+    """hvs_head_decode_fused: 1x1 prediction conv as a tcgen05 GEMM with the decode as its epilogue,
+    against the oracle decode of the same logits (fp64 GEMM of the same bf16 operands)."""
+    import hvs_b200
+    for b, h, w, cin in ((2, 20, 20, 1024), (3, 40, 40, 512), (1, 80, 80, 256), (2, 7, 5, 64)):
+        g = torch.Generator().manual_seed(h * w + cin)
+        tok = (torch.randn(b * h * w, cin, generator=g)).to(torch.bfloat16)
+        wt = (torch.randn(255, cin, generator=g) * (2.0 / cin ** 0.5)).to(torch.bfloat16)
+        bias = torch.randn(255, generator=g) * 0.5
+        bias[4::85] -= 1.0
+        w256 = torch.zeros(256, cin, dtype=torch.bfloat16); w256[:255] = wt
+        b256 = torch.zeros(256); b256[:255] = bias
+        for s in range(3):
+            awh = detect_ref.anchors_wh(s)
+            got = hvs_b200.ops.head_decode_fused(tok.cuda(), w256.cuda(), b256.cuda(), awh.cuda(), b, h, w, want_objectness=True)
+            logits = (tok.double() @ wt.double().t() + bias.double()).float()               # [B*H*W, 255]
+            pred = logits.reshape(b, h, w, 3, 85).permute(0, 3, 1, 2, 4).contiguous()        # [B, A, H, W, 85]
+            want = detect_ref.yolo_decode(pred, awh)
+            assert torch.allclose(got["boxes"].cpu(), want["boxes"], rtol=2e-5, atol=2e-6)
+            assert torch.allclose(got["class_scores"].cpu(), want["class_scores"], rtol=1e-4, atol=1e-7)
+            assert torch.allclose(got["objectness"].cpu(), want["objectness"], rtol=1e-5, atol=1e-7)
+            same = (got["class_indices"].cpu() == want["class_indices"]).float().mean().item()
+            assert same > 0.999, same                       # fp32 accumulation order may flip an exact near-tie
+
+
+def test_detection_head_fused_tail_equals_two_kernel_tail():
+    """The head with fuse_pred_decode: same detections as conv -> decode kernel, no raw prediction tensor."""
+    import hvs_b200
+    torch.manual_seed(5)
+    head = hvs_b200.YOLODetectionHead([64, 128, 256], num_classes=80, use_mhc=False).cuda().eval()
+    with torch.no_grad():
+        for hd in head.pred_heads:
+            hd.pred_conv.weight.normal_(0, 0.2)
+            # make conv outputs exactly representable paths comparable: run the reference path on bf16-rounded operands too
+            hd.pred_conv.weight.copy_(hd.pred_conv.weight.to(torch.bfloat16).float())
+    feats = {"scale_small": torch.randn(2, 64, 16, 16, device="cuda"), "scale_medium": torch.randn(2, 128, 8, 8, device="cuda"),
+             "scale_large": torch.randn(2, 256, 4, 4, device="cuda")}
+    with torch.no_grad():
+        ref = head(feats)
+        head.fuse_pred_decode = True
+        before = hvs_b200._lib.launch_count()
+        out = head(feats)
+        assert hvs_b200._lib.launch_count() - before == 3 and out["predictions"] == {}
+    for s in range(3):
+        a, b = out["decoded"][f"scale_{s}"], ref["decoded"][f"scale_{s}"]
+        assert (a["boxes"] - b["boxes"]).abs().max() < 2e-2          # the fused path rounds the conv INPUT to bf16, the other does not
+        assert (a["class_scores"] - b["class_scores"]).abs().max() < 2e-2
+    dets = head.post_process(out["decoded"], 0.2, 0.45, 50)
+    assert len(dets) == 2 and all(d["boxes"].shape[1] == 4 for d in dets)
