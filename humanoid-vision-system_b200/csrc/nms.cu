@@ -3,6 +3,9 @@
 //   class-aware     NMSFilter.apply / _standard_nms / _compute_iou        src/inference/postprocessing.py:505-607, 772-802
 // and the two-stage multi-scale merge YOLODetectionHead.post_process      src/models/yolo_head.py:571-676.
 //
+// Two kernels.  Large sets (2048 < N <= 24000, the per-scale stage of post_process): nms_sorted_kernel below -- one
+// stable radix sort in shared memory, then every candidate is tested only against the boxes already kept.
+// Small sets: nms_kernel.
 // One CTA per candidate set.  Both reference loops keep at most max_det boxes in descending score
 // order and never look back, so instead of a sort + N x N mask the CTA repeats, at most max_det
 // times: (1) block-wide arg-max over the still-alive scores (ties -> lower index; scores cached in
@@ -166,10 +169,210 @@ __global__ void __launch_bounds__(THREADS) nms_kernel(const NmsArgs a) {
     }
 }
 
+// ---- large candidate sets: sort once, then test a candidate only against the boxes already KEPT ------------------------
+// The arg-max kernel above does kept x N IoUs (one sweep of every alive candidate per kept box: 100 x 19 200 per problem
+// when a random-init model lets every candidate through).  Greedy NMS only ever lets KEPT boxes suppress,
+// so a candidate's fate depends on the kept boxes that precede it in score order alone: sort the passing candidates
+// once (stable LSD radix sort on the score bits, ties -> lower index, 4-bit digits, all in shared memory), then walk
+// them in order 1024 at a time -- every thread tests its candidate against the boxes kept so far, warp 0 then resolves
+// the survivors of the chunk in order with ballots.  IoUs drop from kept x N to about (candidates examined) x kept, and
+// the walk stops at max_det.  Same semantics, same IoU arithmetic, same outputs as nms_kernel.
+constexpr int kSortThreads = 1024;
+constexpr int kSortMaxN = 24000;
+
+__device__ __forceinline__ uint32_t desc_key(float s) {                // ascending order of this key = descending score
+    const uint32_t u = __float_as_uint(s);
+    return ~((u & 0x80000000u) ? ~u : (u | 0x80000000u));
+}
+
+__device__ __forceinline__ bool suppresses(const float4& kb, float karea, int64_t kcls, const float4& cb, int64_t ccls,
+                                           bool class_aware, float thr) {
+    if (class_aware) return kcls == ccls && iou_ref(kb, karea, cb) > thr;     // postprocessing.py:594
+    return !(iou_ref(kb, karea, cb) < thr);                                   // yolo_head.py:727
+}
+
+__global__ void __launch_bounds__(kSortThreads) nms_sorted_kernel(const NmsArgs a) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ int s_warp_tot[32];
+    __shared__ int s_total, s_kept;
+    __shared__ uint32_t s_alive[32];
+    const int p = blockIdx.x;
+    const int gi = a.offsets ? 0 : p % a.num_groups;
+    const int bi = a.offsets ? 0 : p / a.num_groups;
+    const NmsGroup& grp = a.g[gi];
+    int64_t start = (int64_t)bi * grp.stride;
+    int n = grp.n;
+    if (a.offsets) { start = a.offsets[p]; n = (int)(a.offsets[p + 1] - start); }
+    if (a.counts) n = a.counts[p];
+    const float* boxes = grp.boxes + start * 4;
+    const float* scores = grp.scores + start;
+    const int64_t* classes = grp.classes ? grp.classes + start : nullptr;
+    const bool class_aware = (a.mode & 15) == HVS_NMS_CLASS_AWARE;
+    const bool cxcywh = class_aware && !(a.mode & HVS_NMS_BOXES_XYXY);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cap = (n + 1) & ~1;
+    // shared memory: keys [cap] u32 | order A [cap] u16 | order B [cap] u16 | digit counters [16][1024] u16 | kept boxes
+    uint32_t* keys = reinterpret_cast<uint32_t*>(s_raw);
+    uint16_t* ord_a = reinterpret_cast<uint16_t*>(keys + cap);
+    uint16_t* ord_b = ord_a + cap;
+    uint16_t* cnt = ord_b + cap;
+    float4* kbox = reinterpret_cast<float4*>(cnt + 16 * kSortThreads);
+    float* karea = reinterpret_cast<float*>(kbox + a.max_det);
+    int64_t* kcls = reinterpret_cast<int64_t*>(karea + ((a.max_det + 1) & ~1));
+
+    // ---- 1. order-preserving compaction of the candidates with score > thr (strict; NaN never passes, yolo_head.py:605)
+    const int per = (n + kSortThreads - 1) / kSortThreads;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    int c = 0;
+    for (int i = lo; i < hi; ++i) c += scores[i] > a.score_thr;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = s_warp_tot[lane], w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+        s_warp_tot[lane] = w - v;
+        if (lane == 31) s_total = w;
+    }
+    __syncthreads();
+    int pos = s_warp_tot[warp] + incl - c;
+    for (int i = lo; i < hi; ++i) {
+        const float sc = scores[i];
+        if (sc > a.score_thr) { keys[i] = desc_key(sc); ord_a[pos++] = (uint16_t)i; }
+    }
+    const int m = s_total;
+    if (tid == 0) s_kept = 0;
+    __syncthreads();
+
+    // ---- 2. stable LSD radix sort of the compacted indices by key (8 passes of 4 bits)
+    uint16_t* src = ord_a;
+    uint16_t* dst = ord_b;
+    const int mper = (m + kSortThreads - 1) / kSortThreads;
+    const int mlo = min(tid * mper, m), mhi = min(mlo + mper, m);
+    for (int shift = 0; shift < 32 && m > 1; shift += 4) {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) cnt[d * kSortThreads + tid] = 0;
+        for (int q = mlo; q < mhi; ++q) cnt[((keys[src[q]] >> shift) & 15u) * kSortThreads + tid] += 1;
+        __syncthreads();
+        // exclusive scan of the 16 x 1024 counters in (digit, thread) order: thread t owns counters [16 t, 16 t + 16)
+        int local[16];
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { local[k] = cnt[tid * 16 + k]; sum += local[k]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) s_warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int v = s_warp_tot[lane], w = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+            s_warp_tot[lane] = w - v;
+        }
+        __syncthreads();
+        int run = s_warp_tot[warp] + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { cnt[tid * 16 + k] = (uint16_t)run; run += local[k]; }
+        __syncthreads();
+        for (int q = mlo; q < mhi; ++q) {
+            const uint16_t v = src[q];
+            const uint32_t d = (keys[v] >> shift) & 15u;
+            dst[cnt[d * kSortThreads + tid]++] = v;
+        }
+        __syncthreads();
+        uint16_t* t = src; src = dst; dst = t;
+    }
+
+    // ---- 3. walk the sorted candidates, 1024 at a time
+    for (int base = 0; base < m; base += kSortThreads) {
+        const int kept0 = s_kept;
+        if (kept0 >= a.max_det) break;
+        const int q = base + tid;
+        bool alive = q < m;
+        int me = 0;
+        float4 mb = make_float4(0.f, 0.f, 0.f, 0.f);
+        int64_t mc = 0;
+        if (alive) {
+            me = src[q];
+            mb = load_box(boxes, me, cxcywh);
+            mc = class_aware ? classes[me] : 0;
+            for (int k = 0; k < kept0 && alive; ++k) alive = !suppresses(kbox[k], karea[k], kcls[k], mb, mc, class_aware, a.iou_thr);
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) s_alive[warp] = word;
+        __syncthreads();
+        if (warp == 0) {
+            int kept = kept0;
+            for (int sc = 0; sc < 32 && kept < a.max_det; ++sc) {
+                const uint32_t aw = s_alive[sc];
+                if (aw == 0u) continue;
+                const int qq = base + sc * 32 + lane;
+                bool al = (aw >> lane) & 1u;
+                int ci = 0;
+                float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
+                int64_t cc = 0;
+                if (al) {
+                    ci = src[qq];
+                    cb = load_box(boxes, ci, cxcywh);
+                    cc = class_aware ? classes[ci] : 0;
+                    for (int k = kept0; k < kept && al; ++k) al = !suppresses(kbox[k], karea[k], kcls[k], cb, cc, class_aware, a.iou_thr);
+                }
+                uint32_t mask;
+                while ((mask = __ballot_sync(0xffffffffu, al)) != 0u && kept < a.max_det) {
+                    const int ld = __ffs(mask) - 1;                      // best remaining candidate of this group: keep it
+                    const float4 wb = make_float4(__shfl_sync(0xffffffffu, cb.x, ld), __shfl_sync(0xffffffffu, cb.y, ld),
+                                                  __shfl_sync(0xffffffffu, cb.z, ld), __shfl_sync(0xffffffffu, cb.w, ld));
+                    const int64_t wc = __shfl_sync(0xffffffffu, cc, ld);
+                    const float warea = __fmul_rn(__fsub_rn(wb.z, wb.x), __fsub_rn(wb.w, wb.y));
+                    if (lane == ld) {
+                        kbox[kept] = wb; karea[kept] = warea; kcls[kept] = wc;
+                        a.keep_src[(int64_t)p * a.max_det + kept] = ci;
+                        al = false;
+                    }
+                    ++kept;
+                    if (al) al = !suppresses(wb, warea, wc, cb, cc, class_aware, a.iou_thr);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) s_kept = kept;
+        }
+        __syncthreads();
+    }
+    const int kept = s_kept;
+    if (tid == 0) a.keep_count[p] = kept;
+    if (a.keep_idx != nullptr) {      // index into the compacted (score > thr) list
+        for (int r = warp; r < kept; r += kSortThreads / 32) {
+            const int sidx = (int)a.keep_src[(int64_t)p * a.max_det + r];
+            int cn = 0;
+            for (int i0 = 0; i0 < sidx; i0 += 32) {
+                const int i = i0 + lane;
+                cn += __popc(__ballot_sync(0xffffffffu, i < sidx && scores[i] > a.score_thr));
+            }
+            if (lane == 0) a.keep_idx[(int64_t)p * a.max_det + r] = cn;
+        }
+    }
+}
+
+inline size_t sorted_smem_bytes(int64_t max_n, int max_det) {
+    const size_t cap = ((size_t)max_n + 1) & ~(size_t)1;
+    return cap * 4 + cap * 2 * 2 + 16 * kSortThreads * 2 + (size_t)max_det * 16 + (((size_t)max_det + 1) & ~(size_t)1) * 4 + (size_t)max_det * 8 + 64;
+}
+
 int launch_nms(const NmsArgs& a, int num_problems, int64_t max_n, cudaStream_t stream) {
     if (num_problems == 0) return HVS_OK;
     if (max_n > 49152) return HVS_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(max_n > 0 ? max_n : 1) * sizeof(float);
+    if (max_n > 2048 && max_n <= kSortMaxN && sorted_smem_bytes(max_n, a.max_det) <= 232448) {
+        const size_t sb = sorted_smem_bytes(max_n, a.max_det);
+        HVS_SET_MAX_SMEM(nms_sorted_kernel, 232448);
+        nms_sorted_kernel<<<num_problems, kSortThreads, sb, stream>>>(a);
+        count_launch();
+        return launch_status();
+    }
     if (max_n <= 4096) {
         nms_kernel<256><<<num_problems, 256, smem, stream>>>(a);
     } else {
