@@ -366,9 +366,10 @@ int launch_nms(const NmsArgs& a, int num_problems, int64_t max_n, cudaStream_t s
     if (num_problems == 0) return HVS_OK;
     if (max_n > 49152) return HVS_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(max_n > 0 ? max_n : 1) * sizeof(float);
-    if (max_n > 2048 && max_n <= kSortMaxN && sorted_smem_bytes(max_n, a.max_det) <= 232448) {
+    constexpr size_t kSortSmemMax = 232448 - 1024;            // the kernel also has static shared memory
+    if (max_n > 2048 && max_n <= kSortMaxN && sorted_smem_bytes(max_n, a.max_det) <= kSortSmemMax) {
         const size_t sb = sorted_smem_bytes(max_n, a.max_det);
-        HVS_SET_MAX_SMEM(nms_sorted_kernel, 232448);
+        HVS_SET_MAX_SMEM(nms_sorted_kernel, (int)kSortSmemMax);
         nms_sorted_kernel<<<num_problems, kSortThreads, sb, stream>>>(a);
         count_launch();
         return launch_status();
