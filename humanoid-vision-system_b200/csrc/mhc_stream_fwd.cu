@@ -453,6 +453,13 @@ mhc_stream_post_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
 }
 
 }  // namespace
+
+// general shapes / fp32-accurate operand: mhc_stream_generic.cu
+bool generic_stream_shape_ok(int n, int C);
+int launch_generic_stream_fwd(const void* x, const float* phi, const float* bias, const float* alpha, const float* scale, void* y,
+                              void* u, float* coeffs, int64_t T, int n, int C, int iters, float eps_rms, float eps_sk, int split,
+                              cudaStream_t stream);
+int launch_generic_stream_post(const void* x, const float* coeffs, const void* fu, void* y, int64_t T, int n, int C, cudaStream_t stream);
 }  // namespace hvs
 
 extern "C" int hvs_mhc_stream_fwd(const void* x, const float* phi, const float* bias, const float* alpha,
@@ -468,10 +475,21 @@ extern "C" int hvs_mhc_stream_fwd_save(const void* x, const float* phi, const fl
                                        void* stream) {
     using namespace hvs;
     if (T < 0) return HVS_ERR_BAD_ARG;
-    if (n != kN || C != kC || sk_iters < 0 || sk_iters > 64) return HVS_ERR_UNSUPPORTED;
+    if (sk_iters < 0 || sk_iters > 64) return HVS_ERR_UNSUPPORTED;
+    const bool tuned = n == kN && C == kC && !(flags & HVS_MHC_SPLIT_PHI);
+    if (!tuned) {
+        // every other stream shape, and the fp32-accurate operand for all shapes: the general warp-per-token kernel
+        if (!generic_stream_shape_ok(n, C) || saved != nullptr) return HVS_ERR_UNSUPPORTED;
+        if (T == 0) return HVS_OK;
+        if (!x || !phi || !bias || !alpha || !scale) return HVS_ERR_BAD_ARG;
+        if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(u) |
+             reinterpret_cast<uintptr_t>(phi)) & 15)
+            return HVS_ERR_ALIGNMENT;
+        return launch_generic_stream_fwd(x, phi, bias, alpha, scale, y, u, coeffs, T, n, C, sk_iters, eps_rms, eps_sk,
+                                         (flags & HVS_MHC_SPLIT_PHI) ? 1 : 0, (cudaStream_t)stream);
+    }
     if (T == 0) return HVS_OK;
     if (!x || !phi || !bias || !alpha || !scale) return HVS_ERR_BAD_ARG;
-    if (flags & HVS_MHC_SPLIT_PHI) return HVS_ERR_UNSUPPORTED;
     if (T * kN >= (int64_t)1 << 31) return HVS_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(u) |
          reinterpret_cast<uintptr_t>(coeffs) | reinterpret_cast<uintptr_t>(saved)) & 15)
@@ -504,11 +522,12 @@ extern "C" int hvs_mhc_stream_post(const void* x, const float* coeffs, const voi
                                    int C, void* stream) {
     using namespace hvs;
     if (T < 0) return HVS_ERR_BAD_ARG;
-    if (n != kN || C != kC) return HVS_ERR_UNSUPPORTED;
+    if ((n != kN || C != kC) && !generic_stream_shape_ok(n, C)) return HVS_ERR_UNSUPPORTED;
     if (T == 0) return HVS_OK;
     if (!x || !coeffs || !fu || !y) return HVS_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(fu)) & 15)
         return HVS_ERR_ALIGNMENT;
+    if (n != kN || C != kC) return launch_generic_stream_post(x, coeffs, fu, y, T, n, C, (cudaStream_t)stream);
     if (T == 0) return HVS_OK;
     int64_t blocks = (T + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 8;

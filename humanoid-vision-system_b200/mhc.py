@@ -27,6 +27,12 @@ FUSED_BWD_MAX_ITERS = 24      # both backward kernels keep every iteration's sca
 FWD_MAX_ITERS = 64
 
 
+def _check_trainable_shape(n: int, c: int, split_phi: bool = False):
+    if (n, c) != (4, 512) or split_phi:
+        raise HvsError("stream mHC training kernels are built for n_streams = 4, channels = 512 with the bf16 projection operand; "
+                       f"got n = {n}, C = {c}, split_phi = {split_phi} (inference supports n in {{2, 4}}, C % 8 == 0, C <= 1024)")
+
+
 def _check_trainable_iters(sk_iters: int):
     """The forward kernel takes up to 64 Sinkhorn iterations; the backward kernels (fused single-pass and the
     two-kernel recompute form alike) differentiate at most 24.  Reject a training call up front instead of
@@ -44,6 +50,7 @@ class _StreamMHCFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk):
         _check_trainable_iters(sk_iters)
+        _check_trainable_shape(x.shape[1], x.shape[2])
         fused = True
         saved = ops.new_saved(x) if fused else None
         y, _, _ = ops.mhc_stream_fwd(x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk, saved=saved)
@@ -69,16 +76,19 @@ class _StreamMHCFn(torch.autograd.Function):
 class StreamMHC(nn.Module):
     """Stream mHC residual layer:  y = H_res x + H_post (x) fn(H_pre^T x).
 
-    x: [..., n, C] bf16 (n = 4, C = 512 in this build).  ``fn=None`` is the identity (one fused kernel,
-    differentiable through the fused backward).  With a wrapped layer ``fn`` the forward runs the
-    coefficient kernel, ``fn`` on the bf16 layer input, and the mixing kernel (inference path).
+    x: [..., n, C] bf16.  n = 4, C = 512 runs on the tuned TMA / tensor-core kernels (forward AND the fused training
+    backward); every other n in {2, 4}, C % 8 == 0, C <= 1024 -- and ``split_phi=True`` (fp32-accurate projection
+    operand, HVS_MHC_SPLIT_PHI) for all shapes -- runs on the general forward kernel (inference).  ``fn=None`` is the
+    identity (one fused kernel).  With a wrapped layer ``fn`` the forward runs the coefficient kernel, ``fn`` on the
+    bf16 layer input, and the mixing kernel (inference path).
     """
 
     def __init__(self, n_streams: int = 4, channels: int = 512, alpha: float = 0.01, sk_iterations: int = 20,
                  eps: float = 1e-8, phi_std: float = 0.02, fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
-                 device=None):
+                 device=None, split_phi: bool = False):
         super().__init__()
         n, c = n_streams, channels
+        self.split_phi = split_phi
         k = n * n + 2 * n
         self.n_streams, self.channels, self.sk_iterations, self.eps = n, c, sk_iterations, eps
         self.phi = nn.Parameter(torch.randn(n * c, k, device=device) * phi_std)
@@ -91,7 +101,7 @@ class StreamMHC(nn.Module):
         """(H_pre [T,n], H_post [T,n], H_res [T,n,n]) for x [T,n,C]."""
         t, n = x.shape[0], self.n_streams
         _, _, co = ops.mhc_stream_fwd(x, self.phi, self.bias, self.alpha, self.rms_scale, self.sk_iterations,
-                                      self.eps, self.eps, want_y=False, want_coeffs=True)
+                                      self.eps, self.eps, want_y=False, want_coeffs=True, split_phi=self.split_phi)
         return co[:, :n], co[:, n:2 * n], co[:, 2 * n:].reshape(t, n, n)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -100,15 +110,16 @@ class StreamMHC(nn.Module):
         needs_grad = torch.is_grad_enabled() and (xf.requires_grad or any(p.requires_grad for p in self.parameters()))
         if self.fn is None and not needs_grad:
             y, _, _ = ops.mhc_stream_fwd(xf, self.phi, self.bias, self.alpha, self.rms_scale, self.sk_iterations,
-                                         self.eps, self.eps)
+                                         self.eps, self.eps, split_phi=self.split_phi)
         elif self.fn is None:
+            _check_trainable_shape(self.n_streams, self.channels, self.split_phi)
             y = _StreamMHCFn.apply(xf, self.phi, self.bias, self.alpha, self.rms_scale, self.sk_iterations,
                                    self.eps, self.eps)
         else:
             if torch.is_grad_enabled() and (xf.requires_grad or self.phi.requires_grad):
                 raise HvsError("StreamMHC with a wrapped fn is forward-only in this build (fused backward covers fn=None)")
             _, u, co = ops.mhc_stream_fwd(xf, self.phi, self.bias, self.alpha, self.rms_scale, self.sk_iterations,
-                                          self.eps, self.eps, want_y=False, want_u=True, want_coeffs=True)
+                                          self.eps, self.eps, want_y=False, want_u=True, want_coeffs=True, split_phi=self.split_phi)
             fu = self.fn(u).to(torch.bfloat16).contiguous()
             y = ops.mhc_stream_post(xf, co, fu)
         return y.reshape(shape)

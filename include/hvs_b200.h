@@ -53,9 +53,10 @@ uint64_t hvs_launch_count(void);
  *   u      [T, C] bf16          layer input H_pre^T x                      (may be NULL)
  *   coeffs [T, n*n+2n] fp32     H_pre (n) | H_post (n) | H_res (n*n, row-major) (may be NULL)
  *
- * flags: HVS_MHC_SPLIT_PHI keeps the projection operand at fp32 accuracy (two bf16
- * terms) instead of rounding scale*phi to bf16.
- * Supported: n == 4, C == 512, sk_iters in [0, 64].
+ * flags: HVS_MHC_SPLIT_PHI keeps the projection operand scale*phi at fp32 accuracy instead of rounding it to bf16.
+ * Supported: sk_iters in [0, 64]; n == 4, C == 512 on the tuned TMA / tensor-core kernel (the roofline path), and every
+ * n in {2, 4}, C % 8 == 0, C <= 1024 -- and HVS_MHC_SPLIT_PHI for all shapes -- on a general warp-per-token kernel
+ * (forward only: the training entry points below are n == 4, C == 512).
  * ---------------------------------------------------------------------------------- */
 #define HVS_MHC_SPLIT_PHI 1u
 

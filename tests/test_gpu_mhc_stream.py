@@ -93,16 +93,45 @@ def test_zero_iterations_and_empty():
     assert y0.shape == (0, 4, 512)
 
 
+@pytest.mark.parametrize("n,c", [(2, 64), (2, 256), (2, 1024), (4, 64), (4, 128), (4, 256), (4, 1024), (4, 512), (2, 40)])
+@pytest.mark.parametrize("split", [False, True])
+def test_forward_general_shapes_and_split_phi(n, c, split):
+    """Every stream shape the model's call sites have (n in {2, 4}, C from 32 to 1024) on the general
+    forward kernel, and HVS_MHC_SPLIT_PHI (fp32-accurate projection operand) for all shapes incl. n = 4, C = 512."""
+    if (n, c) == (4, 512) and not split:
+        pytest.skip("the tuned kernel: covered above")
+    import hvs_b200
+    t = 333
+    x, phi, bias, al, scale = make_inputs(t, seed=n * c + split, alpha=0.3, phistd=0.03, bstd=0.1, n=n, c=c)
+    y, u, co = run_gpu(x, phi, bias, al, scale, split_phi=split)
+    ref = mhc_ref.stream_mhc_forward(x, phi, bias, al, scale, split_phi=split)
+    check_against_oracle(x, phi, bias, al, scale, y, u, co, ref=ref)
+    # wrapped-layer path: coefficients + mixing kernel with fu = u reproduces y
+    y2 = hvs_b200.ops.mhc_stream_post(x.cuda(), co.cuda(), u.cuda())
+    mag = mhc_ref.mixing_condition_magnitude(x, ref["H_pre"], ref["H_post"], ref["H_res"])
+    assert ((y2.cpu().float() - y.float()).abs() <= 2 * mhc_ref.bf16_ulp(mag)).all()
+    layer = hvs_b200.StreamMHC(n_streams=n, channels=c, split_phi=split, device="cuda")
+    with torch.no_grad():
+        assert layer(x.cuda()).shape == x.shape
+    if (n, c) != (4, 512) or split:
+        with pytest.raises(hvs_b200.HvsError, match="training kernels"):
+            layer(x.cuda().requires_grad_(True))
+
+
 def test_deterministic_and_unsupported_shape():
     import hvs_b200
     inp = make_inputs(2048, seed=3)
     a = run_gpu(*inp)
     b = run_gpu(*inp)
     assert torch.equal(a[0].view(torch.int16), b[0].view(torch.int16)) and torch.equal(a[2], b[2])
-    x = torch.zeros(4, 4, 256, dtype=torch.bfloat16, device="cuda:0")
+    x = torch.zeros(4, 3, 256, dtype=torch.bfloat16, device="cuda:0")          # n = 3: neither kernel takes it
     with pytest.raises(hvs_b200.HvsError):
-        hvs_b200.ops.mhc_stream_fwd(x, torch.zeros(1024, 24, device="cuda:0"), torch.zeros(24, device="cuda:0"),
-                                    torch.zeros(3, device="cuda:0"), torch.ones(1024, device="cuda:0"))
+        hvs_b200.ops.mhc_stream_fwd(x, torch.zeros(768, 15, device="cuda:0"), torch.zeros(15, device="cuda:0"),
+                                    torch.zeros(3, device="cuda:0"), torch.ones(768, device="cuda:0"))
+    x = torch.zeros(4, 4, 2048, dtype=torch.bfloat16, device="cuda:0")         # C > 1024
+    with pytest.raises(hvs_b200.HvsError):
+        hvs_b200.ops.mhc_stream_fwd(x, torch.zeros(8192, 24, device="cuda:0"), torch.zeros(24, device="cuda:0"),
+                                    torch.zeros(3, device="cuda:0"), torch.ones(8192, device="cuda:0"))
 
 
 def test_split_pre_post_equals_fused():
