@@ -69,6 +69,9 @@ _SIGNATURES = {
                                 c_size_t, c_void_p]),
     "hvs_layernorm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int,
                                   c_int, c_float, c_void_p]),
+    "hvs_layernorm_bwd_workspace": (c_size_t, [c_int64, c_int]),
+    "hvs_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float,
+                                  c_void_p, c_size_t, c_void_p]),
     "hvs_mhc_static_coeffs_workspace": (c_size_t, [POINTER(CoeffJob), c_int, c_int, c_int]),
     "hvs_mhc_static_coeffs": (c_int, [POINTER(CoeffJob), c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "hvs_mhc_static_coeffs_bwd": (c_int, [POINTER(CoeffJob), POINTER(CoeffGrad), c_int, c_int, c_float, c_void_p, c_size_t,

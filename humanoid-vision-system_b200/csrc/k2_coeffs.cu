@@ -580,7 +580,13 @@ int run_plan(const hvs_coeff_job* jobs, const hvs_coeff_grad* grads, int num_job
              size_t workspace_bytes, cudaStream_t stream, bool backward, bool size_only, size_t* size_out) {
     if (num_jobs < 0 || iters < 0 || (num_jobs > 0 && !jobs)) return HVS_ERR_BAD_ARG;
     if (num_jobs == 0) { if (size_out) *size_out = 256; return HVS_OK; }
-    const int grid = sm_count();
+    // as many CTAs as the work can feed (>= 8192 matrix elements each): a single 256 x 256 layer (the per-layer backward of
+    // a training step) runs on 8 CTAs whose grid barrier is several times cheaper than one across all 148 SMs
+    double elems = 0;
+    for (int b = 0; b < num_jobs; ++b) elems += (double)jobs[b].D * jobs[b].D;
+    int grid = (int)(elems / 8192.0);
+    if (grid < 1) grid = 1;
+    if (grid > sm_count()) grid = sm_count();
     HostPlan hp;
     int rc = build_plan(hp, jobs, grads, num_jobs, grid, iters, backward);
     if (rc) return rc;

@@ -149,10 +149,17 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&f)[8]) {
     return o;
 }
 
-template <typename TI, int D>
+template <typename TO> __device__ __forceinline__ void store8(TO* p, const float (&f)[8]);
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) { *reinterpret_cast<uint4*>(p) = pack8_bf16(f); }
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+template <typename TI, typename TO, int D>
 __global__ void __launch_bounds__(256)
 layernorm_small_rows_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                            __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ copy, int64_t rows, float eps) {
+                            TO* __restrict__ out, __nv_bfloat16* __restrict__ copy, int64_t rows, float eps) {
     constexpr int kVec = D >= 512 ? D / 256 : 1;            // 8-element vectors per lane
     constexpr int kLanes = D / (8 * kVec);                  // lanes per row (4 ... 32)
     constexpr int kRowsPerWarp = 32 / kLanes;
@@ -198,14 +205,14 @@ layernorm_small_rows_kernel(const TI* __restrict__ x, const float* __restrict__ 
                 float y[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) y[j] = (f[v][j] - mean) * inv * wv[v][j] + bv[v][j];
-                *reinterpret_cast<uint4*>(out + r * D + (v * kLanes + l) * 8) = pack8_bf16(y);
+                store8<TO>(out + r * D + (v * kLanes + l) * 8, y);
             }
         }
     }
 }
 
-template <typename TI>
-bool launch_small_rows(const TI* x, const float* w, const float* b, __nv_bfloat16* out, __nv_bfloat16* copy, int64_t rows, int dim,
+template <typename TI, typename TO>
+bool launch_small_rows(const TI* x, const float* w, const float* b, TO* out, __nv_bfloat16* copy, int64_t rows, int dim,
                        float eps, cudaStream_t stream) {
     int64_t blocks = (rows * (dim >= 512 ? 32 : dim / 8) / 32 + 7) / 8;      // 8 warps per block
     const int64_t cap = (int64_t)sm_count() * 16;
@@ -213,11 +220,129 @@ bool launch_small_rows(const TI* x, const float* w, const float* b, __nv_bfloat1
     if (blocks < 1) blocks = 1;
     const int g = (int)blocks;
     switch (dim) {
-        case 32: layernorm_small_rows_kernel<TI, 32><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
-        case 64: layernorm_small_rows_kernel<TI, 64><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
-        case 128: layernorm_small_rows_kernel<TI, 128><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
-        case 256: layernorm_small_rows_kernel<TI, 256><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
-        case 512: layernorm_small_rows_kernel<TI, 512><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
+        case 32: layernorm_small_rows_kernel<TI, TO, 32><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
+        case 64: layernorm_small_rows_kernel<TI, TO, 64><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
+        case 128: layernorm_small_rows_kernel<TI, TO, 128><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
+        case 256: layernorm_small_rows_kernel<TI, TO, 256><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
+        case 512: layernorm_small_rows_kernel<TI, TO, 512><<<g, 256, 0, stream>>>(x, w, b, out, copy, rows, eps); return true;
+        default: return false;
+    }
+}
+
+// LayerNorm backward for the same small rows (training of the module's norm_pre / norm_post, fp32 statistics):
+//   xhat = (x - mean) rstd, g = dy w:  dx = rstd (g - mean(g) - xhat mean(g xhat));  dw = sum_rows dy xhat;  db = sum_rows dy.
+// A lane owns the same columns for every row it meets, so dw / db accumulate in registers; they are combined across the
+// row sub-groups of the warp, the warps of the CTA (shared memory) and the CTAs (workspace + finalize), all in fixed order.
+template <typename TI, typename TG, int D>
+__global__ void __launch_bounds__(256)
+layernorm_small_rows_bwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const TG* __restrict__ dy,
+                                TI* __restrict__ dx, float* __restrict__ part, int64_t rows, float eps) {
+    constexpr int kVec = D >= 512 ? D / 256 : 1;
+    constexpr int kLanes = D / (8 * kVec);
+    constexpr int kRowsPerWarp = 32 / kLanes;
+    __shared__ float sm[8][2][D];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int sub = lane / kLanes, l = lane % kLanes;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + wid;
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    float wv[kVec][8], aw[kVec][8], ab[kVec][8];
+#pragma unroll
+    for (int v = 0; v < kVec; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { wv[v][j] = w[(v * kLanes + l) * 8 + j]; aw[v][j] = 0.f; ab[v][j] = 0.f; }
+    for (int64_t r0 = warp * kRowsPerWarp; r0 < rows; r0 += nwarps * kRowsPerWarp) {
+        const int64_t r = r0 + sub;
+        const bool ok = r < rows;
+        float f[kVec][8], g[kVec][8];
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < kVec; ++v) {
+            if (ok) {
+                Load8<TI>::ld(x + r * D + (v * kLanes + l) * 8, f[v]);
+                Load8<TG>::ld(dy + r * D + (v * kLanes + l) * 8, g[v]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { f[v][j] = 0.f; g[v][j] = 0.f; }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += f[v][j];
+        }
+#pragma unroll
+        for (int o = kLanes / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / (float)D);
+        float q = 0.f;
+#pragma unroll
+        for (int v = 0; v < kVec; ++v)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = f[v][j] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+        for (int o = kLanes / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.0f / (float)D) + eps);
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int v = 0; v < kVec; ++v)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (f[v][j] - mean) * rstd;
+                f[v][j] = xh;
+                aw[v][j] = fmaf(g[v][j], xh, aw[v][j]);
+                ab[v][j] += g[v][j];
+                g[v][j] *= wv[v][j];
+                sg += g[v][j];
+                sgx = fmaf(g[v][j], xh, sgx);
+            }
+#pragma unroll
+        for (int o = kLanes / 2; o > 0; o >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, o); sgx += __shfl_xor_sync(0xffffffffu, sgx, o); }
+        sg *= (1.0f / (float)D); sgx *= (1.0f / (float)D);
+        if (ok) {
+#pragma unroll
+            for (int v = 0; v < kVec; ++v) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rstd * (g[v][j] - sg - f[v][j] * sgx);
+                store8<TI>(dx + r * D + (v * kLanes + l) * 8, o);
+            }
+        }
+    }
+    // combine the row sub-groups of the warp (lanes with the same l), then the warps, then write the CTA partial
+#pragma unroll
+    for (int v = 0; v < kVec; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int o = kLanes; o < 32; o <<= 1) {
+                aw[v][j] += __shfl_xor_sync(0xffffffffu, aw[v][j], o);
+                ab[v][j] += __shfl_xor_sync(0xffffffffu, ab[v][j], o);
+            }
+            if (sub == 0) { sm[wid][0][(v * kLanes + l) * 8 + j] = aw[v][j]; sm[wid][1][(v * kLanes + l) * 8 + j] = ab[v][j]; }
+        }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * D; c += 256) {
+        const int which = c / D, col = c % D;
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][which][col];
+        part[((size_t)blockIdx.x * 2 + which) * D + col] = t;
+    }
+}
+
+__global__ void ln_bwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ db, int parts, int dim) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    float a = 0.f, b = 0.f;
+    for (int p = 0; p < parts; ++p) { a += part[((size_t)p * 2) * dim + j]; b += part[((size_t)p * 2 + 1) * dim + j]; }
+    dw[j] = a; db[j] = b;
+}
+
+template <typename TI, typename TG>
+bool launch_small_rows_bwd(const TI* x, const float* w, const TG* dy, TI* dx, float* part, int blocks, int64_t rows, int dim, float eps,
+                           cudaStream_t stream) {
+    switch (dim) {
+        case 32: layernorm_small_rows_bwd_kernel<TI, TG, 32><<<blocks, 256, 0, stream>>>(x, w, dy, dx, part, rows, eps); return true;
+        case 64: layernorm_small_rows_bwd_kernel<TI, TG, 64><<<blocks, 256, 0, stream>>>(x, w, dy, dx, part, rows, eps); return true;
+        case 128: layernorm_small_rows_bwd_kernel<TI, TG, 128><<<blocks, 256, 0, stream>>>(x, w, dy, dx, part, rows, eps); return true;
+        case 256: layernorm_small_rows_bwd_kernel<TI, TG, 256><<<blocks, 256, 0, stream>>>(x, w, dy, dx, part, rows, eps); return true;
+        case 512: layernorm_small_rows_bwd_kernel<TI, TG, 512><<<blocks, 256, 0, stream>>>(x, w, dy, dx, part, rows, eps); return true;
         default: return false;
     }
 }
@@ -298,12 +423,14 @@ extern "C" int hvs_layernorm_fwd(const void* x, int x_dtype, const float* weight
     if (!x || !out) return HVS_ERR_BAD_ARG;
     const int g = grid_for_rows(rows);
     __nv_bfloat16* cp = (__nv_bfloat16*)x_bf16_copy;
-    const bool dense = out_ld == dim && (cp == nullptr || copy_ld == dim) && out_dtype == HVS_DTYPE_BF16 &&
+    const bool dense = out_ld == dim && (cp == nullptr || copy_ld == dim) &&
                        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(cp)) & 15) == 0;
     if (dense) {
         bool done = false;
-        if (x_dtype == HVS_DTYPE_BF16) done = launch_small_rows((const __nv_bfloat16*)x, weight, bias, (__nv_bfloat16*)out, cp, rows, dim, eps, stream);
-        else if (x_dtype == HVS_DTYPE_F32) done = launch_small_rows((const float*)x, weight, bias, (__nv_bfloat16*)out, cp, rows, dim, eps, stream);
+        if (x_dtype == HVS_DTYPE_BF16 && out_dtype == HVS_DTYPE_BF16) done = launch_small_rows((const __nv_bfloat16*)x, weight, bias, (__nv_bfloat16*)out, cp, rows, dim, eps, stream);
+        else if (x_dtype == HVS_DTYPE_F32 && out_dtype == HVS_DTYPE_BF16) done = launch_small_rows((const float*)x, weight, bias, (__nv_bfloat16*)out, cp, rows, dim, eps, stream);
+        else if (x_dtype == HVS_DTYPE_BF16 && out_dtype == HVS_DTYPE_F32) done = launch_small_rows((const __nv_bfloat16*)x, weight, bias, (float*)out, cp, rows, dim, eps, stream);
+        else if (x_dtype == HVS_DTYPE_F32 && out_dtype == HVS_DTYPE_F32) done = launch_small_rows((const float*)x, weight, bias, (float*)out, cp, rows, dim, eps, stream);
         if (done) {
             count_launch();
             return launch_status();
@@ -320,5 +447,38 @@ extern "C" int hvs_layernorm_fwd(const void* x, int x_dtype, const float* weight
     else
         return HVS_ERR_UNSUPPORTED;
     count_launch();
+    return launch_status();
+}
+
+extern "C" size_t hvs_layernorm_bwd_workspace(int64_t rows, int dim) {
+    if (rows < 0 || dim <= 0) return 0;
+    int64_t blocks = (rows + 63) / 64;
+    const int64_t cap = (int64_t)hvs::sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (size_t)blocks * 2 * dim * sizeof(float);
+}
+
+extern "C" int hvs_layernorm_bwd(const void* x, int x_dtype, const float* weight, const void* dy, int dy_dtype, void* dx, float* dweight,
+                                 float* dbias, int64_t rows, int dim, float eps, void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (rows < 0 || dim <= 0 || !weight || !dweight || !dbias) return HVS_ERR_BAD_ARG;
+    if (dim != 32 && dim != 64 && dim != 128 && dim != 256 && dim != 512) return HVS_ERR_UNSUPPORTED;
+    if (rows > 0 && (!x || !dy || !dx)) return HVS_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) return HVS_ERR_ALIGNMENT;
+    const size_t need = hvs_layernorm_bwd_workspace(rows, dim);
+    if (!workspace || workspace_bytes < need) return HVS_ERR_WORKSPACE;
+    const int blocks = (int)(need / ((size_t)2 * dim * sizeof(float)));
+    float* part = (float*)workspace;
+    bool ok = false;
+    typedef __nv_bfloat16 bf;
+    if (x_dtype == HVS_DTYPE_F32 && dy_dtype == HVS_DTYPE_F32) ok = launch_small_rows_bwd((const float*)x, weight, (const float*)dy, (float*)dx, part, blocks, rows, dim, eps, stream);
+    else if (x_dtype == HVS_DTYPE_BF16 && dy_dtype == HVS_DTYPE_F32) ok = launch_small_rows_bwd((const bf*)x, weight, (const float*)dy, (bf*)dx, part, blocks, rows, dim, eps, stream);
+    else if (x_dtype == HVS_DTYPE_F32 && dy_dtype == HVS_DTYPE_BF16) ok = launch_small_rows_bwd((const float*)x, weight, (const bf*)dy, (float*)dx, part, blocks, rows, dim, eps, stream);
+    else if (x_dtype == HVS_DTYPE_BF16 && dy_dtype == HVS_DTYPE_BF16) ok = launch_small_rows_bwd((const bf*)x, weight, (const bf*)dy, (bf*)dx, part, blocks, rows, dim, eps, stream);
+    if (!ok) return HVS_ERR_UNSUPPORTED;
+    ln_bwd_finalize_kernel<<<(dim + 127) / 128, 128, 0, stream>>>(part, dweight, dbias, blocks, dim);
+    count_launch(2);
     return launch_status();
 }

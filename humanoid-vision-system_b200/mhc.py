@@ -310,6 +310,37 @@ class RMSNorm(nn.Module):
         return ops.rmsnorm_fwd(x, self.scale.detach(), self.eps)
 
 
+class _LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last axis on this library's row kernels (training of the module's norm_pre / norm_post; the
+    ATen kernels spend 40 ms per 16-image step on the backbone's 32 / 64-wide rows).  fp32 statistics; the output dtype
+    is chosen by the caller: bf16 where the only consumer is an autocast matmul (one rounding of the fp32 result either
+    way), fp32 for the module output."""
+
+    @staticmethod
+    def forward(ctx, x2, weight, bias, eps, out_dtype):
+        x2 = x2.contiguous()
+        out, _ = ops.layernorm_fwd(x2, weight.detach(), bias.detach(), eps, out_dtype=out_dtype)
+        ctx.save_for_backward(x2, weight)
+        ctx.eps = eps
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        if dy.dtype not in (torch.float32, torch.bfloat16):
+            dy = dy.float()
+        dx, dw, db = ops.layernorm_bwd(x2, weight.detach(), dy, ctx.eps)
+        return dx, dw, db, None, None
+
+
+def _layer_norm(mod: nn.LayerNorm, x: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    """mod(x) through _LayerNormFn when the kernels take the shape, else the module itself."""
+    d = x.shape[-1]
+    if x.is_cuda and d in ops.LN_BWD_DIMS and x.dtype in (torch.float32, torch.bfloat16) and mod.weight.dtype == torch.float32:
+        return _LayerNormFn.apply(x.reshape(-1, d), mod.weight, mod.bias, mod.eps, out_dtype).reshape(x.shape)
+    return mod(x)
+
+
 class _CoeffState:
     """Per-module device buffers of the static coefficient path (fp32 matrices, their bf16 transposed copies for the
     GEMM B operands, the scaling history the backward consumes, bf16 copies of the MLP weights)."""
@@ -519,13 +550,14 @@ class ManifoldHyperConnection(nn.Module):
             x = x.reshape(shape[0], -1, shape[-1])
         x_in = x
         h_pre, h_post, h_res = self.constrained_matrices()
-        with torch.autocast("cuda", enabled=self.use_mixed_precision and x.is_cuda, dtype=self.dtype):
-            z = self.norm_pre(x)
+        mixed = self.use_mixed_precision and x.is_cuda
+        with torch.autocast("cuda", enabled=mixed, dtype=self.dtype):
+            z = _layer_norm(self.norm_pre, x, torch.bfloat16 if mixed else torch.float32)
             z = torch.matmul(z, h_pre)
             z = self.mlp(z)
             z = torch.matmul(z, h_post)
             out = torch.matmul(x_in, h_res) + z
-            out = self.norm_post(out)
+            out = _layer_norm(self.norm_post, out, torch.float32)
             out = self.dropout(out)
         if self.training and self.monitor_signal_ratio:
             with torch.no_grad():                        # :295-303, without the per-call eigvalsh

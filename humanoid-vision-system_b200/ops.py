@@ -246,6 +246,26 @@ def layernorm_fwd(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps
     return out, cp
 
 
+LN_BWD_DIMS = (32, 64, 128, 256, 512)
+
+
+@_on_device
+def layernorm_bwd(x: torch.Tensor, weight: torch.Tensor, dy: torch.Tensor, eps: float = 1e-5):
+    """Backward of LayerNorm over the last axis of x [rows, dim] (dim in LN_BWD_DIMS): (dx [x's dtype], dweight, dbias fp32)."""
+    _need_cuda(x, weight, dy)
+    rows, dim = x.shape
+    xc, dyc = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(xc)
+    dw = torch.empty(dim, dtype=torch.float32, device=x.device)
+    db = torch.empty(dim, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    nb = int(lib.hvs_layernorm_bwd_workspace(rows, dim))
+    ws = torch.empty(max(nb, 256), dtype=torch.uint8, device=x.device)
+    check(lib.hvs_layernorm_bwd(_ptr(xc), _NORM_DTYPES[xc.dtype], _ptr(weight), _ptr(dyc), _NORM_DTYPES[dyc.dtype], _ptr(dx), _ptr(dw),
+                                _ptr(db), rows, dim, eps, _ptr(ws), ws.numel(), _stream()), "hvs_layernorm_bwd")
+    return dx, dw, db
+
+
 # ----------------------------------------------------------------------------- K2: batched static coefficients, GEMMs
 def _coeff_arrays(jobs: Sequence[Dict[str, Optional[torch.Tensor]]]):
     arr = (_lib.CoeffJob * len(jobs))()

@@ -149,6 +149,11 @@ int hvs_rmsnorm_bwd(const void* x, int dtype, const float* scale, const void* dy
                     int64_t rows, int dim, float eps, void* workspace, size_t workspace_bytes, void* stream);
 int hvs_layernorm_fwd(const void* x, int x_dtype, const float* weight, const float* bias, void* out, int out_dtype,
                       void* x_bf16_copy, int64_t rows, int dim, int out_ld, int copy_ld, float eps, void* stream);
+/* LayerNorm backward (training of the module's norm_pre / norm_post): x and dy fp32 / bf16 independently -> dx (x's dtype), dweight,
+ * dbias [dim] fp32 (overwritten; fixed-order two-stage reduction through `workspace`).  dim in {32, 64, 128, 256, 512}. */
+size_t hvs_layernorm_bwd_workspace(int64_t rows, int dim);
+int hvs_layernorm_bwd(const void* x, int x_dtype, const float* weight, const void* dy, int dy_dtype, void* dx, float* dweight,
+                      float* dbias, int64_t rows, int dim, float eps, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K2, the reference-literal module: static coefficients of MANY layers in one launch.

@@ -82,6 +82,25 @@ def test_layernorm_small_row_kernel(rows, dim):
         assert none is None and torch.equal(out2, out)
 
 
+@pytest.mark.parametrize("rows,dim", [(4099, 32), (1000, 64), (333, 128), (77, 256), (130, 512)])
+def test_layernorm_backward_kernel(rows, dim):
+    import hvs_b200
+    for xdt, gdt in ((torch.float32, torch.float32), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)):
+        x = (_rand(rows, dim, seed=rows) * 2 + 0.7).to(xdt)
+        w, dy = 1 + 0.1 * _rand(dim, seed=1), _rand(rows, dim, seed=3).to(gdt)
+        xl, wl, bl = x.float().requires_grad_(True), w.clone().requires_grad_(True), torch.zeros(dim, requires_grad=True)
+        torch.nn.functional.layer_norm(xl, (dim,), wl, bl).backward(dy.float())
+        dx, dw, db = hvs_b200.ops.layernorm_bwd(x.to(DEV), w.to(DEV), dy.to(DEV))
+        tol = 2.0 ** -7 if xdt == torch.bfloat16 else 1e-5
+        assert (dx.cpu().float() - xl.grad).abs().max() <= tol * xl.grad.abs().max() + 1e-6
+        assert torch.allclose(dw.cpu(), wl.grad, rtol=1e-4, atol=1e-3) and torch.allclose(db.cpu(), bl.grad, rtol=1e-4, atol=1e-3)
+        dx2, dw2, _ = hvs_b200.ops.layernorm_bwd(x.to(DEV), w.to(DEV), dy.to(DEV))
+        assert torch.equal(dx, dx2) and torch.equal(dw, dw2)
+    # fp32 output from the small-row forward kernel
+    out, _ = hvs_b200.ops.layernorm_fwd(x.to(DEV), w.to(DEV), torch.zeros(dim, device=DEV), 1e-5, torch.float32, dim)
+    assert torch.allclose(out.cpu(), torch.nn.functional.layer_norm(x.float(), (dim,), w, torch.zeros(dim)), rtol=1e-5, atol=2e-6)
+
+
 def test_gemm_partial_k_stage_is_zero_filled():
     """K = 32 / 96 / 160 (not multiples of the 64-element stage): TMA zero-fills the rest of the box on both operands."""
     import hvs_b200
@@ -482,7 +501,7 @@ def test_module_training_path_gradients_vs_oracle():
         xg = x.to(DEV).requires_grad_(True)
         before = hvs_b200._lib.launch_count()
         mod(xg).backward(dy.to(DEV))
-        assert hvs_b200._lib.launch_count() - before == 2           # coefficients forward + backward: nothing unrolled
+        assert hvs_b200._lib.launch_count() - before == 2 + 2 + 4   # coefficients fwd + bwd (nothing unrolled), 2 LayerNorm fwd, 2 x 2 bwd
         grad_keys = ("H_pre_raw", "H_post_raw", "H_res_raw", "mlp.0.weight", "mlp.0.bias", "mlp.3.weight", "mlp.3.bias",
                      "norm_pre.weight", "norm_pre.bias", "norm_post.weight", "norm_post.bias")
         leaf = {k: (v.clone().requires_grad_(True) if k in grad_keys else v) for k, v in p.items()}
