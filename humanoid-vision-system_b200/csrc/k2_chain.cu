@@ -3,7 +3,7 @@
 //
 //     xn = LayerNorm_pre(x)                                   (:250)   in the tile prologue, from the TMA-staged x tile
 //     h0 = xn @ H_pre                                         (:253)   tcgen05.mma -> tensor memory -> bf16 -> shared memory
-//     h1 = GELU(h0 @ W1^T + b1)                               (:164-165)   in 128-column chunks ...
+//     h1 = GELU(h0 @ W1^T + b1)                               (:164-165)   in 64-column chunks ...
 //     h2 = GELU(h1 @ W2^T + b2)                               (:167-168)   ... each chunk is at once a K block of this GEMM
 //     y  = LayerNorm_post(h2 @ H_post + x @ H_res)            (:259-267)   one accumulator, normalised in the epilogue
 //
@@ -15,7 +15,9 @@
 // the order the MMAs consume them), a tcgen05.mma issuer thread, eight epilogue warps (two per tensor-memory lane
 // quadrant, splitting the columns) that also do the LayerNorm prologue and write every intermediate into shared memory
 // in the 128-byte-swizzled K-major layout the next MMA reads it in.  Tensor memory: [0, H) = h0's accumulator, later
-// h2's; [256, 512) = two 128-column accumulators for the h1 chunks, the first of which is reused for the output.
+// h2's; [256, 512) = two accumulators for the 64-column h1 chunks, the first of which is reused for the output.
+// h1 chunks are 64 wide (one K block of the next GEMM): with 128-wide chunks their two buffers took 64 KB and left a
+// two-slot weight ring at D = 64, which bound the chunk loop by TMA round trips (34 k cycles per tile).
 // The h1 chunk loop is software-pipelined: the MMAs of chunk j+1 run while the epilogue warps apply GELU to chunk j.
 #include <cuda_bf16.h>
 #include <math.h>
@@ -82,14 +84,15 @@ __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t g) { return (r >>
 template <int D, int H>
 struct Cfg {
     static constexpr int H2 = 2 * H;
-    static constexpr int NCH = H2 / 128;                 // h1 chunks of 128 columns
+    static constexpr int CW = 64;                        // h1 chunk width = one K block of the h2 GEMM
+    static constexpr int NCH = H2 / CW;                  // h1 chunks
     static constexpr int KBH = H / 64;                   // 64-wide K blocks of an H-wide operand
     static constexpr int kOffX = 0;                      // x tile   [128 x 64] (TMA, columns >= D zero-filled)
     static constexpr int kOffXN = 16384;                 // LN(x)    [128 x 64]
     static constexpr int kOffH0 = 32768;                 // h0 / h2  [128 x H]  = KBH blocks of 16 KB
-    static constexpr int kOffH1 = kOffH0 + KBH * 16384;  // h1 chunk [128 x 128] x 2 buffers
-    static constexpr int kOffRing = kOffH1 + 2 * 32768;
-    static constexpr int kSlots = (D == 32) ? 3 : 2;
+    static constexpr int kOffH1 = kOffH0 + KBH * 16384;  // h1 chunk [128 x 64] x 2 buffers
+    static constexpr int kOffRing = kOffH1 + 2 * 16384;
+    static constexpr int kSlots = (D == 32) ? 4 : 3;
     static constexpr int kOffBar = kOffRing + kSlots * kSlotBytes;
     static constexpr int kSmemBytes = kOffBar + 256 + 1024;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -97,7 +100,7 @@ struct Cfg {
 };
 
 enum { B_XFULL = 0, B_XFREE, B_XN, B_ACCA, B_HA, B_ACC1, B_H1 = B_ACC1 + 2, B_G3 = B_H1 + 2, B_ACC3 = B_G3 + 2, B_ACC3FREE, B_RFULL,
-       B_REMPTY = B_RFULL + 3, B_COUNT = B_REMPTY + 3 };
+       B_REMPTY = B_RFULL + 4, B_COUNT = B_REMPTY + 4 };
 
 template <int D, int H>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -122,7 +125,7 @@ k2_chain_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             mbar_init(&bar[B_ACC1 + b], 1); mbar_init(&bar[B_H1 + b], kEpiWarps); mbar_init(&bar[B_G3 + b], 1);
         }
         mbar_init(&bar[B_ACC3], 1); mbar_init(&bar[B_ACC3FREE], kEpiWarps);
-        for (int s = 0; s < 3; ++s) { mbar_init(&bar[B_RFULL + s], 1); mbar_init(&bar[B_REMPTY + s], 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&bar[B_RFULL + s], 1); mbar_init(&bar[B_REMPTY + s], 1); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -152,27 +155,15 @@ k2_chain_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     tma_load_2d(s, &tm_hpre, &bar[B_RFULL + slot], 0, 0);
                     advance();
                 }
-                auto load_w1 = [&](int j) {               // W1 rows [128 j, +128), all of K = H: two K blocks per slot
-                    for (int kb = 0; kb < C::KBH; kb += 2) {
-                        uint8_t* s = acquire(32768);
-                        tma_load_2d(s, &tm_w1, &bar[B_RFULL + slot], kb * 64, j * 128);
-                        tma_load_2d(s + 16384, &tm_w1, &bar[B_RFULL + slot], (kb + 1) * 64, j * 128);
-                        advance();
-                    }
+                auto load_w1 = [&](int j) {               // W1 rows [64 j, +64), all of K = H: KBH boxes of [64 x 64] in one slot
+                    uint8_t* s = acquire(C::KBH * 8192);
+                    for (int kb = 0; kb < C::KBH; ++kb) tma_load_2d(s + kb * 8192, &tm_w1, &bar[B_RFULL + slot], kb * 64, j * 64);
+                    advance();
                 };
-                auto load_w2 = [&](int j) {               // W2 [H rows] x K columns [128 j, +128): two K blocks of H x 64
-                    if (H == 256) {
-                        for (int k = 0; k < 2; ++k) {
-                            uint8_t* s = acquire(32768);
-                            tma_load_2d(s, &tm_w2, &bar[B_RFULL + slot], j * 128 + k * 64, 0);
-                            advance();
-                        }
-                    } else {
-                        uint8_t* s = acquire(32768);
-                        tma_load_2d(s, &tm_w2, &bar[B_RFULL + slot], j * 128, 0);
-                        tma_load_2d(s + 16384, &tm_w2, &bar[B_RFULL + slot], j * 128 + 64, 0);
-                        advance();
-                    }
+                auto load_w2 = [&](int j) {               // W2 [H rows] x K columns [64 j, +64): one box of [H x 64]
+                    uint8_t* s = acquire(H * 128);
+                    tma_load_2d(s, &tm_w2, &bar[B_RFULL + slot], j * 64, 0);
+                    advance();
                 };
                 for (int j = 0; j < C::NCH; ++j) {
                     load_w1(j);
@@ -230,28 +221,18 @@ k2_chain_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     const int b = j & 1;
                     mbar_wait(&bar[B_H1 + b], n_h1[b]++ & 1u);
                     tc_fence_after();
-                    const uint32_t h1 = base + C::kOffH1 + b * 32768;
-                    if (H == 256) {
-                        for (int k = 0; k < 2; ++k) {
-                            const uint32_t s = slot_wait();
-                            mma_block(accA, h1 + k * 16384, s, H, 4, j == 0 && k == 0);
-                            slot_release();
-                        }
-                    } else {
-                        const uint32_t s = slot_wait();
-                        mma_block(accA, h1, s, H, 4, j == 0);
-                        mma_block(accA, h1 + 16384, s + 16384, H, 4, false);
-                        slot_release();
-                    }
+                    const uint32_t h1 = base + C::kOffH1 + b * 16384;
+                    const uint32_t s = slot_wait();
+                    mma_block(accA, h1, s, H, 4, j == 0);
+                    slot_release();
                     umma_commit(&bar[B_G3 + b]);
                 };
                 for (int j = 0; j < C::NCH; ++j) {
-                    // ---- G2 chunk j: acc1[j & 1] = h0 @ W1[chunk j]^T
+                    // ---- G2 chunk j: acc1[j & 1] = h0 @ W1[chunk j]^T   (N = 64)
                     const uint32_t d = acc1 + (uint32_t)(j & 1) * 128u;
-                    for (int kb = 0; kb < C::KBH; kb += 2) {
+                    {
                         const uint32_t s = slot_wait();
-                        mma_block(d, base + C::kOffH0 + kb * 16384, s, 128, 4, kb == 0);
-                        mma_block(d, base + C::kOffH0 + (kb + 1) * 16384, s + 16384, 128, 4, false);
+                        for (int kb = 0; kb < C::KBH; ++kb) mma_block(d, base + C::kOffH0 + kb * 16384, s + kb * 8192, C::CW, 4, kb == 0);
                         slot_release();
                     }
                     umma_commit(&bar[B_ACC1 + (j & 1)]);
@@ -337,19 +318,19 @@ k2_chain_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar[B_HA]);
 
-            // ---- E1: per 128-column chunk of h1: + b1, GELU, bf16 -> shared memory
+            // ---- E1: per 64-column chunk of h1: + b1, GELU, bf16 -> shared memory (each warp of a quadrant pair takes 32 columns)
             for (int j = 0; j < C::NCH; ++j) {
                 const int b = j & 1;
                 mbar_wait(&bar[B_ACC1 + b], n_acc1[b]++ & 1u);
                 if (n_g3[b] > 0) mbar_wait(&bar[B_G3 + b], (n_g3[b] - 1) & 1u);    // the MMAs that read this h1 buffer last are done
                 ++n_g3[b];
                 tc_fence_after();
-                for (int c = half; c < 4; c += 2) {
+                for (int c = half; c < C::CW / 32; c += 2) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + lane_base + kColAcc1 + (uint32_t)(b * 128 + c * 32), v);
                     tmem_wait_ld();
-                    const float4* b4 = reinterpret_cast<const float4*>(p.b1 + j * 128 + c * 32);
-                    const uint32_t blk = base + C::kOffH1 + (uint32_t)b * 32768u + (uint32_t)(c >> 1) * 16384u;
+                    const float4* b4 = reinterpret_cast<const float4*>(p.b1 + j * C::CW + c * 32);
+                    const uint32_t blk = base + C::kOffH1 + (uint32_t)b * 16384u;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
@@ -446,7 +427,7 @@ int launch_chain(const void* x, const void* hpre_t, const void* w1, const void* 
     int rc;
     if ((rc = make_tmap_bf16_2d_ld(&tx, x, (uint64_t)p.T, D, D, kBM))) return rc;
     if ((rc = make_tmap_bf16_2d_ld(&thpre, hpre_t, H, D, D, H))) return rc;
-    if ((rc = make_tmap_bf16_2d_ld(&tw1, w1, 2 * H, H, H, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d_ld(&tw1, w1, 2 * H, H, H, C::CW))) return rc;
     if ((rc = make_tmap_bf16_2d_ld(&tw2, w2, H, 2 * H, 2 * H, H))) return rc;
     if ((rc = make_tmap_bf16_2d_ld(&thpost, hpost_t, D, H, H, D))) return rc;
     if ((rc = make_tmap_bf16_2d_ld(&thres, hres_t, D, D, D, D))) return rc;

@@ -580,11 +580,12 @@ int run_plan(const hvs_coeff_job* jobs, const hvs_coeff_grad* grads, int num_job
              size_t workspace_bytes, cudaStream_t stream, bool backward, bool size_only, size_t* size_out) {
     if (num_jobs < 0 || iters < 0 || (num_jobs > 0 && !jobs)) return HVS_ERR_BAD_ARG;
     if (num_jobs == 0) { if (size_out) *size_out = 256; return HVS_OK; }
-    // as many CTAs as the work can feed (>= 8192 matrix elements each): a single 256 x 256 layer (the per-layer backward of
-    // a training step) runs on 8 CTAs whose grid barrier is several times cheaper than one across all 148 SMs
+    // as many CTAs as the work can feed (>= 2048 matrix elements each): a single 256 x 256 layer (the per-layer backward of a
+    // training step) runs on 32 CTAs, whose grid barrier is cheaper than one across all 148 SMs.  (8192 per CTA was tried:
+    // the barriers got cheaper still but the first / last pass -- exp, the rank-2n update -- serialised: 233 -> 390 us.)
     double elems = 0;
     for (int b = 0; b < num_jobs; ++b) elems += (double)jobs[b].D * jobs[b].D;
-    int grid = (int)(elems / 8192.0);
+    int grid = (int)(elems / 2048.0);
     if (grid < 1) grid = 1;
     if (grid > sm_count()) grid = sm_count();
     HostPlan hp;
