@@ -19,6 +19,8 @@
 // h1 chunks are 64 wide (one K block of the next GEMM): with 128-wide chunks their two buffers took 64 KB and left a
 // two-slot weight ring at D = 64, which bound the chunk loop by TMA round trips (34 k cycles per tile).
 // The h1 chunk loop is software-pipelined: the MMAs of chunk j+1 run while the epilogue warps apply GELU to chunk j.
+// Tried and dropped: 64-column h1 chunks (frees 32 KB for a third / fourth weight slot) -- 5 % SLOWER (D = 64: 6.20 -> 6.56 ms
+// per 6.5 M tokens): the tile time is set by the chain of ~10 MMA <-> epilogue hand-offs, not by the weight ring.
 #include <cuda_bf16.h>
 #include <math.h>
 
