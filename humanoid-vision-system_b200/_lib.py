@@ -18,6 +18,7 @@ HVS_MHC_SAVED_STRIDE = 28
 HVS_DTYPE_F32, HVS_DTYPE_F16, HVS_DTYPE_BF16 = 0, 1, 2
 HVS_NMS_AGNOSTIC, HVS_NMS_CLASS_AWARE, HVS_NMS_BOXES_XYXY = 0, 1, 16
 HVS_GEMM_EPI_NONE, HVS_GEMM_EPI_BIAS_GELU, HVS_GEMM_EPI_LAYERNORM = 0, 1, 2
+HVS_GEMM_EPI_BIAS_GELU_SAVE, HVS_GEMM_EPI_DGELU = 3, 4
 
 
 class CoeffJob(ctypes.Structure):
@@ -27,6 +28,20 @@ class CoeffJob(ctypes.Structure):
                 ("h_pre_t", c_void_p), ("h_post_t", c_void_p), ("h_res_t", c_void_p),
                 ("uv_history", c_void_p), ("convergence", c_void_p),
                 ("D", c_int32), ("H", c_int32), ("Dp", c_int32), ("reserved", c_int32)]
+
+
+class GemmArgs(ctypes.Structure):
+    """struct hvs_gemm_args."""
+    _fields_ = [("a0", c_void_p), ("lda0", c_int64), ("b0", c_void_p), ("ldb0", c_int64), ("K0", c_int),
+                ("a1", c_void_p), ("lda1", c_int64), ("b1", c_void_p), ("ldb1", c_int64), ("K1", c_int),
+                ("a_mn_major", c_int), ("b_mn_major", c_int), ("bias", c_void_p),
+                ("ln_w", c_void_p), ("ln_b", c_void_p), ("ln_eps", c_float),
+                ("aux", c_void_p), ("ld_aux", c_int64),
+                ("out", c_void_p), ("out_dtype", c_int), ("ldo", c_int64),
+                ("out2", c_void_p), ("ldo2", c_int64),
+                ("M", c_int64), ("N", c_int), ("epilogue", c_int),
+                ("dropout_p", c_float), ("dropout_seed", c_uint32),
+                ("split_k", c_int), ("split_stride", c_int64)]
 
 
 class GradTensor(ctypes.Structure):
@@ -78,6 +93,11 @@ _SIGNATURES = {
                                           c_void_p]),
     "hvs_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p,
                               c_void_p, c_float, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "hvs_gemm_bf16_ex": (c_int, [POINTER(GemmArgs), c_void_p]),
+    "hvs_gemm_choose_split": (c_int, [c_int64, c_int, c_int64]),
+    "hvs_reduce_partials": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "hvs_colsum_bf16_workspace": (c_size_t, [c_int64, c_int]),
+    "hvs_colsum_bf16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hvs_profile_kernel_ms": (c_int, [POINTER(c_float)]),
     "hvs_head_decode_fused": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_int, c_void_p]),

@@ -11,6 +11,18 @@
 // K-major tiles of 64 K-elements, 4-6 stages.
 // LayerNorm needs the whole output row: with N <= 256 the tile spans it; with 256 < N <= 512 the two halves of the
 // row go to the two accumulator buffers and the epilogue normalises across both (no overlap for that GEMM).
+//
+// Training (hvs_gemm_bf16_ex) runs the SAME kernel for the module's forward and for all ten backward GEMMs:
+//   * either operand may be MN-major, i.e. given as its transpose in place ([K, rows] row-major): TMA lands 64(K) x 64
+//     boxes as 128-byte-swizzled MN-major atoms (8 K-rows x 128 B) and the descriptors say so.  Data gradients
+//     dX = dY W read W [out, in] as it lies (B MN-major); weight gradients dW = dY^T X contract over the TOKENS with
+//     both activations [T, features] as they lie (A and B MN-major).  No transposed copies anywhere.
+//   * split-K for the weight gradients (tiny outputs, K = millions of tokens): fp32 partials per split, summed in a
+//     fixed order by hvs_reduce_partials (bitwise reproducible).
+//   * EPI_BIAS_GELU_SAVE  out2 = z = bf16(acc + b), out = dropout(GELU(z)): what the backward needs, one pass.
+//   * EPI_DGELU           out = acc * GELU'(z[m, n]) * dropout mask / (1 - p): the activation backward in the
+//                         data-gradient GEMM's epilogue.  The mask is a counter-based hash of (seed, row, column pair):
+//                         recomputed, never stored.
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -46,8 +58,21 @@ struct GemmParams {
     int epilogue;
     int out_f32;
     float ln_eps;
-    int num_tiles;          // m_tiles * n_outer
+    int num_tiles;          // m_tiles * n_outer * splits
     int n_outer;            // N / (BN * n_sub)
+    // training extensions (hvs_gemm_bf16_ex)
+    int a_mn, b_mn;         // operand given MN-major (its transpose in place)
+    int b_bytes;            // B bytes per stage
+    int splits;             // split-K: partial s covers K blocks [s * kb_split, (s + 1) * kb_split)
+    int kb_split;
+    int64_t split_stride;   // elements between the partial outputs
+    const __nv_bfloat16* aux;   // EPI_DGELU: pre-activation z [M, N]
+    int64_t ld_aux;
+    __nv_bfloat16* out2;    // EPI_BIAS_GELU_SAVE: pre-activation z [M, N]
+    int64_t ldo2;
+    uint32_t drop_thr;      // dropout: element dropped iff its 16 hash bits < drop_thr (0 = no dropout)
+    float drop_scale;       // 1 / (1 - p)
+    uint32_t seed;
     // HVS_GEMM_EPI_YOLO_DECODE (fused prediction conv + decode): outputs in hvs_yolo_decode's layout
     const float* anchor_wh; // [3, 2]
     float* dec_boxes;       // [B, 3, H, W, 4]
@@ -95,7 +120,45 @@ __device__ __forceinline__ uint32_t gelu2_bf16(float x0, float x1) {
     upk2(fma2(hx, pk2(e0, e1), hx), g0, g1);
     return pack_bf16(g0, g1);
 }
+__device__ __forceinline__ uint4 ld_global_nc_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+// GELU'(x) = Phi(x) + x phi(x) with the same erf approximation (absolute error <= 1e-6), two values at once
+__device__ __forceinline__ void gelu_grad2(float x0, float x1, float& d0, float& d1) {
+    const u64 x = pk2(x0, x1);
+    const u64 z = mul2(x, pk2(0.70710678118654752440f, 0.70710678118654752440f));
+    float z0, z1;
+    upk2(z, z0, z1);
+    const u64 az = pk2(fabsf(z0), fabsf(z1));
+    u64 t = fma2(az, pk2(0.0000430638f, 0.0000430638f), pk2(0.0002765672f, 0.0002765672f));
+    t = fma2(az, t, pk2(0.0001520143f, 0.0001520143f));
+    t = fma2(az, t, pk2(0.0092705272f, 0.0092705272f));
+    t = fma2(az, t, pk2(0.0422820123f, 0.0422820123f));
+    t = fma2(az, t, pk2(0.0705230784f, 0.0705230784f));
+    t = fma2(az, t, pk2(1.0f, 1.0f));
+    t = mul2(t, t); t = mul2(t, t); t = mul2(t, t); t = mul2(t, t);
+    float t0, t1;
+    upk2(t, t0, t1);
+    const float e0 = copysignf(1.0f - rcp_approx(t0), z0), e1 = copysignf(1.0f - rcp_approx(t1), z1);
+    // phi(x) = exp(-x^2 / 2) / sqrt(2 pi) = 2^(-x^2 * log2(e) / 2) * 0.3989...
+    float q0, q1;
+    upk2(mul2(mul2(x, x), pk2(-0.72134752044448170368f, -0.72134752044448170368f)), q0, q1);
+    float p0, p1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(q0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(q1));
+    const u64 cdf = fma2(pk2(e0, e1), pk2(0.5f, 0.5f), pk2(0.5f, 0.5f));
+    upk2(fma2(mul2(x, pk2(0.3989422804014327f, 0.3989422804014327f)), pk2(p0, p1), cdf), d0, d1);
+}
+// dropout keep decisions of the column pair (n, n + 1), n even, of row m: 16 hash bits each (lowbias32 finaliser)
+__device__ __forceinline__ uint32_t drop_hash(uint32_t seed, uint32_t row, uint32_t colpair) {
+    uint32_t h = (row * 0x9E3779B1u) ^ (colpair * 0x85EBCA77u) ^ seed;
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return h;
+}
 
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -116,8 +179,9 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int stage_bytes = kABytes + p.BN * 128;
+    const int stage_bytes = kABytes + p.b_bytes;
     const int num_kb = p.kb0 + p.kb1;
+    const int tiles_mn = p.num_tiles / p.splits;         // a tile index = split * tiles_mn + (m_blk * n_outer + n_out)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a0);
@@ -139,16 +203,28 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / p.n_outer, n_out = tile % p.n_outer;
+                const int split = tile / tiles_mn, mn = tile - split * tiles_mn;
+                const int m_blk = mn / p.n_outer, n_out = mn % p.n_outer;
+                const int kb_lo = split * p.kb_split, kb_hi = min(num_kb, kb_lo + p.kb_split);
                 for (int sub = 0; sub < p.n_sub; ++sub) {
                     const int n_row0 = (n_out * p.n_sub + sub) * p.BN;
-                    for (int kb = 0; kb < num_kb; ++kb) {
+                    for (int kb = kb_lo; kb < kb_hi; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1u);
                         uint8_t* sa = smem + (size_t)stage * stage_bytes;
                         mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
                         if (kb < p.kb0) {
-                            tma_load_2d(sa, &tm_a0, &full[stage], kb * kBK, m_blk * kBM);
-                            tma_load_2d(sa + kABytes, &tm_b0, &full[stage], kb * kBK, n_row0);
+                            if (!p.a_mn) {
+                                tma_load_2d(sa, &tm_a0, &full[stage], kb * kBK, m_blk * kBM);
+                            } else {                                 // [K, M] in memory: two 64(K) x 64(M) boxes = MN-major atoms
+                                tma_load_2d(sa, &tm_a0, &full[stage], m_blk * kBM, kb * kBK);
+                                tma_load_2d(sa + 8192, &tm_a0, &full[stage], m_blk * kBM + 64, kb * kBK);
+                            }
+                            if (!p.b_mn) {
+                                tma_load_2d(sa + kABytes, &tm_b0, &full[stage], kb * kBK, n_row0);
+                            } else {
+                                for (int i = 0; i * 8192 < p.b_bytes; ++i)
+                                    tma_load_2d(sa + kABytes + i * 8192, &tm_b0, &full[stage], n_row0 + 64 * i, kb * kBK);
+                            }
                         } else {
                             tma_load_2d(sa, &tm_a1, &full[stage], (kb - p.kb0) * kBK, m_blk * kBM);
                             tma_load_2d(sa + kABytes, &tm_b1, &full[stage], (kb - p.kb0) * kBK, n_row0);
@@ -161,25 +237,31 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kBM, p.BN, 0, 0);
+            const uint32_t idesc = umma_idesc_bf16(kBM, p.BN, p.a_mn, p.b_mn);
+            // K-major: 8-row groups 1 KB apart, a K = 16 step is +32 B.  MN-major: 64-element atoms along M / N 8 KB apart
+            // (one TMA box each), the next 8 K-rows 1 KB on, a K = 16 step is two of those = +2 KB.
+            const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+            const uint64_t a_step = p.a_mn ? 128u : 2u, b_step = p.b_mn ? 128u : 2u;
             int stage = 0;
             uint32_t phase = 0;
             uint32_t acc_it = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int split = tile / tiles_mn;
+                const int kb_lo = split * p.kb_split, kb_hi = min(num_kb, kb_lo + p.kb_split);
                 for (int sub = 0; sub < p.n_sub; ++sub, ++acc_it) {
                     const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
                     mbar_wait(&acc_empty[buf], aph ^ 1u);            // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * kMaxBN;
-                    for (int kb = 0; kb < num_kb; ++kb) {
+                    for (int kb = kb_lo; kb < kb_hi; ++kb) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t sa = base + (uint32_t)(stage * stage_bytes);
-                        const uint64_t adesc = umma_smem_desc(sa, 16, 1024, kUmmaLayoutSw128);
-                        const uint64_t bdesc = umma_smem_desc(sa + kABytes, 16, 1024, kUmmaLayoutSw128);
+                        const uint64_t adesc = umma_smem_desc(sa, a_lbo, 1024, kUmmaLayoutSw128);
+                        const uint64_t bdesc = umma_smem_desc(sa + kABytes, b_lbo, 1024, kUmmaLayoutSw128);
 #pragma unroll
-                        for (int k = 0; k < kBK / 16; ++k)           // +32 bytes (16 bf16) along K per step
-                            umma_bf16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < kBK / 16; ++k)
+                            umma_bf16_ss(d_tmem, adesc + a_step * (uint64_t)k, bdesc + b_step * (uint64_t)k, idesc, (uint32_t)((kb > kb_lo) | (k != 0)));
                         umma_commit(&empty[stage]);                  // stage reusable when these MMAs have read it
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
@@ -195,9 +277,11 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         uint32_t acc_it = 0;
         const int chunks = p.BN >> 5;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / p.n_outer, n_out = tile % p.n_outer;
+            const int split = tile / tiles_mn, mn = tile - split * tiles_mn;
+            const int m_blk = mn / p.n_outer, n_out = mn % p.n_outer;
             const int64_t row = (int64_t)m_blk * kBM + q * 32 + lane;
             const bool row_ok = row < p.M;
+            const int64_t out_off = (int64_t)split * p.split_stride;   // split-K partial
             const uint32_t it0 = acc_it;
             for (int sub = 0; sub < p.n_sub; ++sub) {
                 const uint32_t it = it0 + (uint32_t)sub;
@@ -290,6 +374,65 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     tmem_ld32(t0 + (uint32_t)(c * 32), v);
                     tmem_wait_ld();
                     const int nc = n0 + c * 32;
+                    if (p.epilogue == HVS_GEMM_EPI_BIAS_GELU_SAVE) {
+                        // training forward: z = bf16(acc + b) -> out2, dropout(GELU(z)) -> out (the autocast convention:
+                        // the Linear's bf16 output is what GELU sees and what the backward differentiates at)
+                        uint32_t zz[16], o[16];
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bb = __ldg(b4 + j);
+                            zz[2 * j] = pack_bf16(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+                            zz[2 * j + 1] = pack_bf16(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (p.drop_thr == 0u) {
+                                o[j] = gelu2_bf16(bf16lo(zz[j]), bf16hi(zz[j]));
+                            } else {
+                                const uint32_t h = drop_hash(p.seed, (uint32_t)row, (uint32_t)(nc >> 1) + j);
+                                const float k0 = (h & 0xffffu) < p.drop_thr ? 0.f : p.drop_scale, k1 = (h >> 16) < p.drop_thr ? 0.f : p.drop_scale;
+                                const uint32_t g = gelu2_bf16(bf16lo(zz[j]), bf16hi(zz[j]));
+                                o[j] = pack_bf16(bf16lo(g) * k0, bf16hi(g) * k1);
+                            }
+                        }
+                        if (row_ok) {
+                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + nc;
+                            __nv_bfloat16* zp = p.out2 + row * p.ldo2 + nc;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                st_global_v4(op + 2 * j, o[j], o[j + 1], o[j + 2], o[j + 3]);
+                                st_global_v4(zp + 2 * j, zz[j], zz[j + 1], zz[j + 2], zz[j + 3]);
+                            }
+                        }
+                        continue;
+                    }
+                    if (p.epilogue == HVS_GEMM_EPI_DGELU) {
+                        // training backward: d z = d a * mask / (1 - p) * GELU'(z), z read back as the forward stored it
+                        uint32_t o[16];
+                        uint4 zq[4];
+                        const __nv_bfloat16* zp = p.aux + (row_ok ? row : 0) * p.ld_aux + nc;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) zq[j] = ld_global_nc_v4(zp + 8 * j);
+                        const uint32_t* zz = reinterpret_cast<const uint32_t*>(zq);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float d0, d1;
+                            gelu_grad2(bf16lo(zz[j]), bf16hi(zz[j]), d0, d1);
+                            if (p.drop_thr != 0u) {
+                                const uint32_t h = drop_hash(p.seed, (uint32_t)row, (uint32_t)(nc >> 1) + j);
+                                d0 *= (h & 0xffffu) < p.drop_thr ? 0.f : p.drop_scale;
+                                d1 *= (h >> 16) < p.drop_thr ? 0.f : p.drop_scale;
+                            }
+                            o[j] = pack_bf16(__uint_as_float(v[2 * j]) * d0, __uint_as_float(v[2 * j + 1]) * d1);
+                        }
+                        if (row_ok) {
+                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + nc;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) st_global_v4(op + 2 * j, o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        }
+                        continue;
+                    }
                     if (p.epilogue == HVS_GEMM_EPI_BIAS_GELU && !p.out_f32) {
                         // the hot epilogue (two of the module's four GEMMs, 88 % of its FLOPs): bias + GELU + bf16 pack, packed
                         uint32_t o[16];
@@ -320,7 +463,7 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     }
                     if (row_ok) {
                         if (p.out_f32) {
-                            float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + nc;
+                            float* o = reinterpret_cast<float*>(p.out) + out_off + row * p.ldo + nc;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) st_global_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
                         } else {
@@ -351,55 +494,152 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
 }  // namespace
 }  // namespace hvs
 
-extern "C" int hvs_gemm_bf16(const void* a0, int64_t lda0, const void* b0, int K0, const void* a1, int64_t lda1,
-                             const void* b1, int K1, const float* bias, const float* ln_w, const float* ln_b, float ln_eps,
-                             void* out, int out_dtype, int64_t ldo, int64_t M, int N, int epilogue, void* stream_) {
-    using namespace hvs;
-    cudaStream_t stream = (cudaStream_t)stream_;
+namespace hvs {
+namespace {
+
+// fixed-order sum of split-K partials: out[i] = sum_s part[s * stride + i]
+__global__ void reduce_partials_kernel(const float4* __restrict__ part, int splits, int64_t stride4, int64_t n4, float4* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 a = part[i];
+        for (int s = 1; s < splits; ++s) {
+            const float4 b = part[(int64_t)s * stride4 + i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        out[i] = a;
+    }
+}
+
+// column sums of a bf16 matrix (bias gradients): stage 1, one CTA per block of rows, 8 columns per thread
+constexpr int kColsumRows = 512;
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int64_t rows, int cols,
+                                                             float* __restrict__ part) {
+    const int groups = cols >> 3;                          // 8-column groups
+    const int lanes = groups < 256 ? groups : 256;         // threads along the columns
+    const int rsteps = 256 / lanes;                        // rows handled concurrently
+    const int cg = threadIdx.x % lanes, rg = threadIdx.x / lanes;
+    __shared__ float red[256 * 8];
+    const int64_t r0 = (int64_t)blockIdx.x * kColsumRows;
+    const int64_t r1 = r0 + kColsumRows < rows ? r0 + kColsumRows : rows;
+    for (int g0 = 0; g0 < groups; g0 += lanes) {
+        const int g = g0 + cg;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (g < groups && rg < rsteps)
+            for (int64_t r = r0 + rg; r < r1; r += rsteps) {
+                const uint4 v = *reinterpret_cast<const uint4*>(x + r * ld + 8 * g);
+                acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x); acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
+                acc[4] += bf16lo(v.z); acc[5] += bf16hi(v.z); acc[6] += bf16lo(v.w); acc[7] += bf16hi(v.w);
+            }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[j];
+        __syncthreads();
+        if (rg == 0 && g < groups) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = red[cg * 8 + j];
+            for (int k = 1; k < rsteps; ++k)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] += red[(k * lanes + cg) * 8 + j];
+            float* dst = part + (int64_t)blockIdx.x * cols + 8 * g;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = o[j];
+        }
+        __syncthreads();
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float a = 0.f;
+    for (int i = 0; i < nparts; ++i) a += part[(int64_t)i * cols + c];
+    out[c] = a;
+}
+
+int launch_gemm(const hvs_gemm_args& g, int timer_slot, cudaStream_t stream) {
+    const int64_t M = g.M;
+    const int N = g.N, K0 = g.K0, K1 = g.K1;
     if (M < 0 || N <= 0 || K0 <= 0 || K1 < 0) return HVS_ERR_BAD_ARG;
     if (M == 0) return HVS_OK;
-    if (!a0 || !b0 || !out || (K1 > 0 && (!a1 || !b1))) return HVS_ERR_BAD_ARG;
+    if (!g.a0 || !g.b0 || !g.out || (K1 > 0 && (!g.a1 || !g.b1))) return HVS_ERR_BAD_ARG;
+    const int a_mn = g.a_mn_major ? 1 : 0, b_mn = g.b_mn_major ? 1 : 0;
+    int splits = g.split_k > 1 ? g.split_k : 1;
     // K need not be a multiple of the 64-element stage: the tensor maps carry the true extents and TMA zero-fills the
     // rest of the box on both operands (so a D = 32 layer needs no padded copies); rows must be 16-byte multiples
-    if (K0 % 8 || K1 % 8 || N % 32 || lda0 < K0 || (K1 > 0 && lda1 < K1) || ldo < N) return HVS_ERR_UNSUPPORTED;
-    if (lda0 % 8 || (K1 > 0 && lda1 % 8) || ldo % 8) return HVS_ERR_ALIGNMENT;
-    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return HVS_ERR_ALIGNMENT;
-    if (M >= ((int64_t)1 << 31)) return HVS_ERR_UNSUPPORTED;
-    if (out_dtype != HVS_DTYPE_F32 && out_dtype != HVS_DTYPE_BF16) return HVS_ERR_UNSUPPORTED;
-    if ((reinterpret_cast<uintptr_t>(a0) | reinterpret_cast<uintptr_t>(b0) | reinterpret_cast<uintptr_t>(a1) |
-         reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(out)) & 15)
+    // (an MN-major operand has K as its ROW count: any K)
+    if (((!a_mn || !b_mn) && K0 % 8) || K1 % 8 || N % 32) return HVS_ERR_UNSUPPORTED;
+    if (K1 > 0 && (a_mn || b_mn || splits > 1)) return HVS_ERR_UNSUPPORTED;
+    if (a_mn ? (M % 8 || g.lda0 < M) : (g.lda0 < K0)) return HVS_ERR_UNSUPPORTED;
+    if (b_mn ? (g.ldb0 < N) : (g.ldb0 < K0)) return HVS_ERR_UNSUPPORTED;
+    if ((K1 > 0 && (g.lda1 < K1 || g.ldb1 < K1)) || g.ldo < N) return HVS_ERR_UNSUPPORTED;
+    if (g.lda0 % 8 || g.ldb0 % 8 || (K1 > 0 && (g.lda1 % 8 || g.ldb1 % 8)) || g.ldo % 8) return HVS_ERR_ALIGNMENT;
+    if (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15)) return HVS_ERR_ALIGNMENT;
+    if (M >= ((int64_t)1 << 31) || (int64_t)K0 >= ((int64_t)1 << 31)) return HVS_ERR_UNSUPPORTED;
+    if (g.out_dtype != HVS_DTYPE_F32 && g.out_dtype != HVS_DTYPE_BF16) return HVS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(g.a0) | reinterpret_cast<uintptr_t>(g.b0) | reinterpret_cast<uintptr_t>(g.a1) |
+         reinterpret_cast<uintptr_t>(g.b1) | reinterpret_cast<uintptr_t>(g.out) | reinterpret_cast<uintptr_t>(g.out2) |
+         reinterpret_cast<uintptr_t>(g.aux)) & 15)
         return HVS_ERR_ALIGNMENT;
     GemmParams p{};
-    p.bias = bias; p.ln_w = ln_w; p.ln_b = ln_b; p.out = out; p.ldo = ldo; p.M = M; p.N = N;
+    p.bias = g.bias; p.ln_w = g.ln_w; p.ln_b = g.ln_b; p.out = g.out; p.ldo = g.ldo; p.M = M; p.N = N;
     p.BN = N >= kMaxBN ? kMaxBN : N;
     if (N % p.BN) return HVS_ERR_UNSUPPORTED;
     p.n_sub = 1;
-    p.epilogue = epilogue;
-    if (epilogue == HVS_GEMM_EPI_LAYERNORM) {
-        if (!ln_w || !ln_b || N > 2 * kMaxBN) return N > 2 * kMaxBN ? HVS_ERR_UNSUPPORTED : HVS_ERR_BAD_ARG;
-        p.n_sub = N / p.BN;
-    } else if (epilogue == HVS_GEMM_EPI_BIAS_GELU) {
-        if (!bias) return HVS_ERR_BAD_ARG;
-    } else if (epilogue != HVS_GEMM_EPI_NONE) {
-        return HVS_ERR_UNSUPPORTED;
+    p.epilogue = g.epilogue;
+    p.out_f32 = g.out_dtype == HVS_DTYPE_F32;
+    switch (g.epilogue) {
+        case HVS_GEMM_EPI_NONE: break;
+        case HVS_GEMM_EPI_LAYERNORM:
+            if (!g.ln_w || !g.ln_b) return HVS_ERR_BAD_ARG;
+            if (N > 2 * kMaxBN || splits > 1) return HVS_ERR_UNSUPPORTED;
+            p.n_sub = N / p.BN;
+            break;
+        case HVS_GEMM_EPI_BIAS_GELU:
+            if (!g.bias) return HVS_ERR_BAD_ARG;
+            if (splits > 1) return HVS_ERR_UNSUPPORTED;
+            break;
+        case HVS_GEMM_EPI_BIAS_GELU_SAVE:
+            if (!g.bias || !g.out2) return HVS_ERR_BAD_ARG;
+            if (p.out_f32 || splits > 1 || g.ldo2 < N || g.ldo2 % 8) return HVS_ERR_UNSUPPORTED;
+            break;
+        case HVS_GEMM_EPI_DGELU:
+            if (!g.aux) return HVS_ERR_BAD_ARG;
+            if (p.out_f32 || splits > 1 || g.ld_aux < N || g.ld_aux % 8) return HVS_ERR_UNSUPPORTED;
+            break;
+        default: return HVS_ERR_UNSUPPORTED;
     }
+    if (splits > 1 && (!p.out_f32 || g.bias)) return HVS_ERR_UNSUPPORTED;       // partials are plain fp32 accumulators
+    if (!(g.dropout_p >= 0.f && g.dropout_p < 1.f)) return HVS_ERR_BAD_ARG;
+    p.drop_thr = (uint32_t)(g.dropout_p * 65536.0f + 0.5f);
+    p.drop_scale = p.drop_thr ? 65536.0f / (65536.0f - (float)p.drop_thr) : 1.0f;   // 1 / (1 - p) for the p actually realised
+    p.seed = g.dropout_seed;
+    p.aux = reinterpret_cast<const __nv_bfloat16*>(g.aux); p.ld_aux = g.ld_aux;
+    p.out2 = reinterpret_cast<__nv_bfloat16*>(g.out2); p.ldo2 = g.ldo2;
+    p.a_mn = a_mn; p.b_mn = b_mn;
+    p.b_bytes = b_mn ? ((p.BN + 63) / 64) * 8192 : p.BN * 128;
     p.kb0 = (K0 + kBK - 1) / kBK; p.kb1 = (K1 + kBK - 1) / kBK;
-    p.stages = kStageBudget / (kABytes + p.BN * 128);
+    const int num_kb = p.kb0 + p.kb1;
+    if (splits > num_kb) splits = num_kb;
+    p.kb_split = (num_kb + splits - 1) / splits;
+    splits = (num_kb + p.kb_split - 1) / p.kb_split;            // every split owns at least one K block
+    p.splits = splits;
+    p.split_stride = g.split_stride > 0 ? g.split_stride : M * g.ldo;
+    p.stages = kStageBudget / (kABytes + p.b_bytes);
     if (p.stages > kMaxStages) p.stages = kMaxStages;
-    p.out_f32 = out_dtype == HVS_DTYPE_F32;
-    p.ln_eps = ln_eps;
+    p.ln_eps = g.ln_eps;
     const int64_t m_tiles = (M + kBM - 1) / kBM;
     p.n_outer = N / (p.BN * p.n_sub);
-    p.num_tiles = (int)(m_tiles * p.n_outer);
+    if (m_tiles * p.n_outer * splits >= ((int64_t)1 << 31)) return HVS_ERR_UNSUPPORTED;
+    p.num_tiles = (int)(m_tiles * p.n_outer) * splits;
     CUtensorMap ta0, tb0, ta1, tb1;
-    int rc = make_tmap_bf16_2d_ld(&ta0, a0, (uint64_t)M, (uint64_t)K0, (uint64_t)lda0, kBM);
+    int rc = a_mn ? make_tmap_bf16_2d_ld(&ta0, g.a0, (uint64_t)K0, (uint64_t)M, (uint64_t)g.lda0, kBK)
+                  : make_tmap_bf16_2d_ld(&ta0, g.a0, (uint64_t)M, (uint64_t)K0, (uint64_t)g.lda0, kBM);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d_ld(&tb0, b0, (uint64_t)N, (uint64_t)K0, (uint64_t)K0, (uint32_t)p.BN);
+    rc = b_mn ? make_tmap_bf16_2d_ld(&tb0, g.b0, (uint64_t)K0, (uint64_t)N, (uint64_t)g.ldb0, kBK)
+              : make_tmap_bf16_2d_ld(&tb0, g.b0, (uint64_t)N, (uint64_t)K0, (uint64_t)g.ldb0, (uint32_t)p.BN);
     if (rc) return rc;
     if (K1 > 0) {
-        rc = make_tmap_bf16_2d_ld(&ta1, a1, (uint64_t)M, (uint64_t)K1, (uint64_t)lda1, kBM);
+        rc = make_tmap_bf16_2d_ld(&ta1, g.a1, (uint64_t)M, (uint64_t)K1, (uint64_t)g.lda1, kBM);
         if (rc) return rc;
-        rc = make_tmap_bf16_2d_ld(&tb1, b1, (uint64_t)N, (uint64_t)K1, (uint64_t)K1, (uint32_t)p.BN);
+        rc = make_tmap_bf16_2d_ld(&tb1, g.b1, (uint64_t)N, (uint64_t)K1, (uint64_t)g.ldb1, (uint32_t)p.BN);
         if (rc) return rc;
     } else {
         ta1 = ta0; tb1 = tb0;
@@ -407,10 +647,87 @@ extern "C" int hvs_gemm_bf16(const void* a0, int64_t lda0, const void* b0, int K
     HVS_SET_MAX_SMEM(k2_gemm_kernel, kSmemBytes);
     const int sms = sm_count();
     const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-    timer_begin(4, stream);
+    timer_begin(timer_slot, stream);
     k2_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta0, tb0, ta1, tb1, p);
-    timer_end(4, stream);
+    timer_end(timer_slot, stream);
     count_launch();
+    return launch_status();
+}
+
+}  // namespace
+}  // namespace hvs
+
+extern "C" int hvs_gemm_bf16(const void* a0, int64_t lda0, const void* b0, int K0, const void* a1, int64_t lda1,
+                             const void* b1, int K1, const float* bias, const float* ln_w, const float* ln_b, float ln_eps,
+                             void* out, int out_dtype, int64_t ldo, int64_t M, int N, int epilogue, void* stream_) {
+    if (epilogue != HVS_GEMM_EPI_NONE && epilogue != HVS_GEMM_EPI_BIAS_GELU && epilogue != HVS_GEMM_EPI_LAYERNORM)
+        return HVS_ERR_UNSUPPORTED;
+    hvs_gemm_args g{};
+    g.a0 = a0; g.lda0 = lda0; g.b0 = b0; g.ldb0 = K0; g.K0 = K0;
+    g.a1 = a1; g.lda1 = lda1; g.b1 = b1; g.ldb1 = K1; g.K1 = K1;
+    g.bias = bias; g.ln_w = ln_w; g.ln_b = ln_b; g.ln_eps = ln_eps;
+    g.out = out; g.out_dtype = out_dtype; g.ldo = ldo; g.M = M; g.N = N; g.epilogue = epilogue;
+    return hvs::launch_gemm(g, 4, (cudaStream_t)stream_);
+}
+
+extern "C" int hvs_gemm_bf16_ex(const hvs_gemm_args* args, void* stream_) {
+    if (!args) return HVS_ERR_BAD_ARG;
+    return hvs::launch_gemm(*args, 6, (cudaStream_t)stream_);
+}
+
+// Split count for a weight-gradient GEMM out[M, N] = A^T B over K tokens: enough tiles to fill the SMs, every split at
+// least 8 K blocks (512 tokens) long.
+extern "C" int hvs_gemm_choose_split(int64_t M, int N, int64_t K) {
+    using namespace hvs;
+    if (M <= 0 || N <= 0 || K <= 0) return 1;
+    const int bn = N >= kMaxBN ? kMaxBN : N;
+    const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
+    const int64_t num_kb = (K + kBK - 1) / kBK;
+    int64_t s = (2 * (int64_t)sm_count() + tiles - 1) / tiles;       // about two waves of tiles
+    if (s > num_kb / 8) s = num_kb / 8;
+    if (s < 1) s = 1;
+    if (s > 256) s = 256;
+    const int64_t kb_split = (num_kb + s - 1) / s;
+    return (int)((num_kb + kb_split - 1) / kb_split);
+}
+
+extern "C" int hvs_reduce_partials(const float* partials, int splits, int64_t split_stride, int64_t numel, float* out, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (splits < 1 || numel < 0 || split_stride < numel) return HVS_ERR_BAD_ARG;
+    if (numel == 0) return HVS_OK;
+    if (!partials || !out) return HVS_ERR_BAD_ARG;
+    if (numel % 4 || split_stride % 4) return HVS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(out)) & 15) return HVS_ERR_ALIGNMENT;
+    const int64_t n4 = numel / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    reduce_partials_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(partials), splits, split_stride / 4, n4,
+                                                            reinterpret_cast<float4*>(out));
+    count_launch();
+    return launch_status();
+}
+
+extern "C" size_t hvs_colsum_bf16_workspace(int64_t rows, int cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    return (size_t)((rows + hvs::kColsumRows - 1) / hvs::kColsumRows) * (size_t)cols * 4;
+}
+
+extern "C" int hvs_colsum_bf16(const void* x, int64_t ld, int64_t rows, int cols, float* out, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (rows < 0 || cols <= 0 || !out) return HVS_ERR_BAD_ARG;
+    if (cols % 8 || ld % 8 || ld < cols) return HVS_ERR_UNSUPPORTED;
+    if (rows == 0) { HVS_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)cols * 4, stream)); return HVS_OK; }
+    if (!x || !workspace || (reinterpret_cast<uintptr_t>(x) & 15)) return HVS_ERR_BAD_ARG;
+    if (workspace_bytes < hvs_colsum_bf16_workspace(rows, cols)) return HVS_ERR_WORKSPACE;
+    const int64_t nparts = (rows + kColsumRows - 1) / kColsumRows;
+    if (nparts >= ((int64_t)1 << 31)) return HVS_ERR_UNSUPPORTED;
+    colsum_partial_kernel<<<(int)nparts, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, cols,
+                                                           reinterpret_cast<float*>(workspace));
+    colsum_final_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int)nparts, cols, out);
+    count_launch(2);
     return launch_status();
 }
 
@@ -434,6 +751,7 @@ extern "C" int hvs_head_decode_fused(const void* tokens, int64_t ld_tokens, cons
     GemmParams p{};
     p.bias = bias256; p.M = M; p.N = 256; p.BN = 256; p.n_sub = 1; p.n_outer = 1;
     p.kb0 = (C_in + kBK - 1) / kBK; p.kb1 = 0;
+    p.splits = 1; p.kb_split = p.kb0; p.b_bytes = p.BN * 128;
     p.stages = kStageBudget / (kABytes + p.BN * 128);
     p.epilogue = kEpiYoloDecode;
     p.num_tiles = (int)((M + kBM - 1) / kBM);

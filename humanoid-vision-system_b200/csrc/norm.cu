@@ -347,6 +347,72 @@ bool launch_small_rows_bwd(const TI* x, const float* w, const TG* dy, TI* dx, fl
     }
 }
 
+// Wide rows (D = 1024, 1792: a few thousand tokens at most): a warp per row for dx and the row statistics, then column
+// sums over row chunks.  Same arithmetic and the same fixed-order partial layout as the small-row kernel.
+template <typename TI, typename TG>
+__global__ void __launch_bounds__(256)
+layernorm_wide_bwd_dx_kernel(const TI* __restrict__ x, const float* __restrict__ w, const TG* __restrict__ dy, TI* __restrict__ dx,
+                             float2* __restrict__ stats, int64_t rows, int dim, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    for (int64_t r = warp; r < rows; r += (int64_t)gridDim.x * 8) {
+        const TI* xr = x + r * dim;
+        const TG* gr = dy + r * dim;
+        float s = 0.f;
+        for (int j = lane; j < dim; j += 32) s += ldf(xr, j);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / (float)dim;
+        float q = 0.f;
+        for (int j = lane; j < dim; j += 32) { const float d = ldf(xr, j) - mean; q = fmaf(d, d, q); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q / (float)dim + eps);
+        float sg = 0.f, sgx = 0.f;
+        for (int j = lane; j < dim; j += 32) {
+            const float g = ldf(gr, j) * w[j], xh = (ldf(xr, j) - mean) * rstd;
+            sg += g;
+            sgx = fmaf(g, xh, sgx);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, o); sgx += __shfl_xor_sync(0xffffffffu, sgx, o); }
+        sg /= (float)dim; sgx /= (float)dim;
+        for (int j = lane; j < dim; j += 32) {
+            const float g = ldf(gr, j) * w[j], xh = (ldf(xr, j) - mean) * rstd;
+            stf(dx + r * dim, j, rstd * (g - sg - xh * sgx));
+        }
+        if (lane == 0) stats[r] = make_float2(mean, rstd);
+    }
+}
+template <typename TI, typename TG>
+__global__ void __launch_bounds__(128)
+layernorm_wide_bwd_dw_kernel(const TI* __restrict__ x, const TG* __restrict__ dy, const float2* __restrict__ stats, float* __restrict__ part,
+                             int64_t rows, int dim, int rows_per_part) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col >= dim) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_part;
+    const int64_t r1 = r0 + rows_per_part < rows ? r0 + rows_per_part : rows;
+    float aw = 0.f, ab = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+        const float2 st = stats[r];
+        const float g = ldf(dy, r * dim + col);
+        aw = fmaf(g, (ldf(x, r * dim + col) - st.x) * st.y, aw);
+        ab += g;
+    }
+    part[((size_t)blockIdx.y * 2) * dim + col] = aw;
+    part[((size_t)blockIdx.y * 2 + 1) * dim + col] = ab;
+}
+constexpr int kWideRowsPerPart = 64;
+template <typename TI, typename TG>
+void launch_wide_bwd(const TI* x, const float* w, const TG* dy, TI* dx, float* part, float2* stats, int parts, int64_t rows, int dim,
+                     float eps, cudaStream_t stream) {
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+    layernorm_wide_bwd_dx_kernel<TI, TG><<<(int)blocks, 256, 0, stream>>>(x, w, dy, dx, stats, rows, dim, eps);
+    layernorm_wide_bwd_dw_kernel<TI, TG><<<dim3((dim + 127) / 128, parts), 128, 0, stream>>>(x, dy, stats, part, rows, dim, kWideRowsPerPart);
+}
+inline bool ln_small_dim(int dim) { return dim == 32 || dim == 64 || dim == 128 || dim == 256 || dim == 512; }
+
 inline int grid_for_rows(int64_t rows) {
     int64_t blocks = (rows + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -452,6 +518,10 @@ extern "C" int hvs_layernorm_fwd(const void* x, int x_dtype, const float* weight
 
 extern "C" size_t hvs_layernorm_bwd_workspace(int64_t rows, int dim) {
     if (rows < 0 || dim <= 0) return 0;
+    if (!hvs::ln_small_dim(dim)) {                      // wide rows: partials per 64-row chunk + (mean, rstd) per row
+        const int64_t parts = rows > 0 ? (rows + hvs::kWideRowsPerPart - 1) / hvs::kWideRowsPerPart : 1;
+        return (size_t)parts * 2 * dim * sizeof(float) + (size_t)(rows > 0 ? rows : 1) * sizeof(float2);
+    }
     int64_t blocks = (rows + 63) / 64;
     const int64_t cap = (int64_t)hvs::sm_count() * 4;
     if (blocks > cap) blocks = cap;
@@ -464,15 +534,30 @@ extern "C" int hvs_layernorm_bwd(const void* x, int x_dtype, const float* weight
     using namespace hvs;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (rows < 0 || dim <= 0 || !weight || !dweight || !dbias) return HVS_ERR_BAD_ARG;
-    if (dim != 32 && dim != 64 && dim != 128 && dim != 256 && dim != 512) return HVS_ERR_UNSUPPORTED;
+    if (dim % 8 || dim > 8192) return HVS_ERR_UNSUPPORTED;
     if (rows > 0 && (!x || !dy || !dx)) return HVS_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) return HVS_ERR_ALIGNMENT;
     const size_t need = hvs_layernorm_bwd_workspace(rows, dim);
-    if (!workspace || workspace_bytes < need) return HVS_ERR_WORKSPACE;
-    const int blocks = (int)(need / ((size_t)2 * dim * sizeof(float)));
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15)) return HVS_ERR_WORKSPACE;
     float* part = (float*)workspace;
-    bool ok = false;
     typedef __nv_bfloat16 bf;
+    if (!ln_small_dim(dim)) {
+        const int parts = rows > 0 ? (int)((rows + kWideRowsPerPart - 1) / kWideRowsPerPart) : 0;
+        if (parts > 65535) return HVS_ERR_UNSUPPORTED;                  // gridDim.y: rows <= 4.19 M (the model has 6400 at this width)
+        float2* stats = reinterpret_cast<float2*>(part + (size_t)(parts > 0 ? parts : 1) * 2 * dim);
+        if (rows > 0) {
+            if (x_dtype == HVS_DTYPE_F32 && dy_dtype == HVS_DTYPE_F32) launch_wide_bwd((const float*)x, weight, (const float*)dy, (float*)dx, part, stats, parts, rows, dim, eps, stream);
+            else if (x_dtype == HVS_DTYPE_BF16 && dy_dtype == HVS_DTYPE_F32) launch_wide_bwd((const bf*)x, weight, (const float*)dy, (bf*)dx, part, stats, parts, rows, dim, eps, stream);
+            else if (x_dtype == HVS_DTYPE_F32 && dy_dtype == HVS_DTYPE_BF16) launch_wide_bwd((const float*)x, weight, (const bf*)dy, (float*)dx, part, stats, parts, rows, dim, eps, stream);
+            else if (x_dtype == HVS_DTYPE_BF16 && dy_dtype == HVS_DTYPE_BF16) launch_wide_bwd((const bf*)x, weight, (const bf*)dy, (bf*)dx, part, stats, parts, rows, dim, eps, stream);
+            else return HVS_ERR_UNSUPPORTED;
+        }
+        ln_bwd_finalize_kernel<<<(dim + 127) / 128, 128, 0, stream>>>(part, dweight, dbias, parts, dim);
+        count_launch(3);
+        return launch_status();
+    }
+    const int blocks = (int)(need / ((size_t)2 * dim * sizeof(float)));
+    bool ok = false;
     if (x_dtype == HVS_DTYPE_F32 && dy_dtype == HVS_DTYPE_F32) ok = launch_small_rows_bwd((const float*)x, weight, (const float*)dy, (float*)dx, part, blocks, rows, dim, eps, stream);
     else if (x_dtype == HVS_DTYPE_BF16 && dy_dtype == HVS_DTYPE_F32) ok = launch_small_rows_bwd((const bf*)x, weight, (const float*)dy, (bf*)dx, part, blocks, rows, dim, eps, stream);
     else if (x_dtype == HVS_DTYPE_F32 && dy_dtype == HVS_DTYPE_BF16) ok = launch_small_rows_bwd((const float*)x, weight, (const bf*)dy, (float*)dx, part, blocks, rows, dim, eps, stream);

@@ -30,7 +30,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .detection import YOLODetectionHead
-from .mhc import ManifoldHyperConnection, RMSNorm, refresh_static_coefficients
+from .mhc import (ManifoldHyperConnection, RMSNorm, batched_training_coefficients, clear_training_coefficients,
+                  refresh_static_coefficients)
 
 
 def mhc_over_pixels(mhc: nn.Module, x: torch.Tensor) -> torch.Tensor:
@@ -345,8 +346,18 @@ class HybridVisionSystem(nn.Module):
         return refresh_static_coefficients(self)
 
     def forward(self, x: torch.Tensor, targets=None, text_query=None, task: str = "detection", compute_loss: bool = False) -> Dict[str, Any]:
+        if x.is_cuda and torch.is_grad_enabled():
+            # training: the coefficients of all layers hang on ONE autograd node (one forward launch, one backward launch)
+            batched_training_coefficients(self)
+            try:
+                return self._forward(x, targets, task, compute_loss)
+            finally:
+                clear_training_coefficients(self)
         if x.is_cuda:
             self.refresh_coefficients()
+        return self._forward(x, targets, task, compute_loss)
+
+    def _forward(self, x: torch.Tensor, targets, task: str, compute_loss: bool) -> Dict[str, Any]:
         out: Dict[str, Any] = {}
         feats = self.backbone(x)
         out["backbone_features"] = feats

@@ -419,6 +419,155 @@ class _CoeffFn(torch.autograd.Function):
         return None, outs[0], outs[1], outs[2]
 
 
+_DROPOUT_CALLS = [0]
+
+
+def _next_dropout_seed() -> int:
+    """A fresh 32-bit seed per training forward, reproducible under torch.manual_seed."""
+    _DROPOUT_CALLS[0] += 1
+    return (torch.initial_seed() * 0x9E3779B1 + _DROPOUT_CALLS[0] * 0x85EBCA6B) & 0xFFFFFFFF
+
+
+class _K2TokenPathFn(torch.autograd.Function):
+    """Training form of the module's token path (manifold_layers.py:248-267) on this library's kernels: the forward is
+    LayerNorm -> four tcgen05 GEMM launches (bias + GELU + dropout epilogues that also keep the pre-activations) ->
+    LayerNorm; the backward is the two LayerNorm backward kernels, five data-gradient GEMMs (GELU' x dropout mask in the
+    epilogue; the weights are read as they lie, MN-major), five weight-gradient GEMMs over the token axis (both
+    activations MN-major, split-K with a fixed-order reduction) and two column-sum kernels for the bias gradients.
+    bf16 operands, fp32 accumulation, bf16 activations between the GEMMs: the reference's own CUDA-autocast arithmetic."""
+
+    @staticmethod
+    def forward(ctx, mod, x2, h_pre, h_post, h_res, w1, b1, w2, b2, g_pre, be_pre, g_post, be_post):
+        from . import _lib
+        st = mod._fresh_state()
+        w1b, w2b = mod._mlp_bf16()
+        p = float(mod.mlp[2].p) if mod.training else 0.0
+        seed1 = _next_dropout_seed() if p > 0 else 0
+        seed2 = seed1 ^ 0x5BD1E995
+        x2 = x2.contiguous()
+        bf = torch.bfloat16
+        xn, xb = ops.layernorm_fwd(x2, g_pre.detach(), be_pre.detach(), mod.norm_pre.eps, out_dtype=bf, want_copy=x2.dtype != bf)
+        if xb is None:
+            xb = x2
+        h0 = ops.gemm_bf16(xn, st.h_pre_t)                                                               # :253
+        a1, z1 = ops.gemm_bf16_ex(h0, w1b, bias=b1.detach(), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU_SAVE, dropout_p=p, dropout_seed=seed1)
+        a2, z2 = ops.gemm_bf16_ex(a1, w2b, bias=b2.detach(), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU_SAVE, dropout_p=p, dropout_seed=seed2)
+        pre = ops.gemm_bf16(a2, st.h_post_t, xb, st.h_res_t, out_dtype=bf)                               # :259-263
+        out, _ = ops.layernorm_fwd(pre, g_post.detach(), be_post.detach(), mod.norm_post.eps, out_dtype=mod.output_dtype or torch.float32)
+        ctx.mod, ctx.cfg, ctx.key = mod, (p, seed1, seed2), st.key
+        ctx.save_for_backward(x2, xn, xb, h0, z1, a1, z2, a2, pre, w1b, w2b, g_pre, g_post)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import _lib
+        mod = ctx.mod
+        st = mod._state
+        if st is None or st.key != ctx.key:
+            raise HvsError("static coefficients were refreshed (parameters changed) between the forward and its backward")
+        p, seed1, seed2 = ctx.cfg
+        x2, xn, xb, h0, z1, a1, z2, a2, pre, w1b, w2b, g_pre, g_post = ctx.saved_tensors
+        dge = _lib.HVS_GEMM_EPI_DGELU
+        if dout.dtype not in (torch.float32, torch.bfloat16):
+            dout = dout.float()
+        d_pre, dg_post, dbe_post = ops.layernorm_bwd(pre, g_post.detach(), dout.contiguous(), mod.norm_post.eps)       # bf16 [T, D]
+        dz2 = ops.gemm_bf16_ex(d_pre, st.h_post_t, b_mn=True, epilogue=dge, aux=z2, dropout_p=p, dropout_seed=seed2)   # [T, H]
+        dx_res = ops.gemm_bf16_ex(d_pre, st.h_res_t, b_mn=True)                                                        # [T, D]
+        d_h_post = ops.gemm_wgrad(a2, d_pre)                                                                           # [H, D]
+        d_h_res = ops.gemm_wgrad(xb, d_pre)                                                                            # [D, D]
+        d_b2 = ops.colsum_bf16(dz2)
+        d_w2 = ops.gemm_wgrad(dz2, a1)                                                                                 # [H, 2H]
+        dz1 = ops.gemm_bf16_ex(dz2, w2b, b_mn=True, epilogue=dge, aux=z1, dropout_p=p, dropout_seed=seed1)             # [T, 2H]
+        d_b1 = ops.colsum_bf16(dz1)
+        d_w1 = ops.gemm_wgrad(dz1, h0)                                                                                 # [2H, H]
+        dh0 = ops.gemm_bf16_ex(dz1, w1b, b_mn=True)                                                                    # [T, H]
+        d_h_pre = ops.gemm_wgrad(xn, dh0)                                                                              # [D, H]
+        dxn = ops.gemm_bf16_ex(dh0, st.h_pre_t, b_mn=True)                                                             # [T, D]
+        dx, dg_pre, dbe_pre = ops.layernorm_bwd(x2, g_pre.detach(), dxn, mod.norm_pre.eps)
+        dx = dx + dx_res.to(dx.dtype)
+        return None, dx, d_h_pre, d_h_post, d_h_res, d_w1, d_b1, d_w2, d_b2, dg_pre, dbe_pre, dg_post, dbe_post
+
+
+class _AllCoeffsFn(torch.autograd.Function):
+    """constrained_matrices of EVERY layer of a model as ONE autograd node: the forward is the single batched launch of
+    refresh_static_coefficients, the backward ONE hvs_mhc_static_coeffs_bwd launch for all layers (autograd runs it when
+    every layer's dH has been accumulated, at the end of the backward pass) instead of one cooperative launch per layer
+    (76 launches, 20 ms of a 180 ms training step)."""
+
+    @staticmethod
+    def forward(ctx, mods, *raws):
+        ctx.mods = mods
+        ctx.keys = [m._state.key for m in mods]
+        outs = []
+        for m in mods:
+            st = m._state
+            outs += [st.h_pre.detach(), st.h_post.detach(), st.h_res.detach()]   # aliases of the state buffers (no copy)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        mods = ctx.mods
+        jobs, grads, outs = [], [], []
+        for i, m in enumerate(mods):
+            if m._state.key != ctx.keys[i]:
+                raise HvsError("static coefficients were refreshed (parameters changed) between the forward and its backward")
+            st = m._state
+            g: Dict[str, Optional[torch.Tensor]] = {}
+            any_grad = False
+            for j, (name, raw) in enumerate((("pre", m.H_pre_raw), ("post", m.H_post_raw), ("res", m.H_res_raw))):
+                d = douts[3 * i + j]
+                if d is not None and ctx.needs_input_grad[1 + 3 * i + j]:
+                    g[f"d_h_{name}"] = d.contiguous().float()
+                    o = torch.empty_like(raw, memory_format=torch.contiguous_format)
+                    g[f"d_h_{name}_raw"] = o
+                    outs.append(o)
+                    any_grad = True
+                else:
+                    outs.append(None)
+            if any_grad:
+                jobs.append({"h_pre_raw": m.H_pre_raw.detach(), "h_post_raw": m.H_post_raw.detach(), "h_res_raw": m.H_res_raw.detach(),
+                             "h_res": st.h_res, "uv_history": st.uv_history})
+                grads.append(g)
+        # one launch per (iterations, eps) group -- a model built from the reference has exactly one
+        by_cfg: Dict[Tuple[int, float], Tuple[list, list]] = {}
+        ji = 0
+        for i, m in enumerate(mods):
+            if any(outs[3 * i + j] is not None for j in range(3)):
+                cfg = (m.sinkhorn.num_iterations, m.sinkhorn.epsilon)
+                by_cfg.setdefault(cfg, ([], []))
+                by_cfg[cfg][0].append(jobs[ji])
+                by_cfg[cfg][1].append(grads[ji])
+                ji += 1
+        for (iters, eps), (js, gs) in by_cfg.items():
+            ops.static_coeffs_bwd(js, gs, iters, eps)
+        return (None, *outs)
+
+
+def batched_training_coefficients(model: nn.Module) -> int:
+    """Training counterpart of refresh_static_coefficients: refreshes every layer's coefficients in one launch and hangs
+    them on ONE autograd node, so that the coefficient backward of all layers is one launch too.  Each module's
+    constrained_matrices() returns its slice until clear_training_coefficients(model) is called (the host model does both
+    around its forward).  Returns the number of layers covered."""
+    mods = [m for m in model.modules() if isinstance(m, ManifoldHyperConnection) and m.H_res_raw.is_cuda
+            and any(p.requires_grad for p in (m.H_pre_raw, m.H_post_raw, m.H_res_raw))]
+    if not mods:
+        return 0
+    refresh_static_coefficients(model)
+    raws = []
+    for m in mods:
+        raws += [m.H_pre_raw, m.H_post_raw, m.H_res_raw]
+    outs = _AllCoeffsFn.apply(mods, *raws)
+    for i, m in enumerate(mods):
+        m._train_coeffs = (outs[3 * i], outs[3 * i + 1], outs[3 * i + 2])
+    return len(mods)
+
+
+def clear_training_coefficients(model: nn.Module) -> None:
+    for m in model.modules():
+        if isinstance(m, ManifoldHyperConnection):
+            m._train_coeffs = None
+
+
 class ManifoldHyperConnection(nn.Module):
     """Drop-in for the reference ManifoldHyperConnection (manifold_layers.py:104-346).
 
@@ -459,9 +608,11 @@ class ManifoldHyperConnection(nn.Module):
         self.signal_ratio_idx = 0
         self.dtype = torch.bfloat16 if use_mixed_precision else torch.float32
         self._state: Optional[_CoeffState] = None
+        self._train_coeffs: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None   # batched_training_coefficients
         self.monitor_signal_ratio = True
         self.output_dtype: Optional[torch.dtype] = None      # None: fp32 like the reference (its last op is a LayerNorm under autocast)
         self.use_chain_kernel = True                          # (D, H) = (32, 128) / (64, 256), bf16 input: hvs_mhc_module_fwd
+        self.use_training_kernels = True                      # grad / train mode: _K2TokenPathFn instead of torch ops + library GEMMs
         self._initialize_weights()
 
     def _initialize_weights(self):                       # :191-203
@@ -483,6 +634,8 @@ class ManifoldHyperConnection(nn.Module):
     def constrained_matrices(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:      # :205-221
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in (self.H_pre_raw, self.H_post_raw, self.H_res_raw))
         if needs_grad:
+            if self._train_coeffs is not None:               # one autograd node for all layers of the host model
+                return self._train_coeffs
             return _CoeffFn.apply(self, self.H_pre_raw, self.H_post_raw, self.H_res_raw)
         st = self._fresh_state()
         return st.h_pre, st.h_post, st.h_res
@@ -539,7 +692,23 @@ class ManifoldHyperConnection(nn.Module):
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if x.is_cuda and not needs_grad and not self.training and self.fused_supported() and x.dtype in (torch.float32, torch.bfloat16):
             return self._forward_fused(x.reshape(-1, shape[-1])).reshape(shape)
+        if x.is_cuda and self.use_training_kernels and self.fused_supported() and x.dtype in (torch.float32, torch.bfloat16):
+            return self._forward_training(x.reshape(-1, shape[-1])).reshape(shape)
         return self.forward_library(x)
+
+    def _forward_training(self, x2: torch.Tensor) -> torch.Tensor:
+        """Grad-enabled / train-mode forward on the library's own kernels (_K2TokenPathFn); dropout of the output and the
+        signal-ratio monitor as in forward_library."""
+        h_pre, h_post, h_res = self.constrained_matrices()
+        out = _K2TokenPathFn.apply(self, x2, h_pre, h_post, h_res, self.mlp[0].weight, self.mlp[0].bias, self.mlp[3].weight,
+                                   self.mlp[3].bias, self.norm_pre.weight, self.norm_pre.bias, self.norm_post.weight, self.norm_post.bias)
+        out = self.dropout(out)
+        if self.training and self.monitor_signal_ratio:
+            with torch.no_grad():                        # :295-303, without the per-call eigvalsh
+                ratio = torch.norm(out.float(), dim=-1).mean() / (torch.norm(x2.float(), dim=-1).mean() + 1e-8)
+                self.signal_ratio_history[self.signal_ratio_idx % 1000] = ratio
+                self.signal_ratio_idx += 1
+        return out
 
     def forward_library(self, x: torch.Tensor) -> torch.Tensor:
         """The token path in torch ops (library GEMMs under bf16 autocast, exactly the reference's CUDA execution):

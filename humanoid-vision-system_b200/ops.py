@@ -246,7 +246,7 @@ def layernorm_fwd(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps
     return out, cp
 
 
-LN_BWD_DIMS = (32, 64, 128, 256, 512)
+LN_BWD_DIMS = (32, 64, 128, 256, 512, 1024, 1792)     # tuned small-row kernel up to 512, the wide-row kernels beyond (any dim % 8 == 0)
 
 
 @_on_device
@@ -346,6 +346,85 @@ def gemm_bf16(a0: torch.Tensor, b0: torch.Tensor, a1: Optional[torch.Tensor] = N
     check(_lib.load().hvs_gemm_bf16(_ptr(a0), a0.stride(0), _ptr(b0), k0, _ptr(a1), a1.stride(0) if a1 is not None else 0,
                                     _ptr(b1), k1, _ptr(bias), _ptr(ln_weight), _ptr(ln_bias), ln_eps, _ptr(out),
                                     _NORM_DTYPES[out.dtype], out.stride(0), m, n, epilogue, _stream()), "hvs_gemm_bf16")
+    return out
+
+
+def _check_bf16_2d(*tensors):
+    for t in tensors:
+        if t is not None and (t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1):
+            raise _lib.HvsError("gemm operands must be 2-D bf16 with unit inner stride")
+
+
+@_on_device
+def gemm_bf16_ex(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
+                 epilogue: int = _lib.HVS_GEMM_EPI_NONE, aux: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+                 dropout_p: float = 0.0, dropout_seed: int = 0, want_pre: bool = False):
+    """The training form of the K2 GEMM kernel (hvs_gemm_bf16_ex):  out[M, N] = epilogue(op(a) op(b)^T).
+    a_mn / b_mn: the operand is given as its transpose in place ([K, M] / [K, N] row-major).
+    HVS_GEMM_EPI_BIAS_GELU_SAVE returns (out, z); every other epilogue returns out."""
+    _need_cuda(a, b, bias, aux)
+    _check_bf16_2d(a, b, aux)
+    k, m = (a.shape[0], a.shape[1]) if a_mn else (a.shape[1], a.shape[0])
+    kb, n = (b.shape[0], b.shape[1]) if b_mn else (b.shape[1], b.shape[0])
+    if k != kb:
+        raise _lib.HvsError(f"contraction extents differ: {k} vs {kb}")
+    out = torch.empty((m, n), dtype=out_dtype, device=a.device)
+    z = torch.empty((m, n), dtype=torch.bfloat16, device=a.device) if epilogue == _lib.HVS_GEMM_EPI_BIAS_GELU_SAVE else None
+    g = _lib.GemmArgs()
+    g.a0, g.lda0, g.b0, g.ldb0, g.K0 = _ptr(a), a.stride(0), _ptr(b), b.stride(0), k
+    g.a_mn_major, g.b_mn_major = int(a_mn), int(b_mn)
+    g.bias = _ptr(bias)
+    if aux is not None:
+        g.aux, g.ld_aux = _ptr(aux), aux.stride(0)
+    g.out, g.out_dtype, g.ldo = _ptr(out), _NORM_DTYPES[out_dtype], out.stride(0)
+    if z is not None:
+        g.out2, g.ldo2 = _ptr(z), z.stride(0)
+    g.M, g.N, g.epilogue = m, n, epilogue
+    g.dropout_p, g.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFF
+    g.split_k = 1
+    check(_lib.load().hvs_gemm_bf16_ex(ctypes.byref(g), _stream()), "hvs_gemm_bf16_ex")
+    return (out, z) if z is not None else out
+
+
+@_on_device
+def gemm_wgrad(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Weight gradient  out[Fa, Fb] = a^T b  over the tokens: a [T, Fa], b [T, Fb] bf16 as they lie in memory (both operands
+    MN-major), fp32 result.  Tiny outputs over millions of tokens are cut along T (split-K) into fp32 partials that
+    hvs_reduce_partials sums in a fixed order."""
+    _need_cuda(a, b, out)
+    _check_bf16_2d(a, b)
+    t, fa = a.shape
+    if b.shape[0] != t:
+        raise _lib.HvsError("wgrad operands must share the token axis")
+    fb = b.shape[1]
+    lib = _lib.load()
+    splits = int(lib.hvs_gemm_choose_split(fa, fb, t))
+    if out is None:
+        out = torch.empty((fa, fb), dtype=torch.float32, device=a.device)
+    dst = out if splits == 1 else torch.empty((splits, fa, fb), dtype=torch.float32, device=a.device)
+    g = _lib.GemmArgs()
+    g.a0, g.lda0, g.b0, g.ldb0, g.K0 = _ptr(a), a.stride(0), _ptr(b), b.stride(0), t
+    g.a_mn_major, g.b_mn_major = 1, 1
+    g.out, g.out_dtype, g.ldo = _ptr(dst), _lib.HVS_DTYPE_F32, fb
+    g.M, g.N, g.epilogue = fa, fb, _lib.HVS_GEMM_EPI_NONE
+    g.split_k, g.split_stride = splits, fa * fb
+    check(lib.hvs_gemm_bf16_ex(ctypes.byref(g), _stream()), "hvs_gemm_bf16_ex(wgrad)")
+    if splits > 1:
+        check(lib.hvs_reduce_partials(_ptr(dst), splits, fa * fb, fa * fb, _ptr(out), _stream()), "hvs_reduce_partials")
+    return out
+
+
+@_on_device
+def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
+    """Column sums of a bf16 [rows, cols] matrix in fp32 (bias gradients), fixed summation order."""
+    _need_cuda(x)
+    _check_bf16_2d(x)
+    rows, cols = x.shape
+    lib = _lib.load()
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    nb = int(lib.hvs_colsum_bf16_workspace(rows, cols))
+    ws = torch.empty(max(nb, 256), dtype=torch.uint8, device=x.device)
+    check(lib.hvs_colsum_bf16(_ptr(x), x.stride(0), rows, cols, _ptr(out), _ptr(ws), ws.numel(), _stream()), "hvs_colsum_bf16")
     return out
 
 

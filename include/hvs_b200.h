@@ -216,6 +216,51 @@ int hvs_gemm_bf16(const void* a0, int64_t lda0, const void* b0, int K0, const vo
                   const void* b1, int K1, const float* bias, const float* ln_w, const float* ln_b, float ln_eps,
                   void* out, int out_dtype, int64_t ldo, int64_t M, int N, int epilogue, void* stream);
 
+/* Training form of the same kernel: the module's forward AND the ten GEMMs of its backward (the autograd of
+ * manifold_layers.py:248-267: torch.matmul / nn.Linear / nn.GELU / nn.Dropout backward under bf16 autocast).
+ *   out[M,N] = epilogue( op(A0) op(B0)^T (+ A1 B1^T) )
+ * a_mn_major / b_mn_major = 0: the operand is [rows, K] row-major (K-major), leading dimension ld >= K.
+ *                         = 1: the operand is given as its TRANSPOSE in place, [K, rows] row-major, ld >= rows
+ *                              (rows = M for A, N for B).  Data gradients dX = dY W read W [out, in] as stored
+ *                              (B MN-major); weight gradients dW[M = features_a, N = features_b] = A^T B contract over
+ *                              K = tokens with both activations [T, features] as stored (A and B MN-major).
+ * split_k > 1: out is [split_k', M, ldo] fp32 partials (split_stride elements apart, default M * ldo) of the K range cut
+ *   into split_k' <= split_k parts of whole 64-element blocks; the number actually used is what hvs_gemm_choose_split
+ *   returns / the value passed clamped to the number of K blocks; sum them with hvs_reduce_partials (fixed order).
+ * Epilogues in addition to the three above:
+ *   HVS_GEMM_EPI_BIAS_GELU_SAVE  out2 = z = bf16(acc + bias) (pre-activation, kept for the backward),
+ *                                out  = dropout_p(gelu_erf(z))            nn.Linear -> nn.GELU -> nn.Dropout (:164-169)
+ *   HVS_GEMM_EPI_DGELU           out  = acc * gelu_erf'(aux[m,n]) * keep(m,n) / (1 - p)      their backward
+ * Dropout: element (m, n) is dropped iff 16 bits of a counter-based hash of (dropout_seed, m, n / 2) are below
+ * round(p * 65536); the same (seed, p) in the forward and the backward GEMM reproduces the mask, nothing is stored.
+ * dropout_p = 0 switches it off.  The second operand pair is K-major only and excludes split_k. */
+#define HVS_GEMM_EPI_BIAS_GELU_SAVE 3
+#define HVS_GEMM_EPI_DGELU 4
+typedef struct hvs_gemm_args {
+    const void* a0; int64_t lda0;
+    const void* b0; int64_t ldb0;
+    int K0;
+    const void* a1; int64_t lda1;
+    const void* b1; int64_t ldb1;
+    int K1;
+    int a_mn_major, b_mn_major;
+    const float* bias;
+    const float* ln_w; const float* ln_b; float ln_eps;
+    const void* aux; int64_t ld_aux;
+    void* out; int out_dtype; int64_t ldo;
+    void* out2; int64_t ldo2;
+    int64_t M; int N; int epilogue;
+    float dropout_p; uint32_t dropout_seed;
+    int split_k; int64_t split_stride;
+} hvs_gemm_args;
+int hvs_gemm_bf16_ex(const hvs_gemm_args* args, void* stream);
+int hvs_gemm_choose_split(int64_t M, int N, int64_t K);
+/* out[i] = sum over s < splits of partials[s * split_stride + i], i < numel, in that order (numel, stride multiples of 4). */
+int hvs_reduce_partials(const float* partials, int splits, int64_t split_stride, int64_t numel, float* out, void* stream);
+/* out[c] = sum over rows of x[r, c], x bf16 [rows, cols] with row stride ld (bias gradients: nn.Linear's db = sum_t dz). */
+size_t hvs_colsum_bf16_workspace(int64_t rows, int cols);
+int hvs_colsum_bf16(const void* x, int64_t ld, int64_t rows, int cols, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The whole token path (manifold_layers.py:248-267, eval mode) in ONE kernel per 128-token tile -- LayerNorm_pre in the
  * prologue, the five GEMMs chained through tensor memory and shared memory, GELU / residual / LayerNorm_post in the
  * epilogues -- for the widths whose five-launch path is bound by its HBM round trips (the backbone's first stages):

@@ -484,13 +484,15 @@ def test_refresh_static_coefficients_batches_all_modules():
 
 
 def test_module_training_path_gradients_vs_oracle():
-    """Training (grad mode): coefficient forward / backward on the kernels (hvs_mhc_static_coeffs[_bwd]), token path in
-    torch ops.  fp32 token path (use_mixed_precision=False) against autograd through the fp32 oracle at 1e-3; the bf16
+    """The LIBRARY form of the training path (use_training_kernels = False, and every fp32 module): coefficient forward /
+    backward on the kernels (hvs_mhc_static_coeffs[_bwd]), token path in torch ops; the kernel form is covered by
+    tests/test_gpu_k2_train.py.  fp32 token path (use_mixed_precision=False) against autograd through the fp32 oracle at 1e-3; the bf16
     autocast path on trained-like coefficients at the bf16-operand tolerance."""
     import hvs_b200
     for mixed, raw_std, tol in ((False, 1.0, 5e-3), (True, 1.0, 1e-1)):
         mod, p = _module_pair(64, 4, seed=3, raw_std=raw_std)
         mod.use_mixed_precision = mixed
+        mod.use_training_kernels = False
         mod.train()
         mod.dropout.p = 0.0
         for m in mod.mlp:
