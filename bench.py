@@ -275,7 +275,7 @@ def run_extras(args, dev, world, rank):
     torch.cuda.empty_cache()
     torch.cuda.reset_peak_memory_stats(dev)
     model = train_model
-    tr = harness.training_ddp(model, dev, world, rank, args.train_batch, 640)
+    tr = harness.training_ddp(model, dev, world, rank, args.train_batch, 640, use_graph=not args.train_eager)
     ms_tr = rank_max(tr["ms_per_step"])
     tips = world * tr["batch_per_gpu"] / (ms_tr * 1e-3)
     hv["training"] = dict(tr, workload="BASELINE configs[3]: bf16 autocast training, synthetic COCO-shaped dense targets, YOLOLoss, AdamW, "
@@ -328,6 +328,7 @@ def main():
     ap.add_argument("--skip-hybrid", action="store_true", help="no hybrid_vision legs")
     ap.add_argument("--stream-frames", type=int, default=300)
     ap.add_argument("--train-batch", type=int, default=16)
+    ap.add_argument("--train-eager", action="store_true", help="training step launched eagerly instead of one CUDA graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -347,6 +348,7 @@ def main():
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # the DDP training step is captured in a CUDA graph
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     T = args.tokens

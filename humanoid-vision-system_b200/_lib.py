@@ -41,7 +41,7 @@ class GemmArgs(ctypes.Structure):
                 ("out2", c_void_p), ("ldo2", c_int64),
                 ("M", c_int64), ("N", c_int), ("epilogue", c_int),
                 ("dropout_p", c_float), ("dropout_seed", c_uint32),
-                ("split_k", c_int), ("split_stride", c_int64)]
+                ("split_k", c_int), ("split_stride", c_int64), ("dropout_seed_dev", c_void_p)]
 
 
 class GradTensor(ctypes.Structure):

@@ -74,6 +74,21 @@ int make_tmap_bf16_2d_ld(CUtensorMap* out, const void* gptr, uint64_t rows, uint
     return r == CUDA_SUCCESS ? HVS_OK : HVS_ERR_DRIVER;
 }
 
+int upload_table(void* dst, std::vector<uint8_t>&& table, cudaStream_t stream) {
+    if (table.empty()) return HVS_OK;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) st = cudaStreamCaptureStatusNone;
+    if (st == cudaStreamCaptureStatusActive) {
+        static std::mutex mu;
+        static std::vector<std::vector<uint8_t>>* kept = new std::vector<std::vector<uint8_t>>();   // outlives every graph
+        std::lock_guard<std::mutex> lock(mu);
+        kept->push_back(std::move(table));
+        const std::vector<uint8_t>& t = kept->back();
+        return (int)cudaMemcpyAsync(dst, t.data(), t.size(), cudaMemcpyHostToDevice, stream);
+    }
+    return (int)cudaMemcpyAsync(dst, table.data(), table.size(), cudaMemcpyHostToDevice, stream);
+}
+
 // 3-D view of a [T, 4, 512] bf16 stream tensor as (channel, token, stream): a box of 64 channels x 8 tokens
 // x 4 streams lands in shared memory as four 1 KB swizzle atoms [stream][token][64 channels].
 int make_tmap_bf16_streams3d(CUtensorMap* out, const void* gptr, uint64_t tokens, uint32_t box_tokens) {

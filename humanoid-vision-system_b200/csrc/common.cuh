@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "../../include/hvs_b200.h"
 
@@ -87,6 +88,11 @@ inline void timer_end(int slot, cudaStream_t s) {
     std::lock_guard<std::mutex> lock(g_timer.mu);
     cudaEventRecord(g_timer.end[slot][timer_slot_index(slot)], s);
 }
+
+// Host -> device upload of a small parameter table on `stream`.  Eagerly the (pageable) source may be freed as soon as the
+// call returns; while the stream is being captured into a CUDA graph the copy becomes a graph node that reads the HOST
+// buffer again at every replay, so the table is moved into a process-lifetime registry instead of dying with the caller.
+int upload_table(void* dst, std::vector<uint8_t>&& table, cudaStream_t stream);
 
 // 2-D bf16 tensor map: [rows][cols] row-major, box [box_rows][64 cols] (=128 B inner), 128-byte swizzle.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows);

@@ -601,7 +601,10 @@ int run_plan(const hvs_coeff_job* jobs, const hvs_coeff_grad* grads, int num_job
     memcpy(tables.data() + hp.off_slabs, hp.slabs.data(), hp.slabs.size() * sizeof(Slab));
     memcpy(tables.data() + hp.off_cta, hp.cta_slab.data(), hp.cta_slab.size() * sizeof(int));
     if (!hp.ops.empty()) memcpy(tables.data() + hp.off_ops, hp.ops.data(), hp.ops.size() * sizeof(TransOp));
-    HVS_CUDA_TRY(cudaMemcpyAsync(ws, tables.data(), hp.table_bytes, cudaMemcpyHostToDevice, stream));
+    {
+        const int rcu = upload_table(ws, std::move(tables), stream);
+        if (rcu) return rcu;
+    }
     Plan pl{};
     pl.jobs = reinterpret_cast<const JobDev*>(ws + hp.off_jobs);
     pl.slabs = reinterpret_cast<const Slab*>(ws + hp.off_slabs);

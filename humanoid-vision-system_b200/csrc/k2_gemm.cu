@@ -3,7 +3,7 @@
 //     z  = LN_pre(x) @ H_pre                                       EPI_NONE       (bf16 out)
 //     z  = GELU(z @ W1^T + b1),  z = GELU(z @ W2^T + b2)           EPI_BIAS_GELU  (bf16 out)
 //     y  = LN_post(z @ H_post + x @ H_res)                         EPI_LAYERNORM  (two operand pairs, one accumulator)
-// One persistent warp-specialised kernel for sm_100a: a TMA producer thread, a tcgen05.mma issuer thread, eight
+// One persistent warp-specialised kernel for sm_100a: a TMA producer thread, a tcgen05.mma issuer thread, sixteen
 // epilogue warps.  D[128 x BN] fp32 accumulators live in tensor memory, double buffered (2 x 256 columns), so the
 // epilogue of tile i (tcgen05.ld -> bias / GELU / LayerNorm in registers -> global) overlaps the MMAs of tile i+1.
 // Operands: A [M, K] bf16 row-major (tokens x features), B [N, K] bf16 row-major (= nn.Linear's weight layout; the
@@ -38,7 +38,7 @@ constexpr int kMaxBN = 256;              // UMMA N limit
 constexpr int kMaxStages = 8;
 constexpr int kABytes = kBM * kBK * 2;   // 16 KB
 constexpr int kStageBudget = 196608;     // shared memory for the operand ring
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;               // four per tensor-memory lane quadrant: the epilogues are issue / latency bound
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kSmemBytes = kStageBudget + 1024 /*alignment slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;
@@ -73,6 +73,7 @@ struct GemmParams {
     uint32_t drop_thr;      // dropout: element dropped iff its 16 hash bits < drop_thr (0 = no dropout)
     float drop_scale;       // 1 / (1 - p)
     uint32_t seed;
+    const uint32_t* seed_dev;   // optional device word mixed into the seed (a step counter that lives on the device: CUDA graphs)
     // HVS_GEMM_EPI_YOLO_DECODE (fused prediction conv + decode): outputs in hvs_yolo_decode's layout
     const float* anchor_wh; // [3, 2]
     float* dec_boxes;       // [B, 3, H, W, 4]
@@ -164,6 +165,7 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+template <bool kYolo>                        // the decode epilogue is its own instantiation (its register needs stay out of the GEMMs')
 __global__ void __launch_bounds__(kThreads, 1)
 k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_b0,
                const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_b1, const GemmParams p) {
@@ -272,10 +274,12 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     } else {
         // ------------------------------------------------------------------ epilogue warps
         const int q = warp & 3;                                      // tensor-memory lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;                            // which alternate 32-column chunks it takes
+        const int part = (warp - 2) >> 2;                            // which 32-column chunks it takes (c = part mod 4)
+        constexpr int kParts = kEpiWarps / 4;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         uint32_t acc_it = 0;
         const int chunks = p.BN >> 5;
+        const uint32_t seed = p.seed_dev != nullptr ? (__ldg(p.seed_dev) * 0x9E3779B1u) ^ p.seed : p.seed;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int split = tile / tiles_mn, mn = tile - split * tiles_mn;
             const int m_blk = mn / p.n_outer, n_out = mn % p.n_outer;
@@ -288,28 +292,28 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 mbar_wait(&acc_full[it & 1u], (it >> 1) & 1u);
             }
             tc_fence_after();
-            if (p.epilogue == kEpiYoloDecode) {
+            if constexpr (kYolo) {
                 // ---- YOLODecoder.forward (yolo_head.py:241-285) on the accumulator row: a row is one pixel, its 255 columns are
                 // 3 anchors x (tx, ty, tw, th, obj, 80 classes).  Same arithmetic and order as yolo_decode.cu; the raw
-                // predictions never reach HBM.  Half 0 of the warp pair takes anchors 0 and 1, half 1 anchor 2.
+                // predictions never reach HBM.  Warp `part` of the quadrant takes anchor `part`.
                 const uint32_t t0 = tmem_base + lane_base + (it0 & 1u) * kMaxBN;
                 const int hw = p.grid_h * p.grid_w;
                 const int b = (int)(row / hw), rem = (int)(row % hw);
                 const int gy = rem / p.grid_w, gx = rem % p.grid_w;
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
-                    if ((a == 2) != (half == 1)) continue;
+                    if (a != part) continue;                             // one anchor per warp of the quadrant (the fourth idles)
                     const int lo = 85 * a;
                     float tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, obj = 0.f, best = -INFINITY;
                     int besti = 0;
 #pragma unroll
-                    for (int c = lo / 32; c <= (lo + 84) / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld32(t0 + (uint32_t)(c * 32), v);
+                    for (int c = lo / 16; c <= (lo + 84) / 16; ++c) {
+                        uint32_t v[16];
+                        tmem_ld16(t0 + (uint32_t)(c * 16), v);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int col = 32 * c + j, slot = col - lo;
+                        for (int j = 0; j < 16; ++j) {
+                            const int col = 16 * c + j, slot = col - lo;
                             if (slot < 0 || slot >= 85) continue;
                             const float x = __uint_as_float(v[j]) + __ldg(p.bias + col);
                             if (slot == 0) tx = x;
@@ -369,87 +373,83 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 const uint32_t it = it0 + (uint32_t)sub;
                 const uint32_t t0 = tmem_base + lane_base + (it & 1u) * kMaxBN;
                 const int n0 = (n_out * p.n_sub + sub) * p.BN;
-                for (int c = half; c < chunks; c += 2) {
+                for (int c = part; c < chunks; c += kParts) {
+                    const int nc = n0 + c * 32;
+                    if (!p.out_f32 && (p.epilogue == HVS_GEMM_EPI_BIAS_GELU || p.epilogue == HVS_GEMM_EPI_BIAS_GELU_SAVE ||
+                                       p.epilogue == HVS_GEMM_EPI_DGELU)) {
+                        // the hot epilogues (the module's MLP GEMMs, forward and backward: 88 % of its FLOPs), 16 columns at a
+                        // time (register budget of a 576-thread CTA), packed fp32x2 arithmetic
+#pragma unroll 1
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t v[16], o[8];
+                            tmem_ld16(t0 + (uint32_t)(c * 32 + hh * 16), v);
+                            const int nh = nc + hh * 16;
+                            if (p.epilogue == HVS_GEMM_EPI_DGELU) {
+                                // training backward: d z = d a * mask / (1 - p) * GELU'(z), z read back as the forward stored it
+                                const __nv_bfloat16* zp = p.aux + (row_ok ? row : 0) * p.ld_aux + nh;
+                                const uint4 zq0 = ld_global_nc_v4(zp), zq1 = ld_global_nc_v4(zp + 8);
+                                const uint32_t zz[8] = {zq0.x, zq0.y, zq0.z, zq0.w, zq1.x, zq1.y, zq1.z, zq1.w};
+                                tmem_wait_ld();
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float d0, d1;
+                                    gelu_grad2(bf16lo(zz[j]), bf16hi(zz[j]), d0, d1);
+                                    if (p.drop_thr != 0u) {
+                                        const uint32_t h = drop_hash(seed, (uint32_t)row, (uint32_t)(nh >> 1) + j);
+                                        d0 *= (h & 0xffffu) < p.drop_thr ? 0.f : p.drop_scale;
+                                        d1 *= (h >> 16) < p.drop_thr ? 0.f : p.drop_scale;
+                                    }
+                                    o[j] = pack_bf16(__uint_as_float(v[2 * j]) * d0, __uint_as_float(v[2 * j + 1]) * d1);
+                                }
+                            } else {
+                                tmem_wait_ld();
+                                const float4* b4 = reinterpret_cast<const float4*>(p.bias + nh);
+                                if (p.epilogue == HVS_GEMM_EPI_BIAS_GELU) {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float4 bb = __ldg(b4 + j);
+                                        o[2 * j] = gelu2_bf16(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+                                        o[2 * j + 1] = gelu2_bf16(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+                                    }
+                                } else {
+                                    // training forward: z = bf16(acc + b) -> out2, dropout(GELU(z)) -> out (the autocast convention: the
+                                    // Linear's bf16 output is what GELU sees and what the backward differentiates at)
+                                    uint32_t zz[8];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float4 bb = __ldg(b4 + j);
+                                        zz[2 * j] = pack_bf16(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+                                        zz[2 * j + 1] = pack_bf16(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const uint32_t g = gelu2_bf16(bf16lo(zz[j]), bf16hi(zz[j]));
+                                        if (p.drop_thr == 0u) {
+                                            o[j] = g;
+                                        } else {
+                                            const uint32_t h = drop_hash(seed, (uint32_t)row, (uint32_t)(nh >> 1) + j);
+                                            const float k0 = (h & 0xffffu) < p.drop_thr ? 0.f : p.drop_scale, k1 = (h >> 16) < p.drop_thr ? 0.f : p.drop_scale;
+                                            o[j] = pack_bf16(bf16lo(g) * k0, bf16hi(g) * k1);
+                                        }
+                                    }
+                                    if (row_ok) {
+                                        __nv_bfloat16* zp = p.out2 + row * p.ldo2 + nh;
+                                        st_global_v4(zp, zz[0], zz[1], zz[2], zz[3]);
+                                        st_global_v4(zp + 8, zz[4], zz[5], zz[6], zz[7]);
+                                    }
+                                }
+                            }
+                            if (row_ok) {
+                                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + nh;
+                                st_global_v4(op, o[0], o[1], o[2], o[3]);
+                                st_global_v4(op + 8, o[4], o[5], o[6], o[7]);
+                            }
+                        }
+                        continue;
+                    }
                     uint32_t v[32];
                     tmem_ld32(t0 + (uint32_t)(c * 32), v);
                     tmem_wait_ld();
-                    const int nc = n0 + c * 32;
-                    if (p.epilogue == HVS_GEMM_EPI_BIAS_GELU_SAVE) {
-                        // training forward: z = bf16(acc + b) -> out2, dropout(GELU(z)) -> out (the autocast convention:
-                        // the Linear's bf16 output is what GELU sees and what the backward differentiates at)
-                        uint32_t zz[16], o[16];
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bb = __ldg(b4 + j);
-                            zz[2 * j] = pack_bf16(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
-                            zz[2 * j + 1] = pack_bf16(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (p.drop_thr == 0u) {
-                                o[j] = gelu2_bf16(bf16lo(zz[j]), bf16hi(zz[j]));
-                            } else {
-                                const uint32_t h = drop_hash(p.seed, (uint32_t)row, (uint32_t)(nc >> 1) + j);
-                                const float k0 = (h & 0xffffu) < p.drop_thr ? 0.f : p.drop_scale, k1 = (h >> 16) < p.drop_thr ? 0.f : p.drop_scale;
-                                const uint32_t g = gelu2_bf16(bf16lo(zz[j]), bf16hi(zz[j]));
-                                o[j] = pack_bf16(bf16lo(g) * k0, bf16hi(g) * k1);
-                            }
-                        }
-                        if (row_ok) {
-                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + nc;
-                            __nv_bfloat16* zp = p.out2 + row * p.ldo2 + nc;
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                st_global_v4(op + 2 * j, o[j], o[j + 1], o[j + 2], o[j + 3]);
-                                st_global_v4(zp + 2 * j, zz[j], zz[j + 1], zz[j + 2], zz[j + 3]);
-                            }
-                        }
-                        continue;
-                    }
-                    if (p.epilogue == HVS_GEMM_EPI_DGELU) {
-                        // training backward: d z = d a * mask / (1 - p) * GELU'(z), z read back as the forward stored it
-                        uint32_t o[16];
-                        uint4 zq[4];
-                        const __nv_bfloat16* zp = p.aux + (row_ok ? row : 0) * p.ld_aux + nc;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) zq[j] = ld_global_nc_v4(zp + 8 * j);
-                        const uint32_t* zz = reinterpret_cast<const uint32_t*>(zq);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float d0, d1;
-                            gelu_grad2(bf16lo(zz[j]), bf16hi(zz[j]), d0, d1);
-                            if (p.drop_thr != 0u) {
-                                const uint32_t h = drop_hash(p.seed, (uint32_t)row, (uint32_t)(nc >> 1) + j);
-                                d0 *= (h & 0xffffu) < p.drop_thr ? 0.f : p.drop_scale;
-                                d1 *= (h >> 16) < p.drop_thr ? 0.f : p.drop_scale;
-                            }
-                            o[j] = pack_bf16(__uint_as_float(v[2 * j]) * d0, __uint_as_float(v[2 * j + 1]) * d1);
-                        }
-                        if (row_ok) {
-                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + nc;
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) st_global_v4(op + 2 * j, o[j], o[j + 1], o[j + 2], o[j + 3]);
-                        }
-                        continue;
-                    }
-                    if (p.epilogue == HVS_GEMM_EPI_BIAS_GELU && !p.out_f32) {
-                        // the hot epilogue (two of the module's four GEMMs, 88 % of its FLOPs): bias + GELU + bf16 pack, packed
-                        uint32_t o[16];
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bb = __ldg(b4 + j);
-                            o[2 * j] = gelu2_bf16(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
-                            o[2 * j + 1] = gelu2_bf16(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
-                        }
-                        if (row_ok) {
-                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + nc;
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) st_global_v4(op + 2 * j, o[j], o[j + 1], o[j + 2], o[j + 3]);
-                        }
-                        continue;
-                    }
                     if (p.epilogue == HVS_GEMM_EPI_BIAS_GELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(gelu_erf(__uint_as_float(v[j]) + __ldg(p.bias + nc + j)));
@@ -510,7 +510,7 @@ __global__ void reduce_partials_kernel(const float4* __restrict__ part, int spli
 }
 
 // column sums of a bf16 matrix (bias gradients): stage 1, one CTA per block of rows, 8 columns per thread
-constexpr int kColsumRows = 512;
+constexpr int kColsumRows = 256;
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int64_t rows, int cols,
                                                              float* __restrict__ part) {
     const int groups = cols >> 3;                          // 8-column groups
@@ -523,12 +523,25 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16
     for (int g0 = 0; g0 < groups; g0 += lanes) {
         const int g = g0 + cg;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (g < groups && rg < rsteps)
-            for (int64_t r = r0 + rg; r < r1; r += rsteps) {
-                const uint4 v = *reinterpret_cast<const uint4*>(x + r * ld + 8 * g);
+        if (g < groups && rg < rsteps) {
+            const __nv_bfloat16* col = x + 8 * g;
+            int64_t r = r0 + rg;
+            for (; r + 3 * rsteps < r1; r += 4 * rsteps) {          // four rows in flight (the loads are the latency)
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = ld_global_nc_v4(col + (r + u * rsteps) * ld);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc[0] += bf16lo(v[u].x); acc[1] += bf16hi(v[u].x); acc[2] += bf16lo(v[u].y); acc[3] += bf16hi(v[u].y);
+                    acc[4] += bf16lo(v[u].z); acc[5] += bf16hi(v[u].z); acc[6] += bf16lo(v[u].w); acc[7] += bf16hi(v[u].w);
+                }
+            }
+            for (; r < r1; r += rsteps) {
+                const uint4 v = ld_global_nc_v4(col + r * ld);
                 acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x); acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
                 acc[4] += bf16lo(v.z); acc[5] += bf16hi(v.z); acc[6] += bf16lo(v.w); acc[7] += bf16hi(v.w);
             }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[j];
         __syncthreads();
@@ -611,6 +624,7 @@ int launch_gemm(const hvs_gemm_args& g, int timer_slot, cudaStream_t stream) {
     p.drop_thr = (uint32_t)(g.dropout_p * 65536.0f + 0.5f);
     p.drop_scale = p.drop_thr ? 65536.0f / (65536.0f - (float)p.drop_thr) : 1.0f;   // 1 / (1 - p) for the p actually realised
     p.seed = g.dropout_seed;
+    p.seed_dev = g.dropout_seed_dev;
     p.aux = reinterpret_cast<const __nv_bfloat16*>(g.aux); p.ld_aux = g.ld_aux;
     p.out2 = reinterpret_cast<__nv_bfloat16*>(g.out2); p.ldo2 = g.ldo2;
     p.a_mn = a_mn; p.b_mn = b_mn;
@@ -644,11 +658,11 @@ int launch_gemm(const hvs_gemm_args& g, int timer_slot, cudaStream_t stream) {
     } else {
         ta1 = ta0; tb1 = tb0;
     }
-    HVS_SET_MAX_SMEM(k2_gemm_kernel, kSmemBytes);
+    HVS_SET_MAX_SMEM(k2_gemm_kernel<false>, kSmemBytes);
     const int sms = sm_count();
     const int grid = p.num_tiles < sms ? p.num_tiles : sms;
     timer_begin(timer_slot, stream);
-    k2_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta0, tb0, ta1, tb1, p);
+    k2_gemm_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(ta0, tb0, ta1, tb1, p);
     timer_end(timer_slot, stream);
     count_launch();
     return launch_status();
@@ -762,11 +776,11 @@ extern "C" int hvs_head_decode_fused(const void* tokens, int64_t ld_tokens, cons
     if (rc) return rc;
     rc = make_tmap_bf16_2d_ld(&tb, weight256, 256, (uint64_t)C_in, (uint64_t)C_in, 256);
     if (rc) return rc;
-    HVS_SET_MAX_SMEM(k2_gemm_kernel, kSmemBytes);
+    HVS_SET_MAX_SMEM(k2_gemm_kernel<true>, kSmemBytes);
     const int sms = sm_count();
     const int grid = p.num_tiles < sms ? p.num_tiles : sms;
     timer_begin(5, stream);
-    k2_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, ta, tb, p);
+    k2_gemm_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, ta, tb, p);
     timer_end(5, stream);
     count_launch();
     return launch_status();

@@ -177,7 +177,10 @@ extern "C" int hvs_grad_clip_dual(const hvs_grad_tensor* tensors_host, int num_t
         for (int k = 0; k < n; ++k) ct[c++] = i;
     }
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-    HVS_CUDA_TRY(cudaMemcpyAsync(ws, tab.data(), L.table_bytes, cudaMemcpyHostToDevice, stream));
+    {
+        const int rcu = upload_table(ws, std::move(tab), stream);
+        if (rcu) return rcu;
+    }
     ClipTable tb{};
     tb.tensors = reinterpret_cast<const hvs_grad_tensor*>(ws + L.off_t);
     tb.chunk_tensor = reinterpret_cast<const int*>(ws + L.off_ct);

@@ -175,15 +175,27 @@ def synthetic_targets(batch: int, image: int, rank: int, device, num_classes: in
 
 
 def training_ddp(model: HybridVisionSystem, device, world: int = 1, rank: int = 0, batch_per_gpu: int = 16, image: int = 640,
-                 steps: int = 3, warmup: int = 2) -> Dict[str, Any]:
+                 steps: int = 3, warmup: int = 2, use_graph: Optional[bool] = None) -> Dict[str, Any]:
     """One optimisation step = forward (bf16 autocast) + YOLOLoss + backward (DDP all-reduces the 353.8 M fp32 gradients
-    in 25 MB buckets, overlapped with the backward) + AdamW.  Weak scaling: batch_per_gpu images on every rank."""
+    in 25 MB buckets, overlapped with the backward) + AdamW.  Weak scaling: batch_per_gpu images on every rank.
+    use_graph: the whole step (forward, loss, backward, optimizer; ~5000 launches) captured once into a CUDA graph and
+    replayed -- the step is otherwise bound by the host's launch rate.  Default: on; the DDP step
+    follows the recipe for DistributedDataParallel under capture (DDP built on the side stream, 11 eager warm-up steps so its
+    buckets are final, NCCL's watchdog-side error handling off: bench.py sets TORCH_NCCL_ASYNC_ERROR_HANDLING=0)."""
     import torch.distributed as dist
+    from .mhc import dropout_step_counter
     model.train()
     net: nn.Module = model
+    if use_graph is None:
+        use_graph = True
+    side = torch.cuda.Stream(device)
     if world > 1:
-        net = nn.parallel.DistributedDataParallel(model, device_ids=[device.index], gradient_as_bucket_view=True)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-5, fused=True)
+        # (for a captured step DDP has to be built on the side stream the warm-up and the capture run on)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            net = nn.parallel.DistributedDataParallel(model, device_ids=[device.index], gradient_as_bucket_view=True)
+        torch.cuda.current_stream(device).wait_stream(side)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5, fused=True, capturable=bool(use_graph))
     used = batch_per_gpu
     while True:
         try:
@@ -191,8 +203,10 @@ def training_ddp(model: HybridVisionSystem, device, world: int = 1, rank: int = 
             x = torch.randn(used, 3, image, image, generator=g).to(device).contiguous(memory_format=torch.channels_last)
             targets = synthetic_targets(used, image, rank, device)
             losses = []
+            step_counter = dropout_step_counter(device)
 
-            def step():
+            def eager_step():
+                step_counter.add_(1)                   # new dropout masks every step (also when the step is a graph replay)
                 opt.zero_grad(set_to_none=True)
                 with torch.autocast("cuda", dtype=torch.bfloat16):
                     out = net(x, targets=targets, compute_loss=True)
@@ -201,11 +215,32 @@ def training_ddp(model: HybridVisionSystem, device, world: int = 1, rank: int = 
                     loss = out["loss"]["total_loss"] + 0.0 * out["final_features"].float().sum()
                 loss.backward()
                 opt.step()
-                losses.append(loss.detach())
+                return loss.detach()
 
-            launches0 = _lib.launch_count()
-            ms = _time_steps(step, steps, warmup)
-            launches = (_lib.launch_count() - launches0) // (steps + warmup)
+            graph = None
+            if use_graph:
+                side.wait_stream(torch.cuda.current_stream(device))
+                with torch.cuda.stream(side):
+                    for _ in range(11 if world > 1 else 3):   # allocator, cuDNN plans, optimizer state, DDP buckets: settled before the capture
+                        eager_step()
+                torch.cuda.current_stream(device).wait_stream(side)
+                torch.cuda.synchronize(device)
+                launches0 = _lib.launch_count()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_loss = eager_step()
+                launches = _lib.launch_count() - launches0
+
+                def step():
+                    graph.replay()
+                    losses.append(static_loss.clone())
+                ms = _time_steps(step, steps, warmup)
+            else:
+                def step():
+                    losses.append(eager_step())
+                launches0 = _lib.launch_count()
+                ms = _time_steps(step, steps, warmup)
+                launches = (_lib.launch_count() - launches0) // (steps + warmup)
             break
         except torch.OutOfMemoryError:
             del x
@@ -220,7 +255,8 @@ def training_ddp(model: HybridVisionSystem, device, world: int = 1, rank: int = 
     model.eval()
     return {"ms_per_step": ms, "batch_per_gpu": used, "loss_first": float(vals[0]), "loss_last": float(vals[-1]),
             "finite": bool(torch.isfinite(vals).all()), "grad_allreduce_bytes": grad_bytes if world > 1 else 0,
-            "hvs_launches_per_step": int(launches), "peak_mem_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30}
+            "hvs_launches_per_step": int(launches), "peak_mem_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30,
+            "cuda_graph": bool(use_graph)}
 
 
 # ----------------------------------------------------------------------------------------------- config 5

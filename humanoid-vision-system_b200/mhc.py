@@ -374,6 +374,9 @@ def refresh_static_coefficients(model: nn.Module, force: bool = False) -> int:
     forward).  Returns the number of layers refreshed.  Called by the hybrid_vision harness before a forward / at the
     top of a training step; a module whose cache is stale when its own forward runs refreshes itself."""
     mods = [m for m in model.modules() if isinstance(m, ManifoldHyperConnection) and m.H_res_raw.is_cuda]
+    # a training step that is being captured into a CUDA graph must contain the refresh: the host-side cache check does
+    # not run when the graph is replayed, the parameters change every step
+    force = force or (torch.is_grad_enabled() and torch.cuda.is_current_stream_capturing())
     todo = [m for m in mods if force or m._state is None or m._state.key != m._key()]
     groups: Dict[Tuple[Any, int, float], list] = {}
     for m in todo:
@@ -420,12 +423,24 @@ class _CoeffFn(torch.autograd.Function):
 
 
 _DROPOUT_CALLS = [0]
+_DROPOUT_STEP: Dict[Any, torch.Tensor] = {}
 
 
 def _next_dropout_seed() -> int:
     """A fresh 32-bit seed per training forward, reproducible under torch.manual_seed."""
     _DROPOUT_CALLS[0] += 1
     return (torch.initial_seed() * 0x9E3779B1 + _DROPOUT_CALLS[0] * 0x85EBCA6B) & 0xFFFFFFFF
+
+
+def dropout_step_counter(device) -> torch.Tensor:
+    """Device-resident step counter mixed into every dropout seed of the module kernels on `device`.  A training step
+    captured in a CUDA graph bakes the host-side seeds into the graph; advancing this counter INSIDE the captured step
+    (``dropout_step_counter(dev).add_(1)``) gives every replay new masks, the same in its forward and its backward."""
+    dev = torch.device(device)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _DROPOUT_STEP:
+        _DROPOUT_STEP[key] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return _DROPOUT_STEP[key]
 
 
 class _K2TokenPathFn(torch.autograd.Function):
@@ -444,17 +459,20 @@ class _K2TokenPathFn(torch.autograd.Function):
         p = float(mod.mlp[2].p) if mod.training else 0.0
         seed1 = _next_dropout_seed() if p > 0 else 0
         seed2 = seed1 ^ 0x5BD1E995
+        sdev = dropout_step_counter(x2.device) if p > 0 else None
         x2 = x2.contiguous()
         bf = torch.bfloat16
         xn, xb = ops.layernorm_fwd(x2, g_pre.detach(), be_pre.detach(), mod.norm_pre.eps, out_dtype=bf, want_copy=x2.dtype != bf)
         if xb is None:
             xb = x2
         h0 = ops.gemm_bf16(xn, st.h_pre_t)                                                               # :253
-        a1, z1 = ops.gemm_bf16_ex(h0, w1b, bias=b1.detach(), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU_SAVE, dropout_p=p, dropout_seed=seed1)
-        a2, z2 = ops.gemm_bf16_ex(a1, w2b, bias=b2.detach(), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU_SAVE, dropout_p=p, dropout_seed=seed2)
+        a1, z1 = ops.gemm_bf16_ex(h0, w1b, bias=b1.detach(), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU_SAVE, dropout_p=p, dropout_seed=seed1,
+                                      dropout_seed_dev=sdev)
+        a2, z2 = ops.gemm_bf16_ex(a1, w2b, bias=b2.detach(), epilogue=_lib.HVS_GEMM_EPI_BIAS_GELU_SAVE, dropout_p=p, dropout_seed=seed2,
+                                      dropout_seed_dev=sdev)
         pre = ops.gemm_bf16(a2, st.h_post_t, xb, st.h_res_t, out_dtype=bf)                               # :259-263
         out, _ = ops.layernorm_fwd(pre, g_post.detach(), be_post.detach(), mod.norm_post.eps, out_dtype=mod.output_dtype or torch.float32)
-        ctx.mod, ctx.cfg, ctx.key = mod, (p, seed1, seed2), st.key
+        ctx.mod, ctx.cfg, ctx.key = mod, (p, seed1, seed2, sdev), st.key
         ctx.save_for_backward(x2, xn, xb, h0, z1, a1, z2, a2, pre, w1b, w2b, g_pre, g_post)
         return out
 
@@ -465,19 +483,19 @@ class _K2TokenPathFn(torch.autograd.Function):
         st = mod._state
         if st is None or st.key != ctx.key:
             raise HvsError("static coefficients were refreshed (parameters changed) between the forward and its backward")
-        p, seed1, seed2 = ctx.cfg
+        p, seed1, seed2, sdev = ctx.cfg
         x2, xn, xb, h0, z1, a1, z2, a2, pre, w1b, w2b, g_pre, g_post = ctx.saved_tensors
         dge = _lib.HVS_GEMM_EPI_DGELU
         if dout.dtype not in (torch.float32, torch.bfloat16):
             dout = dout.float()
         d_pre, dg_post, dbe_post = ops.layernorm_bwd(pre, g_post.detach(), dout.contiguous(), mod.norm_post.eps)       # bf16 [T, D]
-        dz2 = ops.gemm_bf16_ex(d_pre, st.h_post_t, b_mn=True, epilogue=dge, aux=z2, dropout_p=p, dropout_seed=seed2)   # [T, H]
+        dz2 = ops.gemm_bf16_ex(d_pre, st.h_post_t, b_mn=True, epilogue=dge, aux=z2, dropout_p=p, dropout_seed=seed2, dropout_seed_dev=sdev)   # [T, H]
         dx_res = ops.gemm_bf16_ex(d_pre, st.h_res_t, b_mn=True)                                                        # [T, D]
         d_h_post = ops.gemm_wgrad(a2, d_pre)                                                                           # [H, D]
         d_h_res = ops.gemm_wgrad(xb, d_pre)                                                                            # [D, D]
         d_b2 = ops.colsum_bf16(dz2)
         d_w2 = ops.gemm_wgrad(dz2, a1)                                                                                 # [H, 2H]
-        dz1 = ops.gemm_bf16_ex(dz2, w2b, b_mn=True, epilogue=dge, aux=z1, dropout_p=p, dropout_seed=seed1)             # [T, 2H]
+        dz1 = ops.gemm_bf16_ex(dz2, w2b, b_mn=True, epilogue=dge, aux=z1, dropout_p=p, dropout_seed=seed1, dropout_seed_dev=sdev)             # [T, 2H]
         d_b1 = ops.colsum_bf16(dz1)
         d_w1 = ops.gemm_wgrad(dz1, h0)                                                                                 # [2H, H]
         dh0 = ops.gemm_bf16_ex(dz1, w1b, b_mn=True)                                                                    # [T, H]
@@ -650,7 +668,7 @@ class ManifoldHyperConnection(nn.Module):
         st = self._state
         w1, w2 = self.mlp[0].weight, self.mlp[3].weight
         key = (w1.data_ptr(), w1._version, w2.data_ptr(), w2._version)
-        if st.wkey != key:
+        if st.wkey != key or (torch.is_grad_enabled() and torch.cuda.is_current_stream_capturing()):
             st.w1 = w1.detach().to(torch.bfloat16).contiguous()
             st.w2 = w2.detach().to(torch.bfloat16).contiguous()
             st.wkey = key

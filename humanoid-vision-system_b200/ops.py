@@ -358,7 +358,7 @@ def _check_bf16_2d(*tensors):
 @_on_device
 def gemm_bf16_ex(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
                  epilogue: int = _lib.HVS_GEMM_EPI_NONE, aux: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
-                 dropout_p: float = 0.0, dropout_seed: int = 0, want_pre: bool = False):
+                 dropout_p: float = 0.0, dropout_seed: int = 0, dropout_seed_dev: Optional[torch.Tensor] = None):
     """The training form of the K2 GEMM kernel (hvs_gemm_bf16_ex):  out[M, N] = epilogue(op(a) op(b)^T).
     a_mn / b_mn: the operand is given as its transpose in place ([K, M] / [K, N] row-major).
     HVS_GEMM_EPI_BIAS_GELU_SAVE returns (out, z); every other epilogue returns out."""
@@ -381,6 +381,11 @@ def gemm_bf16_ex(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: boo
         g.out2, g.ldo2 = _ptr(z), z.stride(0)
     g.M, g.N, g.epilogue = m, n, epilogue
     g.dropout_p, g.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFF
+    if dropout_seed_dev is not None:
+        _need_cuda(dropout_seed_dev)
+        if dropout_seed_dev.dtype not in (torch.int32, torch.int64) or dropout_seed_dev.numel() < 1:
+            raise _lib.HvsError("dropout_seed_dev must be an int32 / int64 device tensor")
+        g.dropout_seed_dev = _ptr(dropout_seed_dev)
     g.split_k = 1
     check(_lib.load().hvs_gemm_bf16_ex(ctypes.byref(g), _stream()), "hvs_gemm_bf16_ex")
     return (out, z) if z is not None else out

@@ -252,6 +252,8 @@ typedef struct hvs_gemm_args {
     int64_t M; int N; int epilogue;
     float dropout_p; uint32_t dropout_seed;
     int split_k; int64_t split_stride;
+    const uint32_t* dropout_seed_dev;   /* optional: a DEVICE word mixed into dropout_seed when the kernel runs (a step counter
+                                           advanced on the device, so a captured CUDA graph draws a new mask every replay) */
 } hvs_gemm_args;
 int hvs_gemm_bf16_ex(const hvs_gemm_args* args, void* stream);
 int hvs_gemm_choose_split(int64_t M, int N, int64_t K);
