@@ -98,6 +98,8 @@ _SIGNATURES = {
     "hvs_reduce_partials": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     "hvs_colsum_bf16_workspace": (c_size_t, [c_int64, c_int]),
     "hvs_colsum_bf16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hvs_signal_ratio_workspace": (c_size_t, [c_int64]),
+    "hvs_signal_ratio": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hvs_profile_kernel_ms": (c_int, [POINTER(c_float)]),
     "hvs_head_decode_fused": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_int, c_void_p]),

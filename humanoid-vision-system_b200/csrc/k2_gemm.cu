@@ -509,29 +509,29 @@ __global__ void reduce_partials_kernel(const float4* __restrict__ part, int spli
     }
 }
 
-// column sums of a bf16 matrix (bias gradients): stage 1, one CTA per block of rows, 8 columns per thread
-constexpr int kColsumRows = 256;
+// column sums of a bf16 matrix (bias gradients): stage 1, one CTA per contiguous block of rows, 8 columns per thread;
+// stage 2, a warp per column sums the partials (lanes stride over them, fixed-order butterfly)
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int64_t rows, int cols,
-                                                             float* __restrict__ part) {
+                                                             int64_t rows_per_cta, float* __restrict__ part) {
     const int groups = cols >> 3;                          // 8-column groups
     const int lanes = groups < 256 ? groups : 256;         // threads along the columns
     const int rsteps = 256 / lanes;                        // rows handled concurrently
     const int cg = threadIdx.x % lanes, rg = threadIdx.x / lanes;
     __shared__ float red[256 * 8];
-    const int64_t r0 = (int64_t)blockIdx.x * kColsumRows;
-    const int64_t r1 = r0 + kColsumRows < rows ? r0 + kColsumRows : rows;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
     for (int g0 = 0; g0 < groups; g0 += lanes) {
         const int g = g0 + cg;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (g < groups && rg < rsteps) {
             const __nv_bfloat16* col = x + 8 * g;
             int64_t r = r0 + rg;
-            for (; r + 3 * rsteps < r1; r += 4 * rsteps) {          // four rows in flight (the loads are the latency)
-                uint4 v[4];
+            for (; r + 7 * rsteps < r1; r += 8 * rsteps) {          // eight rows in flight (the loads are the latency)
+                uint4 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = ld_global_nc_v4(col + (r + u * rsteps) * ld);
+                for (int u = 0; u < 8; ++u) v[u] = ld_global_nc_v4(col + (r + u * rsteps) * ld);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     acc[0] += bf16lo(v[u].x); acc[1] += bf16hi(v[u].x); acc[2] += bf16lo(v[u].y); acc[3] += bf16hi(v[u].y);
                     acc[4] += bf16lo(v[u].z); acc[5] += bf16hi(v[u].z); acc[6] += bf16lo(v[u].w); acc[7] += bf16hi(v[u].w);
                 }
@@ -559,12 +559,19 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16
         __syncthreads();
     }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int cols, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int nparts, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= cols) return;
     float a = 0.f;
-    for (int i = 0; i < nparts; ++i) a += part[(int64_t)i * cols + c];
-    out[c] = a;
+    for (int i = lane; i < nparts; i += 32) a += part[(int64_t)i * cols + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) out[c] = a;
+}
+inline int64_t colsum_rows_per_cta(int64_t rows) {           // at most 4 CTAs per SM, at least 64 rows each
+    const int64_t max_parts = 4 * (int64_t)sm_count();
+    int64_t rpc = (rows + max_parts - 1) / max_parts;
+    return rpc < 64 ? 64 : rpc;
 }
 
 int launch_gemm(const hvs_gemm_args& g, int timer_slot, cudaStream_t stream) {
@@ -724,7 +731,8 @@ extern "C" int hvs_reduce_partials(const float* partials, int splits, int64_t sp
 
 extern "C" size_t hvs_colsum_bf16_workspace(int64_t rows, int cols) {
     if (rows <= 0 || cols <= 0) return 0;
-    return (size_t)((rows + hvs::kColsumRows - 1) / hvs::kColsumRows) * (size_t)cols * 4;
+    const int64_t rpc = hvs::colsum_rows_per_cta(rows);
+    return (size_t)((rows + rpc - 1) / rpc) * (size_t)cols * 4;
 }
 
 extern "C" int hvs_colsum_bf16(const void* x, int64_t ld, int64_t rows, int cols, float* out, void* workspace, size_t workspace_bytes,
@@ -736,11 +744,11 @@ extern "C" int hvs_colsum_bf16(const void* x, int64_t ld, int64_t rows, int cols
     if (rows == 0) { HVS_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)cols * 4, stream)); return HVS_OK; }
     if (!x || !workspace || (reinterpret_cast<uintptr_t>(x) & 15)) return HVS_ERR_BAD_ARG;
     if (workspace_bytes < hvs_colsum_bf16_workspace(rows, cols)) return HVS_ERR_WORKSPACE;
-    const int64_t nparts = (rows + kColsumRows - 1) / kColsumRows;
-    if (nparts >= ((int64_t)1 << 31)) return HVS_ERR_UNSUPPORTED;
-    colsum_partial_kernel<<<(int)nparts, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, cols,
-                                                           reinterpret_cast<float*>(workspace));
-    colsum_final_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int)nparts, cols, out);
+    const int64_t rpc = colsum_rows_per_cta(rows);
+    const int nparts = (int)((rows + rpc - 1) / rpc);
+    colsum_partial_kernel<<<nparts, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, cols, rpc,
+                                                      reinterpret_cast<float*>(workspace));
+    colsum_final_kernel<<<(cols + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const float*>(workspace), nparts, cols, out);
     count_launch(2);
     return launch_status();
 }

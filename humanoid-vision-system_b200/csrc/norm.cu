@@ -326,12 +326,16 @@ layernorm_small_rows_bwd_kernel(const TI* __restrict__ x, const float* __restric
     }
 }
 
+// (a warp per column: lanes stride over the partials, then a fixed-order butterfly -- hundreds of partials summed by one
+// thread each was 16 us per launch, 152 launches per training step)
 __global__ void ln_bwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ db, int parts, int dim) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (j >= dim) return;
     float a = 0.f, b = 0.f;
-    for (int p = 0; p < parts; ++p) { a += part[((size_t)p * 2) * dim + j]; b += part[((size_t)p * 2 + 1) * dim + j]; }
-    dw[j] = a; db[j] = b;
+    for (int p = lane; p < parts; p += 32) { a += part[((size_t)p * 2) * dim + j]; b += part[((size_t)p * 2 + 1) * dim + j]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) { dw[j] = a; db[j] = b; }
 }
 
 template <typename TI, typename TG>
@@ -411,6 +415,51 @@ void launch_wide_bwd(const TI* x, const float* w, const TG* dy, TI* dx, float* p
     layernorm_wide_bwd_dx_kernel<TI, TG><<<(int)blocks, 256, 0, stream>>>(x, w, dy, dx, stats, rows, dim, eps);
     layernorm_wide_bwd_dw_kernel<TI, TG><<<dim3((dim + 127) / 128, parts), 128, 0, stream>>>(x, dy, stats, part, rows, dim, kWideRowsPerPart);
 }
+// Signal-ratio monitor of the module (manifold_layers.py:295-303): mean_rows ||out_r|| / (mean_rows ||x_r|| + 1e-8).  A warp per
+// row, fixed-order partials per CTA, one small second stage: two launches instead of the reference's eight (two casts, two
+// norms, two means, a division, an indexed store).
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256)
+row_norm_sums_kernel(const TA* __restrict__ a, const TB* __restrict__ b, int64_t rows, int dim, float* __restrict__ part) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float sa = 0.f, sb = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + wid; r < rows; r += (int64_t)gridDim.x * 8) {
+        float qa = 0.f, qb = 0.f;
+        for (int j = lane; j < dim; j += 32) {
+            const float va = ldf(a, r * dim + j), vb = ldf(b, r * dim + j);
+            qa = fmaf(va, va, qa);
+            qb = fmaf(vb, vb, qb);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { qa += __shfl_xor_sync(0xffffffffu, qa, o); qb += __shfl_xor_sync(0xffffffffu, qb, o); }
+        sa += sqrtf(qa);
+        sb += sqrtf(qb);
+    }
+    __shared__ float sm[8][2];
+    if (lane == 0) { sm[wid][0] = sa; sm[wid][1] = sb; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+        part[(size_t)blockIdx.x * 2 + threadIdx.x] = t;
+    }
+}
+__global__ void signal_ratio_final_kernel(const float* __restrict__ part, int nparts, int64_t rows, float* __restrict__ dst) {
+    const int lane = threadIdx.x;
+    float sa = 0.f, sb = 0.f;
+    for (int i = lane; i < nparts; i += 32) { sa += part[2 * i]; sb += part[2 * i + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+    if (lane == 0) dst[0] = (sa / (float)rows) / (sb / (float)rows + 1e-8f);
+}
+inline int row_norm_grid(int64_t rows) {
+    int64_t blocks = (rows + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
 inline bool ln_small_dim(int dim) { return dim == 32 || dim == 64 || dim == 128 || dim == 256 || dim == 512; }
 
 inline int grid_for_rows(int64_t rows) {
@@ -552,7 +601,7 @@ extern "C" int hvs_layernorm_bwd(const void* x, int x_dtype, const float* weight
             else if (x_dtype == HVS_DTYPE_BF16 && dy_dtype == HVS_DTYPE_BF16) launch_wide_bwd((const bf*)x, weight, (const bf*)dy, (bf*)dx, part, stats, parts, rows, dim, eps, stream);
             else return HVS_ERR_UNSUPPORTED;
         }
-        ln_bwd_finalize_kernel<<<(dim + 127) / 128, 128, 0, stream>>>(part, dweight, dbias, parts, dim);
+        ln_bwd_finalize_kernel<<<(dim + 3) / 4, 128, 0, stream>>>(part, dweight, dbias, parts, dim);
         count_launch(3);
         return launch_status();
     }
@@ -563,7 +612,30 @@ extern "C" int hvs_layernorm_bwd(const void* x, int x_dtype, const float* weight
     else if (x_dtype == HVS_DTYPE_F32 && dy_dtype == HVS_DTYPE_BF16) ok = launch_small_rows_bwd((const float*)x, weight, (const bf*)dy, (float*)dx, part, blocks, rows, dim, eps, stream);
     else if (x_dtype == HVS_DTYPE_BF16 && dy_dtype == HVS_DTYPE_BF16) ok = launch_small_rows_bwd((const bf*)x, weight, (const bf*)dy, (bf*)dx, part, blocks, rows, dim, eps, stream);
     if (!ok) return HVS_ERR_UNSUPPORTED;
-    ln_bwd_finalize_kernel<<<(dim + 127) / 128, 128, 0, stream>>>(part, dweight, dbias, blocks, dim);
+    ln_bwd_finalize_kernel<<<(dim + 3) / 4, 128, 0, stream>>>(part, dweight, dbias, blocks, dim);
+    count_launch(2);
+    return launch_status();
+}
+
+extern "C" size_t hvs_signal_ratio_workspace(int64_t rows) {
+    return (size_t)hvs::row_norm_grid(rows < 0 ? 0 : rows) * 2 * sizeof(float);
+}
+
+extern "C" int hvs_signal_ratio(const void* out, int out_dtype, const void* x, int x_dtype, int64_t rows, int dim, float* dst,
+                                void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (rows <= 0 || dim <= 0 || !out || !x || !dst) return HVS_ERR_BAD_ARG;
+    if (!workspace || workspace_bytes < hvs_signal_ratio_workspace(rows)) return HVS_ERR_WORKSPACE;
+    const int grid = row_norm_grid(rows);
+    float* part = (float*)workspace;
+    typedef __nv_bfloat16 bf;
+    if (out_dtype == HVS_DTYPE_F32 && x_dtype == HVS_DTYPE_F32) row_norm_sums_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)out, (const float*)x, rows, dim, part);
+    else if (out_dtype == HVS_DTYPE_BF16 && x_dtype == HVS_DTYPE_F32) row_norm_sums_kernel<bf, float><<<grid, 256, 0, stream>>>((const bf*)out, (const float*)x, rows, dim, part);
+    else if (out_dtype == HVS_DTYPE_F32 && x_dtype == HVS_DTYPE_BF16) row_norm_sums_kernel<float, bf><<<grid, 256, 0, stream>>>((const float*)out, (const bf*)x, rows, dim, part);
+    else if (out_dtype == HVS_DTYPE_BF16 && x_dtype == HVS_DTYPE_BF16) row_norm_sums_kernel<bf, bf><<<grid, 256, 0, stream>>>((const bf*)out, (const bf*)x, rows, dim, part);
+    else return HVS_ERR_UNSUPPORTED;
+    signal_ratio_final_kernel<<<1, 32, 0, stream>>>(part, grid, rows, dst);
     count_launch(2);
     return launch_status();
 }

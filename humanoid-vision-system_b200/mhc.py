@@ -722,9 +722,9 @@ class ManifoldHyperConnection(nn.Module):
                                    self.mlp[3].bias, self.norm_pre.weight, self.norm_pre.bias, self.norm_post.weight, self.norm_post.bias)
         out = self.dropout(out)
         if self.training and self.monitor_signal_ratio:
-            with torch.no_grad():                        # :295-303, without the per-call eigvalsh
-                ratio = torch.norm(out.float(), dim=-1).mean() / (torch.norm(x2.float(), dim=-1).mean() + 1e-8)
-                self.signal_ratio_history[self.signal_ratio_idx % 1000] = ratio
+            with torch.no_grad():                        # :295-303, without the per-call eigvalsh: one fused kernel pair
+                i = self.signal_ratio_idx % 1000
+                ops.signal_ratio(out.detach(), x2.detach().contiguous(), self.signal_ratio_history[i:i + 1])
                 self.signal_ratio_idx += 1
         return out
 

@@ -433,6 +433,25 @@ def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
+def signal_ratio(out: torch.Tensor, x: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[0] = mean row norm of out / (mean row norm of x + 1e-8)  (manifold_layers.py:295-303); dst: a 1-element fp32 view
+    on the device (e.g. signal_ratio_history[i:i+1])."""
+    _need_cuda(out, x, dst)
+    if out.shape != x.shape or out.dim() != 2 or not out.is_contiguous() or not x.is_contiguous():
+        raise _lib.HvsError("signal_ratio expects two contiguous [rows, dim] tensors of the same shape")
+    if dst.dtype != torch.float32 or dst.numel() < 1:
+        raise _lib.HvsError("dst must be an fp32 device tensor")
+    rows, dim = out.shape
+    if rows == 0:
+        return
+    lib = _lib.load()
+    nb = int(lib.hvs_signal_ratio_workspace(rows))
+    ws = torch.empty(max(nb, 256), dtype=torch.uint8, device=out.device)
+    check(lib.hvs_signal_ratio(_ptr(out), _NORM_DTYPES[out.dtype], _ptr(x), _NORM_DTYPES[x.dtype], rows, dim, _ptr(dst), _ptr(ws),
+                               ws.numel(), _stream()), "hvs_signal_ratio")
+
+
 def mhc_module_fwd_supported(d: int, h: int) -> bool:
     return bool(_lib.load().hvs_mhc_module_fwd_supported(d, h))
 

@@ -263,6 +263,13 @@ int hvs_reduce_partials(const float* partials, int splits, int64_t split_stride,
 size_t hvs_colsum_bf16_workspace(int64_t rows, int cols);
 int hvs_colsum_bf16(const void* x, int64_t ld, int64_t rows, int cols, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Signal-ratio monitor of ManifoldHyperConnection._monitor_stability (manifold_layers.py:295-303):
+ *   dst[0] = mean_rows ||out[r, :]|| / (mean_rows ||x[r, :]|| + 1e-8),  out, x [rows, dim] contiguous fp32 / bf16.
+ * dst is a device pointer (the module's signal_ratio_history slot); no host synchronisation. */
+size_t hvs_signal_ratio_workspace(int64_t rows);
+int hvs_signal_ratio(const void* out, int out_dtype, const void* x, int x_dtype, int64_t rows, int dim, float* dst,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* The whole token path (manifold_layers.py:248-267, eval mode) in ONE kernel per 128-token tile -- LayerNorm_pre in the
  * prologue, the five GEMMs chained through tensor memory and shared memory, GELU / residual / LayerNorm_post in the
  * epilogues -- for the widths whose five-launch path is bound by its HBM round trips (the backbone's first stages):

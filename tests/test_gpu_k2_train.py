@@ -296,3 +296,21 @@ def test_all_layers_coefficient_backward_is_one_launch_and_matches_per_layer_pat
     assert (hvs_b200._lib.launch_count() - before) - n_batched == len(dims) - 1    # one coefficient backward instead of one per layer
     for k in per_layer:                                                 # same arithmetic; the slab cuts (summation order) differ
         assert ((per_layer[k] - batched[k]).norm() / per_layer[k].norm().clamp_min(1e-30)).item() < 1e-5, k
+
+
+@pytest.mark.parametrize("rows,dim,dts", [(1000, 256, (torch.float32, torch.float32)), (4099, 32, (BF, BF)), (7, 1792, (torch.float32, BF)),
+                                          (200000, 64, (BF, torch.float32))])
+def test_signal_ratio_monitor_kernel(rows, dim, dts):
+    """mean_rows ||out|| / (mean_rows ||x|| + 1e-8) (manifold_layers.py:295-303) written into one slot of the history buffer."""
+    import hvs_b200
+    out = (_rand(rows, dim, seed=31) * 1.7).to(dts[0])
+    x = (_rand(rows, dim, seed=32) * 0.6 + 0.1).to(dts[1])
+    hist = torch.full((5,), -1.0, device=DEV)
+    hvs_b200.ops.signal_ratio(out.to(DEV), x.to(DEV), hist[2:3])
+    want = out.double().norm(dim=-1).mean() / (x.double().norm(dim=-1).mean() + 1e-8)
+    got = hist.cpu()
+    assert abs(got[2].item() - want.item()) < 2e-5 * want.item()
+    assert (got[[0, 1, 3, 4]] == -1.0).all()
+    hist2 = torch.zeros(1, device=DEV)
+    hvs_b200.ops.signal_ratio(out.to(DEV), x.to(DEV), hist2)
+    assert hist2.item() == got[2].item()                                # fixed-order reduction

@@ -37,7 +37,8 @@ else:
 for _ in range(2):
     step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+STACKS = os.environ.get("HVS_PROF_STACKS", "0") == "1"
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], with_stack=STACKS) as prof:
     step()
     torch.cuda.synchronize()
 rows = [(e.key, e.device_time_total, e.count) for e in prof.key_averages() if e.device_time_total > 0 and e.device_type == torch.autograd.DeviceType.CUDA]
@@ -68,3 +69,14 @@ os.makedirs("gpurun_out", exist_ok=True)
 path = f"gpurun_out/hybrid_profile_{'train' if train else 'infer'}_b{batch}.txt"
 open(path, "w").write("\n".join(out) + "\n")
 print("\n".join(out[:14]))
+if STACKS:
+    # which call sites launch the copy / elementwise kernels: aggregate operator device time by (op, innermost repo / torch frames)
+    agg = collections.Counter(); cnt = collections.Counter()
+    for e in prof.key_averages(group_by_stack_n=8):
+        if e.key in ("aten::copy_", "aten::add", "aten::add_", "aten::mul", "aten::contiguous", "aten::to", "aten::_to_copy", "aten::sum", "aten::clone", "aten::linalg_vector_norm") and e.device_time_total > 0:
+            frames = [f for f in e.stack if "hvs_b200" in f or "humanoid-vision" in f or "harness" in f][:3]
+            k = (e.key, " <- ".join(f.strip()[-90:] for f in frames))
+            agg[k] += e.self_device_time_total; cnt[k] += e.count
+    rows2 = [f"  {t/1e3:8.3f} ms x{cnt[k]:<5d} {k[0]:24s} {k[1]}" for k, t in agg.most_common(40)]
+    open(path.replace(".txt", "_stacks.txt"), "w").write("\n".join(rows2) + "\n")
+    print("\n".join(rows2[:25]))
