@@ -12,7 +12,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhvs_b200.so")
 STAMP = os.path.join(PKG_DIR, "build", "sources.sha256")
 
-SOURCES = ["api_common.cu", "mhc_stream_fwd.cu", "mhc_stream_generic.cu", "mhc_stream_bwd.cu", "mhc_stream_bwd_fused.cu", "sinkhorn.cu", "yolo_decode.cu", "nms.cu", "norm.cu", "k2_gemm.cu", "k2_coeffs.cu", "k2_chain.cu", "train_ops.cu"]
+SOURCES = ["api_common.cu", "mhc_stream_fwd.cu", "mhc_stream_generic.cu", "mhc_stream_generic_bwd.cu", "mhc_stream_bwd.cu", "mhc_stream_bwd_fused.cu", "sinkhorn.cu", "yolo_decode.cu", "nms.cu", "norm.cu", "k2_gemm.cu", "k2_coeffs.cu", "k2_chain.cu", "train_ops.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -696,8 +696,17 @@ int launch_bwd_finalize(const float* dw_part, int dw_ctas, const float* cta_accu
 
 }  // namespace hvs
 
+namespace hvs {
+bool generic_stream_shape_ok(int n, int C);
+size_t generic_stream_bwd_workspace(int64_t T, int n, int C);
+int launch_generic_stream_bwd(const void* x, const void* dy, const float* phi, const float* bias, const float* alpha, const float* scale,
+                              void* dx, float* dphi, float* dbias, float* dalpha, float* dscale, int64_t T, int n, int C, int iters,
+                              float eps_rms, float eps_sk, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+}  // namespace hvs
+
 extern "C" size_t hvs_mhc_stream_bwd_workspace(int64_t T, int n, int C) {
     using namespace hvs;
+    if (T >= 0 && (n != kN || C != kC) && generic_stream_shape_ok(n, C)) return generic_stream_bwd_workspace(T, n, C);
     if (T < 0 || n != kN || C != kC) return 0;
     return carve(nullptr, T, sm_count()).total;
 }
@@ -710,10 +719,17 @@ extern "C" int hvs_mhc_stream_bwd(const void* x, const void* dy, const float* ph
     using namespace hvs;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (T < 0) return HVS_ERR_BAD_ARG;
-    if (n != kN || C != kC || sk_iters < 0 || sk_iters > kMaxIters) return HVS_ERR_UNSUPPORTED;
     if (flags & HVS_MHC_SPLIT_PHI) return HVS_ERR_UNSUPPORTED;
     if (!phi || !bias || !alpha || !scale || !dphi || !dbias || !dalpha || !dscale) return HVS_ERR_BAD_ARG;
     if (T > 0 && (!x || !dy || !dx)) return HVS_ERR_BAD_ARG;
+    if ((n != kN || C != kC) && generic_stream_shape_ok(n, C)) {
+        // every other stream shape (n in {2, 4}, C % 8 == 0, C <= 1024): the general three-launch backward
+        if (T >= (int64_t)1 << 31) return HVS_ERR_UNSUPPORTED;
+        if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) return HVS_ERR_ALIGNMENT;
+        return launch_generic_stream_bwd(x, dy, phi, bias, alpha, scale, dx, dphi, dbias, dalpha, dscale, T, n, C, sk_iters, eps_rms, eps_sk,
+                                         workspace, workspace_bytes, stream);
+    }
+    if (n != kN || C != kC || sk_iters < 0 || sk_iters > kMaxIters) return HVS_ERR_UNSUPPORTED;
     if (T * kN >= (int64_t)1 << 31) return HVS_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15)
         return HVS_ERR_ALIGNMENT;

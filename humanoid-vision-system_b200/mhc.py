@@ -28,9 +28,11 @@ FWD_MAX_ITERS = 64
 
 
 def _check_trainable_shape(n: int, c: int, split_phi: bool = False):
-    if (n, c) != (4, 512) or split_phi:
-        raise HvsError("stream mHC training kernels are built for n_streams = 4, channels = 512 with the bf16 projection operand; "
-                       f"got n = {n}, C = {c}, split_phi = {split_phi} (inference supports n in {{2, 4}}, C % 8 == 0, C <= 1024)")
+    """n = 4, C = 512 trains on the tuned kernels (forward saving statistics + ONE fused backward kernel); every other
+    n in {2, 4}, C % 8 == 0, C <= 1024 on the general three-launch backward (mhc_stream_generic_bwd.cu)."""
+    if n not in (2, 4) or c % 8 or not 8 <= c <= 1024 or split_phi:
+        raise HvsError("stream mHC training kernels take n_streams in {2, 4}, channels % 8 == 0, channels <= 1024 with the bf16 "
+                       f"projection operand; got n = {n}, C = {c}, split_phi = {split_phi}")
 
 
 def _check_trainable_iters(sk_iters: int):
@@ -51,7 +53,7 @@ class _StreamMHCFn(torch.autograd.Function):
     def forward(ctx, x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk):
         _check_trainable_iters(sk_iters)
         _check_trainable_shape(x.shape[1], x.shape[2])
-        fused = True
+        fused = (x.shape[1], x.shape[2]) == (4, 512)      # tuned single-pass backward; other shapes recompute (general kernels)
         saved = ops.new_saved(x) if fused else None
         y, _, _ = ops.mhc_stream_fwd(x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk, saved=saved)
         if fused:
@@ -77,8 +79,9 @@ class StreamMHC(nn.Module):
     """Stream mHC residual layer:  y = H_res x + H_post (x) fn(H_pre^T x).
 
     x: [..., n, C] bf16.  n = 4, C = 512 runs on the tuned TMA / tensor-core kernels (forward AND the fused training
-    backward); every other n in {2, 4}, C % 8 == 0, C <= 1024 -- and ``split_phi=True`` (fp32-accurate projection
-    operand, HVS_MHC_SPLIT_PHI) for all shapes -- runs on the general forward kernel (inference).  ``fn=None`` is the
+    backward); every other n in {2, 4}, C % 8 == 0, C <= 1024 runs on the general kernels (forward, and a three-launch
+    backward whose dW contraction is the tcgen05 GEMM); ``split_phi=True`` (fp32-accurate projection operand,
+    HVS_MHC_SPLIT_PHI) is forward-only for all shapes.  ``fn=None`` is the
     identity (one fused kernel).  With a wrapped layer ``fn`` the forward runs the coefficient kernel, ``fn`` on the
     bf16 layer input, and the mixing kernel (inference path).
     """

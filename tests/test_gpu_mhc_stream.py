@@ -113,7 +113,7 @@ def test_forward_general_shapes_and_split_phi(n, c, split):
     layer = hvs_b200.StreamMHC(n_streams=n, channels=c, split_phi=split, device="cuda")
     with torch.no_grad():
         assert layer(x.cuda()).shape == x.shape
-    if (n, c) != (4, 512) or split:
+    if split:                                           # the fp32-accurate operand is forward-only
         with pytest.raises(hvs_b200.HvsError, match="training kernels"):
             layer(x.cuda().requires_grad_(True))
 
@@ -199,6 +199,48 @@ def test_backward_matches_oracle(t):
     dy = torch.randn(t, 4, 512, generator=torch.Generator().manual_seed(t)).to(torch.bfloat16)
     got = run_bwd(*inp[:1], dy, *inp[1:])
     check_bwd(inp, dy, got, f"T={t}")
+
+
+@pytest.mark.parametrize("n,c", [(2, 64), (2, 256), (2, 1024), (4, 64), (4, 128), (4, 256), (4, 1024), (2, 40), (4, 8)])
+def test_backward_general_shapes_match_oracle(n, c):
+    """Every stream shape but (4, 512) trains on the general backward (mhc_stream_generic_bwd.cu: per-token kernel, the
+    tcgen05 GEMM for dW = x^T E, finalize): same bounds as the tuned kernels, bitwise reproducible, and the nn.Module's
+    autograd path goes through it."""
+    import hvs_b200
+    t = 777
+    inp = make_inputs(t, seed=1000 * n + c, alpha=0.3, phistd=0.03, bstd=0.1, n=n, c=c)
+    dy = torch.randn(t, n, c, generator=torch.Generator().manual_seed(c)).to(torch.bfloat16)
+    got = run_bwd(*inp[:1], dy, *inp[1:])
+    check_bwd(inp, dy, got, f"n={n} C={c}")
+    again = run_bwd(*inp[:1], dy, *inp[1:])
+    assert all(torch.equal(got[k], again[k]) for k in got)
+    x, phi, bias, al, scale = inp
+    layer = hvs_b200.StreamMHC(n_streams=n, channels=c, device="cuda:0")
+    with torch.no_grad():
+        layer.phi.copy_(phi); layer.bias.copy_(bias); layer.alpha.copy_(al); layer.rms_scale.copy_(scale)
+    xg = x.to("cuda:0").requires_grad_(True)
+    layer(xg).backward(dy.to("cuda:0"))
+    assert torch.equal(xg.grad.cpu(), got["dx"]) and torch.equal(layer.phi.grad.cpu(), got["dphi"])
+    assert torch.equal(layer.rms_scale.grad.cpu(), got["dscale"]) and torch.equal(layer.alpha.grad.cpu(), got["dalpha"])
+
+
+def test_backward_general_shape_edges():
+    import hvs_b200
+    for t in (1, 5, 4099):
+        inp = make_inputs(t, seed=t, alpha=0.2, n=2, c=128)
+        dy = torch.randn(t, 2, 128, generator=torch.Generator().manual_seed(t)).to(torch.bfloat16)
+        check_bwd(inp, dy, run_bwd(*inp[:1], dy, *inp[1:]), f"T={t}")
+    inp = make_inputs(300, seed=3, alpha=0.2, n=4, c=256)
+    dy = torch.randn(300, 4, 256, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16)
+    for iters in (0, 1, 24):
+        got = run_bwd(*inp[:1], dy, *inp[1:], sk_iters=iters)
+        ref = mhc_ref.stream_mhc_backward(inp[0], dy, *inp[1:], sk_iterations=iters)
+        assert ((got["dphi"].double() - ref["dphi"].double()).norm() / ref["dphi"].double().norm()).item() < 3e-4
+    with pytest.raises(hvs_b200.HvsError):
+        run_bwd(*inp[:1], dy, *inp[1:], sk_iters=25)
+    z = hvs_b200.ops.mhc_stream_bwd(torch.zeros(0, 2, 64, dtype=torch.bfloat16, device="cuda:0"), torch.zeros(0, 2, 64, dtype=torch.bfloat16, device="cuda:0"),
+                                    torch.zeros(128, 8, device="cuda:0"), torch.zeros(8, device="cuda:0"), torch.zeros(3, device="cuda:0"), torch.ones(128, device="cuda:0"))
+    assert z["dx"].shape == (0, 2, 64) and float(z["dphi"].abs().max()) == 0.0 and float(z["dbias"].abs().max()) == 0.0
 
 
 def test_backward_init_scale_logits():
