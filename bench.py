@@ -268,6 +268,11 @@ def run_extras(args, dev, world, rank):
                         "hvs_launches_per_step": inf["hvs_launches_per_step"], "conv_bn_pairs_folded": folded,
                         "e2e": {"img_per_s": 64 / (ms_e2e * 1e-3), "ms_per_batch": ms_e2e, "h2d_bytes_per_step": inf_e2e["h2d_bytes_per_step"],
                                 "d2h_bytes_per_step": inf_e2e["d2h_bytes_per_step"], "note": "per rank: pinned host images -> H2D -> forward -> decode -> NMS -> detections D2H, all timed"}}}
+    if world > 1:
+        # the same step with 64 images on EVERY GPU (weak scaling), next to configs[2]'s strong-scaling split of one batch of 64
+        inf_w = harness.inference_sharded(model, dev, world, rank, 64 * world, 640, steps=3, warmup=1)
+        ms_w = rank_max(inf_w["ms_per_step"])
+        hv["inference"]["weak_scaling_64_per_gpu"] = {"img_per_s": 64 * world / (ms_w * 1e-3), "ms_per_batch": ms_w, "global_batch": 64 * world}
     torch.cuda.empty_cache()
     stream = harness.streaming_latency(model, dev, frames=args.stream_frames)
     hv["streaming"] = dict(stream, workload="BASELINE configs[4]: batch-1 640x640 frames, whole forward + decode + NMS in one CUDA graph")

@@ -81,6 +81,9 @@ int hvs_mhc_stream_post(const void* x, const float* coeffs, const void* fu, void
 /* Backward of hvs_mhc_stream_fwd (F = identity), coefficients recomputed.
  *   dy [T,n,C] bf16 -> dx [T,n,C] bf16, dphi [n*C, n*n+2n] fp32, dbias [n*n+2n], dalpha [3],
  *   dscale [n*C]  (parameter gradients are OVERWRITTEN, not accumulated).
+ * Shapes: n = 4, C = 512 on the tuned two-kernel path (TMA tiles, tensor-memory parking); every other
+ * n in {2, 4}, C % 8 == 0, C <= 1024 on the general path (a per-token kernel, the tcgen05 GEMM kernel for
+ * dW = x^T E with fp32-accurate two-term E, a finalize).  HVS_MHC_SPLIT_PHI is forward-only.
  * sk_iters <= 24 (HVS_ERR_UNSUPPORTED beyond; the forward alone takes up to 64).
  * workspace: hvs_mhc_stream_bwd_workspace(T, n, C) bytes, 256-byte aligned. */
 size_t hvs_mhc_stream_bwd_workspace(int64_t T, int n, int C);

@@ -2,7 +2,7 @@
 import csv, io, json, os, subprocess, sys, collections
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles")
+OUT = os.environ.get("HVS_PROFILE_OUT") or os.path.join(ROOT, "profiles")      # on the GPU box: gpurun_out/profiles (only gpurun_out/ travels back)
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -86,13 +86,19 @@ if __name__ == "__main__":
             "r1f_bench_kernels.ncu-rep": ("r01f_bench_kernels_T1M.txt", "one step earlier than r01g (forward with one shuffle step per Sinkhorn iteration, 1.60 ms); T=2^20"),
             "r1g_bench_kernels.ncu-rep": ("r01g_bench_kernels_T1M.txt", "one step earlier than r01h (backward before the lean reverse sweep and the uniform warp index, 2.86 ms); T=2^20"),
             "r1h_bench_kernels.ncu-rep": ("r01h_bench_kernels_T1M.txt", "SHIPPED training path at T=2^20: forward (saving statistics; shuffle-free Sinkhorn on scalings, fragments parked in tensor memory, y in half tiles), fused single-pass backward, finalize")}
+    reps.update({
+        "r2_train.ncu-rep": ("r02_k2_train_kernels.txt", "round 2 training kernels: ManifoldHyperConnection(512,4) T=2^15 and (64,4) T=2^17 forward+backward on _K2TokenPathFn "
+                             "(k2_gemm_kernel in all its modes: K-major forward, B MN-major data gradients with the GELU' epilogue, A+B MN-major split-K weight gradients; "
+                             "column sums, partial reduction, LayerNorm backward) + the general-shape K1 backward (n=2, C=256, T=2^16); every launch of one forward+backward, in launch order"),
+        "r2_bench_kernels.ncu-rep": ("r02_bench_kernels_T1M.txt", "round 2 re-capture of the SHIPPED K1 training path at T=2^20 (kernels unchanged since r01h): forward saving statistics, fused single-pass backward, finalize"),
+    })
     traffic = {}
     for rep, (out, note) in reps.items():
         path = os.path.join(g, rep)
         if not os.path.exists(path):
             continue
         res = summarize(path, out, note)
-        if rep == "r1h_bench_kernels.ncu-rep":
+        if rep in ("r1h_bench_kernels.ncu-rep", "r2_bench_kernels.ncu-rep"):
             for short, d in res:
                 def gb(k):
                     v, u = d[k]
@@ -117,4 +123,6 @@ if __name__ == "__main__":
         launch_list(os.path.join(g, "r1g_launches.csv"), "r01g_launch_list.txt")
     if os.path.exists(os.path.join(g, "r1h_launches.csv")):
         launch_list(os.path.join(g, "r1h_launches.csv"), "r01h_launch_list.txt")
+    if os.path.exists(os.path.join(g, "r2_launches.csv")):
+        launch_list(os.path.join(g, "r2_launches.csv"), "r02_launch_list.txt")
     print(open(os.path.join(OUT, "traffic.json")).read() if traffic else "no traffic")
