@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace hvs {
 namespace {
@@ -219,6 +220,56 @@ extern "C" int hvs_preprocess_u8(const void* src, int src_h, int src_w, int src_
     else if (dst_dtype == HVS_DTYPE_F16) preprocess_kernel<__half><<<grid, 128, 0, stream>>>(p, (__half*)dst);
     else if (dst_dtype == HVS_DTYPE_BF16) preprocess_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(p, (__nv_bfloat16*)dst);
     else return HVS_ERR_UNSUPPORTED;
+    count_launch();
+    return launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------- squeeze-excite gate + residual
+// The two elementwise passes that follow every mHC hop of the backbone's ConvMHCLayer (src/models/vision_backbone.py:125-133:
+// x = x * channel_attention(x), then + identity) as one pass over the channels-last token view: out[t, c] = y[t, c] * g[b(t), c] (+ r[t, c]).
+namespace hvs {
+namespace {
+__global__ void __launch_bounds__(256) gate_residual_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict__ gate,
+                                                            const uint4* __restrict__ res, uint4* __restrict__ out, int64_t rows,
+                                                            int64_t rows_per_image, int c8) {
+    const int64_t total = rows * c8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / c8;
+        const int g8 = (int)(i - row * c8);
+        const int64_t b = row / rows_per_image;
+        const uint4 yv = y[i];
+        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gate + (b * c8 + g8) * 8));
+        uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+        if (res != nullptr) rv = res[i];
+        const uint32_t ya[4] = {yv.x, yv.y, yv.z, yv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w}, ra[4] = {rv.x, rv.y, rv.z, rv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            o[k] = pack_bf16(fmaf(bf16lo(ya[k]), bf16lo(ga[k]), bf16lo(ra[k])), fmaf(bf16hi(ya[k]), bf16hi(ga[k]), bf16hi(ra[k])));
+        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+}  // namespace
+}  // namespace hvs
+
+extern "C" int hvs_gate_residual_bf16(const void* y, const void* gate, const void* residual, void* out, int64_t images,
+                                      int64_t rows_per_image, int channels, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (images < 0 || rows_per_image <= 0 || channels <= 0) return HVS_ERR_BAD_ARG;
+    if (images == 0) return HVS_OK;
+    if (!y || !gate || !out) return HVS_ERR_BAD_ARG;
+    if (channels % 8) return HVS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gate) | reinterpret_cast<uintptr_t>(residual) |
+         reinterpret_cast<uintptr_t>(out)) & 15)
+        return HVS_ERR_ALIGNMENT;
+    const int64_t rows = images * rows_per_image, total = rows * (channels / 8);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    gate_residual_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(y), reinterpret_cast<const __nv_bfloat16*>(gate),
+                                                          reinterpret_cast<const uint4*>(residual), reinterpret_cast<uint4*>(out), rows,
+                                                          rows_per_image, channels / 8);
     count_launch();
     return launch_status();
 }

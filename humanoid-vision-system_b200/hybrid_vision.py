@@ -29,6 +29,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .detection import YOLODetectionHead
 from .mhc import (ManifoldHyperConnection, RMSNorm, batched_training_coefficients, clear_training_coefficients,
                   refresh_static_coefficients)
@@ -75,7 +76,14 @@ class ConvMHCLayer(nn.Module):
         if self.mhc is not None:
             y = mhc_over_pixels(self.mhc, y)
             if self.channel_attention is not None:
-                y = y * self.channel_attention(y)
+                gate = self.channel_attention(y)
+                cl = torch.channels_last
+                if (not torch.is_grad_enabled() and y.is_cuda and y.dtype == torch.bfloat16 and gate.dtype == torch.bfloat16
+                        and y.shape[1] % 8 == 0 and y.is_contiguous(memory_format=cl)
+                        and (not self.use_residual or (x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=cl)))):
+                    # inference: gate multiply and residual add in one pass (hvs_gate_residual_bf16)
+                    return ops.gate_residual(y, gate, x if self.use_residual else None)
+                y = y * gate
         return y + x if self.use_residual else y
 
 

@@ -508,6 +508,23 @@ def clip_grad_dual(named_parameters, max_grad_norm: float = 1.0, mhc_max_norm: f
     return res
 
 
+@_on_device
+def gate_residual(y: torch.Tensor, gate: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y * gate (+ residual) for channels-last bf16 feature maps [B, C, H, W] and a per-(image, channel) gate [B, C, 1, 1]
+    (vision_backbone.py:125-133) in one pass; returns a channels-last tensor."""
+    _need_cuda(y, gate, residual)
+    b, c, h, w = y.shape
+    cl = torch.channels_last
+    if y.dtype != torch.bfloat16 or not y.is_contiguous(memory_format=cl) or gate.dtype != torch.bfloat16 or gate.numel() != b * c:
+        raise _lib.HvsError("gate_residual expects a channels-last bf16 map and a bf16 [B, C, 1, 1] gate")
+    if residual is not None and (residual.dtype != torch.bfloat16 or residual.shape != y.shape or not residual.is_contiguous(memory_format=cl)):
+        raise _lib.HvsError("residual must be a channels-last bf16 map of y's shape")
+    out = torch.empty_like(y, memory_format=cl)
+    g = gate.reshape(b, c).contiguous()
+    check(_lib.load().hvs_gate_residual_bf16(_ptr(y), _ptr(g), _ptr(residual), _ptr(out), b, h * w, c, _stream()), "hvs_gate_residual_bf16")
+    return out
+
+
 _PRE_DTYPES = {torch.float32: _lib.HVS_DTYPE_F32, torch.float16: _lib.HVS_DTYPE_F16, torch.bfloat16: _lib.HVS_DTYPE_BF16}
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 

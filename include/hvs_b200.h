@@ -308,6 +308,13 @@ size_t hvs_grad_clip_dual_workspace(const hvs_grad_tensor* tensors_host, int num
 int hvs_grad_clip_dual(const hvs_grad_tensor* tensors_host, int num_tensors, float max_norm_group0,
                        float max_norm_group1, float* result4, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Squeeze-excite gate and residual add after an mHC hop of ConvMHCLayer (src/models/vision_backbone.py:125-133) as ONE pass
+ * over the channels-last token view:  out[t, c] = y[t, c] * gate[image(t), c] (+ residual[t, c]);
+ * y, residual, out [images * rows_per_image, channels] bf16 contiguous (may alias), gate [images, channels] bf16,
+ * residual may be NULL; channels % 8 == 0; fp32 arithmetic, one rounding. */
+int hvs_gate_residual_bf16(const void* y, const void* gate, const void* residual, void* out, int64_t images,
+                           int64_t rows_per_image, int channels, void* stream);
+
 /* hvs_preprocess_u8: ImagePreprocessor "accurate" path (src/inference/preprocessing.py:252-273, colour swap :199-203):
  * src HWC uint8 frame (device memory, 1 or 3 channels, row pitch in bytes) -> bilinear resize with cv2.INTER_LINEAR
  * sampling (half-pixel centres, edge clamp; arithmetic in fp32, without cv2's intermediate rounding to uint8) ->

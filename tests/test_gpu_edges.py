@@ -73,3 +73,23 @@ def test_preprocess_frame_matches_cv2_pipeline(shape, out):
         assert ((got - want).abs() * std).max() < 1e-6             # no resampling: identical
     g16 = hvs_b200.ops.preprocess_frame(torch.from_numpy(frame).to(DEV), h, w, out_dtype=torch.bfloat16)
     assert torch.equal(g16.cpu(), got.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("b,c,h,w,with_res", [(2, 64, 7, 5, True), (3, 32, 16, 16, False), (1, 1024, 3, 3, True), (4, 128, 40, 40, True)])
+def test_gate_residual_matches_torch(b, c, h, w, with_res):
+    """y * gate (+ x) of ConvMHCLayer (vision_backbone.py:125-133) in one pass: fp32 arithmetic, one rounding -- within one
+    bf16 ulp of torch's two rounded passes."""
+    import hvs_b200
+    g = torch.Generator().manual_seed(b * c + h)
+    cl = torch.channels_last
+    y = torch.randn(b, c, h, w, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=cl)
+    x = torch.randn(b, c, h, w, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=cl)
+    gate = torch.sigmoid(torch.randn(b, c, 1, 1, generator=g)).to(torch.bfloat16).to(DEV)
+    got = hvs_b200.ops.gate_residual(y, gate, x if with_res else None)
+    exact = y.double() * gate.double() + (x.double() if with_res else 0.0)
+    assert got.shape == y.shape and got.is_contiguous(memory_format=cl) and got.dtype == torch.bfloat16
+    ulp = 2.0 ** (torch.floor(torch.log2(exact.abs().clamp_min(1e-30))) - 7)
+    assert ((got.double() - exact).abs() <= 0.51 * ulp + 1e-30).all()           # fp32 fma, one rounding to bf16
+    want = y * gate + x if with_res else y * gate                              # torch: the product is rounded before the add
+    mag = (y.double() * gate.double()).abs() + (x.double().abs() if with_res else 0.0)
+    assert ((got.double() - want.double()).abs() <= 2.0 ** -7 * mag + 1e-30).all()
