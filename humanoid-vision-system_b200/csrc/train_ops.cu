@@ -273,3 +273,51 @@ extern "C" int hvs_gate_residual_bf16(const void* y, const void* gate, const voi
     count_launch();
     return launch_status();
 }
+
+// ---------------------------------------------------------------------------------------------- folded-BatchNorm bias + activation
+// After eval-mode BatchNorm is folded into the convolution (y = conv_w'(x) + b'), ATen adds the bias in a broadcast pass of its
+// own and the activation in another; here both are one vectorised pass over the channels-last map:
+//   out[t, c] = act(y[t, c] + bias[c]),  act in {identity, SiLU (vision_backbone.py:36-45 default), ReLU}.
+namespace hvs {
+namespace {
+template <int ACT>
+__global__ void __launch_bounds__(256) bias_act_kernel(const uint4* __restrict__ y, const float* __restrict__ bias, uint4* __restrict__ out,
+                                                       int64_t rows, int c8) {
+    const int64_t total = rows * c8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g8 = (int)(i % c8);
+        const uint4 yv = y[i];
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g8), b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g8 + 1);
+        float v[8] = {bf16lo(yv.x) + b0.x, bf16hi(yv.x) + b0.y, bf16lo(yv.y) + b0.z, bf16hi(yv.y) + b0.w,
+                      bf16lo(yv.z) + b1.x, bf16hi(yv.z) + b1.y, bf16lo(yv.w) + b1.z, bf16hi(yv.w) + b1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (ACT == 1) v[k] = __fdividef(v[k], 1.0f + __expf(-v[k]));
+            else if (ACT == 2) v[k] = fmaxf(v[k], 0.f);
+        }
+        out[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+}
+}  // namespace
+}  // namespace hvs
+
+extern "C" int hvs_bias_act_bf16(const void* y, const float* bias, void* out, int64_t rows, int channels, int activation, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (rows < 0 || channels <= 0) return HVS_ERR_BAD_ARG;
+    if (rows == 0) return HVS_OK;
+    if (!y || !bias || !out) return HVS_ERR_BAD_ARG;
+    if (channels % 8 || activation < 0 || activation > 2) return HVS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(out)) & 15) return HVS_ERR_ALIGNMENT;
+    const int64_t total = rows * (channels / 8);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    const uint4* yp = reinterpret_cast<const uint4*>(y);
+    uint4* op = reinterpret_cast<uint4*>(out);
+    if (activation == 0) bias_act_kernel<0><<<(int)blocks, 256, 0, stream>>>(yp, bias, op, rows, channels / 8);
+    else if (activation == 1) bias_act_kernel<1><<<(int)blocks, 256, 0, stream>>>(yp, bias, op, rows, channels / 8);
+    else bias_act_kernel<2><<<(int)blocks, 256, 0, stream>>>(yp, bias, op, rows, channels / 8);
+    count_launch();
+    return launch_status();
+}

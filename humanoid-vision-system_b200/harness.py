@@ -49,7 +49,15 @@ def fold_batchnorm_for_inference(model: nn.Module) -> int:
     n = 0
     for mod in list(model.modules()):
         if hasattr(mod, "conv") and hasattr(mod, "bn") and isinstance(mod.conv, nn.Conv2d) and isinstance(mod.bn, nn.BatchNorm2d):
-            mod.conv = fuse_conv_bn_eval(mod.conv.eval(), mod.bn.eval())
+            fused = fuse_conv_bn_eval(mod.conv.eval(), mod.bn.eval())
+            if hasattr(mod, "folded_bias") and mod.conv.bias is None:
+                # ConvMHCLayer: the folded bias stays OUT of the convolution (ATen would add it in a broadcast pass of its own)
+                # and is applied together with the activation by hvs_bias_act_bf16
+                with torch.no_grad():
+                    mod.conv.weight.copy_(fused.weight)
+                mod.folded_bias = fused.bias.detach().float().clone()
+            else:
+                mod.conv = fused
             mod.bn = nn.Identity()
             n += 1
         if isinstance(mod, nn.Sequential):

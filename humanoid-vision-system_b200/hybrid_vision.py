@@ -65,6 +65,8 @@ class ConvMHCLayer(nn.Module):
         self.activation = {"silu": nn.SiLU, "relu": nn.ReLU, "gelu": nn.GELU}[activation]()
         self.mhc = ManifoldHyperConnection(out_channels, expansion_rate=expansion_rate) if use_mhc else None
         self.use_residual = in_channels == out_channels and stride == 1
+        self.activation_name = activation
+        self.folded_bias: Optional[torch.Tensor] = None      # set by harness.fold_batchnorm_for_inference (bn becomes Identity)
         self.channel_attention = None
         if use_mhc and out_channels >= 32:
             self.channel_attention = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(out_channels, out_channels // 4, 1),
@@ -72,7 +74,15 @@ class ConvMHCLayer(nn.Module):
         nn.init.kaiming_normal_(self.conv.weight, mode="fan_out", nonlinearity="relu")
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        y = self.activation(self.bn(self.conv(x)))
+        if self.folded_bias is not None:
+            y = self.conv(x)                            # BatchNorm folded into the weights; its bias and the activation in one pass
+            if (not torch.is_grad_enabled() and y.is_cuda and y.dtype == torch.bfloat16 and y.shape[1] % 8 == 0
+                    and y.is_contiguous(memory_format=torch.channels_last) and self.activation_name in ops.ACTIVATIONS):
+                y = ops.bias_act(y, self.folded_bias, self.activation_name)
+            else:
+                y = self.activation(y + self.folded_bias.to(y.dtype).view(1, -1, 1, 1))
+        else:
+            y = self.activation(self.bn(self.conv(x)))
         if self.mhc is not None:
             y = mhc_over_pixels(self.mhc, y)
             if self.channel_attention is not None:

@@ -525,6 +525,22 @@ def gate_residual(y: torch.Tensor, gate: torch.Tensor, residual: Optional[torch.
     return out
 
 
+ACTIVATIONS = {"none": 0, "silu": 1, "relu": 2}
+
+
+@_on_device
+def bias_act(y: torch.Tensor, bias: torch.Tensor, activation: str = "silu") -> torch.Tensor:
+    """act(y + bias[c]) for a channels-last bf16 map [B, C, H, W] in place (the bias of a BatchNorm-folded convolution and
+    the activation after it in one pass)."""
+    _need_cuda(y, bias)
+    b, c, h, w = y.shape
+    if y.dtype != torch.bfloat16 or not y.is_contiguous(memory_format=torch.channels_last) or bias.dtype != torch.float32 or bias.numel() != c:
+        raise _lib.HvsError("bias_act expects a channels-last bf16 map and an fp32 bias [C]")
+    check(_lib.load().hvs_bias_act_bf16(_ptr(y), _ptr(bias.contiguous()), _ptr(y), b * h * w, c, ACTIVATIONS[activation], _stream()),
+          "hvs_bias_act_bf16")
+    return y
+
+
 _PRE_DTYPES = {torch.float32: _lib.HVS_DTYPE_F32, torch.float16: _lib.HVS_DTYPE_F16, torch.bfloat16: _lib.HVS_DTYPE_BF16}
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 

@@ -315,6 +315,14 @@ int hvs_grad_clip_dual(const hvs_grad_tensor* tensors_host, int num_tensors, flo
 int hvs_gate_residual_bf16(const void* y, const void* gate, const void* residual, void* out, int64_t images,
                            int64_t rows_per_image, int channels, void* stream);
 
+/* Bias of a BatchNorm-folded convolution + the activation that follows it (ConvMHCLayer, vision_backbone.py:100-110, eval
+ * mode) in one pass over the channels-last map: out[t, c] = act(y[t, c] + bias[c]); y, out [rows, channels] bf16 (may
+ * alias), bias [channels] fp32; activation 0 = identity, 1 = SiLU, 2 = ReLU; channels % 8 == 0. */
+#define HVS_ACT_NONE 0
+#define HVS_ACT_SILU 1
+#define HVS_ACT_RELU 2
+int hvs_bias_act_bf16(const void* y, const float* bias, void* out, int64_t rows, int channels, int activation, void* stream);
+
 /* hvs_preprocess_u8: ImagePreprocessor "accurate" path (src/inference/preprocessing.py:252-273, colour swap :199-203):
  * src HWC uint8 frame (device memory, 1 or 3 channels, row pitch in bytes) -> bilinear resize with cv2.INTER_LINEAR
  * sampling (half-pixel centres, edge clamp; arithmetic in fp32, without cv2's intermediate rounding to uint8) ->

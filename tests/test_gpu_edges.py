@@ -93,3 +93,16 @@ def test_gate_residual_matches_torch(b, c, h, w, with_res):
     want = y * gate + x if with_res else y * gate                              # torch: the product is rounded before the add
     mag = (y.double() * gate.double()).abs() + (x.double().abs() if with_res else 0.0)
     assert ((got.double() - want.double()).abs() <= 2.0 ** -7 * mag + 1e-30).all()
+
+
+@pytest.mark.parametrize("act", ["silu", "relu", "none"])
+def test_bias_act_matches_torch(act):
+    import hvs_b200
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn(3, 64, 9, 11, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(64, generator=g).to(DEV)
+    z = y.double() + bias.double().view(1, -1, 1, 1)
+    want = {"silu": torch.nn.functional.silu, "relu": torch.relu, "none": lambda t: t}[act](z)
+    got = hvs_b200.ops.bias_act(y.clone(memory_format=torch.channels_last), bias, act)
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    assert ((got.double() - want).abs() <= 2.0 ** -8 * want.abs() + 1e-6).all()

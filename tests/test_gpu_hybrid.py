@@ -225,3 +225,29 @@ def test_training_step_on_the_kernels_is_as_close_to_fp32_as_the_library_path():
           f"library {d_l:.3f}; head tail vs fp32: kernels {t_k:.3f} library {t_l:.3f}")
     assert d_k <= 1.1 * d_l + 0.05, (d_k, d_l)
     assert t_k <= 1.1 * t_l + 0.05 and t_k < 0.4, (t_k, t_l)
+
+
+def test_batchnorm_folding_with_fused_bias_activation_keeps_the_outputs(model):
+    """harness.fold_batchnorm_for_inference (eval-mode BatchNorm folded into the convolutions; in ConvMHCLayer the folded
+    bias + SiLU run as hvs_bias_act_bf16, the gate multiply + residual as hvs_gate_residual_bf16): same function, bf16
+    rounding differences only."""
+    import copy
+    import hvs_b200
+    from hvs_b200 import harness
+    m0 = copy.deepcopy(model).eval()
+    hvs_b200.hybrid_vision.to_channels_last(m0)
+    m1 = copy.deepcopy(m0)
+    assert harness.fold_batchnorm_for_inference(m1) >= 40
+    hvs_b200.hybrid_vision.to_channels_last(m1)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 3, 320, 320, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+    before = hvs_b200._lib.launch_count()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        a = m0(x)
+        mid = hvs_b200._lib.launch_count()
+        b = m1(x)
+    assert (hvs_b200._lib.launch_count() - mid) > (mid - before)          # the fused glue kernels are this library's
+    for s in range(3):
+        pa, pb = a["predictions"][f"scale_{s}"].float(), b["predictions"][f"scale_{s}"].float()
+        rel = ((pa - pb).norm() / pa.norm()).item()
+        assert rel < 0.15, (s, rel)                                       # two bf16 pipelines through 76 layers (cf. 9-11 % vs fp32)
