@@ -12,8 +12,8 @@
 // T = 6.5 M tokens at batch 64).  Built for those shapes: D in {32, 64}, hidden H = 4 D.
 //
 // Roles (one CTA per SM, persistent over tiles): a TMA producer thread (x tile + a ring of 32 KB weight slots, in exactly
-// the order the MMAs consume them), a tcgen05.mma issuer thread, eight epilogue warps (two per tensor-memory lane
-// quadrant, splitting the columns) that also do the LayerNorm prologue and write every intermediate into shared memory
+// the order the MMAs consume them), a tcgen05.mma issuer thread, sixteen epilogue warps (four per tensor-memory lane
+// quadrant, splitting the columns in 16-column units) that also do the LayerNorm prologue and write every intermediate into shared memory
 // in the 128-byte-swizzled K-major layout the next MMA reads it in.  Tensor memory: [0, H) = h0's accumulator, later
 // h2's; [256, 512) = two accumulators for the 64-column h1 chunks, the first of which is reused for the output.
 // h1 chunks are 64 wide (one K block of the next GEMM): with 128-wide chunks their two buffers took 64 KB and left a
@@ -32,7 +32,7 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kSlotBytes = 32768;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;               // four per tensor-memory lane quadrant, each taking every fourth 16-column unit
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kColAcc1 = 256;
@@ -258,38 +258,50 @@ k2_chain_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         }
     } else {
         // ================================================================== epilogue warps
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int q = warp & 3, part = (warp - 2) >> 2;
         const uint32_t r = (uint32_t)(q * 32 + lane);                      // tile row = tensor-memory lane of this thread
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         uint32_t t = 0, n_acca = 0, n_acc1[2] = {0, 0}, n_g3[2] = {0, 0};
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
             const int64_t row = (int64_t)tile * kBM + r;
-            // ---- LayerNorm_pre of the staged x tile (half 0: one thread per row)
+            // ---- LayerNorm_pre of the staged x tile (part 0: one thread per row)
             mbar_wait(&bar[B_XFULL], t & 1u);
-            if (half == 0) {
-                float f[D];
-#pragma unroll
-                for (int g = 0; g < D / 8; ++g) {
+            if (part == 0) {
+                // three passes over the row in shared memory (sum, squared deviations, normalise): 8 values live at a time -- a
+                // 576-thread CTA has 96 registers per thread, a whole D = 64 row in registers spilled
+                auto load8 = [&](int g, float (&f)[8]) {
                     const uint4 v = lds128(base + C::kOffX + sw128(r, g));
-                    f[8 * g + 0] = bf16lo(v.x); f[8 * g + 1] = bf16hi(v.x); f[8 * g + 2] = bf16lo(v.y); f[8 * g + 3] = bf16hi(v.y);
-                    f[8 * g + 4] = bf16lo(v.z); f[8 * g + 5] = bf16hi(v.z); f[8 * g + 6] = bf16lo(v.w); f[8 * g + 7] = bf16hi(v.w);
-                }
+                    f[0] = bf16lo(v.x); f[1] = bf16hi(v.x); f[2] = bf16lo(v.y); f[3] = bf16hi(v.y);
+                    f[4] = bf16lo(v.z); f[5] = bf16hi(v.z); f[6] = bf16lo(v.w); f[7] = bf16hi(v.w);
+                };
                 float s = 0.f;
 #pragma unroll
-                for (int j = 0; j < D; ++j) s += f[j];
+                for (int g = 0; g < D / 8; ++g) {
+                    float f[8];
+                    load8(g, f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) s += f[j];
+                }
                 const float mean = s * (1.0f / D);
                 float qv = 0.f;
 #pragma unroll
-                for (int j = 0; j < D; ++j) { const float d = f[j] - mean; qv = fmaf(d, d, qv); }
+                for (int g = 0; g < D / 8; ++g) {
+                    float f[8];
+                    load8(g, f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; qv = fmaf(d, d, qv); }
+                }
                 const float inv = rsqrtf(qv * (1.0f / D) + p.eps_pre);
 #pragma unroll
                 for (int g = 0; g < D / 8; ++g) {
+                    float f[8];
+                    load8(g, f);
                     uint32_t o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int j = 8 * g + 2 * e;
-                        o[e] = pack_bf16((f[j] - mean) * inv * __ldg(p.ln_pre_w + j) + __ldg(p.ln_pre_b + j),
-                                         (f[j + 1] - mean) * inv * __ldg(p.ln_pre_w + j + 1) + __ldg(p.ln_pre_b + j + 1));
+                        o[e] = pack_bf16((f[2 * e] - mean) * inv * __ldg(p.ln_pre_w + j) + __ldg(p.ln_pre_b + j),
+                                         (f[2 * e + 1] - mean) * inv * __ldg(p.ln_pre_w + j + 1) + __ldg(p.ln_pre_b + j + 1));
                     }
                     sts128(base + C::kOffXN + sw128(r, g), make_uint4(o[0], o[1], o[2], o[3]));
                 }
@@ -301,18 +313,18 @@ k2_chain_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             // ---- E0: h0 accumulator -> bf16 -> shared memory (K-major, swizzled)
             mbar_wait(&bar[B_ACCA], n_acca++ & 1u);
             tc_fence_after();
-            for (int c = half; c < H / 32; c += 2) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_base + (uint32_t)(c * 32), v);
+            for (int c = part; c < H / 16; c += 4) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + lane_base + (uint32_t)(c * 16), v);
                 tmem_wait_ld();
-                const uint32_t blk = base + C::kOffH0 + (uint32_t)(c >> 1) * 16384u;
+                const uint32_t blk = base + C::kOffH0 + (uint32_t)(c >> 2) * 16384u;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < 2; ++g) {
                     const uint4 o = make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
                                                pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
                                                pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
                                                pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-                    sts128(blk + sw128(r, (uint32_t)((c & 1) * 4 + g)), o);
+                    sts128(blk + sw128(r, (uint32_t)((c & 3) * 2 + g)), o);
                 }
             }
             tc_fence_before();
@@ -327,20 +339,20 @@ k2_chain_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 if (n_g3[b] > 0) mbar_wait(&bar[B_G3 + b], (n_g3[b] - 1) & 1u);    // the MMAs that read this h1 buffer last are done
                 ++n_g3[b];
                 tc_fence_after();
-                for (int c = half; c < C::CW / 32; c += 2) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_base + kColAcc1 + (uint32_t)(b * 128 + c * 32), v);
+                for (int c = part; c < C::CW / 16; c += 4) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + lane_base + kColAcc1 + (uint32_t)(b * 128 + c * 16), v);
                     tmem_wait_ld();
-                    const float4* b4 = reinterpret_cast<const float4*>(p.b1 + j * C::CW + c * 32);
+                    const float4* b4 = reinterpret_cast<const float4*>(p.b1 + j * C::CW + c * 16);
                     const uint32_t blk = base + C::kOffH1 + (uint32_t)b * 16384u;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
+                    for (int g = 0; g < 2; ++g) {
                         const float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
                         const uint4 o = make_uint4(gelu2_bf16(__uint_as_float(v[8 * g]) + ba.x, __uint_as_float(v[8 * g + 1]) + ba.y),
                                                    gelu2_bf16(__uint_as_float(v[8 * g + 2]) + ba.z, __uint_as_float(v[8 * g + 3]) + ba.w),
                                                    gelu2_bf16(__uint_as_float(v[8 * g + 4]) + bb.x, __uint_as_float(v[8 * g + 5]) + bb.y),
                                                    gelu2_bf16(__uint_as_float(v[8 * g + 6]) + bb.z, __uint_as_float(v[8 * g + 7]) + bb.w));
-                        sts128(blk + sw128(r, (uint32_t)((c & 1) * 4 + g)), o);
+                        sts128(blk + sw128(r, (uint32_t)((c & 3) * 2 + g)), o);
                     }
                 }
                 tc_fence_before();
@@ -352,20 +364,20 @@ k2_chain_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             // ---- E2: h2 accumulator: + b2, GELU, bf16 -> shared memory (over h0, which every G2 MMA has finished reading)
             mbar_wait(&bar[B_ACCA], n_acca++ & 1u);
             tc_fence_after();
-            for (int c = half; c < H / 32; c += 2) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_base + (uint32_t)(c * 32), v);
+            for (int c = part; c < H / 16; c += 4) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + lane_base + (uint32_t)(c * 16), v);
                 tmem_wait_ld();
-                const float4* b4 = reinterpret_cast<const float4*>(p.b2 + c * 32);
-                const uint32_t blk = base + C::kOffH0 + (uint32_t)(c >> 1) * 16384u;
+                const float4* b4 = reinterpret_cast<const float4*>(p.b2 + c * 16);
+                const uint32_t blk = base + C::kOffH0 + (uint32_t)(c >> 2) * 16384u;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < 2; ++g) {
                     const float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
                     const uint4 o = make_uint4(gelu2_bf16(__uint_as_float(v[8 * g]) + ba.x, __uint_as_float(v[8 * g + 1]) + ba.y),
                                                gelu2_bf16(__uint_as_float(v[8 * g + 2]) + ba.z, __uint_as_float(v[8 * g + 3]) + ba.w),
                                                gelu2_bf16(__uint_as_float(v[8 * g + 4]) + bb.x, __uint_as_float(v[8 * g + 5]) + bb.y),
                                                gelu2_bf16(__uint_as_float(v[8 * g + 6]) + bb.z, __uint_as_float(v[8 * g + 7]) + bb.w));
-                    sts128(blk + sw128(r, (uint32_t)((c & 1) * 4 + g)), o);
+                    sts128(blk + sw128(r, (uint32_t)((c & 3) * 2 + g)), o);
                 }
             }
             tc_fence_before();
@@ -373,40 +385,53 @@ k2_chain_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar[B_HA]);
 
-            // ---- E3: LayerNorm_post over the D output columns, store the row (half 0)
+            // ---- E3: LayerNorm_post over the D output columns, store the row (part 0)
             mbar_wait(&bar[B_ACC3], t & 1u);
             tc_fence_after();
-            if (half == 0) {
-                float y[D];
-#pragma unroll
-                for (int c = 0; c < D / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_base + kColAcc1 + (uint32_t)(c * 32), v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) y[c * 32 + j] = __uint_as_float(v[j]);
-                }
+            if (part == 0) {
+                // three passes over the accumulator row in tensor memory, 16 columns at a time (register budget, as above)
+                const uint32_t ta = tmem_base + lane_base + kColAcc1;
                 float s = 0.f;
 #pragma unroll
-                for (int j = 0; j < D; ++j) s += y[j];
+                for (int c = 0; c < D / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(ta + (uint32_t)(c * 16), v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) s += __uint_as_float(v[j]);
+                }
                 const float mean = s * (1.0f / D);
                 float qv = 0.f;
 #pragma unroll
-                for (int j = 0; j < D; ++j) { const float d = y[j] - mean; qv = fmaf(d, d, qv); }
+                for (int c = 0; c < D / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(ta + (uint32_t)(c * 16), v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const float d = __uint_as_float(v[j]) - mean; qv = fmaf(d, d, qv); }
+                }
                 const float inv = rsqrtf(qv * (1.0f / D) + p.eps_post);
 #pragma unroll
-                for (int j = 0; j < D; ++j) y[j] = (y[j] - mean) * inv * __ldg(p.ln_post_w + j) + __ldg(p.ln_post_b + j);
-                if (row < p.T) {
-                    if (p.out_f32) {
-                        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * D);
+                for (int c = 0; c < D / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(ta + (uint32_t)(c * 16), v);
+                    tmem_wait_ld();
+                    float y[16];
 #pragma unroll
-                        for (int j = 0; j < D / 4; ++j) o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-                    } else {
-                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * D);
+                    for (int j = 0; j < 16; ++j)
+                        y[j] = (__uint_as_float(v[j]) - mean) * inv * __ldg(p.ln_post_w + c * 16 + j) + __ldg(p.ln_post_b + c * 16 + j);
+                    if (row < p.T) {
+                        if (p.out_f32) {
+                            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * D + c * 16);
 #pragma unroll
-                        for (int j = 0; j < D / 8; ++j)
-                            o[j] = make_uint4(pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
-                                              pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7]));
+                            for (int j = 0; j < 4; ++j) o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                        } else {
+                            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * D + c * 16);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+                                o[j] = make_uint4(pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
+                                                  pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7]));
+                        }
                     }
                 }
             }
