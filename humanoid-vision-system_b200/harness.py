@@ -235,7 +235,7 @@ def training_ddp(model: HybridVisionSystem, device, world: int = 1, rank: int = 
                 torch.cuda.synchronize(device)
                 launches0 = _lib.launch_count()
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, stream=side):       # the stream DDP and the warm-up ran on (AccumulateGrad nodes live there)
                     static_loss = eager_step()
                 launches = _lib.launch_count() - launches0
 
