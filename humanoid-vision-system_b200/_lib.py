@@ -14,6 +14,7 @@ from . import build as _build
 _LIB = None
 
 HVS_MHC_SPLIT_PHI = 1
+HVS_MHC_ADAPTIVE_ITERS = 2
 HVS_MHC_SAVED_STRIDE = 28
 HVS_DTYPE_F32, HVS_DTYPE_F16, HVS_DTYPE_BF16 = 0, 1, 2
 HVS_NMS_AGNOSTIC, HVS_NMS_CLASS_AWARE, HVS_NMS_BOXES_XYXY = 0, 1, 16

@@ -126,6 +126,15 @@ __device__ __forceinline__ void mma_bf16_1688(float (&d)[4], uint32_t a0, uint32
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
 }
 
+// kAdaptive (HVS_MHC_ADAPTIVE_ITERS): the forward replay stops at the first iteration that changes no entry of P of any token
+// of the warp by more than 2^-20 relative (see mhc_stream_fwd.cu: what the remaining iterations would change is ~2e-6), and
+// the reverse sweep differentiates the iterations actually run.
+__device__ __forceinline__ bool rel_close2(u64 a, u64 b) {      // |a - b| <= 2^-20 a for both halves (a > 0)
+    float a0, a1, b0, b1;
+    upk2(a, a0, a1); upk2(b, b0, b1);
+    return fabsf(a0 - b0) <= 9.5367431640625e-07f * a0 && fabsf(a1 - b1) <= 9.5367431640625e-07f * a1;
+}
+template <bool kAdaptive>
 __global__ void __launch_bounds__(kThreads, 1)
 mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                             const __grid_constant__ CUtensorMap tmap_dx, const FusedParams p) {
@@ -345,10 +354,12 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             HVS_TICK(1);
             // ---- forward Sinkhorn; the cumulative scalings after every iteration are kept for the reverse sweep
             u64 P01 = K01, P23 = K23;
+            int iters_run = p.sk_iters;                   // iterations whose scalings are in the history (kAdaptive: maybe fewer)
             {
                 float ui = 1.f;
                 u64 V01 = pk2(1.f, 1.f), V23 = V01;
                 for (int k = 0; k < p.sk_iters; ++k) {
+                    const u64 Q01 = P01, Q23 = P23;
                     float sa, sb;
                     upk2(add2(P01, P23), sa, sb);
                     const float rw = rcp_approx((sa + sb) + eps);
@@ -370,6 +381,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                         upk2(V01, v0, v1); upk2(V23, v2, v3);
                         *reinterpret_cast<float4*>(skv + (k + 1) * 64) = make_float4(v0, v1, v2, v3);
                     }
+                    if (kAdaptive && __all_sync(0xffffffffu, rel_close2(P01, Q01) && rel_close2(P23, Q23))) { iters_run = k + 1; break; }
                 }
             }
             if (lane == 0) HVS_TR(it, 4);
@@ -442,7 +454,7 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             //      first iteration: no special case for k = 0), and the signs are folded (tn = vb v^2 = -tb, ubn = -ub).
             u64 dK0, dK1;
             {
-                const int last = p.sk_iters - 1;
+                const int last = iters_run - 1;
                 const float* pu = sku + (last + 1) * 64;                        // u_k | v_k of the iteration being undone
                 const float* pv = skv + (last + 1) * 64;
                 float un = *pu;
@@ -810,7 +822,9 @@ extern "C" int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const flo
         if (rc) return rc;
         rc = make_tmap_bf16_streams4d(&tdx, dx, (uint64_t)T, kTok, 1);      // dx leaves one stream (8 KB) at a time
         if (rc) return rc;
-        HVS_SET_MAX_SMEM(mhc_stream_bwd_fused_kernel, kSmemBytes);
+        const bool adaptive = (flags & HVS_MHC_ADAPTIVE_ITERS) != 0;
+        if (adaptive) HVS_SET_MAX_SMEM(mhc_stream_bwd_fused_kernel<true>, kSmemBytes);
+        else HVS_SET_MAX_SMEM(mhc_stream_bwd_fused_kernel<false>, kSmemBytes);
         FusedParams p;
         p.phi = phi; p.bias = bias; p.alpha = alpha; p.scale = scale; p.saved = saved;
         p.dw_part = ws.dw_part; p.cta_accum = ws.cta_accum;
@@ -820,7 +834,8 @@ extern "C" int hvs_mhc_stream_bwd_saved(const void* x, const void* dy, const flo
         p.sk_iters = sk_iters; p.eps_rms = eps_rms; p.eps_sk = eps_sk;
         grid = p.num_tiles < sms ? p.num_tiles : sms;
         timer_begin(1, stream);
-        mhc_stream_bwd_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tx, tdy, tdx, p);
+        if (adaptive) mhc_stream_bwd_fused_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(tx, tdy, tdx, p);
+        else mhc_stream_bwd_fused_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(tx, tdy, tdx, p);
         timer_end(1, stream);
         count_launch();
         const int rc2 = launch_status();

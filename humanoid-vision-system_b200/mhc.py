@@ -50,29 +50,30 @@ class _StreamMHCFn(torch.autograd.Function):
     x and dy).  sk_iters <= 24 (checked before the forward runs)."""
 
     @staticmethod
-    def forward(ctx, x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk):
+    def forward(ctx, x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk, adaptive=False):
         _check_trainable_iters(sk_iters)
         _check_trainable_shape(x.shape[1], x.shape[2])
         fused = (x.shape[1], x.shape[2]) == (4, 512)      # tuned single-pass backward; other shapes recompute (general kernels)
+        adaptive = bool(adaptive) and fused
         saved = ops.new_saved(x) if fused else None
-        y, _, _ = ops.mhc_stream_fwd(x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk, saved=saved)
+        y, _, _ = ops.mhc_stream_fwd(x, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk, saved=saved, adaptive=adaptive)
         if fused:
             ctx.save_for_backward(x, phi, bias, alpha, scale, saved)
         else:
             ctx.save_for_backward(x, phi, bias, alpha, scale)
-        ctx.cfg = (sk_iters, eps_rms, eps_sk, fused)
+        ctx.cfg = (sk_iters, eps_rms, eps_sk, fused, adaptive)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        sk_iters, eps_rms, eps_sk, fused = ctx.cfg
+        sk_iters, eps_rms, eps_sk, fused, adaptive = ctx.cfg
         if fused:
             x, phi, bias, alpha, scale, saved = ctx.saved_tensors
-            g = ops.mhc_stream_bwd_saved(x, dy.contiguous(), saved, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk)
+            g = ops.mhc_stream_bwd_saved(x, dy.contiguous(), saved, phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk, adaptive=adaptive)
         else:
             x, phi, bias, alpha, scale = ctx.saved_tensors
             g = ops.mhc_stream_bwd(x, dy.contiguous(), phi, bias, alpha, scale, sk_iters, eps_rms, eps_sk)
-        return g["dx"], g["dphi"], g["dbias"], g["dalpha"], g["dscale"], None, None, None
+        return g["dx"], g["dphi"], g["dbias"], g["dalpha"], g["dscale"], None, None, None, None
 
 
 class StreamMHC(nn.Module):
@@ -88,10 +89,11 @@ class StreamMHC(nn.Module):
 
     def __init__(self, n_streams: int = 4, channels: int = 512, alpha: float = 0.01, sk_iterations: int = 20,
                  eps: float = 1e-8, phi_std: float = 0.02, fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
-                 device=None, split_phi: bool = False):
+                 device=None, split_phi: bool = False, adaptive_sinkhorn: bool = False):
         super().__init__()
         n, c = n_streams, channels
         self.split_phi = split_phi
+        self.adaptive_sinkhorn = adaptive_sinkhorn         # HVS_MHC_ADAPTIVE_ITERS (n = 4, C = 512): stop at the bitwise fixed point
         k = n * n + 2 * n
         self.n_streams, self.channels, self.sk_iterations, self.eps = n, c, sk_iterations, eps
         self.phi = nn.Parameter(torch.randn(n * c, k, device=device) * phi_std)
@@ -113,11 +115,12 @@ class StreamMHC(nn.Module):
         needs_grad = torch.is_grad_enabled() and (xf.requires_grad or any(p.requires_grad for p in self.parameters()))
         if self.fn is None and not needs_grad:
             y, _, _ = ops.mhc_stream_fwd(xf, self.phi, self.bias, self.alpha, self.rms_scale, self.sk_iterations,
-                                         self.eps, self.eps, split_phi=self.split_phi)
+                                         self.eps, self.eps, split_phi=self.split_phi,
+                                         adaptive=self.adaptive_sinkhorn and not self.split_phi and (self.n_streams, self.channels) == (4, 512))
         elif self.fn is None:
             _check_trainable_shape(self.n_streams, self.channels, self.split_phi)
             y = _StreamMHCFn.apply(xf, self.phi, self.bias, self.alpha, self.rms_scale, self.sk_iterations,
-                                   self.eps, self.eps)
+                                   self.eps, self.eps, self.adaptive_sinkhorn)
         else:
             if torch.is_grad_enabled() and (xf.requires_grad or self.phi.requires_grad):
                 raise HvsError("StreamMHC with a wrapped fn is forward-only in this build (fused backward covers fn=None)")

@@ -59,10 +59,11 @@ def mhc_stream_fwd(x: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor, alpha
                    scale: torch.Tensor, sk_iters: int = 20, eps_rms: float = 1e-8, eps_sk: float = 1e-8,
                    want_y: bool = True, want_u: bool = False, want_coeffs: bool = False,
                    split_phi: bool = False, out: Optional[torch.Tensor] = None,
-                   saved: Optional[torch.Tensor] = None
+                   saved: Optional[torch.Tensor] = None, adaptive: bool = False
                    ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
     """x [T,n,C] bf16 -> (y [T,n,C] bf16, u [T,C] bf16, coeffs [T,n*n+2n] fp32).
-    `saved` ([T, SAVED_STRIDE] fp32, from `new_saved`) receives the statistics `mhc_stream_bwd_saved` consumes."""
+    `saved` ([T, SAVED_STRIDE] fp32, from `new_saved`) receives the statistics `mhc_stream_bwd_saved` consumes.
+    `adaptive` (HVS_MHC_ADAPTIVE_ITERS, n = 4, C = 512): stop the Sinkhorn loop at a bitwise fixed point (same result)."""
     _need_cuda(x, phi, bias, alpha, scale)
     if x.dtype != torch.bfloat16 or x.dim() != 3 or not x.is_contiguous():
         raise _lib.HvsError("x must be a contiguous [T,n,C] bf16 tensor")
@@ -74,7 +75,7 @@ def mhc_stream_fwd(x: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor, alpha
     y = (out if out is not None else torch.empty_like(x)) if want_y else None
     u = torch.empty((t, c), dtype=torch.bfloat16, device=x.device) if want_u else None
     co = torch.empty((t, k), dtype=torch.float32, device=x.device) if want_coeffs else None
-    flags = _lib.HVS_MHC_SPLIT_PHI if split_phi else 0
+    flags = (_lib.HVS_MHC_SPLIT_PHI if split_phi else 0) | (_lib.HVS_MHC_ADAPTIVE_ITERS if adaptive else 0)
     if saved is not None:
         _need_cuda(saved)
         if saved.dtype != torch.float32 or tuple(saved.shape) != (t, _lib.HVS_MHC_SAVED_STRIDE) or not saved.is_contiguous():
@@ -94,8 +95,9 @@ def new_saved(x: torch.Tensor) -> torch.Tensor:
 def mhc_stream_bwd_saved(x: torch.Tensor, dy: torch.Tensor, saved: torch.Tensor, phi: torch.Tensor, bias: torch.Tensor,
                          alpha: torch.Tensor, scale: torch.Tensor, sk_iters: int = 20, eps_rms: float = 1e-8,
                          eps_sk: float = 1e-8, out: Optional[torch.Tensor] = None,
-                         workspace: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-    """Fused single-pass backward (dx and every parameter gradient) from the statistics saved by the forward."""
+                         workspace: Optional[torch.Tensor] = None, adaptive: bool = False) -> Dict[str, torch.Tensor]:
+    """Fused single-pass backward (dx and every parameter gradient) from the statistics saved by the forward.
+    `adaptive` (HVS_MHC_ADAPTIVE_ITERS): replay / differentiate the Sinkhorn iterations only up to their bitwise fixed point."""
     _need_cuda(x, dy, saved, phi, bias, alpha, scale)
     if dy.dtype != torch.bfloat16 or dy.shape != x.shape or not dy.is_contiguous() or not x.is_contiguous():
         raise _lib.HvsError("dy must be contiguous bf16 with x's shape")
@@ -112,7 +114,8 @@ def mhc_stream_bwd_saved(x: torch.Tensor, dy: torch.Tensor, saved: torch.Tensor,
     ws = workspace if workspace is not None else torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=x.device)
     check(lib.hvs_mhc_stream_bwd_saved(_ptr(x), _ptr(dy), _ptr(saved), _ptr(phi), _ptr(bias), _ptr(alpha), _ptr(scale),
                                        _ptr(dx), _ptr(dphi), _ptr(dbias), _ptr(dalpha), _ptr(dscale), t, n, c, sk_iters,
-                                       eps_rms, eps_sk, 0, _ptr(ws), ws.numel(), _stream()), "hvs_mhc_stream_bwd_saved")
+                                       eps_rms, eps_sk, _lib.HVS_MHC_ADAPTIVE_ITERS if adaptive else 0, _ptr(ws), ws.numel(), _stream()),
+          "hvs_mhc_stream_bwd_saved")
     return {"dx": dx, "dphi": dphi, "dbias": dbias, "dalpha": dalpha, "dscale": dscale}
 
 

@@ -59,6 +59,12 @@ uint64_t hvs_launch_count(void);
  * (forward only: the training entry points below are n == 4, C == 512).
  * ---------------------------------------------------------------------------------- */
 #define HVS_MHC_SPLIT_PHI 1u
+/* HVS_MHC_ADAPTIVE_ITERS (opt-in; n = 4, C = 512 kernels): the per-token Sinkhorn loop stops at the first iteration that
+ * changes no scaling (forward) / no entry of P (backward replay) of any token of the warp by more than 2^-20 relative.  The
+ * iteration contracts geometrically, so what the remaining iterations of the reference's fixed count would still change is
+ * ~2e-6 relative (coefficient tolerance: 1e-5); the fused backward differentiates the iterations actually run (gradients
+ * within 1e-5 of the full sweep).  Default off: every call runs all sk_iters like the reference. */
+#define HVS_MHC_ADAPTIVE_ITERS 2u
 
 int hvs_mhc_stream_fwd(const void* x, const float* phi, const float* bias, const float* alpha,
                        const float* scale, void* y, void* u, float* coeffs, int64_t T, int n, int C,

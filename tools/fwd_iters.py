@@ -20,7 +20,11 @@ def t(fn, n=10):
     for _ in range(n): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
-for it in (0, 5, 10, 20, 24):
+for it in (0, 1, 2, 3, 0, 1, 2, 5, 10, 20, 24):
     f = t(lambda: hvs_b200.ops.mhc_stream_fwd(x, phi, bias, alpha, scale, it, 1e-8, 1e-8, out=y, saved=saved))
     b = t(lambda: hvs_b200.ops.mhc_stream_bwd_saved(x, dy, saved, phi, bias, alpha, scale, it, 1e-8, 1e-8, out=dx, workspace=ws))
     print(f"iters {it:2d}: fwd {f:.3f} ms  bwd {b:.3f} ms")
+for it in (3, 20):
+    f = t(lambda: hvs_b200.ops.mhc_stream_fwd(x, phi, bias, alpha, scale, it, 1e-8, 1e-8, out=y, saved=saved, adaptive=True))
+    b = t(lambda: hvs_b200.ops.mhc_stream_bwd_saved(x, dy, saved, phi, bias, alpha, scale, it, 1e-8, 1e-8, out=dx, workspace=ws, adaptive=True))
+    print(f"adaptive, limit {it:2d}: fwd {f:.3f} ms  bwd {b:.3f} ms")
