@@ -42,7 +42,8 @@ class GemmArgs(ctypes.Structure):
                 ("out2", c_void_p), ("ldo2", c_int64),
                 ("M", c_int64), ("N", c_int), ("epilogue", c_int),
                 ("dropout_p", c_float), ("dropout_seed", c_uint32),
-                ("split_k", c_int), ("split_stride", c_int64), ("dropout_seed_dev", c_void_p)]
+                ("split_k", c_int), ("split_stride", c_int64), ("dropout_seed_dev", c_void_p),
+                ("colsum_partials", c_void_p)]
 
 
 class GradTensor(ctypes.Structure):
@@ -97,6 +98,8 @@ _SIGNATURES = {
     "hvs_gemm_bf16_ex": (c_int, [POINTER(GemmArgs), c_void_p]),
     "hvs_gemm_choose_split": (c_int, [c_int64, c_int, c_int64]),
     "hvs_reduce_partials": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "hvs_colsum_f32_workspace": (c_size_t, [c_int64, c_int]),
+    "hvs_colsum_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hvs_colsum_bf16_workspace": (c_size_t, [c_int64, c_int]),
     "hvs_colsum_bf16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hvs_signal_ratio_workspace": (c_size_t, [c_int64]),

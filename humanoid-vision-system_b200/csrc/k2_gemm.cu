@@ -74,6 +74,7 @@ struct GemmParams {
     float drop_scale;       // 1 / (1 - p)
     uint32_t seed;
     const uint32_t* seed_dev;   // optional device word mixed into the seed (a step counter that lives on the device: CUDA graphs)
+    float* colsum_part;     // EPI_DGELU, optional: [4 * m_tiles, N] column sums of the output per 32-row group (bias gradients)
     // HVS_GEMM_EPI_YOLO_DECODE (fused prediction conv + decode): outputs in hvs_yolo_decode's layout
     const float* anchor_wh; // [3, 2]
     float* dec_boxes;       // [B, 3, H, W, 4]
@@ -399,7 +400,39 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                                         d0 *= (h & 0xffffu) < p.drop_thr ? 0.f : p.drop_scale;
                                         d1 *= (h >> 16) < p.drop_thr ? 0.f : p.drop_scale;
                                     }
-                                    o[j] = pack_bf16(__uint_as_float(v[2 * j]) * d0, __uint_as_float(v[2 * j + 1]) * d1);
+                                    const float e0 = __uint_as_float(v[2 * j]) * d0, e1 = __uint_as_float(v[2 * j + 1]) * d1;
+                                    o[j] = pack_bf16(e0, e1);
+                                    v[2 * j] = __float_as_uint(row_ok ? bf16lo(o[j]) : 0.f);       // what the bias gradient sums: the bf16 d z
+                                    v[2 * j + 1] = __float_as_uint(row_ok ? bf16hi(o[j]) : 0.f);
+                                }
+                                if (p.colsum_part != nullptr) {
+                                    // column sums over the warp's 32 rows by a transpose-reduce: after the exchange with lane ^ 16
+                                    // a lane keeps 8 of its 16 columns (summed over 2 rows), then 4, 2, 1; 16 shuffles in all, the
+                                    // order of the additions is fixed.  Lane pairs (bit 0) end with the same column.
+                                    float k8[8], k4[4], k2[2];
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float a = __uint_as_float(v[i]), b = __uint_as_float(v[i + 8]);
+                                        const bool hi = lane & 16;
+                                        k8[i] = (hi ? b : a) + __shfl_xor_sync(0xffffffffu, hi ? a : b, 16);
+                                    }
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const bool hi = lane & 8;
+                                        k4[i] = (hi ? k8[i + 4] : k8[i]) + __shfl_xor_sync(0xffffffffu, hi ? k8[i] : k8[i + 4], 8);
+                                    }
+#pragma unroll
+                                    for (int i = 0; i < 2; ++i) {
+                                        const bool hi = lane & 4;
+                                        k2[i] = (hi ? k4[i + 2] : k4[i]) + __shfl_xor_sync(0xffffffffu, hi ? k4[i] : k4[i + 2], 4);
+                                    }
+                                    const bool hi2 = lane & 2;
+                                    float k1 = (hi2 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, hi2 ? k2[0] : k2[1], 2);
+                                    k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+                                    if (!(lane & 1)) {
+                                        const int col = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+                                        p.colsum_part[((size_t)m_blk * 4 + q) * p.N + nh + col] = k1;
+                                    }
                                 }
                             } else {
                                 tmem_wait_ld();
@@ -500,6 +533,17 @@ namespace {
 // fixed-order sum of split-K partials: out[i] = sum_s part[s * stride + i].  Eight lanes per output float4 stride over the
 // splits and combine in a butterfly (always the same order): a [64 x 64] gradient cut into 146 splits was 67 us with one
 // thread walking all of them.
+__global__ void __launch_bounds__(256) reduce_partials_few_kernel(const float4* __restrict__ part, int splits, int64_t stride4, int64_t n4,
+                                                                  float4* __restrict__ out) {      // a handful of splits: one thread per output
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 a = part[i];
+        for (int s = 1; s < splits; ++s) {
+            const float4 b = part[(int64_t)s * stride4 + i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        out[i] = a;
+    }
+}
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float4* __restrict__ part, int splits, int64_t stride4, int64_t n4,
                                                               float4* __restrict__ out) {
     const int l = threadIdx.x & 7;
@@ -584,6 +628,38 @@ inline int64_t colsum_rows_per_cta(int64_t rows) {           // at most 4 CTAs p
     return rpc < 64 ? 64 : rpc;
 }
 
+// column sums of an fp32 matrix [rows, cols] (the per-32-row partials the EPI_DGELU epilogue writes): lanes along the
+// columns (coalesced), warps and gridDim.y over the rows, fixed order
+__global__ void __launch_bounds__(256) colsum_f32_partial_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t rows_per_block,
+                                                                 float* __restrict__ part) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float a = 0.f;
+    if (c < cols) {
+        int64_t r = r0 + wid;
+        for (; r + 24 < r1; r += 32) {
+            const float v0 = x[r * cols + c], v1 = x[(r + 8) * cols + c], v2 = x[(r + 16) * cols + c], v3 = x[(r + 24) * cols + c];
+            a += v0; a += v1; a += v2; a += v3;
+        }
+        for (; r < r1; r += 8) a += x[r * cols + c];
+    }
+    __shared__ float sm[8][32];
+    sm[wid][lane] = a;
+    __syncthreads();
+    if (wid == 0 && c < cols) {
+        float t = sm[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += sm[k][lane];
+        part[(size_t)blockIdx.y * cols + c] = t;
+    }
+}
+inline int64_t colsum_f32_rows_per_block(int64_t rows) {
+    int64_t rpb = (rows + 63) / 64;                       // at most 64 row blocks
+    return rpb < 64 ? 64 : rpb;
+}
+
 int launch_gemm(const hvs_gemm_args& g, int timer_slot, cudaStream_t stream) {
     const int64_t M = g.M;
     const int N = g.N, K0 = g.K0, K1 = g.K1;
@@ -642,6 +718,7 @@ int launch_gemm(const hvs_gemm_args& g, int timer_slot, cudaStream_t stream) {
     p.drop_scale = p.drop_thr ? 65536.0f / (65536.0f - (float)p.drop_thr) : 1.0f;   // 1 / (1 - p) for the p actually realised
     p.seed = g.dropout_seed;
     p.seed_dev = g.dropout_seed_dev;
+    p.colsum_part = g.epilogue == HVS_GEMM_EPI_DGELU ? g.colsum_partials : nullptr;
     p.aux = reinterpret_cast<const __nv_bfloat16*>(g.aux); p.ld_aux = g.ld_aux;
     p.out2 = reinterpret_cast<__nv_bfloat16*>(g.out2); p.ldo2 = g.ldo2;
     p.a_mn = a_mn; p.b_mn = b_mn;
@@ -731,11 +808,37 @@ extern "C" int hvs_reduce_partials(const float* partials, int splits, int64_t sp
     if (numel % 4 || split_stride % 4) return HVS_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(out)) & 15) return HVS_ERR_ALIGNMENT;
     const int64_t n4 = numel / 4;
-    int64_t blocks = (n4 * 8 + 255) / 256;
+    const bool many = splits >= 16;                           // eight lanes per output only pay when there are splits to share
+    int64_t blocks = ((many ? n4 * 8 : n4) + 255) / 256;
     if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-    reduce_partials_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(partials), splits, split_stride / 4, n4,
-                                                            reinterpret_cast<float4*>(out));
+    if (many)
+        reduce_partials_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(partials), splits, split_stride / 4, n4,
+                                                                reinterpret_cast<float4*>(out));
+    else
+        reduce_partials_few_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(partials), splits, split_stride / 4, n4,
+                                                                    reinterpret_cast<float4*>(out));
     count_launch();
+    return launch_status();
+}
+
+extern "C" size_t hvs_colsum_f32_workspace(int64_t rows, int cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    const int64_t rpb = hvs::colsum_f32_rows_per_block(rows);
+    return (size_t)((rows + rpb - 1) / rpb) * (size_t)cols * 4;
+}
+
+extern "C" int hvs_colsum_f32(const float* x, int64_t rows, int cols, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (rows < 0 || cols <= 0 || !out) return HVS_ERR_BAD_ARG;
+    if (rows == 0) { HVS_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)cols * 4, stream)); return HVS_OK; }
+    if (!x || !workspace) return HVS_ERR_BAD_ARG;
+    if (workspace_bytes < hvs_colsum_f32_workspace(rows, cols)) return HVS_ERR_WORKSPACE;
+    const int64_t rpb = colsum_f32_rows_per_block(rows);
+    const int nblk = (int)((rows + rpb - 1) / rpb);
+    colsum_f32_partial_kernel<<<dim3((cols + 31) / 32, nblk), 256, 0, stream>>>(x, rows, cols, rpb, reinterpret_cast<float*>(workspace));
+    colsum_final_kernel<<<(cols + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const float*>(workspace), nblk, cols, out);
+    count_launch(2);
     return launch_status();
 }
 

@@ -453,8 +453,8 @@ class _K2TokenPathFn(torch.autograd.Function):
     """Training form of the module's token path (manifold_layers.py:248-267) on this library's kernels: the forward is
     LayerNorm -> four tcgen05 GEMM launches (bias + GELU + dropout epilogues that also keep the pre-activations) ->
     LayerNorm; the backward is the two LayerNorm backward kernels, five data-gradient GEMMs (GELU' x dropout mask in the
-    epilogue; the weights are read as they lie, MN-major), five weight-gradient GEMMs over the token axis (both
-    activations MN-major, split-K with a fixed-order reduction) and two column-sum kernels for the bias gradients.
+    epilogue, which also sums the bias gradients per 32-row group; the weights are read as they lie, MN-major) and five
+    weight-gradient GEMMs over the token axis (both activations MN-major, split-K with a fixed-order reduction).
     bf16 operands, fp32 accumulation, bf16 activations between the GEMMs: the reference's own CUDA-autocast arithmetic."""
 
     @staticmethod
@@ -495,14 +495,14 @@ class _K2TokenPathFn(torch.autograd.Function):
         if dout.dtype not in (torch.float32, torch.bfloat16):
             dout = dout.float()
         d_pre, dg_post, dbe_post = ops.layernorm_bwd(pre, g_post.detach(), dout.contiguous(), mod.norm_post.eps)       # bf16 [T, D]
-        dz2 = ops.gemm_bf16_ex(d_pre, st.h_post_t, b_mn=True, epilogue=dge, aux=z2, dropout_p=p, dropout_seed=seed2, dropout_seed_dev=sdev)   # [T, H]
+        dz2, d_b2 = ops.gemm_bf16_ex(d_pre, st.h_post_t, b_mn=True, epilogue=dge, aux=z2, dropout_p=p, dropout_seed=seed2,
+                                     dropout_seed_dev=sdev, want_colsum=True)                                                 # [T, H], [H]
         dx_res = ops.gemm_bf16_ex(d_pre, st.h_res_t, b_mn=True)                                                        # [T, D]
         d_h_post = ops.gemm_wgrad(a2, d_pre)                                                                           # [H, D]
         d_h_res = ops.gemm_wgrad(xb, d_pre)                                                                            # [D, D]
-        d_b2 = ops.colsum_bf16(dz2)
         d_w2 = ops.gemm_wgrad(dz2, a1)                                                                                 # [H, 2H]
-        dz1 = ops.gemm_bf16_ex(dz2, w2b, b_mn=True, epilogue=dge, aux=z1, dropout_p=p, dropout_seed=seed1, dropout_seed_dev=sdev)             # [T, 2H]
-        d_b1 = ops.colsum_bf16(dz1)
+        dz1, d_b1 = ops.gemm_bf16_ex(dz2, w2b, b_mn=True, epilogue=dge, aux=z1, dropout_p=p, dropout_seed=seed1,
+                                     dropout_seed_dev=sdev, want_colsum=True)                                                 # [T, 2H], [2H]
         d_w1 = ops.gemm_wgrad(dz1, h0)                                                                                 # [2H, H]
         dh0 = ops.gemm_bf16_ex(dz1, w1b, b_mn=True)                                                                    # [T, H]
         d_h_pre = ops.gemm_wgrad(xn, dh0)                                                                              # [D, H]

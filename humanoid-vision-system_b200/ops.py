@@ -361,10 +361,12 @@ def _check_bf16_2d(*tensors):
 @_on_device
 def gemm_bf16_ex(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
                  epilogue: int = _lib.HVS_GEMM_EPI_NONE, aux: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
-                 dropout_p: float = 0.0, dropout_seed: int = 0, dropout_seed_dev: Optional[torch.Tensor] = None):
+                 dropout_p: float = 0.0, dropout_seed: int = 0, dropout_seed_dev: Optional[torch.Tensor] = None,
+                 want_colsum: bool = False):
     """The training form of the K2 GEMM kernel (hvs_gemm_bf16_ex):  out[M, N] = epilogue(op(a) op(b)^T).
     a_mn / b_mn: the operand is given as its transpose in place ([K, M] / [K, N] row-major).
-    HVS_GEMM_EPI_BIAS_GELU_SAVE returns (out, z); every other epilogue returns out."""
+    HVS_GEMM_EPI_BIAS_GELU_SAVE returns (out, z); HVS_GEMM_EPI_DGELU with want_colsum returns (out, column sums of out [N] fp32:
+    the bias gradient, summed in the epilogue per 32-row group and finished by hvs_colsum_f32); else out."""
     _need_cuda(a, b, bias, aux)
     _check_bf16_2d(a, b, aux)
     k, m = (a.shape[0], a.shape[1]) if a_mn else (a.shape[1], a.shape[0])
@@ -390,7 +392,20 @@ def gemm_bf16_ex(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: boo
             raise _lib.HvsError("dropout_seed_dev must be an int32 / int64 device tensor")
         g.dropout_seed_dev = _ptr(dropout_seed_dev)
     g.split_k = 1
-    check(_lib.load().hvs_gemm_bf16_ex(ctypes.byref(g), _stream()), "hvs_gemm_bf16_ex")
+    part = None
+    if want_colsum:
+        if epilogue != _lib.HVS_GEMM_EPI_DGELU:
+            raise _lib.HvsError("want_colsum goes with HVS_GEMM_EPI_DGELU")
+        part = torch.empty((4 * ((m + 127) // 128), n), dtype=torch.float32, device=a.device)
+        g.colsum_partials = _ptr(part)
+    lib = _lib.load()
+    check(lib.hvs_gemm_bf16_ex(ctypes.byref(g), _stream()), "hvs_gemm_bf16_ex")
+    if part is not None:
+        db = torch.empty(n, dtype=torch.float32, device=a.device)
+        nb = int(lib.hvs_colsum_f32_workspace(part.shape[0], n))
+        ws = torch.empty(max(nb, 256), dtype=torch.uint8, device=a.device)
+        check(lib.hvs_colsum_f32(_ptr(part), part.shape[0], n, _ptr(db), _ptr(ws), ws.numel(), _stream()), "hvs_colsum_f32")
+        return out, db
     return (out, z) if z is not None else out
 
 

@@ -263,11 +263,17 @@ typedef struct hvs_gemm_args {
     int split_k; int64_t split_stride;
     const uint32_t* dropout_seed_dev;   /* optional: a DEVICE word mixed into dropout_seed when the kernel runs (a step counter
                                            advanced on the device, so a captured CUDA graph draws a new mask every replay) */
+    float* colsum_partials;             /* optional, HVS_GEMM_EPI_DGELU: [4 * ceil(M / 128), N] fp32, row 4 * (m / 128) + (m % 128) / 32 =
+                                           the column sums of the (bf16) output over that group of 32 rows -- nn.Linear's bias gradient
+                                           is hvs_colsum_f32 of it: no second pass over d z */
 } hvs_gemm_args;
 int hvs_gemm_bf16_ex(const hvs_gemm_args* args, void* stream);
 int hvs_gemm_choose_split(int64_t M, int N, int64_t K);
 /* out[i] = sum over s < splits of partials[s * split_stride + i], i < numel, in that order (numel, stride multiples of 4). */
 int hvs_reduce_partials(const float* partials, int splits, int64_t split_stride, int64_t numel, float* out, void* stream);
+/* out[c] = sum over rows of x[r, c] for a contiguous fp32 [rows, cols] matrix (the colsum_partials above), fixed order. */
+size_t hvs_colsum_f32_workspace(int64_t rows, int cols);
+int hvs_colsum_f32(const float* x, int64_t rows, int cols, float* out, void* workspace, size_t workspace_bytes, void* stream);
 /* out[c] = sum over rows of x[r, c], x bf16 [rows, cols] with row stride ld (bias gradients: nn.Linear's db = sum_t dz). */
 size_t hvs_colsum_bf16_workspace(int64_t rows, int cols);
 int hvs_colsum_bf16(const void* x, int64_t ld, int64_t rows, int cols, float* out, void* workspace, size_t workspace_bytes, void* stream);

@@ -104,6 +104,14 @@ def test_gelu_save_and_dgelu_epilogues_without_dropout():
     torch.nn.functional.gelu(zz).backward(dz2.double() @ w2.double())
     mag = (dz2.double().abs() @ w2.double().abs()) * 1.2
     assert ((got.cpu().double() - zz.grad).abs() <= 2.0 ** -8 * mag + 1e-6).all()
+    # the same launch can also produce the bias gradient: column sums of the bf16 output, summed per 32-row group in the
+    # epilogue (transpose-reduce by shuffles) and finished by hvs_colsum_f32 -- no second pass over d z
+    got2, db = hvs_b200.ops.gemm_bf16_ex(dz2.to(DEV), w2.to(DEV), b_mn=True, epilogue=_lib.HVS_GEMM_EPI_DGELU, aux=z, want_colsum=True)
+    assert torch.equal(got2, got)
+    want_db = got.double().sum(0).cpu()
+    assert ((db.cpu().double() - want_db).abs() <= 1e-5 * got.double().abs().sum(0).cpu() + 1e-6).all()
+    _, db_again = hvs_b200.ops.gemm_bf16_ex(dz2.to(DEV), w2.to(DEV), b_mn=True, epilogue=_lib.HVS_GEMM_EPI_DGELU, aux=z, want_colsum=True)
+    assert torch.equal(db, db_again)
 
 
 def test_dropout_mask_is_reproducible_unbiased_and_shared_by_forward_and_backward():
@@ -314,3 +322,17 @@ def test_signal_ratio_monitor_kernel(rows, dim, dts):
     hist2 = torch.zeros(1, device=DEV)
     hvs_b200.ops.signal_ratio(out.to(DEV), x.to(DEV), hist2)
     assert hist2.item() == got[2].item()                                # fixed-order reduction
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 32, 64), (129, 64, 32), (4099, 256, 128), (70000, 128, 32)])
+def test_bias_gradient_from_the_data_gradient_epilogue(m, n, k):
+    import hvs_b200
+    from hvs_b200 import _lib
+    a = _rand(m, k, seed=41).to(BF)
+    w = (_rand(k, n, seed=42) * 0.3).to(BF)
+    z = _rand(m, n, seed=43).to(BF)
+    out, db = hvs_b200.ops.gemm_bf16_ex(a.to(DEV), w.to(DEV), b_mn=True, epilogue=_lib.HVS_GEMM_EPI_DGELU, aux=z.to(DEV), dropout_p=0.1,
+                                        dropout_seed=7, want_colsum=True)
+    want = out.double().sum(0)
+    assert ((db.double() - want).abs() <= 1e-5 * out.double().abs().sum(0) + 1e-6).all()
+    assert torch.equal(hvs_b200.ops.colsum_bf16(out), hvs_b200.ops.colsum_bf16(out)) and (hvs_b200.ops.colsum_bf16(out).double() - want).abs().max() <= 1e-4 * out.double().abs().sum(0).max()
