@@ -643,11 +643,12 @@ mhc_stream_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 if (wtid == 0) HVS_TR(k, 7);
                 const uint32_t sb = stage0 + s * kStageBytes;
                 uint8_t* wrec = smem + kOffWrec + s * kWrecBytes;
+                const int eidx = wtid;                          // (spreading the 192 elements over all 16 warps, 12 lanes each: +1 %)
                 if (wtid < kTok * kL) {
-                    // e = alpha_g * inv_rms * d logit of (token, logit) = (tid / 24, tid % 24): bf16 hi for the W e MMA,
+                    // e = alpha_g * inv_rms * d logit of (token, logit) = (idx / 24, idx % 24): bf16 hi for the W e MMA,
                     // hi and lo into the E tile of the dW MMA (rows = logits, K = token | 8 + token); dbias in registers
-                    const int etok = wtid / kL, er = wtid - etok * kL;
-                    const float dlv = reinterpret_cast<const float*>(smem + kOffDl + s * kDlBytes)[wtid];
+                    const int etok = eidx / kL, er = eidx - etok * kL;
+                    const float dlv = reinterpret_cast<const float*>(smem + kOffDl + s * kDlBytes)[eidx];
                     const float e = dlv * reinterpret_cast<const float*>(wrec + kWrecS)[etok * 3 + (er < kN ? 0 : er < 2 * kN ? 1 : 2)];
                     acc_db += dlv;
                     const __nv_bfloat16 hi = __float2bfloat16_rn(e);

@@ -390,7 +390,8 @@ mhc_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             }
             ssa += __shfl_xor_sync(0xffffffffu, ssa, 1); ssa += __shfl_xor_sync(0xffffffffu, ssa, 2);
             ssb += __shfl_xor_sync(0xffffffffu, ssb, 1); ssb += __shfl_xor_sync(0xffffffffu, ssb, 2);
-            bar_sync(kBarW1, kWorkerThreads);     // previous tile's cross-warp reduction has read `part`
+            bar_sync(kBarW1, kWorkerThreads);     // previous tile's cross-warp reduction has read `part` (dropping it where the
+                                                  // kBarCoef barrier of mix_tile already orders the two measured no gain)
             {
                 float* pa = part + (w * kTileTok + g) * kPartStride;
                 float* pb = pa + 8 * kPartStride;
