@@ -58,7 +58,7 @@ def launch_list(csv_path, out_name):
         t = tot.setdefault(name, [0, 0.0])
         t[0] += 1; t[1] += val * scale
     total = sum(v[1] for v in tot.values())
-    lines = ["# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 3 --warmup 3 --e2e-steps 1 --no-cpu-baseline",
+    lines = ["# ncu --metrics gpu__time_duration.sum --clock-control none [-c 600]  python bench.py --steps K --warmup 3 --e2e-steps 1 --no-cpu-baseline [--skip-hybrid]",
              "# (every launch of the command incl. input generation, warm-up and the e2e leg; compare SHARES, not absolutes)",
              f"{'kernel':62s} {'launches':>8s} {'total_us':>12s} {'share':>7s}"]
     for k, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
@@ -103,9 +103,10 @@ if __name__ == "__main__":
                 def gb(k):
                     v, u = d[k]
                     return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
-                traffic[short + "_bytes_per_launch"] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+                import re
+                traffic[re.sub(r"<[^>]*>", "", short) + "_bytes_per_launch"] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
     if traffic:
-        traffic["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, T=2^20 (profiles/r01h_bench_kernels_T1M.txt)"
+        traffic["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, T=2^20 (profiles/r02_bench_kernels_T1M.txt, the default <kAdaptive = false> instantiations)"
         json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
     if os.path.exists(os.path.join(g, "r1_launches.csv")):
         launch_list(os.path.join(g, "r1_launches.csv"), "r01_launch_list.txt")
