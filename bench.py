@@ -28,6 +28,10 @@ hybrid_vision  the other half of BASELINE.json's metric ("hybrid_vision img/s at
              inference sharded 64/N with no collective, configs[3] bf16 DDP training at 16 images / GPU (gradient
              all-reduce over NCCL), configs[4] streaming batch-1 p50 / p99 under a CUDA graph; configs[0] (the CPU
              forward) is its cpu_baseline.  --skip-hybrid / --skip-extras leave these legs out
+adaptive_sinkhorn  the same K1 step with the OPT-IN HVS_MHC_ADAPTIVE_ITERS flag (Sinkhorn loops stop at convergence to 2^-20;
+             results within 2e-6 of the full run) -- reported next to the headline, which runs all 20 iterations
+             hybrid_vision.training runs the whole optimisation step (DDP all-reduces included) as ONE CUDA graph replay
+             (--train-eager for the eager step); all 76 mHC layers train on this library's forward and backward kernels
 clocks       SM clock and throttle reasons sampled through NVML every 2 ms inside the timed region
 --impl reference   times that CPU implementation alone (the reference is pure PyTorch; its own modules
              cannot travel to the GPU box)

@@ -54,3 +54,19 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_host_side_planning_functions_need_no_gpu():
+    """Size / plan helpers of the C ABI are pure host code: callable here (no compute launch)."""
+    import hvs_b200
+    lib = hvs_b200.load_library()
+    assert lib.hvs_gemm_choose_split(4096, 2048, 25600) <= 4               # enough output tiles: the token axis is not cut
+    s = lib.hvs_gemm_choose_split(256, 128, 409600)
+    assert 64 <= s <= 256                                                  # two tiles: split-K feeds the SMs
+    assert lib.hvs_gemm_choose_split(32, 32, 64) == 1
+    assert lib.hvs_colsum_bf16_workspace(0, 64) == 0 and lib.hvs_colsum_bf16_workspace(100000, 256) >= 256 * 4
+    assert lib.hvs_colsum_f32_workspace(51200, 256) >= 256 * 4
+    assert lib.hvs_signal_ratio_workspace(1000) >= 8
+    assert lib.hvs_layernorm_bwd_workspace(6400, 1024) > lib.hvs_layernorm_bwd_workspace(6400, 512) > 0
+    assert lib.hvs_mhc_stream_bwd_workspace(1000, 2, 256) > 0 and lib.hvs_mhc_stream_bwd_workspace(1000, 3, 256) == 0
+    assert lib.hvs_mhc_stream_bwd_saved_workspace(1000, 4, 512) > 0 and lib.hvs_mhc_stream_bwd_saved_workspace(1000, 2, 256) == 0
