@@ -156,6 +156,152 @@ __global__ void __launch_bounds__(256) decode_four_cells_per_thread(const Decode
     }
 }
 
+// The same mapping when the caller does not ask for the [cells, C] score tensor (the detection path never does): the
+// decoder's outputs then need ONE class score per cell, the first maximum of obj * sigmoid(logit).  decode_four_cells_per_thread
+// evaluates expf + an IEEE division for all C classes (30 instructions per logit: the kernel ran at 60 % issue and
+// 21 % of the HBM roofline).  sigmoid is increasing, so the winner is found on the logits (max, its first index, the
+// largest DIFFERENT logit below it: ~10 instructions per logit) and only the winner's score is evaluated -- with the
+// same sigmoidf_rn on the same input, so the score is bit-identical.  The index is identical too whenever no other
+// class can tie the winner after rounding:
+//     (1 - sigmoid(m)) (m - z) >= 2^-19  =>  sigmoid(z) <= sigmoid(m) (1 - 2^-19)    [d ln sigmoid = (1 - sigmoid) dz, decreasing]
+// against 3 ulp of error in each computed sigmoid and 1/2 ulp in each product: strictly ordered scores.  Cells where
+// that margin fails (saturated sigmoids: logits > 12), with a NaN anywhere, or with a winner score below 1e-30
+// (products rounding into the denormals) take the reference loop of decode_four_cells_per_thread for that cell.
+// Equal logits give equal scores and the first index in both forms.
+template <typename T>
+__device__ __noinline__ void decode_cell_reference_loop(const T* class_logits, int64_t class_stride, int C, float obj,
+                                                        float* score_out, int64_t* idx_out) {
+    float best = -INFINITY;
+    int besti = 0;
+    for (int c = 0; c < C; ++c) {
+        const float sc = obj * sigmoidf_rn(to_f32(class_logits[(int64_t)c * class_stride]));
+        if (c == 0 || sc > best) { best = sc; besti = c; }
+    }
+    *score_out = best;
+    *idx_out = besti;
+}
+
+// 16-bit inputs keep the search in the packed domain: two cells per instruction (HMNMX2 / HSET2 + LOP3), no unpacking --
+// 3.5 instructions per logit.  m is carried with the NaN-propagating maximum, so a NaN logit marks its own cell.
+template <typename T> struct Packed2;
+template <> struct Packed2<__nv_bfloat16> { typedef __nv_bfloat162 type; static constexpr uint32_t kNegInf = 0xFF80FF80u; };
+template <> struct Packed2<__half> { typedef __half2 type; static constexpr uint32_t kNegInf = 0xFC00FC00u; };
+template <> struct Packed2<float> { typedef float type; static constexpr uint32_t kNegInf = 0u; };     // (unused)
+template <typename H2> __device__ __forceinline__ H2 as_h2(uint32_t v) { return *reinterpret_cast<H2*>(&v); }
+template <typename H2> __device__ __forceinline__ uint32_t as_u32(H2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+template <typename H2>
+__device__ __forceinline__ void first_max_step2(uint32_t& m, uint32_t& m2, uint32_t& bi, uint32_t v, uint32_t cidx2) {
+    const H2 hv = as_h2<H2>(v), hm = as_h2<H2>(m);
+    const uint32_t ne = __hne2_mask(hv, hm), gt = __hgt2_mask(hv, hm);
+    const uint32_t m2c = as_u32(__hmax2(as_h2<H2>(m2), __hmin2(hm, hv)));
+    m2 = (m2c & ne) | (m2 & ~ne);
+    bi = (cidx2 & gt) | (bi & ~gt);
+    m = as_u32(__hmax2_nan(hm, hv));
+}
+template <typename T> __device__ __forceinline__ float half_to_f32(uint32_t bits16);
+template <> __device__ __forceinline__ float half_to_f32<__nv_bfloat16>(uint32_t b) { return __uint_as_float(b << 16); }
+template <> __device__ __forceinline__ float half_to_f32<__half>(uint32_t b) { return __half2float(__ushort_as_half((unsigned short)b)); }
+template <> __device__ __forceinline__ float half_to_f32<float>(uint32_t b) { return 0.f; }            // (unused)
+
+template <typename T>
+__global__ void __launch_bounds__(256) decode_four_cells_first_max(const DecodeParams p) {
+    typedef typename Vec4<T>::type V;
+    constexpr int kU = 16;                                          // independent loads in flight per thread
+    const int wq = p.W >> 2;
+    const int64_t nquad = (int64_t)p.B * p.A * p.H * wq;
+    const T* base = reinterpret_cast<const T*>(p.pred);
+    for (int64_t quad = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; quad < nquad; quad += (int64_t)gridDim.x * blockDim.x) {
+        const int w0 = (int)(quad % wq) << 2;
+        int64_t r = quad / wq;
+        const int h = (int)(r % p.H); r /= p.H;
+        const int a = (int)(r % p.A);
+        const int b = (int)(r / p.A);
+        const T* q = base + b * p.s[0] + a * p.s[1] + h * p.s[2] + w0;
+        const int64_t cell0 = (((int64_t)b * p.A + a) * p.H + h) * p.W + w0;
+        V head[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) head[k] = *reinterpret_cast<const V*>(q + k * p.s[4]);
+        const T* qc = q + 5 * p.s[4];
+        float m[4], m2[4];
+        int bi[4];
+        bool bad = false;                                           // fp32 inputs: a NaN logit in any of the four cells
+        if constexpr (sizeof(T) == 2) {
+            typedef typename Packed2<T>::type H2;
+            const V v0 = *reinterpret_cast<const V*>(qc);
+            uint32_t pm[2] = {v0.x, v0.y}, pm2[2] = {Packed2<T>::kNegInf, Packed2<T>::kNegInf}, pbi[2] = {0u, 0u};
+            // always whole groups of kU independent loads: past the last class the index is clamped, and seeing a class twice
+            // changes nothing (it is neither above the maximum nor a new value below it)
+            for (int c = 1; c < p.C; c += kU) {
+                V v[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) v[u] = *reinterpret_cast<const V*>(qc + (int64_t)min(c + u, p.C - 1) * p.s[4]);
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const uint32_t cidx2 = (uint32_t)min(c + u, p.C - 1) * 0x00010001u;
+                    first_max_step2<H2>(pm[0], pm2[0], pbi[0], v[u].x, cidx2);
+                    first_max_step2<H2>(pm[1], pm2[1], pbi[1], v[u].y, cidx2);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int sh = 16 * (j & 1);
+                m[j] = half_to_f32<T>((pm[j >> 1] >> sh) & 0xffffu);      // NaN if the cell had a NaN logit: fails every test below
+                m2[j] = half_to_f32<T>((pm2[j >> 1] >> sh) & 0xffffu);
+                bi[j] = (int)((pbi[j >> 1] >> sh) & 0xffffu);
+            }
+        } else {
+            {
+                float f[4];
+                unpack4<T>(*reinterpret_cast<const V*>(qc), f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { m[j] = f[j]; m2[j] = -INFINITY; bi[j] = 0; bad |= f[j] != f[j]; }
+            }
+            for (int c = 1; c < p.C; c += kU) {
+                V v[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) v[u] = *reinterpret_cast<const V*>(qc + (int64_t)min(c + u, p.C - 1) * p.s[4]);
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    float f[4];
+                    unpack4<T>(v[u], f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float z = f[j];
+                        bad |= z != z;
+                        m2[j] = z != m[j] ? fmaxf(m2[j], fminf(m[j], z)) : m2[j];
+                        bi[j] = z > m[j] ? min(c + u, p.C - 1) : bi[j];
+                        m[j] = fmaxf(m[j], z);
+                    }
+                }
+            }
+        }
+        float t[5][4];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) unpack4<T>(head[k], t[k]);
+        float obj[4], best[4];
+        bool slow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            write_box(p, cell0 + j, a, h, w0 + j, t[0][j], t[1][j], t[2][j], t[3][j]);
+            obj[j] = sigmoidf_rn(t[4][j]);
+            best[j] = obj[j] * sigmoidf_rn(m[j]);
+            // (1 - sigmoid(m)) (m - m2) >= 2^-19 with 1 / (1 - sigmoid(m)) = 1 + e^m; every comparison is false for a NaN
+            const float margin = 1.9073486328125e-06f * (1.0f + expf(m[j]));
+            slow[j] = bad || !(margin <= 3.0e38f) || !(m[j] - m2[j] >= margin) || !(best[j] >= 1e-30f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (slow[j]) {
+                decode_cell_reference_loop<T>(qc + j, p.s[4], p.C, obj[j], p.class_scores + cell0 + j, p.class_idx + cell0 + j);
+            } else {
+                p.class_scores[cell0 + j] = best[j];
+                p.class_idx[cell0 + j] = bi[j];
+            }
+        }
+        if (p.objectness != nullptr) *reinterpret_cast<float4*>(p.objectness + cell0) = make_float4(obj[0], obj[1], obj[2], obj[3]);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) decode_cell_per_warp(const DecodeParams p) {
     const int64_t ncell = (int64_t)p.B * p.A * p.H * p.W;
@@ -214,7 +360,10 @@ int launch_decode(const DecodeParams& p, cudaStream_t stream) {
     } else if (vec_ok) {
         int64_t blocks = (ncell / 4 + 255) / 256;
         if (blocks > cap) blocks = cap;
-        decode_four_cells_per_thread<T><<<(int)blocks, 256, 0, stream>>>(p);
+        // (first-maximum kernel: one block per 1024 cells, no grid cap -- with the cap at 8 blocks per SM and 4 resident the
+        //  batch-64 80x80 grid ran as two waves plus a 16-block third)
+        if (p.scores == nullptr) decode_four_cells_first_max<T><<<(unsigned)((ncell / 4 + 255) / 256), 256, 0, stream>>>(p);
+        else decode_four_cells_per_thread<T><<<(int)blocks, 256, 0, stream>>>(p);
     } else {
         int64_t blocks = (ncell + 255) / 256;
         if (blocks > cap) blocks = cap;

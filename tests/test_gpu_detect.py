@@ -40,6 +40,10 @@ def test_decode_golden_and_layouts(golden):
             assert torch.equal(out["class_indices"].cpu(), torch.from_numpy(g[f"s{s}/class_indices"]))
             ref = detect_ref.yolo_decode(pred.cpu(), awh.cpu())
             assert torch.allclose(out["scores"].cpu(), ref["scores"], rtol=2e-6, atol=1e-8)
+            # the detection path's call (no [cells, C] score tensor: the first-maximum kernel on the strided view)
+            lean = hvs_b200.ops.yolo_decode(p, awh)
+            for k in ("boxes", "class_scores", "class_indices", "objectness"):
+                assert torch.equal(lean[k], out[k]), k
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
@@ -52,6 +56,49 @@ def test_decode_half_inputs(dtype):
     ref = detect_ref.yolo_decode(pred, awh)
     assert torch.allclose(out["boxes"].cpu(), ref["boxes"], rtol=2e-6, atol=2e-7)
     assert torch.allclose(out["class_scores"].cpu(), ref["class_scores"], rtol=2e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_decode_first_maximum_kernel_is_bit_identical_to_the_all_scores_kernel(dtype):
+    """decode_four_cells_first_max finds the winning class on the logits and evaluates one sigmoid per cell; the
+    reference (yolo_head.py:282-285) takes max / first argmax over all obj * sigmoid(cls).  Same bits, same indices --
+    on random logits and on the cases where rounding makes scores tie although the logits differ: saturated sigmoids,
+    logits a few ulp apart, duplicates of the maximum, objectness so small that products fall into the denormals,
+    NaN / +-inf logits."""
+    import hvs_b200
+    g = torch.Generator().manual_seed(11)
+    b, a, h, w, c = 3, 3, 12, 16, 80
+    pred = torch.randn(b, a, 5 + c, h, w, generator=g) * 2.0
+    cls = pred[:, :, 5:]
+    # cls[b, a, :, row] is the [C, W] slab of one grid row
+    cls[0, 0, :, 0] = 15.0 + torch.randn(c, w, generator=g) * 4.0                        # saturated: ties between different logits
+    cls[0, 1, :, 1] = 1.0 + torch.randint(0, 4, (c, w), generator=g) * 2.0 ** -20        # a few fp32 ulp apart
+    cls[0, 2, :, 2] = torch.randint(-2, 3, (c, w), generator=g).float()                  # many duplicates of the maximum
+    cls[1, 0, :, 3] = 0.0
+    cls[1, 1, :, 4] = -95.0 + torch.randn(c, w, generator=g)                             # sigmoid in the denormals
+    pred[1, 2, 4, 5] = -80.0                                                             # objectness ~ 1e-35: products underflow
+    pred[1, 2, 4, 6] = -110.0                                                            # objectness 0: every score 0, index 0
+    cls[2, 0, 7, 7] = float("nan")
+    cls[2, 0, 0, 8] = float("nan")                                                       # NaN in class 0 wins (c == 0 is taken unseen)
+    pred[2, 1, 4, 9] = float("nan")                                                      # NaN objectness
+    cls[2, 1, 9, 10] = float("inf")
+    cls[2, 1, 3, 10] = 60.0                                                              # sigmoid(60) == sigmoid(inf) == 1: first index wins
+    cls[2, 2, :, 11] = float("-inf")
+    cls[2, 2, 5, 0] = float("-inf")
+    cls[2, 0, :, 9] = 100.0 * torch.randn(c, w, generator=g)
+    pred = pred.to(dtype).cuda()
+    view = pred.permute(0, 1, 3, 4, 2)                                                   # [B,A,H,W,85], channel stride H*W
+    awh = detect_ref.anchors_wh(1).cuda()
+    full = hvs_b200.ops.yolo_decode(view, awh, want_scores=True)
+    lean = hvs_b200.ops.yolo_decode(view, awh)
+    assert torch.equal(lean["class_indices"], full["class_indices"])
+    assert torch.equal(lean["class_scores"].view(torch.int32), full["class_scores"].view(torch.int32))
+    assert torch.equal(lean["boxes"].view(torch.int32), full["boxes"].view(torch.int32))
+    assert torch.equal(lean["objectness"].view(torch.int32), full["objectness"].view(torch.int32))
+    # and the all-scores kernel is the reference rule: max / first argmax of its own score tensor
+    sc = full["scores"]
+    finite = ~sc.isnan().any(-1)
+    assert torch.equal(full["class_scores"][finite], sc.max(-1).values[finite])
 
 
 def test_nms_golden_bit_exact(golden):
