@@ -51,6 +51,13 @@ class GradTensor(ctypes.Structure):
     _fields_ = [("grad", c_void_p), ("numel", c_int64), ("group", c_int32), ("reserved", c_int32)]
 
 
+class DecodeScale(ctypes.Structure):
+    """struct hvs_decode_scale."""
+    _fields_ = [("pred", c_void_p), ("pred_stride", c_int64 * 5), ("anchor_wh", c_void_p), ("boxes", c_void_p),
+                ("class_scores", c_void_p), ("class_idx", c_void_p), ("objectness", c_void_p),
+                ("A", c_int), ("H", c_int), ("W", c_int)]
+
+
 class CoeffGrad(ctypes.Structure):
     """struct hvs_coeff_grad."""
     _fields_ = [("d_h_pre", c_void_p), ("d_h_post", c_void_p), ("d_h_res", c_void_p),
@@ -118,6 +125,7 @@ _SIGNATURES = {
                                   POINTER(c_float), POINTER(c_float), c_void_p]),
     "hvs_yolo_decode": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "hvs_yolo_decode_scales": (c_int, [POINTER(DecodeScale), c_int, c_int, c_int, c_int, c_void_p]),
     "hvs_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_int, c_int,
                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "hvs_post_process_workspace": (c_size_t, [c_int, c_int, c_int]),

@@ -204,13 +204,12 @@ template <> __device__ __forceinline__ float half_to_f32<__half>(uint32_t b) { r
 template <> __device__ __forceinline__ float half_to_f32<float>(uint32_t b) { return 0.f; }            // (unused)
 
 template <typename T>
-__global__ void __launch_bounds__(256) decode_four_cells_first_max(const DecodeParams p) {
+__device__ __forceinline__ void first_max_quad(const DecodeParams& p, int64_t quad) {
     typedef typename Vec4<T>::type V;
     constexpr int kU = 16;                                          // independent loads in flight per thread
     const int wq = p.W >> 2;
-    const int64_t nquad = (int64_t)p.B * p.A * p.H * wq;
     const T* base = reinterpret_cast<const T*>(p.pred);
-    for (int64_t quad = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; quad < nquad; quad += (int64_t)gridDim.x * blockDim.x) {
+    {
         const int w0 = (int)(quad % wq) << 2;
         int64_t r = quad / wq;
         const int h = (int)(r % p.H); r /= p.H;
@@ -303,6 +302,33 @@ __global__ void __launch_bounds__(256) decode_four_cells_first_max(const DecodeP
 }
 
 template <typename T>
+__global__ void __launch_bounds__(256) decode_four_cells_first_max(const __grid_constant__ DecodeParams p) {
+    const int64_t nquad = (int64_t)p.B * p.A * p.H * (p.W >> 2);
+    for (int64_t quad = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; quad < nquad; quad += (int64_t)gridDim.x * blockDim.x)
+        first_max_quad<T>(p, quad);
+}
+
+// Every scale of the head in ONE launch (hvs_yolo_decode_scales): the 40x40 and 20x20 grids of a batch are 0.5 and 0.13
+// waves of their own -- latency-bound launches of 20 us each next to 50 us for the 80x80 grid; as the tail blocks of one
+// grid they overlap with it.  Blocks [first_block[k], first_block[k+1]) belong to scale k.
+constexpr int kMaxScales = 4;
+struct MultiDecodeParams {
+    DecodeParams s[kMaxScales];
+    unsigned first_block[kMaxScales + 1];
+    int n;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) decode_scales_first_max(const __grid_constant__ MultiDecodeParams mp) {
+    int k = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxScales; ++i) k += (i < mp.n && blockIdx.x >= mp.first_block[i]) ? 1 : 0;
+    const DecodeParams& p = mp.s[k];
+    const int64_t nquad = (int64_t)p.B * p.A * p.H * (p.W >> 2);
+    const int64_t quad = (int64_t)(blockIdx.x - mp.first_block[k]) * blockDim.x + threadIdx.x;
+    if (quad < nquad) first_max_quad<T>(p, quad);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) decode_cell_per_warp(const DecodeParams p) {
     const int64_t ncell = (int64_t)p.B * p.A * p.H * p.W;
     const T* base = reinterpret_cast<const T*>(p.pred);
@@ -345,13 +371,18 @@ __global__ void __launch_bounds__(256) decode_cell_per_warp(const DecodeParams p
 }
 
 template <typename T>
+bool four_cell_mapping_ok(const DecodeParams& p) {
+    const uintptr_t vec_bytes = 4 * sizeof(T);
+    return p.s[4] != 1 && p.s[3] == 1 && p.W % 4 == 0 && p.s[0] % 4 == 0 && p.s[1] % 4 == 0 && p.s[2] % 4 == 0 && p.s[4] % 4 == 0 &&
+           reinterpret_cast<uintptr_t>(p.pred) % vec_bytes == 0 && reinterpret_cast<uintptr_t>(p.class_scores) % 16 == 0 &&
+           (p.objectness == nullptr || reinterpret_cast<uintptr_t>(p.objectness) % 16 == 0);
+}
+
+template <typename T>
 int launch_decode(const DecodeParams& p, cudaStream_t stream) {
     const int64_t ncell = (int64_t)p.B * p.A * p.H * p.W;
     const int cap = sm_count() * 8;
-    const uintptr_t vec_bytes = 4 * sizeof(T);
-    const bool vec_ok = p.s[3] == 1 && p.W % 4 == 0 && p.s[0] % 4 == 0 && p.s[1] % 4 == 0 && p.s[2] % 4 == 0 && p.s[4] % 4 == 0 &&
-                        reinterpret_cast<uintptr_t>(p.pred) % vec_bytes == 0 && reinterpret_cast<uintptr_t>(p.class_scores) % 16 == 0 &&
-                        (p.objectness == nullptr || reinterpret_cast<uintptr_t>(p.objectness) % 16 == 0);
+    const bool vec_ok = four_cell_mapping_ok<T>(p);
     timer_begin(5, stream);
     if (p.s[4] == 1) {
         int64_t blocks = (ncell + 7) / 8;
@@ -362,7 +393,8 @@ int launch_decode(const DecodeParams& p, cudaStream_t stream) {
         if (blocks > cap) blocks = cap;
         // (first-maximum kernel: one block per 1024 cells, no grid cap -- with the cap at 8 blocks per SM and 4 resident the
         //  batch-64 80x80 grid ran as two waves plus a 16-block third)
-        if (p.scores == nullptr) decode_four_cells_first_max<T><<<(unsigned)((ncell / 4 + 255) / 256), 256, 0, stream>>>(p);
+        const int64_t all_blocks = (ncell / 4 + 255) / 256;      // (the kernel strides over the grid if this is ever clipped)
+        if (p.scores == nullptr) decode_four_cells_first_max<T><<<(unsigned)(all_blocks < 0x7fffffff ? all_blocks : 0x7fffffff), 256, 0, stream>>>(p);
         else decode_four_cells_per_thread<T><<<(int)blocks, 256, 0, stream>>>(p);
     } else {
         int64_t blocks = (ncell + 255) / 256;
@@ -374,8 +406,70 @@ int launch_decode(const DecodeParams& p, cudaStream_t stream) {
     return launch_status();
 }
 
+// all scales in one launch when every one of them takes the first-maximum mapping; otherwise scale by scale
+template <typename T>
+int launch_decode_scales(const DecodeParams* ps, int n, cudaStream_t stream) {
+    bool one_launch = n > 1 && n <= kMaxScales;
+    uint64_t blocks = 0;
+    for (int k = 0; k < n && one_launch; ++k) {
+        one_launch = ps[k].scores == nullptr && four_cell_mapping_ok<T>(ps[k]);
+        blocks += (uint64_t)(((int64_t)ps[k].B * ps[k].A * ps[k].H * ps[k].W / 4 + 255) / 256);
+    }
+    if (!one_launch || blocks >= 0x7fffffffull) {
+        for (int k = 0; k < n; ++k) {
+            const int rc = launch_decode<T>(ps[k], stream);
+            if (rc) return rc;
+        }
+        return HVS_OK;
+    }
+    MultiDecodeParams mp;
+    mp.n = n;
+    unsigned at = 0;
+    for (int k = 0; k < kMaxScales; ++k) {
+        mp.first_block[k] = at;
+        if (k < n) {
+            mp.s[k] = ps[k];
+            at += (unsigned)(((int64_t)ps[k].B * ps[k].A * ps[k].H * ps[k].W / 4 + 255) / 256);
+        } else {
+            mp.s[k] = ps[0];
+        }
+    }
+    mp.first_block[kMaxScales] = at;
+    timer_begin(5, stream);
+    decode_scales_first_max<T><<<at, 256, 0, stream>>>(mp);
+    timer_end(5, stream);
+    count_launch();
+    return launch_status();
+}
+
 }  // namespace
 }  // namespace hvs
+
+extern "C" int hvs_yolo_decode_scales(const hvs_decode_scale* scales_host, int n_scales, int pred_dtype, int B, int C, void* stream) {
+    using namespace hvs;
+    if (!scales_host || n_scales <= 0 || n_scales > 16) return HVS_ERR_BAD_ARG;
+    if (B < 0 || C <= 0) return HVS_ERR_BAD_ARG;
+    DecodeParams ps[16];
+    for (int k = 0; k < n_scales; ++k) {
+        const hvs_decode_scale& q = scales_host[k];
+        if (!q.pred || !q.anchor_wh || !q.boxes || !q.class_scores || !q.class_idx) return HVS_ERR_BAD_ARG;
+        if (q.A <= 0 || q.H <= 0 || q.W <= 0) return HVS_ERR_BAD_ARG;
+        if (reinterpret_cast<uintptr_t>(q.boxes) & 15) return HVS_ERR_ALIGNMENT;
+        DecodeParams& p = ps[k];
+        p.pred = q.pred;
+        for (int i = 0; i < 5; ++i) p.s[i] = q.pred_stride[i];
+        p.anchor_wh = q.anchor_wh; p.boxes = q.boxes; p.class_scores = q.class_scores; p.class_idx = q.class_idx;
+        p.objectness = q.objectness; p.scores = nullptr;
+        p.B = B; p.A = q.A; p.H = q.H; p.W = q.W; p.C = C;
+    }
+    if (B == 0) return HVS_OK;
+    switch (pred_dtype) {
+        case HVS_DTYPE_F32: return launch_decode_scales<float>(ps, n_scales, (cudaStream_t)stream);
+        case HVS_DTYPE_F16: return launch_decode_scales<__half>(ps, n_scales, (cudaStream_t)stream);
+        case HVS_DTYPE_BF16: return launch_decode_scales<__nv_bfloat16>(ps, n_scales, (cudaStream_t)stream);
+        default: return HVS_ERR_UNSUPPORTED;
+    }
+}
 
 extern "C" int hvs_yolo_decode(const void* pred, int pred_dtype, const int64_t* pred_stride_host, const float* anchor_wh,
                                float* boxes, float* class_scores, int64_t* class_idx, float* objectness, float* scores,

@@ -239,8 +239,21 @@ class YOLODetectionHead(nn.Module):
                 continue
             pred = self.pred_heads[i](features[key])
             predictions[f"scale_{i}"] = pred
-            with torch.no_grad():                       # decode is an inference product; the loss works on raw predictions
-                decoded[f"scale_{i}"] = self.decoder(pred.detach(), self.anchor_generator(i), pred.shape[2:4], want_scores=want_scores)
+        pending = [k for k in predictions if k not in decoded]
+        with torch.no_grad():                           # decode is an inference product; the loss works on raw predictions
+            if (not want_scores and len(pending) > 1 and all(predictions[k].is_cuda for k in pending)
+                    and len({(predictions[k].dtype, predictions[k].shape[0], predictions[k].shape[4]) for k in pending}) == 1):
+                # the decode loop of yolo_head.py:536-555 as one launch (the coarse grids are a fraction of a wave each)
+                preds = [predictions[k].detach() for k in pending]
+                awhs = [self.anchor_generator(int(k[6:])).reshape(p.shape[1], -1, 4)[:, 0, 2:4] for k, p in zip(pending, preds)]
+                for k, p, d in zip(pending, preds, ops.yolo_decode_scales(preds, awhs, want_objectness=True)):
+                    d["raw_predictions"] = p
+                    decoded[k] = d
+            else:
+                for k in pending:
+                    pred = predictions[k]
+                    decoded[k] = self.decoder(pred.detach(), self.anchor_generator(int(k[6:])), pred.shape[2:4], want_scores=want_scores)
+        decoded = {k: decoded[k] for k in sorted(decoded)}
         out = {"predictions": predictions, "decoded": decoded}
         if compute_loss and targets is not None:
             out["loss"] = self.loss_fn(predictions, targets)

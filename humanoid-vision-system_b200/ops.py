@@ -612,6 +612,43 @@ def yolo_decode(pred: torch.Tensor, anchor_wh: torch.Tensor, want_scores: bool =
     return out
 
 
+def yolo_decode_scales(preds: Sequence[torch.Tensor], anchor_whs: Sequence[torch.Tensor],
+                       want_objectness: bool = True) -> List[Dict[str, torch.Tensor]]:
+    """Every scale of the head in one launch (hvs_yolo_decode_scales): preds[k] [B,A_k,H_k,W_k,5+C] (any strides, one dtype,
+    one B and C), anchor_whs[k] [A_k,2].  Outputs per scale as yolo_decode without the per-class score tensor."""
+    if len(preds) == 0 or len(preds) != len(anchor_whs):
+        raise _lib.HvsError("yolo_decode_scales: one anchor table per prediction tensor")
+    _need_cuda(*preds, *anchor_whs)
+    p0 = preds[0]
+    if any(p.dim() != 5 or p.dtype != p0.dtype or p.shape[0] != p0.shape[0] or p.shape[4] != p0.shape[4] or p.device != p0.device
+           for p in preds) or p0.dtype not in _DTYPES:
+        raise _lib.HvsError("yolo_decode_scales: preds must be [B,A,H,W,5+C] fp32/fp16/bf16 sharing B, C, dtype and device")
+    dev = p0.device
+    with torch.cuda.device(dev):
+        table = (_lib.DecodeScale * len(preds))()
+        outs, keep = [], []
+        for k, (p, awh) in enumerate(zip(preds, anchor_whs)):
+            b, a, h, w, d = p.shape
+            awh = awh.to(device=dev, dtype=torch.float32).contiguous()
+            boxes = torch.empty((b, a, h, w, 4), dtype=torch.float32, device=dev)
+            cs = torch.empty((b, a, h, w), dtype=torch.float32, device=dev)
+            ci = torch.empty((b, a, h, w), dtype=torch.int64, device=dev)
+            obj = torch.empty((b, a, h, w, 1), dtype=torch.float32, device=dev) if want_objectness else None
+            e = table[k]
+            e.pred, e.anchor_wh, e.boxes, e.class_scores, e.class_idx, e.objectness = _ptr(p), _ptr(awh), _ptr(boxes), _ptr(cs), _ptr(ci), _ptr(obj)
+            for i, st in enumerate(p.stride()):
+                e.pred_stride[i] = st
+            e.A, e.H, e.W = a, h, w
+            keep.append(awh)
+            out = {"boxes": boxes, "class_scores": cs, "class_indices": ci}
+            if obj is not None:
+                out["objectness"] = obj
+            outs.append(out)
+        check(_lib.load().hvs_yolo_decode_scales(table, len(preds), _DTYPES[p0.dtype], p0.shape[0], p0.shape[4] - 5, _stream()),
+              "hvs_yolo_decode_scales")
+    return outs
+
+
 @_on_device
 def head_decode_fused(tokens: torch.Tensor, weight256: torch.Tensor, bias256: torch.Tensor, anchor_wh: torch.Tensor, b: int, h: int,
                       w: int, want_objectness: bool = False) -> Dict[str, torch.Tensor]:

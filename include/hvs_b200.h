@@ -361,6 +361,26 @@ int hvs_yolo_decode(const void* pred, int pred_dtype, const int64_t* pred_stride
                     float* boxes, float* class_scores, int64_t* class_idx, float* objectness, float* scores,
                     int B, int A, int H, int W, int C, void* stream);
 
+/* YOLODetectionHead's decode loop over its scales (src/models/yolo_head.py:536-555: `for scale_idx in range(self.num_scales):
+ * ... self.decoder(pred, anchors, grid_size)`) as ONE launch: the coarse grids of a batch are a fraction of a wave each and would
+ * run as latency-bound launches of their own.  Same outputs per scale as hvs_yolo_decode without the per-class score
+ * tensor (class_scores / class_idx are the max / first argmax of obj * sigmoid(cls), bit-identical to hvs_yolo_decode).
+ * All scales share B, C and the prediction dtype.  Scales that cannot take the vectorised plane-strided mapping
+ * (unit W stride, W % 4 == 0, strides % 4 == 0) make the call fall back to one launch per scale.
+ *   scales_host  host array of n_scales descriptors (read before the call returns) */
+typedef struct {
+    const void* pred;            /* [B, A, H, W, 5+C] through pred_stride (elements) */
+    int64_t pred_stride[5];
+    const float* anchor_wh;      /* [A, 2] fp32 */
+    float* boxes;                /* [B, A, H, W, 4] */
+    float* class_scores;         /* [B, A, H, W] */
+    int64_t* class_idx;          /* [B, A, H, W] */
+    float* objectness;           /* [B, A, H, W] or NULL */
+    int A, H, W;
+} hvs_decode_scale;
+
+int hvs_yolo_decode_scales(const hvs_decode_scale* scales_host, int n_scales, int pred_dtype, int B, int C, void* stream);
+
 /* Fused YOLOPredictionHead tail: the 1x1 prediction convolution (yolo_head.py:193-194) as a tcgen05 GEMM over the
  * head's token view, with YOLODecoder.forward (:241-285) as its epilogue -- the raw [B,3,H,W,85] predictions are never
  * written.  For the model's head: 3 anchors x (5 + 80) = 255 output channels.

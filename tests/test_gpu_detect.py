@@ -101,6 +101,36 @@ def test_decode_first_maximum_kernel_is_bit_identical_to_the_all_scores_kernel(d
     assert torch.equal(full["class_scores"][finite], sc.max(-1).values[finite])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_decode_all_scales_in_one_launch_equals_scale_by_scale(dtype):
+    """hvs_yolo_decode_scales (the head's decode loop, yolo_head.py:536-555, as one launch) against hvs_yolo_decode per
+    scale: identical bits; also when a scale forces the scale-by-scale fallback (channel-contiguous layout)."""
+    import hvs_b200
+    g = torch.Generator().manual_seed(5)
+    preds, awhs = [], []
+    for s, hw in enumerate((40, 20, 12)):
+        nchw = (torch.randn(3, 3 * 85, hw, hw, generator=g) * 1.5).to(dtype).cuda()
+        preds.append(nchw.view(3, 3, 85, hw, hw).permute(0, 1, 3, 4, 2))
+        awhs.append(detect_ref.anchors_wh(s).cuda())
+    for variant in ("strided", "one contiguous"):
+        ps = list(preds)
+        if variant == "one contiguous":
+            ps[1] = ps[1].contiguous()
+        together = hvs_b200.ops.yolo_decode_scales(ps, awhs)
+        for p, a, t in zip(ps, awhs, together):
+            one = hvs_b200.ops.yolo_decode(p, a)
+            for k in ("boxes", "class_scores", "objectness"):
+                assert torch.equal(t[k].view(torch.int32), one[k].view(torch.int32)), (variant, k)
+            assert torch.equal(t["class_indices"], one["class_indices"]), variant
+            ref = detect_ref.yolo_decode(p.float().cpu(), a.cpu())
+            assert torch.allclose(t["boxes"].cpu(), ref["boxes"], rtol=2e-6, atol=2e-7)
+            assert torch.allclose(t["class_scores"].cpu(), ref["class_scores"], rtol=2e-6, atol=1e-8)
+    with pytest.raises(hvs_b200.HvsError):
+        hvs_b200.ops.yolo_decode_scales(preds, awhs[:2])
+    with pytest.raises(hvs_b200.HvsError):
+        hvs_b200.ops.yolo_decode_scales([preds[0], preds[1][:2]], awhs[:2])
+
+
 def test_nms_golden_bit_exact(golden):
     g = golden("nms")
     ki, _ = gpu_keep(g["ka/boxes"], g["ka/scores"], g["ka/classes"], iou_threshold=0.5, class_aware=True, boxes_xyxy=False)
