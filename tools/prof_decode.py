@@ -18,5 +18,11 @@ for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); ops.yolo_decode(p, a, want_scores=False, want_objectness=False); e1.record()
         ev.append((e0, e1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); dec = ops.yolo_decode_scales(preds, list(anchors), want_objectness=False); e1.record()
+    ev.append((e0, e1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.post_process(dec, 0.25, 0.45, 100); e1.record()
+    ev.append((e0, e1))
     torch.cuda.synchronize()
-    print("decode ms per scale:", " ".join(f"{a.elapsed_time(b):.4f}" for a, b in ev))
+    print("ms: decode per scale | all scales in one launch | post_process:", " ".join(f"{a.elapsed_time(b):.4f}" for a, b in ev))
