@@ -3,9 +3,9 @@
 //   class-aware     NMSFilter.apply / _standard_nms / _compute_iou        src/inference/postprocessing.py:505-607, 772-802
 // and the two-stage multi-scale merge YOLODetectionHead.post_process      src/models/yolo_head.py:571-676.
 //
-// Two kernels.  Large sets (2048 < N <= 24000, the per-scale stage of post_process): nms_sorted_kernel below -- one
-// stable radix sort in shared memory, then every candidate is tested only against the boxes already kept.
-// Small sets: nms_kernel.
+// Two kernels.  Sets of 64 < N <= 24000 candidates (both stages of post_process): nms_sorted_kernel below -- one stable
+// sort in shared memory (radix above 1024 passing candidates, one rank-by-counting pass below), then every candidate is
+// tested only against the boxes already kept.  Smaller sets: nms_kernel.
 // One CTA per candidate set.  Both reference loops keep at most max_det boxes in descending score
 // order and never look back, so instead of a sort + N x N mask the CTA repeats, at most max_det
 // times: (1) block-wide arg-max over the still-alive scores (ties -> lower index; scores cached in
@@ -35,6 +35,10 @@ struct NmsGroup {
 struct NmsArgs {
     NmsGroup g[kMaxGroups];
     int num_groups;            // problem p -> group p % num_groups, batch item p / num_groups
+    int batch;                 // problems per group
+    int order[kMaxGroups];     // groups by descending n: CTA x works on group order[x / batch], item x % batch -- the big
+                               // candidate sets start first and the small ones fill in behind them (in problem order the
+                               // 64 + 128 sets of a batch of 64 ran as two waves with big sets in both)
     const int64_t* offsets;    // optional [P+1]: problem p = [offsets[p], offsets[p+1]) of group 0
     const int32_t* counts;     // optional [P]: candidates of problem p (<= g.n)
     float score_thr, iou_thr;
@@ -43,6 +47,13 @@ struct NmsArgs {
     int64_t* keep_src;         // [P, max_det] index into the problem's candidates
     int32_t* keep_count;       // [P]
 };
+
+__device__ __forceinline__ int problem_of_cta(const NmsArgs& a) {
+    const int x = blockIdx.x;
+    if (a.offsets || a.num_groups <= 1) return x;
+    const int slot = x / a.batch;
+    return (x - slot * a.batch) * a.num_groups + a.order[slot];
+}
 
 __device__ __forceinline__ float max_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
 __device__ __forceinline__ float min_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
@@ -73,7 +84,7 @@ __global__ void __launch_bounds__(THREADS) nms_kernel(const NmsArgs a) {
     __shared__ float s_wbest[THREADS / 32];
     __shared__ int s_wbesti[THREADS / 32];
     __shared__ int s_pick;
-    const int p = blockIdx.x;
+    const int p = problem_of_cta(a);
     const int gi = a.offsets ? 0 : p % a.num_groups;
     const int bi = a.offsets ? 0 : p / a.num_groups;
     const NmsGroup& grp = a.g[gi];
@@ -195,8 +206,8 @@ __global__ void __launch_bounds__(kSortThreads) nms_sorted_kernel(const NmsArgs 
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ int s_warp_tot[32];
     __shared__ int s_total, s_kept;
-    __shared__ uint32_t s_alive[32];
-    const int p = blockIdx.x;
+    __shared__ uint32_t s_alive[32], s_sup[32], s_pair[32];
+    const int p = problem_of_cta(a);
     const int gi = a.offsets ? 0 : p % a.num_groups;
     const int bi = a.offsets ? 0 : p / a.num_groups;
     const NmsGroup& grp = a.g[gi];
@@ -252,7 +263,22 @@ __global__ void __launch_bounds__(kSortThreads) nms_sorted_kernel(const NmsArgs 
     uint16_t* dst = ord_b;
     const int mper = (m + kSortThreads - 1) / kSortThreads;
     const int mlo = min(tid * mper, m), mhi = min(mlo + mper, m);
-    for (int shift = 0; shift < 32 && m > 1; shift += 4) {
+    if (m > 1 && m <= kSortThreads) {
+        // up to one candidate per thread (the cross-scale stage: at most 3 x max_det): its place in the order is the number of
+        // candidates that sort before it -- smaller key, or the same key earlier in the list (= lower index).  One pass.
+        if (tid < m) {
+            const uint32_t mine = keys[src[tid]];
+            int rank = 0;
+            for (int q = 0; q < m; ++q) {
+                const uint32_t k = keys[src[q]];
+                rank += (k < mine || (k == mine && q < tid)) ? 1 : 0;
+            }
+            dst[rank] = src[tid];
+        }
+        __syncthreads();
+        uint16_t* t = src; src = dst; dst = t;
+    }
+    for (int shift = 0; shift < 32 && m > kSortThreads; shift += 4) {
 #pragma unroll
         for (int d = 0; d < 16; ++d) cnt[d * kSortThreads + tid] = 0;
         for (int q = mlo; q < mhi; ++q) cnt[((keys[src[q]] >> shift) & 15u) * kSortThreads + tid] += 1;
@@ -287,60 +313,76 @@ __global__ void __launch_bounds__(kSortThreads) nms_sorted_kernel(const NmsArgs 
         uint16_t* t = src; src = dst; dst = t;
     }
 
-    // ---- 3. walk the sorted candidates, 1024 at a time
+    // ---- 3. walk the sorted candidates, 1024 at a time.  A chunk: every thread tests its candidate against the boxes kept
+    //      in earlier chunks; then the chunk's 32 groups of 32 are resolved in order, each in two block-wide steps:
+    //        A  all 1024 threads: candidate `lane` of the group against the boxes kept earlier in this chunk (keep w, w + 32, ..
+    //           for warp w) and against candidate `warp` of the same group (the 32 x 32 pair matrix, one IoU per thread)
+    //        B  warp 0: greedy over the group's alive word with the pair masks -- a few integer instructions per kept box
+    //      (one warp doing both with an IoU per kept box on its dependent chain was 70 % of the kernel: ~100 us per set).
+    __syncthreads();                                         // the digit counters are dead: the chunk buffers live there
+    float4* cbox = reinterpret_cast<float4*>(cnt);
+    int64_t* ccls = reinterpret_cast<int64_t*>(cbox + kSortThreads);
     for (int base = 0; base < m; base += kSortThreads) {
         const int kept0 = s_kept;
         if (kept0 >= a.max_det) break;
-        const int q = base + tid;
-        bool alive = q < m;
-        int me = 0;
-        float4 mb = make_float4(0.f, 0.f, 0.f, 0.f);
-        int64_t mc = 0;
-        if (alive) {
-            me = src[q];
-            mb = load_box(boxes, me, cxcywh);
-            mc = class_aware ? classes[me] : 0;
-            for (int k = 0; k < kept0 && alive; ++k) alive = !suppresses(kbox[k], karea[k], kcls[k], mb, mc, class_aware, a.iou_thr);
-        }
-        const uint32_t word = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) s_alive[warp] = word;
-        __syncthreads();
-        if (warp == 0) {
-            int kept = kept0;
-            for (int sc = 0; sc < 32 && kept < a.max_det; ++sc) {
-                const uint32_t aw = s_alive[sc];
-                if (aw == 0u) continue;
-                const int qq = base + sc * 32 + lane;
-                bool al = (aw >> lane) & 1u;
-                int ci = 0;
-                float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
-                int64_t cc = 0;
-                if (al) {
-                    ci = src[qq];
-                    cb = load_box(boxes, ci, cxcywh);
-                    cc = class_aware ? classes[ci] : 0;
-                    for (int k = kept0; k < kept && al; ++k) al = !suppresses(kbox[k], karea[k], kcls[k], cb, cc, class_aware, a.iou_thr);
-                }
-                uint32_t mask;
-                while ((mask = __ballot_sync(0xffffffffu, al)) != 0u && kept < a.max_det) {
-                    const int ld = __ffs(mask) - 1;                      // best remaining candidate of this group: keep it
-                    const float4 wb = make_float4(__shfl_sync(0xffffffffu, cb.x, ld), __shfl_sync(0xffffffffu, cb.y, ld),
-                                                  __shfl_sync(0xffffffffu, cb.z, ld), __shfl_sync(0xffffffffu, cb.w, ld));
-                    const int64_t wc = __shfl_sync(0xffffffffu, cc, ld);
-                    const float warea = __fmul_rn(__fsub_rn(wb.z, wb.x), __fsub_rn(wb.w, wb.y));
-                    if (lane == ld) {
-                        kbox[kept] = wb; karea[kept] = warea; kcls[kept] = wc;
-                        a.keep_src[(int64_t)p * a.max_det + kept] = ci;
-                        al = false;
-                    }
-                    ++kept;
-                    if (al) al = !suppresses(wb, warea, wc, cb, cc, class_aware, a.iou_thr);
-                }
-                __syncwarp();
+        {
+            const int q = base + tid;
+            bool alive = q < m;
+            float4 mb = make_float4(0.f, 0.f, 0.f, 0.f);
+            int64_t mc = 0;
+            if (alive) {
+                const int me = src[q];
+                mb = load_box(boxes, me, cxcywh);
+                mc = class_aware ? classes[me] : 0;
+                for (int k = 0; k < kept0 && alive; ++k) alive = !suppresses(kbox[k], karea[k], kcls[k], mb, mc, class_aware, a.iou_thr);
             }
-            if (lane == 0) s_kept = kept;
+            cbox[tid] = mb;
+            ccls[tid] = mc;
+            const uint32_t word = __ballot_sync(0xffffffffu, alive);
+            if (lane == 0) s_alive[warp] = word;
         }
         __syncthreads();
+        for (int g = 0; g < 32; ++g) {
+            const int kept = s_kept;                             // (block-uniform: written before the last barrier)
+            if (kept >= a.max_det) break;
+            const uint32_t aw = s_alive[g];
+            if (aw == 0u) continue;
+            const float4 cb = cbox[g * 32 + lane];
+            const int64_t cc = ccls[g * 32 + lane];
+            const bool mine = (aw >> lane) & 1u;
+            bool sup = false;
+            if (mine)
+                for (int k = kept0 + warp; k < kept && !sup; k += 32) sup = suppresses(kbox[k], karea[k], kcls[k], cb, cc, class_aware, a.iou_thr);
+            bool pair = false;
+            if (mine && lane > warp && ((aw >> warp) & 1u)) {
+                const float4 wb = cbox[g * 32 + warp];
+                const float warea = __fmul_rn(__fsub_rn(wb.z, wb.x), __fsub_rn(wb.w, wb.y));
+                pair = suppresses(wb, warea, ccls[g * 32 + warp], cb, cc, class_aware, a.iou_thr);
+            }
+            const uint32_t supw = __ballot_sync(0xffffffffu, sup), pairw = __ballot_sync(0xffffffffu, pair);
+            if (lane == 0) { s_sup[warp] = supw; s_pair[warp] = pairw; }
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t alive_w = aw & ~__reduce_or_sync(0xffffffffu, s_sup[lane]);
+                uint32_t keep_w = 0u;
+                int kk = kept;
+                while (alive_w != 0u && kk < a.max_det) {
+                    const int ld = __ffs(alive_w) - 1;           // best remaining candidate of the group: keep it
+                    keep_w |= 1u << ld;
+                    alive_w &= ~(s_pair[ld] | (1u << ld));
+                    ++kk;
+                }
+                if ((keep_w >> lane) & 1u) {
+                    const int r = kept + __popc(keep_w & ((1u << lane) - 1u));
+                    kbox[r] = cb;
+                    karea[r] = __fmul_rn(__fsub_rn(cb.z, cb.x), __fsub_rn(cb.w, cb.y));
+                    kcls[r] = cc;
+                    a.keep_src[(int64_t)p * a.max_det + r] = src[base + g * 32 + lane];
+                }
+                if (lane == 0) s_kept = kk;
+            }
+            __syncthreads();
+        }
     }
     const int kept = s_kept;
     if (tid == 0) a.keep_count[p] = kept;
@@ -367,7 +409,9 @@ int launch_nms(const NmsArgs& a, int num_problems, int64_t max_n, cudaStream_t s
     if (max_n > 49152) return HVS_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(max_n > 0 ? max_n : 1) * sizeof(float);
     constexpr size_t kSortSmemMax = 232448 - 1024;            // the kernel also has static shared memory
-    if (max_n > 2048 && max_n <= kSortMaxN && sorted_smem_bytes(max_n, a.max_det) <= kSortSmemMax) {
+    // (sets of up to 64 candidates stay on the arg-max kernel: a handful of rounds there; above that the arg-max kernel's
+    //  max_det block-wide rounds -- 150 us for the 300-candidate cross-scale stage -- lose to one sort + one walk)
+    if (max_n > 64 && max_n <= kSortMaxN && sorted_smem_bytes(max_n, a.max_det) <= kSortSmemMax) {
         const size_t sb = sorted_smem_bytes(max_n, a.max_det);
         HVS_SET_MAX_SMEM(nms_sorted_kernel, (int)kSortSmemMax);
         nms_sorted_kernel<<<num_problems, kSortThreads, sb, stream>>>(a);
@@ -474,7 +518,7 @@ extern "C" int hvs_nms(const float* boxes, const float* scores, const int64_t* c
     if (reinterpret_cast<uintptr_t>(boxes) & 15) return HVS_ERR_ALIGNMENT;
     NmsArgs a{};
     a.g[0] = NmsGroup{boxes, scores, classes, 0, 0};
-    a.num_groups = 1;
+    a.num_groups = 1; a.batch = num_problems > 0 ? num_problems : 1; a.order[0] = 0;
     a.offsets = offsets;
     a.counts = nullptr;
     a.score_thr = score_thr; a.iou_thr = iou_thr; a.max_det = max_det; a.mode = mode;
@@ -510,7 +554,10 @@ extern "C" int hvs_post_process(const float* const* boxes_host, const float* con
         a.g[s] = NmsGroup{boxes_host[s], class_scores_host[s], class_idx_host[s], n_per_scale_host[s], n_per_scale_host[s]};
         if (n_per_scale_host[s] > max_n) max_n = n_per_scale_host[s];
     }
-    a.num_groups = num_scales;
+    a.num_groups = num_scales; a.batch = B;
+    for (int s = 0; s < num_scales; ++s) a.order[s] = s;
+    for (int i = 1; i < num_scales; ++i)            // insertion sort, descending n, stable
+        for (int j = i; j > 0 && a.g[a.order[j]].n > a.g[a.order[j - 1]].n; --j) { const int t = a.order[j]; a.order[j] = a.order[j - 1]; a.order[j - 1] = t; }
     a.score_thr = conf_thr; a.iou_thr = iou_thr; a.max_det = max_det; a.mode = HVS_NMS_AGNOSTIC;
     a.keep_idx = nullptr; a.keep_src = w.s1_src; a.keep_count = w.s1_count;
     int rc = launch_nms(a, B * num_scales, max_n, stream);
@@ -527,7 +574,7 @@ extern "C" int hvs_post_process(const float* const* boxes_host, const float* con
     const int cap = num_scales * max_det;
     NmsArgs b2{};
     b2.g[0] = NmsGroup{w.cat_boxes, w.cat_scores, w.cat_labels, cap, cap};
-    b2.num_groups = 1;
+    b2.num_groups = 1; b2.batch = B; b2.order[0] = 0;
     b2.counts = w.cat_count;
     b2.score_thr = -INFINITY; b2.iou_thr = iou_thr; b2.max_det = max_det; b2.mode = HVS_NMS_AGNOSTIC;
     b2.keep_idx = nullptr; b2.keep_src = w.s2_src; b2.keep_count = w.s2_count;
