@@ -282,6 +282,7 @@ def run_extras(args, dev, world, rank):
     model = copy.deepcopy(train_model)                     # inference copy: eval-mode BatchNorm folded into the convolutions
     folded = harness.fold_batchnorm_for_inference(model.eval())
     to_channels_last(model)
+    harness.cast_weights_for_bf16_inference(model)         # the casts autocast would launch on every call, done once
     per = 64 // world
     inf = harness.inference_sharded(model, dev, world, rank, 64, 640)
     inf_real = harness.inference_sharded(model, dev, world, rank, 64, 640, objectness_bias=-4.0, steps=3, warmup=1)

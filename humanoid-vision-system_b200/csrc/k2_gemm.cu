@@ -722,6 +722,13 @@ int launch_gemm(const hvs_gemm_args& g, int timer_slot, cudaStream_t stream) {
     p.aux = reinterpret_cast<const __nv_bfloat16*>(g.aux); p.ld_aux = g.ld_aux;
     p.out2 = reinterpret_cast<__nv_bfloat16*>(g.out2); p.ldo2 = g.ldo2;
     p.a_mn = a_mn; p.b_mn = b_mn;
+    const int sms = sm_count();
+    if ((g.epilogue == HVS_GEMM_EPI_NONE || g.epilogue == HVS_GEMM_EPI_BIAS_GELU) && splits == 1 && !a_mn && !b_mn) {
+        // few row tiles (a batch-1 frame: 401 tokens = 4 tiles): narrower accumulators put the same work on 2-4x the SMs, each
+        // with a quarter of the weight tile to fetch and of the epilogue to run (these launches are latency-, not math-bound)
+        const int64_t mt = (M + kBM - 1) / kBM;
+        while (p.BN > 64 && (p.BN / 2) % 32 == 0 && N % (p.BN / 2) == 0 && mt * (N / p.BN) * 2 <= sms) p.BN /= 2;
+    }
     p.b_bytes = b_mn ? ((p.BN + 63) / 64) * 8192 : p.BN * 128;
     p.kb0 = (K0 + kBK - 1) / kBK; p.kb1 = (K1 + kBK - 1) / kBK;
     const int num_kb = p.kb0 + p.kb1;
@@ -753,7 +760,6 @@ int launch_gemm(const hvs_gemm_args& g, int timer_slot, cudaStream_t stream) {
         ta1 = ta0; tb1 = tb0;
     }
     HVS_SET_MAX_SMEM(k2_gemm_kernel<false>, kSmemBytes);
-    const int sms = sm_count();
     const int grid = p.num_tiles < sms ? p.num_tiles : sms;
     timer_begin(timer_slot, stream);
     k2_gemm_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(ta0, tb0, ta1, tb1, p);

@@ -70,6 +70,32 @@ def fold_batchnorm_for_inference(model: nn.Module) -> int:
     return n
 
 
+def cast_weights_for_bf16_inference(model: nn.Module) -> int:
+    """Store the weights and biases of the host model's convolutions and linear layers in bf16.  Under bf16 autocast those
+    parameters are cast to bf16 on EVERY call (autocast caches a cast only for parameters that require grad inside one
+    autocast region, and a CUDA graph replays the cast kernels anyway): 230 small `bfloat16_copy` launches per forward,
+    0.8 of the 7.4 ms of a batch-1 frame.  Casting once gives the same bf16 operands, so the outputs do not change.
+    The mHC modules are left alone (fp32 master parameters; this library keeps its own bf16 copies of them).  Inference
+    only: use it on a model that will not be trained.  Returns the number of tensors cast."""
+    from .mhc import ManifoldHyperConnection
+    skip = set()
+    for mod in model.modules():
+        if isinstance(mod, ManifoldHyperConnection):
+            skip.update(id(m) for m in mod.modules())
+    n = 0
+    with torch.no_grad():
+        for mod in model.modules():
+            if id(mod) in skip or not isinstance(mod, (nn.Conv2d, nn.Linear, nn.ConvTranspose2d, nn.Conv1d)):
+                continue
+            for name in ("weight", "bias"):
+                t = getattr(mod, name, None)
+                if isinstance(t, nn.Parameter) and t.dtype == torch.float32:
+                    t.data = t.data.to(torch.bfloat16)
+                    t.requires_grad_(False)
+                    n += 1
+    return n
+
+
 def _time_steps(fn, steps: int, warmup: int) -> float:
     for _ in range(warmup):
         fn()

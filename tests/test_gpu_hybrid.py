@@ -251,3 +251,35 @@ def test_batchnorm_folding_with_fused_bias_activation_keeps_the_outputs(model):
         pa, pb = a["predictions"][f"scale_{s}"].float(), b["predictions"][f"scale_{s}"].float()
         rel = ((pa - pb).norm() / pa.norm()).item()
         assert rel < 0.15, (s, rel)                                       # two bf16 pipelines through 76 layers (cf. 9-11 % vs fp32)
+
+
+def test_weights_cast_once_for_bf16_inference_give_the_same_outputs(model):
+    """harness.cast_weights_for_bf16_inference: the per-call bf16 casts of autocast done once.  Same bf16 operands into the
+    same kernels: identical predictions, ~230 fewer launches per forward."""
+    import copy
+    from torch.profiler import profile, ProfilerActivity
+    import hvs_b200
+    from hvs_b200 import harness
+    m0 = copy.deepcopy(model).eval()
+    harness.fold_batchnorm_for_inference(m0)
+    hvs_b200.hybrid_vision.to_channels_last(m0)
+    m1 = copy.deepcopy(m0)
+    assert harness.cast_weights_for_bf16_inference(m1) > 100
+    assert all(p.dtype == torch.float32 for mod in m1.modules() if isinstance(mod, hvs_b200.ManifoldHyperConnection) for p in mod.parameters())
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 3, 320, 320, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+
+    def run(m):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            m(x)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):     # a fresh autocast region: no cached casts
+                out = m(x)
+            torch.cuda.synchronize()
+        return out, sum(e.count for e in prof.key_averages())
+
+    a, launches_a = run(m0)
+    b, launches_b = run(m1)
+    for s in range(3):
+        assert torch.equal(a["predictions"][f"scale_{s}"], b["predictions"][f"scale_{s}"]), s
+    assert launches_a - launches_b > 100, (launches_a, launches_b)

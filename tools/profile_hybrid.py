@@ -15,6 +15,8 @@ if not train and os.environ.get("HVS_FOLD_BN", "1") == "1":
     from hvs_b200.hybrid_vision import to_channels_last
     harness.fold_batchnorm_for_inference(model.eval())
     to_channels_last(model)
+    if os.environ.get("HVS_CAST_WEIGHTS", "1") == "1":
+        harness.cast_weights_for_bf16_inference(model)
 x = torch.randn(batch, 3, 640, 640, device=dev).to(torch.bfloat16 if not train else torch.float32).contiguous(memory_format=torch.channels_last)
 if train:
     model.train()
