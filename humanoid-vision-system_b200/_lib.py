@@ -121,6 +121,9 @@ _SIGNATURES = {
     "hvs_grad_clip_dual": (c_int, [POINTER(GradTensor), c_int, c_float, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hvs_gate_residual_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "hvs_bias_act_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "hvs_se_gate_workspace": (c_size_t, [c_int64, c_int64, c_int]),
+    "hvs_se_gate_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int,
+                                 c_void_p, c_size_t, c_void_p]),
     "hvs_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                   POINTER(c_float), POINTER(c_float), c_void_p]),
     "hvs_yolo_decode": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

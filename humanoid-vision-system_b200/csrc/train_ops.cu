@@ -274,6 +274,201 @@ extern "C" int hvs_gate_residual_bf16(const void* y, const void* gate, const voi
     return launch_status();
 }
 
+// ---------------------------------------------------------------------------------------------- squeeze-excite gate
+// ConvMHCLayer.channel_attention (src/models/vision_backbone.py:77-83, applied :126-127): AdaptiveAvgPool2d(1) -> 1x1 conv
+// C -> C/4 -> activation -> 1x1 conv C/4 -> C -> sigmoid, as ONE launch over the channels-last map.  As torch ops it is a
+// reduce kernel, two tiny GEMMs with their bias passes, an activation and a sigmoid: 6-7 launches per layer, 28 layers --
+// a fifth of the launches of a batch-1 frame.  Here: every CTA sums a slice of an image's rows per channel (16-byte loads,
+// fp32), the slices' partial sums go to the workspace, and the LAST CTA of an image to arrive (one counter per image) adds
+// them in slice order and runs the two small matrix-vector products.  Rounding points are the bf16 autocast path's: the
+// pooled mean, both 1x1 outputs (+ bias), the activation and the sigmoid are each rounded to bf16; accumulation in fp32.
+namespace hvs {
+namespace {
+constexpr int kSeThreads = 256;
+constexpr int kSeMaxC = 2048;
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+template <int ACT>
+__global__ void __launch_bounds__(kSeThreads) se_gate_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict__ w1,
+                                                             const __nv_bfloat16* __restrict__ b1, const __nv_bfloat16* __restrict__ w2,
+                                                             const __nv_bfloat16* __restrict__ b2, __nv_bfloat16* __restrict__ gate,
+                                                             float* __restrict__ part, int* __restrict__ counters,
+                                                             int64_t rows_per_image, int c8, int hidden, int rows_per_cta) {
+    __shared__ float s_red[kSeThreads][9];                 // (+1: the row lanes of a column group land in different banks)
+    __shared__ float s_pool[kSeMaxC];
+    __shared__ float s_hid[kSeMaxC / 2];
+    __shared__ int s_last;
+    const int C = c8 * 8;
+    const int b = blockIdx.y, slice = blockIdx.x, slices = gridDim.x;
+    const int tid = threadIdx.x;
+    // ---- 1. partial sums of rows [r0, r1) of image b: thread = (row lane, column group of 8 channels)
+    const int lanes = kSeThreads / c8 > 0 ? kSeThreads / c8 : 1;     // row lanes per column group (c8 <= 256)
+    const int cg = tid % c8, rl = tid / c8;
+    const int64_t r0 = (int64_t)slice * rows_per_cta;
+    const int64_t r1 = r0 + rows_per_cta < rows_per_image ? r0 + rows_per_cta : rows_per_image;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (rl < lanes) {
+        const uint4* base = y + ((int64_t)b * rows_per_image) * c8 + cg;
+        int64_t r = r0 + rl;
+        for (; r + 3 * lanes < r1; r += 4 * lanes) {       // four independent loads in flight
+            const uint4 v0 = base[r * c8], v1 = base[(r + lanes) * c8], v2 = base[(r + 2 * lanes) * c8], v3 = base[(r + 3 * lanes) * c8];
+            const uint4 vs[4] = {v0, v1, v2, v3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                acc[0] += bf16lo(vs[k].x); acc[1] += bf16hi(vs[k].x); acc[2] += bf16lo(vs[k].y); acc[3] += bf16hi(vs[k].y);
+                acc[4] += bf16lo(vs[k].z); acc[5] += bf16hi(vs[k].z); acc[6] += bf16lo(vs[k].w); acc[7] += bf16hi(vs[k].w);
+            }
+        }
+        for (; r < r1; r += lanes) {
+            const uint4 v = base[r * c8];
+            acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x); acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
+            acc[4] += bf16lo(v.z); acc[5] += bf16hi(v.z); acc[6] += bf16lo(v.w); acc[7] += bf16hi(v.w);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_red[tid][k] = acc[k];
+    __syncthreads();
+    float* my_part = part + ((int64_t)b * slices + slice) * C;
+    for (int c = tid; c < C; c += kSeThreads) {            // channel c = column group c / 8, element c % 8: add the row lanes in order
+        const int g = c >> 3, e = c & 7;
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += s_red[l * c8 + g][e];
+        my_part[c] = t;
+    }
+    // ---- 2. the last CTA of the image to get here finishes the gate
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&counters[b], 1) == slices - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float inv = 1.0f / (float)rows_per_image;
+    for (int c = tid; c < C; c += kSeThreads) {
+        float t = 0.f;
+        const float* pp = part + (int64_t)b * slices * C + c;
+        for (int sl = 0; sl < slices; ++sl) t += __ldcg(pp + (int64_t)sl * C);
+        s_pool[c] = bf16_round(t * inv);                  // AdaptiveAvgPool2d(1) output in bf16
+    }
+    __syncthreads();
+    // Both products: a warp per output, EIGHT outputs per pass, lanes along the inputs in 16-byte pieces -- the weights come
+    // from L2 once, so what counts is loads in flight (one output at a time with 2-byte loads was 50-120 us at C = 512).
+    const int warp = tid >> 5, lane = tid & 31;
+    auto dot8 = [](const uint4& v, const float* x) {
+        return fmaf(bf16lo(v.x), x[0], fmaf(bf16hi(v.x), x[1], fmaf(bf16lo(v.y), x[2], fmaf(bf16hi(v.y), x[3],
+               fmaf(bf16lo(v.z), x[4], fmaf(bf16hi(v.z), x[5], fmaf(bf16lo(v.w), x[6], bf16hi(v.w) * x[7])))))));
+    };
+    // hidden = act(W1 pool + b1)
+    {
+        const uint4* wv = reinterpret_cast<const uint4*>(w1);
+        for (int j0 = warp * 8; j0 < hidden; j0 += (kSeThreads / 32) * 8) {
+            float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int g = lane; g < c8; g += 32) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(wv + (int64_t)min(j0 + u, hidden - 1) * c8 + g);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] += dot8(v[u], s_pool + g * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t[u] += __shfl_xor_sync(0xffffffffu, t[u], o);
+            }
+            if (lane < 8 && j0 + lane < hidden) {
+                float tv = t[0];
+#pragma unroll
+                for (int u = 1; u < 8; ++u) tv = lane == u ? t[u] : tv;
+                float v = bf16_round(tv + __bfloat162float(b1[j0 + lane]));
+                if (ACT == 1) v = __fdividef(v, 1.0f + __expf(-v));
+                else if (ACT == 2) v = fmaxf(v, 0.f);
+                s_hid[j0 + lane] = bf16_round(v);
+            }
+        }
+    }
+    __syncthreads();
+    // gate = sigmoid(W2 hidden + b2)
+    {
+        const uint4* wv = reinterpret_cast<const uint4*>(w2);
+        const int h8 = hidden >> 3;
+        for (int c0 = warp * 8; c0 < C; c0 += (kSeThreads / 32) * 8) {
+            float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int g = lane; g < h8; g += 32) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(wv + (int64_t)(c0 + u) * h8 + g);       // C % 8 == 0: all eight rows exist
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] += dot8(v[u], s_hid + g * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t[u] += __shfl_xor_sync(0xffffffffu, t[u], o);
+            }
+            if (lane < 8) {
+                float tv = t[0];
+#pragma unroll
+                for (int u = 1; u < 8; ++u) tv = lane == u ? t[u] : tv;
+                const float z = bf16_round(tv + __bfloat162float(b2[c0 + lane]));
+                gate[(int64_t)b * C + c0 + lane] = __float2bfloat16_rn(__fdividef(1.0f, 1.0f + __expf(-z)));
+            }
+        }
+    }
+    if (tid == 0) counters[b] = 0;                         // ready for the next launch (also when this one is a graph replay)
+}
+
+struct SePlan { int slices, rows_per_cta; size_t part_bytes, total; };
+SePlan se_plan(int64_t images, int64_t rows_per_image, int channels) {
+    SePlan p;
+    int64_t want = (2 * (int64_t)sm_count() + images - 1) / images;               // about two CTAs per SM over the batch
+    const int lanes = kSeThreads / (channels / 8) > 0 ? kSeThreads / (channels / 8) : 1;
+    const int64_t most = (rows_per_image + 4 * lanes - 1) / (4 * lanes);           // at least four rows per row lane
+    if (want > most) want = most;
+    if (want < 1) want = 1;
+    p.rows_per_cta = (int)((rows_per_image + want - 1) / want);
+    p.slices = (int)((rows_per_image + p.rows_per_cta - 1) / p.rows_per_cta);
+    p.part_bytes = (((size_t)images * p.slices * channels * 4) + 255) & ~(size_t)255;
+    p.total = p.part_bytes + ((((size_t)images * 4) + 255) & ~(size_t)255);
+    return p;
+}
+}  // namespace
+}  // namespace hvs
+
+extern "C" size_t hvs_se_gate_workspace(int64_t images, int64_t rows_per_image, int channels) {
+    if (images <= 0 || rows_per_image <= 0 || channels <= 0 || channels % 8 || channels > hvs::kSeMaxC) return 0;
+    return hvs::se_plan(images, rows_per_image, channels).total;
+}
+
+extern "C" int hvs_se_gate_bf16(const void* y, const void* w1, const void* b1, const void* w2, const void* b2, void* gate,
+                                int64_t images, int64_t rows_per_image, int channels, int hidden, int activation,
+                                void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace hvs;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (images < 0 || rows_per_image <= 0 || channels <= 0 || hidden <= 0) return HVS_ERR_BAD_ARG;
+    if (images == 0) return HVS_OK;
+    if (!y || !w1 || !b1 || !w2 || !b2 || !gate || !workspace) return HVS_ERR_BAD_ARG;
+    if (channels % 8 || hidden % 8 || channels > kSeMaxC || channels / 8 > kSeThreads || hidden > kSeMaxC / 2 || activation < 0 ||
+        activation > 2 || images > 65535)
+        return HVS_ERR_UNSUPPORTED;
+    if (((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(w2)) & 15) ||
+        (reinterpret_cast<uintptr_t>(workspace) & 255))
+        return HVS_ERR_ALIGNMENT;
+    const SePlan pl = se_plan(images, rows_per_image, channels);
+    if (workspace_bytes < pl.total) return HVS_ERR_WORKSPACE;
+    float* part = reinterpret_cast<float*>(workspace);
+    int* counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + pl.part_bytes);
+    const dim3 grid((unsigned)pl.slices, (unsigned)images);
+    const uint4* yp = reinterpret_cast<const uint4*>(y);
+    const __nv_bfloat16 *w1p = reinterpret_cast<const __nv_bfloat16*>(w1), *b1p = reinterpret_cast<const __nv_bfloat16*>(b1);
+    const __nv_bfloat16 *w2p = reinterpret_cast<const __nv_bfloat16*>(w2), *b2p = reinterpret_cast<const __nv_bfloat16*>(b2);
+    __nv_bfloat16* gp = reinterpret_cast<__nv_bfloat16*>(gate);
+    if (activation == 0) se_gate_kernel<0><<<grid, kSeThreads, 0, stream>>>(yp, w1p, b1p, w2p, b2p, gp, part, counters, rows_per_image, channels / 8, hidden, pl.rows_per_cta);
+    else if (activation == 1) se_gate_kernel<1><<<grid, kSeThreads, 0, stream>>>(yp, w1p, b1p, w2p, b2p, gp, part, counters, rows_per_image, channels / 8, hidden, pl.rows_per_cta);
+    else se_gate_kernel<2><<<grid, kSeThreads, 0, stream>>>(yp, w1p, b1p, w2p, b2p, gp, part, counters, rows_per_image, channels / 8, hidden, pl.rows_per_cta);
+    count_launch();
+    return launch_status();
+}
+
 // ---------------------------------------------------------------------------------------------- folded-BatchNorm bias + activation
 // After eval-mode BatchNorm is folded into the convolution (y = conv_w'(x) + b'), ATen adds the bias in a broadcast pass of its
 // own and the activation in another; here both are one vectorised pass over the channels-last map:

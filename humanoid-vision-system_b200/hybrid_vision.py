@@ -67,6 +67,8 @@ class ConvMHCLayer(nn.Module):
         self.use_residual = in_channels == out_channels and stride == 1
         self.activation_name = activation
         self.folded_bias: Optional[torch.Tensor] = None      # set by harness.fold_batchnorm_for_inference (bn becomes Identity)
+        self.fuse_se_gate = True                              # inference under bf16: the squeeze-excite gate as one launch
+        self._se_ws: Optional[torch.Tensor] = None
         self.channel_attention = None
         if use_mhc and out_channels >= 32:
             self.channel_attention = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(out_channels, out_channels // 4, 1),
@@ -86,8 +88,14 @@ class ConvMHCLayer(nn.Module):
         if self.mhc is not None:
             y = mhc_over_pixels(self.mhc, y)
             if self.channel_attention is not None:
-                gate = self.channel_attention(y)
                 cl = torch.channels_last
+                if (self.fuse_se_gate and not torch.is_grad_enabled() and y.is_cuda and y.dtype == torch.bfloat16 and y.shape[1] % 32 == 0
+                        and y.shape[1] <= 2048 and y.is_contiguous(memory_format=cl) and self.activation_name in ops.ACTIVATIONS):
+                    # inference: pool + both 1x1 convolutions + activation + sigmoid in one launch (hvs_se_gate_bf16)
+                    ca = self.channel_attention
+                    gate, self._se_ws = ops.se_gate(y, ca[1].weight, ca[1].bias, ca[3].weight, ca[3].bias, self.activation_name, self._se_ws)
+                else:
+                    gate = self.channel_attention(y)
                 if (not torch.is_grad_enabled() and y.is_cuda and y.dtype == torch.bfloat16 and gate.dtype == torch.bfloat16
                         and y.shape[1] % 8 == 0 and y.is_contiguous(memory_format=cl)
                         and (not self.use_residual or (x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=cl)))):

@@ -559,6 +559,35 @@ def bias_act(y: torch.Tensor, bias: torch.Tensor, activation: str = "silu") -> t
     return y
 
 
+@_on_device
+def se_gate(y: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, activation: str = "silu",
+            workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """sigmoid(W2 act(W1 mean_hw(y) + b1) + b2) for a channels-last bf16 map [B, C, H, W] in one launch (the squeeze-excite
+    gate of ConvMHCLayer, vision_backbone.py:77-83).  w1 [hidden, C(,1,1)], w2 [C, hidden(,1,1)]; parameters are used as bf16
+    (the autocast path).  Returns (gate [B, C, 1, 1] bf16, workspace): pass the workspace back in on the next call of the
+    same shape -- it is created zeroed and the kernel leaves it zeroed."""
+    _need_cuda(y, w1, b1, w2, b2)
+    b, c, h, w = y.shape
+    hidden = w1.shape[0]
+    if (y.dtype != torch.bfloat16 or not y.is_contiguous(memory_format=torch.channels_last) or w1.numel() != hidden * c
+            or w2.numel() != c * hidden or b1.numel() != hidden or b2.numel() != c or activation not in ACTIVATIONS):
+        raise _lib.HvsError("se_gate expects a channels-last bf16 map, w1 [hidden, C], b1 [hidden], w2 [C, hidden], b2 [C]")
+    bf = torch.bfloat16
+    w1, b1, w2, b2 = (t.detach().to(bf).contiguous() for t in (w1, b1, w2, b2))
+    lib = _lib.load()
+    need = int(lib.hvs_se_gate_workspace(b, h * w, c))
+    if need == 0:
+        raise _lib.HvsError(f"se_gate: unsupported shape (C = {c})")
+    key = (b, h * w, c, y.device)
+    if workspace is None or getattr(workspace, "_hvs_se_key", None) != key or workspace.numel() != need:
+        workspace = torch.zeros(need, dtype=torch.uint8, device=y.device)     # (the layout inside depends on the shape)
+        workspace._hvs_se_key = key
+    gate = torch.empty((b, c, 1, 1), dtype=bf, device=y.device)
+    check(lib.hvs_se_gate_bf16(_ptr(y), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(gate), b, h * w, c, hidden, ACTIVATIONS[activation],
+                               _ptr(workspace), workspace.numel(), _stream()), "hvs_se_gate_bf16")
+    return gate, workspace
+
+
 _PRE_DTYPES = {torch.float32: _lib.HVS_DTYPE_F32, torch.float16: _lib.HVS_DTYPE_F16, torch.bfloat16: _lib.HVS_DTYPE_BF16}
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 

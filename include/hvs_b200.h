@@ -327,6 +327,21 @@ int hvs_grad_clip_dual(const hvs_grad_tensor* tensors_host, int num_tensors, flo
 int hvs_gate_residual_bf16(const void* y, const void* gate, const void* residual, void* out, int64_t images,
                            int64_t rows_per_image, int channels, void* stream);
 
+/* The squeeze-excite gate of ConvMHCLayer (src/models/vision_backbone.py:77-83 `channel_attention`, applied :126-127):
+ * AdaptiveAvgPool2d(1) -> 1x1 conv C -> hidden -> activation -> 1x1 conv hidden -> C -> sigmoid, in ONE launch over the
+ * channels-last map (as torch ops: a reduce kernel, two small GEMMs with their bias passes, two elementwise kernels).
+ *   y [images * rows_per_image, channels] bf16 contiguous; w1 [hidden, channels], b1 [hidden], w2 [channels, hidden],
+ *   b2 [channels] bf16; gate [images, channels] bf16; activation as hvs_bias_act_bf16.
+ * Rounding follows the bf16 autocast path (pooled mean, both 1x1 outputs, activation and sigmoid each rounded to bf16,
+ * fp32 accumulation); sums are taken in a fixed order (deterministic).  channels % 8 == 0, hidden % 8 == 0,
+ * channels <= 2048, hidden <= 1024, images <= 65535; y, w1, w2 16-byte aligned.
+ * The workspace (hvs_se_gate_workspace bytes, 256-byte aligned) must be ZERO before its first use with this entry; the
+ * kernel leaves it ready for the next call. */
+size_t hvs_se_gate_workspace(int64_t images, int64_t rows_per_image, int channels);
+int hvs_se_gate_bf16(const void* y, const void* w1, const void* b1, const void* w2, const void* b2, void* gate,
+                     int64_t images, int64_t rows_per_image, int channels, int hidden, int activation,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* Bias of a BatchNorm-folded convolution + the activation that follows it (ConvMHCLayer, vision_backbone.py:100-110, eval
  * mode) in one pass over the channels-last map: out[t, c] = act(y[t, c] + bias[c]); y, out [rows, channels] bf16 (may
  * alias), bias [channels] fp32; activation 0 = identity, 1 = SiLU, 2 = ReLU; channels % 8 == 0. */

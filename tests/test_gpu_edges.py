@@ -106,3 +106,39 @@ def test_bias_act_matches_torch(act):
     got = hvs_b200.ops.bias_act(y.clone(memory_format=torch.channels_last), bias, act)
     assert got.is_contiguous(memory_format=torch.channels_last)
     assert ((got.double() - want).abs() <= 2.0 ** -8 * want.abs() + 1e-6).all()
+
+
+@pytest.mark.parametrize("b,c,hw,act", [(1, 32, (320, 320), "silu"), (3, 64, (40, 28), "silu"), (2, 256, (20, 20), "relu"),
+                                        (64, 512, (20, 20), "silu"), (1, 96, (7, 5), "silu"), (2, 2048, (3, 3), "none"), (5, 160, (9, 11), "relu")])
+def test_se_gate_matches_the_torch_modules_under_autocast(b, c, hw, act):
+    """hvs_se_gate_bf16 against ConvMHCLayer.channel_attention as torch runs it under bf16 autocast
+    (AdaptiveAvgPool2d(1) -> 1x1 conv -> act -> 1x1 conv -> sigmoid, vision_backbone.py:77-83): same rounding points, so the
+    gates agree to a bf16 ulp or two; repeated calls (workspace reuse) are bitwise identical."""
+    import hvs_b200
+    from hvs_b200 import ops
+    g = torch.Generator().manual_seed(c + b)
+    dev = "cuda"
+    y = (torch.randn(b, c, *hw, generator=g) * 1.5 + 0.3).to(torch.bfloat16).to(dev).contiguous(memory_format=torch.channels_last)
+    actm = {"silu": torch.nn.SiLU(), "relu": torch.nn.ReLU(), "none": torch.nn.Identity()}[act]
+    ca = torch.nn.Sequential(torch.nn.AdaptiveAvgPool2d(1), torch.nn.Conv2d(c, c // 4, 1), actm, torch.nn.Conv2d(c // 4, c, 1),
+                             torch.nn.Sigmoid()).to(dev)
+    with torch.no_grad():
+        for m in (ca[1], ca[3]):
+            m.weight.mul_(3.0); m.bias.normal_(0, 0.5, generator=None)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            want = ca(y)
+        got, ws = ops.se_gate(y, ca[1].weight, ca[1].bias, ca[3].weight, ca[3].bias, act)
+        again, ws2 = ops.se_gate(y, ca[1].weight, ca[1].bias, ca[3].weight, ca[3].bias, act, ws)
+        # fp64 evaluation of the same bf16 operands, for scale
+        p = y.double().mean((2, 3))
+        w1, b1 = ca[1].weight.to(torch.bfloat16).double().flatten(1), ca[1].bias.to(torch.bfloat16).double()
+        w2, b2 = ca[3].weight.to(torch.bfloat16).double().flatten(1), ca[3].bias.to(torch.bfloat16).double()
+        hdn = p @ w1.t() + b1
+        hdn = {"silu": torch.nn.functional.silu, "relu": torch.relu, "none": lambda t: t}[act](hdn)
+        exact = torch.sigmoid(hdn @ w2.t() + b2)
+    assert ws2 is ws and torch.equal(got, again)
+    assert got.shape == (b, c, 1, 1) and got.dtype == torch.bfloat16 and want.dtype == torch.bfloat16
+    e_got = (got.double().flatten(1) - exact).abs().max().item()
+    e_torch = (want.double().flatten(1) - exact).abs().max().item()
+    assert e_got <= max(2.0 * e_torch, 8e-3), (e_got, e_torch)            # no further from fp64 than the torch path (bf16 ulp at 1: 7.8e-3)
+    assert (got.float() - want.float()).abs().max().item() <= 1.6e-2      # two bf16 ulp at a gate near 1
