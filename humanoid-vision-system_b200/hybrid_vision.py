@@ -53,6 +53,23 @@ def to_channels_last(model: nn.Module) -> nn.Module:
     return model
 
 
+def interpolate_positions(owner: nn.Module, pos: torch.Tensor, size: int) -> torch.Tensor:
+    """Position embeddings [1, P, E] linearly resampled to `size` tokens (repair R4).  The result depends on the parameter and
+    the token count only, so inference keeps it (keyed on the parameter's version counter: an optimizer step or a checkpoint
+    load invalidates it) instead of launching the resampling on every frame."""
+    if pos.shape[1] == size:
+        return pos
+    if torch.is_grad_enabled() and pos.requires_grad:
+        return F.interpolate(pos.transpose(1, 2), size=(size,), mode="linear").transpose(1, 2)
+    key = (size, pos._version, pos.dtype, pos.device, pos.data_ptr())
+    cache = owner.__dict__.setdefault("_pos_cache", {})
+    if cache.get("key") != key:
+        with torch.no_grad():
+            cache["value"] = F.interpolate(pos.detach().transpose(1, 2), size=(size,), mode="linear").transpose(1, 2).contiguous()
+        cache["key"] = key
+    return cache["value"]
+
+
 class ConvMHCLayer(nn.Module):
     """conv -> BN -> act -> mHC over pixels -> squeeze-excite gate -> (+ identity)   (vision_backbone.py:10-134)."""
 
@@ -214,9 +231,7 @@ class PatchEmbedding(nn.Module):
         tok = self.projection(x).flatten(2).transpose(1, 2)
         tok = self.mhc_enhance(tok)
         tok = torch.cat([self.cls_token.expand(tok.shape[0], -1, -1).to(tok.dtype), tok], dim=1)
-        pos = self.position_embeddings
-        if pos.shape[1] != tok.shape[1]:
-            pos = F.interpolate(pos.transpose(1, 2), size=(tok.shape[1],), mode="linear").transpose(1, 2)
+        pos = interpolate_positions(self, self.position_embeddings, tok.shape[1])
         return self.norm(tok + pos)
 
 
@@ -277,9 +292,7 @@ class HybridVisionEncoder(nn.Module):
     def forward(self, feat: torch.Tensor) -> torch.Tensor:
         b, c, h, w = feat.shape
         tok = self.cnn_to_vit(feat).flatten(2).transpose(1, 2)
-        pos = self.pos_embed
-        if h * w != pos.shape[1]:
-            pos = F.interpolate(pos.transpose(1, 2), size=(h * w,), mode="linear").transpose(1, 2)
+        pos = interpolate_positions(self, self.pos_embed, h * w)
         tok = tok + pos.to(tok.dtype)
         grid = tok.reshape(b, h, w, -1).permute(0, 3, 1, 2)
         cls = self.vit_encoder(grid)
