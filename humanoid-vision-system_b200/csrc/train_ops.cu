@@ -311,11 +311,12 @@ __global__ void __launch_bounds__(kSeThreads) se_gate_kernel(const uint4* __rest
     if (rl < lanes) {
         const uint4* base = y + ((int64_t)b * rows_per_image) * c8 + cg;
         int64_t r = r0 + rl;
-        for (; r + 3 * lanes < r1; r += 4 * lanes) {       // four independent loads in flight
-            const uint4 v0 = base[r * c8], v1 = base[(r + lanes) * c8], v2 = base[(r + 2 * lanes) * c8], v3 = base[(r + 3 * lanes) * c8];
-            const uint4 vs[4] = {v0, v1, v2, v3};
+        for (; r + 7 * lanes < r1; r += 8 * lanes) {       // eight independent loads in flight
+            uint4 vs[8];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 8; ++k) vs[k] = base[(r + k * lanes) * c8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
                 acc[0] += bf16lo(vs[k].x); acc[1] += bf16hi(vs[k].x); acc[2] += bf16lo(vs[k].y); acc[3] += bf16hi(vs[k].y);
                 acc[4] += bf16lo(vs[k].z); acc[5] += bf16hi(vs[k].z); acc[6] += bf16lo(vs[k].w); acc[7] += bf16hi(vs[k].w);
             }
@@ -344,11 +345,26 @@ __global__ void __launch_bounds__(kSeThreads) se_gate_kernel(const uint4* __rest
     if (!s_last) return;
     __threadfence();
     const float inv = 1.0f / (float)rows_per_image;
-    for (int c = tid; c < C; c += kSeThreads) {
-        float t = 0.f;
-        const float* pp = part + (int64_t)b * slices * C + c;
-        for (int sl = 0; sl < slices; ++sl) t += __ldcg(pp + (int64_t)sl * C);
-        s_pool[c] = bf16_round(t * inv);                  // AdaptiveAvgPool2d(1) output in bf16
+    {
+        // the slices' partial sums: up to eight threads per channel, each over every P-th slice (loads independent of the adds, eight
+        // in flight), then the P pieces in order -- a fixed order, whatever the arrival order of the CTAs was
+        const int P = C >= kSeThreads ? 1 : (kSeThreads / C < 8 ? kSeThreads / C : 8);
+        float* piece = &s_red[0][0];                        // (the row-lane sums are dead) [P][C]
+        __syncthreads();
+        for (int i = tid; i < P * C; i += kSeThreads) {
+            const int c = i % C, pi = i / C;
+            const float* pp = part + (int64_t)b * slices * C + c;
+            float t = 0.f;
+#pragma unroll 8
+            for (int sl = pi; sl < slices; sl += P) t += __ldcg(pp + (int64_t)sl * C);
+            piece[pi * C + c] = t;
+        }
+        __syncthreads();
+        for (int c = tid; c < C; c += kSeThreads) {
+            float t = 0.f;
+            for (int pi = 0; pi < P; ++pi) t += piece[pi * C + c];
+            s_pool[c] = bf16_round(t * inv);              // AdaptiveAvgPool2d(1) output in bf16
+        }
     }
     __syncthreads();
     // Both products: a warp per output, EIGHT outputs per pass, lanes along the inputs in 16-byte pieces -- the weights come
