@@ -196,11 +196,21 @@ class MultiHeadManifoldAttention(nn.Module):
         self.q_proj, self.k_proj, self.v_proj, self.out_proj = mk(), mk(), mk(), mk()
         self.dropout = nn.Dropout(dropout)
         self.scaling = self.head_dim ** -0.5
+        self.use_sdpa = True       # bf16 autocast inference: the library's fused attention instead of the five-op form below
 
     def forward(self, query, key, value, key_padding_mask=None, need_weights: bool = False):
         b, n, e = query.shape
         split = lambda t: t.reshape(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
         q, k, v = split(self.q_proj(query)), split(self.k_proj(key)), split(self.v_proj(value))
+        if (self.use_sdpa and not need_weights and not torch.is_grad_enabled() and not self.training and q.is_cuda
+                and torch.is_autocast_enabled()):
+            # the same softmax(q k^T / sqrt(d)) v (a caller of the path, manifold_layers.py:410-424) without the [B, heads, N, N]
+            # score tensor and its fp32 <-> bf16 round trips in HBM: at batch 64 those were 5 ms of a 77 ms forward
+            dt = torch.get_autocast_dtype("cuda")
+            mask = None if key_padding_mask is None else ~key_padding_mask[:, None, None, :]
+            o = F.scaled_dot_product_attention(q.to(dt), k.to(dt), v.to(dt), attn_mask=mask, scale=self.scaling)
+            o = o.transpose(1, 2).reshape(b, n, e)
+            return self.out_proj(o), None
         w = torch.matmul(q, k.transpose(-2, -1)) * self.scaling
         if key_padding_mask is not None:
             w = w.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))

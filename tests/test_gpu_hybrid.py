@@ -283,3 +283,40 @@ def test_weights_cast_once_for_bf16_inference_give_the_same_outputs(model):
     for s in range(3):
         assert torch.equal(a["predictions"][f"scale_{s}"], b["predictions"][f"scale_{s}"]), s
     assert launches_a - launches_b > 100, (launches_a, launches_b)
+
+
+def test_fused_attention_path_tracks_the_five_op_form():
+    """MultiHeadManifoldAttention under bf16 autocast inference uses F.scaled_dot_product_attention; the five-op form
+    (matmul, scale, softmax, matmul: manifold_layers.py:410-424) stays for fp32, training and need_weights.  Same function:
+    both are equally far from an fp64 evaluation of the same q, k, v -- also with a key padding mask.  (Compared BEFORE the
+    output projection: at random initialisation every token's attention output is close to the mean of v, and the
+    projection's LayerNorm amplifies the bf16 rounding of either form to O(1) -- 86 % from fp64 for both.)"""
+    import hvs_b200
+    from hvs_b200.hybrid_vision import MultiHeadManifoldAttention
+    torch.manual_seed(3)
+    att = MultiHeadManifoldAttention(256, 8).to(DEV).eval()
+    att.out_proj = torch.nn.Identity()
+    x = torch.randn(3, 401, 256, device=DEV)
+    pad = torch.zeros(3, 401, dtype=torch.bool, device=DEV)
+    pad[1, 300:] = True
+    rel = lambda u, v: ((u.double() - v.double()).norm() / v.double().norm()).item()
+    with torch.no_grad():
+        split = lambda t: t.reshape(3, -1, 8, 32).transpose(1, 2).double()
+        q, k, v = split(att.q_proj(x)), split(att.k_proj(x)), split(att.v_proj(x))
+        for mask in (None, pad):
+            sc = (q @ k.transpose(-2, -1)) * att.scaling
+            if mask is not None:
+                sc = sc.masked_fill(mask[:, None, None, :], float("-inf"))
+            exact = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(3, 401, 256)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                att.use_sdpa = True
+                a, wa = att(x, x, x, key_padding_mask=mask)
+                att.use_sdpa = False
+                b, _ = att(x, x, x, key_padding_mask=mask)
+            assert wa is None and a.shape == b.shape
+            assert rel(a, exact) < 1e-2 and rel(b, exact) < 1e-2, (rel(a, exact), rel(b, exact))
+            assert rel(a, exact) < 1.5 * rel(b, exact) + 1e-3                 # no further from fp64 than the five-op form
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            att.use_sdpa = True
+            _, w = att(x, x, x, need_weights=True)                   # the weights are only available from the five-op form
+        assert w is not None and w.shape == (3, 8, 401, 401)
