@@ -488,7 +488,8 @@ extern "C" int hvs_se_gate_bf16(const void* y, const void* w1, const void* b1, c
 // ---------------------------------------------------------------------------------------------- folded-BatchNorm bias + activation
 // After eval-mode BatchNorm is folded into the convolution (y = conv_w'(x) + b'), ATen adds the bias in a broadcast pass of its
 // own and the activation in another; here both are one vectorised pass over the channels-last map:
-//   out[t, c] = act(y[t, c] + bias[c]),  act in {identity, SiLU (vision_backbone.py:36-45 default), ReLU}.
+//   out[t, c] = act(y[t, c] + bias[c]),  act in {identity, SiLU (vision_backbone.py:36-45 default), ReLU (feature_fusion.py
+//   refinement stacks), LeakyReLU(0.1) (yolo_head.py:99-112 conv_layers)}.
 namespace hvs {
 namespace {
 template <int ACT>
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const uint4* __restrict__
         for (int k = 0; k < 8; ++k) {
             if (ACT == 1) v[k] = __fdividef(v[k], 1.0f + __expf(-v[k]));
             else if (ACT == 2) v[k] = fmaxf(v[k], 0.f);
+            else if (ACT == 3) v[k] = v[k] > 0.f ? v[k] : 0.1f * v[k];
         }
         out[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
@@ -518,7 +520,7 @@ extern "C" int hvs_bias_act_bf16(const void* y, const float* bias, void* out, in
     if (rows < 0 || channels <= 0) return HVS_ERR_BAD_ARG;
     if (rows == 0) return HVS_OK;
     if (!y || !bias || !out) return HVS_ERR_BAD_ARG;
-    if (channels % 8 || activation < 0 || activation > 2) return HVS_ERR_UNSUPPORTED;
+    if (channels % 8 || activation < 0 || activation > 3) return HVS_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(out)) & 15) return HVS_ERR_ALIGNMENT;
     const int64_t total = rows * (channels / 8);
     int64_t blocks = (total + 255) / 256;
@@ -528,7 +530,8 @@ extern "C" int hvs_bias_act_bf16(const void* y, const float* bias, void* out, in
     uint4* op = reinterpret_cast<uint4*>(out);
     if (activation == 0) bias_act_kernel<0><<<(int)blocks, 256, 0, stream>>>(yp, bias, op, rows, channels / 8);
     else if (activation == 1) bias_act_kernel<1><<<(int)blocks, 256, 0, stream>>>(yp, bias, op, rows, channels / 8);
-    else bias_act_kernel<2><<<(int)blocks, 256, 0, stream>>>(yp, bias, op, rows, channels / 8);
+    else if (activation == 2) bias_act_kernel<2><<<(int)blocks, 256, 0, stream>>>(yp, bias, op, rows, channels / 8);
+    else bias_act_kernel<3><<<(int)blocks, 256, 0, stream>>>(yp, bias, op, rows, channels / 8);
     count_launch();
     return launch_status();
 }

@@ -40,6 +40,33 @@ def build_model(device, seed: int = 0, channels_last: bool = True, bf16_activati
     return model
 
 
+class FoldedBiasAct(nn.Module):
+    """The bias of a BatchNorm-folded convolution and the activation after it as one pass (hvs_bias_act_bf16) -- ATen runs a
+    bias-carrying cuDNN convolution as convolution + a broadcast add pass, then the activation as a third kernel.  Built by
+    fold_batchnorm_for_inference in place of the activation of a conv -> BatchNorm -> activation stack."""
+
+    def __init__(self, bias: torch.Tensor, act: nn.Module, kind: str):
+        super().__init__()
+        self.register_buffer("bias", bias.detach().float().clone())
+        self.act, self.kind = act, kind
+
+    def forward(self, y: torch.Tensor) -> torch.Tensor:
+        if (not torch.is_grad_enabled() and y.is_cuda and y.dtype == torch.bfloat16 and y.dim() == 4 and y.shape[1] % 8 == 0
+                and y.is_contiguous(memory_format=torch.channels_last)):
+            return ops.bias_act(y, self.bias, self.kind)
+        return self.act(y + self.bias.to(y.dtype).view(1, -1, 1, 1))
+
+
+def _act_kind(m: nn.Module) -> Optional[str]:
+    if isinstance(m, nn.ReLU):
+        return "relu"
+    if isinstance(m, nn.SiLU):
+        return "silu"
+    if isinstance(m, nn.LeakyReLU) and abs(m.negative_slope - 0.1) < 1e-12:
+        return "leaky_relu_0.1"
+    return None
+
+
 def fold_batchnorm_for_inference(model: nn.Module) -> int:
     """Eval-mode conv + BatchNorm pairs of the host model (ConvMHCLayer.conv/.bn, the FPN and head conv stacks) folded into
     one convolution with bias: y = conv(x) * g / sqrt(var + eps) + (b - mean * g / sqrt(var + eps)).  A caller-side
@@ -62,9 +89,15 @@ def fold_batchnorm_for_inference(model: nn.Module) -> int:
             n += 1
         if isinstance(mod, nn.Sequential):
             kids = list(mod.named_children())
-            for (na, a), (nb, b) in zip(kids, kids[1:]):
+            for i, ((na, a), (nb, b)) in enumerate(zip(kids, kids[1:])):
                 if isinstance(a, nn.Conv2d) and isinstance(b, nn.BatchNorm2d):
-                    setattr(mod, na, fuse_conv_bn_eval(a.eval(), b.eval()))
+                    fused = fuse_conv_bn_eval(a.eval(), b.eval())
+                    kind = _act_kind(kids[i + 2][1]) if i + 2 < len(kids) else None
+                    if kind is not None and fused.bias is not None and fused.out_channels % 8 == 0:
+                        # conv -> BatchNorm -> activation: the folded bias leaves the convolution and joins the activation
+                        setattr(mod, kids[i + 2][0], FoldedBiasAct(fused.bias, kids[i + 2][1], kind))
+                        fused.bias = None
+                    setattr(mod, na, fused)
                     setattr(mod, nb, nn.Identity())
                     n += 1
     return n

@@ -543,7 +543,7 @@ def gate_residual(y: torch.Tensor, gate: torch.Tensor, residual: Optional[torch.
     return out
 
 
-ACTIVATIONS = {"none": 0, "silu": 1, "relu": 2}
+ACTIVATIONS = {"none": 0, "silu": 1, "relu": 2, "leaky_relu_0.1": 3}
 
 
 @_on_device

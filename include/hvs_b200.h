@@ -344,10 +344,11 @@ int hvs_se_gate_bf16(const void* y, const void* w1, const void* b1, const void* 
 
 /* Bias of a BatchNorm-folded convolution + the activation that follows it (ConvMHCLayer, vision_backbone.py:100-110, eval
  * mode) in one pass over the channels-last map: out[t, c] = act(y[t, c] + bias[c]); y, out [rows, channels] bf16 (may
- * alias), bias [channels] fp32; activation 0 = identity, 1 = SiLU, 2 = ReLU; channels % 8 == 0. */
+ * alias), bias [channels] fp32; activation 0 = identity, 1 = SiLU, 2 = ReLU, 3 = LeakyReLU(0.1); channels % 8 == 0. */
 #define HVS_ACT_NONE 0
 #define HVS_ACT_SILU 1
 #define HVS_ACT_RELU 2
+#define HVS_ACT_LEAKY_RELU_0P1 3   /* LeakyReLU(0.1): the prediction heads' conv stacks (yolo_head.py:99-112) */
 int hvs_bias_act_bf16(const void* y, const float* bias, void* out, int64_t rows, int channels, int activation, void* stream);
 
 /* hvs_preprocess_u8: ImagePreprocessor "accurate" path (src/inference/preprocessing.py:252-273, colour swap :199-203):

@@ -95,14 +95,15 @@ def test_gate_residual_matches_torch(b, c, h, w, with_res):
     assert ((got.double() - want.double()).abs() <= 2.0 ** -7 * mag + 1e-30).all()
 
 
-@pytest.mark.parametrize("act", ["silu", "relu", "none"])
+@pytest.mark.parametrize("act", ["silu", "relu", "none", "leaky_relu_0.1"])
 def test_bias_act_matches_torch(act):
     import hvs_b200
     g = torch.Generator().manual_seed(3)
     y = torch.randn(3, 64, 9, 11, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
     bias = torch.randn(64, generator=g).to(DEV)
     z = y.double() + bias.double().view(1, -1, 1, 1)
-    want = {"silu": torch.nn.functional.silu, "relu": torch.relu, "none": lambda t: t}[act](z)
+    want = {"silu": torch.nn.functional.silu, "relu": torch.relu, "none": lambda t: t,
+            "leaky_relu_0.1": lambda t: torch.nn.functional.leaky_relu(t, 0.1)}[act](z)
     got = hvs_b200.ops.bias_act(y.clone(memory_format=torch.channels_last), bias, act)
     assert got.is_contiguous(memory_format=torch.channels_last)
     assert ((got.double() - want).abs() <= 2.0 ** -8 * want.abs() + 1e-6).all()

@@ -239,6 +239,8 @@ def test_batchnorm_folding_with_fused_bias_activation_keeps_the_outputs(model):
     m1 = copy.deepcopy(m0)
     assert harness.fold_batchnorm_for_inference(m1) >= 40
     hvs_b200.hybrid_vision.to_channels_last(m1)
+    # conv -> BatchNorm -> activation stacks of the FPN and the prediction heads: bias + activation as one pass
+    assert sum(isinstance(mod, harness.FoldedBiasAct) for mod in m1.modules()) >= 12
     g = torch.Generator().manual_seed(11)
     x = torch.randn(2, 3, 320, 320, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
     before = hvs_b200._lib.launch_count()
