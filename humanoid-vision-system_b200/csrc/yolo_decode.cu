@@ -4,9 +4,12 @@
 //   box size    anchor_w * exp(tw), anchor_h * exp(th), anchors / 416      (:269-270, :50-51)
 //   corners     c -/+ size / 2                                             (:273-276)
 //   scores      sigmoid(obj) * sigmoid(cls), max / first argmax over classes (:282-285)
-// HBM-bound streaming kernel: (5+C) values in, 7 values out per cell.  Two mappings:
-//   * channel-strided input (the permuted NCHW conv output): a thread per cell, lanes along W, so
-//     every channel plane is read with full 128-byte lines;
+// HBM-bound streaming kernels: (5+C) values in, 7 values out per cell.  Mappings:
+//   * channel-strided input (the permuted NCHW conv output), unit W stride, W % 4 == 0: four adjacent cells per thread,
+//     every channel plane read with 8 / 16-byte loads -- decode_four_cells_first_max when the [cells, C] score tensor is
+//     not wanted (the class search runs on the logits, one sigmoid per cell; hvs_yolo_decode_scales runs all scales of
+//     the head in one launch), decode_four_cells_per_thread when it is;
+//   * any other strided input: a thread per cell, lanes along W;
 //   * channel-contiguous input: a warp per cell, lanes along the channel axis.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
