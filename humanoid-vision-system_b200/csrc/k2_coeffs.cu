@@ -397,8 +397,11 @@ __device__ void backward_pass_dispatch(const Plan& pl, const Slab& sl, const Job
     else backward_pass_slab<128>(pl, sl, jd, pass, sm_v, sm_part);
 }
 
+constexpr int kRowBlock = 4, kRowFactorIters = 32;
+
 __global__ void __launch_bounds__(kThreads, 1) static_coeffs_bwd_kernel(const Plan pl) {
     extern __shared__ float sm[];
+    __shared__ float s_rowf[kWarps][kRowBlock][2 * kRowFactorIters];
     float* sm_v = sm;
     float* sm_part = sm + pl.max_d;
     cg::grid_group grid = cg::this_grid();
@@ -461,6 +464,60 @@ __global__ void __launch_bounds__(kThreads, 1) static_coeffs_bwd_kernel(const Pl
         const float* K = pl.kbuf + jd.mat_off;
         const float* hist = jd.j.uv_history;
         const float* bh = pl.bwd_hist + (size_t)2 * n * jd.vec_off;
+        if (n <= kRowFactorIters) {
+            // four rows per warp at a time: the 2n column vectors (bh / hist rows at column j) are fetched once for the four, the
+            // rows' own 2n factors wait in shared memory.  (One row at a time fetched four L2 values per element and iteration:
+            // 740 M loads for the model's 76 layers, most of the kernel's time.)  Kbar goes through the output row itself.
+            for (int r = warp * kRowBlock; r < sl.nrows; r += kWarps * kRowBlock) {
+                const int nr = sl.nrows - r < kRowBlock ? sl.nrows - r : kRowBlock;
+                __syncwarp();
+                for (int q = lane; q < kRowBlock * 2 * n; q += 32) {
+                    const int rr = q / (2 * n), kk = q - rr * 2 * n;
+                    const int i = sl.row0 + r + (rr < nr ? rr : nr - 1);
+                    s_rowf[warp][rr][kk] = kk < n ? hist[(size_t)(2 * (kk + 1)) * D + i] : bh[(size_t)(2 * (kk - n) + 1) * D + i];
+                }
+                __syncwarp();
+                float un[kRowBlock], dot[kRowBlock];
+                const float* grow[kRowBlock];
+                const float* krow[kRowBlock];
+                float* orow[kRowBlock];
+#pragma unroll
+                for (int rr = 0; rr < kRowBlock; ++rr) {
+                    const int i = sl.row0 + r + (rr < nr ? rr : nr - 1);
+                    un[rr] = hist[(size_t)(2 * n) * D + i];
+                    dot[rr] = 0.f;
+                    grow[rr] = jd.g.d_h_res + (size_t)i * D;
+                    krow[rr] = K + (size_t)i * D;
+                    orow[rr] = jd.g.d_h_res_raw + (size_t)i * D;
+                }
+                for (int j = lane; j < D; j += 32) {
+                    const float vfin = hist[(size_t)(2 * n + 1) * D + j];
+                    float kb[kRowBlock];
+#pragma unroll
+                    for (int rr = 0; rr < kRowBlock; ++rr) kb[rr] = grow[rr][j] * un[rr] * vfin;
+                    for (int k = 1; k <= n; ++k) {
+                        const float bcol = bh[(size_t)(2 * (k - 1)) * D + j], hcol = hist[(size_t)(2 * (k - 1) + 1) * D + j];
+#pragma unroll
+                        for (int rr = 0; rr < kRowBlock; ++rr) kb[rr] += s_rowf[warp][rr][k - 1] * bcol + s_rowf[warp][rr][n + k - 1] * hcol;
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < kRowBlock; ++rr)
+                        if (rr < nr) {
+                            orow[rr][j] = kb[rr];
+                            dot[rr] = fmaf(kb[rr], krow[rr][j], dot[rr]);
+                        }
+                }
+#pragma unroll
+                for (int rr = 0; rr < kRowBlock; ++rr) dot[rr] = wsum(dot[rr]) / (float)D;
+                for (int j = lane; j < D; j += 32) {
+#pragma unroll
+                    for (int rr = 0; rr < kRowBlock; ++rr)
+                        if (rr < nr) orow[rr][j] = krow[rr][j] * (orow[rr][j] - dot[rr]);      // (this lane wrote orow[rr][j] itself)
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         float* rowbuf = sm_part + warp * D;
         for (int r = warp; r < sl.nrows; r += kWarps) {
             const int i = sl.row0 + r;
