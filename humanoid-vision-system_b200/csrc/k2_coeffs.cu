@@ -127,8 +127,12 @@ __device__ void load_v_forward(const Plan& pl, const JobDev& jd, int iter, float
     for (int j = threadIdx.x; j < D; j += kThreads) {
         float v = 1.0f;
         if (iter > 0) {
+            // (a job's slabs own consecutive D-float pieces of the partial buffer: direct addresses, so the loads of the sum are
+            //  independent -- through the slab table every term was two dependent L2 round trips, 50 in a row for a 1792 matrix)
+            const float* pj = parts + pl.slabs[jd.first_slab].part_off + j;
             float t = 0.f;
-            for (int s = 0; s < jd.nslabs; ++s) t += parts[pl.slabs[jd.first_slab + s].part_off + j];
+#pragma unroll 8
+            for (int s = 0; s < jd.nslabs; ++s) t += pj[(size_t)s * D];
             const float vp = iter > 1 ? vprev[j] : 1.0f;
             v = __fdiv_rn(vp, vp * t + pl.eps);
             if (owner) {
@@ -300,8 +304,10 @@ __device__ void load_t_backward(const Plan& pl, const JobDev& jd, int pass, floa
     const float* vk = jd.j.uv_history + (size_t)(2 * k + 1) * D;
     float* hist = pl.bwd_hist + (size_t)2 * pl.iters * jd.vec_off + (size_t)(2 * (k - 1)) * D;
     for (int j = threadIdx.x; j < D; j += kThreads) {
+        const float* pj = parts + pl.slabs[jd.first_slab].part_off + j;
         float vb = 0.f;
-        for (int s = 0; s < jd.nslabs; ++s) vb += parts[pl.slabs[jd.first_slab + s].part_off + j];
+#pragma unroll 8
+        for (int s = 0; s < jd.nslabs; ++s) vb += pj[(size_t)s * D];
         const float v = vk[j];
         const float tb = -vb * v * v;
         if (owner) hist[j] = tb;
@@ -347,24 +353,66 @@ __device__ void backward_pass_slab(const Plan& pl, const Slab& sl, const JobDev&
         const float* uk = jd.j.uv_history + (size_t)(2 * k) * D;
         const float* ubar0 = pl.vec_u + jd.vec_off;
         float* shist = pl.bwd_hist + (size_t)2 * n * jd.vec_off + (size_t)(2 * (k - 1) + 1) * D;
-        for (int r = warp; r < sl.nrows; r += kWarps) {
-            const int i = sl.row0 + r;
-            const float* krow = K + (size_t)i * D;
-            float a = 0.f;
+        // Narrow matrices have hundreds of rows per warp and one or two elements per lane in each: a row at a time is a chain of
+        // L2 round trips (a pass over the model's D = 32 .. 128 layers took 60-180 us, 20 passes per step).  RU rows in flight.
+        constexpr int RU = NPL <= 2 ? 8 : (NPL <= 8 ? 4 : (NPL <= 16 ? 2 : 1));
+        if constexpr (RU == 1) {                              // wide rows: many loads per lane already, the row streams twice
+            for (int r = warp; r < sl.nrows; r += kWarps) {
+                const int i = sl.row0 + r;
+                const float* krow = K + (size_t)i * D;
+                float a = 0.f;
 #pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-                const int j = lane + 32 * q;
-                if (j < D) a = fmaf(krow[j], sm_v[j], a);
+                for (int q = 0; q < NPL; ++q) {
+                    const int j = lane + 32 * q;
+                    if (j < D) a = fmaf(krow[j], sm_v[j], a);
+                }
+                a = wsum(a);
+                if (pass == 1) a += ubar0[i];
+                const float u = uk[i];
+                const float sb = -a * u * u;
+                if (lane == 0) shist[i] = sb;
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) {
+                    const int j = lane + 32 * q;
+                    if (j < D) cp[q] = fmaf(krow[j], sb, cp[q]);
+                }
             }
-            a = wsum(a);
-            if (pass == 1) a += ubar0[i];
-            const float u = uk[i];
-            const float sb = -a * u * u;
-            if (lane == 0) shist[i] = sb;
+        } else
+        for (int r0 = warp * RU; r0 < sl.nrows; r0 += kWarps * RU) {
+            float kr[RU][NPL], a[RU];
 #pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-                const int j = lane + 32 * q;
-                if (j < D) cp[q] = fmaf(krow[j], sb, cp[q]);
+            for (int u = 0; u < RU; ++u) {
+                const bool ok = r0 + u < sl.nrows;
+                const float* krow = K + (size_t)(sl.row0 + (ok ? r0 + u : r0)) * D;
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) {
+                    const int j = lane + 32 * q;
+                    kr[u][q] = (ok && j < D) ? krow[j] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                a[u] = 0.f;
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) {
+                    const int j = lane + 32 * q;
+                    if (j < D) a[u] = fmaf(kr[u][q], sm_v[j], a[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RU; ++u) a[u] = wsum(a[u]);
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                if (r0 + u < sl.nrows) {
+                    const int i = sl.row0 + r0 + u;
+                    float av = a[u];
+                    if (pass == 1) av += ubar0[i];
+                    const float uu = uk[i];
+                    const float sb = -av * uu * uu;
+                    if (lane == 0) shist[i] = sb;
+#pragma unroll
+                    for (int q = 0; q < NPL; ++q) cp[q] = fmaf(kr[u][q], sb, cp[q]);
+                }
             }
         }
     }
