@@ -119,3 +119,30 @@ def test_host_model_composition_reproduces_reference_forward_on_cpu(golden):
         assert torch.allclose(out["predictions"][f"scale_{s}"], torch.from_numpy(g[f"pred{s}"]), rtol=2e-3, atol=2e-3), s
     assert torch.allclose(out["final_features"], torch.from_numpy(g["final_features"]), rtol=2e-3, atol=2e-3)
     assert torch.allclose(out["vit_features"].mean((2, 3)), torch.from_numpy(g["vit_features_mean"]), rtol=2e-3, atol=2e-3)
+
+
+def test_inference_preparation_helpers_restructure_the_host_model_as_documented():
+    """harness.fold_batchnorm_for_inference / cast_weights_for_bf16_inference on the CPU (module surgery only, no forward):
+    every conv -> BatchNorm pair is folded, the conv -> BatchNorm -> activation stacks of the FPN and the prediction heads
+    hand their bias to a FoldedBiasAct, the mHC modules keep fp32 master parameters, everything else that autocast would
+    cast per call is stored in bf16."""
+    import torch
+    import hvs_b200
+    from hvs_b200 import harness
+    m = harness.build_model(torch.device("cpu"), seed=0).eval()
+    n_bn = sum(isinstance(x, torch.nn.BatchNorm2d) for x in m.modules())
+    assert harness.fold_batchnorm_for_inference(m) == n_bn >= 40
+    assert not any(isinstance(x, torch.nn.BatchNorm2d) for x in m.modules())
+    fused = [x for x in m.modules() if isinstance(x, harness.FoldedBiasAct)]
+    assert len(fused) >= 12 and all(f.bias.dtype == torch.float32 for f in fused)
+    assert {f.kind for f in fused} == {"relu", "leaky_relu_0.1"}
+    n_cast = harness.cast_weights_for_bf16_inference(m)
+    assert n_cast > 100
+    for mod in m.modules():
+        if isinstance(mod, hvs_b200.ManifoldHyperConnection):
+            assert all(p.dtype == torch.float32 for p in mod.parameters())
+    inside = {id(x) for mod in m.modules() if isinstance(mod, hvs_b200.ManifoldHyperConnection) for x in mod.modules()}
+    for mod in m.modules():
+        if isinstance(mod, (torch.nn.Conv2d, torch.nn.Linear)) and id(mod) not in inside:
+            assert mod.weight.dtype == torch.bfloat16
+            assert mod.bias is None or mod.bias.dtype == torch.bfloat16
